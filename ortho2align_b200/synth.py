@@ -1,0 +1,240 @@
+"""Seeded synthetic HSP/background data of the shapes BASELINE.json names.
+
+Null scores:  max(12, rint(Gumbel(17, 3.2)))  (BLASTN word_size 6 => min raw score 12)
+Signal:       3 % of HSPs get + rint(Exp(18)) and are laid out colinearly (a true ortholog)
+Cut HSPs:     2 % of HSPs get score *= U(0.3, 1)  (float scores, `alignment.py:330`)
+Coordinates:  query gene window (from a BED6 or a U-placed 20 kb window); per region a 2.1 Mb
+              subject window; HSP length U[12, 120]; 50 % reverse orientation.
+Background:   the same null, `n_bg` scores per lncRNA.
+
+Everything is generated directly in the columnar layout (`columnar.ColumnarBatch`);
+`to_json_dicts` renders a (small) batch in the reference's JSON schema
+(`genomicranges.py:1077-1082`, `alignment.py:588-601`, `genomicranges.py:796-814`).
+The unit of seeding is a block of lncRNAs: `default_rng([seed, config_id, block_index])`, so any
+rank can regenerate exactly its shard.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .columnar import ColumnarBatch, concat_batches
+
+SUBJECT_WINDOW = 2_100_000
+GENE_WINDOW = 20_000
+_STRRNA_GENES = os.path.join(os.path.dirname(__file__), "data", "strrna_genes.json")
+
+
+def null_scores(rng, n):
+    s = np.rint(rng.gumbel(17.0, 3.2, size=n))
+    return np.maximum(12.0, s)
+
+
+def _gen_block(rng, genes, hsp_counts, aln_off, n_bg, dense=False):
+    """genes: int64 [n_lnc, 2] (start, end); hsp_counts: int64 [n_aln]; aln_off [n_lnc+1]."""
+    n_lnc = len(genes)
+    n_aln = len(hsp_counts)
+    hsp_off = np.zeros(n_aln + 1, dtype=np.int64)
+    np.cumsum(hsp_counts, out=hsp_off[1:])
+    n = int(hsp_off[-1])
+    aln_of_hsp = np.repeat(np.arange(n_aln), hsp_counts)
+    lnc_of_aln = np.repeat(np.arange(n_lnc), np.diff(aln_off))
+    gstart = genes[lnc_of_aln, 0][aln_of_hsp]
+    glen = (genes[lnc_of_aln, 1] - genes[lnc_of_aln, 0])[aln_of_hsp]
+    # subject window per alignment
+    s0_aln = rng.integers(1_000_000, 200_000_000, size=n_aln)
+    s0 = s0_aln[aln_of_hsp]
+    length = rng.integers(12, 121, size=n)
+    length = np.minimum(length, np.maximum(glen - 1, 1))
+    qpos = (rng.random(n) * np.maximum(glen - length, 1)).astype(np.int64)
+    spos = (rng.random(n) * (SUBJECT_WINDOW - 121)).astype(np.int64)
+    slength = np.maximum(1, length + rng.integers(-3, 4, size=n))
+    reverse = rng.random(n) < 0.5
+    score = null_scores(rng, n)
+    if dense:
+        # C4: every HSP scores above any background value -> p = 0, all enter the DP
+        score = score + 200.0
+    else:
+        signal = rng.random(n) < 0.03
+        score = score + np.where(signal, np.rint(rng.exponential(18.0, size=n)), 0.0)
+        # colinear placement of the signal HSPs of an alignment around a diagonal whose
+        # orientation is fixed per alignment
+        aln_rev = (rng.random(n_aln) < 0.5)[aln_of_hsp]
+        diag0 = (rng.random(n_aln) * (SUBJECT_WINDOW - 2 * GENE_WINDOW - 1000)).astype(np.int64)[aln_of_hsp] + 500
+        jitter = np.rint(rng.normal(0.0, 40.0, size=n)).astype(np.int64)
+        sp_dir = diag0 + qpos + jitter
+        sp_rev = diag0 + (glen - qpos) + jitter
+        sp_sig = np.clip(np.where(aln_rev, sp_rev, sp_dir), 0, SUBJECT_WINDOW - 130)
+        spos = np.where(signal, sp_sig, spos)
+        reverse = np.where(signal, aln_rev, reverse)
+        cut = rng.random(n) < 0.02
+        score = np.where(cut, score * rng.uniform(0.3, 1.0, size=n), score)
+    qstart = gstart + qpos
+    qend = qstart + length
+    lo = s0 + spos
+    hi = lo + slength
+    sstart = np.where(reverse, hi, lo)
+    send = np.where(reverse, lo, hi)
+    # qlen/slen as cut_coordinates recomputes them: max+1 over all HSPs (alignment.py:477-487)
+    qlen = np.ones(n_aln, dtype=np.int64)
+    slen = np.ones(n_aln, dtype=np.int64)
+    nz = hsp_counts > 0
+    if n:
+        starts = hsp_off[:-1][nz]
+        qlen[nz] = np.maximum.reduceat(qend, starts) + 1
+        slen[nz] = np.maximum.reduceat(np.maximum(sstart, send), starts) + 1
+    bg = null_scores(rng, n_lnc * n_bg).astype(np.int32)
+    bg_off = np.arange(n_lnc + 1, dtype=np.int64) * n_bg
+    meta = {"s0": s0_aln}
+    return ColumnarBatch(
+        bg_off=bg_off, bg=bg, aln_off=aln_off.astype(np.int64), hsp_off=hsp_off, qlen=qlen, slen=slen,
+        qstart=qstart.astype(np.int32), qend=qend.astype(np.int32),
+        sstart=sstart.astype(np.int32), send=send.astype(np.int32),
+        score=score.astype(np.float64)), meta
+
+
+def load_strrna_bed(path=_STRRNA_GENES):
+    """The 96 genes (chrom, start, end, name, strand) of BASELINE.json config 1."""
+    import json
+    with open(path) as f:
+        return [tuple(g) for g in json.load(f)["genes"]]
+
+
+def workload(config, n_lnc=None, seed=0, lnc_range=None, block=64, with_meta=False,
+             n_bg=None, hsps_per_region=None, regions=None):
+    """Generate the lncRNAs [lnc_range) of BASELINE.json config `config` (1..5).
+
+    Returns ColumnarBatch (names filled) and, if `with_meta`, a list of per-lncRNA dicts with the
+    gene record and per-alignment subject windows (used by `to_json_dicts`).
+    """
+    cfg = int(config)
+    bed = None
+    if cfg == 1:
+        bed = load_strrna_bed()
+        total = len(bed) if n_lnc is None else n_lnc
+        block = 1
+    elif cfg in (2, 3):
+        total = 20_000 if n_lnc is None else n_lnc
+    elif cfg == 4:
+        total = 5_000 if n_lnc is None else n_lnc
+    elif cfg == 5:
+        total = 100_000 if n_lnc is None else n_lnc
+    else:
+        raise ValueError("config must be 1..5")
+    lo, hi = (0, total) if lnc_range is None else lnc_range
+    parts, metas = [], []
+    b0 = (lo // block) * block
+    for bstart in range(b0, hi, block):
+        bend = min(bstart + block, total)
+        nb = bend - bstart
+        rng = np.random.default_rng([seed, cfg, bstart // block])
+        if cfg == 1:
+            g = bed[bstart % len(bed)]
+            genes = np.array([[g[1], g[2]]], dtype=np.int64)
+            n_reg = rng.integers(1, 6, size=nb) if regions is None else np.full(nb, regions)
+            aln_off = np.concatenate([[0], np.cumsum(n_reg)])
+            counts = rng.integers(200, 2001, size=int(aln_off[-1])) if hsps_per_region is None \
+                else np.full(int(aln_off[-1]), hsps_per_region)
+            nbg = 1000 if n_bg is None else n_bg
+            dense = False
+        elif cfg in (2, 3):
+            gs = rng.integers(1_000_000, 200_000_000, size=nb)
+            genes = np.stack([gs, gs + GENE_WINDOW], axis=1)
+            r = 5 if regions is None else regions
+            aln_off = np.arange(nb + 1) * r
+            h = 2000 if hsps_per_region is None else hsps_per_region
+            counts = rng.integers(int(h * 0.9), int(h * 1.1) + 1, size=nb * r)
+            nbg = (10_000 if cfg == 2 else 1_000_000) if n_bg is None else n_bg
+            dense = False
+        elif cfg == 4:
+            gs = rng.integers(1_000_000, 200_000_000, size=nb)
+            genes = np.stack([gs, gs + GENE_WINDOW], axis=1)
+            r = 1 if regions is None else regions
+            aln_off = np.arange(nb + 1) * r
+            h = 50_000 if hsps_per_region is None else hsps_per_region
+            counts = np.full(nb * r, h)
+            nbg = 1000 if n_bg is None else n_bg
+            dense = True
+        else:
+            gs = rng.integers(1_000_000, 200_000_000, size=nb)
+            glen = rng.integers(300, GENE_WINDOW, size=nb)
+            genes = np.stack([gs, gs + glen], axis=1)
+            n_reg = 1 + rng.poisson(1.0, size=nb) if regions is None else np.full(nb, regions)
+            aln_off = np.concatenate([[0], np.cumsum(n_reg)])
+            mean_h = 100.0 if hsps_per_region is None else float(hsps_per_region)
+            sigma = 1.0
+            counts = np.maximum(1, rng.lognormal(np.log(mean_h) - sigma * sigma / 2, sigma,
+                                                 size=int(aln_off[-1])).astype(np.int64))
+            nbg = 1000 if n_bg is None else n_bg
+            dense = False
+        part, meta = _gen_block(rng, genes, np.asarray(counts, dtype=np.int64),
+                                np.asarray(aln_off, dtype=np.int64), nbg, dense=dense)
+        if cfg == 1:
+            part.names = [bed[bstart % len(bed)][3]]
+            chroms = [bed[bstart % len(bed)][0]]
+            strands = [bed[bstart % len(bed)][4]]
+        else:
+            part.names = [f"lnc{cfg}_{i}" for i in range(bstart, bend)]
+            chroms = ["chr1"] * nb
+            strands = ["+" if (i % 2 == 0) else "-" for i in range(bstart, bend)]
+        # trim to requested range inside the block
+        s_lo, s_hi = max(lo, bstart) - bstart, min(hi, bend) - bstart
+        if with_meta:
+            for i in range(s_lo, s_hi):
+                a0, a1 = int(part.aln_off[i]), int(part.aln_off[i + 1])
+                metas.append({"chrom": chroms[i], "start": int(genes[i, 0]), "end": int(genes[i, 1]),
+                              "strand": strands[i], "name": part.names[i],
+                              "s0": [int(x) for x in meta["s0"][a0:a1]]})
+        if s_lo != 0 or s_hi != nb:
+            part = part.slice_lnc(s_lo, s_hi)
+        parts.append(part)
+    batch = concat_batches(parts)
+    if with_meta:
+        return batch, metas
+    return batch
+
+
+def _grange_dict(chrom, start, end, strand, name, relations=None, relations_class=None):
+    return {"chrom": chrom, "start": start, "end": end, "strand": strand, "genome": None,
+            "sequence_file_path": {"path": None}, "name": name,
+            "relations": {} if relations is None else relations,
+            "relations_class": relations_class}
+
+
+def to_json_dicts(batch, metas):
+    """Render each lncRNA of a (small) batch in the reference JSON schema.
+
+    Returns list of (name, alignment_dict_list, background_list)."""
+    out = []
+    for l in range(batch.n_lnc):
+        m = metas[l]
+        a0, a1 = int(batch.aln_off[l]), int(batch.aln_off[l + 1])
+        sranges = []
+        for k, a in enumerate(range(a0, a1)):
+            s0 = m["s0"][k]
+            sranges.append(("chr" + str(1 + (s0 % 19)), s0, s0 + SUBJECT_WINDOW))
+        lifted = {"collection": [_grange_dict(c, s + 50_000, e - 50_000, ".", m["name"])
+                                 for (c, s, e) in sranges],
+                  "sequence_file_path": {"path": None}, "grange_class": "GenomicRange"}
+        alns = []
+        for k, a in enumerate(range(a0, a1)):
+            h0, h1 = int(batch.hsp_off[a]), int(batch.hsp_off[a + 1])
+            hsps = []
+            for h in range(h0, h1):
+                sc = float(batch.score[h])
+                hsps.append({"qstart": int(batch.qstart[h]), "qend": int(batch.qend[h]),
+                             "sstart": int(batch.sstart[h]), "send": int(batch.send[h]),
+                             "score": int(sc) if sc.is_integer() else sc,
+                             "pval": None, "kwargs": {}})
+            c, s, e = sranges[k]
+            alns.append({"HSPs": hsps, "qlen": int(batch.qlen[a]), "slen": int(batch.slen[a]),
+                         "filtered_HSPs": [dict(h) for h in hsps], "filtered": False,
+                         "qrange": _grange_dict(m["chrom"], m["start"], m["end"], m["strand"], m["name"],
+                                                relations={"lifted": lifted},
+                                                relations_class="GenomicRangesList"),
+                         "srange": _grange_dict(c, s, e, ".", None),
+                         "relative": False})
+        b0, b1 = int(batch.bg_off[l]), int(batch.bg_off[l + 1])
+        out.append((m["name"], alns, [int(x) for x in batch.bg[b0:b1]]))
+    return out
