@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — HSPs/sec through build_orthologs + best-ortholog selection (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2] [--lnc L]
+
+A "step" = one pass of the hot path (background fit -> score filter -> p -> q -> chaining -> best
+ortholog) over one batch of synthetic lncRNAs of the named BASELINE config (default configs[1]:
+20k lncRNAs x 5 regions x ~2k HSPs, 10k background scores each, hist fitter).
+  value : device-timed (CUDA events) with the columnar inputs already resident in HBM
+  e2e   : the same call through the C-ABI with pinned HOST buffers: H2D of all inputs and D2H of
+          the result (chains + per-lncRNA selection) inside the timed region
+  roofline : the streaming kernel (k_score), algorithmic bytes / CUDA-event duration vs measured peak
+  cpu_baseline : the oracle port (C, OpenMP, all host threads) on a bounded sample, rank 0, N=1
+`--impl reference` times that oracle port alone (the reference is pure Python and cannot travel to
+the GPU box).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from ortho2align_b200 import synth  # noqa: E402
+from ortho2align_b200.columnar import concat_batches  # noqa: E402
+
+METRIC = "HSPs/sec through build_orthologs+best-ortholog"
+UNIT = "HSPs/s"
+CONFIG_NAMES = {1: "C1 strRNA 96 lncRNAs, 1k bg", 2: "C2 20k lncRNAs x 5 regions x ~2k HSPs, 10k bg/lncRNA",
+                3: "C3 as C2 with 1M bg/lncRNA", 4: "C4 dense chaining 5k regions x 50k HSPs",
+                5: "C5 100k lncRNAs, ~2e7 HSPs"}
+
+
+def _gen_block(args):
+    cfg, lo, hi, seed, total = args
+    return synth.workload(cfg, n_lnc=total, seed=seed, lnc_range=(lo, hi))
+
+
+def generate(cfg, n_lnc, seed, procs):
+    """Synthetic batch of `n_lnc` lncRNAs of config `cfg`, generated block-parallel (fork pool)."""
+    block = 64
+    spans = [(cfg, lo, min(lo + block * 4, n_lnc), seed, n_lnc) for lo in range(0, n_lnc, block * 4)]
+    if procs > 1 and len(spans) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_gen_block, spans)
+    else:
+        parts = [_gen_block(s) for s in spans]
+    return concat_batches(parts)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU every 100 ms (NVML) while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                 "applications_clocks_setting": 0x2}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_rate(batch, fitter, threads, repeats=1):
+    """Oracle port (TEST INFRASTRUCTURE used as the reported CPU baseline) on `batch`: HSPs/s."""
+    from oracle import oracle as O
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.build_batch(batch, fitter, True, n_threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return batch.n_hsp / best, best
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.lib().o2a_oracle_max_threads()
+    sample_lnc = args.ref_lnc
+    batch = generate(args.config, sample_lnc, args.seed, min(threads, 16))
+    for _ in range(args.warmup):
+        O.build_batch(batch, args.fitter, True, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.build_batch(batch, args.fitter, True, n_threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = batch.n_hsp / dt
+    sample = f"{sample_lnc} lncRNAs ({batch.n_hsp} HSPs) of the workload per step"
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": CONFIG_NAMES[args.config], "fitter": args.fitter, "fdr": True,
+                       "boundary": "columnar arrays in host RAM -> result arrays (CORE boundary, SURVEY.md §8d)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--lnc", type=int, default=None, help="lncRNAs per GPU (default: the config's full size)")
+    ap.add_argument("--fitter", default="hist", choices=["hist", "kde", "empirical"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-lnc", type=int, default=2000, help="lncRNAs in the cpu_baseline sample")
+    ap.add_argument("--ref-lnc", type=int, default=2000, help="lncRNAs per step of --impl reference")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    full = {1: 96, 2: 20_000, 3: 20_000, 4: 5_000, 5: 100_000}[args.config]
+    n_lnc = args.lnc or full
+    ncpu = os.cpu_count() or 8
+    procs = max(1, min(32, ncpu // max(world, 1)))
+    t_gen = time.perf_counter()
+    # weak scaling: every rank owns its own full-size shard of lncRNAs (independent units, no exchange)
+    batch = generate(args.config, n_lnc, args.seed + 1000 * rank, procs)
+    t_gen = time.perf_counter() - t_gen
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ortho2align_b200.engine import DeviceBatch, Engine
+
+    eng = Engine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_timing(True)
+    params = eng.params(args.fitter, True, 0.05, 5, 2, "block_length", "max")
+    with_kde = args.fitter == "kde"
+
+    # ---------------- device-resident arm (value) ----------------
+    dbatch = DeviceBatch(batch, dev)
+    dstruct = dbatch.struct(with_kde)
+    counts_t = torch.zeros(5, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(5 * world, dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step_device():
+        c = eng.run(dstruct, params)
+        if world > 1:     # the only collective of the path: gather the result counts on every rank
+            counts_t.copy_(torch.tensor([c.n_survivors, c.n_retained, c.n_chain_hsps, c.n_chains, c.n_failed_lnc]))
+            dist.all_gather_into_tensor(gathered, counts_t)
+        return c
+
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    score_ms = []
+    stage_acc = {}
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        c = step_device()
+        sm = eng.stage_ms()
+        score_ms.append(sm["score"])
+        for k, v in sm.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    hsps_all = batch.n_hsp * world
+    value = hsps_all / (ms_step * 1e-3)
+
+    # roofline of the dominant (streaming) kernel
+    peak, peak_src = measured_peak()
+    alg_bytes = 8.0 * batch.n_hsp + 21.0 * c.n_survivors
+    avg_score_ms = float(np.mean(score_ms))
+    achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_score", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}}
+
+    # ---------------- end-to-end arm (host buffers through the C-ABI) ----------------
+    e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
+    pinned = {}
+    for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
+        src = getattr(batch, k)
+        tp = torch.empty(src.shape, dtype=torch.from_numpy(src[:0]).dtype, pin_memory=True)
+        tp.numpy()[...] = src
+        pinned[k] = tp
+    hb = type(batch)(**{k: pinned[k].numpy() for k in pinned}, kde_factor=batch.kde_factor, names=None)
+    if with_kde:
+        hb.ensure_kde_factor()
+    hstruct = eng.host_struct(hb, with_kde)
+    del dbatch, dstruct
+    torch.cuda.empty_cache()
+
+    def step_e2e():
+        eng.run(hstruct, params)
+        res = eng.fetch(survivors=False)     # per-lncRNA thr/status/best + per-alignment chains
+        return res
+
+    step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = step_e2e()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item()) / e2e_steps
+    h2d = int(hb.nbytes())
+    d2h = int(res.thr.nbytes + res.status.nbytes + res.best_aln.nbytes + res.n_surv.nbytes + res.n_keep.nbytes
+              + res.chain_len.nbytes + res.chain_orient.nbytes + res.chain_score.nbytes + res.orient_scores.nbytes
+              + res.chain_off.nbytes + res.chain_idx.nbytes + res.chain_pq.nbytes + 40)
+    e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        threads = O.lib().o2a_oracle_max_threads()
+        k = min(args.cpu_lnc, batch.n_lnc)
+        sample = batch.slice_lnc(0, k)
+        rate, secs = cpu_port_rate(sample, args.fitter, threads, repeats=2)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {k} lncRNAs ({sample.n_hsp} HSPs) of the workload, {secs:.2f} s, best of 2"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": CONFIG_NAMES[args.config], "lncRNAs_per_gpu": batch.n_lnc,
+                           "alignments_per_gpu": batch.n_aln, "hsps_per_gpu": batch.n_hsp,
+                           "bg_scores_per_gpu": batch.n_bg, "fitter": args.fitter, "fdr": True, "alpha": 0.05,
+                           "survivors_per_gpu": int(c.n_survivors), "orthologs_per_gpu": int(c.n_chains),
+                           "parallelism": f"lncRNA shards x{world}, no data-path collective",
+                           "l2": "inputs (%.2f GB/GPU) larger than L2; no flush needed" % (batch.nbytes() / 1e9),
+                           "gen_seconds": round(t_gen, 1)},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

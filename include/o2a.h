@@ -1,0 +1,170 @@
+/*
+ * o2a.h — C ABI of libo2a_cuda.so: ortho2align's build_orthologs / get_best_orthologs hot path
+ * on one B200 (sm_100a). Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference (dmitrymyl/ortho2align, pure Python) has no FFI; its seams for this path are
+ * Python callables. Each entry point below names the reference interface it replaces
+ * (file:line under /root/reference/ortho2align) — INTEGRATION.md shows the ctypes stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success, a negative O2A_E* code otherwise;
+ *     o2a_last_error(ctx) gives the message. No exceptions cross the boundary.
+ *   - one ctx per GPU; a ctx is single-threaded (caller serialises); different ctxs may be used
+ *     from different threads / processes (one process per GPU under torchrun).
+ *   - the library never frees caller memory. Input pointers are host pointers (mem = O2A_MEM_HOST;
+ *     the library copies them host->device on its stream, pinned memory from o2a_host_alloc makes
+ *     that copy asynchronous) or device pointers on ctx's device (mem = O2A_MEM_DEVICE; zero copy).
+ *   - there is NO CPU fallback: without a usable CUDA device o2a_create fails.
+ *
+ * Data layout (three CSR levels; ortho2align_b200/columnar.py):
+ *   lncRNA l    : bg[bg_off[l] .. bg_off[l+1])  background scores AFTER the reference's patches
+ *                 (pipeline.py:746-754); alignments aln_off[l] .. aln_off[l+1]
+ *   alignment a : HSPs hsp_off[a] .. hsp_off[a+1]; qlen[a], slen[a] as stored in the JSON
+ *                 (alignment.py:477-487) — inputs, never recomputed
+ *   HSP h       : qstart,qend,sstart,send (int32 genomic coordinates), score (float64)
+ */
+#ifndef O2A_H
+#define O2A_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O2A_ABI_VERSION 1
+
+/* fitter: pipeline.py:839-842 maps 'hist' -> HistogramFitter, 'kde' -> KernelFitter.
+ * O2A_FIT_EMPIRICAL is an extension with no reference counterpart. */
+#define O2A_FIT_HIST 0
+#define O2A_FIT_KDE 1
+#define O2A_FIT_EMPIRICAL 2
+
+/* get_best_orthologs -value / -function (pipeline.py:981-989, cli_scripts.py:339-350) */
+#define O2A_BEST_BLOCK_LENGTH 0
+#define O2A_BEST_TOTAL_LENGTH 1
+#define O2A_BEST_BLOCK_COUNT 2
+#define O2A_BEST_WEIGHT 3
+#define O2A_BEST_MAX 0
+#define O2A_BEST_MIN 1
+
+#define O2A_MEM_HOST 0
+#define O2A_MEM_DEVICE 1
+
+/* per-lncRNA status: 0, or what the reference would have raised for this lncRNA (the lncRNA then
+ * belongs in query_exceptions.bed, pipeline.py:797-798, 862-868) */
+#define O2A_STATUS_OK 0
+#define O2A_STATUS_ORIENTATION_NONE 1  /* alignment.py:865-872 KeyError/TypeError */
+#define O2A_STATUS_BRENTQ 2            /* fitting.py:239 RuntimeError (no convergence) */
+#define O2A_STATUS_TOO_MANY_BINS 3     /* fitting.py:152 np.histogram ValueError */
+
+#define O2A_EINVAL (-1)
+#define O2A_ECUDA (-2)
+#define O2A_ENOMEM (-3)
+#define O2A_ESTATE (-4)
+
+typedef struct o2a_ctx o2a_ctx;
+
+typedef struct o2a_batch {
+    int64_t n_lnc, n_aln, n_hsp, n_bg;
+    const int64_t *bg_off;     /* [n_lnc+1] */
+    const int32_t *bg;         /* [n_bg]    */
+    const double  *kde_factor; /* [n_lnc] gaussian_kde.factor per lncRNA (host-side scalar of
+                                  fitting.py:264,295); may be NULL unless fitter == O2A_FIT_KDE */
+    const int64_t *aln_off;    /* [n_lnc+1] */
+    const int64_t *hsp_off;    /* [n_aln+1] */
+    const int64_t *qlen;       /* [n_aln] */
+    const int64_t *slen;       /* [n_aln] */
+    const int32_t *qstart, *qend, *sstart, *send; /* [n_hsp] */
+    const double  *score;      /* [n_hsp] */
+    int32_t mem;               /* O2A_MEM_HOST | O2A_MEM_DEVICE (applies to every pointer above) */
+    int32_t reserved;
+    int64_t max_aln_hsps;      /* max over a of hsp_off[a+1]-hsp_off[a]; 0 = let the library find out */
+    int64_t max_lnc_bg;        /* max over l of bg_off[l+1]-bg_off[l];   0 = let the library find out */
+} o2a_batch;
+
+/* build_orthologs(threshold, gapopen, gapextend, fdr, fitting) + get_best_orthologs(value,
+ * function): pipeline.py:801-812, 959-968 */
+typedef struct o2a_params {
+    int32_t fitter;
+    int32_t fdr;
+    double  alpha;
+    int32_t gapopen, gapextend;
+    int32_t best_value, best_function;
+} o2a_params;
+
+typedef struct o2a_counts {
+    int64_t n_survivors;   /* HSPs with score > isf(alpha)               (pipeline.py:765) */
+    int64_t n_retained;    /* HSPs entering the chaining                 (pipeline.py:774-776) */
+    int64_t n_chain_hsps;  /* HSPs in the chosen chains                  (alignment.py:1032) */
+    int64_t n_chains;      /* alignments with a non-empty chain = ortholog records */
+    int64_t n_failed_lnc;  /* lncRNAs with status != 0 */
+} o2a_counts;
+
+int  o2a_abi_version(void);
+int  o2a_create(o2a_ctx **out, int device);
+void o2a_destroy(o2a_ctx *ctx);
+const char *o2a_last_error(const o2a_ctx *ctx);
+/* run on an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+int  o2a_set_stream(o2a_ctx *ctx, void *cuda_stream);
+
+/* pinned (page-locked, device-mapped) host memory for batch inputs / fetched outputs */
+void *o2a_host_alloc(size_t bytes);
+void  o2a_host_free(void *p);
+
+/*
+ * Replaces the pool fan-out of pipeline.py:846-860: `_build` (pipeline.py:722-798) for EVERY
+ * lncRNA of the batch in one call, plus the selection of get_best_orthologs (pipeline.py:959-1024):
+ *   background fit + isf(alpha)      fitting.py:142-155, 206-215 (hist) / 254-264, 335-356 (kde)
+ *   score filter, strict '>'         alignment.py:618-646, pipeline.py:765
+ *   p-values sf(score)               fitting.py:184-193 (hist) / 282-310 (kde), pipeline.py:766
+ *   q = (m*p)/rank, keep q <= alpha  fitting.py:359-364, pipeline.py:769-776 (ties: stable order)
+ *   best chain per alignment         alignment.py:863-927, 982-1046
+ *   best ortholog per lncRNA         pipeline.py:981-1016
+ * Results stay on the device inside ctx until fetched. Blocks until the counts are known.
+ */
+int o2a_build_batch(o2a_ctx *ctx, const o2a_batch *batch, const o2a_params *params, o2a_counts *counts);
+
+/* Results of the last o2a_build_batch. Output pointers are HOST pointers sized as noted; any may
+ * be NULL to skip that array. */
+int o2a_fetch_lnc(o2a_ctx *ctx, double *thr /*n_lnc*/, int32_t *status /*n_lnc*/, int64_t *best_aln /*n_lnc*/);
+int o2a_fetch_aln(o2a_ctx *ctx, int32_t *n_surv, int32_t *n_keep, int32_t *chain_len /*n_aln each*/,
+                  uint8_t *chain_orient /*n_aln: 0 direct, 1 reverse*/, double *chain_score /*n_aln*/,
+                  double *orient_scores /*2*n_aln: direct, reverse*/);
+int o2a_fetch_survivors(o2a_ctx *ctx, int64_t *surv_off /*n_aln+1*/, int32_t *surv_idx, double *surv_p,
+                        double *surv_pq, uint8_t *surv_keep /*n_survivors each*/);
+int o2a_fetch_chains(o2a_ctx *ctx, int64_t *chain_off /*n_aln+1*/, int32_t *chain_idx, double *chain_pq /*n_chain_hsps*/);
+
+/* Operator-level seams (used by the Python mirrors of the reference classes):
+ *  - fitter plugin `F(data).sf(x)`, `.isf(q)`           fitting.py:8-85 (AbstractFitter seam)
+ *  - `Alignment.best_chain(gapopen, gapextend)`          alignment.py:1032-1046
+ * Host pointers. `bg` must already be patched. Returns 0, or O2A_EINVAL with status in *status. */
+int o2a_fitter_eval(o2a_ctx *ctx, int32_t fitter, const int32_t *bg, int64_t n_bg, double kde_factor,
+                    const double *x, int64_t n_x, double *sf_out,
+                    const double *q, int64_t n_q, double *isf_out, int32_t *status);
+int o2a_best_chain(o2a_ctx *ctx, int64_t n, const int32_t *qstart, const int32_t *qend,
+                   const int32_t *sstart, const int32_t *send, const double *score,
+                   int64_t qlen, int64_t slen, int32_t gapopen, int32_t gapextend,
+                   int32_t *chain_idx /*n*/, int64_t *chain_len, int32_t *orient, double *chain_score,
+                   double *orient_scores /*2*/, int32_t *status);
+
+/* Instrumentation for bench.py: kernels launched by this ctx since creation, and CUDA-event
+ * durations (ms, on the launching stream) of the stages of the last o2a_build_batch when timing
+ * is enabled. Stage ids: */
+#define O2A_STAGE_H2D 0
+#define O2A_STAGE_FIT 1
+#define O2A_STAGE_SCORE 2     /* filter + p-value + rank/q (the HBM-bound streaming kernel) */
+#define O2A_STAGE_RANK_BIG 3
+#define O2A_STAGE_CHAIN 4
+#define O2A_STAGE_BEST 5
+#define O2A_STAGE_COUNT 6
+int64_t o2a_launch_count(const o2a_ctx *ctx);
+int  o2a_set_timing(o2a_ctx *ctx, int enabled);
+int  o2a_get_stage_ms(o2a_ctx *ctx, float *ms /*O2A_STAGE_COUNT*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* O2A_H */

@@ -1,0 +1,747 @@
+// o2a_api.cu — C ABI (include/o2a.h) of libo2a_cuda.so: context, device workspace, stage launches.
+// sm_100a only; there is no CPU fallback anywhere in this library.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/o2a.h"
+#include "o2a_chain.cuh"
+#include "o2a_device.cuh"
+#include "o2a_fit.cuh"
+#include "o2a_kde.cuh"
+#include "o2a_score.cuh"
+
+using namespace o2a;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+constexpr int N_EVENTS = O2A_STAGE_COUNT + 1;
+constexpr int SM_COUNT_FALLBACK = 148;
+constexpr long long UV_MAX_RANGE = 1ll << 20;
+
+}  // namespace
+
+struct o2a_ctx {
+    int device = 0;
+    int sm_count = SM_COUNT_FALLBACK;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    long long launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[N_EVENTS] = {};
+    bool ev_valid = false;
+    // batch geometry of the last build
+    bool have_result = false;
+    o2a_batch b{};          // device pointers of the inputs actually used
+    o2a_params prm{};
+    o2a_counts counts{};
+    // owned copies of host inputs
+    DevBuf in_bg_off, in_bg, in_kde, in_aln_off, in_hsp_off, in_qlen, in_slen, in_qs, in_qe, in_ss, in_se, in_score;
+    // workspace
+    DevBuf aln_lnc, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
+    DevBuf n_surv, n_keep, surv_idx, surv_p, surv_pq, surv_keep;
+    DevBuf chain_len, chain_orient, chain_score, orient_scores, chain_slot, best_key, best_aln;
+    DevBuf big_list, big_count, counters;
+    DevBuf fit_cnt, fit_leaf, fit_leaf_sum, uv_scratch;
+    DevBuf sort_k0, sort_k1, sort_v0, sort_v1;
+    DevBuf cb_qs, cb_qe, cb_ss, cb_se, cb_sc, cb_id, cb_total, cb_prev, cb_f, cb_chain;
+    DevBuf off_a, off_b, out_i32, out_f64a, out_f64b, out_u8, maxred;
+};
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+            return O2A_ECUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                            \
+    do {                                                                                          \
+        ctx->launches++;                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess) {                                                                 \
+            ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e__);                  \
+            return O2A_ECUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+static int ensure(o2a_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return 0;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return O2A_ENOMEM;
+    }
+    b.cap = want;
+    return 0;
+}
+#define ENS(buf, bytes) do { int r__ = ensure(ctx, ctx->buf, (size_t)(bytes)); if (r__) return r__; } while (0)
+
+template <typename T> static T* P(const DevBuf& b) { return reinterpret_cast<T*>(b.p); }
+
+// --------------------------------------------------------------------------------------------
+// small utility kernels
+// --------------------------------------------------------------------------------------------
+__global__ void k_fill_aln_lnc(long long n_lnc, const long long* __restrict__ aln_off, int* __restrict__ aln_lnc)
+{
+    for (long long l = blockIdx.x; l < n_lnc; l += gridDim.x)
+        for (long long a = aln_off[l] + threadIdx.x; a < aln_off[l + 1]; a += blockDim.x) aln_lnc[a] = (int)l;
+}
+
+__global__ void k_max_diff(long long n, const long long* __restrict__ off, unsigned long long* __restrict__ out)
+{
+    long long m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, off[i + 1] - off[i]);
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)m);
+}
+
+__global__ void k_counts(long long n_aln, long long n_lnc, const int* __restrict__ n_surv, const int* __restrict__ n_keep,
+                         const int* __restrict__ chain_len, const int* __restrict__ status,
+                         unsigned long long* __restrict__ out /*5*/)
+{
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < n_aln; a += stride) {
+        c[0] += n_surv[a]; c[1] += n_keep[a]; c[2] += chain_len[a]; c[3] += chain_len[a] > 0;
+    }
+    for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < n_lnc; l += stride) c[4] += status[l] != 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        for (int d = 16; d > 0; d >>= 1) c[k] += __shfl_xor_sync(FULL_MASK, c[k], d);
+        if ((threadIdx.x & 31) == 0 && c[k]) atomicAdd(&out[k], c[k]);
+    }
+}
+
+// exclusive scan of int counts -> int64 offsets [n+1]; single CTA, sequential over chunks
+__global__ void k_scan_offsets(long long n, const int* __restrict__ cnt, long long* __restrict__ off)
+{
+    __shared__ int s_scan[1024 / 32 + 2];
+    __shared__ long long s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (long long i0 = 0; i0 < n; i0 += blockDim.x) {
+        long long i = i0 + threadIdx.x;
+        int v = i < n ? cnt[i] : 0;
+        int tot;
+        int ex = cta_exclusive_scan(v, s_scan, &tot);
+        long long base = s_base;
+        if (i < n) off[i] = base + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n] = s_base;
+}
+
+__global__ void k_gather_surv(long long n_aln, const long long* __restrict__ hsp_off, const long long* __restrict__ off,
+                              const int* __restrict__ surv_idx, const double* __restrict__ surv_p,
+                              const double* __restrict__ surv_pq, const unsigned char* __restrict__ surv_keep,
+                              int* __restrict__ o_idx, double* __restrict__ o_p, double* __restrict__ o_pq,
+                              unsigned char* __restrict__ o_keep)
+{
+    for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
+        const long long h0 = hsp_off[a], o0 = off[a];
+        const int n = (int)(off[a + 1] - o0);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            o_idx[o0 + k] = surv_idx[h0 + k]; o_p[o0 + k] = surv_p[h0 + k];
+            o_pq[o0 + k] = surv_pq[h0 + k]; o_keep[o0 + k] = surv_keep[h0 + k];
+        }
+    }
+}
+
+__global__ void k_gather_chain(long long n_aln, const long long* __restrict__ hsp_off, const long long* __restrict__ off,
+                               const int* __restrict__ chain_slot, const int* __restrict__ surv_idx,
+                               const double* __restrict__ surv_pq, int* __restrict__ o_idx, double* __restrict__ o_pq)
+{
+    for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
+        const long long h0 = hsp_off[a], o0 = off[a];
+        const int n = (int)(off[a + 1] - o0);
+        for (int c = threadIdx.x; c < n; c += blockDim.x) {
+            int s = chain_slot[h0 + c];
+            o_idx[o0 + c] = surv_idx[h0 + s]; o_pq[o0 + c] = surv_pq[h0 + s];
+        }
+    }
+}
+
+// sf at arbitrary points for the fitter seam (o2a_fitter_eval)
+__global__ void k_sf_eval(int fitter, const double* __restrict__ x, long long n_x, const LncFit* __restrict__ fits,
+                          const int* __restrict__ tbl_k, const double* __restrict__ tbl_cum,
+                          const int* __restrict__ uv_val, const int* __restrict__ uv_cnt, const int* __restrict__ uv_n,
+                          double kde_factor, double n_bg, double* __restrict__ out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_x) return;
+    double v = x[i], p;
+    if (fitter == 0) { LncFit f = fits[0]; p = hist_sf(v, f, tbl_k, tbl_cum); }
+    else if (fitter == 1) p = kde_sf_compressed(v, uv_val, uv_cnt, uv_n[0], kde_factor, n_bg);
+    else p = emp_sf_compressed(v, uv_val, uv_cnt, uv_n[0], n_bg);
+    out[i] = p;
+}
+
+__global__ void k_iota_keep(int n, int* __restrict__ idx, unsigned char* __restrict__ keep)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { idx[i] = i; keep[i] = 1; }
+}
+
+// --------------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------------
+extern "C" int o2a_abi_version(void) { return O2A_ABI_VERSION; }
+
+extern "C" int o2a_create(o2a_ctx** out, int device)
+{
+    if (!out) return O2A_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return O2A_ECUDA;   // no CUDA device: there is no CPU fallback
+    }
+    o2a_ctx* ctx = new o2a_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return O2A_ECUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return O2A_ECUDA; }
+    for (int i = 0; i < N_EVENTS; ++i) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return 0;
+}
+
+static void free_all(o2a_ctx* ctx)
+{
+    DevBuf* bufs[] = {&ctx->in_bg_off, &ctx->in_bg, &ctx->in_kde, &ctx->in_aln_off, &ctx->in_hsp_off, &ctx->in_qlen,
+                      &ctx->in_slen, &ctx->in_qs, &ctx->in_qe, &ctx->in_ss, &ctx->in_se, &ctx->in_score,
+                      &ctx->aln_lnc, &ctx->thr, &ctx->fits, &ctx->tbl_k, &ctx->tbl_cum, &ctx->status, &ctx->uv_val,
+                      &ctx->uv_cnt, &ctx->uv_n, &ctx->n_surv, &ctx->n_keep, &ctx->surv_idx, &ctx->surv_p,
+                      &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
+                      &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->big_list,
+                      &ctx->big_count, &ctx->counters, &ctx->fit_cnt, &ctx->fit_leaf, &ctx->fit_leaf_sum,
+                      &ctx->uv_scratch, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
+                      &ctx->cb_qe, &ctx->cb_ss, &ctx->cb_se, &ctx->cb_sc, &ctx->cb_id, &ctx->cb_total, &ctx->cb_prev,
+                      &ctx->cb_f, &ctx->cb_chain, &ctx->off_a, &ctx->off_b, &ctx->out_i32, &ctx->out_f64a,
+                      &ctx->out_f64b, &ctx->out_u8, &ctx->maxred};
+    for (DevBuf* b : bufs) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+}
+
+extern "C" void o2a_destroy(o2a_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_all(ctx);
+    for (int i = 0; i < N_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* o2a_last_error(const o2a_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int o2a_set_stream(o2a_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return O2A_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else {
+        ctx->own_stream = true;
+        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    }
+    return 0;
+}
+
+extern "C" void* o2a_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void o2a_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int64_t o2a_launch_count(const o2a_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
+extern "C" int o2a_set_timing(o2a_ctx* ctx, int enabled) { if (!ctx) return O2A_EINVAL; ctx->timing = enabled != 0; return 0; }
+extern "C" int o2a_get_stage_ms(o2a_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return O2A_EINVAL;
+    if (!ctx->ev_valid) { ctx->err = "no timed build_batch yet (o2a_set_timing)"; return O2A_ESTATE; }
+    for (int i = 0; i < O2A_STAGE_COUNT; ++i) CU(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// stages
+// --------------------------------------------------------------------------------------------
+static int stage_event(o2a_ctx* ctx, int i)
+{
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[i], ctx->stream));
+    return 0;
+}
+
+template <typename T>
+static int upload(o2a_ctx* ctx, DevBuf& dst, const T* src, size_t n, const T** out)
+{
+    int r = ensure(ctx, dst, n * sizeof(T));
+    if (r) return r;
+    if (n) CU(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = reinterpret_cast<const T*>(dst.p);
+    return 0;
+}
+
+static int grid_for(o2a_ctx* ctx, long long items, int per_sm)
+{
+    long long g = (long long)ctx->sm_count * per_sm;
+    if (items < g) g = items;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static int run_fit(o2a_ctx* ctx)
+{
+    const o2a_batch& b = ctx->b;
+    const o2a_params& p = ctx->prm;
+    ENS(thr, b.n_lnc * sizeof(double));
+    ENS(status, b.n_lnc * sizeof(int));
+    if (b.n_lnc == 0) return 0;
+    if (p.fitter == O2A_FIT_HIST) {
+        ENS(fits, b.n_lnc * sizeof(LncFit));
+        ENS(tbl_k, (b.n_bg / 2 + 2) * sizeof(int));
+        ENS(tbl_cum, (b.n_bg / 2 + 2) * sizeof(double));
+        const long long max_B = b.max_lnc_bg / 2;
+        const bool big = max_B > FIT_SMEM_BINS;
+        int grid = grid_for(ctx, b.n_lnc, big ? 2 : 8);
+        long long max_leaves = max_B / 64 + 2;
+        if (big) ENS(fit_cnt, (size_t)grid * max_B * sizeof(int));
+        if (max_B > (long long)FIT_SMEM_LEAVES * 64) {
+            ENS(fit_leaf, (size_t)grid * max_leaves * sizeof(PwNode));
+            ENS(fit_leaf_sum, (size_t)grid * max_leaves * sizeof(double));
+        }
+        k_fit_hist<<<grid, FIT_THREADS, 0, ctx->stream>>>(
+            b.n_lnc, (const long long*)b.bg_off, b.bg, p.alpha, P<double>(ctx->thr), P<LncFit>(ctx->fits),
+            P<int>(ctx->tbl_k), P<double>(ctx->tbl_cum), P<int>(ctx->status), P<int>(ctx->fit_cnt), max_B,
+            P<PwNode>(ctx->fit_leaf), P<double>(ctx->fit_leaf_sum), max_leaves);
+        LAUNCH_CHECK();
+    } else {
+        if (p.fitter == O2A_FIT_KDE && !b.kde_factor) { ctx->err = "kde_factor is required for the KDE fitter"; return O2A_EINVAL; }
+        ENS(uv_val, (b.n_bg + 1) * sizeof(int));
+        ENS(uv_cnt, (b.n_bg + 1) * sizeof(int));
+        ENS(uv_n, b.n_lnc * sizeof(int));
+        int grid = grid_for(ctx, b.n_lnc, 1);
+        ENS(uv_scratch, (size_t)grid * UV_MAX_RANGE * sizeof(int));
+        k_fit_uv<<<grid, UV_THREADS, 0, ctx->stream>>>(
+            b.n_lnc, (const long long*)b.bg_off, b.bg, b.kde_factor, p.fitter, p.alpha, P<double>(ctx->thr),
+            P<int>(ctx->uv_val), P<int>(ctx->uv_cnt), P<int>(ctx->uv_n), P<int>(ctx->status),
+            P<int>(ctx->uv_scratch), UV_MAX_RANGE);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int ensure_sort_scratch(o2a_ctx* ctx, int grid, long long cap)
+{
+    ENS(sort_k0, (size_t)grid * cap * 8); ENS(sort_k1, (size_t)grid * cap * 8);
+    ENS(sort_v0, (size_t)grid * cap * 4); ENS(sort_v1, (size_t)grid * cap * 4);
+    return 0;
+}
+
+static int run_score(o2a_ctx* ctx)
+{
+    const o2a_batch& b = ctx->b;
+    const o2a_params& p = ctx->prm;
+    ENS(n_surv, b.n_aln * sizeof(int)); ENS(n_keep, b.n_aln * sizeof(int));
+    ENS(surv_idx, b.n_hsp * sizeof(int)); ENS(surv_p, b.n_hsp * sizeof(double));
+    ENS(surv_pq, b.n_hsp * sizeof(double)); ENS(surv_keep, b.n_hsp);
+    ENS(big_list, (b.n_aln + 1) * sizeof(int)); ENS(big_count, 2 * sizeof(int));
+    CU(cudaMemsetAsync(ctx->big_count.p, 0, 2 * sizeof(int), ctx->stream));
+    if (b.n_aln == 0) return 0;
+    ScoreArgs A{};
+    A.n_aln = b.n_aln; A.hsp_off = (const long long*)b.hsp_off; A.aln_lnc = P<int>(ctx->aln_lnc);
+    A.score = b.score; A.thr = P<double>(ctx->thr); A.lnc_status = P<int>(ctx->status);
+    A.fits = P<LncFit>(ctx->fits); A.tbl_k = P<int>(ctx->tbl_k); A.tbl_cum = P<double>(ctx->tbl_cum);
+    A.bg_off = (const long long*)b.bg_off;
+    A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt); A.uv_n = P<int>(ctx->uv_n);
+    A.kde_factor = b.kde_factor; A.fitter = p.fitter; A.fdr = p.fdr; A.alpha = p.alpha;
+    A.n_surv = P<int>(ctx->n_surv); A.n_keep = P<int>(ctx->n_keep); A.surv_idx = P<int>(ctx->surv_idx);
+    A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq); A.surv_keep = P<unsigned char>(ctx->surv_keep);
+    A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
+    int grid = grid_for(ctx, b.n_aln, 8);
+    k_score<<<grid, SCORE_THREADS, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
+    int r = stage_event(ctx, O2A_STAGE_RANK_BIG);
+    if (r) return r;
+    if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
+        int g2 = grid_for(ctx, b.n_aln, 2);
+        r = ensure_sort_scratch(ctx, g2, b.max_aln_hsps);
+        if (r) return r;
+        k_rank_big<<<g2, RANKBIG_THREADS, 0, ctx->stream>>>(
+            P<int>(ctx->big_list), P<int>(ctx->big_count), (const long long*)b.hsp_off, p.alpha, P<int>(ctx->n_surv),
+            P<int>(ctx->n_keep), P<double>(ctx->surv_p), P<double>(ctx->surv_pq), P<unsigned char>(ctx->surv_keep),
+            P<unsigned long long>(ctx->sort_k0), P<unsigned long long>(ctx->sort_k1), P<unsigned int>(ctx->sort_v0),
+            P<unsigned int>(ctx->sort_v1), b.max_aln_hsps);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int run_chain(o2a_ctx* ctx)
+{
+    const o2a_batch& b = ctx->b;
+    const o2a_params& p = ctx->prm;
+    ENS(chain_len, b.n_aln * sizeof(int)); ENS(chain_orient, b.n_aln); ENS(chain_score, b.n_aln * sizeof(double));
+    ENS(orient_scores, 2 * b.n_aln * sizeof(double)); ENS(chain_slot, b.n_hsp * sizeof(int));
+    ENS(best_key, b.n_aln * sizeof(double)); ENS(best_aln, b.n_lnc * sizeof(long long));
+    if (b.n_aln > 0) {
+        ChainArgs A{};
+        A.n_aln = b.n_aln; A.hsp_off = (const long long*)b.hsp_off; A.aln_lnc = P<int>(ctx->aln_lnc);
+        A.qlen = (const long long*)b.qlen; A.slen = (const long long*)b.slen;
+        A.qstart = b.qstart; A.qend = b.qend; A.sstart = b.sstart; A.send = b.send; A.score = b.score;
+        A.n_surv = P<int>(ctx->n_surv); A.n_keep = P<int>(ctx->n_keep); A.surv_idx = P<int>(ctx->surv_idx);
+        A.surv_keep = P<unsigned char>(ctx->surv_keep); A.gapopen = p.gapopen; A.gapextend = p.gapextend;
+        A.best_value = p.best_value;
+        A.chain_len = P<int>(ctx->chain_len); A.chain_orient = P<unsigned char>(ctx->chain_orient);
+        A.chain_score = P<double>(ctx->chain_score); A.orient_scores = P<double>(ctx->orient_scores);
+        A.chain_slot = P<int>(ctx->chain_slot); A.best_key = P<double>(ctx->best_key);
+        A.lnc_status = P<int>(ctx->status); A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count) + 1;
+        int grid = grid_for(ctx, b.n_aln, 12);
+        k_chain_small<<<grid, CHAIN_THREADS, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+        if (b.max_aln_hsps > CHAIN_SMALL_MAX) {
+            int g2 = grid_for(ctx, b.n_aln, 2);
+            const long long cap = b.max_aln_hsps;
+            int r = ensure_sort_scratch(ctx, g2, cap);
+            if (r) return r;
+            ENS(cb_qs, (size_t)g2 * cap * 4); ENS(cb_qe, (size_t)g2 * cap * 4); ENS(cb_ss, (size_t)g2 * cap * 4);
+            ENS(cb_se, (size_t)g2 * cap * 4); ENS(cb_sc, (size_t)g2 * cap * 8); ENS(cb_id, (size_t)g2 * cap * 4);
+            ENS(cb_total, (size_t)g2 * (cap + 2) * 8); ENS(cb_prev, (size_t)g2 * (cap + 2) * 4);
+            ENS(cb_f, (size_t)g2 * (cap + 2) * 4); ENS(cb_chain, (size_t)g2 * cap * 2 * 4);
+            ChainBigScratch S{P<unsigned long long>(ctx->sort_k0), P<unsigned long long>(ctx->sort_k1),
+                              P<unsigned int>(ctx->sort_v0), P<unsigned int>(ctx->sort_v1),
+                              P<int>(ctx->cb_qs), P<int>(ctx->cb_qe), P<int>(ctx->cb_ss), P<int>(ctx->cb_se),
+                              P<double>(ctx->cb_sc), P<int>(ctx->cb_id), P<double>(ctx->cb_total), P<int>(ctx->cb_prev),
+                              P<int>(ctx->cb_f), P<int>(ctx->cb_chain), cap};
+            k_chain_big<<<g2, CHAINBIG_THREADS, 0, ctx->stream>>>(A, S);
+            LAUNCH_CHECK();
+        }
+    }
+    int r = stage_event(ctx, O2A_STAGE_BEST);
+    if (r) return r;
+    if (b.n_lnc > 0) {
+        k_best<<<(unsigned)((b.n_lnc + 127) / 128), 128, 0, ctx->stream>>>(
+            b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->status), P<int>(ctx->chain_len), P<double>(ctx->chain_score),
+            P<double>(ctx->best_key), p.best_function, P<long long>(ctx->best_aln));
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int find_max_diff(o2a_ctx* ctx, long long n, const long long* off_dev, long long* out)
+{
+    ENS(maxred, 8);
+    CU(cudaMemsetAsync(ctx->maxred.p, 0, 8, ctx->stream));
+    if (n > 0) {
+        k_max_diff<<<grid_for(ctx, (n + 255) / 256, 4), 256, 0, ctx->stream>>>(n, off_dev, P<unsigned long long>(ctx->maxred));
+        LAUNCH_CHECK();
+    }
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, ctx->maxred.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = (long long)v;
+    return 0;
+}
+
+extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_params* params, o2a_counts* counts)
+{
+    if (!ctx) return O2A_EINVAL;
+    if (!batch || !params) { ctx->err = "null batch/params"; return O2A_EINVAL; }
+    if (batch->n_lnc < 0 || batch->n_aln < 0 || batch->n_hsp < 0 || batch->n_bg < 0) { ctx->err = "negative size"; return O2A_EINVAL; }
+    if (params->fitter < 0 || params->fitter > 2) { ctx->err = "unknown fitter"; return O2A_EINVAL; }
+    if (batch->n_hsp > 0x7fffffffll * 64) { ctx->err = "batch too large"; return O2A_EINVAL; }
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_result = false;
+    ctx->ev_valid = false;
+    ctx->prm = *params;
+    o2a_batch& b = ctx->b;
+    b = *batch;
+    int r;
+    if ((r = stage_event(ctx, O2A_STAGE_H2D))) return r;
+    if (batch->mem == O2A_MEM_HOST) {
+        // the reference pickles file names to workers which json.load them (pipeline.py:743-754);
+        // here the columnar arrays cross PCIe once
+        if ((r = upload(ctx, ctx->in_bg_off, batch->bg_off, (size_t)batch->n_lnc + 1, &b.bg_off))) return r;
+        if ((r = upload(ctx, ctx->in_bg, batch->bg, (size_t)batch->n_bg, &b.bg))) return r;
+        if (batch->kde_factor && params->fitter == O2A_FIT_KDE) {
+            if ((r = upload(ctx, ctx->in_kde, batch->kde_factor, (size_t)batch->n_lnc, &b.kde_factor))) return r;
+        } else b.kde_factor = nullptr;
+        if ((r = upload(ctx, ctx->in_aln_off, batch->aln_off, (size_t)batch->n_lnc + 1, &b.aln_off))) return r;
+        if ((r = upload(ctx, ctx->in_hsp_off, batch->hsp_off, (size_t)batch->n_aln + 1, &b.hsp_off))) return r;
+        if ((r = upload(ctx, ctx->in_qlen, batch->qlen, (size_t)batch->n_aln, &b.qlen))) return r;
+        if ((r = upload(ctx, ctx->in_slen, batch->slen, (size_t)batch->n_aln, &b.slen))) return r;
+        if ((r = upload(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, &b.score))) return r;
+        if ((r = upload(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, &b.qstart))) return r;
+        if ((r = upload(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, &b.qend))) return r;
+        if ((r = upload(ctx, ctx->in_ss, batch->sstart, (size_t)batch->n_hsp, &b.sstart))) return r;
+        if ((r = upload(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, &b.send))) return r;
+        if (b.max_aln_hsps <= 0) {
+            long long m = 0;
+            for (long long a = 0; a < batch->n_aln; ++a) { long long d = batch->hsp_off[a + 1] - batch->hsp_off[a]; if (d > m) m = d; }
+            b.max_aln_hsps = m;
+        }
+        if (b.max_lnc_bg <= 0) {
+            long long m = 0;
+            for (long long l = 0; l < batch->n_lnc; ++l) { long long d = batch->bg_off[l + 1] - batch->bg_off[l]; if (d > m) m = d; }
+            b.max_lnc_bg = m;
+        }
+    } else {
+        if (b.max_aln_hsps <= 0 && (r = find_max_diff(ctx, b.n_aln, (const long long*)b.hsp_off, (long long*)&b.max_aln_hsps))) return r;
+        if (b.max_lnc_bg <= 0 && (r = find_max_diff(ctx, b.n_lnc, (const long long*)b.bg_off, (long long*)&b.max_lnc_bg))) return r;
+    }
+    ENS(aln_lnc, b.n_aln * sizeof(int));
+    if (b.n_lnc > 0) {
+        k_fill_aln_lnc<<<grid_for(ctx, b.n_lnc, 16), 64, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->aln_lnc));
+        LAUNCH_CHECK();
+    }
+    if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
+    if ((r = run_fit(ctx))) return r;
+    if ((r = stage_event(ctx, O2A_STAGE_SCORE))) return r;
+    if ((r = run_score(ctx))) return r;       // records O2A_STAGE_RANK_BIG itself
+    if ((r = stage_event(ctx, O2A_STAGE_CHAIN))) return r;
+    if ((r = run_chain(ctx))) return r;       // records O2A_STAGE_BEST itself
+    ENS(counters, 5 * 8);
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 5 * 8, ctx->stream));
+    {
+        long long items = b.n_aln > b.n_lnc ? b.n_aln : b.n_lnc;
+        k_counts<<<grid_for(ctx, (items + 255) / 256, 4), 256, 0, ctx->stream>>>(
+            b.n_aln, b.n_lnc, P<int>(ctx->n_surv), P<int>(ctx->n_keep), P<int>(ctx->chain_len), P<int>(ctx->status),
+            P<unsigned long long>(ctx->counters));
+        LAUNCH_CHECK();
+    }
+    if ((r = stage_event(ctx, O2A_STAGE_COUNT))) return r;
+    unsigned long long c[5];
+    CU(cudaMemcpyAsync(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->counts.n_survivors = (long long)c[0]; ctx->counts.n_retained = (long long)c[1];
+    ctx->counts.n_chain_hsps = (long long)c[2]; ctx->counts.n_chains = (long long)c[3];
+    ctx->counts.n_failed_lnc = (long long)c[4];
+    if (counts) *counts = ctx->counts;
+    ctx->have_result = true;
+    ctx->ev_valid = ctx->timing;
+    return 0;
+}
+
+#define NEED_RESULT() do { if (!ctx) return O2A_EINVAL; if (!ctx->have_result) { ctx->err = "no result: call o2a_build_batch first"; return O2A_ESTATE; } CU(cudaSetDevice(ctx->device)); } while (0)
+
+template <typename T>
+static int download(o2a_ctx* ctx, T* dst, const void* src, size_t n)
+{
+    if (dst && n) CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+extern "C" int o2a_fetch_lnc(o2a_ctx* ctx, double* thr, int32_t* status, int64_t* best_aln)
+{
+    NEED_RESULT();
+    int r;
+    size_t n = (size_t)ctx->b.n_lnc;
+    if ((r = download(ctx, thr, ctx->thr.p, n))) return r;
+    if ((r = download(ctx, status, ctx->status.p, n))) return r;
+    if ((r = download(ctx, best_aln, ctx->best_aln.p, n))) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int o2a_fetch_aln(o2a_ctx* ctx, int32_t* n_surv, int32_t* n_keep, int32_t* chain_len, uint8_t* chain_orient,
+                             double* chain_score, double* orient_scores)
+{
+    NEED_RESULT();
+    int r;
+    size_t n = (size_t)ctx->b.n_aln;
+    if ((r = download(ctx, n_surv, ctx->n_surv.p, n))) return r;
+    if ((r = download(ctx, n_keep, ctx->n_keep.p, n))) return r;
+    if ((r = download(ctx, chain_len, ctx->chain_len.p, n))) return r;
+    if ((r = download(ctx, chain_orient, ctx->chain_orient.p, n))) return r;
+    if ((r = download(ctx, chain_score, ctx->chain_score.p, n))) return r;
+    if ((r = download(ctx, orient_scores, ctx->orient_scores.p, 2 * n))) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int o2a_fetch_survivors(o2a_ctx* ctx, int64_t* surv_off, int32_t* surv_idx, double* surv_p, double* surv_pq,
+                                   uint8_t* surv_keep)
+{
+    NEED_RESULT();
+    const o2a_batch& b = ctx->b;
+    const size_t tot = (size_t)ctx->counts.n_survivors;
+    ENS(off_a, (b.n_aln + 1) * 8);
+    ENS(out_i32, tot * 4); ENS(out_f64a, tot * 8); ENS(out_f64b, tot * 8); ENS(out_u8, tot);
+    k_scan_offsets<<<1, 1024, 0, ctx->stream>>>(b.n_aln, P<int>(ctx->n_surv), P<long long>(ctx->off_a));
+    LAUNCH_CHECK();
+    if (b.n_aln > 0 && tot > 0) {
+        k_gather_surv<<<grid_for(ctx, b.n_aln, 16), 128, 0, ctx->stream>>>(
+            b.n_aln, (const long long*)b.hsp_off, P<long long>(ctx->off_a), P<int>(ctx->surv_idx), P<double>(ctx->surv_p),
+            P<double>(ctx->surv_pq), P<unsigned char>(ctx->surv_keep), P<int>(ctx->out_i32), P<double>(ctx->out_f64a),
+            P<double>(ctx->out_f64b), P<unsigned char>(ctx->out_u8));
+        LAUNCH_CHECK();
+    }
+    int r;
+    if ((r = download(ctx, surv_off, ctx->off_a.p, (size_t)b.n_aln + 1))) return r;
+    if ((r = download(ctx, surv_idx, ctx->out_i32.p, tot))) return r;
+    if ((r = download(ctx, surv_p, ctx->out_f64a.p, tot))) return r;
+    if ((r = download(ctx, surv_pq, ctx->out_f64b.p, tot))) return r;
+    if ((r = download(ctx, surv_keep, ctx->out_u8.p, tot))) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int o2a_fetch_chains(o2a_ctx* ctx, int64_t* chain_off, int32_t* chain_idx, double* chain_pq)
+{
+    NEED_RESULT();
+    const o2a_batch& b = ctx->b;
+    const size_t tot = (size_t)ctx->counts.n_chain_hsps;
+    ENS(off_b, (b.n_aln + 1) * 8);
+    ENS(out_i32, tot * 4); ENS(out_f64a, tot * 8);
+    k_scan_offsets<<<1, 1024, 0, ctx->stream>>>(b.n_aln, P<int>(ctx->chain_len), P<long long>(ctx->off_b));
+    LAUNCH_CHECK();
+    if (b.n_aln > 0 && tot > 0) {
+        k_gather_chain<<<grid_for(ctx, b.n_aln, 16), 64, 0, ctx->stream>>>(
+            b.n_aln, (const long long*)b.hsp_off, P<long long>(ctx->off_b), P<int>(ctx->chain_slot), P<int>(ctx->surv_idx),
+            P<double>(ctx->surv_pq), P<int>(ctx->out_i32), P<double>(ctx->out_f64a));
+        LAUNCH_CHECK();
+    }
+    int r;
+    if ((r = download(ctx, chain_off, ctx->off_b.p, (size_t)b.n_aln + 1))) return r;
+    if ((r = download(ctx, chain_idx, ctx->out_i32.p, tot))) return r;
+    if ((r = download(ctx, chain_pq, ctx->out_f64a.p, tot))) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// operator-level seams
+// --------------------------------------------------------------------------------------------
+extern "C" int o2a_fitter_eval(o2a_ctx* ctx, int32_t fitter, const int32_t* bg, int64_t n_bg, double kde_factor,
+                               const double* x, int64_t n_x, double* sf_out, const double* q, int64_t n_q,
+                               double* isf_out, int32_t* status)
+{
+    if (!ctx) return O2A_EINVAL;
+    if (!bg || n_bg < 2 || fitter < 0 || fitter > 2) { ctx->err = "bad fitter arguments"; return O2A_EINVAL; }
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_result = false;
+    long long off[2] = {0, n_bg};
+    long long zero2[2] = {0, 0};
+    o2a_batch& b = ctx->b;
+    b = o2a_batch{};
+    b.n_lnc = 1; b.n_bg = n_bg; b.max_lnc_bg = n_bg; b.mem = O2A_MEM_DEVICE;
+    int r;
+    if ((r = upload(ctx, ctx->in_bg_off, (const int64_t*)off, 2, &b.bg_off))) return r;
+    if ((r = upload(ctx, ctx->in_aln_off, (const int64_t*)zero2, 2, &b.aln_off))) return r;
+    if ((r = upload(ctx, ctx->in_bg, bg, (size_t)n_bg, &b.bg))) return r;
+    if ((r = upload(ctx, ctx->in_kde, &kde_factor, 1, &b.kde_factor))) return r;
+    ctx->prm = o2a_params{};
+    ctx->prm.fitter = fitter;
+    int st = 0;
+    const int nq_eff = n_q > 0 ? (int)n_q : 1;
+    for (int k = 0; k < nq_eff; ++k) {
+        ctx->prm.alpha = n_q > 0 ? q[k] : 0.5;
+        if ((r = run_fit(ctx))) return r;
+        double t; int s;
+        CU(cudaMemcpyAsync(&t, ctx->thr.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&s, ctx->status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (n_q > 0 && isf_out) isf_out[k] = t;
+        if (s) st = s;
+    }
+    if (status) *status = st;
+    if (st) { ctx->err = "background fit failed (status " + std::to_string(st) + ")"; return O2A_EINVAL; }
+    if (n_x > 0 && sf_out) {
+        ENS(out_f64a, (size_t)n_x * 8); ENS(out_f64b, (size_t)n_x * 8);
+        CU(cudaMemcpyAsync(ctx->out_f64a.p, x, (size_t)n_x * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_sf_eval<<<(unsigned)((n_x + 127) / 128), 128, 0, ctx->stream>>>(
+            fitter, P<double>(ctx->out_f64a), n_x, P<LncFit>(ctx->fits), P<int>(ctx->tbl_k), P<double>(ctx->tbl_cum),
+            P<int>(ctx->uv_val), P<int>(ctx->uv_cnt), P<int>(ctx->uv_n), kde_factor, (double)n_bg, P<double>(ctx->out_f64b));
+        LAUNCH_CHECK();
+        CU(cudaMemcpyAsync(sf_out, ctx->out_f64b.p, (size_t)n_x * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, const int32_t* qend, const int32_t* sstart,
+                              const int32_t* send, const double* score, int64_t qlen, int64_t slen, int32_t gapopen,
+                              int32_t gapextend, int32_t* chain_idx, int64_t* chain_len, int32_t* orient,
+                              double* chain_score, double* orient_scores, int32_t* status)
+{
+    if (!ctx) return O2A_EINVAL;
+    if (n < 0 || n > 0x7fffffff) { ctx->err = "bad n"; return O2A_EINVAL; }
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_result = false;
+    long long loff[2] = {0, 1}, hoff[2] = {0, n};
+    o2a_batch& b = ctx->b;
+    b = o2a_batch{};
+    b.n_lnc = 1; b.n_aln = 1; b.n_hsp = n; b.max_aln_hsps = n; b.mem = O2A_MEM_DEVICE;
+    int r;
+    if ((r = upload(ctx, ctx->in_aln_off, (const int64_t*)loff, 2, &b.aln_off))) return r;
+    if ((r = upload(ctx, ctx->in_hsp_off, (const int64_t*)hoff, 2, &b.hsp_off))) return r;
+    if ((r = upload(ctx, ctx->in_qlen, &qlen, 1, &b.qlen))) return r;
+    if ((r = upload(ctx, ctx->in_slen, &slen, 1, &b.slen))) return r;
+    if ((r = upload(ctx, ctx->in_qs, qstart, (size_t)n, &b.qstart))) return r;
+    if ((r = upload(ctx, ctx->in_qe, qend, (size_t)n, &b.qend))) return r;
+    if ((r = upload(ctx, ctx->in_ss, sstart, (size_t)n, &b.sstart))) return r;
+    if ((r = upload(ctx, ctx->in_se, send, (size_t)n, &b.send))) return r;
+    if ((r = upload(ctx, ctx->in_score, score, (size_t)n, &b.score))) return r;
+    ctx->prm = o2a_params{};
+    ctx->prm.gapopen = gapopen; ctx->prm.gapextend = gapextend;
+    ENS(aln_lnc, 4); ENS(status, 4); ENS(n_surv, 4); ENS(n_keep, 4);
+    ENS(surv_idx, (size_t)n * 4); ENS(surv_keep, (size_t)n); ENS(surv_pq, (size_t)n * 8);
+    ENS(big_list, 2 * sizeof(int)); ENS(big_count, 2 * sizeof(int));
+    int ni = (int)n;
+    CU(cudaMemsetAsync(ctx->aln_lnc.p, 0, 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->status.p, 0, 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->big_count.p, 0, 8, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->n_surv.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->n_keep.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+        k_iota_keep<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ni, P<int>(ctx->surv_idx), P<unsigned char>(ctx->surv_keep));
+        LAUNCH_CHECK();
+    }
+    bool timing = ctx->timing;
+    ctx->timing = false;
+    r = run_chain(ctx);
+    ctx->timing = timing;
+    if (r) return r;
+    int len = 0, st = 0; unsigned char orr = 1; double cs = 0, os2[2] = {0, 0};
+    CU(cudaMemcpyAsync(&len, ctx->chain_len.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&st, ctx->status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&orr, ctx->chain_orient.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&cs, ctx->chain_score.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(os2, ctx->orient_scores.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (len > 0 && chain_idx) {
+        // chain_slot holds survivor-slot positions == HSP positions here (surv_idx is the identity)
+        CU(cudaMemcpyAsync(chain_idx, ctx->chain_slot.p, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (chain_len) *chain_len = len;
+    if (orient) *orient = orr;
+    if (chain_score) *chain_score = cs;
+    if (orient_scores) { orient_scores[0] = os2[0]; orient_scores[1] = os2[1]; }
+    if (status) *status = st;
+    return 0;
+}

@@ -1,0 +1,397 @@
+// o2a_chain.cuh — K6: dynamic-programming chaining of the retained HSPs of one alignment.
+//
+// Replaces Alignment.best_chain and everything below it (alignment.py:863-927, 982-1046):
+//   _split_orientations   stable sort by (orientation, qstart, sstart)              :863-873
+//   _build_hsp_graph      begin/end sentinels, O(n^2) precede/distance, prune loop  :875-927
+//   _find_best_chain      relax in list order, strict '>', backtrack from end       :982-1013
+//   best_chain            direct wins only if strictly greater                      :1032-1046
+// The O(n^2) graph build is replaced by the equivalent windowed rule (chaining
+// spec): with f(i) = first j > i that i precedes, vertex i keeps exactly the edges i -> j with
+// precede(i, j) and f(i) <= j < f(f(i)). Vertices are pushed in ascending order; all threads of
+// the CTA relax the window of vertex i in parallel (distinct targets, no conflicts), which keeps
+// the reference's "first strict improvement wins" tie-break. Path costs mix genomic coordinates
+// (begin vertex at 0) and possibly fractional scores -> fp64 with the reference's operation order
+// (total + ((G + E*(qd+sd)) - score)), no FMA.
+#pragma once
+#include "o2a_device.cuh"
+
+namespace o2a {
+
+constexpr int CHAIN_THREADS = 128;
+constexpr int CHAIN_SMALL_MAX = 192;      // retained HSPs per alignment handled in shared memory
+constexpr int CHAINBIG_THREADS = 512;
+
+// per-orientation vertex storage: n HSPs, vertex v in 1..n is HSP slot v-1; v=0 begin, v=n+1 end
+struct ChainMem {
+    int* qs; int* qe; int* ss; int* se;   // [n]
+    double* sc;                           // [n]
+    int* id;                              // [n] survivor-slot position of the HSP (chain output)
+    double* total;                        // [n+2]
+    int* prev;                            // [n+2]
+    int* f;                               // [n+2]
+};
+
+struct ChainGeom {
+    int n; bool direct; long long qlen, slen; double G, E;
+};
+
+__device__ __forceinline__ long long v_qs(const ChainMem& M, const ChainGeom& g, int v)
+{ return v == 0 ? 0ll : (v == g.n + 1 ? g.qlen : (long long)M.qs[v - 1]); }
+__device__ __forceinline__ long long v_qe(const ChainMem& M, const ChainGeom& g, int v)
+{ return v == 0 ? 0ll : (v == g.n + 1 ? g.qlen : (long long)M.qe[v - 1]); }
+__device__ __forceinline__ long long v_ss(const ChainMem& M, const ChainGeom& g, int v)
+{   // begin: direct (0,0,0,0) / reverse (0,0,slen,slen); end: direct (..,slen,slen) / reverse (..,0,0)
+    if (v == 0) return g.direct ? 0ll : g.slen;
+    if (v == g.n + 1) return g.direct ? g.slen : 0ll;
+    return (long long)M.ss[v - 1];
+}
+__device__ __forceinline__ long long v_se(const ChainMem& M, const ChainGeom& g, int v)
+{
+    if (v == 0) return g.direct ? 0ll : g.slen;
+    if (v == g.n + 1) return g.direct ? g.slen : 0ll;
+    return (long long)M.se[v - 1];
+}
+
+// HSP.precede (alignment.py:137-168). Quirk kept: both sentinels have orientation None, so a
+// begin->end test uses the `else` (reverse) rule even in the direct graph.
+__device__ __forceinline__ bool v_prec(const ChainMem& M, const ChainGeom& g, int i, int j)
+{
+    bool dir_rule = g.direct && !(i == 0 && j == g.n + 1);
+    bool qp = v_qe(M, g, i) < v_qs(M, g, j);
+    bool sp = dir_rule ? (v_se(M, g, i) < v_ss(M, g, j)) : (v_se(M, g, i) > v_ss(M, g, j));
+    return qp && sp;
+}
+
+// HSP.distance for i preceding j (alignment.py:170-217): gapopen + gapextend*(qdist+sdist) - score_j
+__device__ __forceinline__ double v_weight(const ChainMem& M, const ChainGeom& g, int i, int j)
+{
+    long long qd = v_qs(M, g, j) - v_qe(M, g, i);
+    long long sd = g.direct ? (v_ss(M, g, j) - v_se(M, g, i)) : (v_se(M, g, i) - v_ss(M, g, j));
+    double pen = __dadd_rn(g.G, __dmul_rn(g.E, (double)(qd + sd)));
+    double sj = (j == 0 || j == g.n + 1) ? 0.0 : M.sc[j - 1];
+    return __dsub_rn(pen, sj);
+}
+
+// Best chain of one orientation (HSP slots already sorted by (qstart, sstart, list order)).
+// All threads of the CTA call this. Returns score = -total[end]; chain (survivor-slot positions, in
+// chain order) is written to chain_out by thread 0, its length to *s_len (shared).
+__device__ double chain_orientation(const ChainMem& M, const ChainGeom& g, int* chain_out, int* s_len)
+{
+    const int n = g.n, N = n + 2;
+    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    // ---- f(i): first successor -------------------------------------------------------------
+    for (int i = w; i < N; i += nw) {            // one warp per vertex, lanes scan 32 candidates
+        int fi = N;
+        if (i < N - 1) {
+            long long qe_i = v_qe(M, g, i);
+            // first HSP vertex j > i with qs_j > qe_i (HSP vertices are sorted by qs)
+            int lo = i + 1, hi = n + 1;         // search in [i+1, n+1)
+            while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)M.qs[mid - 1] > qe_i) hi = mid; else lo = mid + 1; }
+            int found = -1;
+            for (int j0 = lo; j0 <= n && found < 0; j0 += 32) {
+                int j = j0 + lane;
+                bool ok = (j <= n) && v_prec(M, g, i, j);
+                unsigned b = __ballot_sync(FULL_MASK, ok);
+                if (b) found = j0 + __ffs(b) - 1;
+            }
+            if (found >= 0) fi = found;
+            else if (v_prec(M, g, i, N - 1)) fi = N - 1;
+        }
+        if (lane == 0) M.f[i] = fi;
+    }
+    for (int v = threadIdx.x; v < N; v += blockDim.x) {
+        M.total[v] = v == 0 ? 0.0 : __longlong_as_double(0x7ff0000000000000ll);
+        M.prev[v] = -1;
+    }
+    __syncthreads();
+    // ---- push DP in list order ----------------------------------------------------------------
+    for (int i = 0; i < N - 1; ++i) {
+        const double ti = M.total[i];
+        const int fi = M.f[i];
+        if (fi < N && ti < __longlong_as_double(0x7ff0000000000000ll)) {   // uniform across the CTA
+            const int gi = M.f[fi] < N ? M.f[fi] : N;      // f(f(i)); f(N-1) = N
+            for (int j = fi + threadIdx.x; j < gi; j += blockDim.x) {
+                if (v_prec(M, g, i, j)) {
+                    double ns = __dadd_rn(ti, v_weight(M, g, i, j));       // HSPVertex._relax
+                    if (M.total[j] > ns) { M.total[j] = ns; M.prev[j] = i; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const double score = -M.total[N - 1];
+    // ---- backtrack (alignment.py:1007-1013) -----------------------------------------------------
+    if (threadIdx.x == 0) {
+        int len = 0, cur = N - 1;
+        while (M.prev[cur] != -1) { cur = M.prev[cur]; if (cur != 0) ++len; }
+        // second walk fills chain_out back to front
+        int pos = len; cur = N - 1;
+        while (M.prev[cur] != -1) { cur = M.prev[cur]; if (cur != 0) chain_out[--pos] = M.id[cur - 1]; }
+        *s_len = len;
+    }
+    __syncthreads();
+    return score;
+}
+
+struct ChainArgs {
+    long long n_aln;
+    const long long* hsp_off;
+    const int* aln_lnc;
+    const long long* qlen; const long long* slen;
+    const int* qstart; const int* qend; const int* sstart; const int* send; const double* score;
+    const int* n_surv; const int* n_keep;
+    const int* surv_idx; const unsigned char* surv_keep;
+    int gapopen, gapextend;
+    int best_value;
+    // outputs
+    int* chain_len; unsigned char* chain_orient; double* chain_score; double* orient_scores;
+    int* chain_slot;           // slot layout: survivor-slot positions of the chain HSPs, chain order
+    double* best_key;          // per alignment: get_best_orthologs key of the chosen chain
+    int* lnc_status;
+    int* big_list; int* big_count;
+};
+
+// key of get_best_orthologs on the QUERY bed12 line (pipeline.py:981-987) for the chosen chain
+__device__ double best_key_of_chain(const ChainArgs& A, long long h0, const int* slots, int len, int which)
+{
+    long long blen = 0; int lo = INT32_MAX, hi = INT32_MIN; double wsum = 0.0;
+    for (int c = 0; c < len; ++c) {
+        long long h = h0 + A.surv_idx[h0 + slots[c]];
+        int qs = A.qstart[h], qe = A.qend[h];
+        int d = qe - qs; blen += d < 0 ? -d : d;
+        lo = min(lo, min(qs, qe)); hi = max(hi, max(qs, qe));
+        wsum = __dadd_rn(wsum, A.score[h]);           // Python sum(): 0 + s0 + s1 + ...
+    }
+    if (which == 0) return (double)blen;
+    if (which == 1) return (double)((long long)hi - (long long)lo);
+    if (which == 2) return (double)len;
+    return wsum;
+}
+
+// Shared-memory path: alignments with at most CHAIN_SMALL_MAX retained HSPs (the common case:
+// ~10-20). Larger ones are queued for k_chain_big.
+__global__ void __launch_bounds__(CHAIN_THREADS)
+k_chain_small(ChainArgs A)
+{
+    constexpr int C = CHAIN_SMALL_MAX;
+    __shared__ int s_qs[C], s_qe[C], s_ss[C], s_se[C], s_id[C];
+    __shared__ double s_sc[C];
+    __shared__ int t_qs[C], t_qe[C], t_ss[C], t_se[C], t_id[C];     // unsorted gather
+    __shared__ double t_sc[C];
+    __shared__ unsigned char t_dir[C];
+    __shared__ double s_total[C + 2];
+    __shared__ int s_prev[C + 2], s_f[C + 2];
+    __shared__ int s_chain[2][C];
+    __shared__ int s_len[2];
+    __shared__ int s_scan[CHAIN_THREADS / 32 + 2];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+
+    for (long long a = blockIdx.x; a < A.n_aln; a += gridDim.x) {
+        const long long h0 = A.hsp_off[a];
+        const int ns = A.n_surv[a];
+        const int r = A.n_keep[a];
+        const int l = A.aln_lnc[a];
+        if (r > C) {
+            if (tid == 0) { int slot = atomicAdd(A.big_count, 1); A.big_list[slot] = (int)a; }
+            continue;
+        }
+        if (r == 0 || A.lnc_status[l] == 2 || A.lnc_status[l] == 3) {
+            if (tid == 0) {
+                A.chain_len[a] = 0; A.chain_orient[a] = 1;
+                A.chain_score[a] = __longlong_as_double(0xfff0000000000000ll);
+                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = __longlong_as_double(0xfff0000000000000ll);
+                A.best_key[a] = 0.0;
+            }
+            continue;
+        }
+        if (tid == 0) s_bad = 0;
+        // ---- gather the retained HSPs in list order ------------------------------------------
+        int got = 0;
+        for (int k0 = 0; k0 < ns; k0 += CHAIN_THREADS) {
+            int k = k0 + tid;
+            bool keep = (k < ns) && A.surv_keep[h0 + k];
+            int tot;
+            int pos = cta_exclusive_scan(keep ? 1 : 0, s_scan, &tot);
+            if (keep) {
+                long long h = h0 + A.surv_idx[h0 + k];
+                int p = got + pos;
+                int qs = A.qstart[h], qe = A.qend[h], ss = A.sstart[h], se = A.send[h];
+                t_qs[p] = qs; t_qe[p] = qe; t_ss[p] = ss; t_se[p] = se; t_sc[p] = A.score[h]; t_id[p] = k;
+                t_dir[p] = (se - ss > 0) ? 1 : 0;                  // alignment.py:107-110
+                if (!(qe - qs > 0)) s_bad = 1;                      // orientation None
+            }
+            got += tot;
+            __syncthreads();
+        }
+        if (s_bad) {                                   // reference raises in _split_orientations
+            if (tid == 0) {
+                atomicMax(&A.lnc_status[l], 1);
+                A.chain_len[a] = 0; A.chain_orient[a] = 1;
+                A.chain_score[a] = __longlong_as_double(0xfff0000000000000ll);
+                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = __longlong_as_double(0xfff0000000000000ll);
+                A.best_key[a] = 0.0;
+            }
+            __syncthreads();
+            continue;
+        }
+        double sco[2];
+        for (int o = 0; o < 2; ++o) {                  // o = 0 direct, 1 reverse
+            // stable rank of each HSP of this orientation by (qstart, sstart, list order)
+            int n_o = 0;
+            for (int p = 0; p < r; ++p) n_o += (t_dir[p] == (o == 0 ? 1 : 0));
+            for (int p = tid; p < r; p += CHAIN_THREADS) {
+                if (t_dir[p] != (o == 0 ? 1 : 0)) continue;
+                int rank = 0;
+                for (int q = 0; q < r; ++q) {
+                    if (t_dir[q] != t_dir[p]) continue;
+                    bool less = (t_qs[q] < t_qs[p]) || (t_qs[q] == t_qs[p] && (t_ss[q] < t_ss[p] || (t_ss[q] == t_ss[p] && q < p)));
+                    rank += less;
+                }
+                s_qs[rank] = t_qs[p]; s_qe[rank] = t_qe[p]; s_ss[rank] = t_ss[p]; s_se[rank] = t_se[p];
+                s_sc[rank] = t_sc[p]; s_id[rank] = t_id[p];
+            }
+            __syncthreads();
+            if (n_o == 0) {
+                sco[o] = __longlong_as_double(0xfff0000000000000ll);
+                if (tid == 0) s_len[o] = 0;
+                __syncthreads();
+                continue;
+            }
+            ChainMem M{s_qs, s_qe, s_ss, s_se, s_sc, s_id, s_total, s_prev, s_f};
+            ChainGeom g{n_o, o == 0, A.qlen[a], A.slen[a], (double)A.gapopen, (double)A.gapextend};
+            sco[o] = chain_orientation(M, g, s_chain[o], &s_len[o]);
+            __syncthreads();
+        }
+        const int pick = (sco[0] > sco[1]) ? 0 : 1;    // alignment.py:1043-1046
+        const int len = s_len[pick];
+        for (int c = tid; c < len; c += CHAIN_THREADS) A.chain_slot[h0 + c] = s_chain[pick][c];
+        __syncthreads();
+        if (tid == 0) {
+            A.chain_len[a] = len; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = sco[pick];
+            A.orient_scores[2 * a] = sco[0]; A.orient_scores[2 * a + 1] = sco[1];
+            A.best_key[a] = len ? best_key_of_chain(A, h0, s_chain[pick], len, A.best_value) : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+// Global-scratch path for dense alignments (BASELINE config 4: ~25k retained HSPs per orientation).
+// Per-CTA scratch of capacity `cap` HSPs (cap = max alignment size).
+struct ChainBigScratch {
+    unsigned long long* k0; unsigned long long* k1; unsigned int* v0; unsigned int* v1;   // sort
+    int* qs; int* qe; int* ss; int* se; double* sc; int* id;                              // sorted HSPs
+    double* total; int* prev; int* f;                                                     // cap + 2
+    int* chain;                                                                           // 2*cap
+    long long cap;
+};
+
+__global__ void __launch_bounds__(CHAINBIG_THREADS)
+k_chain_big(ChainArgs A, ChainBigScratch S)
+{
+    __shared__ int s_sort[32 + (CHAINBIG_THREADS / 32) * 16 + 1];
+    __shared__ int s_scan[CHAINBIG_THREADS / 32 + 2];
+    __shared__ int s_len[2];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    const long long so = (long long)blockIdx.x * S.cap, so2 = (long long)blockIdx.x * (S.cap + 2);
+    unsigned long long *k0 = S.k0 + so, *k1 = S.k1 + so;
+    unsigned int *v0 = S.v0 + so, *v1 = S.v1 + so;
+    ChainMem M{S.qs + so, S.qe + so, S.ss + so, S.se + so, S.sc + so, S.id + so, S.total + so2, S.prev + so2, S.f + so2};
+    int* chain_buf = S.chain + 2 * so;
+    const int nbig = *A.big_count;
+    for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const long long a = A.big_list[b];
+        const long long h0 = A.hsp_off[a];
+        const int ns = A.n_surv[a];
+        const int l = A.aln_lnc[a];
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+        double sco[2];
+        for (int o = 0; o < 2; ++o) {
+            // gather survivor slots of this orientation, in list order, as (key, slot) pairs
+            int n_o = 0;
+            for (int k0i = 0; k0i < ns; k0i += CHAINBIG_THREADS) {
+                int k = k0i + tid;
+                bool take = false; unsigned long long key = 0;
+                if (k < ns && A.surv_keep[h0 + k]) {
+                    long long h = h0 + A.surv_idx[h0 + k];
+                    int qs = A.qstart[h], qe = A.qend[h], ss = A.sstart[h], se = A.send[h];
+                    if (!(qe - qs > 0)) s_bad = 1;
+                    bool dir = (se - ss > 0);
+                    take = (dir == (o == 0));
+                    key = ((unsigned long long)((unsigned)qs ^ 0x80000000u) << 32) | (unsigned long long)((unsigned)ss ^ 0x80000000u);
+                }
+                int tot;
+                int pos = cta_exclusive_scan(take ? 1 : 0, s_scan, &tot);
+                if (take) { k0[n_o + pos] = key; v0[n_o + pos] = (unsigned)k; }
+                n_o += tot;
+                __syncthreads();
+            }
+            if (s_bad) break;
+            if (n_o == 0) {
+                sco[o] = __longlong_as_double(0xfff0000000000000ll);
+                if (tid == 0) s_len[o] = 0;
+                __syncthreads();
+                continue;
+            }
+            int where = cta_radix_sort(k0, v0, k1, v1, n_o, s_sort);
+            __syncthreads();
+            const unsigned int* vs = where ? v1 : v0;
+            for (int p = tid; p < n_o; p += CHAINBIG_THREADS) {
+                int k = (int)vs[p];
+                long long h = h0 + A.surv_idx[h0 + k];
+                M.qs[p] = A.qstart[h]; M.qe[p] = A.qend[h]; M.ss[p] = A.sstart[h]; M.se[p] = A.send[h];
+                M.sc[p] = A.score[h]; M.id[p] = k;
+            }
+            __syncthreads();
+            ChainGeom g{n_o, o == 0, A.qlen[a], A.slen[a], (double)A.gapopen, (double)A.gapextend};
+            sco[o] = chain_orientation(M, g, chain_buf + (long long)o * S.cap, &s_len[o]);
+            __syncthreads();
+        }
+        if (s_bad) {
+            if (tid == 0) {
+                atomicMax(&A.lnc_status[l], 1);
+                A.chain_len[a] = 0; A.chain_orient[a] = 1;
+                A.chain_score[a] = __longlong_as_double(0xfff0000000000000ll);
+                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = __longlong_as_double(0xfff0000000000000ll);
+                A.best_key[a] = 0.0;
+            }
+            __syncthreads();
+            continue;
+        }
+        const int pick = (sco[0] > sco[1]) ? 0 : 1;
+        const int len = s_len[pick];
+        const int* ch = chain_buf + (long long)pick * S.cap;
+        for (int c = tid; c < len; c += CHAINBIG_THREADS) A.chain_slot[h0 + c] = ch[c];
+        __syncthreads();
+        if (tid == 0) {
+            A.chain_len[a] = len; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = sco[pick];
+            A.orient_scores[2 * a] = sco[0]; A.orient_scores[2 * a + 1] = sco[1];
+            A.best_key[a] = len ? best_key_of_chain(A, h0, ch, len, A.best_value) : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+// K7: get_best_orthologs selection per lncRNA (pipeline.py:1004-1016): first extremal key wins.
+// Also clears the chains of lncRNAs the reference would have aborted (status != 0).
+__global__ void k_best(long long n_lnc, const long long* __restrict__ aln_off, const int* __restrict__ lnc_status,
+                       int* __restrict__ chain_len, double* __restrict__ chain_score,
+                       const double* __restrict__ best_key, int best_fn, long long* __restrict__ best_aln)
+{
+    long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lnc) return;
+    long long best = -1; double bk = 0.0;
+    const bool failed = lnc_status[l] != 0;
+    for (long long a = aln_off[l]; a < aln_off[l + 1]; ++a) {
+        if (failed) { chain_len[a] = 0; chain_score[a] = __longlong_as_double(0xfff0000000000000ll); continue; }
+        if (chain_len[a] > 0) {
+            double k = best_key[a];
+            if (best < 0 || (best_fn == 0 ? k > bk : k < bk)) { best = a; bk = k; }
+        }
+    }
+    best_aln[l] = best;
+}
+
+}  // namespace o2a

@@ -1,0 +1,188 @@
+"""Host-side driver of the CUDA library: one `Engine` per GPU (one process per GPU under torchrun).
+
+`Engine.build_batch(batch, ...)` replaces the process-pool fan-out of `_build` over lncRNAs
+(`pipeline.py:846-860`): the whole columnar batch goes through the C-ABI in one call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .columnar import ColumnarBatch
+from .result import BEST_FUNCTIONS, BEST_VALUES, FITTERS, BatchResult
+
+
+class O2AError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class DeviceBatch:
+    """A ColumnarBatch resident in HBM (torch tensors own the memory; the library gets raw pointers)."""
+
+    def __init__(self, batch: ColumnarBatch, device):
+        import torch
+        self.n_lnc, self.n_aln, self.n_hsp, self.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
+        self.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
+        self.max_lnc_bg = int(np.diff(batch.bg_off).max()) if batch.n_lnc else 0
+        self.t = {}
+        for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
+            self.t[k] = torch.from_numpy(getattr(batch, k)).to(device, non_blocking=False)
+        self.t["kde_factor"] = torch.from_numpy(batch.ensure_kde_factor()).to(device)
+        self.nbytes = sum(v.numel() * v.element_size() for v in self.t.values())
+
+    def struct(self, with_kde):
+        s = _lib.O2ABatch()
+        s.n_lnc, s.n_aln, s.n_hsp, s.n_bg = self.n_lnc, self.n_aln, self.n_hsp, self.n_bg
+        for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
+            setattr(s, k, self.t[k].data_ptr())
+        s.kde_factor = self.t["kde_factor"].data_ptr() if with_kde else None
+        s.mem = 1
+        s.max_aln_hsps, s.max_lnc_bg = self.max_aln_hsps, self.max_lnc_bg
+        return s
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.o2a_create(C.byref(h), self.device)
+        if rc != 0:
+            raise O2AError(f"o2a_create(device={device}) failed ({rc}): a CUDA device is required, "
+                           "there is no CPU fallback")
+        self.h = h
+        self.counts = None
+        self._geom = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.o2a_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise O2AError(f"{what} failed ({rc}): {self.lib.o2a_last_error(self.h).decode()}")
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.o2a_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "o2a_set_stream")
+
+    def set_timing(self, on=True):
+        self._check(self.lib.o2a_set_timing(self.h, 1 if on else 0), "o2a_set_timing")
+
+    def stage_ms(self):
+        ms = (C.c_float * 6)()
+        self._check(self.lib.o2a_get_stage_ms(self.h, ms), "o2a_get_stage_ms")
+        return dict(zip(_lib.STAGES, [float(x) for x in ms]))
+
+    def launch_count(self):
+        return int(self.lib.o2a_launch_count(self.h))
+
+    @staticmethod
+    def params(fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
+               best_value="block_length", best_function="max"):
+        p = _lib.O2AParams()
+        p.fitter, p.fdr, p.alpha = FITTERS[fitter], int(bool(fdr)), float(alpha)
+        p.gapopen, p.gapextend = int(gapopen), int(gapextend)
+        p.best_value, p.best_function = BEST_VALUES[best_value], BEST_FUNCTIONS[best_function]
+        return p
+
+    @staticmethod
+    def host_struct(batch: ColumnarBatch, with_kde):
+        s = _lib.O2ABatch()
+        s.n_lnc, s.n_aln, s.n_hsp, s.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
+        for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
+            a = getattr(batch, k)
+            assert a.flags["C_CONTIGUOUS"]
+            setattr(s, k, a.ctypes.data)
+        s.kde_factor = batch.ensure_kde_factor().ctypes.data if with_kde else None
+        s.mem = 0
+        s.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
+        s.max_lnc_bg = int(np.diff(batch.bg_off).max()) if batch.n_lnc else 0
+        return s
+
+    def run(self, batch_struct, params):
+        """Raw call: `o2a_build_batch` on a prepared struct. Returns the counts."""
+        counts = _lib.O2ACounts()
+        self._check(self.lib.o2a_build_batch(self.h, C.byref(batch_struct), C.byref(params), C.byref(counts)),
+                    "o2a_build_batch")
+        self.counts = counts
+        self._geom = (batch_struct.n_lnc, batch_struct.n_aln)
+        return counts
+
+    def fetch_chains(self):
+        n_lnc, n_aln = self._geom
+        chain_off = np.zeros(n_aln + 1, dtype=np.int64)
+        n = int(self.counts.n_chain_hsps)
+        chain_idx = np.zeros(n, dtype=np.int32)
+        chain_pq = np.zeros(n, dtype=np.float64)
+        self._check(self.lib.o2a_fetch_chains(self.h, _p(chain_off), _p(chain_idx), _p(chain_pq)), "o2a_fetch_chains")
+        return chain_off, chain_idx, chain_pq
+
+    def fetch(self, survivors=True) -> BatchResult:
+        n_lnc, n_aln = self._geom
+        thr = np.zeros(n_lnc); status = np.zeros(n_lnc, dtype=np.int32); best = np.zeros(n_lnc, dtype=np.int64)
+        self._check(self.lib.o2a_fetch_lnc(self.h, _p(thr), _p(status), _p(best)), "o2a_fetch_lnc")
+        n_surv = np.zeros(n_aln, dtype=np.int32); n_keep = np.zeros(n_aln, dtype=np.int32)
+        chain_len = np.zeros(n_aln, dtype=np.int32); chain_orient = np.zeros(n_aln, dtype=np.uint8)
+        chain_score = np.zeros(n_aln); orient_scores = np.zeros((n_aln, 2))
+        self._check(self.lib.o2a_fetch_aln(self.h, _p(n_surv), _p(n_keep), _p(chain_len), _p(chain_orient),
+                                           _p(chain_score), _p(orient_scores)), "o2a_fetch_aln")
+        ns = int(self.counts.n_survivors) if survivors else 0
+        surv_off = np.zeros(n_aln + 1, dtype=np.int64)
+        surv_idx = np.zeros(ns, dtype=np.int32); surv_p = np.zeros(ns); surv_pq = np.zeros(ns)
+        surv_keep = np.zeros(ns, dtype=np.uint8)
+        if survivors:
+            self._check(self.lib.o2a_fetch_survivors(self.h, _p(surv_off), _p(surv_idx), _p(surv_p), _p(surv_pq),
+                                                     _p(surv_keep)), "o2a_fetch_survivors")
+        chain_off, chain_idx, chain_pq = self.fetch_chains()
+        return BatchResult(thr, status, best, n_surv, n_keep, chain_len, chain_orient, chain_score, orient_scores,
+                           surv_off, surv_idx, surv_p, surv_pq, surv_keep, chain_off, chain_idx, chain_pq)
+
+    def build_batch(self, batch: ColumnarBatch, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
+                    best_value="block_length", best_function="max", survivors=True) -> BatchResult:
+        """Host buffers in, host results out (the e2e boundary)."""
+        p = self.params(fitter, fdr, alpha, gapopen, gapextend, best_value, best_function)
+        s = self.host_struct(batch, with_kde=(fitter == "kde"))
+        self.run(s, p)
+        return self.fetch(survivors=survivors)
+
+    # ---- operator-level seams -------------------------------------------------------------------
+    def fitter_eval(self, fitter, bg, x=None, q=None, kde_factor=1.0):
+        bg = np.ascontiguousarray(bg, dtype=np.int32)
+        x = np.zeros(0) if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        q = np.zeros(0) if q is None else np.ascontiguousarray(q, dtype=np.float64)
+        sf = np.zeros(len(x)); isf = np.zeros(len(q))
+        st = C.c_int32(0)
+        rc = self.lib.o2a_fitter_eval(self.h, FITTERS[fitter], _p(bg), len(bg), float(kde_factor),
+                                      _p(x), len(x), _p(sf), _p(q), len(q), _p(isf), C.byref(st))
+        if rc != 0:
+            raise O2AError(f"o2a_fitter_eval failed ({rc}, status {st.value}): {self.lib.o2a_last_error(self.h).decode()}")
+        return sf, isf
+
+    def best_chain(self, qstart, qend, sstart, send, score, qlen, slen, gapopen=5, gapextend=2):
+        a32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        qstart, qend, sstart, send = a32(qstart), a32(qend), a32(sstart), a32(send)
+        score = np.ascontiguousarray(score, dtype=np.float64)
+        n = len(score)
+        chain = np.zeros(max(n, 1), dtype=np.int32)
+        clen = C.c_int64(0); orient = C.c_int32(0); cs = C.c_double(0); st = C.c_int32(0)
+        s2 = np.zeros(2)
+        self._check(self.lib.o2a_best_chain(self.h, n, _p(qstart), _p(qend), _p(sstart), _p(send), _p(score),
+                                            int(qlen), int(slen), int(gapopen), int(gapextend), _p(chain),
+                                            C.byref(clen), C.byref(orient), C.byref(cs), _p(s2), C.byref(st)),
+                    "o2a_best_chain")
+        if st.value == 1:
+            raise KeyError("HSP with orientation None (alignment.py:865-872)")
+        return chain[:clen.value].copy(), orient.value, cs.value, (float(s2[0]), float(s2[1]))

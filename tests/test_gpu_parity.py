@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against (a) the golden vectors
+recorded from the unmodified reference and (b) the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from conftest import batch_from_lists, load_golden
+from helpers import KDE_THR_ABS, assert_pq_close, compare_results, compare_with_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,exact", [("build_hist_fdr.json", True), ("build_hist_nofdr.json", True),
+                                        ("build_c5_hist_fdr.json", True), ("build_kde_fdr.json", False)])
+def test_golden_build(engine, name, exact):
+    g = load_golden(name)
+    b = batch_from_lists(g["batch"])
+    res = engine.build_batch(b, g["fitting"], g["fdr"], g["alpha"], g["gapopen"], g["gapextend"])
+    assert (res.status == 0).all()
+    compare_with_golden(res, b, g, exact_p=exact, what=name)
+
+
+def test_golden_fitters(engine):
+    from ortho2align_b200.columnar import kde_factor
+    g = load_golden("fitters.json")
+    for case in g["cases"]:
+        bg = np.asarray(case["bg"], dtype=np.int32)
+        sf, isf = engine.fitter_eval("hist", bg, case["x"], case["alphas"])
+        assert sf.tolist() == case["hist_sf"]
+        assert isf.tolist() == case["hist_isf"]
+        if "kde_sf" in case:
+            sf, isf = engine.fitter_eval("kde", bg, case["x"], case["alphas"][:2], kde_factor=kde_factor(len(bg)))
+            assert_pq_close(sf, case["kde_sf"], "kde sf")
+            assert np.allclose(isf, case["kde_isf"], rtol=0, atol=KDE_THR_ABS)
+
+
+def test_golden_chains(engine):
+    g = load_golden("chains.json")
+    for i, c in enumerate(g["cases"]):
+        chain, orient, score, s2 = engine.best_chain(c["qstart"], c["qend"], c["sstart"], c["send"], c["score"],
+                                                     c["qlen"], c["slen"], c["gapopen"], c["gapextend"])
+        assert chain.tolist() == c["chain"], f"case {i}"
+        assert s2 == (c["score_direct"], c["score_reverse"]), f"case {i}"
+        if c["chain"]:
+            assert orient == c["orient"]
+
+
+def test_orientation_none_raises(engine):
+    with pytest.raises(KeyError):
+        engine.best_chain([10, 30], [20, 30], [5, 50], [9, 60], [30.0, 40.0], 100, 100)
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (1, dict()),                                                   # BASELINE config 1 (96 strRNA genes)
+    (2, dict(n_lnc=48)),                                           # config 2 shape, fewer lncRNAs
+    (5, dict(n_lnc=1500)),                                         # ragged: many tiny alignments
+    (2, dict(n_lnc=6, hsps_per_region=7, n_bg=2)),                 # minimum background size
+    (2, dict(n_lnc=3, n_bg=40000, hsps_per_region=300)),           # B > shared-memory bin budget
+])
+@pytest.mark.parametrize("fitter,fdr", [("hist", True), ("hist", False), ("empirical", True)])
+def test_synthetic_vs_oracle(engine, cfg, kw, fitter, fdr):
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    b = synth.workload(cfg, seed=5, **kw)
+    exp = O.build_batch(b, fitter, fdr)
+    got = engine.build_batch(b, fitter, fdr)
+    compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr}")
+    assert engine.counts.n_survivors == int(exp.n_surv.sum())
+    assert engine.counts.n_chains == int((exp.chain_len > 0).sum())
+
+
+def test_kde_vs_oracle(engine):
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    b = synth.workload(2, n_lnc=12, seed=9, hsps_per_region=400, n_bg=3000)
+    exp = O.build_batch(b, "kde", True)
+    got = engine.build_batch(b, "kde", True)
+    compare_results(got, exp, exact_p=False, what="kde")
+
+
+def test_dense_chaining_and_big_rank_vs_oracle(engine):
+    """BASELINE config 4 shape at a size the O(n^2) oracle finishes: every HSP survives (p = 0) and
+    enters the DP -> exercises k_rank_big (radix sort) and k_chain_big (global scratch)."""
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    b = synth.workload(4, n_lnc=6, seed=2, hsps_per_region=3000)
+    for fdr in (True, False):
+        exp = O.build_batch(b, "hist", fdr)
+        got = engine.build_batch(b, "hist", fdr)
+        assert int(exp.n_keep.min()) == 3000
+        compare_results(got, exp, exact_p=True, what=f"dense fdr={fdr}")
+
+
+def test_medium_survivor_sets_vs_oracle(engine):
+    """Survivor counts around the shared-memory limits of the rank (1024) and chain (192) paths."""
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    b = synth.workload(2, n_lnc=8, seed=4, hsps_per_region=6000, n_bg=500)
+    b.score[::3] += 40.0          # a third of the HSPs become clearly significant
+    exp = O.build_batch(b, "hist", True)
+    got = engine.build_batch(b, "hist", True)
+    assert exp.n_surv.max() > 1024 and exp.n_keep.max() > 192
+    compare_results(got, exp, exact_p=True, what="medium")
+
+
+def test_edge_cases(engine):
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    from ortho2align_b200.columnar import ColumnarBatch, concat_batches
+    b = synth.workload(2, n_lnc=5, seed=8, hsps_per_region=50, n_bg=100)
+    # an alignment with zero HSPs, one lncRNA with zero alignments, one HSP with orientation None
+    empty_aln = ColumnarBatch(
+        bg_off=np.array([0, 3], dtype=np.int64), bg=np.array([5, 5, 1], dtype=np.int32),
+        aln_off=np.array([0, 1], dtype=np.int64), hsp_off=np.array([0, 0], dtype=np.int64),
+        qlen=np.array([1], dtype=np.int64), slen=np.array([1], dtype=np.int64),
+        qstart=np.zeros(0, np.int32), qend=np.zeros(0, np.int32), sstart=np.zeros(0, np.int32),
+        send=np.zeros(0, np.int32), score=np.zeros(0, np.float64))
+    no_aln = ColumnarBatch(
+        bg_off=np.array([0, 2], dtype=np.int64), bg=np.array([1, 0], dtype=np.int32),
+        aln_off=np.array([0, 0], dtype=np.int64), hsp_off=np.array([0], dtype=np.int64),
+        qlen=np.zeros(0, np.int64), slen=np.zeros(0, np.int64),
+        qstart=np.zeros(0, np.int32), qend=np.zeros(0, np.int32), sstart=np.zeros(0, np.int32),
+        send=np.zeros(0, np.int32), score=np.zeros(0, np.float64))
+    bad = b.slice_lnc(0, 1)
+    bad.score[:] = 500.0
+    bad.qend[3] = bad.qstart[3]
+    full = concat_batches([b, empty_aln, no_aln, bad, b.slice_lnc(2, 4)])
+    exp = O.build_batch(full, "hist", True)
+    got = engine.build_batch(full, "hist", True)
+    assert exp.status.tolist().count(1) == 1
+    compare_results(got, exp, exact_p=True, what="edge")
+    assert engine.counts.n_failed_lnc == 1
+    # empty batch
+    empty = concat_batches([])
+    got = engine.build_batch(empty, "hist", True)
+    assert got.thr.shape == (0,) and got.chain_idx.shape == (0,)
+
+
+def test_device_resident_inputs_match_host_inputs(engine):
+    import torch
+    from ortho2align_b200 import synth
+    from ortho2align_b200.engine import DeviceBatch
+    b = synth.workload(2, n_lnc=16, seed=12)
+    host = engine.build_batch(b, "hist", True)
+    db = DeviceBatch(b, torch.device("cuda:0"))
+    torch.cuda.synchronize()
+    engine.run(db.struct(with_kde=False), engine.params("hist", True))
+    dev = engine.fetch()
+    compare_results(dev, host, exact_p=True, what="device-vs-host")
+
+
+def test_round_trip_properties_at_scale(engine):
+    """Size-independent properties on a batch too large for the oracle to be worth running."""
+    from ortho2align_b200 import synth
+    b = synth.workload(2, n_lnc=600, seed=33)
+    r = engine.build_batch(b, "hist", True)
+    assert r.surv_off[-1] == r.n_surv.sum() == engine.counts.n_survivors
+    # survivors are exactly the HSPs with score > thr of their lncRNA, in order
+    lnc_of_aln = np.repeat(np.arange(b.n_lnc), np.diff(b.aln_off))
+    aln_of_hsp = np.repeat(np.arange(b.n_aln), np.diff(b.hsp_off))
+    mask = b.score > r.thr[lnc_of_aln][aln_of_hsp]
+    assert mask.sum() == r.surv_off[-1]
+    aln_of_surv = np.repeat(np.arange(b.n_aln), r.n_surv)
+    gidx = b.hsp_off[:-1][aln_of_surv] + r.surv_idx
+    assert np.array_equal(np.nonzero(mask)[0], gidx)
+    # q = m*p/rank with rank a permutation of 1..n per alignment; keep <=> q <= alpha
+    m = np.diff(b.hsp_off)[aln_of_surv].astype(float)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rank = np.where(r.surv_pq > 0, m * r.surv_p / r.surv_pq, 0)
+    assert np.array_equal(r.surv_keep.astype(bool), r.surv_pq <= 0.05)
+    for a in range(0, b.n_aln, 97):
+        s0, s1 = r.surv_off[a], r.surv_off[a + 1]
+        p = r.surv_p[s0:s1]
+        order = np.argsort(p, kind="stable")
+        rk = np.empty(len(p)); rk[order] = np.arange(len(p)) + 1
+        assert np.array_equal(r.surv_pq[s0:s1], (np.diff(b.hsp_off)[a] * p) / rk)
+    # chains: members are retained HSPs, strictly colinear in the chain's orientation
+    for a in np.nonzero(r.chain_len > 1)[0][:200]:
+        h0 = b.hsp_off[a]
+        ch = r.chain_idx[r.chain_off[a]:r.chain_off[a + 1]] + h0
+        assert (b.qend[ch][:-1] < b.qstart[ch][1:]).all()
+        if r.chain_orient[a] == 0:
+            assert (b.send[ch][:-1] < b.sstart[ch][1:]).all()
+        else:
+            assert (b.send[ch][:-1] > b.sstart[ch][1:]).all()
+    # idempotence
+    r2 = engine.build_batch(b, "hist", True)
+    compare_results(r2, r, exact_p=True, what="idempotence")
