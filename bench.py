@@ -9,7 +9,7 @@ ortholog) over one batch of synthetic lncRNAs of the named BASELINE config (defa
   value : device-timed (CUDA events) with the columnar inputs already resident in HBM
   e2e   : the same call through the C-ABI with pinned HOST buffers: H2D of all inputs and D2H of
           the result (chains + per-lncRNA selection) inside the timed region
-  roofline : the streaming kernel (k_score), algorithmic bytes / CUDA-event duration vs measured peak
+  roofline : the streaming kernel (k_filter), algorithmic bytes / CUDA-event duration vs measured peak
   cpu_baseline : the oracle port (C, OpenMP, all host threads) on a bounded sample, rank 0, N=1
 `--impl reference` times that oracle port alone (the reference is pure Python and cannot travel to
 the GPU box).
@@ -228,7 +228,7 @@ def main():
     for _ in range(args.steps):
         c = step_device()
         sm = eng.stage_ms()
-        score_ms.append(sm["score"])
+        score_ms.append(sm["filter"])
         for k, v in sm.items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     e1.record(stream)
@@ -247,10 +247,11 @@ def main():
 
     # roofline of the dominant (streaming) kernel
     peak, peak_src = measured_peak()
-    alg_bytes = 8.0 * batch.n_hsp + 21.0 * c.n_survivors
+    # k_filter: 8 B score read per HSP + (4 B position + 8 B score) written per survivor
+    alg_bytes = 8.0 * batch.n_hsp + 12.0 * c.n_survivors
     avg_score_ms = float(np.mean(score_ms))
     achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_score", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_filter", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}}
@@ -292,8 +293,12 @@ def main():
     d2h = int(res.thr.nbytes + res.status.nbytes + res.best_aln.nbytes + res.n_surv.nbytes + res.n_keep.nbytes
               + res.chain_len.nbytes + res.chain_orient.nbytes + res.chain_score.nbytes + res.orient_scores.nbytes
               + res.chain_off.nbytes + res.chain_idx.nbytes + res.chain_pq.nbytes + 40)
+    zero_copy = bool(eng.lib.o2a_coords_zero_copy(eng.h))
+    if zero_copy:
+        # coordinates stay in pinned host memory; only the retained HSPs' (4 x int32) are read over PCIe
+        h2d = int(h2d - 4 * hb.qstart.nbytes + 16 * int(res.n_keep.sum()))
     e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

@@ -59,6 +59,8 @@ extern "C" {
 #define O2A_STATUS_ORIENTATION_NONE 1  /* alignment.py:865-872 KeyError/TypeError */
 #define O2A_STATUS_BRENTQ 2            /* fitting.py:239 RuntimeError (no convergence) */
 #define O2A_STATUS_TOO_MANY_BINS 3     /* fitting.py:152 np.histogram ValueError */
+#define O2A_STATUS_UNSUPPORTED 4       /* library limit, not a reference error: background value range
+                                          > 2^18 or > 1024 distinct background values (hist) */
 
 #define O2A_EINVAL (-1)
 #define O2A_ECUDA (-2)
@@ -155,12 +157,14 @@ int o2a_best_chain(o2a_ctx *ctx, int64_t n, const int32_t *qstart, const int32_t
  * is enabled. Stage ids: */
 #define O2A_STAGE_H2D 0
 #define O2A_STAGE_FIT 1
-#define O2A_STAGE_SCORE 2     /* filter + p-value + rank/q (the HBM-bound streaming kernel) */
-#define O2A_STAGE_RANK_BIG 3
+#define O2A_STAGE_FILTER 2    /* score filter + ordered compaction (the HBM-bound streaming kernel) */
+#define O2A_STAGE_PQ 3        /* p-values, ranks, q, keep (survivors only) */
 #define O2A_STAGE_CHAIN 4
 #define O2A_STAGE_BEST 5
 #define O2A_STAGE_COUNT 6
 int64_t o2a_launch_count(const o2a_ctx *ctx);
+/* 1 if the last host-memory o2a_build_batch read the HSP coordinates in place (pinned, mapped) */
+int  o2a_coords_zero_copy(const o2a_ctx *ctx);
 int  o2a_set_timing(o2a_ctx *ctx, int enabled);
 int  o2a_get_stage_ms(o2a_ctx *ctx, float *ms /*O2A_STAGE_COUNT*/);
 

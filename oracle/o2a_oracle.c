@@ -531,7 +531,10 @@ int o2a_oracle_build_batch(
         status[l] = st;
         if (st) {
             best = -1;
-            for (int64_t a = aln_off[l]; a < aln_off[l + 1]; a++) { chain_len[a] = 0; chain_score[a] = -INFINITY; }
+            for (int64_t a = aln_off[l]; a < aln_off[l + 1]; a++) {   /* the reference aborted this lncRNA */
+                n_surv[a] = 0; n_keep[a] = 0; chain_len[a] = 0; chain_score[a] = -INFINITY;
+                orient_scores[2 * a] = orient_scores[2 * a + 1] = -INFINITY;
+            }
         }
         best_aln[l] = best;
         free(hbins); free(hcdf); free(scratch); free(sorted);

@@ -10,7 +10,6 @@
 #include "o2a_chain.cuh"
 #include "o2a_device.cuh"
 #include "o2a_fit.cuh"
-#include "o2a_kde.cuh"
 #include "o2a_score.cuh"
 
 using namespace o2a;
@@ -24,7 +23,7 @@ struct DevBuf {
 
 constexpr int N_EVENTS = O2A_STAGE_COUNT + 1;
 constexpr int SM_COUNT_FALLBACK = 148;
-constexpr long long UV_MAX_RANGE = 1ll << 20;
+constexpr long long UV_MAX_RANGE = 1ll << 18;   // 1 MiB of counters per resident CTA
 
 }  // namespace
 
@@ -49,8 +48,9 @@ struct o2a_ctx {
     DevBuf aln_lnc, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
     DevBuf n_surv, n_keep, surv_idx, surv_p, surv_pq, surv_keep;
     DevBuf chain_len, chain_orient, chain_score, orient_scores, chain_slot, best_key, best_aln;
-    DevBuf big_list, big_count, counters;
-    DevBuf fit_cnt, fit_leaf, fit_leaf_sum, uv_scratch;
+    DevBuf big_list, mid_list, big_count, counters;
+    DevBuf fit_cnt;
+    bool coords_zero_copy = false;   // qstart..send read in place from pinned, device-mapped host memory
     DevBuf sort_k0, sort_k1, sort_v0, sort_v1;
     DevBuf cb_qs, cb_qe, cb_ss, cb_se, cb_sc, cb_id, cb_total, cb_prev, cb_f, cb_chain;
     DevBuf off_a, off_b, out_i32, out_f64a, out_f64b, out_u8, maxred;
@@ -234,8 +234,7 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->uv_cnt, &ctx->uv_n, &ctx->n_surv, &ctx->n_keep, &ctx->surv_idx, &ctx->surv_p,
                       &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
                       &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->big_list,
-                      &ctx->big_count, &ctx->counters, &ctx->fit_cnt, &ctx->fit_leaf, &ctx->fit_leaf_sum,
-                      &ctx->uv_scratch, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
+                      &ctx->mid_list, &ctx->big_count, &ctx->counters, &ctx->fit_cnt, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
                       &ctx->cb_qe, &ctx->cb_ss, &ctx->cb_se, &ctx->cb_sc, &ctx->cb_id, &ctx->cb_total, &ctx->cb_prev,
                       &ctx->cb_f, &ctx->cb_chain, &ctx->off_a, &ctx->off_b, &ctx->out_i32, &ctx->out_f64a,
                       &ctx->out_f64b, &ctx->out_u8, &ctx->maxred};
@@ -278,6 +277,7 @@ extern "C" void* o2a_host_alloc(size_t bytes)
 extern "C" void o2a_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int64_t o2a_launch_count(const o2a_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
+extern "C" int o2a_coords_zero_copy(const o2a_ctx* ctx) { return ctx && ctx->coords_zero_copy ? 1 : 0; }
 extern "C" int o2a_set_timing(o2a_ctx* ctx, int enabled) { if (!ctx) return O2A_EINVAL; ctx->timing = enabled != 0; return 0; }
 extern "C" int o2a_get_stage_ms(o2a_ctx* ctx, float* ms)
 {
@@ -321,37 +321,29 @@ static int run_fit(o2a_ctx* ctx)
     ENS(thr, b.n_lnc * sizeof(double));
     ENS(status, b.n_lnc * sizeof(int));
     if (b.n_lnc == 0) return 0;
+    FitArgs A{};
+    A.n_lnc = b.n_lnc; A.bg_off = (const long long*)b.bg_off; A.bg = b.bg; A.kde_factor = b.kde_factor;
+    A.fitter = p.fitter; A.alpha = p.alpha;
     if (p.fitter == O2A_FIT_HIST) {
         ENS(fits, b.n_lnc * sizeof(LncFit));
         ENS(tbl_k, (b.n_bg / 2 + 2) * sizeof(int));
         ENS(tbl_cum, (b.n_bg / 2 + 2) * sizeof(double));
-        const long long max_B = b.max_lnc_bg / 2;
-        const bool big = max_B > FIT_SMEM_BINS;
-        int grid = grid_for(ctx, b.n_lnc, big ? 2 : 8);
-        long long max_leaves = max_B / 64 + 2;
-        if (big) ENS(fit_cnt, (size_t)grid * max_B * sizeof(int));
-        if (max_B > (long long)FIT_SMEM_LEAVES * 64) {
-            ENS(fit_leaf, (size_t)grid * max_leaves * sizeof(PwNode));
-            ENS(fit_leaf_sum, (size_t)grid * max_leaves * sizeof(double));
-        }
-        k_fit_hist<<<grid, FIT_THREADS, 0, ctx->stream>>>(
-            b.n_lnc, (const long long*)b.bg_off, b.bg, p.alpha, P<double>(ctx->thr), P<LncFit>(ctx->fits),
-            P<int>(ctx->tbl_k), P<double>(ctx->tbl_cum), P<int>(ctx->status), P<int>(ctx->fit_cnt), max_B,
-            P<PwNode>(ctx->fit_leaf), P<double>(ctx->fit_leaf_sum), max_leaves);
-        LAUNCH_CHECK();
     } else {
         if (p.fitter == O2A_FIT_KDE && !b.kde_factor) { ctx->err = "kde_factor is required for the KDE fitter"; return O2A_EINVAL; }
         ENS(uv_val, (b.n_bg + 1) * sizeof(int));
         ENS(uv_cnt, (b.n_bg + 1) * sizeof(int));
         ENS(uv_n, b.n_lnc * sizeof(int));
-        int grid = grid_for(ctx, b.n_lnc, 1);
-        ENS(uv_scratch, (size_t)grid * UV_MAX_RANGE * sizeof(int));
-        k_fit_uv<<<grid, UV_THREADS, 0, ctx->stream>>>(
-            b.n_lnc, (const long long*)b.bg_off, b.bg, b.kde_factor, p.fitter, p.alpha, P<double>(ctx->thr),
-            P<int>(ctx->uv_val), P<int>(ctx->uv_cnt), P<int>(ctx->uv_n), P<int>(ctx->status),
-            P<int>(ctx->uv_scratch), UV_MAX_RANGE);
-        LAUNCH_CHECK();
     }
+    int grid = grid_for(ctx, b.n_lnc, 6);
+    // per-CTA global counters for backgrounds whose value range exceeds the shared-memory budget
+    long long max_range = UV_MAX_RANGE;
+    ENS(fit_cnt, (size_t)grid * max_range * sizeof(int));
+    A.thr = P<double>(ctx->thr); A.fits = P<LncFit>(ctx->fits); A.tbl_k = P<int>(ctx->tbl_k);
+    A.tbl_cum = P<double>(ctx->tbl_cum); A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt);
+    A.uv_n = P<int>(ctx->uv_n); A.status = P<int>(ctx->status); A.g_cnt = P<int>(ctx->fit_cnt);
+    A.max_range = max_range;
+    k_fit<<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
     return 0;
 }
 
@@ -369,24 +361,28 @@ static int run_score(o2a_ctx* ctx)
     ENS(n_surv, b.n_aln * sizeof(int)); ENS(n_keep, b.n_aln * sizeof(int));
     ENS(surv_idx, b.n_hsp * sizeof(int)); ENS(surv_p, b.n_hsp * sizeof(double));
     ENS(surv_pq, b.n_hsp * sizeof(double)); ENS(surv_keep, b.n_hsp);
-    ENS(big_list, (b.n_aln + 1) * sizeof(int)); ENS(big_count, 2 * sizeof(int));
-    CU(cudaMemsetAsync(ctx->big_count.p, 0, 2 * sizeof(int), ctx->stream));
-    if (b.n_aln == 0) return 0;
-    ScoreArgs A{};
+    ENS(big_list, (b.n_aln + 1) * sizeof(int)); ENS(mid_list, (b.n_aln + 1) * sizeof(int));
+    ENS(big_count, 4 * sizeof(int));
+    CU(cudaMemsetAsync(ctx->big_count.p, 0, 4 * sizeof(int), ctx->stream));
+    if (b.n_aln == 0) return stage_event(ctx, O2A_STAGE_PQ);
+    k_filter<<<grid_for(ctx, b.n_aln, 6), FILTER_THREADS, 0, ctx->stream>>>(
+        b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), b.score, P<double>(ctx->thr), P<int>(ctx->status),
+        P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_p));
+    LAUNCH_CHECK();
+    int r = stage_event(ctx, O2A_STAGE_PQ);
+    if (r) return r;
+    PqArgs A{};
     A.n_aln = b.n_aln; A.hsp_off = (const long long*)b.hsp_off; A.aln_lnc = P<int>(ctx->aln_lnc);
-    A.score = b.score; A.thr = P<double>(ctx->thr); A.lnc_status = P<int>(ctx->status);
+    A.lnc_status = P<int>(ctx->status); A.n_surv = P<int>(ctx->n_surv);
     A.fits = P<LncFit>(ctx->fits); A.tbl_k = P<int>(ctx->tbl_k); A.tbl_cum = P<double>(ctx->tbl_cum);
     A.bg_off = (const long long*)b.bg_off;
     A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt); A.uv_n = P<int>(ctx->uv_n);
     A.kde_factor = b.kde_factor; A.fitter = p.fitter; A.fdr = p.fdr; A.alpha = p.alpha;
-    A.n_surv = P<int>(ctx->n_surv); A.n_keep = P<int>(ctx->n_keep); A.surv_idx = P<int>(ctx->surv_idx);
-    A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq); A.surv_keep = P<unsigned char>(ctx->surv_keep);
+    A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
+    A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep);
     A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
-    int grid = grid_for(ctx, b.n_aln, 8);
-    k_score<<<grid, SCORE_THREADS, 0, ctx->stream>>>(A);
+    k_pq<<<grid_for(ctx, b.n_aln, 12), PQ_THREADS, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
-    int r = stage_event(ctx, O2A_STAGE_RANK_BIG);
-    if (r) return r;
     if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
         int g2 = grid_for(ctx, b.n_aln, 2);
         r = ensure_sort_scratch(ctx, g2, b.max_aln_hsps);
@@ -419,10 +415,15 @@ static int run_chain(o2a_ctx* ctx)
         A.chain_len = P<int>(ctx->chain_len); A.chain_orient = P<unsigned char>(ctx->chain_orient);
         A.chain_score = P<double>(ctx->chain_score); A.orient_scores = P<double>(ctx->orient_scores);
         A.chain_slot = P<int>(ctx->chain_slot); A.best_key = P<double>(ctx->best_key);
-        A.lnc_status = P<int>(ctx->status); A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count) + 1;
-        int grid = grid_for(ctx, b.n_aln, 12);
-        k_chain_small<<<grid, CHAIN_THREADS, 0, ctx->stream>>>(A);
+        A.lnc_status = P<int>(ctx->status);
+        A.mid_list = P<int>(ctx->mid_list); A.mid_count = P<int>(ctx->big_count) + 2;
+        A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count) + 1;
+        k_chain_warp<<<grid_for(ctx, (b.n_aln + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
+        if (b.max_aln_hsps > CHAIN_WARP_MAX) {
+            k_chain_small<<<grid_for(ctx, b.n_aln, 8), CHAIN_THREADS, 0, ctx->stream>>>(A);
+            LAUNCH_CHECK();
+        }
         if (b.max_aln_hsps > CHAIN_SMALL_MAX) {
             int g2 = grid_for(ctx, b.n_aln, 2);
             const long long cap = b.max_aln_hsps;
@@ -445,7 +446,8 @@ static int run_chain(o2a_ctx* ctx)
     if (r) return r;
     if (b.n_lnc > 0) {
         k_best<<<(unsigned)((b.n_lnc + 127) / 128), 128, 0, ctx->stream>>>(
-            b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->status), P<int>(ctx->chain_len), P<double>(ctx->chain_score),
+            b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->status), P<int>(ctx->n_surv), P<int>(ctx->n_keep),
+            P<int>(ctx->chain_len), P<double>(ctx->chain_score), P<double>(ctx->orient_scores),
             P<double>(ctx->best_key), p.best_function, P<long long>(ctx->best_aln));
         LAUNCH_CHECK();
     }
@@ -495,10 +497,28 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         if ((r = upload(ctx, ctx->in_qlen, batch->qlen, (size_t)batch->n_aln, &b.qlen))) return r;
         if ((r = upload(ctx, ctx->in_slen, batch->slen, (size_t)batch->n_aln, &b.slen))) return r;
         if ((r = upload(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, &b.score))) return r;
-        if ((r = upload(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, &b.qstart))) return r;
-        if ((r = upload(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, &b.qend))) return r;
-        if ((r = upload(ctx, ctx->in_ss, batch->sstart, (size_t)batch->n_hsp, &b.sstart))) return r;
-        if ((r = upload(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, &b.send))) return r;
+        // Coordinates are only ever read for the HSPs that reach the chaining (~1 %): when the caller's
+        // arrays are pinned + device-mapped (o2a_host_alloc / cudaHostAlloc / cudaHostRegister) the
+        // chaining kernels gather them in place over PCIe instead of copying 16 B per HSP.
+        ctx->coords_zero_copy = false;
+        if (batch->n_hsp > 0 && !getenv("O2A_NO_ZERO_COPY")) {
+            const void* hp[4] = {batch->qstart, batch->qend, batch->sstart, batch->send};
+            const int* dp[4] = {nullptr, nullptr, nullptr, nullptr};
+            bool ok = true;
+            for (int i = 0; i < 4 && ok; ++i) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                    cudaGetLastError(); ok = false;
+                } else dp[i] = (const int*)at.devicePointer;
+            }
+            if (ok) { b.qstart = dp[0]; b.qend = dp[1]; b.sstart = dp[2]; b.send = dp[3]; ctx->coords_zero_copy = true; }
+        }
+        if (!ctx->coords_zero_copy) {
+            if ((r = upload(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, &b.qstart))) return r;
+            if ((r = upload(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, &b.qend))) return r;
+            if ((r = upload(ctx, ctx->in_ss, batch->sstart, (size_t)batch->n_hsp, &b.sstart))) return r;
+            if ((r = upload(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, &b.send))) return r;
+        }
         if (b.max_aln_hsps <= 0) {
             long long m = 0;
             for (long long a = 0; a < batch->n_aln; ++a) { long long d = batch->hsp_off[a + 1] - batch->hsp_off[a]; if (d > m) m = d; }
@@ -520,8 +540,8 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
     }
     if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
     if ((r = run_fit(ctx))) return r;
-    if ((r = stage_event(ctx, O2A_STAGE_SCORE))) return r;
-    if ((r = run_score(ctx))) return r;       // records O2A_STAGE_RANK_BIG itself
+    if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
+    if ((r = run_score(ctx))) return r;       // records O2A_STAGE_PQ itself
     if ((r = stage_event(ctx, O2A_STAGE_CHAIN))) return r;
     if ((r = run_chain(ctx))) return r;       // records O2A_STAGE_BEST itself
     ENS(counters, 5 * 8);
@@ -710,11 +730,11 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     ctx->prm.gapopen = gapopen; ctx->prm.gapextend = gapextend;
     ENS(aln_lnc, 4); ENS(status, 4); ENS(n_surv, 4); ENS(n_keep, 4);
     ENS(surv_idx, (size_t)n * 4); ENS(surv_keep, (size_t)n); ENS(surv_pq, (size_t)n * 8);
-    ENS(big_list, 2 * sizeof(int)); ENS(big_count, 2 * sizeof(int));
+    ENS(big_list, 2 * sizeof(int)); ENS(mid_list, 2 * sizeof(int)); ENS(big_count, 4 * sizeof(int));
     int ni = (int)n;
     CU(cudaMemsetAsync(ctx->aln_lnc.p, 0, 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->status.p, 0, 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->big_count.p, 0, 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->big_count.p, 0, 16, ctx->stream));
     CU(cudaMemcpyAsync(ctx->n_surv.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->n_keep.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
     if (n > 0) {

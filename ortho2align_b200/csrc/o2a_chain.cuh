@@ -18,7 +18,8 @@
 namespace o2a {
 
 constexpr int CHAIN_THREADS = 128;
-constexpr int CHAIN_SMALL_MAX = 192;      // retained HSPs per alignment handled in shared memory
+constexpr int CHAIN_WARP_MAX = 32;        // retained HSPs per alignment handled by ONE warp
+constexpr int CHAIN_SMALL_MAX = 192;      // retained HSPs per alignment handled by a CTA in shared memory
 constexpr int CHAINBIG_THREADS = 512;
 
 // per-orientation vertex storage: n HSPs, vertex v in 1..n is HSP slot v-1; v=0 begin, v=n+1 end
@@ -148,7 +149,8 @@ struct ChainArgs {
     int* chain_slot;           // slot layout: survivor-slot positions of the chain HSPs, chain order
     double* best_key;          // per alignment: get_best_orthologs key of the chosen chain
     int* lnc_status;
-    int* big_list; int* big_count;
+    int* mid_list; int* mid_count;     // alignments with > CHAIN_WARP_MAX retained HSPs (-> k_chain_small)
+    int* big_list; int* big_count;     // alignments with > CHAIN_SMALL_MAX retained HSPs (-> k_chain_big)
 };
 
 // key of get_best_orthologs on the QUERY bed12 line (pipeline.py:981-987) for the chosen chain
@@ -166,6 +168,142 @@ __device__ double best_key_of_chain(const ChainArgs& A, long long h0, const int*
     if (which == 1) return (double)((long long)hi - (long long)lo);
     if (which == 2) return (double)len;
     return wsum;
+}
+
+// Warp path: one warp per alignment with at most CHAIN_WARP_MAX retained HSPs (the common case:
+// ~10-20 retained of ~130 survivors). Everything lives in the warp's slice of shared memory;
+// lane i owns HSP i; the push DP walks the vertices in list order with the lanes on the window.
+constexpr int CHAINW_WARPS = 4;
+
+__global__ void __launch_bounds__(CHAINW_WARPS * 32)
+k_chain_warp(ChainArgs A)
+{
+    constexpr int C = CHAIN_WARP_MAX;
+    __shared__ int s_qs[CHAINW_WARPS][C], s_qe[CHAINW_WARPS][C], s_ss[CHAINW_WARPS][C], s_se[CHAINW_WARPS][C], s_id[CHAINW_WARPS][C];
+    __shared__ double s_sc[CHAINW_WARPS][C];
+    __shared__ double s_total[CHAINW_WARPS][C + 2];
+    __shared__ int s_prev[CHAINW_WARPS][C + 2], s_f[CHAINW_WARPS][C + 2];
+    __shared__ int s_chain[CHAINW_WARPS][2][C];
+    const int lane = lane_id(), w = warp_id();
+    const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
+    const double POS_INF = __longlong_as_double(0x7ff0000000000000ll);
+    const long long nwarps_total = (long long)gridDim.x * CHAINW_WARPS;
+
+    for (long long a = (long long)blockIdx.x * CHAINW_WARPS + w; a < A.n_aln; a += nwarps_total) {
+        const int r = A.n_keep[a];
+        const int l = A.aln_lnc[a];
+        if (r > C) {
+            if (lane == 0) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
+            continue;
+        }
+        if (r == 0 || A.lnc_status[l] == 2 || A.lnc_status[l] == 3 || A.lnc_status[l] == 4) {
+            if (lane == 0) {
+                A.chain_len[a] = 0; A.chain_orient[a] = 1; A.chain_score[a] = NEG_INF;
+                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = NEG_INF; A.best_key[a] = 0.0;
+            }
+            continue;
+        }
+        const long long h0 = A.hsp_off[a];
+        const int ns = A.n_surv[a];
+        // ---- gather: lane p gets the p-th retained HSP (list order) -----------------------------
+        int my_slot = -1;
+        int got = 0;
+        for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
+            int k = k0 + lane;
+            bool keep = (k < ns) && A.surv_keep[h0 + k];
+            unsigned b = __ballot_sync(FULL_MASK, keep);
+            // the lane whose index equals (got + rank of a kept k) takes that k
+            int want = lane - got;                       // which kept element of this chunk is mine
+            if (want >= 0 && want < __popc(b)) {
+                unsigned bb = b;
+                for (int t = 0; t < want; ++t) bb &= bb - 1;     // drop the `want` lowest set bits
+                my_slot = k0 + __ffs(bb) - 1;
+            }
+            got += __popc(b);
+        }
+        int qs = 0, qe = 0, ss = 0, se = 0; double sc = 0.0; bool dir = false; bool bad = false;
+        if (lane < r) {
+            long long h = h0 + A.surv_idx[h0 + my_slot];
+            qs = A.qstart[h]; qe = A.qend[h]; ss = A.sstart[h]; se = A.send[h]; sc = A.score[h];
+            dir = (se - ss > 0);                         // alignment.py:107-110
+            bad = !(qe - qs > 0);                        // orientation None
+        }
+        if (__any_sync(FULL_MASK, bad)) {                // reference raises in _split_orientations
+            if (lane == 0) {
+                atomicMax(&A.lnc_status[l], 1);
+                A.chain_len[a] = 0; A.chain_orient[a] = 1; A.chain_score[a] = NEG_INF;
+                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = NEG_INF; A.best_key[a] = 0.0;
+            }
+            continue;
+        }
+        double sco[2]; int len[2];
+#pragma unroll 1
+        for (int o = 0; o < 2; ++o) {
+            const bool want_dir = (o == 0);
+            const bool mine = (lane < r) && (dir == want_dir);
+            const unsigned members = __ballot_sync(FULL_MASK, mine);
+            const int n_o = __popc(members);
+            if (n_o == 0) { sco[o] = NEG_INF; len[o] = 0; continue; }
+            // stable rank by (qstart, sstart, list order) among the members
+            int rank = 0;
+            for (unsigned mm = members; mm; mm &= mm - 1) {
+                int q = __ffs(mm) - 1;
+                int oqs = __shfl_sync(FULL_MASK, qs, q), oss = __shfl_sync(FULL_MASK, ss, q);
+                rank += (oqs < qs) || (oqs == qs && (oss < ss || (oss == ss && q < lane)));
+            }
+            __syncwarp();
+            if (mine) {
+                s_qs[w][rank] = qs; s_qe[w][rank] = qe; s_ss[w][rank] = ss; s_se[w][rank] = se;
+                s_sc[w][rank] = sc; s_id[w][rank] = my_slot;
+            }
+            __syncwarp();
+            ChainMem M{s_qs[w], s_qe[w], s_ss[w], s_se[w], s_sc[w], s_id[w], s_total[w], s_prev[w], s_f[w]};
+            ChainGeom g{n_o, want_dir, A.qlen[a], A.slen[a], (double)A.gapopen, (double)A.gapextend};
+            const int N = n_o + 2;
+            // f(i): lanes 0..N-1 each scan forward from their own vertex
+            for (int i = lane; i < N; i += 32) {
+                int fi = N;
+                for (int j = i + 1; j < N; ++j) if (v_prec(M, g, i, j)) { fi = j; break; }
+                M.f[i] = fi;
+                M.total[i] = i == 0 ? 0.0 : POS_INF;
+                M.prev[i] = -1;
+            }
+            __syncwarp();
+            for (int i = 0; i < N - 1; ++i) {
+                const double ti = M.total[i];
+                const int fi = M.f[i];
+                if (fi < N && ti < POS_INF) {
+                    const int gi = M.f[fi] < N ? M.f[fi] : N;
+                    for (int j = fi + lane; j < gi; j += 32) {
+                        if (v_prec(M, g, i, j)) {
+                            double nsc = __dadd_rn(ti, v_weight(M, g, i, j));
+                            if (M.total[j] > nsc) { M.total[j] = nsc; M.prev[j] = i; }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            sco[o] = -M.total[N - 1];
+            int ln = 0;
+            if (lane == 0) {
+                int cur = N - 1;
+                while (M.prev[cur] != -1) { cur = M.prev[cur]; if (cur != 0) ++ln; }
+                int pos = ln; cur = N - 1;
+                while (M.prev[cur] != -1) { cur = M.prev[cur]; if (cur != 0) s_chain[w][o][--pos] = M.id[cur - 1]; }
+            }
+            len[o] = __shfl_sync(FULL_MASK, ln, 0);
+            __syncwarp();
+        }
+        const int pick = (sco[0] > sco[1]) ? 0 : 1;      // alignment.py:1043-1046
+        const int ln = len[pick];
+        for (int c = lane; c < ln; c += 32) A.chain_slot[h0 + c] = s_chain[w][pick][c];
+        if (lane == 0) {
+            A.chain_len[a] = ln; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = sco[pick];
+            A.orient_scores[2 * a] = sco[0]; A.orient_scores[2 * a + 1] = sco[1];
+            A.best_key[a] = ln ? best_key_of_chain(A, h0, s_chain[w][pick], ln, A.best_value) : 0.0;
+        }
+        __syncwarp();
+    }
 }
 
 // Shared-memory path: alignments with at most CHAIN_SMALL_MAX retained HSPs (the common case:
@@ -187,22 +325,15 @@ k_chain_small(ChainArgs A)
     __shared__ int s_bad;
     const int tid = threadIdx.x;
 
-    for (long long a = blockIdx.x; a < A.n_aln; a += gridDim.x) {
+    const int nmid = *A.mid_count;
+    for (int bi = blockIdx.x; bi < nmid; bi += gridDim.x) {
+        const long long a = A.mid_list[bi];
         const long long h0 = A.hsp_off[a];
         const int ns = A.n_surv[a];
         const int r = A.n_keep[a];
         const int l = A.aln_lnc[a];
         if (r > C) {
             if (tid == 0) { int slot = atomicAdd(A.big_count, 1); A.big_list[slot] = (int)a; }
-            continue;
-        }
-        if (r == 0 || A.lnc_status[l] == 2 || A.lnc_status[l] == 3) {
-            if (tid == 0) {
-                A.chain_len[a] = 0; A.chain_orient[a] = 1;
-                A.chain_score[a] = __longlong_as_double(0xfff0000000000000ll);
-                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = __longlong_as_double(0xfff0000000000000ll);
-                A.best_key[a] = 0.0;
-            }
             continue;
         }
         if (tid == 0) s_bad = 0;
@@ -377,7 +508,8 @@ k_chain_big(ChainArgs A, ChainBigScratch S)
 // K7: get_best_orthologs selection per lncRNA (pipeline.py:1004-1016): first extremal key wins.
 // Also clears the chains of lncRNAs the reference would have aborted (status != 0).
 __global__ void k_best(long long n_lnc, const long long* __restrict__ aln_off, const int* __restrict__ lnc_status,
-                       int* __restrict__ chain_len, double* __restrict__ chain_score,
+                       int* __restrict__ n_surv, int* __restrict__ n_keep,
+                       int* __restrict__ chain_len, double* __restrict__ chain_score, double* __restrict__ orient_scores,
                        const double* __restrict__ best_key, int best_fn, long long* __restrict__ best_aln)
 {
     long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,7 +517,11 @@ __global__ void k_best(long long n_lnc, const long long* __restrict__ aln_off, c
     long long best = -1; double bk = 0.0;
     const bool failed = lnc_status[l] != 0;
     for (long long a = aln_off[l]; a < aln_off[l + 1]; ++a) {
-        if (failed) { chain_len[a] = 0; chain_score[a] = __longlong_as_double(0xfff0000000000000ll); continue; }
+        if (failed) {   // the reference aborted this lncRNA: it contributes nothing
+            n_surv[a] = 0; n_keep[a] = 0; chain_len[a] = 0; chain_score[a] = __longlong_as_double(0xfff0000000000000ll);
+            orient_scores[2 * a] = orient_scores[2 * a + 1] = __longlong_as_double(0xfff0000000000000ll);
+            continue;
+        }
         if (chain_len[a] > 0) {
             double k = best_key[a];
             if (best < 0 || (best_fn == 0 ? k > bk : k < bk)) { best = a; bk = k; }

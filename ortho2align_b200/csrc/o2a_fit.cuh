@@ -1,217 +1,409 @@
-// o2a_fit.cuh — K1/K2: per-lncRNA histogram background fit + isf(alpha).
+// o2a_fit.cuh — K1/K2: per-lncRNA background fit + isf(alpha) for all three fitters.
 //
-// Replaces HistogramFitter.__init__ / .isf (fitting.py:142-155, 206-215), i.e. numpy 2.3.5
-// np.histogram(bins=len//2, density=True) + scipy 1.18.1 rv_histogram.__init__ + rv_continuous.isf,
-// with their exact operation order:
-//   edges   = linspace(min, max, B+1)            (k*step + first, last edge = max)
-//   index   = int(((x-first)/denom)*B) with numpy's three edge fix-ups
-//   dens    = n/diff(edges)/n.sum();  hp0 = dens/diff(edges)   (rv_histogram's second division)
-//   hpdf    = hp0/np.sum(hp0*w)  — np.sum is numpy's PAIRWISE sum (128-blocks, 8 accumulators)
-//   hcdf    = np.cumsum(hpdf*w)  — sequential, left to right
-//   isf(a)  = np.interp(1-a, hcdf, hbins)
-// One CTA per lncRNA. The only per-lncRNA output besides thr is a COMPACT table of the non-empty
-// bins (bin index, cumulative value): empty bins add exactly 0.0 everywhere, so hcdf is a step
-// function of the non-empty ones — the 2x(B+1) doubles of hbins/hcdf never touch HBM.
+// hist  — replaces HistogramFitter.__init__ / .isf (fitting.py:142-155, 206-215), i.e. numpy 2.3.5
+//         np.histogram(bins=len//2, density=True) + scipy 1.18.1 rv_histogram.__init__ +
+//         rv_continuous.isf, with their exact operation order:
+//           edges   = linspace(min, max, B+1)            (k*step + first, last edge = max)
+//           index   = int(((x-first)/denom)*B) with numpy's three edge fix-ups
+//           dens    = n/diff(edges)/n.sum();  hp0 = dens/diff(edges)  (rv_histogram's 2nd division)
+//           hpdf    = hp0/np.sum(hp0*w)  — np.sum is numpy's PAIRWISE sum (128-blocks, 8 accumulators)
+//           hcdf    = np.cumsum(hpdf*w)  — sequential, left to right
+//           isf(a)  = np.interp(1-a, hcdf, hbins)
+// kde   — KernelFitter (fitting.py:245-356) on the value-compressed background (see below)
+// emp   — extension
+//
+// One CTA per lncRNA. The background is read ONCE (the HBM-bound part) and reduced to its distinct
+// values with multiplicities (integer BLAST scores: ~50 distinct values among 10^4..10^6 scores).
+// Everything after that is exact arithmetic on the few non-empty bins: empty bins contribute
+// exactly +0.0 to numpy's pairwise sum and cumsum, so the B-long hbins/hcdf arrays never exist —
+// the result per lncRNA is a COMPACT table (bin index, cumulative value) of the non-empty bins.
 #pragma once
 #include "o2a_device.cuh"
 
 namespace o2a {
 
 constexpr int FIT_THREADS = 256;
-constexpr int FIT_SMEM_BINS = 8192;     // bin counters kept in shared memory up to this B
-constexpr int FIT_SMEM_LEAVES = 512;    // pairwise-sum leaves kept in shared memory
+constexpr int FIT_SMEM_RANGE = 4096;    // distinct-value counters kept in shared memory up to this range
+constexpr int FIT_SMEM_NNZ = 1024;      // distinct values / non-empty bins staged in shared memory
 
-struct PwNode { long long off; long long n; };
+// ndtr(z) = 0.5*erfc(-z/sqrt2): scipy.special.ndtr is cephes-derived and not bit-reproducible with
+// CUDA's erfc (<= 2.3e-16 absolute apart) — KDE parity is to tolerance.
+__device__ __forceinline__ double ndtr_dev(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
 
-// t_k = hp0_k * w_k of bin k (the summand of rv_histogram's normaliser)
-__device__ __forceinline__ double fit_term(int cnt, long long k, const LncFit& f, double total)
+// KernelFitter.sf (fitting.py:282-310) on the value-compressed background:
+// cdf = sum_v cnt_v * ndtr((x - v)/factor) / n
+__device__ double kde_sf_compressed(double x, const int* __restrict__ val, const int* __restrict__ cnt, int nv,
+                                    double factor, double n)
+{
+    double acc = 0.0;
+    for (int i = 0; i < nv; ++i) acc += (double)cnt[i] * ndtr_dev((x - (double)val[i]) / factor);
+    return 1.0 - acc / n;
+}
+
+// empirical sf (extension): #{bg > x}/n from the sorted distinct values + suffix counts #{bg >= v}
+__device__ double emp_sf_compressed(double x, const int* __restrict__ val, const int* __restrict__ ge, int nv, double n)
+{
+    int lo = 0, hi = nv;                              // first distinct value > x
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((double)val[mid] > x) hi = mid; else lo = mid + 1; }
+    double c = lo < nv ? (double)(ge[lo]) : 0.0;
+    return c / n;
+}
+
+// CTA-wide deterministic sum: per-thread partials, then a fixed shuffle/shared tree.
+__device__ double cta_sum(double v, double* s_red)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+    __syncthreads();
+    if (lane_id() == 0) s_red[warp_id()] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    return t;
+}
+
+__device__ double kde_sf_cta(double x, const int* val, const int* cnt, int nv, double factor, double n, double* s_red)
+{
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) acc += (double)cnt[i] * ndtr_dev((x - (double)val[i]) / factor);
+    return 1.0 - cta_sum(acc, s_red) / n;
+}
+
+// scipy/optimize/Zeros/brentq.c with scipy.optimize.brentq's defaults (xtol=2e-12, rtol=4*eps,
+// maxiter=100); every thread of the CTA executes the same control flow. err: 0 ok, -1 sign, -2 conv.
+__device__ double brentq_cta(double xa, double xb, double q, const int* val, const int* cnt, int nv,
+                             double factor, double n, double* s_red, int* err)
+{
+    const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+    double xpre = xa, xcur = xb, xblk = 0., fpre, fcur, fblk = 0., spre = 0., scur = 0., sbis, delta, stry, dpre, dblk;
+    *err = 0;
+    fpre = kde_sf_cta(xpre, val, cnt, nv, factor, n, s_red) - q;
+    fcur = kde_sf_cta(xcur, val, cnt, nv, factor, n, s_red) - q;
+    if (fpre == 0) return xpre;
+    if (fcur == 0) return xcur;
+    if (signbit(fpre) == signbit(fcur)) { *err = -1; return 0.; }
+    for (int i = 0; i < 100; ++i) {
+        if (fpre != 0 && fcur != 0 && (signbit(fpre) != signbit(fcur))) { xblk = xpre; fblk = fpre; spre = scur = xcur - xpre; }
+        if (fabs(fblk) < fabs(fcur)) { xpre = xcur; xcur = xblk; xblk = xpre; fpre = fcur; fcur = fblk; fblk = fpre; }
+        delta = (xtol + rtol * fabs(xcur)) / 2;
+        sbis = (xblk - xcur) / 2;
+        if (fcur == 0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);
+            else {
+                dpre = (fpre - fcur) / (xpre - xcur);
+                dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            double m1 = fabs(spre), m2 = 3 * fabs(sbis) - delta;
+            if (2 * fabs(stry) < (m1 < m2 ? m1 : m2)) { spre = scur; scur = stry; }
+            else { spre = sbis; scur = sbis; }
+        } else { spre = sbis; scur = sbis; }
+        xpre = xcur; fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur; else xcur += (sbis > 0 ? delta : -delta);
+        fcur = kde_sf_cta(xcur, val, cnt, nv, factor, n, s_red) - q;
+    }
+    *err = -2;
+    return xcur;
+}
+
+// t_k = hp0_k * w_k of bin k (summand of rv_histogram's normaliser); *hp0w = (hp0, w) for reuse
+__device__ __forceinline__ double fit_term(int cnt, long long k, const LncFit& f, double total, double* hp0_out, double* w_out)
 {
     double w = __dsub_rn(hist_edge(k + 1, f), hist_edge(k, f));
     double dens = __ddiv_rn(__ddiv_rn((double)cnt, w), total);
     double hp0 = __ddiv_rn(dens, w);
+    *hp0_out = hp0; *w_out = w;
     return __dmul_rn(hp0, w);
 }
 
-// numpy DOUBLE_pairwise_sum leaf (n <= 128) over bins [off, off+n), zero bins skipped (adding +0.0
-// to a non-negative accumulator is exact)
-__device__ double fit_leaf_sum(const int* cnt, long long off, long long n, const LncFit& f, double total)
+// numpy DOUBLE_pairwise_sum over a B-long array that is zero except at the sorted positions
+// pos[0..m) with values t[0..m): the recursion is walked over the non-empty entries only (a zero
+// subtree returns exactly 0.0 and x + 0.0 == x). Executed by ONE thread.
+__device__ double sparse_pairwise_sum(const int* pos, const double* t, int m, long long B)
 {
-    if (n < 8) {
-        double res = 0.;
-        for (long long i = 0; i < n; ++i) { int c = cnt[off + i]; if (c) res = __dadd_rn(res, fit_term(c, off + i, f, total)); }
-        return res;
+    struct Fr { long long off, n; int lo, hi; int state; };
+    Fr st[48]; double vs[48];
+    int sp = 0, vp = 0;
+    st[sp++] = Fr{0, B, 0, m, 0};
+    while (sp > 0) {
+        Fr& fr = st[sp - 1];
+        if (fr.lo >= fr.hi) { vs[vp++] = 0.0; --sp; continue; }
+        if (fr.n <= 128) {
+            double res;
+            if (fr.n < 8) {
+                res = 0.;
+                for (int e = fr.lo; e < fr.hi; ++e) res = __dadd_rn(res, t[e]);
+            } else {
+                double r[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+                const long long lim = fr.n - (fr.n % 8);
+                int e = fr.lo;
+                for (; e < fr.hi && (long long)pos[e] - fr.off < lim; ++e) {
+                    int j = (int)(((long long)pos[e] - fr.off) & 7);
+                    double v = t[e];
+                    // r[j] += v without dynamic register indexing
+                    r[0] = j == 0 ? __dadd_rn(r[0], v) : r[0]; r[1] = j == 1 ? __dadd_rn(r[1], v) : r[1];
+                    r[2] = j == 2 ? __dadd_rn(r[2], v) : r[2]; r[3] = j == 3 ? __dadd_rn(r[3], v) : r[3];
+                    r[4] = j == 4 ? __dadd_rn(r[4], v) : r[4]; r[5] = j == 5 ? __dadd_rn(r[5], v) : r[5];
+                    r[6] = j == 6 ? __dadd_rn(r[6], v) : r[6]; r[7] = j == 7 ? __dadd_rn(r[7], v) : r[7];
+                }
+                res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                for (; e < fr.hi; ++e) res = __dadd_rn(res, t[e]);
+            }
+            vs[vp++] = res; --sp; continue;
+        }
+        long long n2 = fr.n / 2; n2 -= n2 % 8;
+        if (fr.state == 0) {
+            // split the entries at position off + n2
+            int lo = fr.lo, hi = fr.hi;
+            const long long cut = fr.off + n2;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pos[mid] < cut) lo = mid + 1; else hi = mid; }
+            const int mid_e = lo;
+            fr.state = 1;
+            Fr right{fr.off + n2, fr.n - n2, mid_e, fr.hi, 0};
+            Fr left{fr.off, n2, fr.lo, mid_e, 0};
+            st[sp++] = right;          // evaluated second
+            st[sp++] = left;           // evaluated first
+            // mark that two children are pending by parking the frame in state 1
+        } else {
+            double b = vs[--vp]; double a = vs[--vp];
+            vs[vp++] = __dadd_rn(a, b); --sp;
+        }
     }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { int c = cnt[off + j]; r[j] = c ? fit_term(c, off + j, f, total) : 0.0; }
-    long long i;
-    long long lim = n - (n % 8);
-    for (i = 8; i < lim; i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { int c = cnt[off + i + j]; if (c) r[j] = __dadd_rn(r[j], fit_term(c, off + i + j, f, total)); }
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) { int c = cnt[off + i]; if (c) res = __dadd_rn(res, fit_term(c, off + i, f, total)); }
-    return res;
+    return vs[0];
 }
 
-// Kernel. Global scratch (per CTA): g_cnt [gridDim.x * max_B] ints (only used when B > FIT_SMEM_BINS),
-// g_leaf_off/g_leaf_n/g_leaf_sum [gridDim.x * max_leaves].
-__global__ void __launch_bounds__(FIT_THREADS)
-k_fit_hist(long long n_lnc, const long long* __restrict__ bg_off, const int* __restrict__ bg, double alpha,
-           double* __restrict__ thr, LncFit* __restrict__ fits, int* __restrict__ tbl_k,
-           double* __restrict__ tbl_cum, int* __restrict__ status,
-           int* __restrict__ g_cnt, long long max_B,
-           PwNode* __restrict__ g_leaf, double* __restrict__ g_leaf_sum, long long max_leaves)
-{
-    __shared__ int s_cnt[FIT_SMEM_BINS];
-    __shared__ PwNode s_leaf[FIT_SMEM_LEAVES];
-    __shared__ double s_leaf_sum[FIT_SMEM_LEAVES];
-    __shared__ int s_red[2 * (FIT_THREADS / 32)];
-    __shared__ int s_scan[FIT_THREADS / 32 + 2];
-    __shared__ LncFit s_fit;
-    __shared__ long long s_nleaf;
-    __shared__ double s_S;
-    __shared__ int s_bad;
-    const int tid = threadIdx.x;
+struct FitArgs {
+    long long n_lnc;
+    const long long* bg_off;
+    const int* bg;
+    const double* kde_factor;
+    int fitter;
+    double alpha;
+    double* thr;
+    LncFit* fits;
+    int* tbl_k; double* tbl_cum;        // hist: compact table, slot bg_off[l] >> 1
+    int* uv_val; int* uv_cnt; int* uv_n; // kde / empirical: distinct values, slot bg_off[l]
+    int* status;
+    int* g_cnt; long long max_range;     // per-CTA global counters for value ranges > FIT_SMEM_RANGE
+};
 
-    for (long long l = blockIdx.x; l < n_lnc; l += gridDim.x) {
-        const long long b0 = bg_off[l];
-        const long long n = bg_off[l + 1] - b0;
-        const int* x = bg + b0;
-        const long long B = n / 2;
-        const long long tbase = b0 >> 1;           // table slot of this lncRNA (capacity >= B)
-        // ---- min / max -------------------------------------------------------------------
+// status 4 = value range larger than the counting scratch (max_range)
+__global__ void __launch_bounds__(FIT_THREADS)
+k_fit(FitArgs A)
+{
+    __shared__ int s_cnt[FIT_SMEM_RANGE];
+    __shared__ int s_k[FIT_SMEM_NNZ];        // distinct value (then bin index)
+    __shared__ int s_c[FIT_SMEM_NNZ];        // multiplicity (then bin count)
+    __shared__ double s_t[FIT_SMEM_NNZ];     // term / cumulative
+    __shared__ int s_red_i[2 * (FIT_THREADS / 32)];
+    __shared__ double s_red[FIT_THREADS / 32];
+    __shared__ int s_scan[FIT_THREADS / 32 + 2];
+    __shared__ int s_mn, s_mx, s_bad, s_nnz;
+    __shared__ double s_S;
+    const int tid = threadIdx.x;
+    const double NaN = __longlong_as_double(0x7ff8000000000000ll);
+
+    for (long long l = blockIdx.x; l < A.n_lnc; l += gridDim.x) {
+        const long long b0 = A.bg_off[l];
+        const long long n = A.bg_off[l + 1] - b0;
+        const int* x = A.bg + b0;
+        // ---- min / max (first pass over the background) -------------------------------------
         int mn = INT32_MAX, mx = INT32_MIN;
-        for (long long i = tid; i < n; i += FIT_THREADS) { int v = x[i]; mn = min(mn, v); mx = max(mx, v); }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            mn = min(mn, __shfl_xor_sync(FULL_MASK, mn, d));
-            mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, d));
+        {
+            // 16-byte vector loads over the aligned middle part
+            long long head = ((4 - (b0 & 3)) & 3); if (head > n) head = n;
+            for (long long i = tid; i < head; i += FIT_THREADS) { int v = x[i]; mn = min(mn, v); mx = max(mx, v); }
+            const int4* x4 = reinterpret_cast<const int4*>(x + head);
+            const long long n4 = (n - head) >> 2;
+            for (long long i = tid; i < n4; i += FIT_THREADS) {
+                int4 v = x4[i];
+                mn = min(min(mn, v.x), min(v.y, min(v.z, v.w)));
+                mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
+            }
+            for (long long i = head + (n4 << 2) + tid; i < n; i += FIT_THREADS) { int v = x[i]; mn = min(mn, v); mx = max(mx, v); }
         }
-        if (lane_id() == 0) { s_red[warp_id()] = mn; s_red[FIT_THREADS / 32 + warp_id()] = mx; }
-        if (tid == 0) s_bad = 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { mn = min(mn, __shfl_xor_sync(FULL_MASK, mn, d)); mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, d)); }
+        if (lane_id() == 0) { s_red_i[warp_id()] = mn; s_red_i[FIT_THREADS / 32 + warp_id()] = mx; }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 0; w < FIT_THREADS / 32; ++w) { mn = min(mn, s_red[w]); mx = max(mx, s_red[FIT_THREADS / 32 + w]); }
-            LncFit f;
-            f.first = (double)mn; f.last = (double)mx;
-            if (mn == mx) { f.first = __dsub_rn(f.first, 0.5); f.last = __dadd_rn(f.last, 0.5); }
-            f.denom = __dsub_rn(f.last, f.first);
-            f.B = B;
-            f.step = B > 0 ? __ddiv_rn(f.denom, (double)B) : 0.0;
-            f.tbl_n = 0; f.pad = 0;
-            s_fit = f;
+            for (int w = 0; w < FIT_THREADS / 32; ++w) { mn = min(mn, s_red_i[w]); mx = max(mx, s_red_i[FIT_THREADS / 32 + w]); }
+            s_mn = mn; s_mx = mx; s_bad = 0;
         }
         __syncthreads();
-        const LncFit f = s_fit;
-        if (B < 1) {                                  // cannot happen after the reference's patches
-            if (tid == 0) { thr[l] = __longlong_as_double(0x7ff8000000000000ll); fits[l] = f; status[l] = 3; }
+        mn = s_mn; mx = s_mx;
+        const long long R = (long long)mx - (long long)mn + 1;
+        const long long B = n / 2;
+        if ((R > A.max_range && R > FIT_SMEM_RANGE) || (A.fitter == 0 && B < 1)) {
+            if (tid == 0) {
+                A.thr[l] = NaN; A.status[l] = (B < 1 && A.fitter == 0) ? 3 : 4;
+                if (A.fitter == 0) { LncFit f{}; A.fits[l] = f; } else A.uv_n[l] = 0;
+            }
             __syncthreads();
             continue;
         }
-        // np.histogram raises "Too many bins for data range" unless edges strictly increase
-        for (long long k = tid; k < B; k += FIT_THREADS)
-            if (!(hist_edge(k, f) < hist_edge(k + 1, f))) s_bad = 1;
-        // ---- bin counts ------------------------------------------------------------------
-        int* cnt = (B <= FIT_SMEM_BINS) ? s_cnt : (g_cnt + (long long)blockIdx.x * max_B);
-        for (long long k = tid; k < B; k += FIT_THREADS) cnt[k] = 0;
+        // ---- multiplicity of every distinct value (second pass; L2-resident for typical sizes) ----
+        int* cnt = (R <= FIT_SMEM_RANGE) ? s_cnt : (A.g_cnt + (long long)blockIdx.x * A.max_range);
+        for (long long k = tid; k < R; k += FIT_THREADS) cnt[k] = 0;
+        __syncthreads();
+        for (long long i0 = 0; i0 < n; i0 += FIT_THREADS) {
+            long long i = i0 + tid;
+            bool valid = i < n;
+            unsigned m = __ballot_sync(FULL_MASK, valid);
+            if (valid) {
+                int c = x[i] - mn;
+                unsigned peers = __match_any_sync(m, c);
+                if ((peers & lanemask_lt()) == 0) atomicAdd(&cnt[c], __popc(peers));
+            }
+        }
+        __syncthreads();
+        // ---- compact to (value, count), ascending ------------------------------------------------
+        // staged in shared memory when they fit, else directly in the lncRNA's global slot
+        int* uval = A.fitter == 0 ? nullptr : A.uv_val + b0;
+        int* ucnt = A.fitter == 0 ? nullptr : A.uv_cnt + b0;
+        int nv = 0;
+        bool overflow = false;
+        for (long long k0 = 0; k0 < R; k0 += FIT_THREADS) {
+            long long k = k0 + tid;
+            int c = k < R ? cnt[k] : 0;
+            int tot;
+            int pos = cta_exclusive_scan(c != 0, s_scan, &tot);
+            if (c != 0) {
+                int p = nv + pos;
+                if (p < FIT_SMEM_NNZ) { s_k[p] = (int)(mn + k); s_c[p] = c; }
+                if (uval) { uval[p] = (int)(mn + k); ucnt[p] = c; }
+            }
+            nv += tot;
+            __syncthreads();
+        }
+        if (nv > FIT_SMEM_NNZ) overflow = true;
+        if (A.fitter == 0 && overflow) {
+            // more distinct values than the staging area: not reachable with BLAST scores; report
+            if (tid == 0) { A.thr[l] = NaN; A.status[l] = 4; LncFit f{}; A.fits[l] = f; }
+            __syncthreads();
+            continue;
+        }
+        if (A.fitter == 1) {
+            int err = 0;
+            const double fac = A.kde_factor[l];
+            const int* v = overflow ? uval : s_k; const int* c = overflow ? ucnt : s_c;
+            double r = brentq_cta((double)mn, (double)mx, A.alpha, v, c, nv, fac, (double)n, s_red, &err);
+            int st = 0;
+            if (err == -1) {        // ValueError branch of inverse_approximate_collection (fitting.py:240-241)
+                double fb = fabs(kde_sf_cta((double)mx, v, c, nv, fac, (double)n, s_red) - A.alpha);
+                double fa = fabs(kde_sf_cta((double)mn, v, c, nv, fac, (double)n, s_red) - A.alpha);
+                r = fb < fa ? (double)mx : (double)mn;
+            } else if (err == -2) st = 2;
+            if (tid == 0) { A.thr[l] = r; A.uv_n[l] = nv; A.status[l] = st; }
+            __syncthreads();
+            continue;
+        }
+        if (A.fitter == 2) {
+            if (tid == 0) {
+                // isf = sorted[ceil((1-alpha)*n) - 1]; suffix counts #{bg >= val[i]} replace the counts
+                long long k = (long long)ceil((1.0 - A.alpha) * (double)n) - 1;
+                if (k < 0) k = 0;
+                if (k > n - 1) k = n - 1;
+                long long acc = 0; int t = 0;
+                for (int i = 0; i < nv; ++i) { t = i; if (acc + ucnt[i] > k) break; acc += ucnt[i]; }
+                A.thr[l] = (double)uval[t];
+                long long suf = 0;
+                for (int i = nv - 1; i >= 0; --i) { suf += ucnt[i]; ucnt[i] = (int)suf; }
+                A.uv_n[l] = nv; A.status[l] = 0;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- histogram fitter ------------------------------------------------------------------------
+        LncFit f;
+        f.first = (double)mn; f.last = (double)mx;
+        if (mn == mx) { f.first = __dsub_rn(f.first, 0.5); f.last = __dadd_rn(f.last, 0.5); }
+        f.denom = __dsub_rn(f.last, f.first);
+        f.B = B;
+        f.step = __ddiv_rn(f.denom, (double)B);
+        f.tbl_n = 0; f.pad = 0;
+        // np.histogram raises "Too many bins for data range" unless the edges strictly increase.
+        // step > 8 ulp(max |edge|) guarantees it (each edge carries <= 1.5 ulp of rounding); only
+        // otherwise is the O(B) check needed.
+        {
+            double amax = fmax(fabs(f.first), fabs(f.last));
+            if (!(f.step > amax * 1.7763568394002505e-15)) {
+                for (long long k = tid; k < B; k += FIT_THREADS)
+                    if (!(hist_edge(k, f) < hist_edge(k + 1, f))) s_bad = 1;
+            }
+        }
+        // bin index of every distinct value (np.histogram uniform-bin path incl. its fix-ups)
         __syncthreads();
         if (s_bad) {
-            if (tid == 0) { thr[l] = __longlong_as_double(0x7ff8000000000000ll); fits[l] = f; status[l] = 3; }
+            if (tid == 0) { A.thr[l] = NaN; A.fits[l] = f; A.status[l] = 3; }
             __syncthreads();
             continue;
         }
-        for (long long i = tid; i < n; i += FIT_THREADS) {
-            double v = (double)x[i];
+        for (int i = tid; i < nv; i += FIT_THREADS) {
+            double v = (double)s_k[i];
             double g = __dmul_rn(__ddiv_rn(__dsub_rn(v, f.first), f.denom), (double)B);
             long long idx = (long long)g;
             if (idx == B) idx -= 1;
             if (v < hist_edge(idx, f)) idx -= 1;
             if (v >= hist_edge(idx + 1, f) && idx != B - 1) idx += 1;
-            atomicAdd(&cnt[idx], 1);
+            s_k[i] = (int)idx;            // value -> bin index (non-decreasing in i)
         }
         __syncthreads();
-        // ---- normaliser: numpy pairwise sum over the B terms ---------------------------------
-        const double total = (double)n;
-        PwNode* leaf = (B <= (long long)FIT_SMEM_LEAVES * 64) ? s_leaf : (g_leaf + (long long)blockIdx.x * max_leaves);
-        double* leaf_sum = (B <= (long long)FIT_SMEM_LEAVES * 64) ? s_leaf_sum : (g_leaf_sum + (long long)blockIdx.x * max_leaves);
-        if (tid == 0) {
-            // enumerate the leaves of the recursion (n <= 128) left to right
-            PwNode stack[64];
-            int sp = 0; long long nl = 0;
-            stack[sp++] = PwNode{0, B};
-            while (sp > 0) {
-                PwNode nd = stack[--sp];
-                if (nd.n <= 128) { leaf[nl++] = nd; }
-                else {
-                    long long n2 = nd.n / 2; n2 -= n2 % 8;
-                    stack[sp++] = PwNode{nd.off + n2, nd.n - n2};   // right first: left pops first
-                    stack[sp++] = PwNode{nd.off, n2};
-                }
-            }
-            s_nleaf = nl;
-        }
-        __syncthreads();
-        const long long nleaf = s_nleaf;
-        for (long long q = tid; q < nleaf; q += FIT_THREADS)
-            leaf_sum[q] = fit_leaf_sum(cnt, leaf[q].off, leaf[q].n, f, total);
-        __syncthreads();
-        if (tid == 0) {
-            // combine the leaf sums in the recursion's order: post-order walk with a value stack
-            struct Fr { long long off, n; int state; };
-            Fr st[64]; double vs[64];
-            int sp = 0, vp = 0; long long next_leaf = 0;
-            st[sp++] = Fr{0, B, 0};
-            while (sp > 0) {
-                Fr& t = st[sp - 1];
-                if (t.n <= 128) { vs[vp++] = leaf_sum[next_leaf++]; --sp; continue; }
-                long long n2 = t.n / 2; n2 -= n2 % 8;
-                if (t.state == 0) { t.state = 1; st[sp++] = Fr{t.off, n2, 0}; }
-                else if (t.state == 1) { t.state = 2; st[sp++] = Fr{t.off + n2, t.n - n2, 0}; }
-                else { double b = vs[--vp]; double a = vs[--vp]; vs[vp++] = __dadd_rn(a, b); --sp; }
-            }
-            s_S = vs[0];
-        }
-        __syncthreads();
-        const double S = s_S;
-        // ---- compact the non-empty bins, in bin order ------------------------------------------
+        // merge distinct values that share a bin: head flags -> bin slots
         int nnz = 0;
-        for (long long k0 = 0; k0 < B; k0 += FIT_THREADS) {
-            long long k = k0 + tid;
-            int c = (k < B) ? cnt[k] : 0;
+        for (int i0 = 0; i0 < nv; i0 += FIT_THREADS) {
+            int i = i0 + tid;
+            bool head = i < nv && (i == 0 || s_k[i] != s_k[i - 1]);
             int tot;
-            int pos = cta_exclusive_scan(c != 0, s_scan, &tot);
-            if (c != 0) {
-                // c_k = hpdf_k * w_k with hpdf_k = hp0_k / S
-                double w = __dsub_rn(hist_edge(k + 1, f), hist_edge(k, f));
-                double dens = __ddiv_rn(__ddiv_rn((double)c, w), total);
-                double hp0 = __ddiv_rn(dens, w);
-                double hpdf = __ddiv_rn(hp0, S);
-                tbl_k[tbase + nnz + pos] = (int)k;
-                tbl_cum[tbase + nnz + pos] = __dmul_rn(hpdf, w);
+            int pos = cta_exclusive_scan(head ? 1 : 0, s_scan, &tot);
+            // slot of element i = (number of heads up to and including i) - 1
+            int slot = nnz + pos + (head ? 1 : 0) - 1;
+            int kk = i < nv ? s_k[i] : 0, cc = i < nv ? s_c[i] : 0;
+            __syncthreads();                       // everyone has read s_k/s_c of this chunk
+            if (i < nv) {
+                if (head) { s_k[slot] = kk; s_c[slot] = 0; }
             }
+            __syncthreads();
+            if (i < nv) atomicAdd(&s_c[slot], cc);
             nnz += tot;
             __syncthreads();
         }
-        // ---- np.cumsum (sequential) + isf ---------------------------------------------------------
+        // terms of the normaliser, then S = np.sum(hp0*w) (pairwise), then c_k = (hp0/S)*w
+        const double total = (double)n;
+        for (int t = tid; t < nnz; t += FIT_THREADS) {
+            double hp0, w;
+            s_t[t] = fit_term(s_c[t], s_k[t], f, total, &hp0, &w);
+        }
+        __syncthreads();
+        if (tid == 0) s_S = sparse_pairwise_sum(s_k, s_t, nnz, B);
+        __syncthreads();
+        const double S = s_S;
+        for (int t = tid; t < nnz; t += FIT_THREADS) {
+            double hp0, w;
+            fit_term(s_c[t], s_k[t], f, total, &hp0, &w);
+            s_t[t] = __dmul_rn(__ddiv_rn(hp0, S), w);
+        }
+        __syncthreads();
         if (tid == 0) {
+            // np.cumsum: sequential left to right
             double acc = 0.0;
-            for (int t = 0; t < nnz; ++t) { acc = __dadd_rn(acc, tbl_cum[tbase + t]); tbl_cum[tbase + t] = acc; }
+            for (int t = 0; t < nnz; ++t) { acc = __dadd_rn(acc, s_t[t]); s_t[t] = acc; }
+            // isf(alpha) = np.interp(1 - alpha, hcdf, hbins)
             double r;
+            const double alpha = A.alpha;
             if (alpha == 1.0) r = f.first;
             else if (alpha == 0.0) r = f.last;
-            else if (!(alpha > 0.0 && alpha < 1.0)) r = __longlong_as_double(0x7ff8000000000000ll);
+            else if (!(alpha > 0.0 && alpha < 1.0)) r = NaN;
             else {
                 double y = __dsub_rn(1.0, alpha);
-                // first table entry with cum > y
-                int lo = 0, hi = nnz;
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (tbl_cum[tbase + mid] > y) hi = mid; else lo = mid + 1; }
-                if (lo == nnz) r = f.last;             // y >= hcdf[B]
+                int lo = 0, hi = nnz;                       // first entry with cum > y
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (s_t[mid] > y) hi = mid; else lo = mid + 1; }
+                if (lo == nnz) r = f.last;                 // y >= hcdf[B]
                 else {
-                    long long j = tbl_k[tbase + lo];
-                    double c0 = lo > 0 ? tbl_cum[tbase + lo - 1] : 0.0, c1 = tbl_cum[tbase + lo];
+                    long long j = s_k[lo];
+                    double c0 = lo > 0 ? s_t[lo - 1] : 0.0, c1 = s_t[lo];
                     double xj = hist_edge(j, f);
                     if (c0 == y) r = xj;
                     else {
@@ -220,11 +412,14 @@ k_fit_hist(long long n_lnc, const long long* __restrict__ bg_off, const int* __r
                     }
                 }
             }
-            thr[l] = r;
+            A.thr[l] = r;
             LncFit fo = f; fo.tbl_n = nnz;
-            fits[l] = fo;
-            status[l] = 0;
+            A.fits[l] = fo;
+            A.status[l] = 0;
         }
+        __syncthreads();
+        const long long tbase = b0 >> 1;                   // table slot (capacity >= B >= nnz)
+        for (int t = tid; t < nnz; t += FIT_THREADS) { A.tbl_k[tbase + t] = s_k[t]; A.tbl_cum[tbase + t] = s_t[t]; }
         __syncthreads();
     }
 }

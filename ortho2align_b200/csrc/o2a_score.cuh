@@ -1,55 +1,26 @@
-// o2a_score.cuh — K3+K4+K5: the streaming kernel of the path (the only stage that touches every HSP).
+// o2a_score.cuh — K3 (streaming score filter) and K4+K5 (p-values, rank, q, keep).
 //
-// One CTA per alignment (= lncRNA x syntenic region, the scope of the reference's multiple-testing
-// step, pipeline.py:763-776):
-//   filter_by_score(isf(alpha))  strict '>'                       alignment.py:618-646, pipeline.py:765
-//   pvals = background.sf(scores of survivors)                     pipeline.py:766
-//   fdr:  q = (m * p) / rank(p),  keep q <= alpha  (no cummin)      fitting.py:359-364, pipeline.py:769-776
-// Scores are read once with coalesced 128-bit loads; survivors are compacted IN ORDER (ballot +
-// CTA scan) into the alignment's slot [hsp_off[a], hsp_off[a]+n_surv) of the survivor arrays, so no
-// global scan is needed and only survivors cost write traffic. Ranks use the build's tie policy:
-// stable (ties keep HSP order) — SURVEY.md §8a row 7.
+// k_filter — the only stage that touches every HSP; HBM-bound. One CTA per alignment
+//   (= lncRNA x syntenic region): filter_by_score(isf(alpha)), strict '>'
+//   (alignment.py:618-646, pipeline.py:765). Scores are read once with coalesced 128-bit loads and
+//   the survivors (position + score) are compacted IN ORDER (ballot + CTA scan) into the
+//   alignment's slot [hsp_off[a], hsp_off[a]+n_surv) of the survivor arrays: no global scan, and
+//   only survivors cost write traffic.
+// k_pq — per alignment, on the ~7 % that survived: pvals = background.sf(scores) (pipeline.py:766);
+//   fdr: q = (m*p)/rank(p), keep q <= alpha, no cummin (fitting.py:359-364, pipeline.py:769-776).
+//   Ranks use the build's tie policy: stable (ties keep HSP order) — SURVEY.md §8a row 7.
 #pragma once
 #include "o2a_device.cuh"
+#include "o2a_fit.cuh"
 
 namespace o2a {
 
-constexpr int SCORE_THREADS = 256;
-constexpr int SCORE_ROWS = 4;                        // double2 per thread per row
-constexpr int SCORE_TILE = SCORE_THREADS * 2 * SCORE_ROWS;
-constexpr int RANK_SMALL_MAX = 1024;                 // survivors ranked inside the streaming kernel
+constexpr int FILTER_THREADS = 256;
+constexpr int FILTER_ROWS = 4;                       // double2 per thread per row
+constexpr int FILTER_TILE = FILTER_THREADS * 2 * FILTER_ROWS;
+constexpr int PQ_THREADS = 128;
+constexpr int RANK_SMALL_MAX = 1024;                 // survivors ranked in shared memory
 constexpr int TBL_SMEM_MAX = 256;
-
-struct ScoreArgs {
-    long long n_aln;
-    const long long* hsp_off;
-    const int* aln_lnc;
-    const double* score;
-    const double* thr;
-    const int* lnc_status;
-    // hist
-    const LncFit* fits;
-    const int* tbl_k;
-    const double* tbl_cum;
-    const long long* bg_off;
-    // kde / empirical (compressed background: distinct values + counts, see o2a_kde.cuh)
-    const int* uv_val;
-    const int* uv_cnt;          // kde: multiplicities; empirical: #{bg > value} suffix counts
-    const int* uv_n;
-    const double* kde_factor;
-    int fitter;
-    int fdr;
-    double alpha;
-    // outputs (slot layout)
-    int* n_surv;
-    int* n_keep;
-    int* surv_idx;
-    double* surv_p;
-    double* surv_pq;
-    unsigned char* surv_keep;
-    int* big_list;              // alignments whose survivors exceed RANK_SMALL_MAX (fdr only)
-    int* big_count;
-};
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double* p)
 {
@@ -58,52 +29,104 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double* p)
     return r;
 }
 
-// ndtr(z) = 0.5*erfc(-z/sqrt2): scipy.special.ndtr is cephes-derived and not bit-reproducible with
-// CUDA's erfc (<= 2.3e-16 absolute apart) — KDE parity is to tolerance.
-__device__ __forceinline__ double ndtr_dev(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
-
-// KernelFitter.sf (fitting.py:282-310) on the value-compressed background:
-// cdf = sum_v cnt_v * ndtr((x - v)/factor) / n
-__device__ double kde_sf_compressed(double x, const int* __restrict__ val, const int* __restrict__ cnt, int nv,
-                                    double factor, double n)
+__global__ void __launch_bounds__(FILTER_THREADS, 6)
+k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __restrict__ aln_lnc,
+         const double* __restrict__ score, const double* __restrict__ thr, const int* __restrict__ lnc_status,
+         int* __restrict__ n_surv, int* __restrict__ surv_idx, double* __restrict__ surv_x)
 {
-    double acc = 0.0;
-    for (int i = 0; i < nv; ++i) acc += (double)cnt[i] * ndtr_dev((x - (double)val[i]) / factor);
-    return 1.0 - acc / n;
+    __shared__ int s_cnt[FILTER_ROWS][FILTER_THREADS / 32];
+    const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    constexpr int NW = FILTER_THREADS / 32;
+
+    for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
+        const int l = aln_lnc[a];
+        const long long h0 = hsp_off[a];
+        const int m = (int)(hsp_off[a + 1] - h0);
+        if (lnc_status[l] != 0) {                     // fit failed: the reference raised before the loop
+            if (tid == 0) n_surv[a] = 0;
+            continue;
+        }
+        const double t = thr[l];
+        const double* sc = score + h0;
+        const bool aligned16 = ((h0 & 1) == 0);       // score + h0 is 16-byte aligned
+        int base = 0;
+        for (int t0 = 0; t0 < m; t0 += FILTER_TILE) {
+            double2 v[FILTER_ROWS];
+            unsigned flag = 0;                        // per row: 2 flag bits + 6 "before" bits
+#pragma unroll
+            for (int r = 0; r < FILTER_ROWS; ++r) {
+                int e = t0 + (r * FILTER_THREADS + tid) * 2;
+                if (aligned16 && e + 1 < m) v[r] = ld_stream_f64x2(sc + e);
+                else {
+                    v[r].x = e < m ? sc[e] : 0.0;
+                    v[r].y = e + 1 < m ? sc[e + 1] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < FILTER_ROWS; ++r) {
+                int e = t0 + (r * FILTER_THREADS + tid) * 2;
+                bool fx = (e < m) && (v[r].x > t);
+                bool fy = (e + 1 < m) && (v[r].y > t);
+                unsigned bx = __ballot_sync(FULL_MASK, fx), by = __ballot_sync(FULL_MASK, fy);
+                if (lane == 0) s_cnt[r][w] = __popc(bx) + __popc(by);
+                // survivors of this warp-row before me, in element order (x0 y0 x1 y1 ...)
+                int before = __popc(bx & lanemask_lt()) + __popc(by & lanemask_lt());
+                flag |= ((fx ? 1u : 0u) | (fy ? 2u : 0u) | ((unsigned)before << 2)) << (8 * r);
+            }
+            __syncthreads();
+            int tile_total = 0;
+#pragma unroll
+            for (int r = 0; r < FILTER_ROWS; ++r) {
+                int row_before = 0, row_total = 0;
+#pragma unroll
+                for (int ww = 0; ww < NW; ++ww) { int c = s_cnt[r][ww]; row_before += (ww < w) ? c : 0; row_total += c; }
+                const unsigned fr = (flag >> (8 * r)) & 0xffu;
+                if (fr & 3u) {
+                    long long pos = h0 + base + tile_total + row_before + (int)(fr >> 2);
+                    int e = t0 + (r * FILTER_THREADS + tid) * 2;
+                    if (fr & 1u) { surv_idx[pos] = e; surv_x[pos] = v[r].x; ++pos; }
+                    if (fr & 2u) { surv_idx[pos] = e + 1; surv_x[pos] = v[r].y; }
+                }
+                tile_total += row_total;
+            }
+            base += tile_total;
+            __syncthreads();
+        }
+        if (tid == 0) n_surv[a] = base;
+    }
 }
 
-// empirical sf (extension): #{bg > x}/n from the sorted distinct values + suffix counts
-__device__ double emp_sf_compressed(double x, const int* __restrict__ val, const int* __restrict__ gt, int nv, double n)
-{
-    int lo = 0, hi = nv;                              // first distinct value > x
-    while (lo < hi) { int mid = (lo + hi) >> 1; if ((double)val[mid] > x) hi = mid; else lo = mid + 1; }
-    double c = lo < nv ? (double)(gt[lo]) : 0.0;      // gt[i] = #{bg >= val[i]}
-    return c / n;
-}
+struct PqArgs {
+    long long n_aln;
+    const long long* hsp_off;
+    const int* aln_lnc;
+    const int* lnc_status;
+    const int* n_surv;
+    // hist
+    const LncFit* fits; const int* tbl_k; const double* tbl_cum; const long long* bg_off;
+    // kde / empirical
+    const int* uv_val; const int* uv_cnt; const int* uv_n; const double* kde_factor;
+    int fitter; int fdr; double alpha;
+    double* surv_p;            // in: survivor scores (written by k_filter); out: p-values
+    double* surv_pq; unsigned char* surv_keep; int* n_keep;
+    int* big_list; int* big_count;
+};
 
-__global__ void __launch_bounds__(SCORE_THREADS)
-k_score(ScoreArgs A)
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pq(PqArgs A)
 {
     __shared__ double s_p[RANK_SMALL_MAX];
     __shared__ int s_tk[TBL_SMEM_MAX];
     __shared__ double s_tc[TBL_SMEM_MAX];
-    __shared__ int s_cnt[SCORE_ROWS][SCORE_THREADS / 32];
-    __shared__ int s_base;
     __shared__ int s_keepcnt;
-    const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
-    constexpr int NW = SCORE_THREADS / 32;
+    const int tid = threadIdx.x, lane = lane_id();
 
     for (long long a = blockIdx.x; a < A.n_aln; a += gridDim.x) {
+        const int ns = A.n_surv[a];
+        if (ns == 0) { if (tid == 0) A.n_keep[a] = 0; continue; }
         const int l = A.aln_lnc[a];
         const long long h0 = A.hsp_off[a];
         const int m = (int)(A.hsp_off[a + 1] - h0);
-        if (A.lnc_status[l] != 0) {                   // fit failed: the reference raised before the loop
-            if (tid == 0) { A.n_surv[a] = 0; A.n_keep[a] = 0; }
-            continue;
-        }
-        const double thr = A.thr[l];
-        const double* sc = A.score + h0;
-        // fitter state
         LncFit f; const int* tk = nullptr; const double* tc = nullptr;
         const int* uval = nullptr; const int* ucnt = nullptr; int unv = 0; double kfac = 1.0, nbg = 1.0;
         if (A.fitter == 0) {
@@ -111,7 +134,7 @@ k_score(ScoreArgs A)
             const long long tb = A.bg_off[l] >> 1;
             tk = A.tbl_k + tb; tc = A.tbl_cum + tb;
             if (f.tbl_n <= TBL_SMEM_MAX) {
-                for (int t = tid; t < f.tbl_n; t += SCORE_THREADS) { s_tk[t] = tk[t]; s_tc[t] = tc[t]; }
+                for (int t = tid; t < f.tbl_n; t += PQ_THREADS) { s_tk[t] = tk[t]; s_tc[t] = tc[t]; }
                 tk = s_tk; tc = s_tc;
             }
         } else {
@@ -120,74 +143,37 @@ k_score(ScoreArgs A)
             nbg = (double)(A.bg_off[l + 1] - b0);
             if (A.fitter == 1) kfac = A.kde_factor[l];
         }
-        if (tid == 0) { s_base = 0; s_keepcnt = 0; }
+        if (tid == 0) s_keepcnt = 0;
         __syncthreads();
-        const bool aligned16 = ((h0 & 1) == 0);       // score + h0 is 16-byte aligned
-        for (int t0 = 0; t0 < m; t0 += SCORE_TILE) {
-            double2 v[SCORE_ROWS];
-            unsigned flag = 0;                        // 2 bits per row
-#pragma unroll
-            for (int r = 0; r < SCORE_ROWS; ++r) {
-                int e = t0 + (r * SCORE_THREADS + tid) * 2;
-                if (aligned16 && e + 1 < m) v[r] = ld_stream_f64x2(sc + e);
-                else {
-                    v[r].x = e < m ? sc[e] : 0.0;
-                    v[r].y = e + 1 < m ? sc[e + 1] : 0.0;
-                }
-                bool fx = (e < m) && (v[r].x > thr);
-                bool fy = (e + 1 < m) && (v[r].y > thr);
-                unsigned bx = __ballot_sync(FULL_MASK, fx), by = __ballot_sync(FULL_MASK, fy);
-                if (lane == 0) s_cnt[r][w] = __popc(bx) + __popc(by);
-                // survivors of this warp-row before me, in element order (x0 y0 x1 y1 ...)
-                int before = __popc(bx & lanemask_lt()) + __popc(by & lanemask_lt());
-                flag |= (fx ? 1u : 0u) << (2 * r);
-                flag |= (fy ? 1u : 0u) << (2 * r + 1);
-                flag |= (unsigned)before << (8 + 6 * r);   // before <= 62 fits 6 bits
-            }
-            __syncthreads();
-            const int base = s_base;
-            int tile_total = 0;
-#pragma unroll
-            for (int r = 0; r < SCORE_ROWS; ++r) {
-                int row_before = 0, row_total = 0;
-#pragma unroll
-                for (int ww = 0; ww < NW; ++ww) { int c = s_cnt[r][ww]; if (ww < w) row_before += c; row_total += c; }
-                int pos = base + tile_total + row_before + (int)((flag >> (8 + 6 * r)) & 63u);
-                int e = t0 + (r * SCORE_THREADS + tid) * 2;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if ((flag >> (2 * r + c)) & 1u) {
-                        double x = c ? v[r].y : v[r].x;
-                        double p;
-                        if (A.fitter == 0) p = hist_sf(x, f, tk, tc);
-                        else if (A.fitter == 1) p = kde_sf_compressed(x, uval, ucnt, unv, kfac, nbg);
-                        else p = emp_sf_compressed(x, uval, ucnt, unv, nbg);
-                        A.surv_idx[h0 + pos] = e + c;
-                        A.surv_p[h0 + pos] = p;
-                        if (pos < RANK_SMALL_MAX) s_p[pos] = p;
-                        ++pos;
-                    }
-                }
-                tile_total += row_total;
-            }
-            __syncthreads();
-            if (tid == 0) s_base = base + tile_total;
-            __syncthreads();
+        for (int k = tid; k < ns; k += PQ_THREADS) {
+            const double x = A.surv_p[h0 + k];
+            double p;
+            if (A.fitter == 0) p = hist_sf(x, f, tk, tc);
+            else if (A.fitter == 1) p = kde_sf_compressed(x, uval, ucnt, unv, kfac, nbg);
+            else p = emp_sf_compressed(x, uval, ucnt, unv, nbg);
+            A.surv_p[h0 + k] = p;
+            if (k < RANK_SMALL_MAX) s_p[k] = p;
+            if (!A.fdr) { A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1; }   // pipeline.py:778-780
         }
-        const int ns = s_base;
-        if (!A.fdr) {                                 // pipeline.py:778-780: hsp.pval = p, nothing dropped
-            for (int k = tid; k < ns; k += SCORE_THREADS) {
-                A.surv_pq[h0 + k] = (k < RANK_SMALL_MAX) ? s_p[k] : A.surv_p[h0 + k];
-                A.surv_keep[h0 + k] = 1;
-            }
-            if (tid == 0) { A.n_surv[a] = ns; A.n_keep[a] = ns; }
-        } else if (ns <= RANK_SMALL_MAX) {
+        if (!A.fdr) {
+            if (tid == 0) A.n_keep[a] = ns;
+            __syncthreads();
+            continue;
+        }
+        __syncthreads();
+        if (ns <= RANK_SMALL_MAX) {
             const double md = (double)m;              // total_hsps = len(alignment._all_HSPs)
             int kept = 0;
-            for (int k = tid; k < ns; k += SCORE_THREADS) {
+            for (int k = tid; k < ns; k += PQ_THREADS) {
                 const double p = s_p[k];
                 int rank = 1;
-                for (int j = 0; j < ns; ++j) { double pj = s_p[j]; rank += (pj < p) || (pj == p && j < k); }
+                int j = 0;
+                for (; j + 1 < ns; j += 2) {
+                    double p0 = s_p[j], p1 = s_p[j + 1];
+                    rank += (p0 < p) || (p0 == p && j < k);
+                    rank += (p1 < p) || (p1 == p && j + 1 < k);
+                }
+                if (j < ns) { double p0 = s_p[j]; rank += (p0 < p) || (p0 == p && j < k); }
                 double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);
                 bool keep = q <= A.alpha;
                 A.surv_pq[h0 + k] = q;
@@ -198,13 +184,11 @@ k_score(ScoreArgs A)
             for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(FULL_MASK, kept, d);
             if (lane == 0 && kept) atomicAdd(&s_keepcnt, kept);
             __syncthreads();
-            if (tid == 0) { A.n_surv[a] = ns; A.n_keep[a] = s_keepcnt; }
-        } else {
-            if (tid == 0) {
-                A.n_surv[a] = ns; A.n_keep[a] = 0;
-                int slot = atomicAdd(A.big_count, 1);
-                A.big_list[slot] = (int)a;
-            }
+            if (tid == 0) A.n_keep[a] = s_keepcnt;
+        } else if (tid == 0) {
+            A.n_keep[a] = 0;
+            int slot = atomicAdd(A.big_count, 1);
+            A.big_list[slot] = (int)a;
         }
         __syncthreads();
     }

@@ -74,7 +74,7 @@ def test_kde_vs_oracle(engine):
     b = synth.workload(2, n_lnc=12, seed=9, hsps_per_region=400, n_bg=3000)
     exp = O.build_batch(b, "kde", True)
     got = engine.build_batch(b, "kde", True)
-    compare_results(got, exp, exact_p=False, what="kde")
+    compare_results(got, exp, exact_p=False, what="kde", m_max=float(np.diff(b.hsp_off).max()))
 
 
 def test_dense_chaining_and_big_rank_vs_oracle(engine):
