@@ -171,23 +171,25 @@ __device__ double best_key_of_chain(const ChainArgs& A, long long h0, const int*
 }
 
 // Warp path: one warp per alignment with at most CHAIN_WARP_MAX retained HSPs (the common case:
-// ~10-20 retained of ~130 survivors). Everything lives in the warp's slice of shared memory;
-// lane i owns HSP i; the push DP walks the vertices in list order with the lanes on the window.
+// ~10-20 retained of ~130 survivors). Everything lives in the warp's slice of shared memory, the
+// begin/end sentinels are stored as ordinary vertices (64-bit coordinates), lane i owns vertex i;
+// the push DP walks the vertices in list order with the lanes on the window.
 constexpr int CHAINW_WARPS = 4;
 
 __global__ void __launch_bounds__(CHAINW_WARPS * 32)
 k_chain_warp(ChainArgs A)
 {
-    constexpr int C = CHAIN_WARP_MAX;
-    __shared__ int s_qs[CHAINW_WARPS][C], s_qe[CHAINW_WARPS][C], s_ss[CHAINW_WARPS][C], s_se[CHAINW_WARPS][C], s_id[CHAINW_WARPS][C];
-    __shared__ double s_sc[CHAINW_WARPS][C];
-    __shared__ double s_total[CHAINW_WARPS][C + 2];
-    __shared__ int s_prev[CHAINW_WARPS][C + 2], s_f[CHAINW_WARPS][C + 2];
+    constexpr int C = CHAIN_WARP_MAX, V = CHAIN_WARP_MAX + 2;
+    __shared__ long long s_qs[CHAINW_WARPS][V], s_qe[CHAINW_WARPS][V], s_ss[CHAINW_WARPS][V], s_se[CHAINW_WARPS][V];
+    __shared__ double s_sc[CHAINW_WARPS][V], s_total[CHAINW_WARPS][V];
+    __shared__ int s_id[CHAINW_WARPS][V], s_prev[CHAINW_WARPS][V], s_f[CHAINW_WARPS][V];
     __shared__ int s_chain[CHAINW_WARPS][2][C];
     const int lane = lane_id(), w = warp_id();
     const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
     const double POS_INF = __longlong_as_double(0x7ff0000000000000ll);
     const long long nwarps_total = (long long)gridDim.x * CHAINW_WARPS;
+    long long* Qs = s_qs[w]; long long* Qe = s_qe[w]; long long* Ss = s_ss[w]; long long* Se = s_se[w];
+    double* Sc = s_sc[w]; double* Tot = s_total[w]; int* Id = s_id[w]; int* Prev = s_prev[w]; int* F = s_f[w];
 
     for (long long a = (long long)blockIdx.x * CHAINW_WARPS + w; a < A.n_aln; a += nwarps_total) {
         const int r = A.n_keep[a];
@@ -196,7 +198,7 @@ k_chain_warp(ChainArgs A)
             if (lane == 0) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
             continue;
         }
-        if (r == 0 || A.lnc_status[l] == 2 || A.lnc_status[l] == 3 || A.lnc_status[l] == 4) {
+        if (r == 0 || A.lnc_status[l] >= 2) {
             if (lane == 0) {
                 A.chain_len[a] = 0; A.chain_orient[a] = 1; A.chain_score[a] = NEG_INF;
                 A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = NEG_INF; A.best_key[a] = 0.0;
@@ -209,21 +211,24 @@ k_chain_warp(ChainArgs A)
         int my_slot = -1;
         int got = 0;
         for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
-            int k = k0 + lane;
-            bool keep = (k < ns) && A.surv_keep[h0 + k];
-            unsigned b = __ballot_sync(FULL_MASK, keep);
-            // the lane whose index equals (got + rank of a kept k) takes that k
-            int want = lane - got;                       // which kept element of this chunk is mine
-            if (want >= 0 && want < __popc(b)) {
-                unsigned bb = b;
-                for (int t = 0; t < want; ++t) bb &= bb - 1;     // drop the `want` lowest set bits
-                my_slot = k0 + __ffs(bb) - 1;
-            }
+            const int k = k0 + lane;
+            const bool keep = (k < ns) && A.surv_keep[h0 + k];
+            const unsigned b = __ballot_sync(FULL_MASK, keep);
+            // the j-th kept element of this chunk goes to lane got + j
+            const int dst = got + __popc(b & lanemask_lt());
+            const int src_k = keep ? k : -1;
+            // each lane pulls from the lane holding "its" element: find the (lane-got)-th set bit of b
+            const int want = lane - got;
+            int src_lane = -1;
+            if (want >= 0 && want < __popc(b)) src_lane = __fns(b, 0, want + 1);
+            const int pulled = __shfl_sync(FULL_MASK, src_k, src_lane < 0 ? 0 : src_lane);
+            if (src_lane >= 0) my_slot = pulled;
+            (void)dst;
             got += __popc(b);
         }
         int qs = 0, qe = 0, ss = 0, se = 0; double sc = 0.0; bool dir = false; bool bad = false;
         if (lane < r) {
-            long long h = h0 + A.surv_idx[h0 + my_slot];
+            const long long h = h0 + A.surv_idx[h0 + my_slot];
             qs = A.qstart[h]; qe = A.qend[h]; ss = A.sstart[h]; se = A.send[h]; sc = A.score[h];
             dir = (se - ss > 0);                         // alignment.py:107-110
             bad = !(qe - qs > 0);                        // orientation None
@@ -236,71 +241,108 @@ k_chain_warp(ChainArgs A)
             }
             continue;
         }
-        double sco[2]; int len[2];
+        const long long qlen = A.qlen[a], slen = A.slen[a];
+        const double G = (double)A.gapopen, E = (double)A.gapextend;
+        double sco0 = NEG_INF, sco1 = NEG_INF, key0 = 0.0, key1 = 0.0; int len0 = 0, len1 = 0;
 #pragma unroll 1
         for (int o = 0; o < 2; ++o) {
             const bool want_dir = (o == 0);
             const bool mine = (lane < r) && (dir == want_dir);
             const unsigned members = __ballot_sync(FULL_MASK, mine);
             const int n_o = __popc(members);
-            if (n_o == 0) { sco[o] = NEG_INF; len[o] = 0; continue; }
+            if (n_o == 0) continue;
+            const int N = n_o + 2;
             // stable rank by (qstart, sstart, list order) among the members
             int rank = 0;
             for (unsigned mm = members; mm; mm &= mm - 1) {
-                int q = __ffs(mm) - 1;
-                int oqs = __shfl_sync(FULL_MASK, qs, q), oss = __shfl_sync(FULL_MASK, ss, q);
+                const int q = __ffs(mm) - 1;
+                const int oqs = __shfl_sync(FULL_MASK, qs, q), oss = __shfl_sync(FULL_MASK, ss, q);
                 rank += (oqs < qs) || (oqs == qs && (oss < ss || (oss == ss && q < lane)));
             }
             __syncwarp();
             if (mine) {
-                s_qs[w][rank] = qs; s_qe[w][rank] = qe; s_ss[w][rank] = ss; s_se[w][rank] = se;
-                s_sc[w][rank] = sc; s_id[w][rank] = my_slot;
+                const int v = rank + 1;
+                Qs[v] = qs; Qe[v] = qe; Ss[v] = ss; Se[v] = se; Sc[v] = sc; Id[v] = my_slot;
+            }
+            if (lane == 0) {     // sentinels: alignment.py:893-902
+                Qs[0] = 0; Qe[0] = 0; Ss[0] = want_dir ? 0 : slen; Se[0] = Ss[0]; Sc[0] = 0.0;
+                Qs[N - 1] = qlen; Qe[N - 1] = qlen; Ss[N - 1] = want_dir ? slen : 0; Se[N - 1] = Ss[N - 1]; Sc[N - 1] = 0.0;
             }
             __syncwarp();
-            ChainMem M{s_qs[w], s_qe[w], s_ss[w], s_se[w], s_sc[w], s_id[w], s_total[w], s_prev[w], s_f[w]};
-            ChainGeom g{n_o, want_dir, A.qlen[a], A.slen[a], (double)A.gapopen, (double)A.gapextend};
-            const int N = n_o + 2;
+            // HSP.precede (alignment.py:137-168); sentinel-sentinel pairs use the reverse rule (both None)
+#define O2A_PREC(i, j) ((Qe[i] < Qs[j]) && ((want_dir && !((i) == 0 && (j) == N - 1)) ? (Se[i] < Ss[j]) : (Se[i] > Ss[j])))
             // f(i): lanes 0..N-1 each scan forward from their own vertex
             for (int i = lane; i < N; i += 32) {
                 int fi = N;
-                for (int j = i + 1; j < N; ++j) if (v_prec(M, g, i, j)) { fi = j; break; }
-                M.f[i] = fi;
-                M.total[i] = i == 0 ? 0.0 : POS_INF;
-                M.prev[i] = -1;
+                for (int j = i + 1; j < N; ++j) if (O2A_PREC(i, j)) { fi = j; break; }
+                F[i] = fi;
+                Tot[i] = i == 0 ? 0.0 : POS_INF;
+                Prev[i] = -1;
             }
             __syncwarp();
             for (int i = 0; i < N - 1; ++i) {
-                const double ti = M.total[i];
-                const int fi = M.f[i];
+                const double ti = Tot[i];
+                const int fi = F[i];
                 if (fi < N && ti < POS_INF) {
-                    const int gi = M.f[fi] < N ? M.f[fi] : N;
+                    const int gi = F[fi] < N ? F[fi] : N;
                     for (int j = fi + lane; j < gi; j += 32) {
-                        if (v_prec(M, g, i, j)) {
-                            double nsc = __dadd_rn(ti, v_weight(M, g, i, j));
-                            if (M.total[j] > nsc) { M.total[j] = nsc; M.prev[j] = i; }
+                        if (O2A_PREC(i, j)) {
+                            // HSP.distance (alignment.py:170-217) + HSPVertex._relax (:388-411)
+                            const long long qd = Qs[j] - Qe[i];
+                            const long long sd = want_dir ? (Ss[j] - Se[i]) : (Se[i] - Ss[j]);
+                            const double wgt = __dsub_rn(__dadd_rn(G, __dmul_rn(E, (double)(qd + sd))), Sc[j]);
+                            const double nsc = __dadd_rn(ti, wgt);
+                            if (Tot[j] > nsc) { Tot[j] = nsc; Prev[j] = i; }
                         }
                     }
                 }
                 __syncwarp();
             }
-            sco[o] = -M.total[N - 1];
+#undef O2A_PREC
+            const double sco = -Tot[N - 1];
+            // backtrack (alignment.py:1007-1013): lane 0 walks, then the chain is reversed in place
             int ln = 0;
             if (lane == 0) {
                 int cur = N - 1;
-                while (M.prev[cur] != -1) { cur = M.prev[cur]; if (cur != 0) ++ln; }
-                int pos = ln; cur = N - 1;
-                while (M.prev[cur] != -1) { cur = M.prev[cur]; if (cur != 0) s_chain[w][o][--pos] = M.id[cur - 1]; }
+                while (Prev[cur] != -1) { cur = Prev[cur]; if (cur != 0) F[ln++] = cur; }   // F reused: reversed chain
             }
-            len[o] = __shfl_sync(FULL_MASK, ln, 0);
+            ln = __shfl_sync(FULL_MASK, ln, 0);
+            __syncwarp();
+            // key of get_best_orthologs (pipeline.py:981-987) from the chain's query coordinates
+            double key = 0.0;
+            {
+                int v = lane < ln ? F[ln - 1 - lane] : 0;
+                if (lane < ln) s_chain[w][o][lane] = Id[v];
+                long long blen = 0, lo = INT64_MAX, hi = INT64_MIN;
+                if (lane < ln) {
+                    long long d = Qe[v] - Qs[v]; blen = d < 0 ? -d : d;
+                    lo = Qs[v] < Qe[v] ? Qs[v] : Qe[v]; hi = Qs[v] > Qe[v] ? Qs[v] : Qe[v];
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    blen += __shfl_xor_sync(FULL_MASK, blen, d);
+                    long long olo = __shfl_xor_sync(FULL_MASK, lo, d), ohi = __shfl_xor_sync(FULL_MASK, hi, d);
+                    lo = olo < lo ? olo : lo; hi = ohi > hi ? ohi : hi;
+                }
+                if (A.best_value == 0) key = (double)blen;
+                else if (A.best_value == 1) key = ln ? (double)(hi - lo) : 0.0;
+                else if (A.best_value == 2) key = (double)ln;
+                else {          // weight: Python sum() left to right (genomicranges.py:1225)
+                    double wsum = 0.0;
+                    for (int c = ln - 1; c >= 0; --c) wsum = __dadd_rn(wsum, Sc[F[c]]);
+                    key = wsum;
+                }
+            }
+            if (o == 0) { sco0 = sco; len0 = ln; key0 = key; } else { sco1 = sco; len1 = ln; key1 = key; }
             __syncwarp();
         }
-        const int pick = (sco[0] > sco[1]) ? 0 : 1;      // alignment.py:1043-1046
-        const int ln = len[pick];
+        const int pick = (sco0 > sco1) ? 0 : 1;          // alignment.py:1043-1046
+        const int ln = pick ? len1 : len0;
         for (int c = lane; c < ln; c += 32) A.chain_slot[h0 + c] = s_chain[w][pick][c];
         if (lane == 0) {
-            A.chain_len[a] = ln; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = sco[pick];
-            A.orient_scores[2 * a] = sco[0]; A.orient_scores[2 * a + 1] = sco[1];
-            A.best_key[a] = ln ? best_key_of_chain(A, h0, s_chain[w][pick], ln, A.best_value) : 0.0;
+            A.chain_len[a] = ln; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = pick ? sco1 : sco0;
+            A.orient_scores[2 * a] = sco0; A.orient_scores[2 * a + 1] = sco1;
+            A.best_key[a] = ln ? (pick ? key1 : key0) : 0.0;
         }
         __syncwarp();
     }

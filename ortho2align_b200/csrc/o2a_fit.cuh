@@ -25,6 +25,9 @@ namespace o2a {
 constexpr int FIT_THREADS = 256;
 constexpr int FIT_SMEM_RANGE = 4096;    // distinct-value counters kept in shared memory up to this range
 constexpr int FIT_SMEM_NNZ = 1024;      // distinct values / non-empty bins staged in shared memory
+#ifndef O2A_FIT_MATCH
+#define O2A_FIT_MATCH 0                 // 1: warp-aggregate equal values (match.any) before the shared atomic
+#endif
 
 // ndtr(z) = 0.5*erfc(-z/sqrt2): scipy.special.ndtr is cephes-derived and not bit-reproducible with
 // CUDA's erfc (<= 2.3e-16 absolute apart) — KDE parity is to tolerance.
@@ -117,61 +120,62 @@ __device__ __forceinline__ double fit_term(int cnt, long long k, const LncFit& f
     return __dmul_rn(hp0, w);
 }
 
-// numpy DOUBLE_pairwise_sum over a B-long array that is zero except at the sorted positions
-// pos[0..m) with values t[0..m): the recursion is walked over the non-empty entries only (a zero
-// subtree returns exactly 0.0 and x + 0.0 == x). Executed by ONE thread.
-__device__ double sparse_pairwise_sum(const int* pos, const double* t, int m, long long B)
+// numpy DOUBLE_pairwise_sum over a B-long array that is zero except at a few sorted positions.
+// The recursion (n <= 128: 8-accumulator leaf; else split at n/2 rounded down to a multiple of 8)
+// only matters through the non-empty entries: an all-zero subtree returns exactly 0.0 and
+// x + 0.0 == x. So (1) every entry finds its leaf by descending the recursion, (2) each non-empty
+// leaf is summed with numpy's accumulator order, (3) the leaves are combined in recursion order,
+// which for leaves in position order is an operator-precedence evaluation where the operator
+// between two adjacent leaves binds tighter the deeper their lowest common ancestor is.
+struct PwLeaf { long long off; int n; int depth; unsigned long long path; };
+
+__device__ __forceinline__ PwLeaf pw_find_leaf(long long pos, long long B)
 {
-    struct Fr { long long off, n; int lo, hi; int state; };
-    Fr st[48]; double vs[48];
-    int sp = 0, vp = 0;
-    st[sp++] = Fr{0, B, 0, m, 0};
-    while (sp > 0) {
-        Fr& fr = st[sp - 1];
-        if (fr.lo >= fr.hi) { vs[vp++] = 0.0; --sp; continue; }
-        if (fr.n <= 128) {
-            double res;
-            if (fr.n < 8) {
-                res = 0.;
-                for (int e = fr.lo; e < fr.hi; ++e) res = __dadd_rn(res, t[e]);
-            } else {
-                double r[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-                const long long lim = fr.n - (fr.n % 8);
-                int e = fr.lo;
-                for (; e < fr.hi && (long long)pos[e] - fr.off < lim; ++e) {
-                    int j = (int)(((long long)pos[e] - fr.off) & 7);
-                    double v = t[e];
-                    // r[j] += v without dynamic register indexing
-                    r[0] = j == 0 ? __dadd_rn(r[0], v) : r[0]; r[1] = j == 1 ? __dadd_rn(r[1], v) : r[1];
-                    r[2] = j == 2 ? __dadd_rn(r[2], v) : r[2]; r[3] = j == 3 ? __dadd_rn(r[3], v) : r[3];
-                    r[4] = j == 4 ? __dadd_rn(r[4], v) : r[4]; r[5] = j == 5 ? __dadd_rn(r[5], v) : r[5];
-                    r[6] = j == 6 ? __dadd_rn(r[6], v) : r[6]; r[7] = j == 7 ? __dadd_rn(r[7], v) : r[7];
-                }
-                res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                                __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-                for (; e < fr.hi; ++e) res = __dadd_rn(res, t[e]);
-            }
-            vs[vp++] = res; --sp; continue;
-        }
-        long long n2 = fr.n / 2; n2 -= n2 % 8;
-        if (fr.state == 0) {
-            // split the entries at position off + n2
-            int lo = fr.lo, hi = fr.hi;
-            const long long cut = fr.off + n2;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if ((long long)pos[mid] < cut) lo = mid + 1; else hi = mid; }
-            const int mid_e = lo;
-            fr.state = 1;
-            Fr right{fr.off + n2, fr.n - n2, mid_e, fr.hi, 0};
-            Fr left{fr.off, n2, fr.lo, mid_e, 0};
-            st[sp++] = right;          // evaluated second
-            st[sp++] = left;           // evaluated first
-            // mark that two children are pending by parking the frame in state 1
-        } else {
-            double b = vs[--vp]; double a = vs[--vp];
-            vs[vp++] = __dadd_rn(a, b); --sp;
+    PwLeaf L; L.off = 0; L.depth = 0; L.path = 0ull;
+    long long n = B;
+    while (n > 128) {
+        long long n2 = n / 2; n2 -= n2 % 8;
+        if (pos - L.off < n2) { n = n2; L.path <<= 1; }
+        else { L.off += n2; n -= n2; L.path = (L.path << 1) | 1ull; }
+        ++L.depth;
+    }
+    L.n = (int)n;
+    return L;
+}
+
+// depth of the lowest common ancestor of two different leaves
+__device__ __forceinline__ int pw_lca_depth(const PwLeaf& a, const PwLeaf& b)
+{
+    int m = a.depth < b.depth ? a.depth : b.depth;
+    unsigned long long x = (a.path >> (a.depth - m)) ^ (b.path >> (b.depth - m));
+    return m - (64 - __clzll((long long)x));
+}
+
+// numpy leaf (n <= 128) over the entries e in [lo, hi) (positions pos[e] inside the leaf, values t[e])
+__device__ double pw_leaf_sum(const int* pos, const double* t, int lo, int hi, long long off, int n)
+{
+    double res;
+    if (n < 8) {
+        res = 0.;
+        for (int e = lo; e < hi; ++e) res = __dadd_rn(res, t[e]);
+        return res;
+    }
+    double r0 = 0., r1 = 0., r2 = 0., r3 = 0., r4 = 0., r5 = 0., r6 = 0., r7 = 0.;
+    const int lim = n - (n % 8);
+    int e = lo;
+    for (; e < hi && (int)((long long)pos[e] - off) < lim; ++e) {
+        const int j = (int)((long long)pos[e] - off) & 7;
+        const double v = t[e];
+        switch (j) {
+            case 0: r0 = __dadd_rn(r0, v); break; case 1: r1 = __dadd_rn(r1, v); break;
+            case 2: r2 = __dadd_rn(r2, v); break; case 3: r3 = __dadd_rn(r3, v); break;
+            case 4: r4 = __dadd_rn(r4, v); break; case 5: r5 = __dadd_rn(r5, v); break;
+            case 6: r6 = __dadd_rn(r6, v); break; default: r7 = __dadd_rn(r7, v); break;
         }
     }
-    return vs[0];
+    res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (; e < hi; ++e) res = __dadd_rn(res, t[e]);
+    return res;
 }
 
 struct FitArgs {
@@ -200,8 +204,12 @@ k_fit(FitArgs A)
     __shared__ int s_red_i[2 * (FIT_THREADS / 32)];
     __shared__ double s_red[FIT_THREADS / 32];
     __shared__ int s_scan[FIT_THREADS / 32 + 2];
-    __shared__ int s_mn, s_mx, s_bad, s_nnz;
+    __shared__ int s_mn, s_mx, s_bad, s_oor;
     __shared__ double s_S;
+    __shared__ double s_lsum[FIT_SMEM_NNZ];            // leaf sums (at the leaf's first entry)
+    __shared__ short s_ldep[FIT_SMEM_NNZ];             // LCA depth between this leaf and the previous one
+    __shared__ double s_vstk[72];
+    __shared__ short s_ostk[72];
     const int tid = threadIdx.x;
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
 
@@ -209,20 +217,39 @@ k_fit(FitArgs A)
         const long long b0 = A.bg_off[l];
         const long long n = A.bg_off[l + 1] - b0;
         const int* x = A.bg + b0;
-        // ---- min / max (first pass over the background) -------------------------------------
+        // ---- pass over the background: min / max, and (optimistically) the multiplicities ----------
+        // BLAST scores are small non-negative integers: values in [0, FIT_SMEM_RANGE) are counted
+        // directly in shared memory during the same pass; anything else falls back to the general
+        // two-pass path (min first, then counts relative to it).
+        {
+            int4* z = reinterpret_cast<int4*>(s_cnt);
+            for (int k = tid; k < FIT_SMEM_RANGE / 4; k += FIT_THREADS) z[k] = make_int4(0, 0, 0, 0);
+            if (tid == 0) { s_bad = 0; s_oor = 0; }
+        }
+        __syncthreads();
         int mn = INT32_MAX, mx = INT32_MIN;
         {
+            bool oor = false;
+#if O2A_FIT_MATCH
+#define O2A_FIT_ADD(v) do { int v__ = (v); mn = min(mn, v__); mx = max(mx, v__);                              \
+                if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) { unsigned pe__ = __match_any_sync(__activemask(), v__); \
+                    if ((pe__ & lanemask_lt()) == 0) atomicAdd(&s_cnt[v__], __popc(pe__)); } else oor = true; } while (0)
+#else
+#define O2A_FIT_ADD(v) do { int v__ = (v); mn = min(mn, v__); mx = max(mx, v__);                              \
+                if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) atomicAdd(&s_cnt[v__], 1); else oor = true; } while (0)
+#endif
             // 16-byte vector loads over the aligned middle part
             long long head = ((4 - (b0 & 3)) & 3); if (head > n) head = n;
-            for (long long i = tid; i < head; i += FIT_THREADS) { int v = x[i]; mn = min(mn, v); mx = max(mx, v); }
+            for (long long i = tid; i < head; i += FIT_THREADS) O2A_FIT_ADD(x[i]);
             const int4* x4 = reinterpret_cast<const int4*>(x + head);
-            const long long n4 = (n - head) >> 2;
-            for (long long i = tid; i < n4; i += FIT_THREADS) {
+            const int n4 = (int)((n - head) >> 2);
+            for (int i = tid; i < n4; i += FIT_THREADS) {
                 int4 v = x4[i];
-                mn = min(min(mn, v.x), min(v.y, min(v.z, v.w)));
-                mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
+                O2A_FIT_ADD(v.x); O2A_FIT_ADD(v.y); O2A_FIT_ADD(v.z); O2A_FIT_ADD(v.w);
             }
-            for (long long i = head + (n4 << 2) + tid; i < n; i += FIT_THREADS) { int v = x[i]; mn = min(mn, v); mx = max(mx, v); }
+            for (long long i = head + ((long long)n4 << 2) + tid; i < n; i += FIT_THREADS) O2A_FIT_ADD(x[i]);
+#undef O2A_FIT_ADD
+            if (oor) s_oor = 1;
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { mn = min(mn, __shfl_xor_sync(FULL_MASK, mn, d)); mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, d)); }
@@ -230,13 +257,14 @@ k_fit(FitArgs A)
         __syncthreads();
         if (tid == 0) {
             for (int w = 0; w < FIT_THREADS / 32; ++w) { mn = min(mn, s_red_i[w]); mx = max(mx, s_red_i[FIT_THREADS / 32 + w]); }
-            s_mn = mn; s_mx = mx; s_bad = 0;
+            s_mn = mn; s_mx = mx;
         }
         __syncthreads();
         mn = s_mn; mx = s_mx;
+        const bool fast = (s_oor == 0);
         const long long R = (long long)mx - (long long)mn + 1;
         const long long B = n / 2;
-        if ((R > A.max_range && R > FIT_SMEM_RANGE) || (A.fitter == 0 && B < 1)) {
+        if ((!fast && R > A.max_range && R > FIT_SMEM_RANGE) || (A.fitter == 0 && B < 1)) {
             if (tid == 0) {
                 A.thr[l] = NaN; A.status[l] = (B < 1 && A.fitter == 0) ? 3 : 4;
                 if (A.fitter == 0) { LncFit f{}; A.fits[l] = f; } else A.uv_n[l] = 0;
@@ -244,21 +272,24 @@ k_fit(FitArgs A)
             __syncthreads();
             continue;
         }
-        // ---- multiplicity of every distinct value (second pass; L2-resident for typical sizes) ----
-        int* cnt = (R <= FIT_SMEM_RANGE) ? s_cnt : (A.g_cnt + (long long)blockIdx.x * A.max_range);
-        for (long long k = tid; k < R; k += FIT_THREADS) cnt[k] = 0;
-        __syncthreads();
-        for (long long i0 = 0; i0 < n; i0 += FIT_THREADS) {
-            long long i = i0 + tid;
-            bool valid = i < n;
-            unsigned m = __ballot_sync(FULL_MASK, valid);
-            if (valid) {
-                int c = x[i] - mn;
-                unsigned peers = __match_any_sync(m, c);
-                if ((peers & lanemask_lt()) == 0) atomicAdd(&cnt[c], __popc(peers));
+        // cnt[k] = multiplicity of value mn + k
+        int* cnt = s_cnt + mn;
+        if (!fast) {
+            cnt = (R <= FIT_SMEM_RANGE) ? s_cnt : (A.g_cnt + (long long)blockIdx.x * A.max_range);
+            for (long long k = tid; k < R; k += FIT_THREADS) cnt[k] = 0;
+            __syncthreads();
+            for (long long i0 = 0; i0 < n; i0 += FIT_THREADS) {
+                long long i = i0 + tid;
+                bool valid = i < n;
+                unsigned m = __ballot_sync(FULL_MASK, valid);
+                if (valid) {
+                    int c = x[i] - mn;
+                    unsigned peers = __match_any_sync(m, c);
+                    if ((peers & lanemask_lt()) == 0) atomicAdd(&cnt[c], __popc(peers));
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
         // ---- compact to (value, count), ascending ------------------------------------------------
         // staged in shared memory when they fit, else directly in the lncRNA's global slot
         int* uval = A.fitter == 0 ? nullptr : A.uv_val + b0;
@@ -377,7 +408,41 @@ k_fit(FitArgs A)
             s_t[t] = fit_term(s_c[t], s_k[t], f, total, &hp0, &w);
         }
         __syncthreads();
-        if (tid == 0) s_S = sparse_pairwise_sum(s_k, s_t, nnz, B);
+        // (1)+(2): leaf of every entry; the first entry of each leaf sums its leaf
+        for (int t = tid; t < nnz; t += FIT_THREADS) {
+            const PwLeaf L = pw_find_leaf(s_k[t], B);
+            bool head = true; int dep = -1;
+            if (t > 0) {
+                const PwLeaf P = pw_find_leaf(s_k[t - 1], B);
+                head = (P.off != L.off);
+                if (head) dep = pw_lca_depth(P, L);
+            }
+            s_ldep[t] = (short)(head ? dep : -2);          // -2: not a leaf head
+            if (head) {
+                int hi = t + 1;
+                while (hi < nnz && (long long)s_k[hi] < L.off + L.n) ++hi;
+                s_lsum[t] = pw_leaf_sum(s_k, s_t, t, hi, L.off, L.n);
+            }
+        }
+        __syncthreads();
+        // (3): precedence evaluation over the leaf heads, left to right
+        if (tid == 0) {
+            int vp = 0, op = 0;
+            for (int t = 0; t < nnz; ++t) {
+                const int d = s_ldep[t];
+                if (d == -2) continue;
+                if (t > 0) {                                // operator between the previous leaf and this one
+                    while (op > 0 && s_ostk[op - 1] > d) {
+                        double b = s_vstk[--vp], a = s_vstk[--vp];
+                        s_vstk[vp++] = __dadd_rn(a, b); --op;
+                    }
+                    s_ostk[op++] = (short)d;
+                }
+                s_vstk[vp++] = s_lsum[t];
+            }
+            while (op > 0) { double b = s_vstk[--vp], a = s_vstk[--vp]; s_vstk[vp++] = __dadd_rn(a, b); --op; }
+            s_S = nnz > 0 ? s_vstk[0] : 0.0;
+        }
         __syncthreads();
         const double S = s_S;
         for (int t = tid; t < nnz; t += FIT_THREADS) {

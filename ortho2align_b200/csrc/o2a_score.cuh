@@ -29,70 +29,85 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double* p)
     return r;
 }
 
-__global__ void __launch_bounds__(FILTER_THREADS, 6)
+// Layout inside a tile of FILTER_TILE elements: warp w owns the contiguous chunk
+// [w*FILTER_WCHUNK, (w+1)*FILTER_WCHUNK), as FILTER_ROWS rows of 64 elements (32 lanes x double2,
+// 512 contiguous bytes per warp load). Order-preserving positions then need only: the lane prefix
+// (ballots), the running row prefix (registers) and ONE cross-warp prefix per tile (8 counters).
+__global__ void __launch_bounds__(FILTER_THREADS, 5)
 k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __restrict__ aln_lnc,
          const double* __restrict__ score, const double* __restrict__ thr, const int* __restrict__ lnc_status,
          int* __restrict__ n_surv, int* __restrict__ surv_idx, double* __restrict__ surv_x)
 {
-    __shared__ int s_cnt[FILTER_ROWS][FILTER_THREADS / 32];
-    const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
     constexpr int NW = FILTER_THREADS / 32;
+    constexpr int WCHUNK = FILTER_ROWS * 64;
+    __shared__ int s_wtot[2][NW];
+    const int lane = lane_id(), w = warp_id();
+    const unsigned lt = lanemask_lt();
+    int buf = 0;
 
     for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
         const int l = aln_lnc[a];
         const long long h0 = hsp_off[a];
         const int m = (int)(hsp_off[a + 1] - h0);
         if (lnc_status[l] != 0) {                     // fit failed: the reference raised before the loop
-            if (tid == 0) n_surv[a] = 0;
+            if (threadIdx.x == 0) n_surv[a] = 0;
             continue;
         }
         const double t = thr[l];
         const double* sc = score + h0;
+        int* out_idx = surv_idx + h0;
+        double* out_x = surv_x + h0;
         const bool aligned16 = ((h0 & 1) == 0);       // score + h0 is 16-byte aligned
         int base = 0;
         for (int t0 = 0; t0 < m; t0 += FILTER_TILE) {
+            const int e0 = t0 + w * WCHUNK + lane * 2;            // my first element of row 0
             double2 v[FILTER_ROWS];
-            unsigned flag = 0;                        // per row: 2 flag bits + 6 "before" bits
+            if (aligned16 && t0 + FILTER_TILE <= m) {             // full tile: no bounds checks
 #pragma unroll
-            for (int r = 0; r < FILTER_ROWS; ++r) {
-                int e = t0 + (r * FILTER_THREADS + tid) * 2;
-                if (aligned16 && e + 1 < m) v[r] = ld_stream_f64x2(sc + e);
-                else {
-                    v[r].x = e < m ? sc[e] : 0.0;
-                    v[r].y = e + 1 < m ? sc[e + 1] : 0.0;
+                for (int r = 0; r < FILTER_ROWS; ++r) v[r] = ld_stream_f64x2(sc + e0 + r * 64);
+            } else {
+#pragma unroll
+                for (int r = 0; r < FILTER_ROWS; ++r) {
+                    const int e = e0 + r * 64;
+                    if (aligned16 && e + 1 < m) v[r] = ld_stream_f64x2(sc + e);
+                    else {
+                        // -inf never passes the strict '>' filter
+                        v[r].x = e < m ? sc[e] : __longlong_as_double(0xfff0000000000000ll);
+                        v[r].y = e + 1 < m ? sc[e + 1] : __longlong_as_double(0xfff0000000000000ll);
+                    }
                 }
             }
+            unsigned bx[FILTER_ROWS], by[FILTER_ROWS];
+            int wtot = 0;
 #pragma unroll
             for (int r = 0; r < FILTER_ROWS; ++r) {
-                int e = t0 + (r * FILTER_THREADS + tid) * 2;
-                bool fx = (e < m) && (v[r].x > t);
-                bool fy = (e + 1 < m) && (v[r].y > t);
-                unsigned bx = __ballot_sync(FULL_MASK, fx), by = __ballot_sync(FULL_MASK, fy);
-                if (lane == 0) s_cnt[r][w] = __popc(bx) + __popc(by);
-                // survivors of this warp-row before me, in element order (x0 y0 x1 y1 ...)
-                int before = __popc(bx & lanemask_lt()) + __popc(by & lanemask_lt());
-                flag |= ((fx ? 1u : 0u) | (fy ? 2u : 0u) | ((unsigned)before << 2)) << (8 * r);
+                bx[r] = __ballot_sync(FULL_MASK, v[r].x > t);
+                by[r] = __ballot_sync(FULL_MASK, v[r].y > t);
+                wtot += __popc(bx[r]) + __popc(by[r]);
             }
+            if (lane == 0) s_wtot[buf][w] = wtot;
             __syncthreads();
-            int tile_total = 0;
+            int wbase = 0, tile_total = 0;
 #pragma unroll
-            for (int r = 0; r < FILTER_ROWS; ++r) {
-                int row_before = 0, row_total = 0;
+            for (int ww = 0; ww < NW; ++ww) { const int c = s_wtot[buf][ww]; wbase += (ww < w) ? c : 0; tile_total += c; }
+            buf ^= 1;                                             // double-buffered: one barrier per tile
+            if (wtot) {
+                int pos = base + wbase;
 #pragma unroll
-                for (int ww = 0; ww < NW; ++ww) { int c = s_cnt[r][ww]; row_before += (ww < w) ? c : 0; row_total += c; }
-                const unsigned fr = (flag >> (8 * r)) & 0xffu;
-                if (fr & 3u) {
-                    long long pos = h0 + base + tile_total + row_before + (int)(fr >> 2);
-                    int e = t0 + (r * FILTER_THREADS + tid) * 2;
-                    if (fr & 1u) { surv_idx[pos] = e; surv_x[pos] = v[r].x; ++pos; }
-                    if (fr & 2u) { surv_idx[pos] = e + 1; surv_x[pos] = v[r].y; }
+                for (int r = 0; r < FILTER_ROWS; ++r) {
+                    const unsigned mx = bx[r], my = by[r];
+                    if (mx | my) {
+                        int p = pos + __popc(mx & lt) + __popc(my & lt);
+                        const int e = e0 + r * 64;
+                        if ((mx >> lane) & 1u) { out_idx[p] = e; out_x[p] = v[r].x; ++p; }
+                        if ((my >> lane) & 1u) { out_idx[p] = e + 1; out_x[p] = v[r].y; }
+                        pos += __popc(mx) + __popc(my);
+                    }
                 }
-                tile_total += row_total;
             }
             base += tile_total;
-            __syncthreads();
         }
-        if (tid == 0) n_surv[a] = base;
+        if (threadIdx.x == 0) n_surv[a] = base;
     }
 }
 
@@ -166,14 +181,10 @@ k_pq(PqArgs A)
             int kept = 0;
             for (int k = tid; k < ns; k += PQ_THREADS) {
                 const double p = s_p[k];
+                // stable rank: 1 + #{j < k : p_j <= p} + #{j > k : p_j < p}
                 int rank = 1;
-                int j = 0;
-                for (; j + 1 < ns; j += 2) {
-                    double p0 = s_p[j], p1 = s_p[j + 1];
-                    rank += (p0 < p) || (p0 == p && j < k);
-                    rank += (p1 < p) || (p1 == p && j + 1 < k);
-                }
-                if (j < ns) { double p0 = s_p[j]; rank += (p0 < p) || (p0 == p && j < k); }
+                for (int j = 0; j < k; ++j) rank += (s_p[j] <= p);
+                for (int j = k + 1; j < ns; ++j) rank += (s_p[j] < p);
                 double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);
                 bool keep = q <= A.alpha;
                 A.surv_pq[h0 + k] = q;
