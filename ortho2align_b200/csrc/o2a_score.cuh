@@ -54,29 +54,30 @@ k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __re
             continue;
         }
         const double t = thr[l];
-        const double* sc = score + h0;
+        // the stream is read from the 16-byte aligned address at or just below score + h0: stream
+        // element i is HSP i - sh of the alignment (sh = 0 or 1); element -1 belongs to the neighbour
+        const int sh = (int)(h0 & 1);
+        const double* sc = score + h0 - sh;
+        const int ms = m + sh;                        // stream length
         int* out_idx = surv_idx + h0;
         double* out_x = surv_x + h0;
-        const bool aligned16 = ((h0 & 1) == 0);       // score + h0 is 16-byte aligned
+        const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);   // never passes the strict '>'
         int base = 0;
-        for (int t0 = 0; t0 < m; t0 += FILTER_TILE) {
-            const int e0 = t0 + w * WCHUNK + lane * 2;            // my first element of row 0
+        for (int t0 = 0; t0 < ms; t0 += FILTER_TILE) {
+            const int e0 = t0 + w * WCHUNK + lane * 2;            // my first stream element of row 0
             double2 v[FILTER_ROWS];
-            if (aligned16 && t0 + FILTER_TILE <= m) {             // full tile: no bounds checks
 #pragma unroll
-                for (int r = 0; r < FILTER_ROWS; ++r) v[r] = ld_stream_f64x2(sc + e0 + r * 64);
-            } else {
-#pragma unroll
-                for (int r = 0; r < FILTER_ROWS; ++r) {
+            for (int r = 0; r < FILTER_ROWS; ++r) {
+                const int rs = t0 + w * WCHUNK + r * 64;          // row start (warp-uniform)
+                if (rs + 64 <= ms) v[r] = ld_stream_f64x2(sc + e0 + r * 64);
+                else if (rs >= ms) { v[r].x = NEG_INF; v[r].y = NEG_INF; }
+                else {
                     const int e = e0 + r * 64;
-                    if (aligned16 && e + 1 < m) v[r] = ld_stream_f64x2(sc + e);
-                    else {
-                        // -inf never passes the strict '>' filter
-                        v[r].x = e < m ? sc[e] : __longlong_as_double(0xfff0000000000000ll);
-                        v[r].y = e + 1 < m ? sc[e + 1] : __longlong_as_double(0xfff0000000000000ll);
-                    }
+                    v[r].x = e < ms ? sc[e] : NEG_INF;
+                    v[r].y = e + 1 < ms ? sc[e + 1] : NEG_INF;
                 }
             }
+            if (sh && t0 == 0 && w == 0 && lane == 0) v[0].x = NEG_INF;   // the neighbour's last HSP
             unsigned bx[FILTER_ROWS], by[FILTER_ROWS];
             int wtot = 0;
 #pragma unroll
@@ -98,7 +99,7 @@ k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __re
                     const unsigned mx = bx[r], my = by[r];
                     if (mx | my) {
                         int p = pos + __popc(mx & lt) + __popc(my & lt);
-                        const int e = e0 + r * 64;
+                        const int e = e0 + r * 64 - sh;          // HSP position inside the alignment
                         if ((mx >> lane) & 1u) { out_idx[p] = e; out_x[p] = v[r].x; ++p; }
                         if ((my >> lane) & 1u) { out_idx[p] = e + 1; out_x[p] = v[r].y; }
                         pos += __popc(mx) + __popc(my);
@@ -183,7 +184,9 @@ k_pq(PqArgs A)
                 const double p = s_p[k];
                 // stable rank: 1 + #{j < k : p_j <= p} + #{j > k : p_j < p}
                 int rank = 1;
+#pragma unroll 4
                 for (int j = 0; j < k; ++j) rank += (s_p[j] <= p);
+#pragma unroll 4
                 for (int j = k + 1; j < ns; ++j) rank += (s_p[j] < p);
                 double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);
                 bool keep = q <= A.alpha;
