@@ -202,14 +202,12 @@ def main():
     # ---------------- device-resident arm (value) ----------------
     dbatch = DeviceBatch(batch, dev)
     dstruct = dbatch.struct(with_kde)
-    counts_t = torch.zeros(5, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(5 * world, dtype=torch.int64, device=dev) if world > 1 else None
+    from ortho2align_b200.distributed import gather_counts
 
     def step_device():
         c = eng.run(dstruct, params)
-        if world > 1:     # the only collective of the path: gather the result counts on every rank
-            counts_t.copy_(torch.tensor([c.n_survivors, c.n_retained, c.n_chain_hsps, c.n_chains, c.n_failed_lnc]))
-            dist.all_gather_into_tensor(gathered, counts_t)
+        if world > 1:     # the only collective of the path: gather the result counts on every rank (NCCL)
+            gather_counts([c.n_survivors, c.n_retained, c.n_chain_hsps, c.n_chains, c.n_failed_lnc], dev)
         return c
 
     for _ in range(max(args.warmup, 1)):

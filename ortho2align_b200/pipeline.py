@@ -1,0 +1,276 @@
+"""Drop-in `build_orthologs` / `get_best_orthologs` (same names, arguments, files and stats block as
+`ortho2align/pipeline.py:801-956, 959-1024`) with the per-lncRNA `_build` workers
+(`pipeline.py:722-798`) replaced by ONE batched call into the CUDA library per GPU.
+
+What stays on the host, in Python, like in the reference: directory listing, JSON decoding, text
+assembly of the BED/TSV records, the "dropped" / "exception" bookkeeping and the stats block.
+There is no CPU fallback for the compute: `Engine` raises if the CUDA library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import json
+import os
+import threading
+from collections import Counter
+from pathlib import Path
+
+import numpy as np
+
+from .columnar import PackError, concat_batches, pack_lncrna
+from .records import (Range, as_pvals, bed6_lines, chain_records, drop_duplicates, find_neighbours,
+                      sort_key)
+from .result import STATUS_OK
+
+_STATUS_TEXT = {1: "None", 2: "Failed to converge after 100 iterations.",
+                3: "Too many bins for data range. Cannot create finite-sized bins.",
+                4: "background outside the range supported by the CUDA fitter"}
+
+
+class ExceptionLogger(Exception):
+    """Same shape as the reference's `parallel.ExceptionLogger` (`parallel.py:491-520`)."""
+
+    def __init__(self, exception, variable, message=""):
+        self.exception, self.variable, self.message = exception, variable, message
+
+    def __str__(self):
+        return f'The exception "{self.exception}" has been raised. ' \
+               f'Important variable is {self.variable}. {self.message}'
+
+
+def simple_hist(data):
+    """`utils.simple_hist` (`utils.py:89-101`)."""
+    counts = Counter(data)
+    return "\n".join(f"{k}: {v}" for k, v in sorted(counts.items(), key=lambda i: (i[0], i[1])))
+
+
+def lpt_shards(weights, n_shards):
+    """Longest-processing-time greedy partition of lncRNAs by HSP count.
+    Returns a list of index lists; lncRNAs are independent, so any partition is exact."""
+    order = np.argsort(-np.asarray(weights), kind="stable")
+    loads = [0] * n_shards
+    shards = [[] for _ in range(n_shards)]
+    for i in order:
+        k = loads.index(min(loads))
+        shards[k].append(int(i))
+        loads[k] += int(weights[i])
+    return [sorted(s) for s in shards]
+
+
+def _load_lncrna(align_file, bg_file):
+    """JSON -> (alignment dicts, ColumnarBatch) — the ingest half of `_build` (pipeline.py:743-754)."""
+    with open(align_file, "r") as f:
+        alignment_dicts = json.load(f)
+    if os.path.exists(bg_file):
+        with open(bg_file, "r") as f:
+            bg = json.load(f)
+    else:
+        bg = None
+    return alignment_dicts, pack_lncrna(alignment_dicts, bg)
+
+
+def _run_shards(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
+    """One Engine (= one o2a_ctx) per GPU, each on its own thread; ctypes releases the GIL."""
+    from .engine import Engine
+    results = [None] * len(batches)
+    errors = []
+
+    def work(k):
+        try:
+            eng = Engine(devices[k])
+            try:
+                results[k] = eng.build_batch(batches[k], fitter, fdr, alpha, gapopen, gapextend, survivors=False)
+            finally:
+                eng.close()
+        except Exception as e:  # surfaced below, on the caller's thread
+            errors.append(e)
+
+    if len(batches) == 1:
+        work(0)
+    else:
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(batches))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gapopen=5, gapextend=2,
+                    fdr=False, cores=1, timeout=None, silent=False, stats_filename=None, devices=None):
+    """A build_orthologs step of the pipeline (signature of `pipeline.py:801-812`).
+
+    `cores`/`timeout` are accepted for CLI compatibility: the per-lncRNA process pool they
+    configured does not exist here. `devices`: CUDA device indices (default: [0]); with several,
+    lncRNAs are LPT-sharded by HSP count and every GPU runs its shard independently.
+    `fitting`: 'hist' | 'kde' (reference) or 'empirical' (extension).
+    """
+    alignments_dir = Path(alignments)
+    background_dir = Path(background)
+    if fitting not in ("hist", "kde", "empirical"):
+        # the reference leaves `fitter` unbound and dies with UnboundLocalError (pipeline.py:839-847)
+        raise UnboundLocalError("cannot access local variable 'fitter' where it is not associated with a value")
+    devices = [0] if not devices else list(devices)
+
+    alignments_files = [os.path.join(alignments_dir, fn) for fn in os.listdir(alignments_dir) if fn.endswith("json")]
+    total_alignments = len(alignments_files)
+    bg_files = [os.path.join(background_dir, os.path.basename(f)) for f in alignments_files]
+    total_bgs = len(bg_files)
+
+    # ---- ingest -------------------------------------------------------------------------------
+    loaded = []        # per file: (alignment_dicts, batch) or an ExceptionLogger
+    for af, bf in zip(alignments_files, bg_files):
+        alignment_dicts, batch = None, None
+        try:
+            alignment_dicts, batch = _load_lncrna(af, bf)
+            loaded.append((alignment_dicts, batch))
+        except PackError as e:
+            qr = Range.from_dict(alignment_dicts[0]["qrange"]) if alignment_dicts else None
+            loaded.append(ExceptionLogger(e, qr))
+    ok_idx = [i for i, x in enumerate(loaded) if not isinstance(x, ExceptionLogger)]
+
+    # ---- compute: shard by lncRNA across GPUs, one batched call each ---------------------------------
+    per_lnc = {}
+    if ok_idx:
+        n_dev = min(len(devices), len(ok_idx))
+        weights = [loaded[i][1].n_hsp + 1 for i in ok_idx]
+        shards = lpt_shards(weights, n_dev)
+        batches = [concat_batches([loaded[ok_idx[j]][1] for j in shard]) for shard in shards]
+        results = _run_shards(batches, devices[:n_dev], fitting, fdr, threshold, gapopen, gapextend)
+        for shard, batch, res in zip(shards, batches, results):
+            for local, j in enumerate(shard):
+                per_lnc[ok_idx[j]] = (batch, res, local)
+
+    # ---- assemble exactly what the pool would have returned ---------------------------------------------
+    orthologs, exceptions = [], []
+    for i, item in enumerate(loaded):
+        if isinstance(item, ExceptionLogger):
+            exceptions.append(item)
+            continue
+        alignment_dicts, _ = item
+        batch, res, l = per_lnc[i]
+        qrange0 = Range.from_dict(alignment_dicts[0]["qrange"]) if alignment_dicts else None
+        if res.status[l] != STATUS_OK:
+            st = int(res.status[l])
+            err = KeyError(None) if st == 1 else (RuntimeError if st == 2 else ValueError)(_STATUS_TEXT.get(st, st))
+            exceptions.append(ExceptionLogger(err, qrange0))
+            continue
+        q_orth, s_orth, q_dropped, s_dropped, aligned = [], [], None, [], False
+        a0 = int(batch.aln_off[l])
+        for k, d in enumerate(alignment_dicts):
+            a = a0 + k
+            qrange = Range.from_dict(d["qrange"])
+            srange = Range.from_dict(d["srange"])
+            srange.name = qrange.name                                   # pipeline.py:781
+            c0, c1 = int(res.chain_off[a]), int(res.chain_off[a + 1])
+            if c1 > c0:
+                hsps = [d["HSPs"][j] for j in res.chain_idx[c0:c1]]
+                rec = chain_records(hsps, as_pvals(res.chain_pq[c0:c1]), qrange, srange.chrom, qrange.name)
+                q_orth.append((rec[0], rec[1]))
+                s_orth.append((rec[2], rec[3]))
+                aligned = True
+            else:                                                       # ValueError branch, pipeline.py:789-791
+                q_dropped = qrange
+                s_dropped.append(srange)
+        orthologs.append((q_orth, s_orth, [] if aligned else [q_dropped, s_dropped]))
+
+    total_exceptions = len(exceptions)
+    query_exception_ranges = []
+    if total_exceptions > 0:
+        if not silent:
+            print(f"{len(exceptions)} exceptions occured:")
+        for exception in exceptions:
+            if not silent:
+                print(str(exception))
+            query_exception_ranges.append(exception.variable)
+
+    dist_found = [len(group[0]) for group in orthologs]
+    query_orthologs_bed12 = [o[1] for g in orthologs for o in g[0]]
+    subject_orthologs_bed12 = [o[1] for g in orthologs for o in g[1]]
+    query_orthologs_total = [o[0] for g in orthologs for o in g[0]]
+    subject_orthologs_total = [o[0] for g in orthologs for o in g[1]]
+
+    query_dropped, subject_dropped = [], []
+    for g in orthologs:                                                 # pipeline.py:895-908
+        item = g[2]
+        if len(item) != 2:
+            continue
+        qd, sds = item
+        query_dropped.append(qd)
+        for grange in sds:
+            subject_dropped.extend(find_neighbours(grange, qd.lifted))
+    query_dropped = sorted(query_dropped, key=sort_key)
+    subject_dropped = drop_duplicates(sorted(subject_dropped, key=sort_key))
+    total_dropped = len(query_dropped)
+    query_exception_list = sorted(query_exception_ranges, key=sort_key)
+
+    if not os.path.exists(outdir):
+        os.mkdir(outdir)
+    j = lambda n: os.path.join(outdir, n)
+    for name, records in (("significant.query_orthologs.bed", query_orthologs_bed12),
+                          ("significant.subject_orthologs.bed", subject_orthologs_bed12),
+                          ("significant.query_orthologs.tsv", query_orthologs_total),
+                          ("significant.subject_orthologs.tsv", subject_orthologs_total)):
+        with open(j(name), "w") as f:
+            for record in records:
+                f.write(record + "\n")
+    for name, ranges in (("insignificant.query_orthologs.bed", query_dropped),
+                         ("insignificant.subject_orthologs.bed", subject_dropped),
+                         ("query_exceptions.bed", query_exception_list)):
+        with open(j(name), "w") as f:
+            f.writelines(bed6_lines(ranges))
+
+    stats_msg = "-----------------------\n" \
+                f"build_orthologs stats:\n" \
+                f"Recieved {total_alignments} transcript alignments and {total_bgs} backgrounds.\n" \
+                f"Built orthologs for {total_alignments - total_dropped - total_exceptions} of transcripts.\n" \
+                f"Found only unsignificant orthologs for {total_dropped} transcripts.\n" \
+                f"Caught {total_exceptions} exceptions.\n" \
+                f"Distribution of amount of orthologs:\n{simple_hist(dist_found)}\n" \
+                f"Reported all significant orthologs for each transcript.\n" \
+                "-----------------------"
+    if isinstance(stats_filename, str):
+        with open(stats_filename, "a") as f:
+            f.write(stats_msg + "\n")
+    elif not silent:
+        print(stats_msg)
+
+
+_EXTRACT = {
+    "total_length": lambda line: int(line.strip().split("\t")[2]) - int(line.strip().split("\t")[1]),
+    "block_count": lambda line: int(line.strip().split("\t")[9]),
+    "block_length": lambda line: sum([int(i) for i in line.strip().split("\t")[10].split(",")]),
+    "weight": lambda line: float(line.strip().split("\t")[4]),
+    "name": lambda line: line.strip().split("\t")[3],
+}
+
+
+def get_best_orthologs(query_orthologs, query_total, subject_orthologs, subject_total, value, function,
+                       outfile_query, outfile_query_total, outfile_subject, outfile_subject_total):
+    """A get_best_orthologs step of the pipeline (`pipeline.py:959-1024`): streams the four
+    `significant.*` files in lock-step, groups CONSECUTIVE records of the same query name and keeps
+    the first extremal one by `value` computed on the query BED12 line. (The batched C-ABI call
+    also returns this selection per lncRNA — `BatchResult.best_aln` — for in-memory callers; the
+    file-based step costs < 1 ms per 100 records and stays text-driven like the reference's.)"""
+    func = {"min": min, "max": max}[function]
+    key = _EXTRACT[value]
+    with open(Path(query_orthologs)) as q_in, open(Path(query_total)) as qt_in, \
+            open(Path(subject_orthologs)) as s_in, open(Path(subject_total)) as st_in, \
+            open(Path(outfile_query), "w") as q_out, open(Path(outfile_query_total), "w") as qt_out, \
+            open(Path(outfile_subject), "w") as s_out, open(Path(outfile_subject_total), "w") as st_out:
+        outs = (q_out, qt_out, s_out, st_out)
+
+        def flush(group):
+            best = func(group, key=lambda rec: key(rec[0]))
+            for o, line in zip(outs, best):
+                o.write(line)
+
+        purge = []
+        for rec in zip(q_in, qt_in, s_in, st_in):
+            if purge and _EXTRACT["name"](purge[-1][0]) != _EXTRACT["name"](rec[0]):
+                flush(purge)
+                purge = []
+            purge.append(rec)
+        if purge:
+            flush(purge)

@@ -1,0 +1,107 @@
+"""Host logic of the drop-in pipeline (ingest, record text, dropped/exception bookkeeping, stats,
+get_best_orthologs) against the files the unmodified reference wrote (tests/golden/e2e.json).
+CPU tests inject the oracle in place of the GPU call; the gpu test runs the real thing."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+
+def _materialise(tmp_path, g):
+    ad, bd = tmp_path / "align", tmp_path / "bg"
+    ad.mkdir(); bd.mkdir()
+    for item in g["inputs"]:
+        (ad / (item["name"] + ".json")).write_text(json.dumps(item["alignments"]))
+        if item["name"] != g["missing_bg"]:
+            (bd / (item["name"] + ".json")).write_text(json.dumps(item["bg"]))
+    return str(ad), str(bd)
+
+
+def _oracle_runner(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
+    from oracle import oracle as O
+    return [O.build_batch(b, fitter, fdr, alpha, gapopen, gapextend) for b in batches]
+
+
+def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact):
+    from ortho2align_b200 import pipeline
+    ad, bd = _materialise(tmp_path, g)
+    real_listdir = os.listdir
+    monkeypatch.setattr(os, "listdir", lambda p: list(g["listdir_order"]) if str(p) == ad else real_listdir(p))
+    od = str(tmp_path / f"out_{key}")
+    stats = str(tmp_path / f"{key}.stats.txt")
+    pipeline.build_orthologs(ad, bd, fitting, od, threshold=0.05, gapopen=5, gapextend=2, fdr=fdr, cores=1,
+                             timeout=None, silent=True, stats_filename=stats)
+    j = lambda n: os.path.join(od, n)
+    pipeline.get_best_orthologs(j("significant.query_orthologs.bed"), j("significant.query_orthologs.tsv"),
+                                j("significant.subject_orthologs.bed"), j("significant.subject_orthologs.tsv"),
+                                "block_length", "max",
+                                j("bestSignificant.query_orthologs.bed"), j("bestSignificant.query_orthologs.tsv"),
+                                j("bestSignificant.subject_orthologs.bed"), j("bestSignificant.subject_orthologs.tsv"))
+    want = g["runs"][key]
+    for fn, text in want.items():
+        got = open(stats).read() if fn == "stats.txt" else open(j(fn)).read()
+        if exact or not fn.endswith(".tsv"):
+            assert got == text, f"{key}: {fn} differs"
+        else:
+            # KDE: the 13th TSV column (p/q values) is compared to tolerance, everything else verbatim
+            gl, wl = got.splitlines(), text.splitlines()
+            assert len(gl) == len(wl)
+            for a, b in zip(gl, wl):
+                ca, cb = a.split("\t"), b.split("\t")
+                assert ca[:12] == cb[:12]
+                pa = np.array([float(x) for x in ca[12].split(",")]); pb = np.array([float(x) for x in cb[12].split(",")])
+                assert np.all(np.abs(pa - pb) <= np.maximum(1e-12 * np.abs(pb), 16 * 2.0 ** -53 * 200))
+
+
+@pytest.mark.parametrize("key,fitting,fdr,exact", [("hist_1", "hist", True, True), ("hist_0", "hist", False, True),
+                                                   ("kde_1", "kde", True, False)])
+def test_host_logic_with_oracle_injected(tmp_path, monkeypatch, key, fitting, fdr, exact):
+    from ortho2align_b200 import pipeline
+    monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
+    _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), key, fitting, fdr, exact)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,fitting,fdr,exact", [("hist_1", "hist", True, True), ("hist_0", "hist", False, True),
+                                                   ("kde_1", "kde", True, False)])
+def test_drop_in_pipeline_on_gpu(tmp_path, monkeypatch, key, fitting, fdr, exact):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), key, fitting, fdr, exact)
+
+
+def test_cli_parses_reference_flags():
+    from ortho2align_b200.cli import make_parser
+    from ortho2align_b200.pipeline import build_orthologs, get_best_orthologs
+    a = make_parser().parse_args("build_orthologs -alignments A -background B -fitting hist -threshold 0.01 "
+                                 "--fdr -outdir O -cores 4 --silent".split())
+    assert a.func is build_orthologs and a.fdr and a.fitting == "hist" and a.threshold == 0.01 and a.timeout is None
+    b = make_parser().parse_args("get_best_orthologs -query_orthologs q -query_total qt -subject_orthologs s "
+                                 "-subject_total st -value block_length -function max -outfile_query a "
+                                 "-outfile_query_total b -outfile_subject c -outfile_subject_total d".split())
+    assert b.func is get_best_orthologs and b.value == "block_length"
+
+
+def test_lpt_shards_cover_everything_once():
+    from ortho2align_b200.pipeline import lpt_shards
+    rng = np.random.default_rng(0)
+    w = rng.integers(1, 1000, size=57)
+    for n in (1, 2, 4, 8):
+        sh = lpt_shards(w, n)
+        assert sorted(i for s in sh for i in s) == list(range(57))
+        loads = [int(w[s].sum()) for s in sh]
+        assert max(loads) - min(loads) <= int(w.max())
+
+
+def test_background_patches_follow_the_reference_order():
+    from ortho2align_b200.columnar import patch_background
+    assert patch_background(None) == [0, 1]
+    assert patch_background([]) == [1, 0]
+    assert patch_background([1]) == [1, 1, 0]
+    assert patch_background([5, 5]) == [5, 5, 1]
+    assert patch_background([1, 7]) == [1, 7, 0]
+    assert patch_background([3, 4]) == [3, 4]
