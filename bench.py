@@ -118,9 +118,8 @@ def cpu_port_rate(batch, fitter, threads, repeats=1):
     from oracle import oracle as O
     best = None
     for _ in range(repeats):
-        t0 = time.perf_counter()
-        O.build_batch(batch, fitter, True, n_threads=threads)
-        dt = time.perf_counter() - t0
+        O.build_batch(batch, fitter, True, n_threads=threads, compact=False)
+        dt = O.LAST_CALL_SECONDS          # the C call only (no Python-side result packing)
         best = dt if best is None else min(best, dt)
     return batch.n_hsp / best, best
 
@@ -129,15 +128,16 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.lib().o2a_oracle_max_threads()
+    threads = O.host_threads()
     sample_lnc = args.ref_lnc
     batch = generate(args.config, sample_lnc, args.seed, min(threads, 16))
     for _ in range(args.warmup):
-        O.build_batch(batch, args.fitter, True, n_threads=threads)
-    t0 = time.perf_counter()
+        O.build_batch(batch, args.fitter, True, n_threads=threads, compact=False)
+    dt = 0.0
     for _ in range(args.steps):
-        O.build_batch(batch, args.fitter, True, n_threads=threads)
-    dt = (time.perf_counter() - t0) / args.steps
+        O.build_batch(batch, args.fitter, True, n_threads=threads, compact=False)
+        dt += O.LAST_CALL_SECONDS
+    dt /= args.steps
     v = batch.n_hsp / dt
     sample = f"{sample_lnc} lncRNAs ({batch.n_hsp} HSPs) of the workload per step"
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -202,12 +202,19 @@ def main():
     # ---------------- device-resident arm (value) ----------------
     dbatch = DeviceBatch(batch, dev)
     dstruct = dbatch.struct(with_kde)
-    from ortho2align_b200.distributed import gather_counts
+    counts_host = torch.zeros(5, dtype=torch.int64).pin_memory()
+    counts_dev = torch.zeros(5, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(5 * world, dtype=torch.int64, device=dev)
 
     def step_device():
         c = eng.run(dstruct, params)
-        if world > 1:     # the only collective of the path: gather the result counts on every rank (NCCL)
-            gather_counts([c.n_survivors, c.n_retained, c.n_chain_hsps, c.n_chains, c.n_failed_lnc], dev)
+        if world > 1:
+            # the only collective of the path: every rank learns every shard's result counts (NCCL
+            # all_gather, stream-ordered: no extra host synchronisation inside the step)
+            counts_host[0], counts_host[1], counts_host[2] = c.n_survivors, c.n_retained, c.n_chain_hsps
+            counts_host[3], counts_host[4] = c.n_chains, c.n_failed_lnc
+            counts_dev.copy_(counts_host, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, counts_dev)
         return c
 
     for _ in range(max(args.warmup, 1)):
@@ -302,13 +309,16 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
-        threads = O.lib().o2a_oracle_max_threads()
+        threads = O.host_threads()
         k = min(args.cpu_lnc, batch.n_lnc)
         sample = batch.slice_lnc(0, k)
         rate, secs = cpu_port_rate(sample, args.fitter, threads, repeats=2)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {k} lncRNAs ({sample.n_hsp} HSPs) of the workload, {secs:.2f} s, best of 2"}
 
+    if world > 1:
+        g = gathered.view(world, 5).cpu().numpy()
+        assert int(g[rank, 0]) == int(c.n_survivors)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

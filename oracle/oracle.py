@@ -138,9 +138,24 @@ def best_chain(qstart, qend, sstart, send, score, qlen, slen, gapopen=5, gapexte
     return chain[:r].copy(), orient.value, cs.value, (float(s2[0]), float(s2[1]))
 
 
+LAST_CALL_SECONDS = 0.0   # wall time of the last o2a_oracle_build_batch C call (bench.py's cpu_baseline)
+
+
+def host_threads():
+    """Threads the CPU baseline may use: the process's CPU affinity (torchrun exports
+    OMP_NUM_THREADS=1, which must not throttle the baseline)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def build_batch(batch, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
-                best_value="block_length", best_function="max", n_threads=0):
-    """`_build` over the whole columnar batch + best-ortholog selection. Returns BatchResult."""
+                best_value="block_length", best_function="max", n_threads=0, compact=True):
+    """`_build` over the whole columnar batch + best-ortholog selection. Returns BatchResult
+    (or None with compact=False: only the C call runs, for timing)."""
+    global LAST_CALL_SECONDS
+    import time
     b = batch
     n_lnc, n_aln, n_hsp = b.n_lnc, b.n_aln, b.n_hsp
     kf = b.ensure_kde_factor() if FITTERS[fitter] == 1 else np.zeros(max(n_lnc, 1))
@@ -159,7 +174,9 @@ def build_batch(batch, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend
     surv_pq = np.zeros(cap)
     surv_keep = np.zeros(cap, dtype=np.uint8)
     chain_idx = np.zeros(cap, dtype=np.int32)
-    rc = lib().o2a_oracle_build_batch(
+    L = lib()
+    t0 = time.perf_counter()
+    rc = L.o2a_oracle_build_batch(
         n_lnc, _p(b.bg_off), _p(b.bg), _p(kf), _p(b.aln_off), _p(b.hsp_off), _p(b.qlen), _p(b.slen),
         _p(b.qstart), _p(b.qend), _p(b.sstart), _p(b.send), _p(b.score),
         FITTERS[fitter], int(bool(fdr)), float(alpha), int(gapopen), int(gapextend),
@@ -167,8 +184,11 @@ def build_batch(batch, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend
         _p(thr), _p(status), _p(best_aln), _p(n_surv), _p(n_keep), _p(chain_len), _p(chain_orient),
         _p(chain_score), _p(orient_scores), _p(surv_idx), _p(surv_p), _p(surv_pq), _p(surv_keep),
         _p(chain_idx))
+    LAST_CALL_SECONDS = time.perf_counter() - t0
     if rc != 0:
         raise RuntimeError(f"oracle build_batch failed ({rc})")
+    if not compact:
+        return None
     surv_off, (s_idx, s_p, s_pq, s_keep) = compact_slots(b.hsp_off, n_surv, surv_idx, surv_p, surv_pq, surv_keep)
     chain_off, (c_idx,) = compact_slots(b.hsp_off, chain_len, chain_idx)
     # hsp.pval of the chain HSPs: look the chain HSP up among the survivors of its alignment
