@@ -272,7 +272,10 @@ def main():
     hb = type(batch)(**{k: pinned[k].numpy() for k in pinned}, kde_factor=batch.kde_factor, names=None)
     if with_kde:
         hb.ensure_kde_factor()
-    hstruct = eng.host_struct(hb, with_kde)
+    # coordinates as one AoS array in pinned memory: read in place (zero-copy), 16 B per retained HSP
+    c4 = torch.empty((batch.n_hsp, 4), dtype=torch.int32, pin_memory=True)
+    c4.numpy()[...] = batch.coords4()
+    hstruct = eng.host_struct(hb, with_kde, coords=c4.numpy())
     del dbatch, dstruct
     torch.cuda.empty_cache()
 
@@ -290,6 +293,7 @@ def main():
         res = step_e2e()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    e2e_stage_ms = eng.stage_ms()
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,9 +305,10 @@ def main():
     zero_copy = bool(eng.lib.o2a_coords_zero_copy(eng.h))
     if zero_copy:
         # coordinates stay in pinned host memory; only the retained HSPs' (4 x int32) are read over PCIe
-        h2d = int(h2d - 4 * hb.qstart.nbytes + 16 * int(res.n_keep.sum()))
+        h2d = int(h2d - 4 * hb.qstart.nbytes + 32 * int(res.n_keep.sum()))   # one 32 B sector per retained HSP
     e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy}
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy,
+           "stage_ms_last_step": e2e_stage_ms}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

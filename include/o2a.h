@@ -79,12 +79,15 @@ typedef struct o2a_batch {
     const int64_t *hsp_off;    /* [n_aln+1] */
     const int64_t *qlen;       /* [n_aln] */
     const int64_t *slen;       /* [n_aln] */
-    const int32_t *qstart, *qend, *sstart, *send; /* [n_hsp] */
+    const int32_t *qstart, *qend, *sstart, *send; /* [n_hsp] SoA coordinates; ignored when `coords` is set */
     const double  *score;      /* [n_hsp] */
     int32_t mem;               /* O2A_MEM_HOST | O2A_MEM_DEVICE (applies to every pointer above) */
     int32_t reserved;
     int64_t max_aln_hsps;      /* max over a of hsp_off[a+1]-hsp_off[a]; 0 = let the library find out */
     int64_t max_lnc_bg;        /* max over l of bg_off[l+1]-bg_off[l];   0 = let the library find out */
+    const int32_t *coords;     /* optional [4*n_hsp] AoS (qstart,qend,sstart,send) per HSP, 16-byte aligned:
+                                  one 16 B read per retained HSP instead of four (matters for zero-copy
+                                  reads from pinned host memory); NULL = use the four SoA arrays */
 } o2a_batch;
 
 /* build_orthologs(threshold, gapopen, gapextend, fdr, fitting) + get_best_orthologs(value,
@@ -159,9 +162,10 @@ int o2a_best_chain(o2a_ctx *ctx, int64_t n, const int32_t *qstart, const int32_t
 #define O2A_STAGE_FIT 1
 #define O2A_STAGE_FILTER 2    /* score filter + ordered compaction (the HBM-bound streaming kernel) */
 #define O2A_STAGE_PQ 3        /* p-values, ranks, q, keep (survivors only) */
-#define O2A_STAGE_CHAIN 4
-#define O2A_STAGE_BEST 5
-#define O2A_STAGE_COUNT 6
+#define O2A_STAGE_GATHER 4    /* coordinates + score of the retained HSPs (zero-copy over PCIe for pinned host input) */
+#define O2A_STAGE_CHAIN 5
+#define O2A_STAGE_BEST 6
+#define O2A_STAGE_COUNT 7
 int64_t o2a_launch_count(const o2a_ctx *ctx);
 /* 1 if the last host-memory o2a_build_batch read the HSP coordinates in place (pinned, mapped) */
 int  o2a_coords_zero_copy(const o2a_ctx *ctx);

@@ -12,7 +12,7 @@ EXPORTS = ["o2a_abi_version", "o2a_create", "o2a_destroy", "o2a_last_error", "o2
            "o2a_fetch_survivors", "o2a_fetch_chains", "o2a_fitter_eval", "o2a_best_chain",
            "o2a_launch_count", "o2a_coords_zero_copy", "o2a_set_timing", "o2a_get_stage_ms"]
 
-STAGES = ["h2d", "fit", "filter", "pq", "chain", "best"]
+STAGES = ["h2d", "fit", "filter", "pq", "gather", "chain", "best"]
 
 
 class O2ABatch(C.Structure):
@@ -21,7 +21,7 @@ class O2ABatch(C.Structure):
                 ("aln_off", C.c_void_p), ("hsp_off", C.c_void_p), ("qlen", C.c_void_p), ("slen", C.c_void_p),
                 ("qstart", C.c_void_p), ("qend", C.c_void_p), ("sstart", C.c_void_p), ("send", C.c_void_p),
                 ("score", C.c_void_p), ("mem", C.c_int32), ("reserved", C.c_int32),
-                ("max_aln_hsps", C.c_int64), ("max_lnc_bg", C.c_int64)]
+                ("max_aln_hsps", C.c_int64), ("max_lnc_bg", C.c_int64), ("coords", C.c_void_p)]
 
 
 class O2AParams(C.Structure):

@@ -88,6 +88,14 @@ class ColumnarBatch:
     def n_bg(self):
         return int(self.bg_off[-1])
 
+    def coords4(self):
+        """AoS view (qstart,qend,sstart,send) per HSP for `o2a_batch.coords` (built once, cached)."""
+        c = getattr(self, "_coords4", None)
+        if c is None or len(c) != self.n_hsp:
+            c = np.ascontiguousarray(np.stack([self.qstart, self.qend, self.sstart, self.send], axis=1))
+            self._coords4 = c
+        return c
+
     def ensure_kde_factor(self):
         if self.kde_factor is None:
             n = np.diff(self.bg_off)

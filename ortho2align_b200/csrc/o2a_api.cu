@@ -48,6 +48,8 @@ struct o2a_ctx {
     DevBuf aln_lnc, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
     DevBuf n_surv, n_keep, surv_idx, surv_p, surv_pq, surv_keep;
     DevBuf chain_len, chain_orient, chain_score, orient_scores, chain_slot, best_key, best_aln;
+    DevBuf ret_coord, ret_score, ret_slot, in_coords;
+    const int4* coords4 = nullptr;    // AoS coordinates actually used (device or mapped host), or null
     DevBuf big_list, mid_list, big_count, counters;
     DevBuf fit_cnt;
     bool coords_zero_copy = false;   // qstart..send read in place from pinned, device-mapped host memory
@@ -167,14 +169,15 @@ __global__ void k_gather_surv(long long n_aln, const long long* __restrict__ hsp
 }
 
 __global__ void k_gather_chain(long long n_aln, const long long* __restrict__ hsp_off, const long long* __restrict__ off,
-                               const int* __restrict__ chain_slot, const int* __restrict__ surv_idx,
+                               const int* __restrict__ chain_slot, const int* __restrict__ ret_slot,
+                               const int* __restrict__ surv_idx,
                                const double* __restrict__ surv_pq, int* __restrict__ o_idx, double* __restrict__ o_pq)
 {
     for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
         const long long h0 = hsp_off[a], o0 = off[a];
         const int n = (int)(off[a + 1] - o0);
         for (int c = threadIdx.x; c < n; c += blockDim.x) {
-            int s = chain_slot[h0 + c];
+            int s = ret_slot[h0 + chain_slot[h0 + c]];     // retained-list position -> survivor slot
             o_idx[o0 + c] = surv_idx[h0 + s]; o_pq[o0 + c] = surv_pq[h0 + s];
         }
     }
@@ -233,7 +236,8 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->aln_lnc, &ctx->thr, &ctx->fits, &ctx->tbl_k, &ctx->tbl_cum, &ctx->status, &ctx->uv_val,
                       &ctx->uv_cnt, &ctx->uv_n, &ctx->n_surv, &ctx->n_keep, &ctx->surv_idx, &ctx->surv_p,
                       &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
-                      &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->big_list,
+                      &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->ret_coord,
+                      &ctx->ret_score, &ctx->ret_slot, &ctx->in_coords, &ctx->big_list,
                       &ctx->mid_list, &ctx->big_count, &ctx->counters, &ctx->fit_cnt, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
                       &ctx->cb_qe, &ctx->cb_ss, &ctx->cb_se, &ctx->cb_sc, &ctx->cb_id, &ctx->cb_total, &ctx->cb_prev,
                       &ctx->cb_f, &ctx->cb_chain, &ctx->off_a, &ctx->off_b, &ctx->out_i32, &ctx->out_f64a,
@@ -404,11 +408,14 @@ static int run_chain(o2a_ctx* ctx)
     ENS(chain_len, b.n_aln * sizeof(int)); ENS(chain_orient, b.n_aln); ENS(chain_score, b.n_aln * sizeof(double));
     ENS(orient_scores, 2 * b.n_aln * sizeof(double)); ENS(chain_slot, b.n_hsp * sizeof(int));
     ENS(best_key, b.n_aln * sizeof(double)); ENS(best_aln, b.n_lnc * sizeof(long long));
+    ENS(ret_coord, b.n_hsp * sizeof(int4)); ENS(ret_score, b.n_hsp * sizeof(double)); ENS(ret_slot, b.n_hsp * sizeof(int));
     if (b.n_aln > 0) {
         ChainArgs A{};
         A.n_aln = b.n_aln; A.hsp_off = (const long long*)b.hsp_off; A.aln_lnc = P<int>(ctx->aln_lnc);
         A.qlen = (const long long*)b.qlen; A.slen = (const long long*)b.slen;
         A.qstart = b.qstart; A.qend = b.qend; A.sstart = b.sstart; A.send = b.send; A.score = b.score;
+        A.coords4 = ctx->coords4;
+        A.ret_coord = P<int4>(ctx->ret_coord); A.ret_score = P<double>(ctx->ret_score); A.ret_slot = P<int>(ctx->ret_slot);
         A.n_surv = P<int>(ctx->n_surv); A.n_keep = P<int>(ctx->n_keep); A.surv_idx = P<int>(ctx->surv_idx);
         A.surv_keep = P<unsigned char>(ctx->surv_keep); A.gapopen = p.gapopen; A.gapextend = p.gapextend;
         A.best_value = p.best_value;
@@ -418,6 +425,12 @@ static int run_chain(o2a_ctx* ctx)
         A.lnc_status = P<int>(ctx->status);
         A.mid_list = P<int>(ctx->mid_list); A.mid_count = P<int>(ctx->big_count) + 2;
         A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count) + 1;
+        k_gather_retained<<<grid_for(ctx, (b.n_aln + 7) / 8, 8), 256, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+        {
+            int r = stage_event(ctx, O2A_STAGE_CHAIN);
+            if (r) return r;
+        }
         k_chain_warp<<<grid_for(ctx, (b.n_aln + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
         if (b.max_aln_hsps > CHAIN_WARP_MAX) {
@@ -499,25 +512,41 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         if ((r = upload(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, &b.score))) return r;
         // Coordinates are only ever read for the HSPs that reach the chaining (~1 %): when the caller's
         // arrays are pinned + device-mapped (o2a_host_alloc / cudaHostAlloc / cudaHostRegister) the
-        // chaining kernels gather them in place over PCIe instead of copying 16 B per HSP.
+        // gather kernel reads them in place over PCIe instead of copying 16 B per HSP.
         ctx->coords_zero_copy = false;
-        if (batch->n_hsp > 0 && !getenv("O2A_NO_ZERO_COPY")) {
-            const void* hp[4] = {batch->qstart, batch->qend, batch->sstart, batch->send};
-            const int* dp[4] = {nullptr, nullptr, nullptr, nullptr};
-            bool ok = true;
-            for (int i = 0; i < 4 && ok; ++i) {
-                cudaPointerAttributes at;
-                if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-                    cudaGetLastError(); ok = false;
-                } else dp[i] = (const int*)at.devicePointer;
+        ctx->coords4 = nullptr;
+        auto mapped = [](const void* hp) -> const void* {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hp) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                return nullptr;
             }
-            if (ok) { b.qstart = dp[0]; b.qend = dp[1]; b.sstart = dp[2]; b.send = dp[3]; ctx->coords_zero_copy = true; }
-        }
-        if (!ctx->coords_zero_copy) {
-            if ((r = upload(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, &b.qstart))) return r;
-            if ((r = upload(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, &b.qend))) return r;
-            if ((r = upload(ctx, ctx->in_ss, batch->sstart, (size_t)batch->n_hsp, &b.sstart))) return r;
-            if ((r = upload(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, &b.send))) return r;
+            return at.devicePointer;
+        };
+        const bool try_zero_copy = batch->n_hsp > 0 && !getenv("O2A_NO_ZERO_COPY");
+        if (batch->coords) {
+            const void* dp = try_zero_copy ? mapped(batch->coords) : nullptr;
+            if (dp) { ctx->coords4 = (const int4*)dp; ctx->coords_zero_copy = true; }
+            else {
+                const int32_t* d = nullptr;
+                if ((r = upload(ctx, ctx->in_coords, batch->coords, (size_t)batch->n_hsp * 4, &d))) return r;
+                ctx->coords4 = (const int4*)d;
+            }
+            b.qstart = b.qend = b.sstart = b.send = nullptr;
+        } else {
+            if (try_zero_copy) {
+                const void* dp[4] = {mapped(batch->qstart), mapped(batch->qend), mapped(batch->sstart), mapped(batch->send)};
+                if (dp[0] && dp[1] && dp[2] && dp[3]) {
+                    b.qstart = (const int*)dp[0]; b.qend = (const int*)dp[1]; b.sstart = (const int*)dp[2]; b.send = (const int*)dp[3];
+                    ctx->coords_zero_copy = true;
+                }
+            }
+            if (!ctx->coords_zero_copy) {
+                if ((r = upload(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, &b.qstart))) return r;
+                if ((r = upload(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, &b.qend))) return r;
+                if ((r = upload(ctx, ctx->in_ss, batch->sstart, (size_t)batch->n_hsp, &b.sstart))) return r;
+                if ((r = upload(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, &b.send))) return r;
+            }
         }
         if (b.max_aln_hsps <= 0) {
             long long m = 0;
@@ -530,6 +559,8 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
             b.max_lnc_bg = m;
         }
     } else {
+        ctx->coords4 = (const int4*)batch->coords;
+        ctx->coords_zero_copy = false;
         if (b.max_aln_hsps <= 0 && (r = find_max_diff(ctx, b.n_aln, (const long long*)b.hsp_off, (long long*)&b.max_aln_hsps))) return r;
         if (b.max_lnc_bg <= 0 && (r = find_max_diff(ctx, b.n_lnc, (const long long*)b.bg_off, (long long*)&b.max_lnc_bg))) return r;
     }
@@ -542,8 +573,8 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
     if ((r = run_fit(ctx))) return r;
     if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
     if ((r = run_score(ctx))) return r;       // records O2A_STAGE_PQ itself
-    if ((r = stage_event(ctx, O2A_STAGE_CHAIN))) return r;
-    if ((r = run_chain(ctx))) return r;       // records O2A_STAGE_BEST itself
+    if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
+    if ((r = run_chain(ctx))) return r;       // records O2A_STAGE_CHAIN and O2A_STAGE_BEST itself
     ENS(counters, 5 * 8);
     CU(cudaMemsetAsync(ctx->counters.p, 0, 5 * 8, ctx->stream));
     {
@@ -641,7 +672,8 @@ extern "C" int o2a_fetch_chains(o2a_ctx* ctx, int64_t* chain_off, int32_t* chain
     LAUNCH_CHECK();
     if (b.n_aln > 0 && tot > 0) {
         k_gather_chain<<<grid_for(ctx, b.n_aln, 16), 64, 0, ctx->stream>>>(
-            b.n_aln, (const long long*)b.hsp_off, P<long long>(ctx->off_b), P<int>(ctx->chain_slot), P<int>(ctx->surv_idx),
+            b.n_aln, (const long long*)b.hsp_off, P<long long>(ctx->off_b), P<int>(ctx->chain_slot), P<int>(ctx->ret_slot),
+            P<int>(ctx->surv_idx),
             P<double>(ctx->surv_pq), P<int>(ctx->out_i32), P<double>(ctx->out_f64a));
         LAUNCH_CHECK();
     }
@@ -727,6 +759,7 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     if ((r = upload(ctx, ctx->in_se, send, (size_t)n, &b.send))) return r;
     if ((r = upload(ctx, ctx->in_score, score, (size_t)n, &b.score))) return r;
     ctx->prm = o2a_params{};
+    ctx->coords4 = nullptr;
     ctx->prm.gapopen = gapopen; ctx->prm.gapextend = gapextend;
     ENS(aln_lnc, 4); ENS(status, 4); ENS(n_surv, 4); ENS(n_keep, 4);
     ENS(surv_idx, (size_t)n * 4); ENS(surv_keep, (size_t)n); ENS(surv_pq, (size_t)n * 8);
@@ -754,7 +787,7 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     CU(cudaMemcpyAsync(os2, ctx->orient_scores.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (len > 0 && chain_idx) {
-        // chain_slot holds survivor-slot positions == HSP positions here (surv_idx is the identity)
+        // chain_slot holds retained-list positions == HSP positions here (everything is retained)
         CU(cudaMemcpyAsync(chain_idx, ctx->chain_slot.p, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }

@@ -140,13 +140,16 @@ struct ChainArgs {
     const int* aln_lnc;
     const long long* qlen; const long long* slen;
     const int* qstart; const int* qend; const int* sstart; const int* send; const double* score;
+    const int4* coords4;       // optional AoS (qstart,qend,sstart,send) per HSP; replaces the four SoA arrays
     const int* n_surv; const int* n_keep;
     const int* surv_idx; const unsigned char* surv_keep;
+    // retained HSPs of alignment a, list order, at [hsp_off[a], hsp_off[a] + n_keep[a]) (k_gather_retained)
+    int4* ret_coord; double* ret_score; int* ret_slot;
     int gapopen, gapextend;
     int best_value;
     // outputs
     int* chain_len; unsigned char* chain_orient; double* chain_score; double* orient_scores;
-    int* chain_slot;           // slot layout: survivor-slot positions of the chain HSPs, chain order
+    int* chain_slot;           // slot layout: positions in the retained list of the chain HSPs, chain order
     double* best_key;          // per alignment: get_best_orthologs key of the chosen chain
     int* lnc_status;
     int* mid_list; int* mid_count;     // alignments with > CHAIN_WARP_MAX retained HSPs (-> k_chain_small)
@@ -158,16 +161,49 @@ __device__ double best_key_of_chain(const ChainArgs& A, long long h0, const int*
 {
     long long blen = 0; int lo = INT32_MAX, hi = INT32_MIN; double wsum = 0.0;
     for (int c = 0; c < len; ++c) {
-        long long h = h0 + A.surv_idx[h0 + slots[c]];
-        int qs = A.qstart[h], qe = A.qend[h];
+        const int4 q = A.ret_coord[h0 + slots[c]];
+        int qs = q.x, qe = q.y;
         int d = qe - qs; blen += d < 0 ? -d : d;
         lo = min(lo, min(qs, qe)); hi = max(hi, max(qs, qe));
-        wsum = __dadd_rn(wsum, A.score[h]);           // Python sum(): 0 + s0 + s1 + ...
+        wsum = __dadd_rn(wsum, A.ret_score[h0 + slots[c]]);   // Python sum(): 0 + s0 + s1 + ...
     }
     if (which == 0) return (double)blen;
     if (which == 1) return (double)((long long)hi - (long long)lo);
     if (which == 2) return (double)len;
     return wsum;
+}
+
+// Gather stage: one warp per alignment compacts the retained HSPs (keep flags of k_pq) in list order
+// and copies their coordinates + score next to each other. This is the only place that touches the
+// coordinate arrays — ~1 % of the HSPs — and, for host batches in pinned memory, the only traffic
+// they ever cause over PCIe (zero-copy reads straight from the caller's arrays).
+__global__ void __launch_bounds__(256)
+k_gather_retained(ChainArgs A)
+{
+    const int lane = lane_id();
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long a = warp; a < A.n_aln; a += nwarps) {
+        const int r = A.n_keep[a];
+        if (r == 0) continue;
+        const long long h0 = A.hsp_off[a];
+        const int ns = A.n_surv[a];
+        int got = 0;
+        for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
+            const int k = k0 + lane;
+            const bool keep = (k < ns) && A.surv_keep[h0 + k];
+            const unsigned b = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+                const long long pos = h0 + got + __popc(b & lanemask_lt());
+                const long long h = h0 + A.surv_idx[h0 + k];
+                int4 c;
+                if (A.coords4) c = A.coords4[h];
+                else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
+                A.ret_coord[pos] = c; A.ret_score[pos] = A.score[h]; A.ret_slot[pos] = k;
+            }
+            got += __popc(b);
+        }
+    }
 }
 
 // Warp path: one warp per alignment with at most CHAIN_WARP_MAX retained HSPs (the common case:
@@ -206,30 +242,12 @@ k_chain_warp(ChainArgs A)
             continue;
         }
         const long long h0 = A.hsp_off[a];
-        const int ns = A.n_surv[a];
-        // ---- gather: lane p gets the p-th retained HSP (list order) -----------------------------
-        int my_slot = -1;
-        int got = 0;
-        for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
-            const int k = k0 + lane;
-            const bool keep = (k < ns) && A.surv_keep[h0 + k];
-            const unsigned b = __ballot_sync(FULL_MASK, keep);
-            // the j-th kept element of this chunk goes to lane got + j
-            const int dst = got + __popc(b & lanemask_lt());
-            const int src_k = keep ? k : -1;
-            // each lane pulls from the lane holding "its" element: find the (lane-got)-th set bit of b
-            const int want = lane - got;
-            int src_lane = -1;
-            if (want >= 0 && want < __popc(b)) src_lane = __fns(b, 0, want + 1);
-            const int pulled = __shfl_sync(FULL_MASK, src_k, src_lane < 0 ? 0 : src_lane);
-            if (src_lane >= 0) my_slot = pulled;
-            (void)dst;
-            got += __popc(b);
-        }
+        // lane p owns the p-th retained HSP (list order); my_slot = its position in the retained list
+        const int my_slot = lane;
         int qs = 0, qe = 0, ss = 0, se = 0; double sc = 0.0; bool dir = false; bool bad = false;
         if (lane < r) {
-            const long long h = h0 + A.surv_idx[h0 + my_slot];
-            qs = A.qstart[h]; qe = A.qend[h]; ss = A.sstart[h]; se = A.send[h]; sc = A.score[h];
+            const int4 c = A.ret_coord[h0 + lane];
+            qs = c.x; qe = c.y; ss = c.z; se = c.w; sc = A.ret_score[h0 + lane];
             dir = (se - ss > 0);                         // alignment.py:107-110
             bad = !(qe - qs > 0);                        // orientation None
         }
@@ -363,7 +381,6 @@ k_chain_small(ChainArgs A)
     __shared__ int s_prev[C + 2], s_f[C + 2];
     __shared__ int s_chain[2][C];
     __shared__ int s_len[2];
-    __shared__ int s_scan[CHAIN_THREADS / 32 + 2];
     __shared__ int s_bad;
     const int tid = threadIdx.x;
 
@@ -371,7 +388,6 @@ k_chain_small(ChainArgs A)
     for (int bi = blockIdx.x; bi < nmid; bi += gridDim.x) {
         const long long a = A.mid_list[bi];
         const long long h0 = A.hsp_off[a];
-        const int ns = A.n_surv[a];
         const int r = A.n_keep[a];
         const int l = A.aln_lnc[a];
         if (r > C) {
@@ -379,24 +395,15 @@ k_chain_small(ChainArgs A)
             continue;
         }
         if (tid == 0) s_bad = 0;
-        // ---- gather the retained HSPs in list order ------------------------------------------
-        int got = 0;
-        for (int k0 = 0; k0 < ns; k0 += CHAIN_THREADS) {
-            int k = k0 + tid;
-            bool keep = (k < ns) && A.surv_keep[h0 + k];
-            int tot;
-            int pos = cta_exclusive_scan(keep ? 1 : 0, s_scan, &tot);
-            if (keep) {
-                long long h = h0 + A.surv_idx[h0 + k];
-                int p = got + pos;
-                int qs = A.qstart[h], qe = A.qend[h], ss = A.sstart[h], se = A.send[h];
-                t_qs[p] = qs; t_qe[p] = qe; t_ss[p] = ss; t_se[p] = se; t_sc[p] = A.score[h]; t_id[p] = k;
-                t_dir[p] = (se - ss > 0) ? 1 : 0;                  // alignment.py:107-110
-                if (!(qe - qs > 0)) s_bad = 1;                      // orientation None
-            }
-            got += tot;
-            __syncthreads();
+        // ---- the retained HSPs, list order (k_gather_retained) --------------------------------------
+        __syncthreads();
+        for (int p = tid; p < r; p += CHAIN_THREADS) {
+            const int4 c = A.ret_coord[h0 + p];
+            t_qs[p] = c.x; t_qe[p] = c.y; t_ss[p] = c.z; t_se[p] = c.w; t_sc[p] = A.ret_score[h0 + p]; t_id[p] = p;
+            t_dir[p] = (c.w - c.z > 0) ? 1 : 0;                    // alignment.py:107-110
+            if (!(c.y - c.x > 0)) s_bad = 1;                        // orientation None
         }
+        __syncthreads();
         if (s_bad) {                                   // reference raises in _split_orientations
             if (tid == 0) {
                 atomicMax(&A.lnc_status[l], 1);
@@ -476,24 +483,23 @@ k_chain_big(ChainArgs A, ChainBigScratch S)
     for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
         const long long a = A.big_list[b];
         const long long h0 = A.hsp_off[a];
-        const int ns = A.n_surv[a];
         const int l = A.aln_lnc[a];
         if (tid == 0) s_bad = 0;
         __syncthreads();
         double sco[2];
         for (int o = 0; o < 2; ++o) {
-            // gather survivor slots of this orientation, in list order, as (key, slot) pairs
+            // retained HSPs of this orientation, in list order, as (key, retained-list position) pairs
             int n_o = 0;
-            for (int k0i = 0; k0i < ns; k0i += CHAINBIG_THREADS) {
+            const int r = A.n_keep[a];
+            for (int k0i = 0; k0i < r; k0i += CHAINBIG_THREADS) {
                 int k = k0i + tid;
                 bool take = false; unsigned long long key = 0;
-                if (k < ns && A.surv_keep[h0 + k]) {
-                    long long h = h0 + A.surv_idx[h0 + k];
-                    int qs = A.qstart[h], qe = A.qend[h], ss = A.sstart[h], se = A.send[h];
-                    if (!(qe - qs > 0)) s_bad = 1;
-                    bool dir = (se - ss > 0);
+                if (k < r) {
+                    const int4 c = A.ret_coord[h0 + k];
+                    if (!(c.y - c.x > 0)) s_bad = 1;
+                    bool dir = (c.w - c.z > 0);
                     take = (dir == (o == 0));
-                    key = ((unsigned long long)((unsigned)qs ^ 0x80000000u) << 32) | (unsigned long long)((unsigned)ss ^ 0x80000000u);
+                    key = ((unsigned long long)((unsigned)c.x ^ 0x80000000u) << 32) | (unsigned long long)((unsigned)c.z ^ 0x80000000u);
                 }
                 int tot;
                 int pos = cta_exclusive_scan(take ? 1 : 0, s_scan, &tot);
@@ -513,9 +519,9 @@ k_chain_big(ChainArgs A, ChainBigScratch S)
             const unsigned int* vs = where ? v1 : v0;
             for (int p = tid; p < n_o; p += CHAINBIG_THREADS) {
                 int k = (int)vs[p];
-                long long h = h0 + A.surv_idx[h0 + k];
-                M.qs[p] = A.qstart[h]; M.qe[p] = A.qend[h]; M.ss[p] = A.sstart[h]; M.se[p] = A.send[h];
-                M.sc[p] = A.score[h]; M.id[p] = k;
+                const int4 c = A.ret_coord[h0 + k];
+                M.qs[p] = c.x; M.qe[p] = c.y; M.ss[p] = c.z; M.se[p] = c.w;
+                M.sc[p] = A.ret_score[h0 + k]; M.id[p] = k;
             }
             __syncthreads();
             ChainGeom g{n_o, o == 0, A.qlen[a], A.slen[a], (double)A.gapopen, (double)A.gapextend};

@@ -25,7 +25,7 @@ def _p(a):
 class DeviceBatch:
     """A ColumnarBatch resident in HBM (torch tensors own the memory; the library gets raw pointers)."""
 
-    def __init__(self, batch: ColumnarBatch, device):
+    def __init__(self, batch: ColumnarBatch, device, aos=True):
         import torch
         self.n_lnc, self.n_aln, self.n_hsp, self.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
         self.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
@@ -34,6 +34,9 @@ class DeviceBatch:
         for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
             self.t[k] = torch.from_numpy(getattr(batch, k)).to(device, non_blocking=False)
         self.t["kde_factor"] = torch.from_numpy(batch.ensure_kde_factor()).to(device)
+        self.aos = aos
+        if aos:
+            self.t["coords"] = torch.from_numpy(batch.coords4()).to(device)
         self.nbytes = sum(v.numel() * v.element_size() for v in self.t.values())
 
     def struct(self, with_kde):
@@ -42,6 +45,7 @@ class DeviceBatch:
         for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
             setattr(s, k, self.t[k].data_ptr())
         s.kde_factor = self.t["kde_factor"].data_ptr() if with_kde else None
+        s.coords = self.t["coords"].data_ptr() if self.aos else None
         s.mem = 1
         s.max_aln_hsps, s.max_lnc_bg = self.max_aln_hsps, self.max_lnc_bg
         return s
@@ -82,7 +86,7 @@ class Engine:
         self._check(self.lib.o2a_set_timing(self.h, 1 if on else 0), "o2a_set_timing")
 
     def stage_ms(self):
-        ms = (C.c_float * 6)()
+        ms = (C.c_float * len(_lib.STAGES))()
         self._check(self.lib.o2a_get_stage_ms(self.h, ms), "o2a_get_stage_ms")
         return dict(zip(_lib.STAGES, [float(x) for x in ms]))
 
@@ -99,7 +103,8 @@ class Engine:
         return p
 
     @staticmethod
-    def host_struct(batch: ColumnarBatch, with_kde):
+    def host_struct(batch: ColumnarBatch, with_kde, coords=None):
+        """`coords`: optional AoS int32 [n_hsp, 4] array (e.g. pinned) used instead of the SoA arrays."""
         s = _lib.O2ABatch()
         s.n_lnc, s.n_aln, s.n_hsp, s.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
         for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
@@ -107,6 +112,7 @@ class Engine:
             assert a.flags["C_CONTIGUOUS"]
             setattr(s, k, a.ctypes.data)
         s.kde_factor = batch.ensure_kde_factor().ctypes.data if with_kde else None
+        s.coords = coords.ctypes.data if coords is not None else None
         s.mem = 0
         s.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
         s.max_lnc_bg = int(np.diff(batch.bg_off).max()) if batch.n_lnc else 0
@@ -151,10 +157,10 @@ class Engine:
                            surv_off, surv_idx, surv_p, surv_pq, surv_keep, chain_off, chain_idx, chain_pq)
 
     def build_batch(self, batch: ColumnarBatch, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
-                    best_value="block_length", best_function="max", survivors=True) -> BatchResult:
+                    best_value="block_length", best_function="max", survivors=True, aos=False) -> BatchResult:
         """Host buffers in, host results out (the e2e boundary)."""
         p = self.params(fitter, fdr, alpha, gapopen, gapextend, best_value, best_function)
-        s = self.host_struct(batch, with_kde=(fitter == "kde"))
+        s = self.host_struct(batch, with_kde=(fitter == "kde"), coords=batch.coords4() if aos else None)
         self.run(s, p)
         return self.fetch(survivors=survivors)
 

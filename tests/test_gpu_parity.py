@@ -64,6 +64,8 @@ def test_synthetic_vs_oracle(engine, cfg, kw, fitter, fdr):
     exp = O.build_batch(b, fitter, fdr)
     got = engine.build_batch(b, fitter, fdr)
     compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr}")
+    got = engine.build_batch(b, fitter, fdr, aos=True)          # AoS coordinates (o2a_batch.coords)
+    compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr} aos")
     assert engine.counts.n_survivors == int(exp.n_surv.sum())
     assert engine.counts.n_chains == int((exp.chain_len > 0).sum())
 
@@ -141,11 +143,33 @@ def test_device_resident_inputs_match_host_inputs(engine):
     from ortho2align_b200.engine import DeviceBatch
     b = synth.workload(2, n_lnc=16, seed=12)
     host = engine.build_batch(b, "hist", True)
-    db = DeviceBatch(b, torch.device("cuda:0"))
-    torch.cuda.synchronize()
-    engine.run(db.struct(with_kde=False), engine.params("hist", True))
-    dev = engine.fetch()
-    compare_results(dev, host, exact_p=True, what="device-vs-host")
+    for aos in (True, False):
+        db = DeviceBatch(b, torch.device("cuda:0"), aos=aos)
+        torch.cuda.synchronize()
+        engine.run(db.struct(with_kde=False), engine.params("hist", True))
+        dev = engine.fetch()
+        compare_results(dev, host, exact_p=True, what=f"device-vs-host aos={aos}")
+
+
+def test_pinned_host_inputs_use_zero_copy_coordinates(engine):
+    import torch
+    from ortho2align_b200 import synth
+    from ortho2align_b200.columnar import ColumnarBatch
+    b = synth.workload(2, n_lnc=16, seed=13)
+    ref = engine.build_batch(b, "hist", True)
+    pinned = {}
+    for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
+        src = getattr(b, k)
+        t = torch.empty(src.shape, dtype=torch.from_numpy(src[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = src
+        pinned[k] = t
+    hb = ColumnarBatch(**{k: v.numpy() for k, v in pinned.items()})
+    c4 = torch.empty((b.n_hsp, 4), dtype=torch.int32, pin_memory=True)
+    c4.numpy()[...] = b.coords4()
+    for coords in (None, c4.numpy()):
+        engine.run(engine.host_struct(hb, False, coords=coords), engine.params("hist", True))
+        assert engine.lib.o2a_coords_zero_copy(engine.h) == 1
+        compare_results(engine.fetch(), ref, exact_p=True, what="pinned zero-copy")
 
 
 def test_round_trip_properties_at_scale(engine):
