@@ -377,7 +377,7 @@ static int run_score(o2a_ctx* ctx)
     if (r) return r;
     PqArgs A{};
     A.n_aln = b.n_aln; A.hsp_off = (const long long*)b.hsp_off; A.aln_lnc = P<int>(ctx->aln_lnc);
-    A.lnc_status = P<int>(ctx->status); A.n_surv = P<int>(ctx->n_surv);
+    A.lnc_status = P<int>(ctx->status); A.n_surv = P<int>(ctx->n_surv); A.thr = P<double>(ctx->thr);
     A.fits = P<LncFit>(ctx->fits); A.tbl_k = P<int>(ctx->tbl_k); A.tbl_cum = P<double>(ctx->tbl_cum);
     A.bg_off = (const long long*)b.bg_off;
     A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt); A.uv_n = P<int>(ctx->uv_n);
@@ -385,7 +385,7 @@ static int run_score(o2a_ctx* ctx)
     A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
     A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep);
     A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
-    k_pq<<<grid_for(ctx, b.n_aln, 12), PQ_THREADS, 0, ctx->stream>>>(A);
+    k_pq<<<grid_for(ctx, b.n_aln, 16), PQ_THREADS, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
     if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
         int g2 = grid_for(ctx, b.n_aln, 2);

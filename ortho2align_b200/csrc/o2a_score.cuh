@@ -18,7 +18,7 @@ namespace o2a {
 constexpr int FILTER_THREADS = 256;
 constexpr int FILTER_ROWS = 4;                       // double2 per thread per row
 constexpr int FILTER_TILE = FILTER_THREADS * 2 * FILTER_ROWS;
-constexpr int PQ_THREADS = 128;
+constexpr int PQ_THREADS = 64;
 constexpr int RANK_SMALL_MAX = 1024;                 // survivors ranked in shared memory
 constexpr int TBL_SMEM_MAX = 256;
 
@@ -118,6 +118,7 @@ struct PqArgs {
     const int* aln_lnc;
     const int* lnc_status;
     const int* n_surv;
+    const double* thr;
     // hist
     const LncFit* fits; const int* tbl_k; const double* tbl_cum; const long long* bg_off;
     // kde / empirical
@@ -128,13 +129,45 @@ struct PqArgs {
     int* big_list; int* big_count;
 };
 
+// Survivor scores of one alignment are mostly small integers (BLAST raw scores) with few distinct
+// values, and p = sf(score) depends on the score only. k_pq therefore works on SCORE CLASSES:
+//   direct classes   : integer-valued scores in [floor(thr), floor(thr) + PQ_DIRECT)  (slot = offset)
+//   overflow classes : anything else (cut HSPs with fractional scores, huge scores), one per HSP
+// sf is evaluated once per class; for every class L = #{survivors with strictly smaller p} and the
+// tie group g = first class with the same p; one warp then walks the survivors in list order and
+// counts, per tie group, the survivors seen so far (match.any) -> the stable rank
+//   rank_k = 1 + L[class_k] + #{j < k : p_j == p_k}
+// exactly as np.argsort(kind='stable') would assign it. More than PQ_OVER overflow classes fall back
+// to the plain all-pairs rank.
+constexpr int PQ_DIRECT = 256;
+constexpr int PQ_OVER = 128;
+constexpr int PQ_SLOTS = PQ_DIRECT + PQ_OVER;
+
+struct PqFit {
+    LncFit f; const int* tk; const double* tc;
+    const int* uval; const int* ucnt; int unv; double kfac, nbg; int fitter;
+};
+
+__device__ __forceinline__ double pq_sf(double x, const PqFit& F)
+{
+    if (F.fitter == 0) return hist_sf(x, F.f, F.tk, F.tc);
+    if (F.fitter == 1) return kde_sf_compressed(x, F.uval, F.ucnt, F.unv, F.kfac, F.nbg);
+    return emp_sf_compressed(x, F.uval, F.ucnt, F.unv, F.nbg);
+}
+
 __global__ void __launch_bounds__(PQ_THREADS)
 k_pq(PqArgs A)
 {
-    __shared__ double s_p[RANK_SMALL_MAX];
+    __shared__ double s_p[RANK_SMALL_MAX];          // fallback path only
     __shared__ int s_tk[TBL_SMEM_MAX];
     __shared__ double s_tc[TBL_SMEM_MAX];
-    __shared__ int s_keepcnt;
+    __shared__ int s_cnt[PQ_SLOTS];                 // class multiplicity, later the running tie counters
+    __shared__ double s_pe[PQ_SLOTS];               // p of the class
+    __shared__ int s_L[PQ_SLOTS];                   // survivors with strictly smaller p
+    __shared__ short s_g[PQ_SLOTS];                 // tie group = first slot with the same p
+    __shared__ double s_ox[PQ_OVER];                // scores of the overflow classes
+    __shared__ short s_slot[RANK_SMALL_MAX];        // class of every survivor
+    __shared__ int s_keepcnt, s_nover, s_maxslot;
     const int tid = threadIdx.x, lane = lane_id();
 
     for (long long a = blockIdx.x; a < A.n_aln; a += gridDim.x) {
@@ -143,55 +176,81 @@ k_pq(PqArgs A)
         const int l = A.aln_lnc[a];
         const long long h0 = A.hsp_off[a];
         const int m = (int)(A.hsp_off[a + 1] - h0);
-        LncFit f; const int* tk = nullptr; const double* tc = nullptr;
-        const int* uval = nullptr; const int* ucnt = nullptr; int unv = 0; double kfac = 1.0, nbg = 1.0;
+        PqFit F; F.fitter = A.fitter; F.tk = nullptr; F.tc = nullptr; F.uval = nullptr; F.ucnt = nullptr;
+        F.unv = 0; F.kfac = 1.0; F.nbg = 1.0;
+        __syncthreads();                              // previous alignment is done with the shared tables
         if (A.fitter == 0) {
-            f = A.fits[l];
+            F.f = A.fits[l];
             const long long tb = A.bg_off[l] >> 1;
-            tk = A.tbl_k + tb; tc = A.tbl_cum + tb;
-            if (f.tbl_n <= TBL_SMEM_MAX) {
-                for (int t = tid; t < f.tbl_n; t += PQ_THREADS) { s_tk[t] = tk[t]; s_tc[t] = tc[t]; }
-                tk = s_tk; tc = s_tc;
+            F.tk = A.tbl_k + tb; F.tc = A.tbl_cum + tb;
+            if (F.f.tbl_n <= TBL_SMEM_MAX) {
+                for (int t = tid; t < F.f.tbl_n; t += PQ_THREADS) { s_tk[t] = F.tk[t]; s_tc[t] = F.tc[t]; }
+                F.tk = s_tk; F.tc = s_tc;
             }
         } else {
             const long long b0 = A.bg_off[l];
-            uval = A.uv_val + b0; ucnt = A.uv_cnt + b0; unv = A.uv_n[l];
-            nbg = (double)(A.bg_off[l + 1] - b0);
-            if (A.fitter == 1) kfac = A.kde_factor[l];
+            F.uval = A.uv_val + b0; F.ucnt = A.uv_cnt + b0; F.unv = A.uv_n[l];
+            F.nbg = (double)(A.bg_off[l + 1] - b0);
+            if (A.fitter == 1) F.kfac = A.kde_factor[l];
         }
-        if (tid == 0) s_keepcnt = 0;
-        __syncthreads();
-        for (int k = tid; k < ns; k += PQ_THREADS) {
-            const double x = A.surv_p[h0 + k];
-            double p;
-            if (A.fitter == 0) p = hist_sf(x, f, tk, tc);
-            else if (A.fitter == 1) p = kde_sf_compressed(x, uval, ucnt, unv, kfac, nbg);
-            else p = emp_sf_compressed(x, uval, ucnt, unv, nbg);
-            A.surv_p[h0 + k] = p;
-            if (k < RANK_SMALL_MAX) s_p[k] = p;
-            if (!A.fdr) { A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1; }   // pipeline.py:778-780
-        }
-        if (!A.fdr) {
-            if (tid == 0) A.n_keep[a] = ns;
+        double* xs = A.surv_p + h0;                   // in: scores, out: p-values
+        if (ns > RANK_SMALL_MAX) {
+            // big survivor set: p per survivor here, ranks by radix sort in k_rank_big
             __syncthreads();
+            for (int k = tid; k < ns; k += PQ_THREADS) {
+                const double p = pq_sf(xs[k], F);
+                xs[k] = p;
+                if (!A.fdr) { A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1; }
+            }
+            if (tid == 0) {
+                if (A.fdr) { A.n_keep[a] = 0; int slot = atomicAdd(A.big_count, 1); A.big_list[slot] = (int)a; }
+                else A.n_keep[a] = ns;
+            }
             continue;
         }
+        // ---- classes ---------------------------------------------------------------------------------
+        for (int t = tid; t < PQ_SLOTS; t += PQ_THREADS) s_cnt[t] = 0;
+        if (tid == 0) { s_keepcnt = 0; s_nover = 0; s_maxslot = 0; }
         __syncthreads();
-        if (ns <= RANK_SMALL_MAX) {
-            const double md = (double)m;              // total_hsps = len(alignment._all_HSPs)
+        const double thr = A.thr[l];
+        const long long xlo = (long long)floor(thr);
+        for (int k = tid; k < ns; k += PQ_THREADS) {
+            const double x = xs[k];
+            const long long xi = (long long)x;
+            const long long off = xi - xlo;
+            int slot;
+            if ((double)xi == x && off >= 0 && off < PQ_DIRECT) {
+                slot = (int)off;
+                atomicAdd(&s_cnt[slot], 1);
+                atomicMax(&s_maxslot, slot);
+            } else {
+                const int o = atomicAdd(&s_nover, 1);
+                slot = PQ_DIRECT + (o < PQ_OVER ? o : 0);
+                if (o < PQ_OVER) { s_ox[o] = x; s_cnt[slot] = 1; }
+            }
+            s_slot[k] = (short)slot;
+        }
+        __syncthreads();
+        const int nover = s_nover;
+        if (nover > PQ_OVER) {
+            // ---- fallback: all-pairs stable rank ---------------------------------------------------------
+            for (int k = tid; k < ns; k += PQ_THREADS) {
+                const double p = pq_sf(xs[k], F);
+                s_p[k] = p; xs[k] = p;
+                if (!A.fdr) { A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1; }
+            }
+            __syncthreads();
+            if (!A.fdr) { if (tid == 0) A.n_keep[a] = ns; continue; }
+            const double md = (double)m;
             int kept = 0;
             for (int k = tid; k < ns; k += PQ_THREADS) {
                 const double p = s_p[k];
-                // stable rank: 1 + #{j < k : p_j <= p} + #{j > k : p_j < p}
                 int rank = 1;
-#pragma unroll 4
                 for (int j = 0; j < k; ++j) rank += (s_p[j] <= p);
-#pragma unroll 4
                 for (int j = k + 1; j < ns; ++j) rank += (s_p[j] < p);
-                double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);
-                bool keep = q <= A.alpha;
-                A.surv_pq[h0 + k] = q;
-                A.surv_keep[h0 + k] = keep ? 1 : 0;
+                const double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);
+                const bool keep = q <= A.alpha;
+                A.surv_pq[h0 + k] = q; A.surv_keep[h0 + k] = keep ? 1 : 0;
                 kept += keep;
             }
 #pragma unroll
@@ -199,12 +258,74 @@ k_pq(PqArgs A)
             if (lane == 0 && kept) atomicAdd(&s_keepcnt, kept);
             __syncthreads();
             if (tid == 0) A.n_keep[a] = s_keepcnt;
-        } else if (tid == 0) {
-            A.n_keep[a] = 0;
-            int slot = atomicAdd(A.big_count, 1);
-            A.big_list[slot] = (int)a;
+            continue;
+        }
+        // ---- sf once per class -----------------------------------------------------------------------------
+        const int ndir = s_maxslot + 1;
+        const int ncls = ndir + nover;                 // class index e -> slot
+        for (int e = tid; e < ncls; e += PQ_THREADS) {
+            const int slot = e < ndir ? e : PQ_DIRECT + (e - ndir);
+            if (s_cnt[slot] > 0) s_pe[slot] = pq_sf(e < ndir ? (double)(xlo + slot) : s_ox[e - ndir], F);
         }
         __syncthreads();
+        if (!A.fdr) {                                  // pipeline.py:778-780: hsp.pval = p, nothing dropped
+            for (int k = tid; k < ns; k += PQ_THREADS) {
+                const double p = s_pe[s_slot[k]];
+                xs[k] = p; A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1;
+            }
+            if (tid == 0) A.n_keep[a] = ns;
+            continue;
+        }
+        // ---- per class: survivors with strictly smaller p, and the tie group -----------------------------------
+        for (int e = tid; e < ncls; e += PQ_THREADS) {
+            const int slot = e < ndir ? e : PQ_DIRECT + (e - ndir);
+            if (s_cnt[slot] == 0) continue;
+            const double p = s_pe[slot];
+            int L = 0, g = slot;
+            for (int e2 = 0; e2 < ncls; ++e2) {
+                const int s2 = e2 < ndir ? e2 : PQ_DIRECT + (e2 - ndir);
+                const int c2 = s_cnt[s2];
+                if (c2 == 0) continue;
+                const double p2 = s_pe[s2];
+                L += (p2 < p) ? c2 : 0;
+                if (p2 == p && s2 < g) g = s2;
+            }
+            s_L[slot] = L; s_g[slot] = (short)g;
+        }
+        __syncthreads();
+        for (int t = tid; t < PQ_SLOTS; t += PQ_THREADS) s_cnt[t] = 0;     // now: survivors seen per tie group
+        __syncthreads();
+        // ---- one warp walks the survivors in list order ----------------------------------------------------------
+        if (tid < 32) {
+            const double md = (double)m;              // total_hsps = len(alignment._all_HSPs)
+            int kept = 0;
+            for (int k0 = 0; k0 < ns; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < ns;
+                const unsigned vm = __ballot_sync(FULL_MASK, valid);
+                int slot = 0, g = 0, base = 0, before = 0; unsigned peers = 0;
+                if (valid) {
+                    slot = s_slot[k]; g = s_g[slot];
+                    peers = __match_any_sync(vm, g);
+                    before = __popc(peers & lanemask_lt());
+                    base = s_cnt[g];
+                }
+                __syncwarp();
+                if (valid && before == 0) s_cnt[g] = base + __popc(peers);
+                __syncwarp();
+                if (valid) {
+                    const double p = s_pe[slot];
+                    const int rank = 1 + s_L[slot] + base + before;
+                    const double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);
+                    const bool keep = q <= A.alpha;
+                    xs[k] = p; A.surv_pq[h0 + k] = q; A.surv_keep[h0 + k] = keep ? 1 : 0;
+                    kept += keep;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(FULL_MASK, kept, d);
+            if (lane == 0) A.n_keep[a] = kept;
+        }
     }
 }
 
