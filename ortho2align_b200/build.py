@@ -13,6 +13,24 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
 
+INGEST_LIB = os.path.join(LIB_DIR, "libo2a_ingest.so")
+INGEST_SRC = os.path.join(CSRC, "o2a_ingest.cpp")
+
+
+def build_ingest(force=False):
+    """Host-only C++ JSON ingest library (g++)."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    hdr = os.path.join(os.path.dirname(HERE), "include", "o2a_ingest.h")
+    if not force and os.path.exists(INGEST_LIB) and all(os.path.getmtime(INGEST_LIB) >= os.path.getmtime(d) for d in (INGEST_SRC, hdr)):
+        return INGEST_LIB
+    cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-o", INGEST_LIB, INGEST_SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building libo2a_ingest.so")
+    return INGEST_LIB
+
+
 def _deps():
     out = list(SOURCES)
     for fn in os.listdir(CSRC):
@@ -40,3 +58,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_ingest(force="--force" in sys.argv))

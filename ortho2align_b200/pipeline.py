@@ -68,6 +68,42 @@ def _load_lncrna(align_file, bg_file):
     return alignment_dicts, pack_lncrna(alignment_dicts, bg)
 
 
+def _ingest_json(alignments_files, bg_files):
+    out = []
+    for af, bf in zip(alignments_files, bg_files):
+        alignment_dicts = None
+        try:
+            alignment_dicts, batch = _load_lncrna(af, bf)
+        except PackError as e:
+            qr = Range.from_dict(alignment_dicts[0]["qrange"]) if alignment_dicts else None
+            out.append(ExceptionLogger(e, qr))
+            continue
+        d = alignment_dicts
+        out.append((batch, len(d), (lambda k, d=d: d[k]["qrange"]), (lambda k, d=d: d[k]["srange"]),
+                    (lambda k, j, d=d: d[k]["HSPs"][j])))
+    return out
+
+
+def _ingest_native(alignments_files, bg_files, threads):
+    from . import ingest as native
+    r = native.load_files(alignments_files, bg_files, threads=threads or 1)
+    out = [None] * len(alignments_files)
+    for i in np.nonzero(r.file_status)[0]:
+        if r.file_status[i] == 1:
+            raise ValueError(f"{alignments_files[i]}: {r.errors[int(i)]}")
+        # values outside the columnar types: report like the Python packer does
+        with open(alignments_files[i]) as f:
+            d = json.load(f)
+        out[i] = ExceptionLogger(PackError(r.errors[int(i)]), Range.from_dict(d[0]["qrange"]) if d else None)
+    b = r.batch
+    for l, i in enumerate(r.lnc_file):
+        a0, a1 = int(b.aln_off[l]), int(b.aln_off[l + 1])
+        out[int(i)] = (b.slice_lnc(l, l + 1), a1 - a0,
+                       (lambda k, a0=a0: r.range_dict(a0 + k, "q")), (lambda k, a0=a0: r.range_dict(a0 + k, "s")),
+                       (lambda k, j, a0=a0: r.hsp_dict(int(b.hsp_off[a0 + k]) + j)))
+    return out
+
+
 def _run_shards(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
     """One Engine (= one o2a_ctx) per GPU, each on its own thread; ctypes releases the GIL."""
     from .engine import Engine
@@ -98,12 +134,15 @@ def _run_shards(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
 
 
 def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gapopen=5, gapextend=2,
-                    fdr=False, cores=1, timeout=None, silent=False, stats_filename=None, devices=None):
+                    fdr=False, cores=1, timeout=None, silent=False, stats_filename=None, devices=None,
+                    ingest="native"):
     """A build_orthologs step of the pipeline (signature of `pipeline.py:801-812`).
 
-    `cores`/`timeout` are accepted for CLI compatibility: the per-lncRNA process pool they
-    configured does not exist here. `devices`: CUDA device indices (default: [0]); with several,
-    lncRNAs are LPT-sharded by HSP count and every GPU runs its shard independently.
+    `cores` = threads of the native JSON ingest (the per-lncRNA process pool it configured in the
+    reference does not exist here); `timeout` is accepted for CLI compatibility. `devices`: CUDA
+    device indices (default: [0]); with several, lncRNAs are LPT-sharded by HSP count and every
+    GPU runs its shard independently. `ingest`: 'native' (libo2a_ingest.so, C++) or 'json'
+    (json.load + Python packer; same results, used to cross-check the native reader).
     `fitting`: 'hist' | 'kde' (reference) or 'empirical' (extension).
     """
     alignments_dir = Path(alignments)
@@ -119,24 +158,18 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     total_bgs = len(bg_files)
 
     # ---- ingest -------------------------------------------------------------------------------
-    loaded = []        # per file: (alignment_dicts, batch) or an ExceptionLogger
-    for af, bf in zip(alignments_files, bg_files):
-        alignment_dicts, batch = None, None
-        try:
-            alignment_dicts, batch = _load_lncrna(af, bf)
-            loaded.append((alignment_dicts, batch))
-        except PackError as e:
-            qr = Range.from_dict(alignment_dicts[0]["qrange"]) if alignment_dicts else None
-            loaded.append(ExceptionLogger(e, qr))
+    # per file: an ExceptionLogger, or (single-lncRNA batch, n_alignments, accessors)
+    loaded = _ingest_native(alignments_files, bg_files, cores) if ingest == "native" \
+        else _ingest_json(alignments_files, bg_files)
     ok_idx = [i for i, x in enumerate(loaded) if not isinstance(x, ExceptionLogger)]
 
     # ---- compute: shard by lncRNA across GPUs, one batched call each ---------------------------------
     per_lnc = {}
     if ok_idx:
         n_dev = min(len(devices), len(ok_idx))
-        weights = [loaded[i][1].n_hsp + 1 for i in ok_idx]
+        weights = [loaded[i][0].n_hsp + 1 for i in ok_idx]
         shards = lpt_shards(weights, n_dev)
-        batches = [concat_batches([loaded[ok_idx[j]][1] for j in shard]) for shard in shards]
+        batches = [concat_batches([loaded[ok_idx[j]][0] for j in shard]) for shard in shards]
         results = _run_shards(batches, devices[:n_dev], fitting, fdr, threshold, gapopen, gapextend)
         for shard, batch, res in zip(shards, batches, results):
             for local, j in enumerate(shard):
@@ -148,24 +181,23 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
         if isinstance(item, ExceptionLogger):
             exceptions.append(item)
             continue
-        alignment_dicts, _ = item
+        _, n_alns, qrange_of, srange_of, hsp_of = item
         batch, res, l = per_lnc[i]
-        qrange0 = Range.from_dict(alignment_dicts[0]["qrange"]) if alignment_dicts else None
         if res.status[l] != STATUS_OK:
             st = int(res.status[l])
             err = KeyError(None) if st == 1 else (RuntimeError if st == 2 else ValueError)(_STATUS_TEXT.get(st, st))
-            exceptions.append(ExceptionLogger(err, qrange0))
+            exceptions.append(ExceptionLogger(err, Range.from_dict(qrange_of(0)) if n_alns else None))
             continue
         q_orth, s_orth, q_dropped, s_dropped, aligned = [], [], None, [], False
         a0 = int(batch.aln_off[l])
-        for k, d in enumerate(alignment_dicts):
+        for k in range(n_alns):
             a = a0 + k
-            qrange = Range.from_dict(d["qrange"])
-            srange = Range.from_dict(d["srange"])
+            qrange = Range.from_dict(qrange_of(k))
+            srange = Range.from_dict(srange_of(k))
             srange.name = qrange.name                                   # pipeline.py:781
             c0, c1 = int(res.chain_off[a]), int(res.chain_off[a + 1])
             if c1 > c0:
-                hsps = [d["HSPs"][j] for j in res.chain_idx[c0:c1]]
+                hsps = [hsp_of(k, int(j)) for j in res.chain_idx[c0:c1]]
                 rec = chain_records(hsps, as_pvals(res.chain_pq[c0:c1]), qrange, srange.chrom, qrange.name)
                 q_orth.append((rec[0], rec[1]))
                 s_orth.append((rec[2], rec[3]))

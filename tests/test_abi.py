@@ -27,6 +27,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.o2a_abi_version() == 1
 
 
+def test_ingest_library_exports_every_declared_symbol():
+    from ortho2align_b200 import build, ingest
+    build.build_ingest()
+    lib = ingest.load_lib()
+    with open(os.path.join(ROOT, "include", "o2a_ingest.h")) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(o2a_ingest_[a-z_0-9]+)\s*\(", src)))
+    assert set(names) == set(ingest.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n)
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
     if torch.cuda.is_available():

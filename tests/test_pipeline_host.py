@@ -25,7 +25,7 @@ def _oracle_runner(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
     return [O.build_batch(b, fitter, fdr, alpha, gapopen, gapextend) for b in batches]
 
 
-def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact):
+def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest="native"):
     from ortho2align_b200 import pipeline
     ad, bd = _materialise(tmp_path, g)
     real_listdir = os.listdir
@@ -33,7 +33,7 @@ def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact):
     od = str(tmp_path / f"out_{key}")
     stats = str(tmp_path / f"{key}.stats.txt")
     pipeline.build_orthologs(ad, bd, fitting, od, threshold=0.05, gapopen=5, gapextend=2, fdr=fdr, cores=1,
-                             timeout=None, silent=True, stats_filename=stats)
+                             timeout=None, silent=True, stats_filename=stats, ingest=ingest)
     j = lambda n: os.path.join(od, n)
     pipeline.get_best_orthologs(j("significant.query_orthologs.bed"), j("significant.query_orthologs.tsv"),
                                 j("significant.subject_orthologs.bed"), j("significant.subject_orthologs.tsv"),
@@ -58,10 +58,11 @@ def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact):
 
 @pytest.mark.parametrize("key,fitting,fdr,exact", [("hist_1", "hist", True, True), ("hist_0", "hist", False, True),
                                                    ("kde_1", "kde", True, False)])
-def test_host_logic_with_oracle_injected(tmp_path, monkeypatch, key, fitting, fdr, exact):
+@pytest.mark.parametrize("ingest", ["native", "json"])
+def test_host_logic_with_oracle_injected(tmp_path, monkeypatch, key, fitting, fdr, exact, ingest):
     from ortho2align_b200 import pipeline
     monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
-    _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), key, fitting, fdr, exact)
+    _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), key, fitting, fdr, exact, ingest=ingest)
 
 
 @pytest.mark.gpu
