@@ -45,7 +45,7 @@ struct o2a_ctx {
     // owned copies of host inputs
     DevBuf in_bg_off, in_bg, in_kde, in_aln_off, in_hsp_off, in_qlen, in_slen, in_qs, in_qe, in_ss, in_se, in_score;
     // workspace
-    DevBuf aln_lnc, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
+    DevBuf aln_lnc, thr_aln, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
     DevBuf n_surv, n_keep, surv_idx, surv_p, surv_pq, surv_keep;
     DevBuf chain_len, chain_orient, chain_score, orient_scores, chain_slot, best_key, best_aln;
     DevBuf ret_coord, ret_score, ret_slot, in_coords;
@@ -233,7 +233,7 @@ static void free_all(o2a_ctx* ctx)
 {
     DevBuf* bufs[] = {&ctx->in_bg_off, &ctx->in_bg, &ctx->in_kde, &ctx->in_aln_off, &ctx->in_hsp_off, &ctx->in_qlen,
                       &ctx->in_slen, &ctx->in_qs, &ctx->in_qe, &ctx->in_ss, &ctx->in_se, &ctx->in_score,
-                      &ctx->aln_lnc, &ctx->thr, &ctx->fits, &ctx->tbl_k, &ctx->tbl_cum, &ctx->status, &ctx->uv_val,
+                      &ctx->aln_lnc, &ctx->thr_aln, &ctx->thr, &ctx->fits, &ctx->tbl_k, &ctx->tbl_cum, &ctx->status, &ctx->uv_val,
                       &ctx->uv_cnt, &ctx->uv_n, &ctx->n_surv, &ctx->n_keep, &ctx->surv_idx, &ctx->surv_p,
                       &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
                       &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->ret_coord,
@@ -324,8 +324,10 @@ static int run_fit(o2a_ctx* ctx)
     const o2a_params& p = ctx->prm;
     ENS(thr, b.n_lnc * sizeof(double));
     ENS(status, b.n_lnc * sizeof(int));
+    ENS(thr_aln, b.n_aln * sizeof(double));
     if (b.n_lnc == 0) return 0;
     FitArgs A{};
+    A.aln_off = (const long long*)b.aln_off; A.thr_aln = P<double>(ctx->thr_aln);
     A.n_lnc = b.n_lnc; A.bg_off = (const long long*)b.bg_off; A.bg = b.bg; A.kde_factor = b.kde_factor;
     A.fitter = p.fitter; A.alpha = p.alpha;
     if (p.fitter == O2A_FIT_HIST) {

@@ -191,7 +191,17 @@ struct FitArgs {
     int* uv_val; int* uv_cnt; int* uv_n; // kde / empirical: distinct values, slot bg_off[l]
     int* status;
     int* g_cnt; long long max_range;     // per-CTA global counters for value ranges > FIT_SMEM_RANGE
+    const long long* aln_off;            // [n_lnc+1]
+    double* thr_aln;                     // [n_aln] threshold of every alignment (+inf if the fit failed)
 };
+
+// thr_aln[a] for the alignments of lncRNA l: what k_filter compares against (+inf: nothing survives,
+// the reference raised before its alignment loop)
+__device__ __forceinline__ void fit_publish_thr(const FitArgs& A, long long l, double t, int st)
+{
+    const double v = st == 0 ? t : __longlong_as_double(0x7ff0000000000000ll);
+    for (long long a = A.aln_off[l] + threadIdx.x; a < A.aln_off[l + 1]; a += blockDim.x) A.thr_aln[a] = v;
+}
 
 // status 4 = value range larger than the counting scratch (max_range)
 __global__ void __launch_bounds__(FIT_THREADS)
@@ -214,6 +224,11 @@ k_fit(FitArgs A)
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
 
     for (long long l = blockIdx.x; l < A.n_lnc; l += gridDim.x) {
+        if (l != (long long)blockIdx.x) {
+            // results of the previous lncRNA are visible to the whole CTA (every path ends in a barrier)
+            const long long lp = l - gridDim.x;
+            fit_publish_thr(A, lp, A.thr[lp], A.status[lp]);
+        }
         const long long b0 = A.bg_off[l];
         const long long n = A.bg_off[l + 1] - b0;
         const int* x = A.bg + b0;
@@ -486,6 +501,11 @@ k_fit(FitArgs A)
         const long long tbase = b0 >> 1;                   // table slot (capacity >= B >= nnz)
         for (int t = tid; t < nnz; t += FIT_THREADS) { A.tbl_k[tbase + t] = s_k[t]; A.tbl_cum[tbase + t] = s_t[t]; }
         __syncthreads();
+    }
+    {   // the last lncRNA of this CTA
+        long long last = -1;
+        for (long long l = blockIdx.x; l < A.n_lnc; l += gridDim.x) last = l;
+        if (last >= 0) fit_publish_thr(A, last, A.thr[last], A.status[last]);
     }
 }
 

@@ -16,7 +16,7 @@
 namespace o2a {
 
 constexpr int FILTER_THREADS = 256;
-constexpr int FILTER_ROWS = 4;                       // double2 per thread per row
+constexpr int FILTER_ROWS = 4;                       // rows (double2 per lane) per warp and pass
 constexpr int FILTER_TILE = FILTER_THREADS * 2 * FILTER_ROWS;
 constexpr int PQ_THREADS = 64;
 constexpr int RANK_SMALL_MAX = 1024;                 // survivors ranked in shared memory
