@@ -387,7 +387,7 @@ static int run_score(o2a_ctx* ctx)
     A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
     A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep);
     A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
-    k_pq<<<grid_for(ctx, b.n_aln, 16), PQ_THREADS, 0, ctx->stream>>>(A);
+    k_pq<<<grid_for(ctx, b.n_aln, 14), PQ_THREADS, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
     if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
         int g2 = grid_for(ctx, b.n_aln, 2);

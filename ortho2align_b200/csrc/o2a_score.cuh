@@ -155,18 +155,23 @@ __device__ __forceinline__ double pq_sf(double x, const PqFit& F)
     return emp_sf_compressed(x, F.uval, F.ucnt, F.unv, F.nbg);
 }
 
-__global__ void __launch_bounds__(PQ_THREADS)
+__global__ void __launch_bounds__(PQ_THREADS, 14)
 k_pq(PqArgs A)
 {
-    __shared__ double s_p[RANK_SMALL_MAX];          // fallback path only
+    // class tables; the all-pairs fallback (s_p) aliases them — the two are never live together
+    __shared__ __align__(16) unsigned char s_raw[PQ_SLOTS * (8 + 4 + 4 + 2 + 2) + PQ_OVER * 8];
+    static_assert(sizeof(s_raw) >= RANK_SMALL_MAX * sizeof(double), "fallback buffer must fit");
+    double* s_p = reinterpret_cast<double*>(s_raw);                        // fallback path only
+    double* s_pe = reinterpret_cast<double*>(s_raw);                       // p of the class
+    double* s_ox = s_pe + PQ_SLOTS;                                        // scores of the overflow classes
+    int* s_cnt = reinterpret_cast<int*>(s_ox + PQ_OVER);                   // class multiplicity, later tie counters
+    int* s_L = s_cnt + PQ_SLOTS;                                           // survivors with strictly smaller p
+    short* s_g = reinterpret_cast<short*>(s_L + PQ_SLOTS);                 // tie group = first slot with the same p
+    short* s_dense = s_g + PQ_SLOTS;                                       // non-empty classes, slot order
     __shared__ int s_tk[TBL_SMEM_MAX];
     __shared__ double s_tc[TBL_SMEM_MAX];
-    __shared__ int s_cnt[PQ_SLOTS];                 // class multiplicity, later the running tie counters
-    __shared__ double s_pe[PQ_SLOTS];               // p of the class
-    __shared__ int s_L[PQ_SLOTS];                   // survivors with strictly smaller p
-    __shared__ short s_g[PQ_SLOTS];                 // tie group = first slot with the same p
-    __shared__ double s_ox[PQ_OVER];                // scores of the overflow classes
     __shared__ short s_slot[RANK_SMALL_MAX];        // class of every survivor
+    __shared__ int s_scan[PQ_THREADS / 32 + 2];
     __shared__ int s_keepcnt, s_nover, s_maxslot;
     const int tid = threadIdx.x, lane = lane_id();
 
@@ -277,17 +282,26 @@ k_pq(PqArgs A)
             continue;
         }
         // ---- per class: survivors with strictly smaller p, and the tie group -----------------------------------
-        for (int e = tid; e < ncls; e += PQ_THREADS) {
+        // dense list of the non-empty classes (slot order) so the all-pairs loop runs on ~35 entries
+        int nd = 0;
+        for (int e0 = 0; e0 < ncls; e0 += PQ_THREADS) {
+            const int e = e0 + tid;
             const int slot = e < ndir ? e : PQ_DIRECT + (e - ndir);
-            if (s_cnt[slot] == 0) continue;
+            const bool used = e < ncls && s_cnt[slot] > 0;
+            int tot;
+            const int pos = cta_exclusive_scan(used ? 1 : 0, s_scan, &tot);
+            if (used) s_dense[nd + pos] = (short)slot;
+            nd += tot;
+            __syncthreads();
+        }
+        for (int d = tid; d < nd; d += PQ_THREADS) {
+            const int slot = s_dense[d];
             const double p = s_pe[slot];
             int L = 0, g = slot;
-            for (int e2 = 0; e2 < ncls; ++e2) {
-                const int s2 = e2 < ndir ? e2 : PQ_DIRECT + (e2 - ndir);
-                const int c2 = s_cnt[s2];
-                if (c2 == 0) continue;
+            for (int d2 = 0; d2 < nd; ++d2) {
+                const int s2 = s_dense[d2];
                 const double p2 = s_pe[s2];
-                L += (p2 < p) ? c2 : 0;
+                L += (p2 < p) ? s_cnt[s2] : 0;
                 if (p2 == p && s2 < g) g = s2;
             }
             s_L[slot] = L; s_g[slot] = (short)g;
