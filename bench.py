@@ -31,6 +31,7 @@ from ortho2align_b200 import synth  # noqa: E402
 from ortho2align_b200.columnar import concat_batches  # noqa: E402
 
 METRIC = "HSPs/sec through build_orthologs+best-ortholog"
+LAYOUTS = {0: "float64", 16: "int16 + exception lists (lossless)", 32: "int32 + exception lists (lossless)"}
 UNIT = "HSPs/s"
 CONFIG_NAMES = {1: "C1 strRNA 96 lncRNAs, 1k bg", 2: "C2 20k lncRNAs x 5 regions x ~2k HSPs, 10k bg/lncRNA",
                 3: "C3 as C2 with 1M bg/lncRNA", 4: "C4 dense chaining 5k regions x 50k HSPs",
@@ -164,6 +165,11 @@ def main():
     ap.add_argument("--ref-lnc", type=int, default=2000, help="lncRNAs per step of --impl reference")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--score-bits", type=int, default=0, choices=[0, 16, 32],
+                    help="score layout of the device-resident arm: 0 = float64 (the reference's dtype), "
+                         "16/32 = lossless narrow ints + exception lists")
+    ap.add_argument("--e2e-score-bits", type=int, default=16, choices=[0, 16, 32],
+                    help="score layout of the pinned host buffers of the e2e arm (PCIe-bound: narrow is faster)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -200,7 +206,7 @@ def main():
     with_kde = args.fitter == "kde"
 
     # ---------------- device-resident arm (value) ----------------
-    dbatch = DeviceBatch(batch, dev)
+    dbatch = DeviceBatch(batch, dev, aos=True, score_bits=args.score_bits)
     dstruct = dbatch.struct(with_kde)
     counts_host = torch.zeros(5, dtype=torch.int64).pin_memory()
     counts_dev = torch.zeros(5, dtype=torch.int64, device=dev)
@@ -252,8 +258,11 @@ def main():
 
     # roofline of the dominant (streaming) kernel
     peak, peak_src = measured_peak()
-    # k_filter: 8 B score read per HSP + (4 B position + 8 B score) written per survivor
-    alg_bytes = 8.0 * batch.n_hsp + 12.0 * c.n_survivors
+    # k_filter: score read per HSP (8 B float64, or 2/4 B narrow + 12 B per exception entry) +
+    # (4 B position + 8 B score) written per survivor
+    score_bytes = {0: 8.0, 16: 2.0, 32: 4.0}[args.score_bits]
+    n_exc = int(dbatch.t["exc_pos"].numel()) if args.score_bits else 0
+    alg_bytes = score_bytes * batch.n_hsp + 12.0 * n_exc + 12.0 * c.n_survivors
     avg_score_ms = float(np.mean(score_ms))
     achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_filter", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -275,7 +284,16 @@ def main():
     # coordinates as one AoS array in pinned memory: read in place (zero-copy), 16 B per retained HSP
     c4 = torch.empty((batch.n_hsp, 4), dtype=torch.int32, pin_memory=True)
     c4.numpy()[...] = batch.coords4()
-    hstruct = eng.host_struct(hb, with_kde, coords=c4.numpy())
+    narrow = None
+    if args.e2e_score_bits:
+        qs = batch.quantized_scores(args.e2e_score_bits)
+        keep_alive = []
+        for arr in qs:
+            tp = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
+            tp.numpy()[...] = arr
+            keep_alive.append(tp)
+        narrow = (args.e2e_score_bits,) + tuple(t_.numpy() for t_ in keep_alive)
+    hstruct = eng.host_struct(hb, with_kde, coords=c4.numpy(), narrow=narrow)
     del dbatch, dstruct
     torch.cuda.empty_cache()
 
@@ -299,6 +317,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item()) / e2e_steps
     h2d = int(hb.nbytes())
+    if narrow is not None:
+        h2d = int(h2d - hb.score.nbytes + sum(a_.nbytes for a_ in narrow[1:]))
     d2h = int(res.thr.nbytes + res.status.nbytes + res.best_aln.nbytes + res.n_surv.nbytes + res.n_keep.nbytes
               + res.chain_len.nbytes + res.chain_orient.nbytes + res.chain_score.nbytes + res.orient_scores.nbytes
               + res.chain_off.nbytes + res.chain_idx.nbytes + res.chain_pq.nbytes + 40)
@@ -308,6 +328,7 @@ def main():
         h2d = int(h2d - 4 * hb.qstart.nbytes + 32 * int(res.n_keep.sum()))   # one 32 B sector per retained HSP
     e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy,
+           "score_layout": LAYOUTS[args.e2e_score_bits],
            "stage_ms_last_step": e2e_stage_ms}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
@@ -331,6 +352,7 @@ def main():
                 "config": {"workload": CONFIG_NAMES[args.config], "lncRNAs_per_gpu": batch.n_lnc,
                            "alignments_per_gpu": batch.n_aln, "hsps_per_gpu": batch.n_hsp,
                            "bg_scores_per_gpu": batch.n_bg, "fitter": args.fitter, "fdr": True, "alpha": 0.05,
+                           "score_layout": LAYOUTS[args.score_bits],
                            "survivors_per_gpu": int(c.n_survivors), "orthologs_per_gpu": int(c.n_chains),
                            "parallelism": f"lncRNA shards x{world}, no data-path collective",
                            "l2": "inputs (%.2f GB/GPU) larger than L2; no flush needed" % (batch.nbytes() / 1e9),

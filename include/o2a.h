@@ -88,6 +88,17 @@ typedef struct o2a_batch {
     const int32_t *coords;     /* optional [4*n_hsp] AoS (qstart,qend,sstart,send) per HSP, 16-byte aligned:
                                   one 16 B read per retained HSP instead of four (matters for zero-copy
                                   reads from pinned host memory); NULL = use the four SoA arrays */
+    /* Optional narrow scores (BLAST raw scores are integers; only HSPs cut at a gene boundary are
+     * fractional, alignment.py:330). score_bits = 16 or 32: `score_q` holds the scores as int16 /
+     * int32; the most negative value marks an HSP whose exact float64 score is listed in the
+     * alignment's exception list exc_pos[exc_off[a]..exc_off[a+1]) (ascending HSP positions inside
+     * the alignment) / exc_val. score_bits = 0: `score` (float64) is used. Lossless either way. */
+    int32_t score_bits;
+    int32_t reserved2;
+    const void    *score_q;    /* [n_hsp] int16 or int32 */
+    const int64_t *exc_off;    /* [n_aln+1] */
+    const int32_t *exc_pos;    /* [n_exc] */
+    const double  *exc_val;    /* [n_exc] */
 } o2a_batch;
 
 /* build_orthologs(threshold, gapopen, gapextend, fdr, fitting) + get_best_orthologs(value,

@@ -96,6 +96,24 @@ class ColumnarBatch:
             self._coords4 = c
         return c
 
+    def quantized_scores(self, bits=16):
+        """Lossless narrow encoding of `score` for `o2a_batch.score_q` (score_bits = 16 | 32):
+        integral scores inside the integer type as-is; every other HSP (fractional score of a cut
+        HSP, out-of-range value) gets the sentinel (most negative value) and an entry in its
+        alignment's exception list. Returns (score_q, exc_off, exc_pos, exc_val)."""
+        dt = {16: np.int16, 32: np.int32}[bits]
+        info = np.iinfo(dt)
+        sc = self.score
+        with np.errstate(invalid="ignore"):
+            ok = (sc == np.floor(sc)) & (sc > info.min) & (sc <= info.max)
+        q = np.where(ok, sc, info.min).astype(dt)
+        exc = np.nonzero(~ok)[0]
+        aln_of = np.searchsorted(self.hsp_off, exc, side="right") - 1
+        exc_off = np.zeros(self.n_aln + 1, dtype=np.int64)
+        np.cumsum(np.bincount(aln_of, minlength=self.n_aln), out=exc_off[1:])
+        exc_pos = (exc - self.hsp_off[aln_of]).astype(np.int32)
+        return np.ascontiguousarray(q), exc_off, np.ascontiguousarray(exc_pos), np.ascontiguousarray(sc[exc])
+
     def ensure_kde_factor(self):
         if self.kde_factor is None:
             n = np.diff(self.bg_off)

@@ -46,7 +46,8 @@ struct o2a_ctx {
     DevBuf in_bg_off, in_bg, in_kde, in_aln_off, in_hsp_off, in_qlen, in_slen, in_qs, in_qe, in_ss, in_se, in_score;
     // workspace
     DevBuf aln_lnc, thr_aln, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
-    DevBuf n_surv, n_keep, surv_idx, surv_p, surv_pq, surv_keep;
+    DevBuf n_surv, n_keep, surv_idx, surv_x, surv_p, surv_pq, surv_keep;
+    DevBuf in_score_q, in_exc_off, in_exc_pos, in_exc_val;
     DevBuf chain_len, chain_orient, chain_score, orient_scores, chain_slot, best_key, best_aln;
     DevBuf ret_coord, ret_score, ret_slot, in_coords;
     const int4* coords4 = nullptr;    // AoS coordinates actually used (device or mapped host), or null
@@ -198,10 +199,11 @@ __global__ void k_sf_eval(int fitter, const double* __restrict__ x, long long n_
     out[i] = p;
 }
 
-__global__ void k_iota_keep(int n, int* __restrict__ idx, unsigned char* __restrict__ keep)
+__global__ void k_iota_keep(int n, const double* __restrict__ score, int* __restrict__ idx, unsigned char* __restrict__ keep,
+                            double* __restrict__ surv_x)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { idx[i] = i; keep[i] = 1; }
+    if (i < n) { idx[i] = i; keep[i] = 1; surv_x[i] = score[i]; }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -234,7 +236,8 @@ static void free_all(o2a_ctx* ctx)
     DevBuf* bufs[] = {&ctx->in_bg_off, &ctx->in_bg, &ctx->in_kde, &ctx->in_aln_off, &ctx->in_hsp_off, &ctx->in_qlen,
                       &ctx->in_slen, &ctx->in_qs, &ctx->in_qe, &ctx->in_ss, &ctx->in_se, &ctx->in_score,
                       &ctx->aln_lnc, &ctx->thr_aln, &ctx->thr, &ctx->fits, &ctx->tbl_k, &ctx->tbl_cum, &ctx->status, &ctx->uv_val,
-                      &ctx->uv_cnt, &ctx->uv_n, &ctx->n_surv, &ctx->n_keep, &ctx->surv_idx, &ctx->surv_p,
+                      &ctx->uv_cnt, &ctx->uv_n, &ctx->n_surv, &ctx->n_keep, &ctx->surv_idx, &ctx->surv_x, &ctx->in_score_q,
+                      &ctx->in_exc_off, &ctx->in_exc_pos, &ctx->in_exc_val, &ctx->surv_p,
                       &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
                       &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->ret_coord,
                       &ctx->ret_score, &ctx->ret_slot, &ctx->in_coords, &ctx->big_list,
@@ -365,15 +368,26 @@ static int run_score(o2a_ctx* ctx)
     const o2a_batch& b = ctx->b;
     const o2a_params& p = ctx->prm;
     ENS(n_surv, b.n_aln * sizeof(int)); ENS(n_keep, b.n_aln * sizeof(int));
-    ENS(surv_idx, b.n_hsp * sizeof(int)); ENS(surv_p, b.n_hsp * sizeof(double));
+    ENS(surv_idx, b.n_hsp * sizeof(int)); ENS(surv_p, b.n_hsp * sizeof(double)); ENS(surv_x, b.n_hsp * sizeof(double));
     ENS(surv_pq, b.n_hsp * sizeof(double)); ENS(surv_keep, b.n_hsp);
     ENS(big_list, (b.n_aln + 1) * sizeof(int)); ENS(mid_list, (b.n_aln + 1) * sizeof(int));
     ENS(big_count, 4 * sizeof(int));
     CU(cudaMemsetAsync(ctx->big_count.p, 0, 4 * sizeof(int), ctx->stream));
     if (b.n_aln == 0) return stage_event(ctx, O2A_STAGE_PQ);
-    k_filter<<<grid_for(ctx, b.n_aln, 6), FILTER_THREADS, 0, ctx->stream>>>(
-        b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), b.score, P<double>(ctx->thr), P<int>(ctx->status),
-        P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_p));
+    if (b.score_bits == 16)
+        k_filter_q<short><<<grid_for(ctx, b.n_aln, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
+            b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), (const short*)b.score_q, (const long long*)b.exc_off,
+            b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
+            P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
+    else if (b.score_bits == 32)
+        k_filter_q<int><<<grid_for(ctx, b.n_aln, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
+            b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), (const int*)b.score_q, (const long long*)b.exc_off,
+            b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
+            P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
+    else
+        k_filter<<<grid_for(ctx, b.n_aln, 6), FILTER_THREADS, 0, ctx->stream>>>(
+            b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), b.score, P<double>(ctx->thr), P<int>(ctx->status),
+            P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
     LAUNCH_CHECK();
     int r = stage_event(ctx, O2A_STAGE_PQ);
     if (r) return r;
@@ -384,7 +398,7 @@ static int run_score(o2a_ctx* ctx)
     A.bg_off = (const long long*)b.bg_off;
     A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt); A.uv_n = P<int>(ctx->uv_n);
     A.kde_factor = b.kde_factor; A.fitter = p.fitter; A.fdr = p.fdr; A.alpha = p.alpha;
-    A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
+    A.surv_x = P<double>(ctx->surv_x); A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
     A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep);
     A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
     k_pq<<<grid_for(ctx, b.n_aln, 14), PQ_THREADS, 0, ctx->stream>>>(A);
@@ -419,7 +433,8 @@ static int run_chain(o2a_ctx* ctx)
         A.coords4 = ctx->coords4;
         A.ret_coord = P<int4>(ctx->ret_coord); A.ret_score = P<double>(ctx->ret_score); A.ret_slot = P<int>(ctx->ret_slot);
         A.n_surv = P<int>(ctx->n_surv); A.n_keep = P<int>(ctx->n_keep); A.surv_idx = P<int>(ctx->surv_idx);
-        A.surv_keep = P<unsigned char>(ctx->surv_keep); A.gapopen = p.gapopen; A.gapextend = p.gapextend;
+        A.surv_keep = P<unsigned char>(ctx->surv_keep); A.surv_x = P<double>(ctx->surv_x);
+        A.gapopen = p.gapopen; A.gapextend = p.gapextend;
         A.best_value = p.best_value;
         A.chain_len = P<int>(ctx->chain_len); A.chain_orient = P<unsigned char>(ctx->chain_orient);
         A.chain_score = P<double>(ctx->chain_score); A.orient_scores = P<double>(ctx->orient_scores);
@@ -511,7 +526,19 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         if ((r = upload(ctx, ctx->in_hsp_off, batch->hsp_off, (size_t)batch->n_aln + 1, &b.hsp_off))) return r;
         if ((r = upload(ctx, ctx->in_qlen, batch->qlen, (size_t)batch->n_aln, &b.qlen))) return r;
         if ((r = upload(ctx, ctx->in_slen, batch->slen, (size_t)batch->n_aln, &b.slen))) return r;
-        if ((r = upload(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, &b.score))) return r;
+        if (batch->score_bits == 16 || batch->score_bits == 32) {
+            if (!batch->score_q || !batch->exc_off) { ctx->err = "score_bits set but score_q/exc_off missing"; return O2A_EINVAL; }
+            const size_t esz = batch->score_bits / 8;
+            const unsigned char* d8 = nullptr;
+            if ((r = upload(ctx, ctx->in_score_q, (const unsigned char*)batch->score_q, (size_t)batch->n_hsp * esz, &d8))) return r;
+            b.score_q = d8;
+            if ((r = upload(ctx, ctx->in_exc_off, batch->exc_off, (size_t)batch->n_aln + 1, &b.exc_off))) return r;
+            const size_t n_exc = batch->n_aln > 0 ? (size_t)batch->exc_off[batch->n_aln] : 0;
+            if ((r = upload(ctx, ctx->in_exc_pos, batch->exc_pos, n_exc, &b.exc_pos))) return r;
+            if ((r = upload(ctx, ctx->in_exc_val, batch->exc_val, n_exc, &b.exc_val))) return r;
+            b.score = nullptr;
+        } else if (batch->score_bits != 0) { ctx->err = "score_bits must be 0, 16 or 32"; return O2A_EINVAL; }
+        else if ((r = upload(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, &b.score))) return r;
         // Coordinates are only ever read for the HSPs that reach the chaining (~1 %): when the caller's
         // arrays are pinned + device-mapped (o2a_host_alloc / cudaHostAlloc / cudaHostRegister) the
         // gather kernel reads them in place over PCIe instead of copying 16 B per HSP.
@@ -764,7 +791,7 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     ctx->coords4 = nullptr;
     ctx->prm.gapopen = gapopen; ctx->prm.gapextend = gapextend;
     ENS(aln_lnc, 4); ENS(status, 4); ENS(n_surv, 4); ENS(n_keep, 4);
-    ENS(surv_idx, (size_t)n * 4); ENS(surv_keep, (size_t)n); ENS(surv_pq, (size_t)n * 8);
+    ENS(surv_idx, (size_t)n * 4); ENS(surv_keep, (size_t)n); ENS(surv_pq, (size_t)n * 8); ENS(surv_x, (size_t)n * 8);
     ENS(big_list, 2 * sizeof(int)); ENS(mid_list, 2 * sizeof(int)); ENS(big_count, 4 * sizeof(int));
     int ni = (int)n;
     CU(cudaMemsetAsync(ctx->aln_lnc.p, 0, 4, ctx->stream));
@@ -773,7 +800,7 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     CU(cudaMemcpyAsync(ctx->n_surv.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->n_keep.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
     if (n > 0) {
-        k_iota_keep<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ni, P<int>(ctx->surv_idx), P<unsigned char>(ctx->surv_keep));
+        k_iota_keep<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ni, b.score, P<int>(ctx->surv_idx), P<unsigned char>(ctx->surv_keep), P<double>(ctx->surv_x));
         LAUNCH_CHECK();
     }
     bool timing = ctx->timing;

@@ -143,6 +143,7 @@ struct ChainArgs {
     const int4* coords4;       // optional AoS (qstart,qend,sstart,send) per HSP; replaces the four SoA arrays
     const int* n_surv; const int* n_keep;
     const int* surv_idx; const unsigned char* surv_keep;
+    const double* surv_x;      // survivor scores (slot layout)
     // retained HSPs of alignment a, list order, at [hsp_off[a], hsp_off[a] + n_keep[a]) (k_gather_retained)
     int4* ret_coord; double* ret_score; int* ret_slot;
     int gapopen, gapextend;
@@ -199,7 +200,7 @@ k_gather_retained(ChainArgs A)
                 int4 c;
                 if (A.coords4) c = A.coords4[h];
                 else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
-                A.ret_coord[pos] = c; A.ret_score[pos] = A.score[h]; A.ret_slot[pos] = k;
+                A.ret_coord[pos] = c; A.ret_score[pos] = A.surv_x[h0 + k]; A.ret_slot[pos] = k;
             }
             got += __popc(b);
         }

@@ -112,6 +112,187 @@ k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __re
     }
 }
 
+// Narrow-score variant: integral scores as int16 / int32 (BLAST raw scores are integers; only HSPs
+// cut at a gene boundary carry fractional scores, alignment.py:330). The sentinel (most negative
+// value of T) marks an HSP whose score is not representable: its exact float64 value sits in the
+// alignment's exception list (exc_pos ascending HSP positions, exc_val). Same ordered compaction as
+// k_filter; one 16-byte load carries 8 (int16) or 4 (int32) scores per lane, `score > thr` is the
+// integer test `q > floor(thr)` (the sentinel never passes it), and the few exceptions that DO pass
+// (value > thr) are resolved once per alignment into a tiny shared list that sentinel lanes consult.
+template <typename T> struct QTraits;
+template <> struct QTraits<short> { static constexpr int PER = 8; static constexpr int SENT = -32768; };
+template <> struct QTraits<int> { static constexpr int PER = 4; static constexpr int SENT = INT32_MIN; };
+
+constexpr int FILTERQ_ROWS = 2;               // 16-byte loads per lane per pass
+constexpr int FILTERQ_THREADS = 64;           // narrow scores: small CTAs, many alignments in flight per SM
+constexpr int FILTERQ_PASS_SMEM = 128;        // passing exceptions kept in shared memory per alignment
+
+template <typename T>
+__device__ __forceinline__ int q_at(const int4& raw, int c)
+{
+    if (sizeof(T) == 4) return c == 0 ? raw.x : c == 1 ? raw.y : c == 2 ? raw.z : raw.w;
+    const int wsel = c >> 1;
+    const int word = wsel == 0 ? raw.x : wsel == 1 ? raw.y : wsel == 2 ? raw.z : raw.w;
+    return (c & 1) ? (word >> 16) : (int)(short)(word & 0xffff);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FILTERQ_THREADS, 20)
+k_filter_q(long long n_aln, const long long* __restrict__ hsp_off, const int* __restrict__ aln_lnc,
+           const T* __restrict__ score_q, const long long* __restrict__ exc_off, const int* __restrict__ exc_pos,
+           const double* __restrict__ exc_val, long long n_hsp_total,
+           const double* __restrict__ thr, const int* __restrict__ lnc_status,
+           int* __restrict__ n_surv, int* __restrict__ surv_idx, double* __restrict__ surv_x)
+{
+    constexpr int NW = FILTERQ_THREADS / 32;
+    constexpr int PER = QTraits<T>::PER;                 // scores per 16-byte load
+    constexpr int SENT = QTraits<T>::SENT;
+    constexpr int ROWLEN = 32 * PER;                     // scores per warp load
+    constexpr int WCHUNK = FILTERQ_ROWS * ROWLEN;
+    constexpr int TILE = NW * WCHUNK;
+    __shared__ int s_wtot[2][NW];
+    __shared__ int s_ppos[FILTERQ_PASS_SMEM];            // positions of the exceptions with value > thr
+    __shared__ double s_pval[FILTERQ_PASS_SMEM];
+    __shared__ int s_np;
+    const int lane = lane_id(), w = warp_id();
+    int buf = 0;
+
+    for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
+        const int l = aln_lnc[a];
+        const long long h0 = hsp_off[a];
+        const int m = (int)(hsp_off[a + 1] - h0);
+        if (lnc_status[l] != 0) { if (threadIdx.x == 0) n_surv[a] = 0; continue; }
+        const double t = thr[l];
+        // q > thr  <=>  q > floor(thr) for integers; clamped so that the sentinel can never pass
+        const double tf = floor(t);
+        const int tq = tf >= 2147483647.0 ? 2147483647 : (tf <= (double)SENT ? SENT : (int)tf);
+        const long long x0 = exc_off[a];
+        const int ne = (int)(exc_off[a + 1] - x0);
+        const int sh = (int)(h0 & (PER - 1));                  // stream starts at the aligned address below
+        const T* sc = score_q + h0 - sh;
+        const int ms = m + sh;
+        const long long g0 = h0 - sh;                          // global index of stream element 0
+        int* out_idx = surv_idx + h0;
+        double* out_x = surv_x + h0;
+        auto load_row = [&](int e) -> int4 {
+            if (g0 + e + PER <= n_hsp_total) return *reinterpret_cast<const int4*>(sc + e);
+            T q[PER];                                          // tail of the whole score array
+#pragma unroll
+            for (int c = 0; c < PER; ++c) q[c] = (g0 + e + c < n_hsp_total) ? sc[e + c] : (T)SENT;
+            int4 r4; memcpy(&r4, q, 16); return r4;
+        };
+        // the first tile's loads are issued before the exception pre-pass so both latencies overlap
+        int4 raw[FILTERQ_ROWS];
+#pragma unroll
+        for (int r = 0; r < FILTERQ_ROWS; ++r) raw[r] = load_row(w * WCHUNK + lane * PER + r * ROWLEN);
+        __syncthreads();                                       // previous alignment is done with s_ppos / s_np
+        if (threadIdx.x == 0) s_np = 0;
+        __syncthreads();
+        // exceptions that pass the filter (value > thr): usually a handful; order is irrelevant
+        for (int i = threadIdx.x; i < ne; i += FILTERQ_THREADS) {
+            const double v = exc_val[x0 + i];
+            if (v > t) {
+                const int p = atomicAdd(&s_np, 1);
+                if (p < FILTERQ_PASS_SMEM) { s_ppos[p] = exc_pos[x0 + i]; s_pval[p] = v; }
+            }
+        }
+        __syncthreads();
+        const int np = s_np;                                   // > FILTERQ_PASS_SMEM: fall back to the global list
+        int base = 0;
+        for (int t0 = 0; t0 < ms; t0 += TILE) {
+            const int e0 = t0 + w * WCHUNK + lane * PER;
+            if (t0 > 0) {
+#pragma unroll
+                for (int r = 0; r < FILTERQ_ROWS; ++r) raw[r] = load_row(e0 + r * ROWLEN);
+            }
+            unsigned pass[FILTERQ_ROWS];                       // PER flag bits per row
+            int cnt[FILTERQ_ROWS];
+#pragma unroll
+            for (int r = 0; r < FILTERQ_ROWS; ++r) {
+                const int e = e0 + r * ROWLEN;                 // stream index of my first score of this row
+                unsigned msk = 0, sent = 0;
+#pragma unroll
+                for (int c = 0; c < PER; ++c) {
+                    const int q = q_at<T>(raw[r], c);
+                    msk |= (q > tq ? 1u : 0u) << c;
+                    sent |= (q == SENT ? 1u : 0u) << c;
+                }
+                // lanes straddling the alignment borders drop what is outside [sh, ms)
+                if (e < sh || e + PER > ms) {
+                    unsigned inside = 0;
+#pragma unroll
+                    for (int c = 0; c < PER; ++c) inside |= ((e + c >= sh && e + c < ms) ? 1u : 0u) << c;
+                    msk &= inside; sent &= inside;
+                }
+                // exceptions: pass iff listed among the passing ones
+                while (sent) {
+                    const int c = __ffs(sent) - 1; sent &= sent - 1;
+                    const int pos = e + c - sh;
+                    bool ok = false;
+                    if (np <= FILTERQ_PASS_SMEM) {
+                        for (int i = 0; i < np; ++i) if (s_ppos[i] == pos) { ok = true; break; }
+                    } else {
+                        int lo = 0, hi = ne;
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < pos) lo = mid + 1; else hi = mid; }
+                        ok = lo < ne && exc_pos[x0 + lo] == pos && exc_val[x0 + lo] > t;
+                    }
+                    if (ok) msk |= 1u << c;
+                }
+                pass[r] = msk;
+                cnt[r] = __popc(msk);
+            }
+            // warp-inclusive scan of the per-lane counts of both rows (row 0 precedes row 1 for every lane?
+            // no: element order is row-major, so each row is scanned on its own)
+            int incl[FILTERQ_ROWS];
+#pragma unroll
+            for (int r = 0; r < FILTERQ_ROWS; ++r) {
+                int x = cnt[r];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += y; }
+                incl[r] = x;
+            }
+            int rowtot[FILTERQ_ROWS];
+            int wtot = 0;
+#pragma unroll
+            for (int r = 0; r < FILTERQ_ROWS; ++r) { rowtot[r] = __shfl_sync(FULL_MASK, incl[r], 31); wtot += rowtot[r]; }
+            if (lane == 0) s_wtot[buf][w] = wtot;
+            __syncthreads();
+            int wbase = 0, tile_total = 0;
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) { const int c = s_wtot[buf][ww]; wbase += (ww < w) ? c : 0; tile_total += c; }
+            buf ^= 1;
+            int pos = base + wbase;
+#pragma unroll
+            for (int r = 0; r < FILTERQ_ROWS; ++r) {
+                unsigned msk = pass[r];
+                if (msk) {
+                    int p = pos + incl[r] - cnt[r];
+                    const int e = e0 + r * ROWLEN - sh;        // HSP position of my first score of this row
+#pragma unroll
+                    for (int c = 0; c < PER; ++c) {
+                        if ((msk >> c) & 1u) {
+                            const int q = q_at<T>(raw[r], c);
+                            double x = (double)q;
+                            if (q == SENT) {                    // a passing exception: its float64 value
+                                if (np <= FILTERQ_PASS_SMEM) { for (int i = 0; i < np; ++i) if (s_ppos[i] == e + c) { x = s_pval[i]; break; } }
+                                else {
+                                    int lo = 0, hi = ne;
+                                    while (lo < hi) { int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < e + c) lo = mid + 1; else hi = mid; }
+                                    x = exc_val[x0 + lo];
+                                }
+                            }
+                            out_idx[p] = e + c; out_x[p] = x; ++p;
+                        }
+                    }
+                }
+                pos += rowtot[r];
+            }
+            base += tile_total;
+        }
+        if (threadIdx.x == 0) n_surv[a] = base;
+    }
+}
+
 struct PqArgs {
     long long n_aln;
     const long long* hsp_off;
@@ -124,7 +305,8 @@ struct PqArgs {
     // kde / empirical
     const int* uv_val; const int* uv_cnt; const int* uv_n; const double* kde_factor;
     int fitter; int fdr; double alpha;
-    double* surv_p;            // in: survivor scores (written by k_filter); out: p-values
+    const double* surv_x;      // survivor scores (written by k_filter)
+    double* surv_p;            // out: p-values
     double* surv_pq; unsigned char* surv_keep; int* n_keep;
     int* big_list; int* big_count;
 };
@@ -198,12 +380,13 @@ k_pq(PqArgs A)
             F.nbg = (double)(A.bg_off[l + 1] - b0);
             if (A.fitter == 1) F.kfac = A.kde_factor[l];
         }
-        double* xs = A.surv_p + h0;                   // in: scores, out: p-values
+        const double* xin = A.surv_x + h0;            // survivor scores
+        double* xs = A.surv_p + h0;                   // out: p-values
         if (ns > RANK_SMALL_MAX) {
             // big survivor set: p per survivor here, ranks by radix sort in k_rank_big
             __syncthreads();
             for (int k = tid; k < ns; k += PQ_THREADS) {
-                const double p = pq_sf(xs[k], F);
+                const double p = pq_sf(xin[k], F);
                 xs[k] = p;
                 if (!A.fdr) { A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1; }
             }
@@ -220,7 +403,7 @@ k_pq(PqArgs A)
         const double thr = A.thr[l];
         const long long xlo = (long long)floor(thr);
         for (int k = tid; k < ns; k += PQ_THREADS) {
-            const double x = xs[k];
+            const double x = xin[k];
             const long long xi = (long long)x;
             const long long off = xi - xlo;
             int slot;
@@ -240,7 +423,7 @@ k_pq(PqArgs A)
         if (nover > PQ_OVER) {
             // ---- fallback: all-pairs stable rank ---------------------------------------------------------
             for (int k = tid; k < ns; k += PQ_THREADS) {
-                const double p = pq_sf(xs[k], F);
+                const double p = pq_sf(xin[k], F);
                 s_p[k] = p; xs[k] = p;
                 if (!A.fdr) { A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1; }
             }

@@ -25,7 +25,7 @@ def _p(a):
 class DeviceBatch:
     """A ColumnarBatch resident in HBM (torch tensors own the memory; the library gets raw pointers)."""
 
-    def __init__(self, batch: ColumnarBatch, device, aos=True):
+    def __init__(self, batch: ColumnarBatch, device, aos=True, score_bits=0):
         import torch
         self.n_lnc, self.n_aln, self.n_hsp, self.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
         self.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
@@ -37,15 +37,27 @@ class DeviceBatch:
         self.aos = aos
         if aos:
             self.t["coords"] = torch.from_numpy(batch.coords4()).to(device)
+        self.score_bits = score_bits
+        if score_bits:
+            q, eo, ep, ev = batch.quantized_scores(score_bits)
+            for k, v in (("score_q", q), ("exc_off", eo), ("exc_pos", ep), ("exc_val", ev)):
+                self.t[k] = torch.from_numpy(v).to(device)
+            del self.t["score"]
         self.nbytes = sum(v.numel() * v.element_size() for v in self.t.values())
 
     def struct(self, with_kde):
         s = _lib.O2ABatch()
         s.n_lnc, s.n_aln, s.n_hsp, s.n_bg = self.n_lnc, self.n_aln, self.n_hsp, self.n_bg
-        for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
+        for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send"):
             setattr(s, k, self.t[k].data_ptr())
         s.kde_factor = self.t["kde_factor"].data_ptr() if with_kde else None
         s.coords = self.t["coords"].data_ptr() if self.aos else None
+        s.score_bits = self.score_bits
+        if self.score_bits:
+            for k in ("score_q", "exc_off", "exc_pos", "exc_val"):
+                setattr(s, k, self.t[k].data_ptr())
+        else:
+            s.score = self.t["score"].data_ptr()
         s.mem = 1
         s.max_aln_hsps, s.max_lnc_bg = self.max_aln_hsps, self.max_lnc_bg
         return s
@@ -103,8 +115,10 @@ class Engine:
         return p
 
     @staticmethod
-    def host_struct(batch: ColumnarBatch, with_kde, coords=None):
-        """`coords`: optional AoS int32 [n_hsp, 4] array (e.g. pinned) used instead of the SoA arrays."""
+    def host_struct(batch: ColumnarBatch, with_kde, coords=None, narrow=None):
+        """`coords`: optional AoS int32 [n_hsp, 4] array (e.g. pinned) used instead of the SoA arrays.
+        `narrow`: optional (bits, score_q, exc_off, exc_pos, exc_val) from `quantized_scores` (the arrays
+        must stay alive until the call returns) used instead of the float64 `score`."""
         s = _lib.O2ABatch()
         s.n_lnc, s.n_aln, s.n_hsp, s.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
         for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
@@ -113,6 +127,10 @@ class Engine:
             setattr(s, k, a.ctypes.data)
         s.kde_factor = batch.ensure_kde_factor().ctypes.data if with_kde else None
         s.coords = coords.ctypes.data if coords is not None else None
+        if narrow is not None:
+            s.score_bits = int(narrow[0])
+            s.score_q, s.exc_off = narrow[1].ctypes.data, narrow[2].ctypes.data
+            s.exc_pos, s.exc_val = narrow[3].ctypes.data, narrow[4].ctypes.data
         s.mem = 0
         s.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
         s.max_lnc_bg = int(np.diff(batch.bg_off).max()) if batch.n_lnc else 0
@@ -157,10 +175,12 @@ class Engine:
                            surv_off, surv_idx, surv_p, surv_pq, surv_keep, chain_off, chain_idx, chain_pq)
 
     def build_batch(self, batch: ColumnarBatch, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
-                    best_value="block_length", best_function="max", survivors=True, aos=False) -> BatchResult:
+                    best_value="block_length", best_function="max", survivors=True, aos=False,
+                    score_bits=0) -> BatchResult:
         """Host buffers in, host results out (the e2e boundary)."""
         p = self.params(fitter, fdr, alpha, gapopen, gapextend, best_value, best_function)
-        s = self.host_struct(batch, with_kde=(fitter == "kde"), coords=batch.coords4() if aos else None)
+        narrow = (score_bits,) + batch.quantized_scores(score_bits) if score_bits else None
+        s = self.host_struct(batch, with_kde=(fitter == "kde"), coords=batch.coords4() if aos else None, narrow=narrow)
         self.run(s, p)
         return self.fetch(survivors=survivors)
 

@@ -66,8 +66,33 @@ def test_synthetic_vs_oracle(engine, cfg, kw, fitter, fdr):
     compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr}")
     got = engine.build_batch(b, fitter, fdr, aos=True)          # AoS coordinates (o2a_batch.coords)
     compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr} aos")
+    for bits in (16, 32):                                       # narrow scores + exception lists
+        got = engine.build_batch(b, fitter, fdr, aos=True, score_bits=bits)
+        compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr} score_bits={bits}")
     assert engine.counts.n_survivors == int(exp.n_surv.sum())
     assert engine.counts.n_chains == int((exp.chain_len > 0).sum())
+
+
+def test_narrow_scores_with_many_exceptions(engine):
+    """Scores outside int16, fractional scores everywhere, NaN-free extremes: the narrow encodings stay lossless."""
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    b = synth.workload(5, n_lnc=300, seed=17)
+    rng = np.random.default_rng(1)
+    b.score[rng.random(b.n_hsp) < 0.3] *= 0.77          # 30 % fractional
+    b.score[rng.random(b.n_hsp) < 0.05] += 40000.0      # beyond int16
+    b.score[rng.random(b.n_hsp) < 0.01] = -32768.0      # collides with the int16 sentinel value
+    exp = O.build_batch(b, "hist", True)
+    for bits in (16, 32):
+        q, eo, ep, ev = b.quantized_scores(bits)
+        assert eo[-1] == len(ep) > 0
+        got = engine.build_batch(b, "hist", True, score_bits=bits)
+        compare_results(got, exp, exact_p=True, what=f"narrow {bits}")
+    import torch
+    from ortho2align_b200.engine import DeviceBatch
+    db = DeviceBatch(b, torch.device("cuda:0"), aos=True, score_bits=16)
+    engine.run(db.struct(False), engine.params("hist", True))
+    compare_results(engine.fetch(), exp, exact_p=True, what="narrow device-resident")
 
 
 def test_kde_vs_oracle(engine):
