@@ -31,7 +31,8 @@ from ortho2align_b200 import synth  # noqa: E402
 from ortho2align_b200.columnar import concat_batches  # noqa: E402
 
 METRIC = "HSPs/sec through build_orthologs+best-ortholog"
-LAYOUTS = {0: "float64", 16: "int16 + exception lists (lossless)", 32: "int32 + exception lists (lossless)"}
+LAYOUTS = {0: "float64 scores, int32 background", 16: "int16 scores + exception lists, int16 background (lossless)",
+           32: "int32 scores + exception lists, int32 background (lossless)"}
 UNIT = "HSPs/s"
 CONFIG_NAMES = {1: "C1 strRNA 96 lncRNAs, 1k bg", 2: "C2 20k lncRNAs x 5 regions x ~2k HSPs, 10k bg/lncRNA",
                 3: "C3 as C2 with 1M bg/lncRNA", 4: "C4 dense chaining 5k regions x 50k HSPs",
@@ -161,8 +162,8 @@ def main():
     ap.add_argument("--lnc", type=int, default=None, help="lncRNAs per GPU (default: the config's full size)")
     ap.add_argument("--fitter", default="hist", choices=["hist", "kde", "empirical"])
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-lnc", type=int, default=2000, help="lncRNAs in the cpu_baseline sample")
-    ap.add_argument("--ref-lnc", type=int, default=2000, help="lncRNAs per step of --impl reference")
+    ap.add_argument("--cpu-lnc", type=int, default=20000, help="lncRNAs in the cpu_baseline sample")
+    ap.add_argument("--ref-lnc", type=int, default=20000, help="lncRNAs per step of --impl reference")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--score-bits", type=int, default=0, choices=[0, 16, 32],
@@ -206,7 +207,7 @@ def main():
     with_kde = args.fitter == "kde"
 
     # ---------------- device-resident arm (value) ----------------
-    dbatch = DeviceBatch(batch, dev, aos=True, score_bits=args.score_bits)
+    dbatch = DeviceBatch(batch, dev, aos=True, score_bits=args.score_bits, bg_bits=16 if args.score_bits == 16 else 32)
     dstruct = dbatch.struct(with_kde)
     counts_host = torch.zeros(5, dtype=torch.int64).pin_memory()
     counts_dev = torch.zeros(5, dtype=torch.int64, device=dev)
@@ -272,30 +273,47 @@ def main():
 
     # ---------------- end-to-end arm (host buffers through the C-ABI) ----------------
     e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
-    pinned = {}
-    for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
-        src = getattr(batch, k)
-        tp = torch.empty(src.shape, dtype=torch.from_numpy(src[:0]).dtype, pin_memory=True)
-        tp.numpy()[...] = src
-        pinned[k] = tp
-    hb = type(batch)(**{k: pinned[k].numpy() for k in pinned}, kde_factor=batch.kde_factor, names=None)
-    if with_kde:
-        hb.ensure_kde_factor()
-    # coordinates as one AoS array in pinned memory: read in place (zero-copy), 16 B per retained HSP
-    c4 = torch.empty((batch.n_hsp, 4), dtype=torch.int32, pin_memory=True)
-    c4.numpy()[...] = batch.coords4()
-    narrow = None
-    if args.e2e_score_bits:
-        qs = batch.quantized_scores(args.e2e_score_bits)
-        keep_alive = []
-        for arr in qs:
-            tp = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
-            tp.numpy()[...] = arr
-            keep_alive.append(tp)
-        narrow = (args.e2e_score_bits,) + tuple(t_.numpy() for t_ in keep_alive)
-    hstruct = eng.host_struct(hb, with_kde, coords=c4.numpy(), narrow=narrow)
     del dbatch, dstruct
     torch.cuda.empty_cache()
+
+    def pin(arr):
+        tp = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
+        tp.numpy()[...] = arr
+        return tp
+
+    # only what the chosen layout actually hands to the library is pinned (host RAM: 8 ranks share one box)
+    narrow_bits = args.e2e_score_bits
+    keep_alive = {k: pin(getattr(batch, k)) for k in ("bg_off", "aln_off", "hsp_off", "qlen", "slen")}
+    # coordinates as one AoS array in pinned memory: read in place (zero-copy), 16 B per retained HSP
+    keep_alive["coords"] = pin(batch.coords4())
+    batch._coords4 = None
+    fields = {k: keep_alive[k].numpy() for k in ("bg_off", "aln_off", "hsp_off", "qlen", "slen")}
+    narrow, bg16 = None, None
+    if narrow_bits:
+        qs = batch.quantized_scores(narrow_bits)
+        for name, arr in zip(("score_q", "exc_off", "exc_pos", "exc_val"), qs):
+            keep_alive[name] = pin(arr)
+        del qs
+        narrow = (narrow_bits,) + tuple(keep_alive[n].numpy() for n in ("score_q", "exc_off", "exc_pos", "exc_val"))
+        fields["score"] = batch.score            # not handed to the library in this layout
+    else:
+        keep_alive["score"] = pin(batch.score)
+        fields["score"] = keep_alive["score"].numpy()
+    if narrow_bits == 16:
+        keep_alive["bg16"] = pin(batch.bg16())
+        batch._bg16 = None
+        bg16 = keep_alive["bg16"].numpy()
+        fields["bg"] = batch.bg
+    else:
+        keep_alive["bg"] = pin(batch.bg)
+        fields["bg"] = keep_alive["bg"].numpy()
+    for k in ("qstart", "qend", "sstart", "send"):
+        fields[k] = getattr(batch, k)            # SoA coordinates are ignored when `coords` is set
+    hb = type(batch)(**fields, kde_factor=batch.kde_factor, names=None)
+    if with_kde:
+        hb.ensure_kde_factor()
+    hstruct = eng.host_struct(hb, with_kde, coords=keep_alive["coords"].numpy(), narrow=narrow, bg16=bg16)
+    h2d = sum(int(keep_alive[k].numpy().nbytes) for k in keep_alive if k != "coords")
 
     def step_e2e():
         eng.run(hstruct, params)
@@ -316,16 +334,15 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item()) / e2e_steps
-    h2d = int(hb.nbytes())
-    if narrow is not None:
-        h2d = int(h2d - hb.score.nbytes + sum(a_.nbytes for a_ in narrow[1:]))
     d2h = int(res.thr.nbytes + res.status.nbytes + res.best_aln.nbytes + res.n_surv.nbytes + res.n_keep.nbytes
               + res.chain_len.nbytes + res.chain_orient.nbytes + res.chain_score.nbytes + res.orient_scores.nbytes
               + res.chain_off.nbytes + res.chain_idx.nbytes + res.chain_pq.nbytes + 40)
     zero_copy = bool(eng.lib.o2a_coords_zero_copy(eng.h))
     if zero_copy:
-        # coordinates stay in pinned host memory; only the retained HSPs' (4 x int32) are read over PCIe
-        h2d = int(h2d - 4 * hb.qstart.nbytes + 32 * int(res.n_keep.sum()))   # one 32 B sector per retained HSP
+        # coordinates stay in pinned host memory; only the retained HSPs are read over PCIe (one 32 B sector each)
+        h2d = int(h2d + 32 * int(res.n_keep.sum()))
+    else:
+        h2d = int(h2d + keep_alive["coords"].numpy().nbytes)
     e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy,
            "score_layout": LAYOUTS[args.e2e_score_bits],
@@ -338,9 +355,9 @@ def main():
         threads = O.host_threads()
         k = min(args.cpu_lnc, batch.n_lnc)
         sample = batch.slice_lnc(0, k)
-        rate, secs = cpu_port_rate(sample, args.fitter, threads, repeats=2)
+        rate, secs = cpu_port_rate(sample, args.fitter, threads, repeats=3)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {k} lncRNAs ({sample.n_hsp} HSPs) of the workload, {secs:.2f} s, best of 2"}
+               "sample": f"first {k} lncRNAs ({sample.n_hsp} HSPs) of the workload, {secs:.2f} s per pass, best of 3"}
 
     if world > 1:
         g = gathered.view(world, 5).cpu().numpy()

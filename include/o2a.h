@@ -72,7 +72,7 @@ typedef struct o2a_ctx o2a_ctx;
 typedef struct o2a_batch {
     int64_t n_lnc, n_aln, n_hsp, n_bg;
     const int64_t *bg_off;     /* [n_lnc+1] */
-    const int32_t *bg;         /* [n_bg]    */
+    const int32_t *bg;         /* [n_bg] (int16 data when bg_bits == 16) */
     const double  *kde_factor; /* [n_lnc] gaussian_kde.factor per lncRNA (host-side scalar of
                                   fitting.py:264,295); may be NULL unless fitter == O2A_FIT_KDE */
     const int64_t *aln_off;    /* [n_lnc+1] */
@@ -94,7 +94,7 @@ typedef struct o2a_batch {
      * alignment's exception list exc_pos[exc_off[a]..exc_off[a+1]) (ascending HSP positions inside
      * the alignment) / exc_val. score_bits = 0: `score` (float64) is used. Lossless either way. */
     int32_t score_bits;
-    int32_t reserved2;
+    int32_t bg_bits;           /* 0 or 32: `bg` is int32 [n_bg]; 16: `bg` points to int16 [n_bg] */
     const void    *score_q;    /* [n_hsp] int16 or int32 */
     const int64_t *exc_off;    /* [n_aln+1] */
     const int32_t *exc_pos;    /* [n_exc] */

@@ -22,7 +22,7 @@ class O2ABatch(C.Structure):
                 ("qstart", C.c_void_p), ("qend", C.c_void_p), ("sstart", C.c_void_p), ("send", C.c_void_p),
                 ("score", C.c_void_p), ("mem", C.c_int32), ("reserved", C.c_int32),
                 ("max_aln_hsps", C.c_int64), ("max_lnc_bg", C.c_int64), ("coords", C.c_void_p),
-                ("score_bits", C.c_int32), ("reserved2", C.c_int32), ("score_q", C.c_void_p),
+                ("score_bits", C.c_int32), ("bg_bits", C.c_int32), ("score_q", C.c_void_p),
                 ("exc_off", C.c_void_p), ("exc_pos", C.c_void_p), ("exc_val", C.c_void_p)]
 
 

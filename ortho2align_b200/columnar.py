@@ -96,6 +96,16 @@ class ColumnarBatch:
             self._coords4 = c
         return c
 
+    def bg16(self):
+        """int16 copy of the background for `o2a_batch.bg_bits = 16` (BLAST raw scores fit easily)."""
+        b = getattr(self, "_bg16", None)
+        if b is None or len(b) != self.n_bg:
+            if self.n_bg and (self.bg.max() > 32767 or self.bg.min() < -32768):
+                raise PackError("background scores do not fit int16")
+            b = self.bg.astype(np.int16)
+            self._bg16 = b
+        return b
+
     def quantized_scores(self, bits=16):
         """Lossless narrow encoding of `score` for `o2a_batch.score_q` (score_bits = 16 | 32):
         integral scores inside the integer type as-is; every other HSP (fractional score of a cut

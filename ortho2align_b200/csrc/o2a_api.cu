@@ -351,7 +351,8 @@ static int run_fit(o2a_ctx* ctx)
     A.tbl_cum = P<double>(ctx->tbl_cum); A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt);
     A.uv_n = P<int>(ctx->uv_n); A.status = P<int>(ctx->status); A.g_cnt = P<int>(ctx->fit_cnt);
     A.max_range = max_range;
-    k_fit<<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
+    if (b.bg_bits == 16) k_fit<short><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
+    else k_fit<int><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
     return 0;
 }
@@ -518,7 +519,13 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         // the reference pickles file names to workers which json.load them (pipeline.py:743-754);
         // here the columnar arrays cross PCIe once
         if ((r = upload(ctx, ctx->in_bg_off, batch->bg_off, (size_t)batch->n_lnc + 1, &b.bg_off))) return r;
-        if ((r = upload(ctx, ctx->in_bg, batch->bg, (size_t)batch->n_bg, &b.bg))) return r;
+        if (batch->bg_bits != 0 && batch->bg_bits != 16 && batch->bg_bits != 32) { ctx->err = "bg_bits must be 0, 16 or 32"; return O2A_EINVAL; }
+        {
+            const unsigned char* d8 = nullptr;
+            const size_t esz = batch->bg_bits == 16 ? 2 : 4;
+            if ((r = upload(ctx, ctx->in_bg, (const unsigned char*)batch->bg, (size_t)batch->n_bg * esz, &d8))) return r;
+            b.bg = (const int32_t*)d8;
+        }
         if (batch->kde_factor && params->fitter == O2A_FIT_KDE) {
             if ((r = upload(ctx, ctx->in_kde, batch->kde_factor, (size_t)batch->n_lnc, &b.kde_factor))) return r;
         } else b.kde_factor = nullptr;
@@ -734,6 +741,7 @@ extern "C" int o2a_fitter_eval(o2a_ctx* ctx, int32_t fitter, const int32_t* bg, 
     if ((r = upload(ctx, ctx->in_bg_off, (const int64_t*)off, 2, &b.bg_off))) return r;
     if ((r = upload(ctx, ctx->in_aln_off, (const int64_t*)zero2, 2, &b.aln_off))) return r;
     if ((r = upload(ctx, ctx->in_bg, bg, (size_t)n_bg, &b.bg))) return r;
+    b.bg_bits = 32;
     if ((r = upload(ctx, ctx->in_kde, &kde_factor, 1, &b.kde_factor))) return r;
     ctx->prm = o2a_params{};
     ctx->prm.fitter = fitter;

@@ -181,7 +181,7 @@ __device__ double pw_leaf_sum(const int* pos, const double* t, int lo, int hi, l
 struct FitArgs {
     long long n_lnc;
     const long long* bg_off;
-    const int* bg;
+    const void* bg;                      // int32 (BG = int) or int16 (BG = short)
     const double* kde_factor;
     int fitter;
     double alpha;
@@ -204,9 +204,11 @@ __device__ __forceinline__ void fit_publish_thr(const FitArgs& A, long long l, d
 }
 
 // status 4 = value range larger than the counting scratch (max_range)
+template <typename BG>
 __global__ void __launch_bounds__(FIT_THREADS)
 k_fit(FitArgs A)
 {
+    constexpr int PER = 16 / (int)sizeof(BG);           // background scores per 16-byte load
     __shared__ int s_cnt[FIT_SMEM_RANGE];
     __shared__ int s_k[FIT_SMEM_NNZ];        // distinct value (then bin index)
     __shared__ int s_c[FIT_SMEM_NNZ];        // multiplicity (then bin count)
@@ -231,7 +233,7 @@ k_fit(FitArgs A)
         }
         const long long b0 = A.bg_off[l];
         const long long n = A.bg_off[l + 1] - b0;
-        const int* x = A.bg + b0;
+        const BG* x = reinterpret_cast<const BG*>(A.bg) + b0;
         // ---- pass over the background: min / max, and (optimistically) the multiplicities ----------
         // BLAST scores are small non-negative integers: values in [0, FIT_SMEM_RANGE) are counted
         // directly in shared memory during the same pass; anything else falls back to the general
@@ -254,15 +256,21 @@ k_fit(FitArgs A)
                 if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) atomicAdd(&s_cnt[v__], 1); else oor = true; } while (0)
 #endif
             // 16-byte vector loads over the aligned middle part
-            long long head = ((4 - (b0 & 3)) & 3); if (head > n) head = n;
+            long long head = ((PER - (b0 & (PER - 1))) & (PER - 1)); if (head > n) head = n;
             for (long long i = tid; i < head; i += FIT_THREADS) O2A_FIT_ADD(x[i]);
             const int4* x4 = reinterpret_cast<const int4*>(x + head);
-            const int n4 = (int)((n - head) >> 2);
+            const int n4 = (int)((n - head) / PER);
             for (int i = tid; i < n4; i += FIT_THREADS) {
-                int4 v = x4[i];
-                O2A_FIT_ADD(v.x); O2A_FIT_ADD(v.y); O2A_FIT_ADD(v.z); O2A_FIT_ADD(v.w);
+                const int4 v = x4[i];
+                if (PER == 4) { O2A_FIT_ADD(v.x); O2A_FIT_ADD(v.y); O2A_FIT_ADD(v.z); O2A_FIT_ADD(v.w); }
+                else {
+                    O2A_FIT_ADD((int)(short)(v.x & 0xffff)); O2A_FIT_ADD(v.x >> 16);
+                    O2A_FIT_ADD((int)(short)(v.y & 0xffff)); O2A_FIT_ADD(v.y >> 16);
+                    O2A_FIT_ADD((int)(short)(v.z & 0xffff)); O2A_FIT_ADD(v.z >> 16);
+                    O2A_FIT_ADD((int)(short)(v.w & 0xffff)); O2A_FIT_ADD(v.w >> 16);
+                }
             }
-            for (long long i = head + ((long long)n4 << 2) + tid; i < n; i += FIT_THREADS) O2A_FIT_ADD(x[i]);
+            for (long long i = head + (long long)n4 * PER + tid; i < n; i += FIT_THREADS) O2A_FIT_ADD(x[i]);
 #undef O2A_FIT_ADD
             if (oor) s_oor = 1;
         }
@@ -298,7 +306,7 @@ k_fit(FitArgs A)
                 bool valid = i < n;
                 unsigned m = __ballot_sync(FULL_MASK, valid);
                 if (valid) {
-                    int c = x[i] - mn;
+                    int c = (int)x[i] - mn;
                     unsigned peers = __match_any_sync(m, c);
                     if ((peers & lanemask_lt()) == 0) atomicAdd(&cnt[c], __popc(peers));
                 }

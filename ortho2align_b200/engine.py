@@ -25,7 +25,7 @@ def _p(a):
 class DeviceBatch:
     """A ColumnarBatch resident in HBM (torch tensors own the memory; the library gets raw pointers)."""
 
-    def __init__(self, batch: ColumnarBatch, device, aos=True, score_bits=0):
+    def __init__(self, batch: ColumnarBatch, device, aos=True, score_bits=0, bg_bits=32):
         import torch
         self.n_lnc, self.n_aln, self.n_hsp, self.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
         self.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
@@ -37,6 +37,9 @@ class DeviceBatch:
         self.aos = aos
         if aos:
             self.t["coords"] = torch.from_numpy(batch.coords4()).to(device)
+        self.bg_bits = bg_bits
+        if bg_bits == 16:
+            self.t["bg"] = torch.from_numpy(batch.bg16()).to(device)
         self.score_bits = score_bits
         if score_bits:
             q, eo, ep, ev = batch.quantized_scores(score_bits)
@@ -52,6 +55,7 @@ class DeviceBatch:
             setattr(s, k, self.t[k].data_ptr())
         s.kde_factor = self.t["kde_factor"].data_ptr() if with_kde else None
         s.coords = self.t["coords"].data_ptr() if self.aos else None
+        s.bg_bits = self.bg_bits
         s.score_bits = self.score_bits
         if self.score_bits:
             for k in ("score_q", "exc_off", "exc_pos", "exc_val"):
@@ -115,10 +119,11 @@ class Engine:
         return p
 
     @staticmethod
-    def host_struct(batch: ColumnarBatch, with_kde, coords=None, narrow=None):
+    def host_struct(batch: ColumnarBatch, with_kde, coords=None, narrow=None, bg16=None):
         """`coords`: optional AoS int32 [n_hsp, 4] array (e.g. pinned) used instead of the SoA arrays.
         `narrow`: optional (bits, score_q, exc_off, exc_pos, exc_val) from `quantized_scores` (the arrays
-        must stay alive until the call returns) used instead of the float64 `score`."""
+        must stay alive until the call returns) used instead of the float64 `score`.
+        `bg16`: optional int16 copy of `batch.bg` (`ColumnarBatch.bg16`) used instead of the int32 array."""
         s = _lib.O2ABatch()
         s.n_lnc, s.n_aln, s.n_hsp, s.n_bg = batch.n_lnc, batch.n_aln, batch.n_hsp, batch.n_bg
         for k in ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score"):
@@ -127,6 +132,9 @@ class Engine:
             setattr(s, k, a.ctypes.data)
         s.kde_factor = batch.ensure_kde_factor().ctypes.data if with_kde else None
         s.coords = coords.ctypes.data if coords is not None else None
+        if bg16 is not None:
+            assert bg16.dtype == np.int16 and len(bg16) == batch.n_bg
+            s.bg, s.bg_bits = bg16.ctypes.data, 16
         if narrow is not None:
             s.score_bits = int(narrow[0])
             s.score_q, s.exc_off = narrow[1].ctypes.data, narrow[2].ctypes.data
@@ -176,11 +184,12 @@ class Engine:
 
     def build_batch(self, batch: ColumnarBatch, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
                     best_value="block_length", best_function="max", survivors=True, aos=False,
-                    score_bits=0) -> BatchResult:
+                    score_bits=0, bg_bits=32) -> BatchResult:
         """Host buffers in, host results out (the e2e boundary)."""
         p = self.params(fitter, fdr, alpha, gapopen, gapextend, best_value, best_function)
         narrow = (score_bits,) + batch.quantized_scores(score_bits) if score_bits else None
-        s = self.host_struct(batch, with_kde=(fitter == "kde"), coords=batch.coords4() if aos else None, narrow=narrow)
+        s = self.host_struct(batch, with_kde=(fitter == "kde"), coords=batch.coords4() if aos else None, narrow=narrow,
+                             bg16=batch.bg16() if bg_bits == 16 else None)
         self.run(s, p)
         return self.fetch(survivors=survivors)
 

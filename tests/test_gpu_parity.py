@@ -67,7 +67,7 @@ def test_synthetic_vs_oracle(engine, cfg, kw, fitter, fdr):
     got = engine.build_batch(b, fitter, fdr, aos=True)          # AoS coordinates (o2a_batch.coords)
     compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr} aos")
     for bits in (16, 32):                                       # narrow scores + exception lists
-        got = engine.build_batch(b, fitter, fdr, aos=True, score_bits=bits)
+        got = engine.build_batch(b, fitter, fdr, aos=True, score_bits=bits, bg_bits=bits)
         compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr} score_bits={bits}")
     assert engine.counts.n_survivors == int(exp.n_surv.sum())
     assert engine.counts.n_chains == int((exp.chain_len > 0).sum())
