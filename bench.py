@@ -317,7 +317,7 @@ def main():
 
     def step_e2e():
         eng.run(hstruct, params)
-        res = eng.fetch(survivors=False)     # per-lncRNA thr/status/best + per-alignment chains
+        res = eng.fetch(survivors=False, pinned=True)   # per-lncRNA thr/status/best + per-alignment chains
         return res
 
     step_e2e()

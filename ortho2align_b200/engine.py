@@ -19,7 +19,7 @@ class O2AError(RuntimeError):
 
 
 def _p(a):
-    return None if a is None else C.c_void_p(a.ctypes.data)
+    return None if a is None else C.c_void_p(a.__array_interface__["data"][0])
 
 
 class DeviceBatch:
@@ -79,11 +79,34 @@ class Engine:
         self.h = h
         self.counts = None
         self._geom = None
+        self._pinned = {}        # name -> (capacity in bytes, address): reusable page-locked result buffers
 
     def close(self):
         if getattr(self, "h", None):
+            for _, addr in self._pinned.values():
+                self.lib.o2a_host_free(C.c_void_p(addr))
+            self._pinned = {}
             self.lib.o2a_destroy(self.h)
             self.h = None
+
+    def _out(self, name, n, dtype, pinned):
+        """Result array: a fresh numpy array, or (pinned=True) a view of a reusable page-locked
+        buffer — valid until the next fetch on this engine, D2H at full PCIe rate."""
+        dtype = np.dtype(dtype)
+        if not pinned:
+            return np.zeros(n, dtype=dtype)
+        need = max(int(n) * dtype.itemsize, 16)
+        cap, addr = self._pinned.get(name, (0, 0))
+        if cap < need:
+            if addr:
+                self.lib.o2a_host_free(C.c_void_p(addr))
+            cap = need + need // 4
+            addr = self.lib.o2a_host_alloc(cap)
+            if not addr:
+                raise O2AError("o2a_host_alloc failed")
+            self._pinned[name] = (cap, addr)
+        buf = (C.c_char * need).from_address(addr)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
 
     def __del__(self):
         try:
@@ -140,6 +163,7 @@ class Engine:
             s.score_q, s.exc_off = narrow[1].ctypes.data, narrow[2].ctypes.data
             s.exc_pos, s.exc_val = narrow[3].ctypes.data, narrow[4].ctypes.data
         s.mem = 0
+        s._keepalive = (batch, coords, narrow, bg16)     # the struct holds raw addresses only
         s.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
         s.max_lnc_bg = int(np.diff(batch.bg_off).max()) if batch.n_lnc else 0
         return s
@@ -153,32 +177,38 @@ class Engine:
         self._geom = (batch_struct.n_lnc, batch_struct.n_aln)
         return counts
 
-    def fetch_chains(self):
+    def fetch_chains(self, pinned=False):
         n_lnc, n_aln = self._geom
-        chain_off = np.zeros(n_aln + 1, dtype=np.int64)
+        chain_off = self._out("chain_off", n_aln + 1, np.int64, pinned)
         n = int(self.counts.n_chain_hsps)
-        chain_idx = np.zeros(n, dtype=np.int32)
-        chain_pq = np.zeros(n, dtype=np.float64)
+        chain_idx = self._out("chain_idx", n, np.int32, pinned)
+        chain_pq = self._out("chain_pq", n, np.float64, pinned)
         self._check(self.lib.o2a_fetch_chains(self.h, _p(chain_off), _p(chain_idx), _p(chain_pq)), "o2a_fetch_chains")
         return chain_off, chain_idx, chain_pq
 
-    def fetch(self, survivors=True) -> BatchResult:
+    def fetch(self, survivors=True, pinned=False) -> BatchResult:
+        """Results of the last run. pinned=True returns views of reusable page-locked buffers (valid
+        until the next fetch on this engine) instead of fresh arrays."""
         n_lnc, n_aln = self._geom
-        thr = np.zeros(n_lnc); status = np.zeros(n_lnc, dtype=np.int32); best = np.zeros(n_lnc, dtype=np.int64)
+        o = lambda name, n, dt: self._out(name, n, dt, pinned)
+        thr, status, best = o("thr", n_lnc, np.float64), o("status", n_lnc, np.int32), o("best", n_lnc, np.int64)
         self._check(self.lib.o2a_fetch_lnc(self.h, _p(thr), _p(status), _p(best)), "o2a_fetch_lnc")
-        n_surv = np.zeros(n_aln, dtype=np.int32); n_keep = np.zeros(n_aln, dtype=np.int32)
-        chain_len = np.zeros(n_aln, dtype=np.int32); chain_orient = np.zeros(n_aln, dtype=np.uint8)
-        chain_score = np.zeros(n_aln); orient_scores = np.zeros((n_aln, 2))
+        n_surv, n_keep = o("n_surv", n_aln, np.int32), o("n_keep", n_aln, np.int32)
+        chain_len, chain_orient = o("chain_len", n_aln, np.int32), o("chain_orient", n_aln, np.uint8)
+        chain_score = o("chain_score", n_aln, np.float64)
+        orient_scores = o("orient_scores", 2 * n_aln, np.float64).reshape(n_aln, 2)
         self._check(self.lib.o2a_fetch_aln(self.h, _p(n_surv), _p(n_keep), _p(chain_len), _p(chain_orient),
                                            _p(chain_score), _p(orient_scores)), "o2a_fetch_aln")
         ns = int(self.counts.n_survivors) if survivors else 0
-        surv_off = np.zeros(n_aln + 1, dtype=np.int64)
-        surv_idx = np.zeros(ns, dtype=np.int32); surv_p = np.zeros(ns); surv_pq = np.zeros(ns)
-        surv_keep = np.zeros(ns, dtype=np.uint8)
+        surv_off = o("surv_off", n_aln + 1, np.int64)
+        surv_idx, surv_p, surv_pq = o("surv_idx", ns, np.int32), o("surv_p", ns, np.float64), o("surv_pq", ns, np.float64)
+        surv_keep = o("surv_keep", ns, np.uint8)
         if survivors:
             self._check(self.lib.o2a_fetch_survivors(self.h, _p(surv_off), _p(surv_idx), _p(surv_p), _p(surv_pq),
                                                      _p(surv_keep)), "o2a_fetch_survivors")
-        chain_off, chain_idx, chain_pq = self.fetch_chains()
+        elif pinned:
+            surv_off[:] = 0
+        chain_off, chain_idx, chain_pq = self.fetch_chains(pinned)
         return BatchResult(thr, status, best, n_surv, n_keep, chain_len, chain_orient, chain_score, orient_scores,
                            surv_off, surv_idx, surv_p, surv_pq, surv_keep, chain_off, chain_idx, chain_pq)
 

@@ -197,6 +197,17 @@ def test_pinned_host_inputs_use_zero_copy_coordinates(engine):
         compare_results(engine.fetch(), ref, exact_p=True, what="pinned zero-copy")
 
 
+def test_pinned_result_buffers_match_fresh_arrays(engine):
+    from ortho2align_b200 import synth
+    b = synth.workload(2, n_lnc=20, seed=21)
+    fresh = engine.build_batch(b, "hist", True)
+    engine.run(engine.host_struct(b, False), engine.params("hist", True))
+    compare_results(engine.fetch(pinned=True), fresh, exact_p=True, what="pinned results")
+    engine.run(engine.host_struct(b.slice_lnc(0, 5), False), engine.params("hist", True))
+    small = engine.fetch(pinned=True)        # buffers are reused: shapes follow the new batch
+    assert small.thr.shape == (5,) and np.array_equal(small.thr, fresh.thr[:5])
+
+
 def test_round_trip_properties_at_scale(engine):
     """Size-independent properties on a batch too large for the oracle to be worth running."""
     from ortho2align_b200 import synth
