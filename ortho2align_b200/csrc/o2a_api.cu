@@ -386,7 +386,7 @@ static int run_score(o2a_ctx* ctx)
             b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
             P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
     else
-        k_filter<<<grid_for(ctx, b.n_aln, 6), FILTER_THREADS, 0, ctx->stream>>>(
+        k_filter<<<grid_for(ctx, b.n_aln, 20), FILTER_THREADS, 0, ctx->stream>>>(
             b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), b.score, P<double>(ctx->thr), P<int>(ctx->status),
             P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
     LAUNCH_CHECK();

@@ -15,8 +15,8 @@
 
 namespace o2a {
 
-constexpr int FILTER_THREADS = 256;
-constexpr int FILTER_ROWS = 4;                       // rows (double2 per lane) per warp and pass
+constexpr int FILTER_THREADS = 64;
+constexpr int FILTER_ROWS = 8;                       // rows (double2 per lane) per warp and pass
 constexpr int FILTER_TILE = FILTER_THREADS * 2 * FILTER_ROWS;
 constexpr int PQ_THREADS = 64;
 constexpr int RANK_SMALL_MAX = 1024;                 // survivors ranked in shared memory
@@ -33,7 +33,7 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double* p)
 // [w*FILTER_WCHUNK, (w+1)*FILTER_WCHUNK), as FILTER_ROWS rows of 64 elements (32 lanes x double2,
 // 512 contiguous bytes per warp load). Order-preserving positions then need only: the lane prefix
 // (ballots), the running row prefix (registers) and ONE cross-warp prefix per tile (8 counters).
-__global__ void __launch_bounds__(FILTER_THREADS, 5)
+__global__ void __launch_bounds__(FILTER_THREADS, 20)
 k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __restrict__ aln_lnc,
          const double* __restrict__ score, const double* __restrict__ thr, const int* __restrict__ lnc_status,
          int* __restrict__ n_surv, int* __restrict__ surv_idx, double* __restrict__ surv_x)
