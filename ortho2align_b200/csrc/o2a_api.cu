@@ -343,7 +343,7 @@ static int run_fit(o2a_ctx* ctx)
         ENS(uv_cnt, (b.n_bg + 1) * sizeof(int));
         ENS(uv_n, b.n_lnc * sizeof(int));
     }
-    int grid = grid_for(ctx, b.n_lnc, 8);
+    int grid = grid_for(ctx, b.n_lnc, 12);
     // per-CTA global counters for backgrounds whose value range exceeds the shared-memory budget
     long long max_range = UV_MAX_RANGE;
     ENS(fit_cnt, (size_t)grid * max_range * sizeof(int));

@@ -22,8 +22,8 @@
 
 namespace o2a {
 
-constexpr int FIT_THREADS = 128;
-constexpr int FIT_SMEM_RANGE = 2048;    // distinct-value counters kept in shared memory up to this range
+constexpr int FIT_THREADS = 64;
+constexpr int FIT_SMEM_RANGE = 1024;    // distinct-value counters kept in shared memory up to this range
 constexpr int FIT_SMEM_NNZ = 512;       // distinct values / non-empty bins staged in shared memory
 #ifndef O2A_FIT_MATCH
 #define O2A_FIT_MATCH 0                 // 1: warp-aggregate equal values (match.any) before the shared atomic
