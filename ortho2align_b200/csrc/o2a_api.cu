@@ -402,8 +402,14 @@ static int run_score(o2a_ctx* ctx)
     A.surv_x = P<double>(ctx->surv_x); A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
     A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep);
     A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
-    k_pq<<<grid_for(ctx, b.n_aln, 14), PQ_THREADS, 0, ctx->stream>>>(A);
+    // warp variant: alignments with <= 256 survivors; CTA variant: the rest (up to RANK_SMALL_MAX in shared
+    // memory, beyond that p only + k_rank_big)
+    k_pq<32, 32, 0, 256, 128, 32, 128><<<grid_for(ctx, b.n_aln, 32), 32, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
+    if (b.max_aln_hsps > 256) {
+        k_pq<64, 14, 256, RANK_SMALL_MAX, 256, 128, TBL_SMEM_MAX><<<grid_for(ctx, b.n_aln, 14), 64, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+    }
     if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
         int g2 = grid_for(ctx, b.n_aln, 2);
         r = ensure_sort_scratch(ctx, g2, b.max_aln_hsps);

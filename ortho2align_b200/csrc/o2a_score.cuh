@@ -18,7 +18,6 @@ namespace o2a {
 constexpr int FILTER_THREADS = 64;
 constexpr int FILTER_ROWS = 8;                       // rows (double2 per lane) per warp and pass
 constexpr int FILTER_TILE = FILTER_THREADS * 2 * FILTER_ROWS;
-constexpr int PQ_THREADS = 64;
 constexpr int RANK_SMALL_MAX = 1024;                 // survivors ranked in shared memory
 constexpr int TBL_SMEM_MAX = 256;
 
@@ -321,9 +320,9 @@ struct PqArgs {
 //   rank_k = 1 + L[class_k] + #{j < k : p_j == p_k}
 // exactly as np.argsort(kind='stable') would assign it. More than PQ_OVER overflow classes fall back
 // to the plain all-pairs rank.
-constexpr int PQ_DIRECT = 256;
-constexpr int PQ_OVER = 128;
-constexpr int PQ_SLOTS = PQ_DIRECT + PQ_OVER;
+// Two instantiations: the warp variant (32 threads, <= 256 survivors, small tables: 32 CTAs per SM, so
+// 32 alignments in flight per SM hide the per-alignment latency chain) and the CTA variant for larger
+// survivor sets. Each skips the alignments of the other's domain.
 
 struct PqFit {
     LncFit f; const int* tk; const double* tc;
@@ -337,12 +336,14 @@ __device__ __forceinline__ double pq_sf(double x, const PqFit& F)
     return emp_sf_compressed(x, F.uval, F.ucnt, F.unv, F.nbg);
 }
 
-__global__ void __launch_bounds__(PQ_THREADS, 14)
+template <int PQ_THREADS, int MIN_BLOCKS, int SMAX_LO, int SMAX, int PQ_DIRECT, int PQ_OVER, int TBL_MAX>
+__global__ void __launch_bounds__(PQ_THREADS, MIN_BLOCKS)
 k_pq(PqArgs A)
 {
+    constexpr int PQ_SLOTS = PQ_DIRECT + PQ_OVER;     // survivors in (SMAX_LO, SMAX] are this instantiation's
     // class tables; the all-pairs fallback (s_p) aliases them — the two are never live together
     __shared__ __align__(16) unsigned char s_raw[PQ_SLOTS * (8 + 4 + 4 + 2 + 2) + PQ_OVER * 8];
-    static_assert(sizeof(s_raw) >= RANK_SMALL_MAX * sizeof(double), "fallback buffer must fit");
+    static_assert(sizeof(s_raw) >= SMAX * sizeof(double), "fallback buffer must fit");
     double* s_p = reinterpret_cast<double*>(s_raw);                        // fallback path only
     double* s_pe = reinterpret_cast<double*>(s_raw);                       // p of the class
     double* s_ox = s_pe + PQ_SLOTS;                                        // scores of the overflow classes
@@ -350,16 +351,17 @@ k_pq(PqArgs A)
     int* s_L = s_cnt + PQ_SLOTS;                                           // survivors with strictly smaller p
     short* s_g = reinterpret_cast<short*>(s_L + PQ_SLOTS);                 // tie group = first slot with the same p
     short* s_dense = s_g + PQ_SLOTS;                                       // non-empty classes, slot order
-    __shared__ int s_tk[TBL_SMEM_MAX];
-    __shared__ double s_tc[TBL_SMEM_MAX];
-    __shared__ short s_slot[RANK_SMALL_MAX];        // class of every survivor
+    __shared__ int s_tk[TBL_MAX];
+    __shared__ double s_tc[TBL_MAX];
+    __shared__ short s_slot[SMAX];        // class of every survivor
     __shared__ int s_scan[PQ_THREADS / 32 + 2];
     __shared__ int s_keepcnt, s_nover, s_maxslot;
     const int tid = threadIdx.x, lane = lane_id();
 
     for (long long a = blockIdx.x; a < A.n_aln; a += gridDim.x) {
         const int ns = A.n_surv[a];
-        if (ns == 0) { if (tid == 0) A.n_keep[a] = 0; continue; }
+        if (ns == 0) { if (tid == 0 && SMAX_LO == 0) A.n_keep[a] = 0; continue; }
+        if (ns <= SMAX_LO || (ns > SMAX && SMAX < RANK_SMALL_MAX)) continue;    // the other instantiation's
         const int l = A.aln_lnc[a];
         const long long h0 = A.hsp_off[a];
         const int m = (int)(A.hsp_off[a + 1] - h0);
@@ -370,7 +372,7 @@ k_pq(PqArgs A)
             F.f = A.fits[l];
             const long long tb = A.bg_off[l] >> 1;
             F.tk = A.tbl_k + tb; F.tc = A.tbl_cum + tb;
-            if (F.f.tbl_n <= TBL_SMEM_MAX) {
+            if (F.f.tbl_n <= TBL_MAX) {
                 for (int t = tid; t < F.f.tbl_n; t += PQ_THREADS) { s_tk[t] = F.tk[t]; s_tc[t] = F.tc[t]; }
                 F.tk = s_tk; F.tc = s_tc;
             }
@@ -382,7 +384,7 @@ k_pq(PqArgs A)
         }
         const double* xin = A.surv_x + h0;            // survivor scores
         double* xs = A.surv_p + h0;                   // out: p-values
-        if (ns > RANK_SMALL_MAX) {
+        if (ns > SMAX) {
             // big survivor set: p per survivor here, ranks by radix sort in k_rank_big
             __syncthreads();
             for (int k = tid; k < ns; k += PQ_THREADS) {
