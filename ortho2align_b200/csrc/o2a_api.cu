@@ -52,7 +52,7 @@ struct o2a_ctx {
     DevBuf ret_coord, ret_score, ret_slot, in_coords;
     const int4* coords4 = nullptr;    // AoS coordinates actually used (device or mapped host), or null
     DevBuf big_list, mid_list, big_count, counters;
-    DevBuf fit_cnt;
+    DevBuf fit_cnt, fc_val, fc_cnt, fc_n, fit_list, fit_list_n;
     bool coords_zero_copy = false;   // qstart..send read in place from pinned, device-mapped host memory
     DevBuf sort_k0, sort_k1, sort_v0, sort_v1;
     DevBuf cb_qs, cb_qe, cb_ss, cb_se, cb_sc, cb_id, cb_total, cb_prev, cb_f, cb_chain;
@@ -241,7 +241,8 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
                       &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->ret_coord,
                       &ctx->ret_score, &ctx->ret_slot, &ctx->in_coords, &ctx->big_list,
-                      &ctx->mid_list, &ctx->big_count, &ctx->counters, &ctx->fit_cnt, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
+                      &ctx->mid_list, &ctx->big_count, &ctx->counters, &ctx->fit_cnt, &ctx->fc_val, &ctx->fc_cnt, &ctx->fc_n, &ctx->fit_list,
+                      &ctx->fit_list_n, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
                       &ctx->cb_qe, &ctx->cb_ss, &ctx->cb_se, &ctx->cb_sc, &ctx->cb_id, &ctx->cb_total, &ctx->cb_prev,
                       &ctx->cb_f, &ctx->cb_chain, &ctx->off_a, &ctx->off_b, &ctx->out_i32, &ctx->out_f64a,
                       &ctx->out_f64b, &ctx->out_u8, &ctx->maxred};
@@ -351,6 +352,21 @@ static int run_fit(o2a_ctx* ctx)
     A.tbl_cum = P<double>(ctx->tbl_cum); A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt);
     A.uv_n = P<int>(ctx->uv_n); A.status = P<int>(ctx->status); A.g_cnt = P<int>(ctx->fit_cnt);
     A.max_range = max_range;
+    if (p.fitter == O2A_FIT_HIST) {
+        // fast path: count distinct values (CTA per lncRNA), exact numpy/scipy arithmetic (warp per lncRNA);
+        // what it cannot take is listed and goes through the general kernel
+        ENS(fc_val, (size_t)b.n_lnc * FITW_CAP * sizeof(int)); ENS(fc_cnt, (size_t)b.n_lnc * FITW_CAP * sizeof(int));
+        ENS(fc_n, b.n_lnc * sizeof(int)); ENS(fit_list, (b.n_lnc + 1) * sizeof(int)); ENS(fit_list_n, sizeof(int));
+        CU(cudaMemsetAsync(ctx->fit_list_n.p, 0, sizeof(int), ctx->stream));
+        A.fc_val = P<int>(ctx->fc_val); A.fc_cnt = P<int>(ctx->fc_cnt); A.fc_n = P<int>(ctx->fc_n);
+        A.list = P<int>(ctx->fit_list); A.list_n = P<int>(ctx->fit_list_n);
+        const int gc = grid_for(ctx, b.n_lnc, 8);
+        if (b.bg_bits == 16) k_fit_count<short><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
+        else k_fit_count<int><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+        k_fit_hist_tail<<<grid_for(ctx, (b.n_lnc + FITW_WARPS - 1) / FITW_WARPS, 8), FITW_WARPS * 32, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+    }
     if (b.bg_bits == 16) k_fit<short><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     else k_fit<int><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();

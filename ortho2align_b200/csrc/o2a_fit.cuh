@@ -193,6 +193,10 @@ struct FitArgs {
     int* g_cnt; long long max_range;     // per-CTA global counters for value ranges > FIT_SMEM_RANGE
     const long long* aln_off;            // [n_lnc+1]
     double* thr_aln;                     // [n_aln] threshold of every alignment (+inf if the fit failed)
+    // hist fast path (k_fit_count + k_fit_hist_tail): fixed-capacity (value, count) slots per lncRNA;
+    // lncRNAs it cannot take (wide value range, > FITW_CAP distinct values) are listed for k_fit
+    int* fc_val; int* fc_cnt; int* fc_n;
+    int* list; int* list_n;              // when list != nullptr, k_fit processes list[0..*list_n) only
 };
 
 // thr_aln[a] for the alignments of lncRNA l: what k_filter compares against (+inf: nothing survives,
@@ -225,10 +229,13 @@ k_fit(FitArgs A)
     const int tid = threadIdx.x;
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
 
-    for (long long l = blockIdx.x; l < A.n_lnc; l += gridDim.x) {
-        if (l != (long long)blockIdx.x) {
+    const long long n_items = A.list ? (long long)*A.list_n : A.n_lnc;
+    for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const long long l = A.list ? (long long)A.list[it] : it;
+        if (it != (long long)blockIdx.x) {
             // results of the previous lncRNA are visible to the whole CTA (every path ends in a barrier)
-            const long long lp = l - gridDim.x;
+            const long long ip = it - gridDim.x;
+            const long long lp = A.list ? (long long)A.list[ip] : ip;
             fit_publish_thr(A, lp, A.thr[lp], A.status[lp]);
         }
         const long long b0 = A.bg_off[l];
@@ -512,8 +519,236 @@ k_fit(FitArgs A)
     }
     {   // the last lncRNA of this CTA
         long long last = -1;
-        for (long long l = blockIdx.x; l < A.n_lnc; l += gridDim.x) last = l;
-        if (last >= 0) fit_publish_thr(A, last, A.thr[last], A.status[last]);
+        for (long long it = blockIdx.x; it < n_items; it += gridDim.x) last = it;
+        if (last >= 0) { const long long ll = A.list ? (long long)A.list[last] : last; fit_publish_thr(A, ll, A.thr[ll], A.status[ll]); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Histogram fast path, stage 1: one CTA per lncRNA streams the background once and counts the
+// distinct values (values in [0, FIT_SMEM_RANGE), the BLAST case) -> up to FITW_CAP (value, count)
+// pairs per lncRNA. Anything else is flagged (fc_n = -1) for the general kernel k_fit.
+// ---------------------------------------------------------------------------------------------
+constexpr int FITC_THREADS = 128;
+constexpr int FITW_CAP = 128;            // distinct background values handled by the warp-level tail
+
+template <typename BG>
+__global__ void __launch_bounds__(FITC_THREADS)
+k_fit_count(FitArgs A)
+{
+    constexpr int PER = 16 / (int)sizeof(BG);
+    __shared__ int s_cnt[FIT_SMEM_RANGE];
+    __shared__ int s_scan[FITC_THREADS / 32 + 2];
+    __shared__ int s_oor;
+    const int tid = threadIdx.x;
+    for (long long l = blockIdx.x; l < A.n_lnc; l += gridDim.x) {
+        const long long b0 = A.bg_off[l];
+        const long long n = A.bg_off[l + 1] - b0;
+        const BG* x = reinterpret_cast<const BG*>(A.bg) + b0;
+        {
+            int4* z = reinterpret_cast<int4*>(s_cnt);
+            for (int k = tid; k < FIT_SMEM_RANGE / 4; k += FITC_THREADS) z[k] = make_int4(0, 0, 0, 0);
+            if (tid == 0) s_oor = 0;
+        }
+        __syncthreads();
+        {
+            bool oor = false;
+#define O2A_CNT(v) do { int v__ = (v); if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) atomicAdd(&s_cnt[v__], 1); else oor = true; } while (0)
+            long long head = ((PER - (b0 & (PER - 1))) & (PER - 1)); if (head > n) head = n;
+            for (long long i = tid; i < head; i += FITC_THREADS) O2A_CNT(x[i]);
+            const int4* x4 = reinterpret_cast<const int4*>(x + head);
+            const int n4 = (int)((n - head) / PER);
+            for (int i = tid; i < n4; i += FITC_THREADS) {
+                const int4 v = x4[i];
+                if (PER == 4) { O2A_CNT(v.x); O2A_CNT(v.y); O2A_CNT(v.z); O2A_CNT(v.w); }
+                else {
+                    O2A_CNT((int)(short)(v.x & 0xffff)); O2A_CNT(v.x >> 16); O2A_CNT((int)(short)(v.y & 0xffff)); O2A_CNT(v.y >> 16);
+                    O2A_CNT((int)(short)(v.z & 0xffff)); O2A_CNT(v.z >> 16); O2A_CNT((int)(short)(v.w & 0xffff)); O2A_CNT(v.w >> 16);
+                }
+            }
+            for (long long i = head + (long long)n4 * PER + tid; i < n; i += FITC_THREADS) O2A_CNT(x[i]);
+#undef O2A_CNT
+            if (oor) s_oor = 1;
+        }
+        __syncthreads();
+        int nv = 0;
+        if (s_oor == 0) {
+            int* ov = A.fc_val + l * FITW_CAP; int* oc = A.fc_cnt + l * FITW_CAP;
+            for (int k0 = 0; k0 < FIT_SMEM_RANGE; k0 += FITC_THREADS) {
+                const int c = s_cnt[k0 + tid];
+                int tot;
+                const int pos = cta_exclusive_scan(c != 0, s_scan, &tot);
+                if (c != 0 && nv + pos < FITW_CAP) { ov[nv + pos] = k0 + tid; oc[nv + pos] = c; }
+                nv += tot;
+                __syncthreads();
+            }
+        }
+        if (tid == 0) A.fc_n[l] = (s_oor == 0 && nv <= FITW_CAP) ? nv : -1;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Histogram fast path, stage 2: one WARP per lncRNA does the exact numpy/scipy arithmetic on the
+// distinct values (same steps as k_fit's histogram branch, warp-synchronous): many lncRNAs in
+// flight per SM hide the serial parts (pairwise-sum combine, cumsum, isf).
+// ---------------------------------------------------------------------------------------------
+constexpr int FITW_WARPS = 4;
+
+__global__ void __launch_bounds__(FITW_WARPS * 32)
+k_fit_hist_tail(FitArgs A)
+{
+    __shared__ int s_k[FITW_WARPS][FITW_CAP];
+    __shared__ int s_c[FITW_WARPS][FITW_CAP];
+    __shared__ double s_t[FITW_WARPS][FITW_CAP];
+    __shared__ double s_lsum[FITW_WARPS][FITW_CAP];
+    __shared__ short s_ldep[FITW_WARPS][FITW_CAP];
+    __shared__ double s_vstk[FITW_WARPS][72];
+    __shared__ short s_ostk[FITW_WARPS][72];
+    const int lane = lane_id(), w = warp_id();
+    int* K = s_k[w]; int* Cn = s_c[w]; double* T = s_t[w]; double* LS = s_lsum[w]; short* LD = s_ldep[w];
+    double* VS = s_vstk[w]; short* OS = s_ostk[w];
+    const double NaN = __longlong_as_double(0x7ff8000000000000ll);
+    const long long nwarps = (long long)gridDim.x * FITW_WARPS;
+    for (long long l = (long long)blockIdx.x * FITW_WARPS + w; l < A.n_lnc; l += nwarps) {
+        const int nv = A.fc_n[l];
+        if (nv < 0) {                                    // general kernel takes it
+            if (lane == 0) { const int slot = atomicAdd(A.list_n, 1); A.list[slot] = (int)l; }
+            continue;
+        }
+        const long long b0 = A.bg_off[l];
+        const long long n = A.bg_off[l + 1] - b0;
+        const long long B = n / 2;
+        __syncwarp();
+        for (int i = lane; i < nv; i += 32) { K[i] = A.fc_val[l * FITW_CAP + i]; Cn[i] = A.fc_cnt[l * FITW_CAP + i]; }
+        __syncwarp();
+        int st = 0; double thr_v = NaN;
+        LncFit f{};
+        if (B < 1 || nv < 1) st = 3;
+        else {
+            const int mn = K[0], mx = K[nv - 1];
+            f.first = (double)mn; f.last = (double)mx;
+            if (mn == mx) { f.first = __dsub_rn(f.first, 0.5); f.last = __dadd_rn(f.last, 0.5); }
+            f.denom = __dsub_rn(f.last, f.first);
+            f.B = B;
+            f.step = __ddiv_rn(f.denom, (double)B);
+            // "Too many bins for data range" unless the edges strictly increase (see k_fit)
+            const double amax = fmax(fabs(f.first), fabs(f.last));
+            if (!(f.step > amax * 1.7763568394002505e-15)) {
+                bool bad = false;
+                for (long long k = lane; k < B; k += 32) if (!(hist_edge(k, f) < hist_edge(k + 1, f))) bad = true;
+                if (__any_sync(FULL_MASK, bad)) st = 3;
+            }
+        }
+        int nnz = 0;
+        if (st == 0) {
+            // bin index of every distinct value (np.histogram uniform-bin path incl. its fix-ups)
+            for (int i = lane; i < nv; i += 32) {
+                const double v = (double)K[i];
+                const double g = __dmul_rn(__ddiv_rn(__dsub_rn(v, f.first), f.denom), (double)B);
+                long long idx = (long long)g;
+                if (idx == B) idx -= 1;
+                if (v < hist_edge(idx, f)) idx -= 1;
+                if (v >= hist_edge(idx + 1, f) && idx != B - 1) idx += 1;
+                K[i] = (int)idx;
+            }
+            __syncwarp();
+            // merge distinct values that share a bin (bins are non-decreasing): head flags -> slots
+            for (int i0 = 0; i0 < nv; i0 += 32) {
+                const int i = i0 + lane;
+                const bool head = i < nv && (i == 0 || K[i] != K[i - 1]);
+                const unsigned hb = __ballot_sync(FULL_MASK, head);
+                const int slot = nnz + __popc(hb & (lanemask_lt() | (1u << lane))) - 1;
+                const int kk = i < nv ? K[i] : 0, cc = i < nv ? Cn[i] : 0;
+                __syncwarp();
+                if (head) { K[slot] = kk; Cn[slot] = 0; }
+                __syncwarp();
+                if (i < nv) atomicAdd(&Cn[slot], cc);
+                nnz += __popc(hb);
+                __syncwarp();
+            }
+            const double total = (double)n;
+            for (int t = lane; t < nnz; t += 32) { double hp0, ww; T[t] = fit_term(Cn[t], K[t], f, total, &hp0, &ww); }
+            __syncwarp();
+            // numpy pairwise sum: leaves (heads sum their leaf), then precedence evaluation
+            for (int t = lane; t < nnz; t += 32) {
+                const PwLeaf L = pw_find_leaf(K[t], B);
+                bool head = true; int dep = -1;
+                if (t > 0) {
+                    const PwLeaf P = pw_find_leaf(K[t - 1], B);
+                    head = (P.off != L.off);
+                    if (head) dep = pw_lca_depth(P, L);
+                }
+                LD[t] = (short)(head ? dep : -2);
+                if (head) {
+                    int hi = t + 1;
+                    while (hi < nnz && (long long)K[hi] < L.off + L.n) ++hi;
+                    LS[t] = pw_leaf_sum(K, T, t, hi, L.off, L.n);
+                }
+            }
+            __syncwarp();
+            double S = 0.0;
+            if (lane == 0) {
+                int vp = 0, op = 0;
+                for (int t = 0; t < nnz; ++t) {
+                    const int d = LD[t];
+                    if (d == -2) continue;
+                    if (t > 0) {
+                        while (op > 0 && OS[op - 1] > d) { double b2 = VS[--vp], a2 = VS[--vp]; VS[vp++] = __dadd_rn(a2, b2); --op; }
+                        OS[op++] = (short)d;
+                    }
+                    VS[vp++] = LS[t];
+                }
+                while (op > 0) { double b2 = VS[--vp], a2 = VS[--vp]; VS[vp++] = __dadd_rn(a2, b2); --op; }
+                S = nnz > 0 ? VS[0] : 0.0;
+            }
+            S = __shfl_sync(FULL_MASK, S, 0);
+            for (int t = lane; t < nnz; t += 32) {
+                double hp0, ww;
+                fit_term(Cn[t], K[t], f, total, &hp0, &ww);
+                T[t] = __dmul_rn(__ddiv_rn(hp0, S), ww);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                double acc = 0.0;                          // np.cumsum: sequential left to right
+                for (int t = 0; t < nnz; ++t) { acc = __dadd_rn(acc, T[t]); T[t] = acc; }
+                const double alpha = A.alpha;
+                double r;
+                if (alpha == 1.0) r = f.first;
+                else if (alpha == 0.0) r = f.last;
+                else if (!(alpha > 0.0 && alpha < 1.0)) r = NaN;
+                else {
+                    const double y = __dsub_rn(1.0, alpha);
+                    int lo = 0, hi = nnz;                   // first entry with cum > y
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (T[mid] > y) hi = mid; else lo = mid + 1; }
+                    if (lo == nnz) r = f.last;
+                    else {
+                        const long long j = K[lo];
+                        const double c0 = lo > 0 ? T[lo - 1] : 0.0, c1 = T[lo];
+                        const double xj = hist_edge(j, f);
+                        if (c0 == y) r = xj;
+                        else {
+                            const double slope = __ddiv_rn(__dsub_rn(hist_edge(j + 1, f), xj), __dsub_rn(c1, c0));
+                            r = __dadd_rn(__dmul_rn(slope, __dsub_rn(y, c0)), xj);
+                        }
+                    }
+                }
+                thr_v = r;
+            }
+            thr_v = __shfl_sync(FULL_MASK, thr_v, 0);
+            __syncwarp();
+            const long long tbase = b0 >> 1;
+            for (int t = lane; t < nnz; t += 32) { A.tbl_k[tbase + t] = K[t]; A.tbl_cum[tbase + t] = T[t]; }
+        }
+        if (lane == 0) {
+            LncFit fo = f; fo.tbl_n = st == 0 ? nnz : 0;
+            A.thr[l] = st == 0 ? thr_v : NaN; A.fits[l] = fo; A.status[l] = st;
+        }
+        {   // thr_aln for the alignments of this lncRNA
+            const double v = st == 0 ? thr_v : __longlong_as_double(0x7ff0000000000000ll);
+            for (long long a = A.aln_off[l] + lane; a < A.aln_off[l + 1]; a += 32) A.thr_aln[a] = v;
+        }
+        __syncwarp();
     }
 }
 
