@@ -95,6 +95,47 @@ def test_narrow_scores_with_many_exceptions(engine):
     compare_results(engine.fetch(), exp, exact_p=True, what="narrow device-resident")
 
 
+@pytest.mark.parametrize("value", ["block_length", "total_length", "block_count", "weight"])
+@pytest.mark.parametrize("function", ["max", "min"])
+def test_best_ortholog_selection_variants(engine, value, function):
+    """get_best_orthologs -value/-function (pipeline.py:981-989): device selection == oracle == the
+    reference's text-streaming step applied to records formatted from the chains."""
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    b = synth.workload(1, n_lnc=40, seed=31, hsps_per_region=400, n_bg=500)
+    exp = O.build_batch(b, "hist", True, best_value=value, best_function=function)
+    got = engine.build_batch(b, "hist", True, best_value=value, best_function=function)
+    compare_results(got, exp, exact_p=True, what=f"best {value}/{function}")
+    # independent check: recompute the key per alignment from the chain like the reference's extract lambdas
+    for l in range(b.n_lnc):
+        keys = []
+        for a in range(b.aln_off[l], b.aln_off[l + 1]):
+            c = got.chain_idx[got.chain_off[a]:got.chain_off[a + 1]] + b.hsp_off[a]
+            if len(c) == 0:
+                continue
+            qs, qe = b.qstart[c].astype(np.int64), b.qend[c].astype(np.int64)
+            k = {"block_length": int(np.abs(qe - qs).sum()),
+                 "total_length": int(max(qs.max(), qe.max()) - min(qs.min(), qe.min())),
+                 "block_count": len(c), "weight": float(sum(b.score[c].tolist()))}[value]
+            keys.append((a, k))
+        if not keys:
+            assert got.best_aln[l] == -1
+            continue
+        pick = (max if function == "max" else min)(keys, key=lambda t: t[1])      # first extremal element
+        assert got.best_aln[l] == pick[0]
+
+
+@pytest.mark.parametrize("alpha,gapopen,gapextend", [(0.01, 5, 2), (0.2, 0, 0), (0.05, 11, 1)])
+def test_parameter_variants(engine, alpha, gapopen, gapextend):
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    b = synth.workload(2, n_lnc=24, seed=41, hsps_per_region=800, n_bg=2000)
+    for fitter in ("hist", "empirical"):
+        exp = O.build_batch(b, fitter, True, alpha, gapopen, gapextend)
+        got = engine.build_batch(b, fitter, True, alpha, gapopen, gapextend)
+        compare_results(got, exp, exact_p=True, what=f"{fitter} a={alpha} G={gapopen} E={gapextend}")
+
+
 def test_kde_vs_oracle(engine):
     from oracle import oracle as O
     from ortho2align_b200 import synth
