@@ -341,6 +341,7 @@ def main():
               + res.chain_len.nbytes + res.chain_orient.nbytes + res.chain_score.nbytes + res.orient_scores.nbytes
               + res.chain_off.nbytes + res.chain_idx.nbytes + res.chain_pq.nbytes + 40)
     zero_copy = bool(eng.lib.o2a_coords_zero_copy(eng.h))
+    chunks = int(eng.lib.o2a_pipeline_chunks(eng.h))
     if zero_copy:
         # coordinates stay in pinned host memory; only the retained HSPs are read over PCIe (one 32 B sector each)
         h2d = int(h2d + 32 * int(res.n_keep.sum()))
@@ -349,7 +350,8 @@ def main():
     e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy,
            "score_layout": LAYOUTS[args.e2e_score_bits],
-           "stage_ms_last_step": e2e_stage_ms}
+           "pipelined_chunks": chunks,
+           ("stage_ms_last_step" if chunks <= 1 else "stage_ms_last_chunk"): e2e_stage_ms}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

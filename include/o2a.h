@@ -180,6 +180,11 @@ int o2a_best_chain(o2a_ctx *ctx, int64_t n, const int32_t *qstart, const int32_t
 int64_t o2a_launch_count(const o2a_ctx *ctx);
 /* 1 if the last host-memory o2a_build_batch read the HSP coordinates in place (pinned, mapped) */
 int  o2a_coords_zero_copy(const o2a_ctx *ctx);
+/* number of lncRNA chunks the last o2a_build_batch pipelined its host uploads in (1 = single pass).
+ * Host batches of >= 4 Mi HSPs are cut into chunks (default 8; env O2A_CHUNKS=1..16, O2A_NO_PIPELINE=1,
+ * O2A_PIPELINE_MIN_HSPS) so that the H2D copy of chunk c+1 overlaps the kernels of chunk c; with more than
+ * one chunk the stage times of o2a_get_stage_ms are those of the LAST chunk and "h2d" spans the others. */
+int  o2a_pipeline_chunks(const o2a_ctx *ctx);
 int  o2a_set_timing(o2a_ctx *ctx, int enabled);
 int  o2a_get_stage_ms(o2a_ctx *ctx, float *ms /*O2A_STAGE_COUNT*/);
 

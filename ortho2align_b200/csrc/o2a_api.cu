@@ -54,6 +54,11 @@ struct o2a_ctx {
     DevBuf big_list, mid_list, big_count, counters;
     DevBuf fit_cnt, fc_val, fc_cnt, fc_n, fit_list, fit_list_n;
     bool coords_zero_copy = false;   // qstart..send read in place from pinned, device-mapped host memory
+    // chunk view [vl0, vl1) lncRNAs / [va0, va1) alignments the stage launchers work on (whole batch by default)
+    long long vl0 = 0, vl1 = 0, va0 = 0, va1 = 0;
+    cudaStream_t copy_stream = nullptr;      // host path: H2D of chunk c+1 overlaps the kernels of chunk c
+    cudaEvent_t copy_ev[16] = {};
+    int pipelined_chunks = 0;
     DevBuf sort_k0, sort_k1, sort_v0, sort_v1;
     DevBuf cb_qs, cb_qe, cb_ss, cb_se, cb_sc, cb_id, cb_total, cb_prev, cb_f, cb_chain;
     DevBuf off_a, off_b, out_i32, out_f64a, out_f64b, out_u8, maxred;
@@ -227,6 +232,8 @@ extern "C" int o2a_create(o2a_ctx** out, int device)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return O2A_ECUDA; }
     for (int i = 0; i < N_EVENTS; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
     *out = ctx;
     return 0;
 }
@@ -256,6 +263,8 @@ extern "C" void o2a_destroy(o2a_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_all(ctx);
     for (int i = 0; i < N_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 16; ++i) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -286,6 +295,7 @@ extern "C" void o2a_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int64_t o2a_launch_count(const o2a_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
 extern "C" int o2a_coords_zero_copy(const o2a_ctx* ctx) { return ctx && ctx->coords_zero_copy ? 1 : 0; }
+extern "C" int o2a_pipeline_chunks(const o2a_ctx* ctx) { return ctx ? ctx->pipelined_chunks : 0; }
 extern "C" int o2a_set_timing(o2a_ctx* ctx, int enabled) { if (!ctx) return O2A_EINVAL; ctx->timing = enabled != 0; return 0; }
 extern "C" int o2a_get_stage_ms(o2a_ctx* ctx, float* ms)
 {
@@ -314,6 +324,24 @@ static int upload(o2a_ctx* ctx, DevBuf& dst, const T* src, size_t n, const T** o
     return 0;
 }
 
+// Bulk per-HSP / per-background / per-exception arrays of a host batch: when the call is pipelined the
+// copy is deferred and issued slice by slice on the copy stream (o2a_build_batch), else it is made here.
+enum { SLICE_BG = 0, SLICE_HSP = 1, SLICE_EXC = 2 };
+struct DeferredCopy { unsigned char* dst; const unsigned char* src; size_t esz; int kind; };
+
+static int upload_bulk(o2a_ctx* ctx, DevBuf& dst, const void* src, size_t n, size_t esz, int kind,
+                       std::vector<DeferredCopy>* deferred, const void** out)
+{
+    int r = ensure(ctx, dst, n * esz);
+    if (r) return r;
+    if (n) {
+        if (deferred) deferred->push_back({(unsigned char*)dst.p, (const unsigned char*)src, esz, kind});
+        else CU(cudaMemcpyAsync(dst.p, src, n * esz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    *out = dst.p;
+    return 0;
+}
+
 static int grid_for(o2a_ctx* ctx, long long items, int per_sm)
 {
     long long g = (long long)ctx->sm_count * per_sm;
@@ -329,10 +357,12 @@ static int run_fit(o2a_ctx* ctx)
     ENS(thr, b.n_lnc * sizeof(double));
     ENS(status, b.n_lnc * sizeof(int));
     ENS(thr_aln, b.n_aln * sizeof(double));
-    if (b.n_lnc == 0) return 0;
+    const long long l0 = ctx->vl0, nl = ctx->vl1 - ctx->vl0;
+    if (nl <= 0) return 0;
     FitArgs A{};
-    A.aln_off = (const long long*)b.aln_off; A.thr_aln = P<double>(ctx->thr_aln);
-    A.n_lnc = b.n_lnc; A.bg_off = (const long long*)b.bg_off; A.bg = b.bg; A.kde_factor = b.kde_factor;
+    A.aln_off = (const long long*)b.aln_off + l0; A.thr_aln = P<double>(ctx->thr_aln);
+    A.n_lnc = nl; A.bg_off = (const long long*)b.bg_off + l0; A.bg = b.bg;
+    A.kde_factor = b.kde_factor ? b.kde_factor + l0 : nullptr;
     A.fitter = p.fitter; A.alpha = p.alpha;
     if (p.fitter == O2A_FIT_HIST) {
         ENS(fits, b.n_lnc * sizeof(LncFit));
@@ -344,13 +374,14 @@ static int run_fit(o2a_ctx* ctx)
         ENS(uv_cnt, (b.n_bg + 1) * sizeof(int));
         ENS(uv_n, b.n_lnc * sizeof(int));
     }
-    int grid = grid_for(ctx, b.n_lnc, 12);
+    int grid = grid_for(ctx, nl, 12);
     // per-CTA global counters for backgrounds whose value range exceeds the shared-memory budget
     long long max_range = UV_MAX_RANGE;
-    ENS(fit_cnt, (size_t)grid * max_range * sizeof(int));
-    A.thr = P<double>(ctx->thr); A.fits = P<LncFit>(ctx->fits); A.tbl_k = P<int>(ctx->tbl_k);
+    ENS(fit_cnt, (size_t)grid_for(ctx, b.n_lnc, 12) * max_range * sizeof(int));
+    // per-lncRNA arrays are indexed relative to the view; tables / uv slots by absolute bg offsets
+    A.thr = P<double>(ctx->thr) + l0; A.fits = P<LncFit>(ctx->fits) + l0; A.tbl_k = P<int>(ctx->tbl_k);
     A.tbl_cum = P<double>(ctx->tbl_cum); A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt);
-    A.uv_n = P<int>(ctx->uv_n); A.status = P<int>(ctx->status); A.g_cnt = P<int>(ctx->fit_cnt);
+    A.uv_n = P<int>(ctx->uv_n) + l0; A.status = P<int>(ctx->status) + l0; A.g_cnt = P<int>(ctx->fit_cnt);
     A.max_range = max_range;
     if (p.fitter == O2A_FIT_HIST) {
         // fast path: count distinct values (CTA per lncRNA), exact numpy/scipy arithmetic (warp per lncRNA);
@@ -358,13 +389,14 @@ static int run_fit(o2a_ctx* ctx)
         ENS(fc_val, (size_t)b.n_lnc * FITW_CAP * sizeof(int)); ENS(fc_cnt, (size_t)b.n_lnc * FITW_CAP * sizeof(int));
         ENS(fc_n, b.n_lnc * sizeof(int)); ENS(fit_list, (b.n_lnc + 1) * sizeof(int)); ENS(fit_list_n, sizeof(int));
         CU(cudaMemsetAsync(ctx->fit_list_n.p, 0, sizeof(int), ctx->stream));
-        A.fc_val = P<int>(ctx->fc_val); A.fc_cnt = P<int>(ctx->fc_cnt); A.fc_n = P<int>(ctx->fc_n);
+        A.fc_val = P<int>(ctx->fc_val) + l0 * FITW_CAP; A.fc_cnt = P<int>(ctx->fc_cnt) + l0 * FITW_CAP;
+        A.fc_n = P<int>(ctx->fc_n) + l0;
         A.list = P<int>(ctx->fit_list); A.list_n = P<int>(ctx->fit_list_n);
-        const int gc = grid_for(ctx, b.n_lnc, 8);
+        const int gc = grid_for(ctx, nl, 8);
         if (b.bg_bits == 16) k_fit_count<short><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
         else k_fit_count<int><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
-        k_fit_hist_tail<<<grid_for(ctx, (b.n_lnc + FITW_WARPS - 1) / FITW_WARPS, 8), FITW_WARPS * 32, 0, ctx->stream>>>(A);
+        k_fit_hist_tail<<<grid_for(ctx, (nl + FITW_WARPS - 1) / FITW_WARPS, 8), FITW_WARPS * 32, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
     }
     if (b.bg_bits == 16) k_fit<short><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
@@ -390,40 +422,44 @@ static int run_score(o2a_ctx* ctx)
     ENS(big_list, (b.n_aln + 1) * sizeof(int)); ENS(mid_list, (b.n_aln + 1) * sizeof(int));
     ENS(big_count, 4 * sizeof(int));
     CU(cudaMemsetAsync(ctx->big_count.p, 0, 4 * sizeof(int), ctx->stream));
-    if (b.n_aln == 0) return stage_event(ctx, O2A_STAGE_PQ);
+    // per-alignment arrays are indexed relative to the view; everything per HSP / per lncRNA absolutely
+    const long long a0 = ctx->va0, na = ctx->va1 - ctx->va0;
+    if (na <= 0) return stage_event(ctx, O2A_STAGE_PQ);
+    const long long* hsp_off_v = (const long long*)b.hsp_off + a0;
+    const int* aln_lnc_v = P<int>(ctx->aln_lnc) + a0;
     if (b.score_bits == 16)
-        k_filter_q<short><<<grid_for(ctx, b.n_aln, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
-            b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), (const short*)b.score_q, (const long long*)b.exc_off,
+        k_filter_q<short><<<grid_for(ctx, na, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
+            na, hsp_off_v, aln_lnc_v, (const short*)b.score_q, (const long long*)b.exc_off + a0,
             b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
-            P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
+            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
     else if (b.score_bits == 32)
-        k_filter_q<int><<<grid_for(ctx, b.n_aln, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
-            b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), (const int*)b.score_q, (const long long*)b.exc_off,
+        k_filter_q<int><<<grid_for(ctx, na, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
+            na, hsp_off_v, aln_lnc_v, (const int*)b.score_q, (const long long*)b.exc_off + a0,
             b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
-            P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
+            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
     else
-        k_filter<<<grid_for(ctx, b.n_aln, 20), FILTER_THREADS, 0, ctx->stream>>>(
-            b.n_aln, (const long long*)b.hsp_off, P<int>(ctx->aln_lnc), b.score, P<double>(ctx->thr), P<int>(ctx->status),
-            P<int>(ctx->n_surv), P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
+        k_filter<<<grid_for(ctx, na, 20), FILTER_THREADS, 0, ctx->stream>>>(
+            na, hsp_off_v, aln_lnc_v, b.score, P<double>(ctx->thr), P<int>(ctx->status),
+            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
     LAUNCH_CHECK();
     int r = stage_event(ctx, O2A_STAGE_PQ);
     if (r) return r;
     PqArgs A{};
-    A.n_aln = b.n_aln; A.hsp_off = (const long long*)b.hsp_off; A.aln_lnc = P<int>(ctx->aln_lnc);
-    A.lnc_status = P<int>(ctx->status); A.n_surv = P<int>(ctx->n_surv); A.thr = P<double>(ctx->thr);
+    A.n_aln = na; A.hsp_off = hsp_off_v; A.aln_lnc = aln_lnc_v;
+    A.lnc_status = P<int>(ctx->status); A.n_surv = P<int>(ctx->n_surv) + a0; A.thr = P<double>(ctx->thr);
     A.fits = P<LncFit>(ctx->fits); A.tbl_k = P<int>(ctx->tbl_k); A.tbl_cum = P<double>(ctx->tbl_cum);
     A.bg_off = (const long long*)b.bg_off;
     A.uv_val = P<int>(ctx->uv_val); A.uv_cnt = P<int>(ctx->uv_cnt); A.uv_n = P<int>(ctx->uv_n);
     A.kde_factor = b.kde_factor; A.fitter = p.fitter; A.fdr = p.fdr; A.alpha = p.alpha;
     A.surv_x = P<double>(ctx->surv_x); A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
-    A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep);
+    A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep) + a0;
     A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
     // warp variant: alignments with <= 256 survivors; CTA variant: the rest (up to RANK_SMALL_MAX in shared
     // memory, beyond that p only + k_rank_big)
-    k_pq<32, 32, 0, 256, 128, 32, 128><<<grid_for(ctx, b.n_aln, 32), 32, 0, ctx->stream>>>(A);
+    k_pq<32, 32, 0, 256, 128, 32, 128><<<grid_for(ctx, na, 32), 32, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
     if (b.max_aln_hsps > 256) {
-        k_pq<64, 14, 256, RANK_SMALL_MAX, 256, 128, TBL_SMEM_MAX><<<grid_for(ctx, b.n_aln, 14), 64, 0, ctx->stream>>>(A);
+        k_pq<64, 14, 256, RANK_SMALL_MAX, 256, 128, TBL_SMEM_MAX><<<grid_for(ctx, na, 14), 64, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
     }
     if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
@@ -431,8 +467,8 @@ static int run_score(o2a_ctx* ctx)
         r = ensure_sort_scratch(ctx, g2, b.max_aln_hsps);
         if (r) return r;
         k_rank_big<<<g2, RANKBIG_THREADS, 0, ctx->stream>>>(
-            P<int>(ctx->big_list), P<int>(ctx->big_count), (const long long*)b.hsp_off, p.alpha, P<int>(ctx->n_surv),
-            P<int>(ctx->n_keep), P<double>(ctx->surv_p), P<double>(ctx->surv_pq), P<unsigned char>(ctx->surv_keep),
+            P<int>(ctx->big_list), P<int>(ctx->big_count), hsp_off_v, p.alpha, P<int>(ctx->n_surv) + a0,
+            P<int>(ctx->n_keep) + a0, P<double>(ctx->surv_p), P<double>(ctx->surv_pq), P<unsigned char>(ctx->surv_keep),
             P<unsigned long long>(ctx->sort_k0), P<unsigned long long>(ctx->sort_k1), P<unsigned int>(ctx->sort_v0),
             P<unsigned int>(ctx->sort_v1), b.max_aln_hsps);
         LAUNCH_CHECK();
@@ -448,33 +484,34 @@ static int run_chain(o2a_ctx* ctx)
     ENS(orient_scores, 2 * b.n_aln * sizeof(double)); ENS(chain_slot, b.n_hsp * sizeof(int));
     ENS(best_key, b.n_aln * sizeof(double)); ENS(best_aln, b.n_lnc * sizeof(long long));
     ENS(ret_coord, b.n_hsp * sizeof(int4)); ENS(ret_score, b.n_hsp * sizeof(double)); ENS(ret_slot, b.n_hsp * sizeof(int));
-    if (b.n_aln > 0) {
+    const long long l0 = ctx->vl0, nl = ctx->vl1 - ctx->vl0, a0 = ctx->va0, na = ctx->va1 - ctx->va0;
+    if (na > 0) {
         ChainArgs A{};
-        A.n_aln = b.n_aln; A.hsp_off = (const long long*)b.hsp_off; A.aln_lnc = P<int>(ctx->aln_lnc);
-        A.qlen = (const long long*)b.qlen; A.slen = (const long long*)b.slen;
+        A.n_aln = na; A.hsp_off = (const long long*)b.hsp_off + a0; A.aln_lnc = P<int>(ctx->aln_lnc) + a0;
+        A.qlen = (const long long*)b.qlen + a0; A.slen = (const long long*)b.slen + a0;
         A.qstart = b.qstart; A.qend = b.qend; A.sstart = b.sstart; A.send = b.send; A.score = b.score;
         A.coords4 = ctx->coords4;
         A.ret_coord = P<int4>(ctx->ret_coord); A.ret_score = P<double>(ctx->ret_score); A.ret_slot = P<int>(ctx->ret_slot);
-        A.n_surv = P<int>(ctx->n_surv); A.n_keep = P<int>(ctx->n_keep); A.surv_idx = P<int>(ctx->surv_idx);
+        A.n_surv = P<int>(ctx->n_surv) + a0; A.n_keep = P<int>(ctx->n_keep) + a0; A.surv_idx = P<int>(ctx->surv_idx);
         A.surv_keep = P<unsigned char>(ctx->surv_keep); A.surv_x = P<double>(ctx->surv_x);
         A.gapopen = p.gapopen; A.gapextend = p.gapextend;
         A.best_value = p.best_value;
-        A.chain_len = P<int>(ctx->chain_len); A.chain_orient = P<unsigned char>(ctx->chain_orient);
-        A.chain_score = P<double>(ctx->chain_score); A.orient_scores = P<double>(ctx->orient_scores);
-        A.chain_slot = P<int>(ctx->chain_slot); A.best_key = P<double>(ctx->best_key);
+        A.chain_len = P<int>(ctx->chain_len) + a0; A.chain_orient = P<unsigned char>(ctx->chain_orient) + a0;
+        A.chain_score = P<double>(ctx->chain_score) + a0; A.orient_scores = P<double>(ctx->orient_scores) + 2 * a0;
+        A.chain_slot = P<int>(ctx->chain_slot); A.best_key = P<double>(ctx->best_key) + a0;
         A.lnc_status = P<int>(ctx->status);
         A.mid_list = P<int>(ctx->mid_list); A.mid_count = P<int>(ctx->big_count) + 2;
         A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count) + 1;
-        k_gather_retained<<<grid_for(ctx, (b.n_aln + 7) / 8, 8), 256, 0, ctx->stream>>>(A);
+        k_gather_retained<<<grid_for(ctx, (na + 7) / 8, 8), 256, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
         {
             int r = stage_event(ctx, O2A_STAGE_CHAIN);
             if (r) return r;
         }
-        k_chain_warp<<<grid_for(ctx, (b.n_aln + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0, ctx->stream>>>(A);
+        k_chain_warp<<<grid_for(ctx, (na + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
         if (b.max_aln_hsps > CHAIN_WARP_MAX) {
-            k_chain_small<<<grid_for(ctx, b.n_aln, 8), CHAIN_THREADS, 0, ctx->stream>>>(A);
+            k_chain_small<<<grid_for(ctx, na, 8), CHAIN_THREADS, 0, ctx->stream>>>(A);
             LAUNCH_CHECK();
         }
         if (b.max_aln_hsps > CHAIN_SMALL_MAX) {
@@ -497,11 +534,12 @@ static int run_chain(o2a_ctx* ctx)
     }
     int r = stage_event(ctx, O2A_STAGE_BEST);
     if (r) return r;
-    if (b.n_lnc > 0) {
-        k_best<<<(unsigned)((b.n_lnc + 127) / 128), 128, 0, ctx->stream>>>(
-            b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->status), P<int>(ctx->n_surv), P<int>(ctx->n_keep),
+    if (nl > 0) {
+        // aln_off values are absolute alignment indices: per-alignment arrays are passed unshifted here
+        k_best<<<(unsigned)((nl + 127) / 128), 128, 0, ctx->stream>>>(
+            nl, (const long long*)b.aln_off + l0, P<int>(ctx->status) + l0, P<int>(ctx->n_surv), P<int>(ctx->n_keep),
             P<int>(ctx->chain_len), P<double>(ctx->chain_score), P<double>(ctx->orient_scores),
-            P<double>(ctx->best_key), p.best_function, P<long long>(ctx->best_aln));
+            P<double>(ctx->best_key), p.best_function, P<long long>(ctx->best_aln) + l0);
         LAUNCH_CHECK();
     }
     return 0;
@@ -537,15 +575,30 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
     b = *batch;
     int r;
     if ((r = stage_event(ctx, O2A_STAGE_H2D))) return r;
+    // Host batches large enough to amortise the extra launches are processed as a few lncRNA chunks:
+    // the bulk arrays of chunk c+1 cross PCIe on the copy stream while the kernels of chunk c (whose
+    // gather reads the coordinates of the retained HSPs in place over the same link) run.
+    std::vector<DeferredCopy> deferred_copies;
+    int n_chunks = 1;
+    long long pipeline_min_hsps = 4ll << 20;
+    if (const char* e = getenv("O2A_PIPELINE_MIN_HSPS")) pipeline_min_hsps = atoll(e);
+    if (batch->mem == O2A_MEM_HOST && batch->n_lnc >= 8 && batch->n_hsp >= pipeline_min_hsps && !getenv("O2A_NO_PIPELINE")) {
+        n_chunks = 8;
+        if (const char* e = getenv("O2A_CHUNKS")) n_chunks = atoi(e);
+        if (n_chunks < 1) n_chunks = 1;
+        if (n_chunks > 16) n_chunks = 16;
+    }
+    std::vector<DeferredCopy>* deferred = n_chunks > 1 ? &deferred_copies : nullptr;
+    ctx->pipelined_chunks = n_chunks;
     if (batch->mem == O2A_MEM_HOST) {
         // the reference pickles file names to workers which json.load them (pipeline.py:743-754);
         // here the columnar arrays cross PCIe once
         if ((r = upload(ctx, ctx->in_bg_off, batch->bg_off, (size_t)batch->n_lnc + 1, &b.bg_off))) return r;
         if (batch->bg_bits != 0 && batch->bg_bits != 16 && batch->bg_bits != 32) { ctx->err = "bg_bits must be 0, 16 or 32"; return O2A_EINVAL; }
         {
-            const unsigned char* d8 = nullptr;
+            const void* d8 = nullptr;
             const size_t esz = batch->bg_bits == 16 ? 2 : 4;
-            if ((r = upload(ctx, ctx->in_bg, (const unsigned char*)batch->bg, (size_t)batch->n_bg * esz, &d8))) return r;
+            if ((r = upload_bulk(ctx, ctx->in_bg, batch->bg, (size_t)batch->n_bg, esz, SLICE_BG, deferred, &d8))) return r;
             b.bg = (const int32_t*)d8;
         }
         if (batch->kde_factor && params->fitter == O2A_FIT_KDE) {
@@ -558,16 +611,22 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         if (batch->score_bits == 16 || batch->score_bits == 32) {
             if (!batch->score_q || !batch->exc_off) { ctx->err = "score_bits set but score_q/exc_off missing"; return O2A_EINVAL; }
             const size_t esz = batch->score_bits / 8;
-            const unsigned char* d8 = nullptr;
-            if ((r = upload(ctx, ctx->in_score_q, (const unsigned char*)batch->score_q, (size_t)batch->n_hsp * esz, &d8))) return r;
+            const void* d8 = nullptr;
+            if ((r = upload_bulk(ctx, ctx->in_score_q, batch->score_q, (size_t)batch->n_hsp, esz, SLICE_HSP, deferred, &d8))) return r;
             b.score_q = d8;
             if ((r = upload(ctx, ctx->in_exc_off, batch->exc_off, (size_t)batch->n_aln + 1, &b.exc_off))) return r;
             const size_t n_exc = batch->n_aln > 0 ? (size_t)batch->exc_off[batch->n_aln] : 0;
-            if ((r = upload(ctx, ctx->in_exc_pos, batch->exc_pos, n_exc, &b.exc_pos))) return r;
-            if ((r = upload(ctx, ctx->in_exc_val, batch->exc_val, n_exc, &b.exc_val))) return r;
+            if ((r = upload_bulk(ctx, ctx->in_exc_pos, batch->exc_pos, n_exc, sizeof(int32_t), SLICE_EXC, deferred, &d8))) return r;
+            b.exc_pos = (const int32_t*)d8;
+            if ((r = upload_bulk(ctx, ctx->in_exc_val, batch->exc_val, n_exc, sizeof(double), SLICE_EXC, deferred, &d8))) return r;
+            b.exc_val = (const double*)d8;
             b.score = nullptr;
         } else if (batch->score_bits != 0) { ctx->err = "score_bits must be 0, 16 or 32"; return O2A_EINVAL; }
-        else if ((r = upload(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, &b.score))) return r;
+        else {
+            const void* d8 = nullptr;
+            if ((r = upload_bulk(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, sizeof(double), SLICE_HSP, deferred, &d8))) return r;
+            b.score = (const double*)d8;
+        }
         // Coordinates are only ever read for the HSPs that reach the chaining (~1 %): when the caller's
         // arrays are pinned + device-mapped (o2a_host_alloc / cudaHostAlloc / cudaHostRegister) the
         // gather kernel reads them in place over PCIe instead of copying 16 B per HSP.
@@ -586,8 +645,8 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
             const void* dp = try_zero_copy ? mapped(batch->coords) : nullptr;
             if (dp) { ctx->coords4 = (const int4*)dp; ctx->coords_zero_copy = true; }
             else {
-                const int32_t* d = nullptr;
-                if ((r = upload(ctx, ctx->in_coords, batch->coords, (size_t)batch->n_hsp * 4, &d))) return r;
+                const void* d = nullptr;
+                if ((r = upload_bulk(ctx, ctx->in_coords, batch->coords, (size_t)batch->n_hsp, 16, SLICE_HSP, deferred, &d))) return r;
                 ctx->coords4 = (const int4*)d;
             }
             b.qstart = b.qend = b.sstart = b.send = nullptr;
@@ -600,10 +659,15 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
                 }
             }
             if (!ctx->coords_zero_copy) {
-                if ((r = upload(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, &b.qstart))) return r;
-                if ((r = upload(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, &b.qend))) return r;
-                if ((r = upload(ctx, ctx->in_ss, batch->sstart, (size_t)batch->n_hsp, &b.sstart))) return r;
-                if ((r = upload(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, &b.send))) return r;
+                const void* d = nullptr;
+                if ((r = upload_bulk(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, 4, SLICE_HSP, deferred, &d))) return r;
+                b.qstart = (const int32_t*)d;
+                if ((r = upload_bulk(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, 4, SLICE_HSP, deferred, &d))) return r;
+                b.qend = (const int32_t*)d;
+                if ((r = upload_bulk(ctx, ctx->in_ss, batch->sstart, (size_t)batch->n_hsp, 4, SLICE_HSP, deferred, &d))) return r;
+                b.sstart = (const int32_t*)d;
+                if ((r = upload_bulk(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, 4, SLICE_HSP, deferred, &d))) return r;
+                b.send = (const int32_t*)d;
             }
         }
         if (b.max_aln_hsps <= 0) {
@@ -627,12 +691,57 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         k_fill_aln_lnc<<<grid_for(ctx, b.n_lnc, 16), 64, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->aln_lnc));
         LAUNCH_CHECK();
     }
-    if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
-    if ((r = run_fit(ctx))) return r;
-    if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
-    if ((r = run_score(ctx))) return r;       // records O2A_STAGE_PQ itself
-    if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
-    if ((r = run_chain(ctx))) return r;       // records O2A_STAGE_CHAIN and O2A_STAGE_BEST itself
+    if (n_chunks > 1) {
+        // lncRNA boundaries that split the HSPs evenly (lncRNAs are independent units of the path)
+        long long lb[17];
+        lb[0] = 0; lb[n_chunks] = batch->n_lnc;
+        for (int c = 1; c < n_chunks; ++c) {
+            const long long target = batch->n_hsp / n_chunks * c;
+            long long lo = lb[c - 1], hi = batch->n_lnc;
+            while (lo < hi) {
+                long long mid = (lo + hi) >> 1;
+                if (batch->hsp_off[batch->aln_off[mid]] < target) lo = mid + 1; else hi = mid;
+            }
+            lb[c] = lo;
+        }
+        // the copy stream starts after everything already queued on the compute stream
+        CU(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        for (int c = 0; c < n_chunks; ++c) {
+            const long long l0 = lb[c], l1 = lb[c + 1];
+            const long long a0 = batch->aln_off[l0], a1 = batch->aln_off[l1];
+            const long long lo_of[3] = {batch->bg_off[l0], batch->hsp_off[a0], batch->exc_off ? batch->exc_off[a0] : 0};
+            const long long hi_of[3] = {batch->bg_off[l1], batch->hsp_off[a1], batch->exc_off ? batch->exc_off[a1] : 0};
+            for (const DeferredCopy& d : deferred_copies) {
+                const long long lo = lo_of[d.kind], hi = hi_of[d.kind];
+                if (hi > lo)
+                    CU(cudaMemcpyAsync(d.dst + lo * d.esz, d.src + lo * d.esz, (size_t)(hi - lo) * d.esz,
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+            CU(cudaEventRecord(ctx->copy_ev[c], ctx->copy_stream));
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[c], 0));
+            ctx->vl0 = lb[c]; ctx->vl1 = lb[c + 1];
+            ctx->va0 = batch->aln_off[lb[c]]; ctx->va1 = batch->aln_off[lb[c + 1]];
+            // stage events keep the times of the last chunk; "h2d" then spans the earlier chunks too
+            if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
+            if ((r = run_fit(ctx))) return r;
+            if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
+            if ((r = run_score(ctx))) return r;
+            if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
+            if ((r = run_chain(ctx))) return r;
+        }
+    } else {
+        ctx->vl0 = 0; ctx->vl1 = b.n_lnc; ctx->va0 = 0; ctx->va1 = b.n_aln;
+        if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
+        if ((r = run_fit(ctx))) return r;
+        if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
+        if ((r = run_score(ctx))) return r;       // records O2A_STAGE_PQ itself
+        if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
+        if ((r = run_chain(ctx))) return r;       // records O2A_STAGE_CHAIN and O2A_STAGE_BEST itself
+    }
+    ctx->vl0 = 0; ctx->vl1 = b.n_lnc; ctx->va0 = 0; ctx->va1 = b.n_aln;
     ENS(counters, 5 * 8);
     CU(cudaMemsetAsync(ctx->counters.p, 0, 5 * 8, ctx->stream));
     {
@@ -767,6 +876,7 @@ extern "C" int o2a_fitter_eval(o2a_ctx* ctx, int32_t fitter, const int32_t* bg, 
     if ((r = upload(ctx, ctx->in_kde, &kde_factor, 1, &b.kde_factor))) return r;
     ctx->prm = o2a_params{};
     ctx->prm.fitter = fitter;
+    ctx->vl0 = 0; ctx->vl1 = 1; ctx->va0 = 0; ctx->va1 = 0;
     int st = 0;
     const int nq_eff = n_q > 0 ? (int)n_q : 1;
     for (int k = 0; k < nq_eff; ++k) {
@@ -835,6 +945,7 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     }
     bool timing = ctx->timing;
     ctx->timing = false;
+    ctx->vl0 = 0; ctx->vl1 = 1; ctx->va0 = 0; ctx->va1 = 1;
     r = run_chain(ctx);
     ctx->timing = timing;
     if (r) return r;

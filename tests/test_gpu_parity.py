@@ -238,6 +238,35 @@ def test_pinned_host_inputs_use_zero_copy_coordinates(engine):
         compare_results(engine.fetch(), ref, exact_p=True, what="pinned zero-copy")
 
 
+@pytest.mark.parametrize("chunks", [2, 3, 16])
+@pytest.mark.parametrize("fitter", ["hist", "kde", "empirical"])
+def test_chunked_host_pipeline_matches_single_pass(engine, monkeypatch, chunks, fitter):
+    """Large host batches are cut into lncRNA chunks whose uploads overlap the previous chunk's kernels;
+    the result must not depend on the cut (lncRNAs are independent, pipeline.py:846-860)."""
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    kw = dict(n_lnc=40, n_bg=300, hsps_per_region=150) if fitter == "kde" else dict(n_lnc=70)
+    b = synth.workload(2, seed=41, **kw)
+    exp = O.build_batch(b, fitter, True)
+    monkeypatch.setenv("O2A_NO_PIPELINE", "1")
+    single = engine.build_batch(b, fitter, True)
+    monkeypatch.delenv("O2A_NO_PIPELINE")
+    monkeypatch.setenv("O2A_PIPELINE_MIN_HSPS", "0")
+    monkeypatch.setenv("O2A_CHUNKS", str(chunks))
+    for kwargs in (dict(), dict(aos=True), dict(aos=True, score_bits=16, bg_bits=16)):
+        got = engine.build_batch(b, fitter, True, **kwargs)
+        assert engine.lib.o2a_pipeline_chunks(engine.h) == chunks
+        compare_results(got, single, exact_p=True, what=f"chunks={chunks} {kwargs} vs single pass")
+        compare_results(got, exp, exact_p=(fitter != "kde"), what=f"chunks={chunks} {kwargs} vs oracle",
+                        m_max=float(np.diff(b.hsp_off).max()))
+    # ragged cut: first lncRNAs empty, one lncRNA holding most HSPs
+    e = synth.workload(5, n_lnc=200, seed=42)
+    monkeypatch.setenv("O2A_NO_PIPELINE", "1")
+    single = engine.build_batch(e, fitter, True)
+    monkeypatch.delenv("O2A_NO_PIPELINE")
+    compare_results(engine.build_batch(e, fitter, True), single, exact_p=True, what="ragged chunks")
+
+
 def test_pinned_result_buffers_match_fresh_arrays(engine):
     from ortho2align_b200 import synth
     b = synth.workload(2, n_lnc=20, seed=21)
