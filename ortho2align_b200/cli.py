@@ -25,6 +25,8 @@ def make_parser():
     b.add_argument("-timeout", type=int, nargs="?", default=None)
     b.add_argument("--silent", action="store_true")
     b.add_argument("-devices", type=int, nargs="*", default=None, help="CUDA device indices (default: 0)")
+    b.add_argument("-cache", type=str, nargs="?", default=None,
+                   help="columnar sidecar file: written after the first JSON parse, reused while inputs are unchanged")
     g = sub.add_parser("get_best_orthologs", help="Select one ortholog for each query gene.")
     g.set_defaults(func=get_best_orthologs)
     g.add_argument("-query_orthologs", type=str, nargs="?", required=True)

@@ -80,12 +80,17 @@ class IngestResult:
         self._lib.o2a_ingest_span(self._h, int(self.lnc_file[l]), int(b), int(e), buf, n)
         return json.loads(buf.raw[:n])
 
+    def range_text(self, a, which):
+        """Raw JSON text of the qrange / srange object of alignment `a` (bytes)."""
+        l = int(np.searchsorted(self.batch.aln_off, a, side="right") - 1)
+        b, e = (self.spans[a, 0], self.spans[a, 1]) if which == "q" else (self.spans[a, 2], self.spans[a, 3])
+        n = int(e - b)
+        buf = C.create_string_buffer(n)
+        self._lib.o2a_ingest_span(self._h, int(self.lnc_file[l]), int(b), int(e), buf, n)
+        return buf.raw[:n]
+
     def hsp_dict(self, h):
-        """HSP `h` (global index) as the reference's JSON object, with the JSON number types."""
-        b = self.batch
-        sc = float(b.score[h])
-        return {"qstart": int(b.qstart[h]), "qend": int(b.qend[h]), "sstart": int(b.sstart[h]), "send": int(b.send[h]),
-                "score": int(sc) if self.score_is_int[h] else sc}
+        return _hsp_dict(self.batch, self.score_is_int, h)
 
     def close(self):
         if self._h:
@@ -97,6 +102,115 @@ class IngestResult:
             self.close()
         except Exception:
             pass
+
+
+def _hsp_dict(b, score_is_int, h):
+    """HSP `h` (global index) as the reference's JSON object, with the JSON number types."""
+    sc = float(b.score[h])
+    return {"qstart": int(b.qstart[h]), "qend": int(b.qend[h]), "sstart": int(b.sstart[h]), "send": int(b.send[h]),
+            "score": int(sc) if score_is_int[h] else sc}
+
+
+# --------------------------------------------------------------------------------------------------
+# Columnar sidecar: the parsed batch written once next to the JSON directories (SURVEY.md §8f rank 1,
+# "optional binary sidecar written once"). One file: 16-byte preamble, a JSON directory, then the
+# arrays as raw little-endian sections aligned to 4 KiB so that they can be memory-mapped (or read
+# straight into pinned buffers) without any parsing.
+# --------------------------------------------------------------------------------------------------
+SIDECAR_MAGIC = b"O2ACOL01"
+_SIDECAR_ALIGN = 4096
+_SIDECAR_ARRAYS = ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score")
+
+
+def _manifest(align_files, bg_files):
+    """What makes a sidecar stale: the ordered file list with sizes and mtimes (missing bg files included)."""
+    def stat(p):
+        try:
+            st = os.stat(p)
+            return [st.st_size, st.st_mtime_ns]
+        except OSError:
+            return None
+    return [[os.path.basename(a), stat(a), stat(b)] for a, b in zip(align_files, bg_files)]
+
+
+def save_sidecar(path, r, align_files, bg_files):
+    """Write the IngestResult `r` (all files parsed) as a columnar sidecar; atomic via rename."""
+    b = r.batch
+    n_aln = b.n_aln
+    texts = [r.range_text(a, w) for a in range(n_aln) for w in ("q", "s")]
+    range_off = np.zeros(2 * n_aln + 1, dtype=np.int64)
+    np.cumsum([len(t) for t in texts], out=range_off[1:])
+    sections = {k: np.ascontiguousarray(getattr(b, k)) for k in _SIDECAR_ARRAYS}
+    sections["score_is_int"] = np.ascontiguousarray(r.score_is_int)
+    sections["lnc_file"] = np.ascontiguousarray(r.lnc_file)
+    sections["range_off"] = range_off
+    sections["range_text"] = np.frombuffer(b"".join(texts), dtype=np.uint8)
+    directory = {"version": 1, "n_files": len(align_files), "manifest": _manifest(align_files, bg_files), "sections": {}}
+    # two passes: the directory's own length decides where the first section starts
+    def layout(base):
+        off = base
+        for k, arr in sections.items():
+            off = (off + _SIDECAR_ALIGN - 1) // _SIDECAR_ALIGN * _SIDECAR_ALIGN
+            directory["sections"][k] = {"dtype": arr.dtype.str, "shape": list(arr.shape), "offset": off}
+            off += arr.nbytes
+        return off
+    layout(1 << 40)                                            # widest offsets -> upper bound of the JSON length
+    head_len = len(json.dumps(directory).encode()) + 64
+    layout(16 + head_len)
+    head = json.dumps(directory).encode().ljust(head_len, b" ")
+    tmp = f"{path}.tmp{os.getpid()}"
+    with open(tmp, "wb") as f:
+        f.write(SIDECAR_MAGIC + np.int64(head_len).tobytes())
+        f.write(head)
+        for k, arr in sections.items():
+            f.seek(directory["sections"][k]["offset"])
+            arr.tofile(f)
+    os.replace(tmp, path)
+
+
+class SidecarResult:
+    """A sidecar opened for reading: same surface as IngestResult (batch, lnc_file, file_status, errors,
+    score_is_int, range_dict, hsp_dict), arrays memory-mapped from the file."""
+
+    def __init__(self, path, directory):
+        sec = directory["sections"]
+        def arr(k):
+            d = sec[k]
+            n = int(np.prod(d["shape"])) if d["shape"] else 1
+            if n == 0:
+                return np.zeros(d["shape"], dtype=np.dtype(d["dtype"]))
+            return np.memmap(path, dtype=np.dtype(d["dtype"]), mode="r", offset=d["offset"], shape=tuple(d["shape"]))
+        self.batch = ColumnarBatch(*[arr(k) for k in _SIDECAR_ARRAYS])
+        self.score_is_int = arr("score_is_int")
+        self.lnc_file = arr("lnc_file")
+        self._range_off, self._range_text = arr("range_off"), arr("range_text")
+        self.file_status = np.zeros(directory["n_files"], dtype=np.int32)
+        self.errors = {}
+
+    def range_dict(self, a, which):
+        k = 2 * a + (0 if which == "q" else 1)
+        return json.loads(bytes(self._range_text[self._range_off[k]:self._range_off[k + 1]]))
+
+    def hsp_dict(self, h):
+        return _hsp_dict(self.batch, self.score_is_int, h)
+
+    def close(self):
+        pass
+
+
+def open_sidecar(path, align_files, bg_files):
+    """SidecarResult if `path` holds a sidecar written for exactly these files (names, sizes, mtimes), else None."""
+    try:
+        with open(path, "rb") as f:
+            pre = f.read(16)
+            if len(pre) != 16 or pre[:8] != SIDECAR_MAGIC:
+                return None
+            directory = json.loads(f.read(int(np.frombuffer(pre[8:], dtype=np.int64)[0])))
+    except (OSError, ValueError):
+        return None
+    if directory.get("version") != 1 or directory.get("manifest") != _manifest(align_files, bg_files):
+        return None
+    return SidecarResult(path, directory)
 
 
 def load_files(align_files, bg_files, threads=0) -> IngestResult:

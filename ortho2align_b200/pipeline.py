@@ -84,9 +84,13 @@ def _ingest_json(alignments_files, bg_files):
     return out
 
 
-def _ingest_native(alignments_files, bg_files, threads):
+def _ingest_native(alignments_files, bg_files, threads, cache=None):
     from . import ingest as native
-    r = native.load_files(alignments_files, bg_files, threads=threads or 1)
+    r = native.open_sidecar(cache, alignments_files, bg_files) if cache else None
+    if r is None:
+        r = native.load_files(alignments_files, bg_files, threads=threads or 1)
+        if cache and not r.file_status.any():
+            native.save_sidecar(cache, r, alignments_files, bg_files)
     out = [None] * len(alignments_files)
     for i in np.nonzero(r.file_status)[0]:
         if r.file_status[i] == 1:
@@ -135,7 +139,7 @@ def _run_shards(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
 
 def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gapopen=5, gapextend=2,
                     fdr=False, cores=1, timeout=None, silent=False, stats_filename=None, devices=None,
-                    ingest="native"):
+                    ingest="native", cache=None):
     """A build_orthologs step of the pipeline (signature of `pipeline.py:801-812`).
 
     `cores` = threads of the native JSON ingest (the per-lncRNA process pool it configured in the
@@ -143,7 +147,9 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     device indices (default: [0]); with several, lncRNAs are LPT-sharded by HSP count and every
     GPU runs its shard independently. `ingest`: 'native' (libo2a_ingest.so, C++) or 'json'
     (json.load + Python packer; same results, used to cross-check the native reader).
-    `fitting`: 'hist' | 'kde' (reference) or 'empirical' (extension).
+    `fitting`: 'hist' | 'kde' (reference) or 'empirical' (extension). `cache`: path of a columnar
+    sidecar (ingest.save_sidecar): written after the first native parse of these directories, and read
+    back instead of the JSON on later runs as long as file names, sizes and mtimes are unchanged.
     """
     alignments_dir = Path(alignments)
     background_dir = Path(background)
@@ -159,7 +165,7 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
 
     # ---- ingest -------------------------------------------------------------------------------
     # per file: an ExceptionLogger, or (single-lncRNA batch, n_alignments, accessors)
-    loaded = _ingest_native(alignments_files, bg_files, cores) if ingest == "native" \
+    loaded = _ingest_native(alignments_files, bg_files, cores, cache) if ingest == "native" \
         else _ingest_json(alignments_files, bg_files)
     ok_idx = [i for i, x in enumerate(loaded) if not isinstance(x, ExceptionLogger)]
 

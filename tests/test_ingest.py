@@ -87,3 +87,32 @@ def test_native_ingest_on_the_reference_golden_inputs(tmp_path):
     af, bf = _write_dirs(tmp_path, items, missing={g["missing_bg"]})
     r = ingest.load_files(af, bf)
     _same(r.batch, _python_batch(af, bf))
+
+
+def test_sidecar_round_trip(tmp_path):
+    """The columnar sidecar holds exactly what the native parse produced, range texts included."""
+    from ortho2align_b200 import ingest, synth
+    b, m = synth.workload(1, n_lnc=9, with_meta=True, hsps_per_region=80, n_bg=100, seed=8)
+    items = synth.to_json_dicts(b, m)
+    items[3] = (items[3][0], items[3][1], [])
+    af, bf = _write_dirs(tmp_path, items, missing={items[1][0]})
+    r = ingest.load_files(af, bf, threads=2)
+    path = str(tmp_path / "c.o2ac")
+    ingest.save_sidecar(path, r, af, bf)
+    s = ingest.open_sidecar(path, af, bf)
+    assert s is not None
+    _same(s.batch, r.batch)
+    assert np.array_equal(s.lnc_file, r.lnc_file) and np.array_equal(s.score_is_int, r.score_is_int)
+    for a in range(r.batch.n_aln):
+        assert s.range_dict(a, "q") == r.range_dict(a, "q") and s.range_dict(a, "s") == r.range_dict(a, "s")
+    for h in range(0, r.batch.n_hsp, 37):
+        assert s.hsp_dict(h) == r.hsp_dict(h) and type(s.hsp_dict(h)["score"]) is type(r.hsp_dict(h)["score"])
+    # stale: different order, a rewritten file, a background that appeared, garbage in the file
+    assert ingest.open_sidecar(path, af[::-1], bf[::-1]) is None
+    assert ingest.open_sidecar(str(tmp_path / "missing.o2ac"), af, bf) is None
+    with open(bf[1], "w") as f:
+        f.write("[3, 4, 5]")
+    assert ingest.open_sidecar(path, af, bf) is None
+    with open(path, "r+b") as f:
+        f.write(b"garbage!")
+    assert ingest.open_sidecar(path, af, bf) is None

@@ -25,15 +25,15 @@ def _oracle_runner(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
     return [O.build_batch(b, fitter, fdr, alpha, gapopen, gapextend) for b in batches]
 
 
-def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest="native"):
+def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest="native", cache=None, dirs=None):
     from ortho2align_b200 import pipeline
-    ad, bd = _materialise(tmp_path, g)
+    ad, bd = dirs or _materialise(tmp_path, g)
     real_listdir = os.listdir
     monkeypatch.setattr(os, "listdir", lambda p: list(g["listdir_order"]) if str(p) == ad else real_listdir(p))
     od = str(tmp_path / f"out_{key}")
     stats = str(tmp_path / f"{key}.stats.txt")
     pipeline.build_orthologs(ad, bd, fitting, od, threshold=0.05, gapopen=5, gapextend=2, fdr=fdr, cores=1,
-                             timeout=None, silent=True, stats_filename=stats, ingest=ingest)
+                             timeout=None, silent=True, stats_filename=stats, ingest=ingest, cache=cache)
     j = lambda n: os.path.join(od, n)
     pipeline.get_best_orthologs(j("significant.query_orthologs.bed"), j("significant.query_orthologs.tsv"),
                                 j("significant.subject_orthologs.bed"), j("significant.subject_orthologs.tsv"),
@@ -63,6 +63,32 @@ def test_host_logic_with_oracle_injected(tmp_path, monkeypatch, key, fitting, fd
     from ortho2align_b200 import pipeline
     monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
     _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), key, fitting, fdr, exact, ingest=ingest)
+
+
+def test_columnar_sidecar_replaces_the_json_parse(tmp_path, monkeypatch):
+    """First run parses the JSON and writes the sidecar; the second reads only the sidecar; a touched input
+    makes it stale. Output files are the reference's in all three runs."""
+    from ortho2align_b200 import ingest, pipeline
+    monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
+    g = load_golden("e2e.json")
+    dirs = _materialise(tmp_path, g)
+    cache = str(tmp_path / "columnar.o2ac")
+    calls = []
+    real = ingest.load_files
+    monkeypatch.setattr(ingest, "load_files", lambda *a, **k: calls.append(1) or real(*a, **k))
+    _run_and_compare(tmp_path, monkeypatch, g, "hist_1", "hist", True, True, cache=cache, dirs=dirs)
+    assert os.path.exists(cache) and len(calls) == 1
+    for sub in ("out_hist_1", "hist_1.stats.txt"):
+        os.rename(tmp_path / sub, tmp_path / (sub + ".first"))
+    _run_and_compare(tmp_path, monkeypatch, g, "hist_1", "hist", True, True, cache=cache, dirs=dirs)
+    assert len(calls) == 1                                        # no JSON was parsed
+    for sub in ("out_hist_1", "hist_1.stats.txt"):
+        os.rename(tmp_path / sub, tmp_path / (sub + ".second"))
+    first = sorted(os.listdir(dirs[0]))[0]
+    st = os.stat(os.path.join(dirs[0], first))
+    os.utime(os.path.join(dirs[0], first), ns=(st.st_atime_ns, st.st_mtime_ns + 10 ** 9))
+    _run_and_compare(tmp_path, monkeypatch, g, "hist_1", "hist", True, True, cache=cache, dirs=dirs)
+    assert len(calls) == 2                                        # stale -> parsed again and rewritten
 
 
 @pytest.mark.gpu
