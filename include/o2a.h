@@ -188,6 +188,54 @@ int  o2a_pipeline_chunks(const o2a_ctx *ctx);
 int  o2a_set_timing(o2a_ctx *ctx, int enabled);
 int  o2a_get_stage_ms(o2a_ctx *ctx, float *ms /*O2A_STAGE_COUNT*/);
 
+/* ---------------------------------------------------------------------------------------------
+ * Producer side of the alignment JSON: what `_align_syntenies`
+ * (pipeline.py:525-532) applies to the HSPs of every BLAST table between `from_file_blast` and
+ * `to_dict`, for a whole batch of alignments in one call:
+ *     alignment.to_genomic()                                    genomicranges.py:1108-1129
+ *     alignment.cut_coordinates(qleft, qright, sleft, sright)   alignment.py:734-803, 267-333;
+ *                                                               genomicranges.py:1153-1158
+ *     qlen / slen of the new alignment                          alignment.py:477-487
+ * Input coordinates are what `from_file_blast` leaves (0-based, half-open, sequence-relative;
+ * alignment.py:574-581). The result stays on the device in the layout o2a_build_batch takes
+ * (o2a_cut_view) and can be fetched (o2a_fetch_cut). Kept HSPs keep their order.
+ * ------------------------------------------------------------------------------------------- */
+#define O2A_NO_BOUND INT64_MIN             /* a boundary that is None */
+#define O2A_CUT_STATUS_RANGE 1             /* a kept coordinate does not fit int32 */
+#define O2A_CUT_STATUS_INEXACT 2           /* an intermediate product beyond 2^53 (Python's exact ints would differ) */
+
+typedef struct o2a_cut_input {
+    int64_t n_aln, n_hsp;
+    const int64_t *hsp_off;                       /* [n_aln+1] */
+    const int32_t *qstart, *qend, *sstart, *send; /* [n_hsp] */
+    const double  *score;                         /* [n_hsp] */
+    const uint8_t *score_is_int;                  /* [n_hsp] optional: 0 = the table held a non-integral score (a Python
+                                                     float before any cut); NULL = all ints. Only carried to `cut` */
+    /* per alignment [n_aln]: query range (the flanked neighbourhood) and subject range (the syntenic
+     * window): start, end, strand == '-' (genomicranges.py:1112, 1121) */
+    const int64_t *q_start, *q_end;
+    const int8_t  *q_minus;
+    const int64_t *s_start, *s_end;
+    const int8_t  *s_minus;
+    const uint8_t *relative;                      /* [n_aln] 0 = to_genomic is a no-op (:1109-1110); NULL = all 1 */
+    const int64_t *qleft, *qright, *sleft, *sright; /* [n_aln] each; NULL array or O2A_NO_BOUND entry = None */
+    int32_t mem;                                  /* O2A_MEM_HOST | O2A_MEM_DEVICE, applies to every pointer */
+    int32_t reserved;
+} o2a_cut_input;
+
+int o2a_cut_batch(o2a_ctx *ctx, const o2a_cut_input *in, int64_t *n_kept);
+/* any pointer may be NULL. hsp_off[n_aln+1]; per kept HSP: coordinates, score, cut (bit 0 = the score was
+ * scaled by a cut, bit 1 = it was a float already: the reference's JSON number is an int iff cut == 0);
+ * per alignment: qlen, slen, status */
+int o2a_fetch_cut(o2a_ctx *ctx, int64_t *hsp_off, int32_t *qstart, int32_t *qend, int32_t *sstart, int32_t *send,
+                  double *score, uint8_t *cut, int64_t *qlen, int64_t *slen, int32_t *status);
+/* device pointers of the last cut in `out` (n_aln, n_hsp, hsp_off, qlen, slen, qstart..send, score,
+ * mem = O2A_MEM_DEVICE; everything else zero): add aln_off / bg (device) and hand it to o2a_build_batch.
+ * Valid until the next o2a_cut_batch on this ctx. */
+int o2a_cut_view(o2a_ctx *ctx, o2a_batch *out);
+/* CUDA-event durations (ms) of the last o2a_cut_batch when timing is enabled: h2d, count pass, scan, write pass */
+int o2a_get_cut_ms(o2a_ctx *ctx, float *ms /*4*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,14 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libo2a_oracle.so")
 SRC = os.path.join(HERE, "o2a_oracle.c")
+SRCS = [SRC, os.path.join(HERE, "o2a_oracle_producer.c")]
 
 
 def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(s) for s in SRCS):
         return LIB
     cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-fno-fast-math",
-           "-Wall", "-Wno-unused-function", "-o", LIB, SRC, "-lm"]
+           "-Wall", "-Wno-unused-function", "-o", LIB] + SRCS + ["-lm"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libo2a_cuda.so")
 EXPORTS = ["o2a_abi_version", "o2a_create", "o2a_destroy", "o2a_last_error", "o2a_set_stream",
            "o2a_host_alloc", "o2a_host_free", "o2a_build_batch", "o2a_fetch_lnc", "o2a_fetch_aln",
            "o2a_fetch_survivors", "o2a_fetch_chains", "o2a_fitter_eval", "o2a_best_chain",
-           "o2a_launch_count", "o2a_coords_zero_copy", "o2a_pipeline_chunks", "o2a_set_timing", "o2a_get_stage_ms"]
+           "o2a_launch_count", "o2a_coords_zero_copy", "o2a_pipeline_chunks", "o2a_set_timing", "o2a_get_stage_ms",
+           "o2a_cut_batch", "o2a_fetch_cut", "o2a_cut_view", "o2a_get_cut_ms"]
 
 STAGES = ["h2d", "fit", "filter", "pq", "gather", "chain", "best"]
 
@@ -24,6 +25,15 @@ class O2ABatch(C.Structure):
                 ("max_aln_hsps", C.c_int64), ("max_lnc_bg", C.c_int64), ("coords", C.c_void_p),
                 ("score_bits", C.c_int32), ("bg_bits", C.c_int32), ("score_q", C.c_void_p),
                 ("exc_off", C.c_void_p), ("exc_pos", C.c_void_p), ("exc_val", C.c_void_p)]
+
+
+class O2ACutInput(C.Structure):
+    _fields_ = [("n_aln", C.c_int64), ("n_hsp", C.c_int64), ("hsp_off", C.c_void_p),
+                ("qstart", C.c_void_p), ("qend", C.c_void_p), ("sstart", C.c_void_p), ("send", C.c_void_p),
+                ("score", C.c_void_p), ("score_is_int", C.c_void_p), ("q_start", C.c_void_p), ("q_end", C.c_void_p), ("q_minus", C.c_void_p),
+                ("s_start", C.c_void_p), ("s_end", C.c_void_p), ("s_minus", C.c_void_p), ("relative", C.c_void_p),
+                ("qleft", C.c_void_p), ("qright", C.c_void_p), ("sleft", C.c_void_p), ("sright", C.c_void_p),
+                ("mem", C.c_int32), ("reserved", C.c_int32)]
 
 
 class O2AParams(C.Structure):
@@ -92,6 +102,14 @@ def load():
     lib.o2a_set_timing.argtypes = [P, C.c_int]
     lib.o2a_get_stage_ms.restype = C.c_int
     lib.o2a_get_stage_ms.argtypes = [P, P]
+    lib.o2a_cut_batch.restype = C.c_int
+    lib.o2a_cut_batch.argtypes = [P, C.POINTER(O2ACutInput), C.POINTER(i64)]
+    lib.o2a_fetch_cut.restype = C.c_int
+    lib.o2a_fetch_cut.argtypes = [P] + [P] * 10
+    lib.o2a_cut_view.restype = C.c_int
+    lib.o2a_cut_view.argtypes = [P, C.POINTER(O2ABatch)]
+    lib.o2a_get_cut_ms.restype = C.c_int
+    lib.o2a_get_cut_ms.argtypes = [P, P]
     if lib.o2a_abi_version() != 1:
         raise LibraryMissing("libo2a_cuda.so ABI version mismatch; rebuild")
     _lib = lib

@@ -8,6 +8,7 @@
 
 #include "../../include/o2a.h"
 #include "o2a_chain.cuh"
+#include "o2a_cut.cuh"
 #include "o2a_device.cuh"
 #include "o2a_fit.cuh"
 #include "o2a_score.cuh"
@@ -62,6 +63,14 @@ struct o2a_ctx {
     DevBuf sort_k0, sort_k1, sort_v0, sort_v1;
     DevBuf cb_qs, cb_qe, cb_ss, cb_se, cb_sc, cb_id, cb_total, cb_prev, cb_f, cb_chain;
     DevBuf off_a, off_b, out_i32, out_f64a, out_f64b, out_u8, maxred;
+    // producer side (o2a_cut_batch)
+    DevBuf ci_isint, ci_qstart, ci_qend, ci_sstart, ci_send, ci_qminus, ci_sminus, ci_rel, ci_ql, ci_qr, ci_sl, ci_sr;
+    DevBuf ct_n, ct_off, ct_aln, ct_cnt, ct_out, ct_sums, ct_maxq, ct_maxs;
+    DevBuf co_off, co_qs, co_qe, co_ss, co_se, co_score, co_cut, co_qlen, co_slen, co_status;
+    bool have_cut = false;
+    long long cut_n_aln = 0, cut_n_kept = 0;
+    cudaEvent_t cut_ev[5] = {};
+    bool cut_ev_valid = false;
 };
 
 #define CU(call)                                                                                  \
@@ -234,6 +243,7 @@ extern "C" int o2a_create(o2a_ctx** out, int device)
     for (int i = 0; i < N_EVENTS; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->cut_ev[i]);
     *out = ctx;
     return 0;
 }
@@ -252,7 +262,12 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->fit_list_n, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
                       &ctx->cb_qe, &ctx->cb_ss, &ctx->cb_se, &ctx->cb_sc, &ctx->cb_id, &ctx->cb_total, &ctx->cb_prev,
                       &ctx->cb_f, &ctx->cb_chain, &ctx->off_a, &ctx->off_b, &ctx->out_i32, &ctx->out_f64a,
-                      &ctx->out_f64b, &ctx->out_u8, &ctx->maxred};
+                      &ctx->out_f64b, &ctx->out_u8, &ctx->maxred,
+                      &ctx->ci_isint, &ctx->ci_qstart, &ctx->ci_qend, &ctx->ci_sstart, &ctx->ci_send, &ctx->ci_qminus, &ctx->ci_sminus,
+                      &ctx->ci_rel, &ctx->ci_ql, &ctx->ci_qr, &ctx->ci_sl, &ctx->ci_sr, &ctx->ct_n, &ctx->ct_off,
+                      &ctx->ct_aln, &ctx->ct_cnt, &ctx->ct_out, &ctx->ct_sums, &ctx->ct_maxq, &ctx->ct_maxs,
+                      &ctx->co_off, &ctx->co_qs, &ctx->co_qe, &ctx->co_ss, &ctx->co_se, &ctx->co_score, &ctx->co_cut,
+                      &ctx->co_qlen, &ctx->co_slen, &ctx->co_status};
     for (DevBuf* b : bufs) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }
 
@@ -264,6 +279,7 @@ extern "C" void o2a_destroy(o2a_ctx* ctx)
     free_all(ctx);
     for (int i = 0; i < N_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+    for (int i = 0; i < 5; ++i) if (ctx->cut_ev[i]) cudaEventDestroy(ctx->cut_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -966,5 +982,160 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     if (chain_score) *chain_score = cs;
     if (orient_scores) { orient_scores[0] = os2[0]; orient_scores[1] = os2[1]; }
     if (status) *status = st;
+    return 0;
+}
+
+
+// --------------------------------------------------------------------------------------------
+// producer side: to_genomic + cut_coordinates over a batch of alignments (o2a_cut.cuh)
+// --------------------------------------------------------------------------------------------
+extern "C" int o2a_cut_batch(o2a_ctx* ctx, const o2a_cut_input* in, int64_t* n_kept)
+{
+    if (!ctx) return O2A_EINVAL;
+    if (!in) { ctx->err = "null input"; return O2A_EINVAL; }
+    if (in->n_aln < 0 || in->n_hsp < 0) { ctx->err = "negative size"; return O2A_EINVAL; }
+    if (in->n_aln > 0 && (!in->hsp_off || !in->q_start || !in->q_end || !in->q_minus || !in->s_start || !in->s_end || !in->s_minus)) {
+        ctx->err = "hsp_off and the six per-alignment range arrays are required"; return O2A_EINVAL;
+    }
+    if (in->n_hsp > 0 && (!in->qstart || !in->qend || !in->sstart || !in->send || !in->score)) {
+        ctx->err = "null HSP array"; return O2A_EINVAL;
+    }
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_cut = false;
+    ctx->cut_ev_valid = false;
+    const long long n_aln = in->n_aln, n_hsp = in->n_hsp;
+    int r;
+    if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[0], ctx->stream));
+    CutArgs A{};
+    A.n_aln = n_aln;
+    if (in->mem == O2A_MEM_HOST) {
+        const int64_t* p64 = nullptr; const int32_t* p32 = nullptr; const double* pd = nullptr;
+        const int8_t* p8 = nullptr; const uint8_t* pu8 = nullptr;
+        if ((r = upload(ctx, ctx->in_hsp_off, in->hsp_off, (size_t)n_aln + 1, &p64))) return r;
+        A.hsp_off = (const long long*)p64;
+        if ((r = upload(ctx, ctx->in_qs, in->qstart, (size_t)n_hsp, &p32))) return r; A.qs = p32;
+        if ((r = upload(ctx, ctx->in_qe, in->qend, (size_t)n_hsp, &p32))) return r; A.qe = p32;
+        if ((r = upload(ctx, ctx->in_ss, in->sstart, (size_t)n_hsp, &p32))) return r; A.ss = p32;
+        if ((r = upload(ctx, ctx->in_se, in->send, (size_t)n_hsp, &p32))) return r; A.se = p32;
+        if ((r = upload(ctx, ctx->in_score, in->score, (size_t)n_hsp, &pd))) return r; A.score = pd;
+        if (in->score_is_int) { if ((r = upload(ctx, ctx->ci_isint, in->score_is_int, (size_t)n_hsp, &pu8))) return r; A.is_int = pu8; }
+        if ((r = upload(ctx, ctx->ci_qstart, in->q_start, (size_t)n_aln, &p64))) return r; A.q_start = (const long long*)p64;
+        if ((r = upload(ctx, ctx->ci_qend, in->q_end, (size_t)n_aln, &p64))) return r; A.q_end = (const long long*)p64;
+        if ((r = upload(ctx, ctx->ci_sstart, in->s_start, (size_t)n_aln, &p64))) return r; A.s_start = (const long long*)p64;
+        if ((r = upload(ctx, ctx->ci_send, in->s_end, (size_t)n_aln, &p64))) return r; A.s_end = (const long long*)p64;
+        if ((r = upload(ctx, ctx->ci_qminus, in->q_minus, (size_t)n_aln, &p8))) return r; A.q_minus = (const signed char*)p8;
+        if ((r = upload(ctx, ctx->ci_sminus, in->s_minus, (size_t)n_aln, &p8))) return r; A.s_minus = (const signed char*)p8;
+        if (in->relative) { if ((r = upload(ctx, ctx->ci_rel, in->relative, (size_t)n_aln, &pu8))) return r; A.relative = pu8; }
+        if (in->qleft) { if ((r = upload(ctx, ctx->ci_ql, in->qleft, (size_t)n_aln, &p64))) return r; A.qleft = (const long long*)p64; }
+        if (in->qright) { if ((r = upload(ctx, ctx->ci_qr, in->qright, (size_t)n_aln, &p64))) return r; A.qright = (const long long*)p64; }
+        if (in->sleft) { if ((r = upload(ctx, ctx->ci_sl, in->sleft, (size_t)n_aln, &p64))) return r; A.sleft = (const long long*)p64; }
+        if (in->sright) { if ((r = upload(ctx, ctx->ci_sr, in->sright, (size_t)n_aln, &p64))) return r; A.sright = (const long long*)p64; }
+    } else {
+        A.hsp_off = (const long long*)in->hsp_off;
+        A.qs = in->qstart; A.qe = in->qend; A.ss = in->sstart; A.se = in->send; A.score = in->score;
+        A.is_int = in->score_is_int;
+        A.q_start = (const long long*)in->q_start; A.q_end = (const long long*)in->q_end;
+        A.s_start = (const long long*)in->s_start; A.s_end = (const long long*)in->s_end;
+        A.q_minus = (const signed char*)in->q_minus; A.s_minus = (const signed char*)in->s_minus;
+        A.relative = in->relative;
+        A.qleft = (const long long*)in->qleft; A.qright = (const long long*)in->qright;
+        A.sleft = (const long long*)in->sleft; A.sright = (const long long*)in->sright;
+    }
+    if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[1], ctx->stream));
+    // tile table: ceil(n/CUT_TILE) tiles per alignment, at most n_hsp/CUT_TILE + n_aln in total
+    const long long max_tiles = n_hsp / CUT_TILE + n_aln;
+    const long long max_chunks = (max_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1;
+    ENS(ct_n, (n_aln + 1) * sizeof(int)); ENS(ct_off, (n_aln + 1) * 8); ENS(ct_aln, (max_tiles + 1) * sizeof(int));
+    ENS(ct_cnt, (max_tiles + 1) * sizeof(int)); ENS(ct_out, (max_tiles + 2) * 8); ENS(ct_sums, (max_chunks + 1) * 8);
+    ENS(ct_maxq, (n_aln + 1) * sizeof(int)); ENS(ct_maxs, (n_aln + 1) * sizeof(int));
+    ENS(co_off, (n_aln + 1) * 8); ENS(co_qlen, (n_aln + 1) * 8); ENS(co_slen, (n_aln + 1) * 8); ENS(co_status, (n_aln + 1) * sizeof(int));
+    ENS(co_qs, n_hsp * 4); ENS(co_qe, n_hsp * 4); ENS(co_ss, n_hsp * 4); ENS(co_se, n_hsp * 4);
+    ENS(co_score, n_hsp * 8); ENS(co_cut, n_hsp);
+    A.tile_off = P<long long>(ctx->ct_off); A.tile_aln = P<int>(ctx->ct_aln); A.tile_cnt = P<int>(ctx->ct_cnt);
+    A.tile_out = P<long long>(ctx->ct_out);
+    A.oqs = P<int>(ctx->co_qs); A.oqe = P<int>(ctx->co_qe); A.oss = P<int>(ctx->co_ss); A.ose = P<int>(ctx->co_se);
+    A.oscore = P<double>(ctx->co_score); A.ocut = P<unsigned char>(ctx->co_cut);
+    A.max_q = P<int>(ctx->ct_maxq); A.max_s = P<int>(ctx->ct_maxs); A.status = P<int>(ctx->co_status);
+    A.out_off = P<long long>(ctx->co_off); A.qlen = P<long long>(ctx->co_qlen); A.slen = P<long long>(ctx->co_slen);
+    if (n_aln > 0) {
+        k_cut_tiles_per_aln<<<grid_for(ctx, (n_aln + 255) / 256, 4), 256, 0, ctx->stream>>>(n_aln, A.hsp_off, P<int>(ctx->ct_n));
+        LAUNCH_CHECK();
+    }
+    k_scan_offsets<<<1, 1024, 0, ctx->stream>>>(n_aln, P<int>(ctx->ct_n), P<long long>(ctx->ct_off));
+    LAUNCH_CHECK();
+    if (n_aln > 0) {
+        k_cut_fill_tile_aln<<<grid_for(ctx, n_aln, 16), 64, 0, ctx->stream>>>(n_aln, A.tile_off, P<int>(ctx->ct_aln), A.max_q, A.max_s, A.status);
+        LAUNCH_CHECK();
+    }
+    const int tile_grid = grid_for(ctx, (max_tiles + CUT_WARPS - 1) / CUT_WARPS, 8);
+    k_cut<false><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
+    if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[2], ctx->stream));
+    // tile bases: exclusive scan of the per-tile counts (n_tiles = tile_off[n_aln] lives on the device)
+    const long long* n_tiles_ptr = A.tile_off + n_aln;
+    const int scan_grid = grid_for(ctx, max_chunks, 8);
+    k_scan_chunk_sums<<<scan_grid, 256, 0, ctx->stream>>>(n_tiles_ptr, A.tile_cnt, P<long long>(ctx->ct_sums));
+    LAUNCH_CHECK();
+    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(n_tiles_ptr, P<long long>(ctx->ct_sums));
+    LAUNCH_CHECK();
+    k_scan_chunks<<<scan_grid, 256, 0, ctx->stream>>>(n_tiles_ptr, A.tile_cnt, P<long long>(ctx->ct_sums), P<long long>(ctx->ct_out));
+    LAUNCH_CHECK();
+    if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[3], ctx->stream));
+    k_cut<true><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
+    k_cut_finish<<<grid_for(ctx, (n_aln + 256) / 256, 4), 256, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
+    if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[4], ctx->stream));
+    long long kept = 0;
+    CU(cudaMemcpyAsync(&kept, P<long long>(ctx->co_off) + n_aln, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cut_n_aln = n_aln; ctx->cut_n_kept = kept;
+    ctx->have_cut = true;
+    ctx->cut_ev_valid = ctx->timing;
+    if (n_kept) *n_kept = kept;
+    return 0;
+}
+
+#define NEED_CUT() do { if (!ctx) return O2A_EINVAL; if (!ctx->have_cut) { ctx->err = "no result: call o2a_cut_batch first"; return O2A_ESTATE; } CU(cudaSetDevice(ctx->device)); } while (0)
+
+extern "C" int o2a_fetch_cut(o2a_ctx* ctx, int64_t* hsp_off, int32_t* qstart, int32_t* qend, int32_t* sstart, int32_t* send,
+                             double* score, uint8_t* cut, int64_t* qlen, int64_t* slen, int32_t* status)
+{
+    NEED_CUT();
+    int r;
+    const size_t na = (size_t)ctx->cut_n_aln, nk = (size_t)ctx->cut_n_kept;
+    if ((r = download(ctx, hsp_off, ctx->co_off.p, na + 1))) return r;
+    if ((r = download(ctx, qstart, ctx->co_qs.p, nk))) return r;
+    if ((r = download(ctx, qend, ctx->co_qe.p, nk))) return r;
+    if ((r = download(ctx, sstart, ctx->co_ss.p, nk))) return r;
+    if ((r = download(ctx, send, ctx->co_se.p, nk))) return r;
+    if ((r = download(ctx, score, ctx->co_score.p, nk))) return r;
+    if ((r = download(ctx, cut, ctx->co_cut.p, nk))) return r;
+    if ((r = download(ctx, qlen, ctx->co_qlen.p, na))) return r;
+    if ((r = download(ctx, slen, ctx->co_slen.p, na))) return r;
+    if ((r = download(ctx, status, ctx->co_status.p, na))) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int o2a_cut_view(o2a_ctx* ctx, o2a_batch* out)
+{
+    NEED_CUT();
+    if (!out) { ctx->err = "null out"; return O2A_EINVAL; }
+    memset(out, 0, sizeof(*out));
+    out->n_aln = ctx->cut_n_aln; out->n_hsp = ctx->cut_n_kept;
+    out->hsp_off = P<int64_t>(ctx->co_off); out->qlen = P<int64_t>(ctx->co_qlen); out->slen = P<int64_t>(ctx->co_slen);
+    out->qstart = P<int32_t>(ctx->co_qs); out->qend = P<int32_t>(ctx->co_qe);
+    out->sstart = P<int32_t>(ctx->co_ss); out->send = P<int32_t>(ctx->co_se);
+    out->score = P<double>(ctx->co_score);
+    out->mem = O2A_MEM_DEVICE;
+    return 0;
+}
+
+extern "C" int o2a_get_cut_ms(o2a_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return O2A_EINVAL;
+    if (!ctx->cut_ev_valid) { ctx->err = "no timed o2a_cut_batch yet (o2a_set_timing)"; return O2A_ESTATE; }
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms[i], ctx->cut_ev[i], ctx->cut_ev[i + 1]));
     return 0;
 }

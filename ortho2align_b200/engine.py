@@ -223,6 +223,78 @@ class Engine:
         self.run(s, p)
         return self.fetch(survivors=survivors)
 
+    # ---- producer side: to_genomic + cut_coordinates over a batch -----------------
+    CUT_STAGES = ["h2d", "count", "scan", "write"]
+
+    @staticmethod
+    def cut_struct(rel, ranges, device=False):
+        """o2a_cut_input over numpy arrays (host) or torch CUDA tensors (device=True). `rel`: hsp_off,
+        qstart, qend, sstart, send, score; `ranges`: q_start, q_end, q_minus, s_start, s_end, s_minus and
+        optionally relative, qleft, qright, sleft, sright (per alignment; NO_BOUND entries = None)."""
+        from ._lib import O2ACutInput
+        s = O2ACutInput()
+        keep = []
+
+        def ptr(v, dtype):
+            if v is None:
+                return None
+            if device:
+                assert v.is_cuda and v.is_contiguous() and str(v.dtype).endswith(np.dtype(dtype).name), (v.dtype, dtype)
+                keep.append(v)
+                return v.data_ptr()
+            a = np.ascontiguousarray(v, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data
+
+        n_aln = len(rel["hsp_off"]) - 1
+        s.n_aln, s.n_hsp = n_aln, len(rel["score"])
+        s.hsp_off = ptr(rel["hsp_off"], np.int64)
+        for k in ("qstart", "qend", "sstart", "send"):
+            setattr(s, k, ptr(rel[k], np.int32))
+        s.score = ptr(rel["score"], np.float64)
+        s.score_is_int = ptr(rel.get("score_is_int"), np.uint8)
+        for k in ("q_start", "q_end", "s_start", "s_end"):
+            setattr(s, k, ptr(ranges[k], np.int64))
+        s.q_minus, s.s_minus = ptr(ranges["q_minus"], np.int8), ptr(ranges["s_minus"], np.int8)
+        s.relative = ptr(ranges.get("relative"), np.uint8)
+        for k in ("qleft", "qright", "sleft", "sright"):
+            setattr(s, k, ptr(ranges.get(k), np.int64))
+        s.mem = 1 if device else 0
+        s._keepalive = keep
+        return s
+
+    def run_cut(self, cut_struct):
+        n = C.c_int64(0)
+        self._check(self.lib.o2a_cut_batch(self.h, C.byref(cut_struct), C.byref(n)), "o2a_cut_batch")
+        self.cut_n_aln, self.cut_n_kept = int(cut_struct.n_aln), int(n.value)
+        return self.cut_n_kept
+
+    def fetch_cut(self):
+        na, nk = self.cut_n_aln, self.cut_n_kept
+        out = dict(hsp_off=np.zeros(na + 1, np.int64), qstart=np.zeros(nk, np.int32), qend=np.zeros(nk, np.int32),
+                   sstart=np.zeros(nk, np.int32), send=np.zeros(nk, np.int32), score=np.zeros(nk), cut=np.zeros(nk, np.uint8),
+                   qlen=np.zeros(na, np.int64), slen=np.zeros(na, np.int64), status=np.zeros(na, np.int32))
+        self._check(self.lib.o2a_fetch_cut(self.h, *[_p(out[k]) for k in ("hsp_off", "qstart", "qend", "sstart", "send",
+                                                                         "score", "cut", "qlen", "slen", "status")]),
+                    "o2a_fetch_cut")
+        return out
+
+    def cut_batch(self, rel, ranges):
+        """Host arrays in, host arrays out: dict(hsp_off, qstart, qend, sstart, send, score, cut, qlen, slen, status)."""
+        self.run_cut(self.cut_struct(rel, ranges))
+        return self.fetch_cut()
+
+    def cut_view(self):
+        """O2ABatch with the device pointers of the last cut (mem = DEVICE): fill aln_off / bg and pass to run()."""
+        s = _lib.O2ABatch()
+        self._check(self.lib.o2a_cut_view(self.h, C.byref(s)), "o2a_cut_view")
+        return s
+
+    def cut_ms(self):
+        ms = (C.c_float * 4)()
+        self._check(self.lib.o2a_get_cut_ms(self.h, ms), "o2a_get_cut_ms")
+        return dict(zip(self.CUT_STAGES, [float(x) for x in ms]))
+
     # ---- operator-level seams -------------------------------------------------------------------
     def fitter_eval(self, fitter, bg, x=None, q=None, kde_factor=1.0):
         bg = np.ascontiguousarray(bg, dtype=np.int32)

@@ -238,3 +238,79 @@ def to_json_dicts(batch, metas):
         b0, b1 = int(batch.bg_off[l]), int(batch.bg_off[l + 1])
         out.append((m["name"], alns, [int(x) for x in batch.bg[b0:b1]]))
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Producer side: what `_align_syntenies` (pipeline.py:507-546) sees before it
+# writes the alignment JSON — BLAST "7 std score" tables of a flanked query neighbourhood against a
+# syntenic window, in sequence-relative 1-based inclusive coordinates.
+# --------------------------------------------------------------------------------------------------
+BLAST_FIELDS = ("query acc.ver, subject acc.ver, % identity, alignment length, mismatches, gap opens, "
+                "q. start, q. end, s. start, s. end, evalue, bit score, score")
+
+
+def relative_hits(rng, n, q_len, s_len):
+    """n BLAST hits as 1-based inclusive (qstart, qend, sstart, send, score) rows; 50 % minus-strand subject
+    (s. start > s. end, as blastn prints them)."""
+    ln = rng.integers(12, 121, size=n)
+    qs = rng.integers(1, max(2, q_len - 121), size=n)
+    qe = qs + ln - 1
+    ss = rng.integers(1, max(2, s_len - 121), size=n)
+    se = ss + ln - 1 + rng.integers(-3, 4, size=n)          # gapped: subject span differs a little
+    rev = rng.random(n) < 0.5
+    ss, se = np.where(rev, se, ss), np.where(rev, ss, se)
+    return qs, qe, ss, se, null_scores(rng, n).astype(np.int64)
+
+
+def blast_tabular(qs, qe, ss, se, score, qname="query", sname="subject", fields=BLAST_FIELDS):
+    """Render hits as `blastn -outfmt "7 std score"` text (the stream `from_file_blast` parses,
+    alignment.py:515-586)."""
+    head = [f"# BLASTN 2.12.0+", f"# Query: {qname}", f"# Database: User specified sequence set (Input: {sname}.fa)"]
+    if len(qs) == 0:
+        return "\n".join(head + ["# 0 hits found", "# BLAST processed 1 queries", ""])
+    rows = [f"{qname}\t{sname}\t{90 + (int(s) % 10)}.000\t{abs(int(b) - int(a)) + 1}\t0\t0\t{a}\t{b}\t{c}\t{d}\t1e-05\t{int(s) * 1.8:.1f}\t{s}"
+            for a, b, c, d, s in zip(qs, qe, ss, se, score)]
+    return "\n".join(head + [f"# Fields: {fields}", f"# {len(qs)} hits found"] + rows + ["# BLAST processed 1 queries", ""])
+
+
+def producer_workload(n_lnc, seed=0, regions=5, hits_per_region=2000, flank=50_000, strands=("+", "-", ".")):
+    """Per query gene: a flanked neighbourhood aligned to `regions` syntenic windows.
+
+    Returns (rel, ranges): `rel` = dict of flat arrays in the layout `o2a_cut_batch` takes (hsp_off and
+    0-based half-open relative coordinates as `from_file_blast` leaves them, float64 scores); `ranges` =
+    per-alignment int64 arrays q_start, q_end, q_minus, s_start, s_end, s_minus (the neighbourhood and the
+    syntenic window, genomicranges.py:1108-1129) and qleft, qright (the gene itself, pipeline.py:530-531)."""
+    rng = np.random.default_rng([seed, 77])
+    n_aln = n_lnc * regions
+    counts = np.maximum(1, rng.poisson(hits_per_region, size=n_aln)) if hits_per_region > 0 else np.zeros(n_aln, np.int64)
+    hsp_off = np.zeros(n_aln + 1, dtype=np.int64)
+    np.cumsum(counts, out=hsp_off[1:])
+    n = int(hsp_off[-1])
+    aln_of = np.repeat(np.arange(n_aln), counts)
+    gene_len = np.repeat(rng.integers(300, GENE_WINDOW, size=n_lnc), regions)
+    gene_start = np.repeat(rng.integers(flank + 1, 200_000_000, size=n_lnc), regions)
+    q_start, q_end = gene_start - flank, gene_start + gene_len + flank
+    s_start = rng.integers(1, 200_000_000, size=n_aln)
+    s_end = s_start + SUBJECT_WINDOW
+    q_minus = np.repeat(rng.choice([s == "-" for s in strands], size=n_lnc), regions).astype(np.int8)
+    s_minus = rng.choice([s == "-" for s in strands], size=n_aln).astype(np.int8)
+    # hits concentrate around the gene (60 %) so that a realistic share survives the cut and some straddle it
+    q_span = (q_end - q_start)[aln_of]
+    near = rng.random(n) < 0.6
+    centre = np.where(q_minus[aln_of] == 1, q_span - flank - gene_len[aln_of] // 2, flank + gene_len[aln_of] // 2)
+    qs = np.where(near, centre + (rng.normal(0, 1, size=n) * gene_len[aln_of]).astype(np.int64),
+                  rng.integers(0, 1 << 62, size=n) % np.maximum(1, q_span - 130))
+    ln = rng.integers(12, 121, size=n)
+    qs = np.clip(qs, 0, q_span - 130)
+    qe = qs + ln
+    ss = rng.integers(0, SUBJECT_WINDOW - 130, size=n)
+    se = ss + ln + rng.integers(-3, 4, size=n)
+    rev = rng.random(n) < 0.5
+    # minus-strand subject hit as from_file_blast leaves it: (s. start - 1, s. end) with s. start > s. end
+    ss, se = np.where(rev, se - 1, ss), np.where(rev, ss + 1, se)
+    rel = dict(hsp_off=hsp_off, qstart=qs.astype(np.int32), qend=qe.astype(np.int32), sstart=ss.astype(np.int32),
+               send=se.astype(np.int32), score=null_scores(rng, n).astype(np.float64))
+    ranges = dict(q_start=q_start.astype(np.int64), q_end=q_end.astype(np.int64), q_minus=q_minus,
+                  s_start=s_start.astype(np.int64), s_end=s_end.astype(np.int64), s_minus=s_minus,
+                  qleft=gene_start.astype(np.int64), qright=(gene_start + gene_len).astype(np.int64))
+    return rel, ranges

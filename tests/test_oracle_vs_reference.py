@@ -51,3 +51,50 @@ def test_random_chains_against_live_reference():
         chain, orient, score, s2 = O.best_chain(qs, qe, ss, se, sc, al.qlen, al.slen, 5, 2)
         assert chain.tolist() == [h.kwargs["kw"] for h in best.HSPs]
         assert s2 == (float(ch["direct"].score), float(ch["reverse"].score))
+
+
+def test_random_cuts_against_live_reference():
+    """to_genomic + cut_coordinates: 400 random alignments, every strand combination,
+    random subsets of the four boundaries, float and int table scores — coordinates, order, scores (bit-exact),
+    score types and qlen/slen identical to the reference's objects."""
+    from oracle import producer as OP
+    ref = rh.import_reference()
+    GR, GRA, HV = ref.genomicranges.GenomicRange, ref.genomicranges.GenomicRangesAlignment, ref.alignment.HSPVertex
+    rng = np.random.default_rng(77)
+    n_cut = 0
+    for it in range(400):
+        n = int(rng.integers(0, 40))
+        qs = rng.integers(0, 2000, size=n); ln = rng.integers(1, 300, size=n)
+        ss = rng.integers(0, 5000, size=n); sl = ln + rng.integers(-3, 4, size=n).clip(-ln + 1, None)
+        rev = rng.random(n) < 0.5
+        s1, s2 = np.where(rev, ss + sl, ss), np.where(rev, ss, ss + sl)
+        is_int = rng.random(n) < 0.8
+        sc = np.where(is_int, rng.integers(12, 200, size=n), rng.integers(12, 200, size=n) * 0.37)
+        q0, s0 = int(rng.integers(1, 10 ** 6)), int(rng.integers(1, 10 ** 6))
+        qstrand, sstrand = "+-."[rng.integers(3)], "+-."[rng.integers(3)]
+        relative = bool(rng.random() < 0.85)
+        hsps = [HV(int(a), int(b), int(c), int(d), int(e) if i else float(e)) for a, b, c, d, e, i in zip(qs, qs + ln, s1, s2, sc, is_int)]
+        aln = GRA(hsps, GR("c1", q0, q0 + 2400, qstrand), GR("c2", s0, s0 + 5400, sstrand), relative=relative)
+        aln.to_genomic()
+        lo_q, hi_q = (q0, q0 + 2400) if relative else (0, 2400)
+        lo_s, hi_s = (s0, s0 + 5400) if relative else (0, 5400)
+        bounds = {}
+        for k, lo, hi in (("qleft", lo_q, hi_q), ("qright", lo_q, hi_q), ("sleft", lo_s, hi_s), ("sright", lo_s, hi_s)):
+            if rng.random() < 0.6:
+                bounds[k] = int(rng.integers(lo, hi))
+        cut = aln.cut_coordinates(**bounds)
+        rel = dict(hsp_off=np.array([0, n]), qstart=qs, qend=qs + ln, sstart=s1, send=s2, score=sc.astype(float),
+                   score_is_int=is_int.astype(np.uint8))
+        one = lambda v: np.array([v], dtype=np.int64)
+        rg = dict(q_start=one(q0), q_end=one(q0 + 2400), q_minus=np.array([qstrand == "-"]), s_start=one(s0),
+                  s_end=one(s0 + 5400), s_minus=np.array([sstrand == "-"]), relative=np.array([relative], dtype=np.uint8),
+                  **{k: one(bounds.get(k, OP.NO_BOUND)) for k in ("qleft", "qright", "sleft", "sright")})
+        r = OP.cut_batch(rel, rg)
+        want = cut._all_HSPs
+        got = np.stack([r["qstart"], r["qend"], r["sstart"], r["send"]], 1).tolist() if len(want) else []
+        assert got == [[h.qstart, h.qend, h.sstart, h.send] for h in want], (it, bounds)
+        assert r["score"].tolist() == [float(h.score) for h in want], (it, bounds)
+        assert [c != 0 for c in r["cut"]] == [isinstance(h.score, float) for h in want]
+        assert (int(r["qlen"][0]), int(r["slen"][0])) == (cut.qlen, cut.slen)
+        n_cut += int((r["cut"] & 1).sum())
+    assert n_cut > 200
