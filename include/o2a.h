@@ -201,7 +201,8 @@ int  o2a_get_stage_ms(o2a_ctx *ctx, float *ms /*O2A_STAGE_COUNT*/);
  * (o2a_cut_view) and can be fetched (o2a_fetch_cut). Kept HSPs keep their order.
  * ------------------------------------------------------------------------------------------- */
 #define O2A_NO_BOUND INT64_MIN             /* a boundary that is None */
-#define O2A_CUT_STATUS_RANGE 1             /* a kept coordinate does not fit int32 */
+#define O2A_CUT_STATUS_RANGE 1             /* a kept coordinate does not fit int32: the alignment's coordinates,
+                                              qlen and slen are not meaningful */
 #define O2A_CUT_STATUS_INEXACT 2           /* an intermediate product beyond 2^53 (Python's exact ints would differ) */
 
 typedef struct o2a_cut_input {

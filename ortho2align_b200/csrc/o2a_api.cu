@@ -1068,10 +1068,12 @@ extern "C" int o2a_cut_batch(o2a_ctx* ctx, const o2a_cut_input* in, int64_t* n_k
         LAUNCH_CHECK();
     }
     const int tile_grid = grid_for(ctx, (max_tiles + CUT_WARPS - 1) / CUT_WARPS, 8);
-    k_cut<false><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
+    // count pass (fast class + general class), scan of the tile counts, write pass, straddler fix-up
+    k_cut_fast<false><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
+    k_cut_general<false><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
     if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[2], ctx->stream));
-    // tile bases: exclusive scan of the per-tile counts (n_tiles = tile_off[n_aln] lives on the device)
     const long long* n_tiles_ptr = A.tile_off + n_aln;
     const int scan_grid = grid_for(ctx, max_chunks, 8);
     k_scan_chunk_sums<<<scan_grid, 256, 0, ctx->stream>>>(n_tiles_ptr, A.tile_cnt, P<long long>(ctx->ct_sums));
@@ -1080,11 +1082,19 @@ extern "C" int o2a_cut_batch(o2a_ctx* ctx, const o2a_cut_input* in, int64_t* n_k
     LAUNCH_CHECK();
     k_scan_chunks<<<scan_grid, 256, 0, ctx->stream>>>(n_tiles_ptr, A.tile_cnt, P<long long>(ctx->ct_sums), P<long long>(ctx->ct_out));
     LAUNCH_CHECK();
+    k_cut_offsets<<<grid_for(ctx, (n_aln + 256) / 256, 4), 256, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
     if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[3], ctx->stream));
-    k_cut<true><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
+    k_cut_fast<true><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
-    k_cut_finish<<<grid_for(ctx, (n_aln + 256) / 256, 4), 256, 0, ctx->stream>>>(A);
+    k_cut_general<true><<<tile_grid, CUT_WARPS * 32, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
+    k_cut_fixup<<<grid_for(ctx, n_hsp / FIXUP_SPAN + 1, 4), FIXUP_THREADS, 0, ctx->stream>>>(A);
+    LAUNCH_CHECK();
+    if (n_aln > 0) {
+        k_cut_finish<<<grid_for(ctx, (n_aln + 255) / 256, 4), 256, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+    }
     if (ctx->timing) CU(cudaEventRecord(ctx->cut_ev[4], ctx->stream));
     long long kept = 0;
     CU(cudaMemcpyAsync(&kept, P<long long>(ctx->co_off) + n_aln, 8, cudaMemcpyDeviceToHost, ctx->stream));
