@@ -65,7 +65,7 @@ struct o2a_ctx {
     DevBuf off_a, off_b, out_i32, out_f64a, out_f64b, out_u8, maxred;
     // producer side (o2a_cut_batch)
     DevBuf ci_isint, ci_qstart, ci_qend, ci_sstart, ci_send, ci_qminus, ci_sminus, ci_rel, ci_ql, ci_qr, ci_sl, ci_sr;
-    DevBuf ct_n, ct_off, ct_aln, ct_cnt, ct_out, ct_sums, ct_maxq, ct_maxs;
+    DevBuf ct_n, ct_off, ct_aln, ct_cnt, ct_out, ct_sums, ct_maxq, ct_maxs, ct_gen, ct_gen_n, ct_fast, ct_nal, ct_span;
     DevBuf co_off, co_qs, co_qe, co_ss, co_se, co_score, co_cut, co_qlen, co_slen, co_status;
     bool have_cut = false;
     long long cut_n_aln = 0, cut_n_kept = 0;
@@ -265,7 +265,7 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->out_f64b, &ctx->out_u8, &ctx->maxred,
                       &ctx->ci_isint, &ctx->ci_qstart, &ctx->ci_qend, &ctx->ci_sstart, &ctx->ci_send, &ctx->ci_qminus, &ctx->ci_sminus,
                       &ctx->ci_rel, &ctx->ci_ql, &ctx->ci_qr, &ctx->ci_sl, &ctx->ci_sr, &ctx->ct_n, &ctx->ct_off,
-                      &ctx->ct_aln, &ctx->ct_cnt, &ctx->ct_out, &ctx->ct_sums, &ctx->ct_maxq, &ctx->ct_maxs,
+                      &ctx->ct_aln, &ctx->ct_cnt, &ctx->ct_out, &ctx->ct_sums, &ctx->ct_maxq, &ctx->ct_maxs, &ctx->ct_gen, &ctx->ct_gen_n, &ctx->ct_fast, &ctx->ct_nal, &ctx->ct_span,
                       &ctx->co_off, &ctx->co_qs, &ctx->co_qe, &ctx->co_ss, &ctx->co_se, &ctx->co_score, &ctx->co_cut,
                       &ctx->co_qlen, &ctx->co_slen, &ctx->co_status};
     for (DevBuf* b : bufs) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
@@ -1051,20 +1051,34 @@ extern "C" int o2a_cut_batch(o2a_ctx* ctx, const o2a_cut_input* in, int64_t* n_k
     ENS(co_off, (n_aln + 1) * 8); ENS(co_qlen, (n_aln + 1) * 8); ENS(co_slen, (n_aln + 1) * 8); ENS(co_status, (n_aln + 1) * sizeof(int));
     ENS(co_qs, n_hsp * 4); ENS(co_qe, n_hsp * 4); ENS(co_ss, n_hsp * 4); ENS(co_se, n_hsp * 4);
     ENS(co_score, n_hsp * 8); ENS(co_cut, n_hsp);
+    ENS(ct_gen, (max_tiles + 1) * 8); ENS(ct_gen_n, 16); ENS(ct_fast, n_aln + 1);
+    ENS(ct_span, (n_hsp / FIXUP_SPAN + 2) * sizeof(int));
+    A.span_aln = P<int>(ctx->ct_span);
+    CU(cudaMemsetAsync(ctx->ct_gen_n.p, 0, 16, ctx->stream));
+    A.gen_tiles = P<long long>(ctx->ct_gen); A.gen_n = P<unsigned long long>(ctx->ct_gen_n); A.aln_fast = P<unsigned char>(ctx->ct_fast);
     A.tile_off = P<long long>(ctx->ct_off); A.tile_aln = P<int>(ctx->ct_aln); A.tile_cnt = P<int>(ctx->ct_cnt);
     A.tile_out = P<long long>(ctx->ct_out);
     A.oqs = P<int>(ctx->co_qs); A.oqe = P<int>(ctx->co_qe); A.oss = P<int>(ctx->co_ss); A.ose = P<int>(ctx->co_se);
     A.oscore = P<double>(ctx->co_score); A.ocut = P<unsigned char>(ctx->co_cut);
     A.max_q = P<int>(ctx->ct_maxq); A.max_s = P<int>(ctx->ct_maxs); A.status = P<int>(ctx->co_status);
     A.out_off = P<long long>(ctx->co_off); A.qlen = P<long long>(ctx->co_qlen); A.slen = P<long long>(ctx->co_slen);
-    if (n_aln > 0) {
-        k_cut_tiles_per_aln<<<grid_for(ctx, (n_aln + 255) / 256, 4), 256, 0, ctx->stream>>>(n_aln, A.hsp_off, P<int>(ctx->ct_n));
+    // tiles per alignment -> tile_off (exclusive scan over the alignments)
+    ENS(ct_nal, 16);
+    k_cut_tiles_per_aln<<<grid_for(ctx, (n_aln + 255) / 256, 4), 256, 0, ctx->stream>>>(n_aln, A.hsp_off, P<int>(ctx->ct_n), P<long long>(ctx->ct_nal));
+    LAUNCH_CHECK();
+    {
+        const long long aln_chunks = (n_aln + SCAN_CHUNK - 1) / SCAN_CHUNK + 1;
+        ENS(ct_sums, ((max_chunks > aln_chunks ? max_chunks : aln_chunks) + 1) * 8);
+        const int g = grid_for(ctx, aln_chunks, 8);
+        k_scan_chunk_sums<<<g, 256, 0, ctx->stream>>>(P<long long>(ctx->ct_nal), P<int>(ctx->ct_n), P<long long>(ctx->ct_sums));
+        LAUNCH_CHECK();
+        k_scan_sums<<<1, 1024, 0, ctx->stream>>>(P<long long>(ctx->ct_nal), P<long long>(ctx->ct_sums));
+        LAUNCH_CHECK();
+        k_scan_chunks<<<g, 256, 0, ctx->stream>>>(P<long long>(ctx->ct_nal), P<int>(ctx->ct_n), P<long long>(ctx->ct_sums), P<long long>(ctx->ct_off));
         LAUNCH_CHECK();
     }
-    k_scan_offsets<<<1, 1024, 0, ctx->stream>>>(n_aln, P<int>(ctx->ct_n), P<long long>(ctx->ct_off));
-    LAUNCH_CHECK();
     if (n_aln > 0) {
-        k_cut_fill_tile_aln<<<grid_for(ctx, n_aln, 16), 64, 0, ctx->stream>>>(n_aln, A.tile_off, P<int>(ctx->ct_aln), A.max_q, A.max_s, A.status);
+        k_cut_fill_tile_aln<<<grid_for(ctx, n_aln, 32), 32, 0, ctx->stream>>>(A, P<int>(ctx->ct_aln));
         LAUNCH_CHECK();
     }
     const int tile_grid = grid_for(ctx, (max_tiles + CUT_WARPS - 1) / CUT_WARPS, 8);

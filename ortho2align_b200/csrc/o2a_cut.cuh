@@ -56,6 +56,10 @@ struct CutArgs {
     const long long* tile_off;   // [n_aln + 1] first tile of each alignment
     const int* tile_aln;         // [n_tiles]
     int* tile_cnt;               // [n_tiles] kept HSPs per tile
+    long long* gen_tiles;        // tiles of the general-class alignments (any order)
+    unsigned long long* gen_n;   // their number
+    unsigned char* aln_fast;     // [n_aln] class of each alignment
+    int* span_aln;               // [n_out / FIXUP_SPAN + 1] alignment holding the first output of each fix-up span
     const long long* tile_out;   // [n_tiles + 1] exclusive scan of tile_cnt
     // outputs
     int *oqs, *oqe, *oss, *ose;
@@ -193,18 +197,26 @@ __device__ __forceinline__ void cut_load_aln(const CutArgs& A, long long a, CutA
 }
 
 // tiles per alignment (int, scanned into tile_off by the host-side launcher)
-__global__ void k_cut_tiles_per_aln(long long n_aln, const long long* __restrict__ hsp_off, int* __restrict__ n_tiles)
+__global__ void k_cut_tiles_per_aln(long long n_aln, const long long* __restrict__ hsp_off, int* __restrict__ n_tiles,
+                                    long long* __restrict__ n_aln_dev)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_aln_dev = n_aln;          // length of the scan that follows
     for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < n_aln; a += (long long)gridDim.x * blockDim.x)
         n_tiles[a] = (int)((hsp_off[a + 1] - hsp_off[a] + CUT_TILE - 1) / CUT_TILE);
 }
 
-__global__ void k_cut_fill_tile_aln(long long n_aln, const long long* __restrict__ tile_off, int* __restrict__ tile_aln,
-                                    int* __restrict__ max_q, int* __restrict__ max_s, int* __restrict__ status)
+// tile -> alignment map, per-alignment accumulators, alignment class; the (few) tiles of general-class alignments
+// are listed so that k_cut_general touches nothing else
+__global__ void k_cut_fill_tile_aln(CutArgs A, int* __restrict__ tile_aln)
 {
-    for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
-        for (long long t = tile_off[a] + threadIdx.x; t < tile_off[a + 1]; t += blockDim.x) tile_aln[t] = (int)a;
-        if (threadIdx.x == 0) { max_q[a] = INT32_MIN; max_s[a] = INT32_MIN; status[a] = 0; }
+    for (long long a = blockIdx.x; a < A.n_aln; a += gridDim.x) {
+        CutAln al;
+        cut_load_aln(A, a, al);
+        const long long t0 = A.tile_off[a], t1 = A.tile_off[a + 1];
+        for (long long t = t0 + threadIdx.x; t < t1; t += blockDim.x) tile_aln[t] = (int)a;
+        if (!al.fast)
+            for (long long t = t0 + threadIdx.x; t < t1; t += blockDim.x) A.gen_tiles[atomicAdd(A.gen_n, 1ull)] = t;
+        if (threadIdx.x == 0) { A.max_q[a] = INT32_MIN; A.max_s[a] = INT32_MIN; A.status[a] = 0; A.aln_fast[a] = al.fast ? 1 : 0; }
     }
 }
 
@@ -228,16 +240,16 @@ __device__ __forceinline__ int cut_classify(const CutAln& al, T qs, T qe, T& gqs
 // Fast class, pass 1 (WRITE = false): kept HSPs per tile from qstart / qend alone.
 // Pass 2 (WRITE = true): genomic coordinates of the kept HSPs in order; straddlers raw + CUT_MARK.
 template <bool WRITE>
-__global__ void __launch_bounds__(CUT_WARPS * 32) k_cut_fast(CutArgs A)
+__global__ void __launch_bounds__(CUT_WARPS * 32, 4) k_cut_fast(CutArgs A)
 {
     const int lane = lane_id();
     const long long n_tiles = A.tile_off[A.n_aln];
     const long long warps = (long long)gridDim.x * CUT_WARPS;
     for (long long t = (long long)blockIdx.x * CUT_WARPS + warp_id(); t < n_tiles; t += warps) {
         const long long a = A.tile_aln[t];
+        if (!A.aln_fast[a]) continue;                               // k_cut_general's tile
         CutAln al;
         cut_load_aln(A, a, al);
-        if (!al.fast) continue;                                     // k_cut_general's tile
         const long long h0 = A.hsp_off[a] + (t - A.tile_off[a]) * CUT_TILE;
         const int n_tile = (int)min((long long)CUT_TILE, A.hsp_off[a + 1] - h0);
         // tile-relative addressing: one 64-bit base per array, 32-bit offsets from there on
@@ -309,13 +321,11 @@ template <bool WRITE>
 __global__ void __launch_bounds__(CUT_WARPS * 32) k_cut_general(CutArgs A)
 {
     const int lane = lane_id();
-    const long long n_tiles = A.tile_off[A.n_aln];
+    const long long n_gen = (long long)*A.gen_n;
     const long long warps = (long long)gridDim.x * CUT_WARPS;
-    for (long long t = (long long)blockIdx.x * CUT_WARPS + warp_id(); t < n_tiles; t += warps) {
+    for (long long g = (long long)blockIdx.x * CUT_WARPS + warp_id(); g < n_gen; g += warps) {
+        const long long t = A.gen_tiles[g];
         const long long a = A.tile_aln[t];
-        CutAln al;
-        cut_load_aln(A, a, al);
-        if (al.fast) continue;
         CutRange r; CutBounds b;
         cut_load_alignment(A, a, r, b);
         const long long h0 = A.hsp_off[a] + (t - A.tile_off[a]) * CUT_TILE;
@@ -362,28 +372,57 @@ __global__ void __launch_bounds__(CUT_WARPS * 32) k_cut_general(CutArgs A)
     }
 }
 
-// out_off[a] = base of the alignment's first tile (needed by k_cut_fixup to find the alignment of an output)
+constexpr int FIXUP_THREADS = 256;
+constexpr int FIXUP_PER_THREAD = 64;                // flag bytes per thread per iteration (4 x 16 B loads)
+constexpr int FIXUP_SPAN = FIXUP_THREADS * FIXUP_PER_THREAD;      // outputs scanned per CTA iteration (< 65536)
+constexpr int FIXUP_STAGE = 512;
+
+// out_off[a] = base of the alignment's first tile; span_aln[s] = the alignment that holds output s * FIXUP_SPAN
+// (k_cut_fixup brackets its alignment search with it)
 __global__ void k_cut_offsets(CutArgs A)
 {
-    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a <= A.n_aln; a += (long long)gridDim.x * blockDim.x)
-        A.out_off[a] = A.tile_out[A.tile_off[a]];
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a <= A.n_aln; a += (long long)gridDim.x * blockDim.x) {
+        const long long lo = A.tile_out[A.tile_off[a]];
+        A.out_off[a] = lo;
+        if (a < A.n_aln) {
+            const long long hi = A.tile_out[A.tile_off[a + 1]];
+            for (long long sp = (lo + FIXUP_SPAN - 1) / FIXUP_SPAN; sp * FIXUP_SPAN < hi; ++sp) A.span_aln[sp] = (int)a;
+        }
+    }
 }
 
 // Straddling HSPs of the fast class: find the marked outputs, pack them, one lane each through the reference's
 // arithmetic (to_genomic + both query cuts in 64-bit integers / float64), results written in place.
-constexpr int FIXUP_THREADS = 256;
-constexpr int FIXUP_SPAN = FIXUP_THREADS * 16;      // outputs scanned per CTA iteration
 
 __global__ void __launch_bounds__(FIXUP_THREADS) k_cut_fixup(CutArgs A)
 {
-    __shared__ int s_list[FIXUP_SPAN];
+    __shared__ unsigned short s_list[FIXUP_SPAN];
     __shared__ int s_n;
+    __shared__ long long s_alo, s_ahi;
+    __shared__ long long s_off[FIXUP_STAGE];            // out_off of the span's alignments, when they are few enough
     const long long n_out = A.out_off[A.n_aln];
+    // last alignment a with out_off[a] <= o, searched in [lo, hi]
+    auto find_aln = [&](long long o, long long lo, long long hi) {
+        while (lo < hi) {
+            const long long mid = (lo + hi + 1) >> 1;
+            if (A.out_off[mid] <= o) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    };
     for (long long c0 = (long long)blockIdx.x * FIXUP_SPAN; c0 < n_out; c0 += (long long)gridDim.x * FIXUP_SPAN) {
-        if (threadIdx.x == 0) s_n = 0;
+        if (threadIdx.x == 0) {
+            // the outputs of this span belong to a short run of alignments, bracketed by the span table
+            s_n = 0;
+            s_alo = A.span_aln[c0 / FIXUP_SPAN];
+            s_ahi = c0 + FIXUP_SPAN < n_out ? A.span_aln[c0 / FIXUP_SPAN + 1] : max(A.n_aln - 1, 0ll);
+        }
         __syncthreads();
-        {   // 16 flag bytes per thread: one 16 B load (c0 is a multiple of 4096, the buffer is 256 B aligned)
-            const long long o = c0 + threadIdx.x * 16;
+        // flag bytes, 16 per load (c0 is a multiple of the span, the buffer is 256 B aligned); thread-interleaved
+        // so that a warp reads 512 contiguous bytes per load
+#pragma unroll
+        for (int v4 = 0; v4 < FIXUP_PER_THREAD / 16; ++v4) {
+            const int off = (v4 * FIXUP_THREADS + threadIdx.x) * 16;
+            const long long o = c0 + off;
             if (o + 16 <= n_out) {
                 const uint4 v = *reinterpret_cast<const uint4*>(A.ocut + o);
                 const unsigned w[4] = {v.x, v.y, v.z, v.w};
@@ -393,25 +432,32 @@ __global__ void __launch_bounds__(FIXUP_THREADS) k_cut_fixup(CutArgs A)
                     while (marks) {
                         const int bit = __ffs(marks) - 1;
                         marks &= marks - 1;
-                        s_list[atomicAdd(&s_n, 1)] = threadIdx.x * 16 + j * 4 + (bit >> 3);
+                        s_list[atomicAdd(&s_n, 1)] = (unsigned short)(off + j * 4 + (bit >> 3));
                     }
                 }
             } else {
                 for (int j = 0; j < 16 && o + j < n_out; ++j)
-                    if (A.ocut[o + j] & CUT_MARK) s_list[atomicAdd(&s_n, 1)] = threadIdx.x * 16 + j;
+                    if (A.ocut[o + j] & CUT_MARK) s_list[atomicAdd(&s_n, 1)] = (unsigned short)(off + j);
             }
         }
         __syncthreads();
         const int n = s_n;
+        const long long alo = s_alo, ahi = s_ahi;
+        const bool staged = ahi - alo < FIXUP_STAGE;
+        if (staged && n > 0)
+            for (long long k = threadIdx.x; k <= ahi - alo; k += FIXUP_THREADS) s_off[k] = A.out_off[alo + k];
+        __syncthreads();
         for (int e = threadIdx.x; e < n; e += FIXUP_THREADS) {
             const long long o = c0 + s_list[e];
-            // alignment of output o: last a with out_off[a] <= o
-            long long lo = 0, hi = A.n_aln;
-            while (lo < hi) {
-                const long long mid = (lo + hi + 1) >> 1;
-                if (A.out_off[mid] <= o) lo = mid; else hi = mid - 1;
-            }
-            const long long a = lo;
+            long long a;
+            if (staged) {
+                int lo = 0, hi = (int)(ahi - alo);
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= o) lo = mid; else hi = mid - 1;
+                }
+                a = alo + lo;
+            } else a = find_aln(o, alo, ahi);
             CutRange r; CutBounds b;
             cut_load_alignment(A, a, r, b);
             CutHsp h;
@@ -443,7 +489,7 @@ __global__ void k_cut_finish(CutArgs A)
 }
 
 // ---- exclusive scan int -> int64 over up to ~10^7 items: per-chunk sums, scan of the sums, per-chunk rescan ----
-constexpr int SCAN_CHUNK = 8192;
+constexpr int SCAN_CHUNK = 1024;
 
 __global__ void __launch_bounds__(256) k_scan_chunk_sums(const long long* __restrict__ n_ptr, const int* __restrict__ v,
                                                          long long* __restrict__ sums)
