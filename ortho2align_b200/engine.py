@@ -269,11 +269,14 @@ class Engine:
         self.cut_n_aln, self.cut_n_kept = int(cut_struct.n_aln), int(n.value)
         return self.cut_n_kept
 
-    def fetch_cut(self):
+    def fetch_cut(self, pinned=False):
+        """pinned=True: views of reusable page-locked buffers (valid until the next fetch_cut on this engine)."""
         na, nk = self.cut_n_aln, self.cut_n_kept
-        out = dict(hsp_off=np.zeros(na + 1, np.int64), qstart=np.zeros(nk, np.int32), qend=np.zeros(nk, np.int32),
-                   sstart=np.zeros(nk, np.int32), send=np.zeros(nk, np.int32), score=np.zeros(nk), cut=np.zeros(nk, np.uint8),
-                   qlen=np.zeros(na, np.int64), slen=np.zeros(na, np.int64), status=np.zeros(na, np.int32))
+        o = lambda k, n, dt: self._out("cut_" + k, n, dt, pinned)
+        out = dict(hsp_off=o("hsp_off", na + 1, np.int64), qstart=o("qstart", nk, np.int32), qend=o("qend", nk, np.int32),
+                   sstart=o("sstart", nk, np.int32), send=o("send", nk, np.int32), score=o("score", nk, np.float64),
+                   cut=o("cut", nk, np.uint8), qlen=o("qlen", na, np.int64), slen=o("slen", na, np.int64),
+                   status=o("status", na, np.int32))
         self._check(self.lib.o2a_fetch_cut(self.h, *[_p(out[k]) for k in ("hsp_off", "qstart", "qend", "sstart", "send",
                                                                          "score", "cut", "qlen", "slen", "status")]),
                     "o2a_fetch_cut")

@@ -328,6 +328,7 @@ def test_cut_accepts_device_resident_inputs(engine):
     torch.cuda.synchronize()
     engine.run_cut(engine.cut_struct(d_rel, d_rg, device=True))
     _same_cut(engine.fetch_cut(), host, "device-resident inputs")
+    _same_cut(engine.fetch_cut(pinned=True), host, "pinned result buffers")
 
 
 @pytest.mark.gpu

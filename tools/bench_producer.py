@@ -78,12 +78,12 @@ def main():
     h_rel = {k: keep_alive[k].numpy() for k in rel}
     h_rg = {k: keep_alive[k].numpy() for k in rg}
     hs = eng.cut_struct(h_rel, h_rg)
-    eng.run_cut(hs); eng.fetch_cut()
+    eng.run_cut(hs); eng.fetch_cut(pinned=True)
     e2e_steps = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         eng.run_cut(hs)
-        out = eng.fetch_cut()
+        out = eng.fetch_cut(pinned=True)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     h2d = sum(int(v.numpy().nbytes) for v in keep_alive.values())
     d2h = sum(int(v.nbytes) for v in out.values())
