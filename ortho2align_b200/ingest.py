@@ -72,13 +72,9 @@ class IngestResult:
         self.errors = {i: lib.o2a_ingest_file_error(handle, i).decode() for i in np.nonzero(self.file_status)[0]}
 
     def range_dict(self, a, which):
-        """Decoded qrange ('q') or srange ('s') dict of global alignment index `a`."""
-        l = int(np.searchsorted(self.batch.aln_off, a, side="right") - 1)
-        b, e = (self.spans[a, 0], self.spans[a, 1]) if which == "q" else (self.spans[a, 2], self.spans[a, 3])
-        n = int(e - b)
-        buf = C.create_string_buffer(n)
-        self._lib.o2a_ingest_span(self._h, int(self.lnc_file[l]), int(b), int(e), buf, n)
-        return json.loads(buf.raw[:n])
+        """Decoded qrange ('q') or srange ('s') dict of global alignment index `a`. Consecutive alignments of
+        a lncRNA carry the same qrange text: the same dict object is returned for identical text."""
+        return _decode_cached(self, self.range_text(a, which))
 
     def range_text(self, a, which):
         """Raw JSON text of the qrange / srange object of alignment `a` (bytes)."""
@@ -92,6 +88,9 @@ class IngestResult:
     def hsp_dict(self, h):
         return _hsp_dict(self.batch, self.score_is_int, h)
 
+    def hsp_dicts(self, idx):
+        return _hsp_dicts(self.batch, self.score_is_int, idx)
+
     def close(self):
         if self._h:
             self._lib.o2a_ingest_destroy(self._h)
@@ -102,6 +101,25 @@ class IngestResult:
             self.close()
         except Exception:
             pass
+
+
+def _decode_cached(owner, text):
+    last = getattr(owner, "_last_range", None)
+    if last is not None and last[0] == text:
+        return last[1]
+    d = json.loads(text)
+    owner._last_range = (text, d)
+    return d
+
+
+def _hsp_dicts(b, score_is_int, idx):
+    """HSPs `idx` (global indices, array) as the reference's JSON objects: one gather per column."""
+    idx = np.asarray(idx, dtype=np.int64)
+    cols = [np.asarray(getattr(b, k))[idx].tolist() for k in ("qstart", "qend", "sstart", "send")]
+    sc = np.asarray(b.score)[idx].tolist()
+    isint = np.asarray(score_is_int)[idx].tolist()
+    return [{"qstart": a, "qend": e, "sstart": c, "send": d, "score": int(v) if i else v}
+            for a, e, c, d, v, i in zip(*cols, sc, isint)]
 
 
 def _hsp_dict(b, score_is_int, h):
@@ -179,7 +197,8 @@ class SidecarResult:
             n = int(np.prod(d["shape"])) if d["shape"] else 1
             if n == 0:
                 return np.zeros(d["shape"], dtype=np.dtype(d["dtype"]))
-            return np.memmap(path, dtype=np.dtype(d["dtype"]), mode="r", offset=d["offset"], shape=tuple(d["shape"]))
+            m = np.memmap(path, dtype=np.dtype(d["dtype"]), mode="r", offset=d["offset"], shape=tuple(d["shape"]))
+            return np.asarray(m)           # plain ndarray view of the mapping: np.memmap's own indexing is slow
         self.batch = ColumnarBatch(*[arr(k) for k in _SIDECAR_ARRAYS])
         self.score_is_int = arr("score_is_int")
         self.lnc_file = arr("lnc_file")
@@ -187,12 +206,18 @@ class SidecarResult:
         self.file_status = np.zeros(directory["n_files"], dtype=np.int32)
         self.errors = {}
 
-    def range_dict(self, a, which):
+    def range_text(self, a, which):
         k = 2 * a + (0 if which == "q" else 1)
-        return json.loads(bytes(self._range_text[self._range_off[k]:self._range_off[k + 1]]))
+        return bytes(self._range_text[self._range_off[k]:self._range_off[k + 1]])
+
+    def range_dict(self, a, which):
+        return _decode_cached(self, self.range_text(a, which))
 
     def hsp_dict(self, h):
         return _hsp_dict(self.batch, self.score_is_int, h)
+
+    def hsp_dicts(self, idx):
+        return _hsp_dicts(self.batch, self.score_is_int, idx)
 
     def close(self):
         pass

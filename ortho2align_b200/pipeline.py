@@ -11,6 +11,7 @@ from __future__ import annotations
 import json
 import os
 import threading
+import time
 from collections import Counter
 from pathlib import Path
 
@@ -79,9 +80,12 @@ def _ingest_json(alignments_files, bg_files):
             out.append(ExceptionLogger(e, qr))
             continue
         d = alignment_dicts
-        out.append((batch, len(d), (lambda k, d=d: d[k]["qrange"]), (lambda k, d=d: d[k]["srange"]),
-                    (lambda k, j, d=d: d[k]["HSPs"][j])))
+        out.append((batch, 0, len(d), (lambda k, d=d: d[k]["qrange"]), (lambda k, d=d: d[k]["srange"]),
+                    (lambda k, idx, d=d: [d[k]["HSPs"][int(j)] for j in idx])))
     return out
+
+
+PHASES = {}      # wall seconds of the phases of the last build_orthologs call (tools/bench_e2e_files.py)
 
 
 def _ingest_native(alignments_files, bg_files, threads, cache=None):
@@ -100,11 +104,12 @@ def _ingest_native(alignments_files, bg_files, threads, cache=None):
             d = json.load(f)
         out[i] = ExceptionLogger(PackError(r.errors[int(i)]), Range.from_dict(d[0]["qrange"]) if d else None)
     b = r.batch
-    for l, i in enumerate(r.lnc_file):
-        a0, a1 = int(b.aln_off[l]), int(b.aln_off[l + 1])
-        out[int(i)] = (b.slice_lnc(l, l + 1), a1 - a0,
-                       (lambda k, a0=a0: r.range_dict(a0 + k, "q")), (lambda k, a0=a0: r.range_dict(a0 + k, "s")),
-                       (lambda k, j, a0=a0: r.hsp_dict(int(b.hsp_off[a0 + k]) + j)))
+    aln_off, hsp_off = b.aln_off.tolist(), b.hsp_off
+    for l, i in enumerate(r.lnc_file.tolist()):
+        a0, a1 = aln_off[l], aln_off[l + 1]
+        out[i] = (b, l, a1 - a0,
+                  (lambda k, a0=a0: r.range_dict(a0 + k, "q")), (lambda k, a0=a0: r.range_dict(a0 + k, "s")),
+                  (lambda k, idx, a0=a0: r.hsp_dicts(int(hsp_off[a0 + k]) + idx)))
     return out
 
 
@@ -164,30 +169,44 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     total_bgs = len(bg_files)
 
     # ---- ingest -------------------------------------------------------------------------------
-    # per file: an ExceptionLogger, or (single-lncRNA batch, n_alignments, accessors)
+    # per file: an ExceptionLogger, or (source batch, lncRNA index in it, n_alignments, accessors)
+    t_phase = time.perf_counter()
     loaded = _ingest_native(alignments_files, bg_files, cores, cache) if ingest == "native" \
         else _ingest_json(alignments_files, bg_files)
     ok_idx = [i for i, x in enumerate(loaded) if not isinstance(x, ExceptionLogger)]
 
+    PHASES["ingest"] = time.perf_counter() - t_phase
+    t_phase = time.perf_counter()
     # ---- compute: shard by lncRNA across GPUs, one batched call each ---------------------------------
     per_lnc = {}
     if ok_idx:
         n_dev = min(len(devices), len(ok_idx))
-        weights = [loaded[i][0].n_hsp + 1 for i in ok_idx]
+        src, src_l = [loaded[i][0] for i in ok_idx], [loaded[i][1] for i in ok_idx]
+        one_source = all(x is src[0] for x in src)             # native ingest: every lncRNA lives in one batch
+        if one_source:
+            per_lnc_hsps = src[0].hsp_off[src[0].aln_off[1:]] - src[0].hsp_off[src[0].aln_off[:-1]]
+            weights = (per_lnc_hsps[src_l] + 1).tolist()
+        else:
+            weights = [x.n_hsp + 1 for x in src]
         shards = lpt_shards(weights, n_dev)
-        batches = [concat_batches([loaded[ok_idx[j]][0] for j in shard]) for shard in shards]
+        if one_source:
+            batches = [src[0].take_lnc([src_l[j] for j in shard]) for shard in shards]
+        else:
+            batches = [concat_batches([src[j] for j in shard]) for shard in shards]
         results = _run_shards(batches, devices[:n_dev], fitting, fdr, threshold, gapopen, gapextend)
         for shard, batch, res in zip(shards, batches, results):
             for local, j in enumerate(shard):
                 per_lnc[ok_idx[j]] = (batch, res, local)
 
+    PHASES["compute"] = time.perf_counter() - t_phase
+    t_phase = time.perf_counter()
     # ---- assemble exactly what the pool would have returned ---------------------------------------------
     orthologs, exceptions = [], []
     for i, item in enumerate(loaded):
         if isinstance(item, ExceptionLogger):
             exceptions.append(item)
             continue
-        _, n_alns, qrange_of, srange_of, hsp_of = item
+        _, _, n_alns, qrange_of, srange_of, hsps_of = item
         batch, res, l = per_lnc[i]
         if res.status[l] != STATUS_OK:
             st = int(res.status[l])
@@ -196,14 +215,17 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
             continue
         q_orth, s_orth, q_dropped, s_dropped, aligned = [], [], None, [], False
         a0 = int(batch.aln_off[l])
+        last_qd, qrange = None, None
         for k in range(n_alns):
             a = a0 + k
-            qrange = Range.from_dict(qrange_of(k))
+            qd = qrange_of(k)
+            if qd is not last_qd:                       # the alignments of a lncRNA share their qrange (never mutated here)
+                last_qd, qrange = qd, Range.from_dict(qd)
             srange = Range.from_dict(srange_of(k))
             srange.name = qrange.name                                   # pipeline.py:781
             c0, c1 = int(res.chain_off[a]), int(res.chain_off[a + 1])
             if c1 > c0:
-                hsps = [hsp_of(k, int(j)) for j in res.chain_idx[c0:c1]]
+                hsps = hsps_of(k, res.chain_idx[c0:c1])
                 rec = chain_records(hsps, as_pvals(res.chain_pq[c0:c1]), qrange, srange.chrom, qrange.name)
                 q_orth.append((rec[0], rec[1]))
                 s_orth.append((rec[2], rec[3]))
@@ -273,6 +295,7 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
             f.write(stats_msg + "\n")
     elif not silent:
         print(stats_msg)
+    PHASES["records_and_files"] = time.perf_counter() - t_phase
 
 
 _EXTRACT = {

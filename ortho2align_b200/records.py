@@ -159,10 +159,12 @@ def chain_records(hsps, pvals, qrange, srange_chrom, name):
         sizes.reverse(); starts.reverse(); pv.reverse()
     sides.append((srange_chrom, c0, c1, name, score, strand, c0, c1, "0", len(hsps), sizes, starts, pv))
 
-    def join(side, n):
-        return "\t".join((",".join(str(v) for v in item) if isinstance(item, list) else str(item))
-                         for item in side[:n])
-    return join(sides[0], 13), join(sides[0], 12), join(sides[1], 13), join(sides[1], 12)
+    def join(side):
+        """(13-column TSV line, 12-column BED12 line): the TSV is the BED12 plus the p/q-value list"""
+        bed12 = "\t".join((",".join([str(v) for v in item]) if isinstance(item, list) else str(item)) for item in side[:12])
+        return bed12 + "\t" + ",".join([str(v) for v in side[12]]), bed12
+    q, s = join(sides[0]), join(sides[1])
+    return q[0], q[1], s[0], s[1]
 
 
 def as_pvals(values):
