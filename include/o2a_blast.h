@@ -46,6 +46,19 @@ int o2a_blast_export(const o2a_blast *b, int32_t *status, int64_t *hsp_off,
 /* name of the exception the reference raises for table i ("" when status is 0), e.g. "ValueError" */
 const char *o2a_blast_error(const o2a_blast *b, int64_t table);
 
+/* ---------------------------------------------------------------------------------------------
+ * Background collection: `_estimate_bg_for_single_query_blast/_seqfile`
+ * (pipeline.py:223-233, 259-269) keep at most `observations` of the BLAST scores found for a query:
+ *     if score_size > observations: scores = random.Random(); .seed(seed); .sample(scores, observations)
+ * The algorithm lives in CPython, not in the reference tree: Lib/random.py (Random.sample,
+ * _randbelow_with_getrandbits; unchanged 3.11 .. 3.13) over Modules/_randommodule.c (MT19937, seeding by
+ * init_by_array over the 32-bit words of abs(seed), getrandbits(k) = genrand_uint32() >> (32 - k)).
+ * o2a_bg_sample restates it: out receives min(n, observations) scores — all of them in order when
+ * n <= observations, else the sample in the order `sample` returns it. Returns the count written, -1 on
+ * invalid arguments.
+ * ------------------------------------------------------------------------------------------- */
+int64_t o2a_bg_sample(const int32_t *scores, int64_t n, int64_t observations, uint64_t seed, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

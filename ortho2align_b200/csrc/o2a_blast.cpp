@@ -268,3 +268,106 @@ extern "C" const char* o2a_blast_error(const o2a_blast* b, int64_t i)
     if (!b || i < 0 || i >= (int64_t)b->tables.size()) return "";
     return b->tables[(size_t)i].error;
 }
+
+
+// --------------------------------------------------------------------------------------------------
+// random.Random(seed).sample(population, k) of CPython (see include/o2a_blast.h for the sources restated)
+// --------------------------------------------------------------------------------------------------
+namespace {
+
+struct MT19937 {
+    static constexpr int N = 624, M = 397;
+    uint32_t mt[N];
+    int idx = N;
+
+    void init_genrand(uint32_t s)
+    {
+        mt[0] = s;
+        for (int i = 1; i < N; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = N;
+    }
+    void init_by_array(const uint32_t* key, int len)
+    {
+        init_genrand(19650218u);
+        int i = 1, j = 0;
+        for (int k = N > len ? N : len; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+            ++i; ++j;
+            if (i >= N) { mt[0] = mt[N - 1]; i = 1; }
+            if (j >= len) j = 0;
+        }
+        for (int k = N - 1; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+            ++i;
+            if (i >= N) { mt[0] = mt[N - 1]; i = 1; }
+        }
+        mt[0] = 0x80000000u;
+    }
+    uint32_t next()
+    {
+        if (idx >= N) {
+            static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
+            int kk = 0;
+            for (; kk < N - M; ++kk) {
+                uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + M] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            for (; kk < N - 1; ++kk) {
+                uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            uint32_t y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ mag01[y & 1u];
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    // Random._randbelow_with_getrandbits for 0 < n < 2^32
+    uint32_t randbelow(uint32_t n)
+    {
+        int k = 32 - __builtin_clz(n);              // n.bit_length()
+        uint32_t r = next() >> (32 - k);
+        while (r >= n) r = next() >> (32 - k);
+        return r;
+    }
+};
+
+}  // namespace
+
+extern "C" int64_t o2a_bg_sample(const int32_t* scores, int64_t n, int64_t observations, uint64_t seed, int32_t* out)
+{
+    if (n < 0 || observations < 0 || n >= (1ll << 32) || (n > 0 && (!scores || !out))) return -1;
+    if (n <= observations) {                         // pipeline.py:227, 263: sampled only when there are more
+        if (n) memcpy(out, scores, (size_t)n * sizeof(int32_t));
+        return n;
+    }
+    const int64_t k = observations;
+    MT19937 g;
+    uint32_t key[2] = {(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
+    g.init_by_array(key, key[1] ? 2 : 1);            // random_seed: 32-bit words of abs(seed), at least one
+    // setsize = 21 (+ 4 ** ceil(log(3k, 4)) for k > 5): 3k is never a power of 4, so the ceiling is the smallest e with 4^e >= 3k
+    int64_t setsize = 21;
+    if (k > 5) { int64_t p = 1; while (p < 3 * k) p *= 4; setsize += p; }
+    if (n <= setsize) {
+        std::vector<int32_t> pool(scores, scores + n);
+        for (int64_t i = 0; i < k; ++i) {
+            uint32_t j = g.randbelow((uint32_t)(n - i));
+            out[i] = pool[j];
+            pool[j] = pool[(size_t)(n - i - 1)];     // move non-selected item into vacancy
+        }
+    } else {
+        std::vector<uint8_t> selected((size_t)n, 0); // `j in selected` — membership only, so a bitmap does
+        for (int64_t i = 0; i < k; ++i) {
+            uint32_t j = g.randbelow((uint32_t)n);
+            while (selected[j]) j = g.randbelow((uint32_t)n);
+            selected[j] = 1;
+            out[i] = scores[j];
+        }
+    }
+    return k;
+}

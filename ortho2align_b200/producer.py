@@ -29,7 +29,7 @@ from .ingest import LIB_PATH
 
 NO_BOUND = np.iinfo(np.int64).min          # O2A_NO_BOUND: a boundary that is None
 BLAST_EXPORTS = ["o2a_blast_create", "o2a_blast_destroy", "o2a_blast_parse", "o2a_blast_sizes", "o2a_blast_export",
-                 "o2a_blast_error"]
+                 "o2a_blast_error", "o2a_bg_sample"]
 _lib = None
 
 
@@ -59,6 +59,8 @@ def load_lib():
         lib.o2a_blast_export.argtypes = [P] + [P] * 10
         lib.o2a_blast_error.restype = C.c_char_p
         lib.o2a_blast_error.argtypes = [P, i64]
+        lib.o2a_bg_sample.restype = i64
+        lib.o2a_bg_sample.argtypes = [P, i64, i64, C.c_uint64, P]
         _lib = lib
     return _lib
 
@@ -92,6 +94,38 @@ def parse_blast_tables(tables, threads=0, start_type=1, end_type="inclusive"):
     finally:
         lib.o2a_blast_destroy(h)
     return out
+
+
+def sample_background(scores, observations=1000, seed=0):
+    """The scores `_estimate_bg_for_single_query_*` would dump for a query (`pipeline.py:223-233, 259-269`):
+    all of them when there are at most `observations`, else `random.Random(seed).sample(scores, observations)`
+    — restated natively (CPython's MT19937 + `Random.sample`), bit-identical to the interpreter's."""
+    lib = load_lib()
+    sc = np.ascontiguousarray(scores, dtype=np.int32)
+    out = np.zeros(min(len(sc), int(observations)), dtype=np.int32)
+    n = lib.o2a_bg_sample(sc.ctypes.data_as(C.c_void_p), len(sc), int(observations), abs(int(seed)),
+                          out.ctypes.data_as(C.c_void_p))
+    if n < 0:
+        raise ValueError("o2a_bg_sample: invalid arguments")
+    return out[:n]
+
+
+def backgrounds_from_tables(tables, table_query, n_queries, observations=1000, seed=0, threads=0):
+    """Background score arrays straight from BLAST tables (no bg_files/*.json): `tables[t]` belongs to query
+    `table_query[t]` (ascending); the scores of a query's tables are concatenated in table order
+    (`pipeline.py:223-226`) and sampled like the reference does. Returns (bg_off, bg, n_found) — `bg` still
+    needs `columnar.patch_background` semantics, which `pack`/ingest apply at build time (`pipeline.py:746-754`)."""
+    r = parse_blast_tables(tables, threads=threads)
+    table_query = np.asarray(table_query, dtype=np.int64)
+    parts, found = [], np.zeros(n_queries, dtype=np.int64)
+    for q in range(n_queries):
+        ts = np.nonzero(table_query == q)[0]
+        sc = np.concatenate([r["score"][r["hsp_off"][t]:r["hsp_off"][t + 1]] for t in ts]) if len(ts) else np.zeros(0)
+        found[q] = len(sc)
+        parts.append(sample_background(sc.astype(np.int32), observations, seed))
+    bg_off = np.zeros(n_queries + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in parts], out=bg_off[1:])
+    return bg_off, (np.concatenate(parts) if parts else np.zeros(0, np.int32)).astype(np.int32), found
 
 
 def ranges_from_granges(qranges, sranges, genes=None, bounds=None):

@@ -128,10 +128,54 @@ def test_blast_reader_symbols_are_exported():
     lib = producer.load_lib()
     with open(os.path.join(ROOT, "include", "o2a_blast.h")) as f:
         src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
-    names = sorted(set(re.findall(r"\b(o2a_blast_[a-z_0-9]+)\s*\(", src)))
+    names = sorted(set(re.findall(r"\b(o2a_(?:blast|bg)_[a-z_0-9]+)\s*\(", src)))
     assert set(names) == set(producer.BLAST_EXPORTS)
     for n in names:
         assert hasattr(lib, n)
+
+
+def test_background_sampling_is_cpythons_random_sample():
+    """`random.Random(seed).sample(scores, observations)` (pipeline.py:228-231, 264-267) restated natively: the
+    interpreter's own `random` module is the reference here (both branches of `sample`, seeds beyond 32 bits)."""
+    import random
+    from ortho2align_b200 import build, producer
+    build.build_ingest()
+    rng = np.random.default_rng(0)
+    cases = [(5000, 1000, 0), (1001, 1000, 0), (4117, 1000, 3), (4118, 1000, 3), (27, 6, 2 ** 40 + 5), (100000, 1000, 123456789),
+             (10, 10, 0), (7, 3, 0), (21, 5, 9), (22, 5, 0), (2, 1, 0), (300, 64, 2 ** 32), (1, 5, 0), (0, 5, 0)]
+    cases += [(int(rng.integers(1, 3000)), int(rng.integers(1, 400)), int(rng.integers(0, 2 ** 62))) for _ in range(150)]
+    for n, k, seed in cases:
+        sc = rng.integers(12, 90, size=n).astype(np.int32)
+        if n > k:
+            r = random.Random()
+            r.seed(seed)
+            want = r.sample(sc.tolist(), k)
+        else:
+            want = sc.tolist()
+        assert producer.sample_background(sc, k, seed).tolist() == want, (n, k, seed)
+
+
+def test_backgrounds_from_blast_tables(tmp_path):
+    """BLAST tables of the background alignments -> per-query background arrays, as
+    `_estimate_bg_for_single_query_blast` would dump them (scores of the tables concatenated in order, then sampled)."""
+    import random
+    from oracle import producer as OP
+    from ortho2align_b200 import producer, synth
+    rng = np.random.default_rng(6)
+    tables, owner = [], []
+    for q in range(5):
+        for _ in range(int(rng.integers(1, 4))):
+            tables.append(synth.blast_tabular(*synth.relative_hits(rng, int(rng.integers(0, 90)), 3000, 50_000)))
+            owner.append(q)
+    bg_off, bg, found = producer.backgrounds_from_tables(tables, owner, 6, observations=70, seed=3, threads=2)
+    assert len(bg_off) == 7 and found[5] == 0 and bg_off[6] == bg_off[5]
+    for q in range(5):
+        scores = [h[4] for t, o in zip(tables, owner) if o == q for h in OP.parse_blast(t)["hsps"]]
+        if len(scores) > 70:
+            r = random.Random()
+            r.seed(3)
+            scores = r.sample(scores, 70)
+        assert bg[bg_off[q]:bg_off[q + 1]].tolist() == scores and found[q] >= len(scores)
 
 
 def test_oracle_cut_is_thread_count_independent_and_ordered():
