@@ -57,6 +57,8 @@ struct o2a_ctx {
     bool coords_zero_copy = false;   // qstart..send read in place from pinned, device-mapped host memory
     // chunk view [vl0, vl1) lncRNAs / [va0, va1) alignments the stage launchers work on (whole batch by default)
     long long vl0 = 0, vl1 = 0, va0 = 0, va1 = 0;
+    cudaStream_t aux_stream = nullptr;       // kernels over disjoint alignment classes run beside the main stream
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     cudaStream_t copy_stream = nullptr;      // host path: H2D of chunk c+1 overlaps the kernels of chunk c
     cudaEvent_t copy_ev[16] = {};
     int pipelined_chunks = 0;
@@ -242,6 +244,13 @@ extern "C" int o2a_create(o2a_ctx** out, int device)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return O2A_ECUDA; }
     for (int i = 0; i < N_EVENTS; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    {   // highest priority: its few CTAs are placed before the main stream's machine-filling grids
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi);
+    }
+    cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
     for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
     for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->cut_ev[i]);
     *out = ctx;
@@ -281,6 +290,9 @@ extern "C" void o2a_destroy(o2a_ctx* ctx)
     for (int i = 0; i < 16; ++i) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
     for (int i = 0; i < 5; ++i) if (ctx->cut_ev[i]) cudaEventDestroy(ctx->cut_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -472,12 +484,18 @@ static int run_score(o2a_ctx* ctx)
     A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
     // warp variant: alignments with <= 256 survivors; CTA variant: the rest (up to RANK_SMALL_MAX in shared
     // memory, beyond that p only + k_rank_big)
+    // (the two variants own disjoint alignments: the CTA variant runs beside the warp variant on the second stream)
+    const bool fork = b.max_aln_hsps > 256;
+    if (fork) {
+        CU(cudaEventRecord(ctx->aux_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+        k_pq<64, 14, 256, RANK_SMALL_MAX, 256, 128, TBL_SMEM_MAX><<<grid_for(ctx, na, 14), 64, 0, ctx->aux_stream>>>(A);
+        LAUNCH_CHECK();
+        CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+    }
     k_pq<32, 32, 0, 256, 128, 32, 128><<<grid_for(ctx, na, 32), 32, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
-    if (b.max_aln_hsps > 256) {
-        k_pq<64, 14, 256, RANK_SMALL_MAX, 256, 128, TBL_SMEM_MAX><<<grid_for(ctx, na, 14), 64, 0, ctx->stream>>>(A);
-        LAUNCH_CHECK();
-    }
+    if (fork) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
     if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
         int g2 = grid_for(ctx, b.n_aln, 2);
         r = ensure_sort_scratch(ctx, g2, b.max_aln_hsps);
@@ -524,11 +542,22 @@ static int run_chain(o2a_ctx* ctx)
             int r = stage_event(ctx, O2A_STAGE_CHAIN);
             if (r) return r;
         }
-        k_chain_warp<<<grid_for(ctx, (na + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0, ctx->stream>>>(A);
-        LAUNCH_CHECK();
-        if (b.max_aln_hsps > CHAIN_WARP_MAX) {
+        // The few alignments beyond the warp path (queued by the gather) are chained beside it: k_chain_small goes
+        // first on the main stream (a grid of mostly idle CTAs around ~10^2 long serial ones) and the machine-filling
+        // k_chain_warp follows on the second stream as soon as the gather is done, not after k_chain_small.
+        const bool fork = b.max_aln_hsps > CHAIN_WARP_MAX;
+        if (fork) {
+            CU(cudaEventRecord(ctx->aux_fork, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
             k_chain_small<<<grid_for(ctx, na, 8), CHAIN_THREADS, 0, ctx->stream>>>(A);
             LAUNCH_CHECK();
+        }
+        k_chain_warp<<<grid_for(ctx, (na + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0,
+                       fork ? ctx->aux_stream : ctx->stream>>>(A);
+        LAUNCH_CHECK();
+        if (fork) {
+            CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
         }
         if (b.max_aln_hsps > CHAIN_SMALL_MAX) {
             int g2 = grid_for(ctx, b.n_aln, 2);

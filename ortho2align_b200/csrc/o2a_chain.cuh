@@ -187,41 +187,56 @@ k_gather_retained(ChainArgs A)
     for (long long a = warp; a < A.n_aln; a += nwarps) {
         const int r = A.n_keep[a];
         if (r == 0) continue;
+        // alignments too large for the warp path are queued here, so that k_chain_small can run beside k_chain_warp
+        if (r > CHAIN_WARP_MAX && lane == 0) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
         const long long h0 = A.hsp_off[a];
         const int ns = A.n_surv[a];
         int got = 0;
-        for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
-            const int k = k0 + lane;
-            const bool keep = (k < ns) && A.surv_keep[h0 + k];
-            const unsigned b = __ballot_sync(FULL_MASK, keep);
-            if (keep) {
-                const long long pos = h0 + got + __popc(b & lanemask_lt());
-                const long long h = h0 + A.surv_idx[h0 + k];
-                int4 c;
-                if (A.coords4) c = A.coords4[h];
-                else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
-                A.ret_coord[pos] = c; A.ret_score[pos] = A.surv_x[h0 + k]; A.ret_slot[pos] = k;
+        // keep flags of up to 128 survivors per round, all four loads in flight before the first use
+        for (int k0 = 0; k0 < ns && got < r; k0 += 128) {
+            bool keep[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 32 + lane;
+                keep[u] = (k < ns) && A.surv_keep[h0 + k];
             }
-            got += __popc(b);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 32 + lane;
+                const unsigned b = __ballot_sync(FULL_MASK, keep[u]);
+                if (keep[u]) {
+                    const long long pos = h0 + got + __popc(b & lanemask_lt());
+                    const long long h = h0 + A.surv_idx[h0 + k];
+                    int4 c;
+                    if (A.coords4) c = A.coords4[h];
+                    else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
+                    A.ret_coord[pos] = c; A.ret_score[pos] = A.surv_x[h0 + k]; A.ret_slot[pos] = k;
+                }
+                got += __popc(b);
+            }
         }
     }
 }
 
 // Warp path: one warp per alignment with at most CHAIN_WARP_MAX retained HSPs (the common case:
-// ~10-20 retained of ~130 survivors). Everything lives in the warp's slice of shared memory, the
-// begin/end sentinels are stored as ordinary vertices (64-bit coordinates), lane i owns vertex i;
-// the push DP walks the vertices in list order with the lanes on the window.
+// ~10-20 retained of ~130 survivors). Everything lives in the warp's slice of shared memory; the
+// begin/end sentinels are stored as ordinary vertices (64-bit coordinates). The two orientations are
+// independent graphs (alignment.py:1015-1030) and are chained AT THE SAME TIME: their vertices sit in
+// consecutive index ranges [0, N0) and [N0, N0 + N1), lanes 0-15 push the window of the direct
+// graph's vertex `step` while lanes 16-31 push the reverse graph's, so the serial part of the DP is
+// max(N0, N1) steps instead of N0 + N1.
 constexpr int CHAINW_WARPS = 4;
 
 __global__ void __launch_bounds__(CHAINW_WARPS * 32)
 k_chain_warp(ChainArgs A)
 {
-    constexpr int C = CHAIN_WARP_MAX, V = CHAIN_WARP_MAX + 2;
+    constexpr int C = CHAIN_WARP_MAX, V = CHAIN_WARP_MAX + 4;
     __shared__ long long s_qs[CHAINW_WARPS][V], s_qe[CHAINW_WARPS][V], s_ss[CHAINW_WARPS][V], s_se[CHAINW_WARPS][V];
     __shared__ double s_sc[CHAINW_WARPS][V], s_total[CHAINW_WARPS][V];
     __shared__ int s_id[CHAINW_WARPS][V], s_prev[CHAINW_WARPS][V], s_f[CHAINW_WARPS][V];
     __shared__ int s_chain[CHAINW_WARPS][2][C];
     const int lane = lane_id(), w = warp_id();
+    const int half = lane >> 4, hl = lane & 15;          // half 0: direct graph, half 1: reverse graph
     const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
     const double POS_INF = __longlong_as_double(0x7ff0000000000000ll);
     const long long nwarps_total = (long long)gridDim.x * CHAINW_WARPS;
@@ -231,10 +246,7 @@ k_chain_warp(ChainArgs A)
     for (long long a = (long long)blockIdx.x * CHAINW_WARPS + w; a < A.n_aln; a += nwarps_total) {
         const int r = A.n_keep[a];
         const int l = A.aln_lnc[a];
-        if (r > C) {
-            if (lane == 0) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
-            continue;
-        }
+        if (r > C) continue;                              // queued for k_chain_small by k_gather_retained
         if (r == 0 || A.lnc_status[l] >= 2) {
             if (lane == 0) {
                 A.chain_len[a] = 0; A.chain_orient[a] = 1; A.chain_score[a] = NEG_INF;
@@ -243,8 +255,7 @@ k_chain_warp(ChainArgs A)
             continue;
         }
         const long long h0 = A.hsp_off[a];
-        // lane p owns the p-th retained HSP (list order); my_slot = its position in the retained list
-        const int my_slot = lane;
+        // lane p owns the p-th retained HSP (list order)
         int qs = 0, qe = 0, ss = 0, se = 0; double sc = 0.0; bool dir = false; bool bad = false;
         if (lane < r) {
             const int4 c = A.ret_coord[h0 + lane];
@@ -262,106 +273,119 @@ k_chain_warp(ChainArgs A)
         }
         const long long qlen = A.qlen[a], slen = A.slen[a];
         const double G = (double)A.gapopen, E = (double)A.gapextend;
-        double sco0 = NEG_INF, sco1 = NEG_INF, key0 = 0.0, key1 = 0.0; int len0 = 0, len1 = 0;
-#pragma unroll 1
-        for (int o = 0; o < 2; ++o) {
-            const bool want_dir = (o == 0);
-            const bool mine = (lane < r) && (dir == want_dir);
-            const unsigned members = __ballot_sync(FULL_MASK, mine);
-            const int n_o = __popc(members);
-            if (n_o == 0) continue;
-            const int N = n_o + 2;
-            // stable rank by (qstart, sstart, list order) among the members
-            int rank = 0;
-            for (unsigned mm = members; mm; mm &= mm - 1) {
-                const int q = __ffs(mm) - 1;
-                const int oqs = __shfl_sync(FULL_MASK, qs, q), oss = __shfl_sync(FULL_MASK, ss, q);
-                rank += (oqs < qs) || (oqs == qs && (oss < ss || (oss == ss && q < lane)));
+        const unsigned mem_d = __ballot_sync(FULL_MASK, lane < r && dir);
+        const unsigned mem_r = __ballot_sync(FULL_MASK, lane < r && !dir);
+        const int n0 = __popc(mem_d), n1 = __popc(mem_r);
+        const int N0 = n0 ? n0 + 2 : 0, N1 = n1 ? n1 + 2 : 0;     // vertices per graph incl. sentinels
+        // stable rank by (qstart, sstart, list order) among the HSPs of the own orientation
+        int rank = 0;
+        for (int q = 0; q < r; ++q) {
+            const int oqs = __shfl_sync(FULL_MASK, qs, q), oss = __shfl_sync(FULL_MASK, ss, q);
+            const bool same = (((mem_d >> q) & 1u) != 0) == dir;
+            rank += same && ((oqs < qs) || (oqs == qs && (oss < ss || (oss == ss && q < lane))));
+        }
+        __syncwarp();
+        if (lane < r) {
+            const int v = (dir ? 0 : N0) + rank + 1;
+            Qs[v] = qs; Qe[v] = qe; Ss[v] = ss; Se[v] = se; Sc[v] = sc; Id[v] = lane;
+        }
+        if (hl == 0) {           // sentinels (alignment.py:893-902): lane 0 for the direct graph, lane 16 for the reverse one
+            const int Nn = half ? N1 : N0, base = half ? N0 : 0;
+            if (Nn) {
+                const bool d = half == 0;
+                Qs[base] = 0; Qe[base] = 0; Ss[base] = d ? 0 : slen; Se[base] = Ss[base]; Sc[base] = 0.0;
+                const int e = base + Nn - 1;
+                Qs[e] = qlen; Qe[e] = qlen; Ss[e] = d ? slen : 0; Se[e] = Ss[e]; Sc[e] = 0.0;
             }
-            __syncwarp();
-            if (mine) {
-                const int v = rank + 1;
-                Qs[v] = qs; Qe[v] = qe; Ss[v] = ss; Se[v] = se; Sc[v] = sc; Id[v] = my_slot;
-            }
-            if (lane == 0) {     // sentinels: alignment.py:893-902
-                Qs[0] = 0; Qe[0] = 0; Ss[0] = want_dir ? 0 : slen; Se[0] = Ss[0]; Sc[0] = 0.0;
-                Qs[N - 1] = qlen; Qe[N - 1] = qlen; Ss[N - 1] = want_dir ? slen : 0; Se[N - 1] = Ss[N - 1]; Sc[N - 1] = 0.0;
-            }
-            __syncwarp();
-            // HSP.precede (alignment.py:137-168); sentinel-sentinel pairs use the reverse rule (both None)
-#define O2A_PREC(i, j) ((Qe[i] < Qs[j]) && ((want_dir && !((i) == 0 && (j) == N - 1)) ? (Se[i] < Ss[j]) : (Se[i] > Ss[j])))
-            // f(i): lanes 0..N-1 each scan forward from their own vertex
-            for (int i = lane; i < N; i += 32) {
-                int fi = N;
-                for (int j = i + 1; j < N; ++j) if (O2A_PREC(i, j)) { fi = j; break; }
-                F[i] = fi;
-                Tot[i] = i == 0 ? 0.0 : POS_INF;
-                Prev[i] = -1;
-            }
-            __syncwarp();
-            for (int i = 0; i < N - 1; ++i) {
-                const double ti = Tot[i];
-                const int fi = F[i];
-                if (fi < N && ti < POS_INF) {
-                    const int gi = F[fi] < N ? F[fi] : N;
-                    for (int j = fi + lane; j < gi; j += 32) {
-                        if (O2A_PREC(i, j)) {
-                            // HSP.distance (alignment.py:170-217) + HSPVertex._relax (:388-411)
-                            const long long qd = Qs[j] - Qe[i];
-                            const long long sd = want_dir ? (Ss[j] - Se[i]) : (Se[i] - Ss[j]);
-                            const double wgt = __dsub_rn(__dadd_rn(G, __dmul_rn(E, (double)(qd + sd))), Sc[j]);
-                            const double nsc = __dadd_rn(ti, wgt);
-                            if (Tot[j] > nsc) { Tot[j] = nsc; Prev[j] = i; }
+        }
+        __syncwarp();
+        // HSP.precede (alignment.py:137-168) inside graph [base, end); the begin-end pair uses the reverse rule (both None)
+#define O2A_PREC(isdir, base, end, i, j) ((Qe[i] < Qs[j]) && (((isdir) && !((i) == (base) && (j) == (end) - 1)) ? (Se[i] < Ss[j]) : (Se[i] > Ss[j])))
+        // f(i): every vertex scans forward inside its own graph
+        for (int v = lane; v < N0 + N1; v += 32) {
+            const bool isd = v < N0;
+            const int base = isd ? 0 : N0, end = isd ? N0 : N0 + N1;
+            int fi = end;
+            for (int j = v + 1; j < end; ++j) if (O2A_PREC(isd, base, end, v, j)) { fi = j; break; }
+            F[v] = fi;
+            Tot[v] = v == base ? 0.0 : POS_INF;
+            Prev[v] = -1;
+        }
+        __syncwarp();
+        {
+            const bool isd = half == 0;
+            const int Nn = isd ? N0 : N1, base = isd ? 0 : N0, end = base + Nn;
+            const int steps = max(N0, N1) - 1;
+            for (int step = 0; step < steps; ++step) {
+                if (step < Nn - 1) {
+                    const int i = base + step;
+                    const double ti = Tot[i];
+                    const int fi = F[i];
+                    if (fi < end && ti < POS_INF) {
+                        const int gi = F[fi];                    // f(f(i)), `end` if none
+                        for (int j = fi + hl; j < gi; j += 16) {
+                            if (O2A_PREC(isd, base, end, i, j)) {
+                                // HSP.distance (alignment.py:170-217) + HSPVertex._relax (:388-411)
+                                const long long qd = Qs[j] - Qe[i];
+                                const long long sd = isd ? (Ss[j] - Se[i]) : (Se[i] - Ss[j]);
+                                const double wgt = __dsub_rn(__dadd_rn(G, __dmul_rn(E, (double)(qd + sd))), Sc[j]);
+                                const double nsc = __dadd_rn(ti, wgt);
+                                if (Tot[j] > nsc) { Tot[j] = nsc; Prev[j] = i; }
+                            }
                         }
                     }
                 }
                 __syncwarp();
             }
-#undef O2A_PREC
-            const double sco = -Tot[N - 1];
-            // backtrack (alignment.py:1007-1013): lane 0 walks, then the chain is reversed in place
-            int ln = 0;
-            if (lane == 0) {
-                int cur = N - 1;
-                while (Prev[cur] != -1) { cur = Prev[cur]; if (cur != 0) F[ln++] = cur; }   // F reused: reversed chain
-            }
-            ln = __shfl_sync(FULL_MASK, ln, 0);
-            __syncwarp();
-            // key of get_best_orthologs (pipeline.py:981-987) from the chain's query coordinates
-            double key = 0.0;
-            {
-                int v = lane < ln ? F[ln - 1 - lane] : 0;
-                if (lane < ln) s_chain[w][o][lane] = Id[v];
-                long long blen = 0, lo = INT64_MAX, hi = INT64_MIN;
-                if (lane < ln) {
-                    long long d = Qe[v] - Qs[v]; blen = d < 0 ? -d : d;
-                    lo = Qs[v] < Qe[v] ? Qs[v] : Qe[v]; hi = Qs[v] > Qe[v] ? Qs[v] : Qe[v];
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    blen += __shfl_xor_sync(FULL_MASK, blen, d);
-                    long long olo = __shfl_xor_sync(FULL_MASK, lo, d), ohi = __shfl_xor_sync(FULL_MASK, hi, d);
-                    lo = olo < lo ? olo : lo; hi = ohi > hi ? ohi : hi;
-                }
-                if (A.best_value == 0) key = (double)blen;
-                else if (A.best_value == 1) key = ln ? (double)(hi - lo) : 0.0;
-                else if (A.best_value == 2) key = (double)ln;
-                else {          // weight: Python sum() left to right (genomicranges.py:1225)
-                    double wsum = 0.0;
-                    for (int c = ln - 1; c >= 0; --c) wsum = __dadd_rn(wsum, Sc[F[c]]);
-                    key = wsum;
-                }
-            }
-            if (o == 0) { sco0 = sco; len0 = ln; key0 = key; } else { sco1 = sco; len1 = ln; key1 = key; }
-            __syncwarp();
         }
+#undef O2A_PREC
+        // per graph (half-warp): score, backtrack, key of get_best_orthologs
+        const bool isd = half == 0;
+        const int Nn = isd ? N0 : N1, base = isd ? 0 : N0, end = base + Nn;
+        const double sco_h = Nn ? -Tot[end - 1] : NEG_INF;
+        int ln = 0;
+        if (hl == 0 && Nn) {     // backtrack (alignment.py:1007-1013): reversed chain into F[base..]
+            int cur = end - 1;
+            while (Prev[cur] != -1) { cur = Prev[cur]; if (cur != base) F[base + ln++] = cur; }
+        }
+        ln = __shfl_sync(FULL_MASK, ln, half << 4);
+        __syncwarp();
+        double key = 0.0;
+        {
+            long long blen = 0, lo = INT64_MAX, hi = INT64_MIN;
+            for (int c = hl; c < ln; c += 16) {
+                const int v = F[base + ln - 1 - c];
+                s_chain[w][half][c] = Id[v];
+                const long long d = Qe[v] - Qs[v];
+                blen += d < 0 ? -d : d;
+                lo = min(lo, min(Qs[v], Qe[v])); hi = max(hi, max(Qs[v], Qe[v]));
+            }
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) {        // stays inside the half-warp
+                blen += __shfl_xor_sync(FULL_MASK, blen, d);
+                const long long olo = __shfl_xor_sync(FULL_MASK, lo, d), ohi = __shfl_xor_sync(FULL_MASK, hi, d);
+                lo = olo < lo ? olo : lo; hi = ohi > hi ? ohi : hi;
+            }
+            if (A.best_value == 0) key = (double)blen;
+            else if (A.best_value == 1) key = ln ? (double)(hi - lo) : 0.0;
+            else if (A.best_value == 2) key = (double)ln;
+            else {              // weight: Python sum() left to right (genomicranges.py:1225)
+                double wsum = 0.0;
+                for (int c = ln - 1; c >= 0; --c) wsum = __dadd_rn(wsum, Sc[F[base + c]]);
+                key = wsum;
+            }
+        }
+        const double sco0 = __shfl_sync(FULL_MASK, sco_h, 0), sco1 = __shfl_sync(FULL_MASK, sco_h, 16);
+        const double key0 = __shfl_sync(FULL_MASK, key, 0), key1 = __shfl_sync(FULL_MASK, key, 16);
+        const int len0 = __shfl_sync(FULL_MASK, ln, 0), len1 = __shfl_sync(FULL_MASK, ln, 16);
+        __syncwarp();
         const int pick = (sco0 > sco1) ? 0 : 1;          // alignment.py:1043-1046
-        const int ln = pick ? len1 : len0;
-        for (int c = lane; c < ln; c += 32) A.chain_slot[h0 + c] = s_chain[w][pick][c];
+        const int lnp = pick ? len1 : len0;
+        for (int c = lane; c < lnp; c += 32) A.chain_slot[h0 + c] = s_chain[w][pick][c];
         if (lane == 0) {
-            A.chain_len[a] = ln; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = pick ? sco1 : sco0;
+            A.chain_len[a] = lnp; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = pick ? sco1 : sco0;
             A.orient_scores[2 * a] = sco0; A.orient_scores[2 * a + 1] = sco1;
-            A.best_key[a] = ln ? (pick ? key1 : key0) : 0.0;
+            A.best_key[a] = lnp ? (pick ? key1 : key0) : 0.0;
         }
         __syncwarp();
     }
