@@ -192,7 +192,8 @@ k_gather_retained(ChainArgs A)
         const long long h0 = A.hsp_off[a];
         const int ns = A.n_surv[a];
         int got = 0;
-        // keep flags of up to 128 survivors per round, all four loads in flight before the first use
+        // up to 128 survivors per round; each dependent level (keep flags -> survivor index -> coordinates / score)
+        // is issued for all four rows before the next level uses it
         for (int k0 = 0; k0 < ns && got < r; k0 += 128) {
             bool keep[4];
 #pragma unroll
@@ -200,19 +201,28 @@ k_gather_retained(ChainArgs A)
                 const int k = k0 + u * 32 + lane;
                 keep[u] = (k < ns) && A.surv_keep[h0 + k];
             }
+            long long pos[4], h[4];
+            double x[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int k = k0 + u * 32 + lane;
                 const unsigned b = __ballot_sync(FULL_MASK, keep[u]);
-                if (keep[u]) {
-                    const long long pos = h0 + got + __popc(b & lanemask_lt());
-                    const long long h = h0 + A.surv_idx[h0 + k];
-                    int4 c;
-                    if (A.coords4) c = A.coords4[h];
-                    else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
-                    A.ret_coord[pos] = c; A.ret_score[pos] = A.surv_x[h0 + k]; A.ret_slot[pos] = k;
-                }
+                pos[u] = h0 + got + __popc(b & lanemask_lt());
                 got += __popc(b);
+                h[u] = keep[u] ? h0 + A.surv_idx[h0 + k] : 0;
+                x[u] = keep[u] ? A.surv_x[h0 + k] : 0.0;
+            }
+            int4 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (keep[u]) {
+                    if (A.coords4) c[u] = A.coords4[h[u]];
+                    else { c[u].x = A.qstart[h[u]]; c[u].y = A.qend[h[u]]; c[u].z = A.sstart[h[u]]; c[u].w = A.send[h[u]]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (keep[u]) { A.ret_coord[pos[u]] = c[u]; A.ret_score[pos[u]] = x[u]; A.ret_slot[pos[u]] = k0 + u * 32 + lane; }
             }
         }
     }

@@ -558,14 +558,20 @@ k_fit_count(FitArgs A)
             for (long long i = tid; i < head; i += FITC_THREADS) O2A_CNT(x[i]);
             const int4* x4 = reinterpret_cast<const int4*>(x + head);
             const int n4 = (int)((n - head) / PER);
-            for (int i = tid; i < n4; i += FITC_THREADS) {
-                const int4 v = x4[i];
-                if (PER == 4) { O2A_CNT(v.x); O2A_CNT(v.y); O2A_CNT(v.z); O2A_CNT(v.w); }
-                else {
-                    O2A_CNT((int)(short)(v.x & 0xffff)); O2A_CNT(v.x >> 16); O2A_CNT((int)(short)(v.y & 0xffff)); O2A_CNT(v.y >> 16);
-                    O2A_CNT((int)(short)(v.z & 0xffff)); O2A_CNT(v.z >> 16); O2A_CNT((int)(short)(v.w & 0xffff)); O2A_CNT(v.w >> 16);
-                }
+#define O2A_CNT16(v) do { if (PER == 4) { O2A_CNT((v).x); O2A_CNT((v).y); O2A_CNT((v).z); O2A_CNT((v).w); } else {                      \
+                    O2A_CNT((int)(short)((v).x & 0xffff)); O2A_CNT((v).x >> 16); O2A_CNT((int)(short)((v).y & 0xffff)); O2A_CNT((v).y >> 16); \
+                    O2A_CNT((int)(short)((v).z & 0xffff)); O2A_CNT((v).z >> 16); O2A_CNT((int)(short)((v).w & 0xffff)); O2A_CNT((v).w >> 16); } } while (0)
+            int i = tid;
+            // eight 16-byte loads in flight per thread before the first shared-memory atomic
+            for (; i + 7 * FITC_THREADS < n4; i += 8 * FITC_THREADS) {
+                int4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = x4[i + u * FITC_THREADS];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) O2A_CNT16(v[u]);
             }
+            for (; i < n4; i += FITC_THREADS) { const int4 v = x4[i]; O2A_CNT16(v); }
+#undef O2A_CNT16
             for (long long i = head + (long long)n4 * PER + tid; i < n; i += FITC_THREADS) O2A_CNT(x[i]);
 #undef O2A_CNT
             if (oor) s_oor = 1;
