@@ -31,7 +31,8 @@ from ortho2align_b200 import synth  # noqa: E402
 from ortho2align_b200.columnar import concat_batches  # noqa: E402
 
 METRIC = "HSPs/sec through build_orthologs+best-ortholog"
-LAYOUTS = {0: "float64 scores, int32 background", 16: "int16 scores + exception lists, int16 background (lossless)",
+LAYOUTS = {0: "float64 scores, int32 background", 8: "int8 scores + exception lists, int8 background (lossless)",
+           16: "int16 scores + exception lists, int16 background (lossless)",
            32: "int32 scores + exception lists, int32 background (lossless)"}
 UNIT = "HSPs/s"
 CONFIG_NAMES = {1: "C1 strRNA 96 lncRNAs, 1k bg", 2: "C2 20k lncRNAs x 5 regions x ~2k HSPs, 10k bg/lncRNA",
@@ -166,11 +167,12 @@ def main():
     ap.add_argument("--ref-lnc", type=int, default=20000, help="lncRNAs per step of --impl reference")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--score-bits", type=int, default=0, choices=[0, 16, 32],
+    ap.add_argument("--score-bits", type=int, default=0, choices=[0, 8, 16, 32],
                     help="score layout of the device-resident arm: 0 = float64 (the reference's dtype), "
-                         "16/32 = lossless narrow ints + exception lists")
-    ap.add_argument("--e2e-score-bits", type=int, default=16, choices=[0, 16, 32],
-                    help="score layout of the pinned host buffers of the e2e arm (PCIe-bound: narrow is faster)")
+                         "8/16/32 = lossless narrow ints + exception lists")
+    ap.add_argument("--e2e-score-bits", type=int, default=8, choices=[0, 8, 16, 32],
+                    help="score layout of the pinned host buffers of the e2e arm (PCIe-bound: narrow is faster; every "
+                         "width is lossless — scores that do not fit go to per-alignment exception lists as float64)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -207,7 +209,7 @@ def main():
     with_kde = args.fitter == "kde"
 
     # ---------------- device-resident arm (value) ----------------
-    dbatch = DeviceBatch(batch, dev, aos=True, score_bits=args.score_bits, bg_bits=16 if args.score_bits == 16 else 32)
+    dbatch = DeviceBatch(batch, dev, aos=True, score_bits=args.score_bits, bg_bits=args.score_bits if args.score_bits in (8, 16) else 32)
     dstruct = dbatch.struct(with_kde)
     # the only collective of the path: every rank learns every shard's result counts (NCCL all_gather, 40 B per
     # rank and step). It is issued asynchronously from its own ring slot, so the next step's kernels do not wait
@@ -271,7 +273,7 @@ def main():
     peak, peak_src = measured_peak()
     # k_filter: score read per HSP (8 B float64, or 2/4 B narrow + 12 B per exception entry) +
     # (4 B position + 8 B score) written per survivor
-    score_bytes = {0: 8.0, 16: 2.0, 32: 4.0}[args.score_bits]
+    score_bytes = {0: 8.0, 8: 1.0, 16: 2.0, 32: 4.0}[args.score_bits]
     n_exc = int(dbatch.t["exc_pos"].numel()) if args.score_bits else 0
     alg_bytes = score_bytes * batch.n_hsp + 12.0 * n_exc + 12.0 * c.n_survivors
     avg_score_ms = float(np.mean(score_ms))
@@ -312,9 +314,9 @@ def main():
     else:
         keep_alive["score"] = pin(batch.score)
         fields["score"] = keep_alive["score"].numpy()
-    if narrow_bits == 16:
-        keep_alive["bg16"] = pin(batch.bg16())
-        batch._bg16 = None
+    if narrow_bits in (8, 16):
+        keep_alive["bg16"] = pin(batch.bg_narrow(narrow_bits))
+        batch._bg_narrow = None
         bg16 = keep_alive["bg16"].numpy()
         fields["bg"] = batch.bg
     else:

@@ -89,13 +89,14 @@ typedef struct o2a_batch {
                                   one 16 B read per retained HSP instead of four (matters for zero-copy
                                   reads from pinned host memory); NULL = use the four SoA arrays */
     /* Optional narrow scores (BLAST raw scores are integers; only HSPs cut at a gene boundary are
-     * fractional, alignment.py:330). score_bits = 16 or 32: `score_q` holds the scores as int16 /
-     * int32; the most negative value marks an HSP whose exact float64 score is listed in the
+     * fractional, alignment.py:330). score_bits = 8, 16 or 32: `score_q` holds the scores as int8 /
+     * int16 / int32; the most negative value marks an HSP whose exact float64 score is listed in the
      * alignment's exception list exc_pos[exc_off[a]..exc_off[a+1]) (ascending HSP positions inside
      * the alignment) / exc_val. score_bits = 0: `score` (float64) is used. Lossless either way. */
     int32_t score_bits;
-    int32_t bg_bits;           /* 0 or 32: `bg` is int32 [n_bg]; 16: `bg` points to int16 [n_bg] */
-    const void    *score_q;    /* [n_hsp] int16 or int32 */
+    int32_t bg_bits;           /* 0 or 32: `bg` is int32 [n_bg]; 16 / 8: `bg` points to int16 / int8 [n_bg]
+                                  (the caller picks a width every background score fits) */
+    const void    *score_q;    /* [n_hsp] int8, int16 or int32 */
     const int64_t *exc_off;    /* [n_aln+1] */
     const int32_t *exc_pos;    /* [n_exc] */
     const double  *exc_val;    /* [n_exc] */

@@ -96,22 +96,29 @@ class ColumnarBatch:
             self._coords4 = c
         return c
 
-    def bg16(self):
-        """int16 copy of the background for `o2a_batch.bg_bits = 16` (BLAST raw scores fit easily)."""
-        b = getattr(self, "_bg16", None)
-        if b is None or len(b) != self.n_bg:
-            if self.n_bg and (self.bg.max() > 32767 or self.bg.min() < -32768):
-                raise PackError("background scores do not fit int16")
-            b = self.bg.astype(np.int16)
-            self._bg16 = b
+    def bg_narrow(self, bits):
+        """int16 / int8 copy of the background for `o2a_batch.bg_bits = 16 | 8`; PackError if a score does not fit
+        (BLAST raw scores of background alignments are small: int8 holds them in practice, int16 always)."""
+        dt = {8: np.int8, 16: np.int16}[bits]
+        cache = getattr(self, "_bg_narrow", None)
+        if cache is not None and cache[0] == bits and len(cache[1]) == self.n_bg:
+            return cache[1]
+        info = np.iinfo(dt)
+        if self.n_bg and (self.bg.max() > info.max or self.bg.min() < info.min):
+            raise PackError(f"background scores do not fit int{bits}")
+        b = self.bg.astype(dt)
+        self._bg_narrow = (bits, b)
         return b
 
+    def bg16(self):
+        return self.bg_narrow(16)
+
     def quantized_scores(self, bits=16):
-        """Lossless narrow encoding of `score` for `o2a_batch.score_q` (score_bits = 16 | 32):
+        """Lossless narrow encoding of `score` for `o2a_batch.score_q` (score_bits = 8 | 16 | 32):
         integral scores inside the integer type as-is; every other HSP (fractional score of a cut
         HSP, out-of-range value) gets the sentinel (most negative value) and an entry in its
         alignment's exception list. Returns (score_q, exc_off, exc_pos, exc_val)."""
-        dt = {16: np.int16, 32: np.int32}[bits]
+        dt = {8: np.int8, 16: np.int16, 32: np.int32}[bits]
         info = np.iinfo(dt)
         sc = self.score
         with np.errstate(invalid="ignore"):

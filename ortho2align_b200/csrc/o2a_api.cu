@@ -421,13 +421,15 @@ static int run_fit(o2a_ctx* ctx)
         A.fc_n = P<int>(ctx->fc_n) + l0;
         A.list = P<int>(ctx->fit_list); A.list_n = P<int>(ctx->fit_list_n);
         const int gc = grid_for(ctx, nl, 8);
-        if (b.bg_bits == 16) k_fit_count<short><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
+        if (b.bg_bits == 8) k_fit_count<signed char><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
+        else if (b.bg_bits == 16) k_fit_count<short><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
         else k_fit_count<int><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
         k_fit_hist_tail<<<grid_for(ctx, (nl + FITW_WARPS - 1) / FITW_WARPS, 8), FITW_WARPS * 32, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
     }
-    if (b.bg_bits == 16) k_fit<short><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
+    if (b.bg_bits == 8) k_fit<signed char><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
+    else if (b.bg_bits == 16) k_fit<short><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     else k_fit<int><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
     return 0;
@@ -455,7 +457,12 @@ static int run_score(o2a_ctx* ctx)
     if (na <= 0) return stage_event(ctx, O2A_STAGE_PQ);
     const long long* hsp_off_v = (const long long*)b.hsp_off + a0;
     const int* aln_lnc_v = P<int>(ctx->aln_lnc) + a0;
-    if (b.score_bits == 16)
+    if (b.score_bits == 8)
+        k_filter_q<signed char><<<grid_for(ctx, na, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
+            na, hsp_off_v, aln_lnc_v, (const signed char*)b.score_q, (const long long*)b.exc_off + a0,
+            b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
+            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
+    else if (b.score_bits == 16)
         k_filter_q<short><<<grid_for(ctx, na, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
             na, hsp_off_v, aln_lnc_v, (const short*)b.score_q, (const long long*)b.exc_off + a0,
             b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
@@ -639,10 +646,10 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         // the reference pickles file names to workers which json.load them (pipeline.py:743-754);
         // here the columnar arrays cross PCIe once
         if ((r = upload(ctx, ctx->in_bg_off, batch->bg_off, (size_t)batch->n_lnc + 1, &b.bg_off))) return r;
-        if (batch->bg_bits != 0 && batch->bg_bits != 16 && batch->bg_bits != 32) { ctx->err = "bg_bits must be 0, 16 or 32"; return O2A_EINVAL; }
+        if (batch->bg_bits != 0 && batch->bg_bits != 8 && batch->bg_bits != 16 && batch->bg_bits != 32) { ctx->err = "bg_bits must be 0, 8, 16 or 32"; return O2A_EINVAL; }
         {
             const void* d8 = nullptr;
-            const size_t esz = batch->bg_bits == 16 ? 2 : 4;
+            const size_t esz = batch->bg_bits == 8 ? 1 : batch->bg_bits == 16 ? 2 : 4;
             if ((r = upload_bulk(ctx, ctx->in_bg, batch->bg, (size_t)batch->n_bg, esz, SLICE_BG, deferred, &d8))) return r;
             b.bg = (const int32_t*)d8;
         }
@@ -653,7 +660,7 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         if ((r = upload(ctx, ctx->in_hsp_off, batch->hsp_off, (size_t)batch->n_aln + 1, &b.hsp_off))) return r;
         if ((r = upload(ctx, ctx->in_qlen, batch->qlen, (size_t)batch->n_aln, &b.qlen))) return r;
         if ((r = upload(ctx, ctx->in_slen, batch->slen, (size_t)batch->n_aln, &b.slen))) return r;
-        if (batch->score_bits == 16 || batch->score_bits == 32) {
+        if (batch->score_bits == 8 || batch->score_bits == 16 || batch->score_bits == 32) {
             if (!batch->score_q || !batch->exc_off) { ctx->err = "score_bits set but score_q/exc_off missing"; return O2A_EINVAL; }
             const size_t esz = batch->score_bits / 8;
             const void* d8 = nullptr;
@@ -666,7 +673,7 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
             if ((r = upload_bulk(ctx, ctx->in_exc_val, batch->exc_val, n_exc, sizeof(double), SLICE_EXC, deferred, &d8))) return r;
             b.exc_val = (const double*)d8;
             b.score = nullptr;
-        } else if (batch->score_bits != 0) { ctx->err = "score_bits must be 0, 16 or 32"; return O2A_EINVAL; }
+        } else if (batch->score_bits != 0) { ctx->err = "score_bits must be 0, 8, 16 or 32"; return O2A_EINVAL; }
         else {
             const void* d8 = nullptr;
             if ((r = upload_bulk(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, sizeof(double), SLICE_HSP, deferred, &d8))) return r;

@@ -207,6 +207,14 @@ __device__ __forceinline__ void fit_publish_thr(const FitArgs& A, long long l, d
     for (long long a = A.aln_off[l] + threadIdx.x; a < A.aln_off[l + 1]; a += blockDim.x) A.thr_aln[a] = v;
 }
 
+// every background value packed in one 32-bit word of a 16-byte load (BG = int, short or signed char)
+#define O2A_BG_WORD(OP, w) do {                                                                                   \
+        if (PER == 4) { OP(w); }                                                                                  \
+        else if (PER == 8) { OP((int)(short)((w) & 0xffff)); OP((w) >> 16); }                                     \
+        else { OP((int)(signed char)((w) & 0xff)); OP((int)(signed char)(((w) >> 8) & 0xff));                     \
+               OP((int)(signed char)(((w) >> 16) & 0xff)); OP((w) >> 24); } } while (0)
+#define O2A_BG_VEC(OP, v) do { O2A_BG_WORD(OP, (v).x); O2A_BG_WORD(OP, (v).y); O2A_BG_WORD(OP, (v).z); O2A_BG_WORD(OP, (v).w); } while (0)
+
 // status 4 = value range larger than the counting scratch (max_range)
 template <typename BG>
 __global__ void __launch_bounds__(FIT_THREADS)
@@ -269,13 +277,7 @@ k_fit(FitArgs A)
             const int n4 = (int)((n - head) / PER);
             for (int i = tid; i < n4; i += FIT_THREADS) {
                 const int4 v = x4[i];
-                if (PER == 4) { O2A_FIT_ADD(v.x); O2A_FIT_ADD(v.y); O2A_FIT_ADD(v.z); O2A_FIT_ADD(v.w); }
-                else {
-                    O2A_FIT_ADD((int)(short)(v.x & 0xffff)); O2A_FIT_ADD(v.x >> 16);
-                    O2A_FIT_ADD((int)(short)(v.y & 0xffff)); O2A_FIT_ADD(v.y >> 16);
-                    O2A_FIT_ADD((int)(short)(v.z & 0xffff)); O2A_FIT_ADD(v.z >> 16);
-                    O2A_FIT_ADD((int)(short)(v.w & 0xffff)); O2A_FIT_ADD(v.w >> 16);
-                }
+                O2A_BG_VEC(O2A_FIT_ADD, v);
             }
             for (long long i = head + (long long)n4 * PER + tid; i < n; i += FIT_THREADS) O2A_FIT_ADD(x[i]);
 #undef O2A_FIT_ADD
@@ -558,9 +560,7 @@ k_fit_count(FitArgs A)
             for (long long i = tid; i < head; i += FITC_THREADS) O2A_CNT(x[i]);
             const int4* x4 = reinterpret_cast<const int4*>(x + head);
             const int n4 = (int)((n - head) / PER);
-#define O2A_CNT16(v) do { if (PER == 4) { O2A_CNT((v).x); O2A_CNT((v).y); O2A_CNT((v).z); O2A_CNT((v).w); } else {                      \
-                    O2A_CNT((int)(short)((v).x & 0xffff)); O2A_CNT((v).x >> 16); O2A_CNT((int)(short)((v).y & 0xffff)); O2A_CNT((v).y >> 16); \
-                    O2A_CNT((int)(short)((v).z & 0xffff)); O2A_CNT((v).z >> 16); O2A_CNT((int)(short)((v).w & 0xffff)); O2A_CNT((v).w >> 16); } } while (0)
+#define O2A_CNT16(v) O2A_BG_VEC(O2A_CNT, v)
             int i = tid;
             // eight 16-byte loads in flight per thread before the first shared-memory atomic
             for (; i + 7 * FITC_THREADS < n4; i += 8 * FITC_THREADS) {

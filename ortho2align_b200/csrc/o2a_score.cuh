@@ -111,16 +111,17 @@ k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __re
     }
 }
 
-// Narrow-score variant: integral scores as int16 / int32 (BLAST raw scores are integers; only HSPs
+// Narrow-score variant: integral scores as int8 / int16 / int32 (BLAST raw scores are integers; only HSPs
 // cut at a gene boundary carry fractional scores, alignment.py:330). The sentinel (most negative
 // value of T) marks an HSP whose score is not representable: its exact float64 value sits in the
 // alignment's exception list (exc_pos ascending HSP positions, exc_val). Same ordered compaction as
-// k_filter; one 16-byte load carries 8 (int16) or 4 (int32) scores per lane, `score > thr` is the
+// k_filter; one 16-byte load carries 16 (int8), 8 (int16) or 4 (int32) scores per lane, `score > thr` is the
 // integer test `q > floor(thr)` (the sentinel never passes it), and the few exceptions that DO pass
 // (value > thr) are resolved once per alignment into a tiny shared list that sentinel lanes consult.
 template <typename T> struct QTraits;
 template <> struct QTraits<short> { static constexpr int PER = 8; static constexpr int SENT = -32768; };
 template <> struct QTraits<int> { static constexpr int PER = 4; static constexpr int SENT = INT32_MIN; };
+template <> struct QTraits<signed char> { static constexpr int PER = 16; static constexpr int SENT = -128; };
 
 constexpr int FILTERQ_ROWS = 2;               // 16-byte loads per lane per pass
 constexpr int FILTERQ_THREADS = 64;           // narrow scores: small CTAs, many alignments in flight per SM
@@ -130,6 +131,11 @@ template <typename T>
 __device__ __forceinline__ int q_at(const int4& raw, int c)
 {
     if (sizeof(T) == 4) return c == 0 ? raw.x : c == 1 ? raw.y : c == 2 ? raw.z : raw.w;
+    if (sizeof(T) == 1) {
+        const int ws = c >> 2;
+        const int word = ws == 0 ? raw.x : ws == 1 ? raw.y : ws == 2 ? raw.z : raw.w;
+        return (int)(signed char)((word >> ((c & 3) * 8)) & 0xff);
+    }
     const int wsel = c >> 1;
     const int word = wsel == 0 ? raw.x : wsel == 1 ? raw.y : wsel == 2 ? raw.z : raw.w;
     return (c & 1) ? (word >> 16) : (int)(short)(word & 0xffff);

@@ -38,8 +38,8 @@ class DeviceBatch:
         if aos:
             self.t["coords"] = torch.from_numpy(batch.coords4()).to(device)
         self.bg_bits = bg_bits
-        if bg_bits == 16:
-            self.t["bg"] = torch.from_numpy(batch.bg16()).to(device)
+        if bg_bits in (8, 16):
+            self.t["bg"] = torch.from_numpy(batch.bg_narrow(bg_bits)).to(device)
         self.score_bits = score_bits
         if score_bits:
             q, eo, ep, ev = batch.quantized_scores(score_bits)
@@ -155,9 +155,9 @@ class Engine:
             setattr(s, k, a.ctypes.data)
         s.kde_factor = batch.ensure_kde_factor().ctypes.data if with_kde else None
         s.coords = coords.ctypes.data if coords is not None else None
-        if bg16 is not None:
-            assert bg16.dtype == np.int16 and len(bg16) == batch.n_bg
-            s.bg, s.bg_bits = bg16.ctypes.data, 16
+        if bg16 is not None:           # int16 or int8 copy of the background (ColumnarBatch.bg_narrow)
+            assert bg16.dtype in (np.int16, np.int8) and len(bg16) == batch.n_bg
+            s.bg, s.bg_bits = bg16.ctypes.data, 8 * bg16.dtype.itemsize
         if narrow is not None:
             s.score_bits = int(narrow[0])
             s.score_q, s.exc_off = narrow[1].ctypes.data, narrow[2].ctypes.data
@@ -219,7 +219,7 @@ class Engine:
         p = self.params(fitter, fdr, alpha, gapopen, gapextend, best_value, best_function)
         narrow = (score_bits,) + batch.quantized_scores(score_bits) if score_bits else None
         s = self.host_struct(batch, with_kde=(fitter == "kde"), coords=batch.coords4() if aos else None, narrow=narrow,
-                             bg16=batch.bg16() if bg_bits == 16 else None)
+                             bg16=batch.bg_narrow(bg_bits) if bg_bits in (8, 16) else None)
         self.run(s, p)
         return self.fetch(survivors=survivors)
 

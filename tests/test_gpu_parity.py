@@ -66,7 +66,7 @@ def test_synthetic_vs_oracle(engine, cfg, kw, fitter, fdr):
     compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr}")
     got = engine.build_batch(b, fitter, fdr, aos=True)          # AoS coordinates (o2a_batch.coords)
     compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr} aos")
-    for bits in (16, 32):                                       # narrow scores + exception lists
+    for bits in (8, 16, 32):                                    # narrow scores + exception lists
         got = engine.build_batch(b, fitter, fdr, aos=True, score_bits=bits, bg_bits=bits)
         compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {fitter} fdr={fdr} score_bits={bits}")
     assert engine.counts.n_survivors == int(exp.n_surv.sum())
@@ -82,17 +82,21 @@ def test_narrow_scores_with_many_exceptions(engine):
     b.score[rng.random(b.n_hsp) < 0.3] *= 0.77          # 30 % fractional
     b.score[rng.random(b.n_hsp) < 0.05] += 40000.0      # beyond int16
     b.score[rng.random(b.n_hsp) < 0.01] = -32768.0      # collides with the int16 sentinel value
+    b.score[rng.random(b.n_hsp) < 0.01] = -128.0        # ... and with the int8 one
+    b.score[rng.random(b.n_hsp) < 0.02] = 127.0         # largest int8 value: stays inline
+    b.score[rng.random(b.n_hsp) < 0.02] = 128.0         # first value beyond int8
     exp = O.build_batch(b, "hist", True)
-    for bits in (16, 32):
+    for bits in (8, 16, 32):
         q, eo, ep, ev = b.quantized_scores(bits)
         assert eo[-1] == len(ep) > 0
         got = engine.build_batch(b, "hist", True, score_bits=bits)
         compare_results(got, exp, exact_p=True, what=f"narrow {bits}")
     import torch
     from ortho2align_b200.engine import DeviceBatch
-    db = DeviceBatch(b, torch.device("cuda:0"), aos=True, score_bits=16)
-    engine.run(db.struct(False), engine.params("hist", True))
-    compare_results(engine.fetch(), exp, exact_p=True, what="narrow device-resident")
+    for bits in (8, 16):
+        db = DeviceBatch(b, torch.device("cuda:0"), aos=True, score_bits=bits, bg_bits=bits)
+        engine.run(db.struct(False), engine.params("hist", True))
+        compare_results(engine.fetch(), exp, exact_p=True, what=f"narrow device-resident {bits}")
 
 
 @pytest.mark.parametrize("value", ["block_length", "total_length", "block_count", "weight"])
@@ -253,7 +257,7 @@ def test_chunked_host_pipeline_matches_single_pass(engine, monkeypatch, chunks, 
     monkeypatch.delenv("O2A_NO_PIPELINE")
     monkeypatch.setenv("O2A_PIPELINE_MIN_HSPS", "0")
     monkeypatch.setenv("O2A_CHUNKS", str(chunks))
-    for kwargs in (dict(), dict(aos=True), dict(aos=True, score_bits=16, bg_bits=16)):
+    for kwargs in (dict(), dict(aos=True), dict(aos=True, score_bits=16, bg_bits=16), dict(aos=True, score_bits=8, bg_bits=8)):
         got = engine.build_batch(b, fitter, True, **kwargs)
         assert engine.lib.o2a_pipeline_chunks(engine.h) == chunks
         compare_results(got, single, exact_p=True, what=f"chunks={chunks} {kwargs} vs single pass")
