@@ -280,7 +280,7 @@ def main():
     achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of one k_filter launch from the `ncu --set full` capture of
     # this command at the default workload (profiles/r1_ncu_full_summary_c2.txt); other workloads: not captured
-    traffic = 1.745914e9 if (args.config == 2 and batch.n_lnc == 20_000 and args.score_bits == 0) else None
+    traffic = 1.746377e9 if (args.config == 2 and batch.n_lnc == 20_000 and args.score_bits == 0) else None
     roofline = {"bound": "hbm", "kernel": "k_filter" if args.score_bits == 0 else "k_filter_q", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms,
