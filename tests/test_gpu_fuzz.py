@@ -1,0 +1,97 @@
+"""Randomised parity sweep: many small batches of random shape, parameters and input layout through the C-ABI
+against the oracle — every integer / index / decision output identical, p and q bit-exact (KDE: to tolerance).
+Seeded, so a failure reproduces; sized to finish in well under a minute on a B200."""
+import numpy as np
+import pytest
+
+from helpers import compare_results
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_batch(rng, it):
+    from ortho2align_b200 import synth
+    cfg = int(rng.choice([1, 2, 2, 4, 5]))
+    kw = dict(seed=1000 + it)
+    if cfg == 5:
+        kw["n_lnc"] = int(rng.integers(1, 120))
+    elif cfg == 4:
+        kw.update(n_lnc=int(rng.integers(1, 3)), hsps_per_region=int(rng.integers(20, 700)), n_bg=int(rng.integers(2, 400)))
+    else:
+        kw.update(n_lnc=int(rng.integers(1, 25)), hsps_per_region=int(rng.integers(1, 700)), n_bg=int(rng.integers(2, 3000)),
+                  regions=int(rng.integers(1, 7)))
+    b = synth.workload(cfg, **kw)
+    # perturb: fractional scores, large scores, duplicated scores (ties in p), a flat background
+    n = b.n_hsp
+    if n:
+        if rng.random() < 0.5:
+            b.score[rng.random(n) < 0.2] *= float(rng.choice([0.5, 0.77, 0.999]))
+        if rng.random() < 0.4:
+            b.score[rng.random(n) < 0.05] += float(rng.choice([100.0, 300.0, 40000.0]))
+        if rng.random() < 0.3:
+            b.score[:] = np.round(b.score / 4) * 4                       # heavy ties
+    if rng.random() < 0.2 and b.n_lnc:
+        l = int(rng.integers(0, b.n_lnc))
+        b.bg[b.bg_off[l]:b.bg_off[l + 1] - 1] = 17                       # nearly constant background
+    return b, cfg
+
+
+@pytest.mark.parametrize("block", range(10))
+def test_random_batches_match_the_oracle(engine, block):
+    from oracle import oracle as O
+    rng = np.random.default_rng(20250 + block)
+    for it in range(20):
+        b, cfg = _random_batch(rng, 100 * block + it)
+        fitter = str(rng.choice(["hist", "hist", "hist", "empirical", "kde"]))
+        if fitter == "kde" and (b.n_hsp > 6000 or cfg == 4):
+            fitter = "hist"
+        fdr = bool(rng.random() < 0.8)
+        alpha = float(rng.choice([0.01, 0.05, 0.05, 0.3]))
+        go, ge = (5, 2) if rng.random() < 0.6 else (int(rng.integers(0, 12)), int(rng.integers(0, 4)))
+        value = str(rng.choice(["block_length", "total_length", "block_count", "weight"]))
+        func = str(rng.choice(["max", "min"]))
+        exp = O.build_batch(b, fitter, fdr, alpha, go, ge, value, func)
+        kw = {}
+        lay = int(rng.integers(0, 5))
+        if lay == 1:
+            kw = dict(aos=True)
+        elif lay >= 2:
+            bits = [8, 16, 32][lay - 2]
+            kw = dict(aos=True, score_bits=bits)
+            try:
+                b.bg_narrow(bits) if bits < 32 else None
+                kw["bg_bits"] = bits
+            except Exception:
+                kw["bg_bits"] = 32
+        got = engine.build_batch(b, fitter, fdr, alpha, go, ge, value, func, **kw)
+        what = f"block {block} it {it}: cfg{cfg} {fitter} fdr={fdr} a={alpha} gap=({go},{ge}) {value}/{func} {kw}"
+        compare_results(got, exp, exact_p=(fitter != "kde"), what=what,
+                        m_max=float(np.diff(b.hsp_off).max()) if b.n_aln else 1.0)
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_random_cuts_match_the_oracle(engine, block):
+    from oracle import producer as OP
+    from ortho2align_b200 import synth
+    rng = np.random.default_rng(777 + block)
+    for it in range(10):
+        rel, rg = synth.producer_workload(int(rng.integers(1, 40)), seed=int(rng.integers(0, 10 ** 6)),
+                                          hits_per_region=int(rng.integers(0, 900)), regions=int(rng.integers(1, 6)),
+                                          flank=int(rng.choice([0, 500, 50_000])))
+        n_aln = len(rg["qleft"])
+        for k in ("qleft", "qright"):
+            rg[k] = np.where(rng.random(n_aln) < 0.85, rg[k], OP.NO_BOUND)
+        if rng.random() < 0.5:                                           # subject boundaries on some alignments
+            rg["sleft"] = np.where(rng.random(n_aln) < 0.5, rg["s_start"] + rng.integers(0, 10 ** 6, size=n_aln), OP.NO_BOUND)
+            rg["sright"] = np.where(rng.random(n_aln) < 0.5, rg["s_end"] - rng.integers(0, 10 ** 6, size=n_aln), OP.NO_BOUND)
+        if rng.random() < 0.3:
+            rg["relative"] = (rng.random(n_aln) < 0.8).astype(np.uint8)
+        if rng.random() < 0.3:                                           # inverted query boundaries: general-class kernels
+            sw = rng.random(n_aln) < 0.2
+            rg["qleft"], rg["qright"] = np.where(sw, rg["qright"], rg["qleft"]), np.where(sw, rg["qleft"], rg["qright"])
+        rel["score_is_int"] = (rng.random(len(rel["score"])) < 0.9).astype(np.uint8)
+        got, exp = engine.cut_batch(rel, rg), OP.cut_batch(rel, rg)
+        for k in ("hsp_off", "qstart", "qend", "sstart", "send", "score", "cut", "status"):
+            assert np.array_equal(got[k], exp[k]), f"cut block {block} it {it}: {k}"
+        ok = (exp["status"] & 1) == 0
+        assert np.array_equal(got["qlen"][ok], exp["qlen"][ok]) and np.array_equal(got["slen"][ok], exp["slen"][ok])
