@@ -153,7 +153,282 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------
+# Secondary measurements (`--stage producer | ingest | files`): the rows SURVEY.md 8f adds around the hot path.
+# They live here because their CPU-baseline legs run the oracle / the reference harness, which only tests/,
+# smoke() and bench.py may touch. `tools/bench_*.py` are thin wrappers.
+# --------------------------------------------------------------------------------------------------
+def stage_producer(argv):
+    ap = argparse.ArgumentParser(prog="bench.py --stage producer")
+    ap.add_argument("--lnc", type=int, default=10000)
+    ap.add_argument("--hits", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cpu-lnc", type=int, default=2000)
+    ap.add_argument("--tables", type=int, default=200)
+    args = ap.parse_args(argv)
+    import torch
+    from ortho2align_b200 import producer, synth
+    from ortho2align_b200.engine import Engine
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: the producer path has no CPU fallback")
+    dev = torch.device("cuda:0")
+    t0 = time.perf_counter()
+    rel, rg = synth.producer_workload(args.lnc, seed=1, hits_per_region=args.hits)
+    gen_s = time.perf_counter() - t0
+    n_hsp, n_aln = len(rel["score"]), len(rg["qleft"])
+    eng = Engine(0)
+    eng.set_timing(True)
+    d_rel = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in rel.items()}
+    d_rg = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in rg.items()}
+    torch.cuda.synchronize()
+    s = eng.cut_struct(d_rel, d_rg, device=True)
+    for _ in range(args.warmup):
+        kept = eng.run_cut(s)
+    l0 = eng.launch_count()
+    stage = {k: 0.0 for k in eng.CUT_STAGES}
+    for _ in range(args.steps):
+        eng.run_cut(s)
+        for k, v in eng.cut_ms().items():
+            stage[k] += v
+    launches = eng.launch_count() - l0
+    stage = {k: v / args.steps for k, v in stage.items()}
+    kern_ms = stage["count"] + stage["scan"] + stage["write"]
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6548.8))
+    alg_bytes = 24.0 * n_hsp + 25.0 * kept + 8.0 * 9 * n_aln
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    # end to end: pinned host arrays -> host arrays
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    keep_alive = {k: pin(v) for k, v in {**rel, **rg}.items()}
+    h_rel = {k: keep_alive[k].numpy() for k in rel}
+    h_rg = {k: keep_alive[k].numpy() for k in rg}
+    hs = eng.cut_struct(h_rel, h_rg)
+    eng.run_cut(hs); eng.fetch_cut(pinned=True)
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.run_cut(hs)
+        out = eng.fetch_cut(pinned=True)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = sum(int(v.numpy().nbytes) for v in keep_alive.values())
+    d2h = sum(int(v.nbytes) for v in out.values())
+    # CPU port on a bounded sample of the same workload
+    from oracle import oracle as O
+    from oracle import producer as OP
+    c_aln = min(n_aln, args.cpu_lnc * 5)
+    c_h = int(rel["hsp_off"][c_aln])
+    c_rel = {k: (v[:c_aln + 1] if k == "hsp_off" else v[:c_h]) for k, v in rel.items()}
+    c_rg = {k: v[:c_aln] for k, v in rg.items()}
+    threads = O.host_threads()
+    best = None
+    for _ in range(3):
+        OP.cut_batch(c_rel, c_rg, n_threads=threads)
+        best = OP.LAST_CALL_SECONDS if best is None else min(best, OP.LAST_CALL_SECONDS)
+    # BLAST table reader
+    rng = np.random.default_rng(4)
+    tables = [synth.blast_tabular(*synth.relative_hits(rng, args.hits, 120_000, 2_100_000)) for _ in range(args.tables)]
+    tb = sum(len(t) for t in tables)
+    reader = {"tables": args.tables, "hits_per_table": args.hits, "mb": round(tb / 1e6, 1)}
+    raw = [t.encode() for t in tables]
+    for nt in (1, threads):
+        bt = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r = producer.parse_blast_tables(raw, threads=nt)
+            dt = time.perf_counter() - t0
+            bt = dt if bt is None else min(bt, dt)
+        assert not r["status"].any() and len(r["score"]) == args.tables * args.hits
+        reader[f"native_{nt}_threads"] = {"hsps_per_s": len(r["score"]) / bt, "mb_per_s": tb / 1e6 / bt}
+    t0 = time.perf_counter()
+    for t in tables[:10]:
+        OP.parse_blast(t)
+    reader["python_restatement_1_thread"] = {"hsps_per_s": 10 * args.hits / (time.perf_counter() - t0)}
+    line = {
+        "metric": "input HSPs/sec through to_genomic + cut_coordinates (o2a_cut_batch)", "unit": "HSPs/s",
+        "value": n_hsp / (kern_ms * 1e-3), "ms_per_step": kern_ms, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": 1, "dtype": "int32 coordinates / f64 scores", "data": "synthetic (synth.producer_workload)",
+        "config": {"workload": f"{args.lnc} genes x 5 syntenic regions x ~{args.hits} BLAST hits, gene-boundary cut",
+                   "alignments": n_aln, "input_hsps": n_hsp, "kept_hsps": int(kept), "cut_hsps": int((out['cut'] & 1).sum()),
+                   "l2": f"inputs {24 * n_hsp / 1e9:.2f} GB larger than L2; no flush needed", "gen_seconds": round(gen_s, 1)},
+        "stage_ms": stage, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "algorithmic_bytes": alg_bytes},
+        "e2e": {"value": n_hsp / e2e_s, "unit": "HSPs/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "cpu_baseline": {"value": c_h / best, "unit": "HSPs/s", "cores": threads, "kind": "port",
+                         "sample": f"first {c_aln} alignments ({c_h} HSPs), best of 3"},
+        "blast_reader": reader,
+    }
+    print(json.dumps(line))
+
+
+
+def stage_ingest(argv):
+    ap = argparse.ArgumentParser(prog="bench.py --stage ingest")
+    ap.add_argument("--lnc", type=int, default=48)
+    ap.add_argument("--threads", type=int, default=0)
+    args = ap.parse_args(argv)
+    import tempfile
+    from ortho2align_b200 import ingest
+    from ortho2align_b200.pipeline import _load_lncrna
+    b, m = synth.workload(2, n_lnc=args.lnc, with_meta=True, seed=1)
+    items = synth.to_json_dicts(b, m)
+    with tempfile.TemporaryDirectory(prefix="o2a_ingest_") as tmp:
+        ad, bd = os.path.join(tmp, "align"), os.path.join(tmp, "bg")
+        os.makedirs(ad), os.makedirs(bd)
+        af, bf, nbytes = [], [], 0
+        for name, alns, bg in items:
+            pa, pb = os.path.join(ad, name + ".json"), os.path.join(bd, name + ".json")
+            with open(pa, "w") as f:
+                json.dump(alns, f)
+            with open(pb, "w") as f:
+                json.dump(bg, f)
+            nbytes += os.path.getsize(pa) + os.path.getsize(pb)
+            af.append(pa); bf.append(pb)
+        out = {"lncRNAs": args.lnc, "hsps": b.n_hsp, "json_mb": round(nbytes / 1e6, 1)}
+        t0 = time.perf_counter()
+        for a, c in zip(af, bf):
+            _load_lncrna(a, c)
+        dt = time.perf_counter() - t0
+        out["python_json_pack"] = {"hsps_per_s": b.n_hsp / dt, "mb_per_s": nbytes / 1e6 / dt, "threads": 1}
+        nthreads = args.threads or len(os.sched_getaffinity(0))
+        for nt in (1, nthreads):
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                r = ingest.load_files(af, bf, threads=nt)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+                assert r.batch.n_hsp == b.n_hsp
+                r.close()
+            out[f"native_{nt}_threads"] = {"hsps_per_s": b.n_hsp / best, "mb_per_s": nbytes / 1e6 / best, "threads": nt}
+        # columnar sidecar: written once, then memory-mapped and copied into fresh arrays (what a run touches)
+        r = ingest.load_files(af, bf, threads=nthreads)
+        side = os.path.join(tmp, "columnar.o2ac")
+        t0 = time.perf_counter()
+        ingest.save_sidecar(side, r, af, bf)
+        out["sidecar_write_s"] = time.perf_counter() - t0
+        out["sidecar_mb"] = round(os.path.getsize(side) / 1e6, 1)
+        r.close()
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            s = ingest.open_sidecar(side, af, bf)
+            total = sum(int(getattr(s.batch, k).sum(dtype="int64")) for k in ("bg", "qstart", "qend", "sstart", "send"))
+            total += float(s.batch.score.sum())
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out["sidecar_read"] = {"hsps_per_s": b.n_hsp / best, "mb_per_s": os.path.getsize(side) / 1e6 / best, "threads": 1,
+                               "note": "open + manifest check + one full pass over every mapped array"}
+        try:
+            sys.path.insert(0, ROOT)
+            from oracle import ref_harness as rh
+            if rh.reference_available():
+                ref = rh.import_reference()
+                t0 = time.perf_counter()
+                for a in af[:8]:
+                    with open(a) as f:
+                        [ref.genomicranges.GenomicRangesAlignment.from_dict(d) for d in json.load(f)]
+                dt = time.perf_counter() - t0
+                frac = sum(len(al["HSPs"]) for it in items[:8] for al in it[1])
+                out["reference_json_from_dict"] = {"hsps_per_s": frac / dt, "threads": 1, "sample_lncRNAs": 8}
+        except Exception as e:  # pragma: no cover
+            out["reference_json_from_dict"] = {"error": str(e)}
+        print(json.dumps(out))
+
+
+
+def stage_files(argv):
+    ap = argparse.ArgumentParser(prog="bench.py --stage files")
+    ap.add_argument("--lnc", type=int, default=100)
+    ap.add_argument("--cores", type=int, default=0)
+    ap.add_argument("--runner", default="gpu", choices=["gpu", "oracle"])
+    ap.add_argument("--reference", action="store_true")
+    ap.add_argument("--ref-lnc", type=int, default=8)
+    args = ap.parse_args(argv)
+    import tempfile
+    from ortho2align_b200 import pipeline, synth
+    cores = args.cores or len(os.sched_getaffinity(0))
+    if args.runner == "oracle":
+        from oracle import oracle as O
+        pipeline._run_shards = lambda batches, devices, fitter, fdr, alpha, go, ge: [O.build_batch(b, fitter, fdr, alpha, go, ge) for b in batches]
+    b, m = synth.workload(2, n_lnc=args.lnc, with_meta=True, seed=1)
+    items = synth.to_json_dicts(b, m)
+    out = {"lncRNAs": args.lnc, "hsps": b.n_hsp, "cores": cores, "runner": args.runner}
+    with tempfile.TemporaryDirectory(prefix="o2a_e2e_") as tmp:
+        ad, bd = os.path.join(tmp, "align"), os.path.join(tmp, "bg")
+        os.makedirs(ad), os.makedirs(bd)
+        nbytes = 0
+        for name, alns, bg in items:
+            for d, obj in ((ad, alns), (bd, bg)):
+                p = os.path.join(d, name + ".json")
+                with open(p, "w") as f:
+                    json.dump(obj, f)
+                nbytes += os.path.getsize(p)
+        out["json_mb"] = round(nbytes / 1e6, 1)
+        del items
+
+        def run(tag, **kw):
+            od = os.path.join(tmp, "out_" + tag)
+            pipeline.PHASES.clear()
+            t0 = time.perf_counter()
+            pipeline.build_orthologs(ad, bd, "hist", od, fdr=True, cores=cores, silent=True,
+                                     stats_filename=os.path.join(tmp, tag + ".stats"), **kw)
+            t1 = time.perf_counter()
+            j = lambda n: os.path.join(od, n)
+            pipeline.get_best_orthologs(j("significant.query_orthologs.bed"), j("significant.query_orthologs.tsv"),
+                                        j("significant.subject_orthologs.bed"), j("significant.subject_orthologs.tsv"),
+                                        "block_length", "max", j("best.q.bed"), j("best.q.tsv"), j("best.s.bed"), j("best.s.tsv"))
+            t2 = time.perf_counter()
+            n_orth = sum(1 for _ in open(j("significant.query_orthologs.bed")))
+            out[tag] = {"build_orthologs_s": t1 - t0, "get_best_orthologs_s": t2 - t1, "hsps_per_s": b.n_hsp / (t2 - t0),
+                        "orthologs": n_orth, "phases_s": dict(pipeline.PHASES)}
+            return od
+
+        if args.runner == "gpu":
+            run("warmup")                                    # CUDA context, library load
+        cache = os.path.join(tmp, "columnar.o2ac")
+        run("cold_json", cache=cache)
+        run("warm_sidecar", cache=cache)
+        if args.reference:
+            from oracle import ref_harness as rh
+            if rh.reference_available():
+                sub_a, sub_b = os.path.join(tmp, "ra"), os.path.join(tmp, "rb")
+                os.makedirs(sub_a), os.makedirs(sub_b)
+                names = sorted(os.listdir(ad))[:args.ref_lnc]
+                for n in names:
+                    os.symlink(os.path.join(ad, n), os.path.join(sub_a, n))
+                    os.symlink(os.path.join(bd, n), os.path.join(sub_b, n))
+                h = sum(len(a["HSPs"]) for n in names for a in json.load(open(os.path.join(ad, n))))
+                t0 = time.perf_counter()
+                rh.run_reference_build(sub_a, sub_b, os.path.join(tmp, "ref_out"), fitting="hist", fdr=True, cores=1, pool="serial")
+                dt = time.perf_counter() - t0
+                out["reference_1_core"] = {"lncRNAs": len(names), "hsps": h, "seconds": dt, "hsps_per_s": h / dt}
+    print(json.dumps(out))
+
+
+
 def main():
+    if "--stage" in sys.argv:
+        k = sys.argv.index("--stage")
+        stage = sys.argv[k + 1] if k + 1 < len(sys.argv) else ""
+        rest = sys.argv[1:k] + sys.argv[k + 2:]
+        fn = {"producer": stage_producer, "ingest": stage_ingest, "files": stage_files}.get(stage)
+        if stage != "build":
+            if fn is None:
+                raise SystemExit("--stage must be one of build, producer, ingest, files")
+            return fn(rest)
+        sys.argv = [sys.argv[0]] + rest
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
