@@ -581,6 +581,11 @@ def main():
     narrow, bg16 = None, None
     if narrow_bits:
         qs = batch.quantized_scores(narrow_bits)
+        # a width that sends many scores to the exception lists (12 B each) is the wrong choice for this data:
+        # what a caller would do is take the next one
+        while narrow_bits < 32 and len(qs[2]) > 0.1 * max(batch.n_hsp, 1):
+            narrow_bits *= 2
+            qs = batch.quantized_scores(narrow_bits)
         for name, arr in zip(("score_q", "exc_off", "exc_pos", "exc_val"), qs):
             keep_alive[name] = pin(arr)
         del qs
@@ -636,7 +641,7 @@ def main():
         h2d = int(h2d + keep_alive["coords"].numpy().nbytes)
     e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy,
-           "score_layout": LAYOUTS[args.e2e_score_bits],
+           "score_layout": LAYOUTS[narrow_bits],
            "pipelined_chunks": chunks,
            ("stage_ms_last_step" if chunks <= 1 else "stage_ms_last_chunk"): e2e_stage_ms}
 

@@ -636,6 +636,10 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
     if (const char* e = getenv("O2A_PIPELINE_MIN_HSPS")) pipeline_min_hsps = atoll(e);
     if (batch->mem == O2A_MEM_HOST && batch->n_lnc >= 8 && batch->n_hsp >= pipeline_min_hsps && !getenv("O2A_NO_PIPELINE")) {
         n_chunks = 8;
+        // every chunk must still fill the machine: kernels that take one CTA per (large) alignment would otherwise
+        // run chunk after chunk at a fraction of the SMs (600 x 50 k-HSP alignments: 8 chunks tripled the step)
+        const long long by_alignments = batch->n_aln / 2048;
+        if (by_alignments < n_chunks) n_chunks = (int)(by_alignments < 1 ? 1 : by_alignments);
         if (const char* e = getenv("O2A_CHUNKS")) n_chunks = atoi(e);
         if (n_chunks < 1) n_chunks = 1;
         if (n_chunks > 16) n_chunks = 16;
