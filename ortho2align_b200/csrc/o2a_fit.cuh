@@ -541,21 +541,22 @@ k_fit_count(FitArgs A)
     constexpr int PER = 16 / (int)sizeof(BG);
     __shared__ int s_cnt[FIT_SMEM_RANGE];
     __shared__ int s_scan[FITC_THREADS / 32 + 2];
-    __shared__ int s_oor;
+    __shared__ int s_oor, s_lo, s_hi;
     const int tid = threadIdx.x;
+    {   // the counters are zeroed once; every lncRNA re-zeroes only the range it touched
+        int4* z = reinterpret_cast<int4*>(s_cnt);
+        for (int k = tid; k < FIT_SMEM_RANGE / 4; k += FITC_THREADS) z[k] = make_int4(0, 0, 0, 0);
+    }
     for (long long l = blockIdx.x; l < A.n_lnc; l += gridDim.x) {
         const long long b0 = A.bg_off[l];
         const long long n = A.bg_off[l + 1] - b0;
         const BG* x = reinterpret_cast<const BG*>(A.bg) + b0;
-        {
-            int4* z = reinterpret_cast<int4*>(s_cnt);
-            for (int k = tid; k < FIT_SMEM_RANGE / 4; k += FITC_THREADS) z[k] = make_int4(0, 0, 0, 0);
-            if (tid == 0) s_oor = 0;
-        }
+        if (tid == 0) { s_oor = 0; s_lo = FIT_SMEM_RANGE; s_hi = -1; }
         __syncthreads();
         {
             bool oor = false;
-#define O2A_CNT(v) do { int v__ = (v); if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) atomicAdd(&s_cnt[v__], 1); else oor = true; } while (0)
+            int lo = FIT_SMEM_RANGE, hi = -1;           // range of the values this thread counted
+#define O2A_CNT(v) do { int v__ = (v); if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) { atomicAdd(&s_cnt[v__], 1); lo = min(lo, v__); hi = max(hi, v__); } else oor = true; } while (0)
             long long head = ((PER - (b0 & (PER - 1))) & (PER - 1)); if (head > n) head = n;
             for (long long i = tid; i < head; i += FITC_THREADS) O2A_CNT(x[i]);
             const int4* x4 = reinterpret_cast<const int4*>(x + head);
@@ -575,21 +576,24 @@ k_fit_count(FitArgs A)
             for (long long i = head + (long long)n4 * PER + tid; i < n; i += FITC_THREADS) O2A_CNT(x[i]);
 #undef O2A_CNT
             if (oor) s_oor = 1;
+            lo = __reduce_min_sync(FULL_MASK, lo); hi = __reduce_max_sync(FULL_MASK, hi);
+            if (lane_id() == 0 && hi >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
         }
         __syncthreads();
         int nv = 0;
-        if (s_oor == 0) {
-            int* ov = A.fc_val + l * FITW_CAP; int* oc = A.fc_cnt + l * FITW_CAP;
-            for (int k0 = 0; k0 < FIT_SMEM_RANGE; k0 += FITC_THREADS) {
-                const int c = s_cnt[k0 + tid];
-                int tot;
-                const int pos = cta_exclusive_scan(c != 0, s_scan, &tot);
-                if (c != 0 && nv + pos < FITW_CAP) { ov[nv + pos] = k0 + tid; oc[nv + pos] = c; }
-                nv += tot;
-                __syncthreads();
-            }
+        const int k_lo = s_hi >= 0 ? (s_lo / FITC_THREADS) * FITC_THREADS : 0, k_hi = s_hi;   // touched counters only
+        const bool in_range = s_oor == 0;
+        int* ov = A.fc_val + l * FITW_CAP; int* oc = A.fc_cnt + l * FITW_CAP;
+        for (int k0 = k_lo; k0 <= k_hi; k0 += FITC_THREADS) {
+            const int c = s_cnt[k0 + tid];
+            s_cnt[k0 + tid] = 0;                                  // ready for the next lncRNA
+            int tot;
+            const int pos = cta_exclusive_scan(c != 0, s_scan, &tot);
+            if (in_range && c != 0 && nv + pos < FITW_CAP) { ov[nv + pos] = k0 + tid; oc[nv + pos] = c; }
+            nv += tot;
+            __syncthreads();
         }
-        if (tid == 0) A.fc_n[l] = (s_oor == 0 && nv <= FITW_CAP) ? nv : -1;
+        if (tid == 0) A.fc_n[l] = (in_range && nv <= FITW_CAP) ? nv : -1;
         __syncthreads();
     }
 }
