@@ -613,11 +613,10 @@ k_fit_hist_tail(FitArgs A)
     __shared__ double s_t[FITW_WARPS][FITW_CAP];
     __shared__ double s_lsum[FITW_WARPS][FITW_CAP];
     __shared__ short s_ldep[FITW_WARPS][FITW_CAP];
-    __shared__ double s_vstk[FITW_WARPS][72];
-    __shared__ short s_ostk[FITW_WARPS][72];
+    __shared__ short s_rep[FITW_WARPS][FITW_CAP];
     const int lane = lane_id(), w = warp_id();
     int* K = s_k[w]; int* Cn = s_c[w]; double* T = s_t[w]; double* LS = s_lsum[w]; short* LD = s_ldep[w];
-    double* VS = s_vstk[w]; short* OS = s_ostk[w];
+    short* RP = s_rep[w];
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
     const long long nwarps = (long long)gridDim.x * FITW_WARPS;
     for (long long l = (long long)blockIdx.x * FITW_WARPS + w; l < A.n_lnc; l += nwarps) {
@@ -697,22 +696,31 @@ k_fit_hist_tail(FitArgs A)
                 }
             }
             __syncwarp();
-            double S = 0.0;
-            if (lane == 0) {
-                int vp = 0, op = 0;
-                for (int t = 0; t < nnz; ++t) {
-                    const int d = LD[t];
-                    if (d == -2) continue;
-                    if (t > 0) {
-                        while (op > 0 && OS[op - 1] > d) { double b2 = VS[--vp], a2 = VS[--vp]; VS[vp++] = __dadd_rn(a2, b2); --op; }
-                        OS[op++] = (short)d;
-                    }
-                    VS[vp++] = LS[t];
+            // Combine the leaf sums exactly as numpy's recursion does: the "operator" between two consecutive non-empty
+            // leaves is the tree node that is their lowest common ancestor, and a deeper node is summed first. Every
+            // node joins the finished group on its left (which starts after the nearest shallower operator) with the
+            // finished group on its right (which starts at its own leaf); nodes of equal depth belong to disjoint
+            // subtrees, so one pass per depth, deepest first, evaluates the whole tree with all lanes busy.
+            int dmax = -1;
+            for (int t = lane; t < nnz; t += 32) {
+                const int d = LD[t];
+                int rep = 0;
+                if (d >= 0) {
+                    int u = t - 1;
+                    for (; u > 0; --u) { const int du = LD[u]; if (du != -2 && du < d) break; }
+                    rep = u;
+                    dmax = max(dmax, d);
                 }
-                while (op > 0) { double b2 = VS[--vp], a2 = VS[--vp]; VS[vp++] = __dadd_rn(a2, b2); --op; }
-                S = nnz > 0 ? VS[0] : 0.0;
+                RP[t] = (short)rep;
             }
-            S = __shfl_sync(FULL_MASK, S, 0);
+            dmax = __reduce_max_sync(FULL_MASK, dmax);
+            __syncwarp();
+            for (int D = dmax; D >= 0; --D) {
+                for (int t = lane; t < nnz; t += 32)
+                    if (LD[t] == D) { const int rp = RP[t]; LS[rp] = __dadd_rn(LS[rp], LS[t]); }
+                __syncwarp();
+            }
+            double S = nnz > 0 ? LS[0] : 0.0;
             for (int t = lane; t < nnz; t += 32) {
                 double hp0, ww;
                 fit_term(Cn[t], K[t], f, total, &hp0, &ww);
