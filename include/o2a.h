@@ -15,6 +15,10 @@
  *   - the library never frees caller memory. Input pointers are host pointers (mem = O2A_MEM_HOST;
  *     the library copies them host->device on its stream, pinned memory from o2a_host_alloc makes
  *     that copy asynchronous) or device pointers on ctx's device (mem = O2A_MEM_DEVICE; zero copy).
+ *   - besides the caller's stream (o2a_set_stream) a ctx owns two internal streams: one for the chunked
+ *     host->device copies of large host batches, one for kernels that run beside the main ones. Both are
+ *     forked from and joined back into the caller's stream with events inside every call; when a call
+ *     returns, all of its work has completed.
  *   - there is NO CPU fallback: without a usable CUDA device o2a_create fails.
  *
  * Data layout (three CSR levels; ortho2align_b200/columnar.py):
