@@ -25,7 +25,8 @@ def _oracle_runner(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
     return [O.build_batch(b, fitter, fdr, alpha, gapopen, gapextend) for b in batches]
 
 
-def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest="native", cache=None, dirs=None):
+def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest="native", cache=None, dirs=None,
+                     devices=None):
     from ortho2align_b200 import pipeline
     ad, bd = dirs or _materialise(tmp_path, g)
     real_listdir = os.listdir
@@ -33,7 +34,7 @@ def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest=
     od = str(tmp_path / f"out_{key}")
     stats = str(tmp_path / f"{key}.stats.txt")
     pipeline.build_orthologs(ad, bd, fitting, od, threshold=0.05, gapopen=5, gapextend=2, fdr=fdr, cores=1,
-                             timeout=None, silent=True, stats_filename=stats, ingest=ingest, cache=cache)
+                             timeout=None, silent=True, stats_filename=stats, ingest=ingest, cache=cache, devices=devices)
     j = lambda n: os.path.join(od, n)
     pipeline.get_best_orthologs(j("significant.query_orthologs.bed"), j("significant.query_orthologs.tsv"),
                                 j("significant.subject_orthologs.bed"), j("significant.subject_orthologs.tsv"),
@@ -63,6 +64,21 @@ def test_host_logic_with_oracle_injected(tmp_path, monkeypatch, key, fitting, fd
     from ortho2align_b200 import pipeline
     monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
     _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), key, fitting, fdr, exact, ingest=ingest)
+
+
+@pytest.mark.parametrize("ingest", ["native", "json"])
+def test_lncrna_shards_over_several_devices_give_the_same_files(tmp_path, monkeypatch, ingest):
+    """devices=[...] shards the lncRNAs (LPT by HSP count) into one batched call per device; the files do not change."""
+    from ortho2align_b200 import pipeline
+    seen = []
+
+    def runner(batches, devices, *a):
+        seen.append((len(batches), list(devices)))
+        return _oracle_runner(batches, devices, *a)
+    monkeypatch.setattr(pipeline, "_run_shards", runner)
+    _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), "hist_1", "hist", True, True, ingest=ingest,
+                     devices=[0, 1, 2])
+    assert seen and seen[0][0] == 3 and seen[0][1] == [0, 1, 2]
 
 
 def test_columnar_sidecar_replaces_the_json_parse(tmp_path, monkeypatch):
@@ -99,6 +115,15 @@ def test_drop_in_pipeline_on_gpu(tmp_path, monkeypatch, key, fitting, fdr, exact
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), key, fitting, fdr, exact)
+
+
+@pytest.mark.gpu
+def test_drop_in_pipeline_with_two_engines_on_one_gpu(tmp_path, monkeypatch):
+    """devices=[0, 0]: two shards, two o2a_ctx on their own threads (what devices=[0, 1] does on a 2-GPU box)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _run_and_compare(tmp_path, monkeypatch, load_golden("e2e.json"), "hist_1", "hist", True, True, devices=[0, 0])
 
 
 def test_cli_parses_reference_flags():
