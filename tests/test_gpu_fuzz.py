@@ -65,6 +65,16 @@ def test_random_batches_match_the_oracle(engine, block):
                 kw["bg_bits"] = 32
         got = engine.build_batch(b, fitter, fdr, alpha, go, ge, value, func, **kw)
         what = f"block {block} it {it}: cfg{cfg} {fitter} fdr={fdr} a={alpha} gap=({go},{ge}) {value}/{func} {kw}"
+        if fitter == "kde":
+            # A KDE threshold is a brentq root, reproducible to ~1e-10 only. When the root sits ON a score
+            # value — sf(v) == alpha exactly, i.e. #(bg > v) + #(bg == v)/2 == alpha*n, not rare with integer scores — the
+            # strict `score > isf` of an HSP scoring v hangs on that last bit, in the reference as much as here.
+            lnc_of_hsp = np.repeat(np.repeat(np.arange(b.n_lnc), np.diff(b.aln_off)), np.diff(b.hsp_off))
+            ok = exp.status == 0
+            assert np.array_equal(got.status, exp.status), what
+            assert np.allclose(got.thr[ok], exp.thr[ok], rtol=0, atol=1e-9), what
+            if np.any(np.abs(b.score - exp.thr[lnc_of_hsp]) < 1e-9):
+                continue
         compare_results(got, exp, exact_p=(fitter != "kde"), what=what,
                         m_max=float(np.diff(b.hsp_off).max()) if b.n_aln else 1.0)
 
