@@ -154,7 +154,7 @@ def run_reference_arm(args, rank):
 
 
 # --------------------------------------------------------------------------------------------------
-# Secondary measurements (`--stage producer | ingest | files`): the rows SURVEY.md 8f adds around the hot path.
+# Secondary measurements (`--stage producer | ingest | files | annotate`): the rows SURVEY.md 8f adds around the hot path.
 # They live here because their CPU-baseline legs run the oracle / the reference harness, which only tests/,
 # smoke() and bench.py may touch. `tools/bench_*.py` are thin wrappers.
 # --------------------------------------------------------------------------------------------------
@@ -271,6 +271,104 @@ def stage_producer(argv):
     }
     print(json.dumps(line))
 
+
+
+def stage_annotate(argv):
+    """annotate_orthologs' interval join: o2a_annotate_batch on synthetic orthologs x annotation."""
+    ap = argparse.ArgumentParser(prog="bench.py --stage annotate")
+    ap.add_argument("--orthologs", type=int, default=4_000_000)
+    ap.add_argument("--annotation", type=int, default=4_000_000)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cpu-orthologs", type=int, default=20000)
+    args = ap.parse_args(argv)
+    import torch
+    from ortho2align_b200 import synth
+    from ortho2align_b200.engine import Engine
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: the annotate path has no CPU fallback")
+    dev = torch.device("cuda:0")
+    t0 = time.perf_counter()
+    q, a = synth.annotate_workload(args.orthologs, args.annotation, seed=1, span=1_000_000_000)
+    gen_s = time.perf_counter() - t0
+    n_q, n_a = len(q["start"]), len(a["start"])
+    eng = Engine(0)
+    eng.set_timing(True)
+    dq = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in q.items()}
+    da = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in a.items()}
+    torch.cuda.synchronize()
+    s = eng.ann_struct(dq, da, 0, True, device=True)
+    for _ in range(args.warmup):
+        pairs = eng.run_annotate(s)
+    l0 = eng.launch_count()
+    stage = {k: 0.0 for k in eng.ANN_STAGES}
+    for _ in range(args.steps):
+        eng.run_annotate(s)
+        for k, v in eng.annotate_ms().items():
+            stage[k] += v
+    launches = eng.launch_count() - l0
+    stage = {k: v / args.steps for k, v in stage.items()}
+    kern_ms = stage["prefmax"] + stage["count"] + stage["write"]
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6548.8))
+    # algorithmic bytes: every ortholog (17 B) and annotation range (17 B) read once, 8 B offset + 20 B per pair written
+    alg_bytes = 17.0 * n_q + 17.0 * n_a + 8.0 * n_q + 20.0 * pairs
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+
+    def pin(v):
+        v = np.ascontiguousarray(v)
+        t = torch.empty(v.shape, dtype=torch.from_numpy(v[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = v
+        return t
+    keep_q, keep_a = {k: pin(v) for k, v in q.items()}, {k: pin(v) for k, v in a.items()}
+    hs = eng.ann_struct({k: v.numpy() for k, v in keep_q.items()}, {k: v.numpy() for k, v in keep_a.items()}, 0, True)
+    eng.run_annotate(hs); eng.fetch_annotation(pinned=True)
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.run_annotate(hs)
+        out = eng.fetch_annotation(pinned=True)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = sum(int(v.numpy().nbytes) for v in list(keep_q.values()) + list(keep_a.values()))
+    d2h = sum(int(v.nbytes) for v in out.values())
+    # CPU port (the reference's loops, literally: O(chromosome) backward scan per ortholog) on a bounded sample
+    from oracle import annotate as OA
+    from oracle import oracle as O
+    threads = O.host_threads()
+    c_q = min(n_q, args.cpu_orthologs)
+    sel = np.linspace(0, n_q - 1, c_q).astype(np.int64) if c_q else np.zeros(0, np.int64)
+    cq = {k: np.ascontiguousarray(v[sel]) for k, v in q.items()}
+    best = None
+    for _ in range(2):
+        exp = OA.annotate_batch(cq, a, 0, True, n_threads=threads)
+        best = OA.LAST_CALL_SECONDS if best is None else min(best, OA.LAST_CALL_SECONDS)
+    # the sample doubles as a parity check of the timed call's result
+    off = out["nb_off"]
+    for j, i in enumerate(sel[:2000].tolist()):
+        assert np.array_equal(out["nb_idx"][off[i]:off[i + 1]], exp["nb_idx"][exp["nb_off"][j]:exp["nb_off"][j + 1]]), i
+    line = {
+        "metric": "orthologs/sec through find_neighbours + calc_JI + calc_OC (o2a_annotate_batch)", "unit": "orthologs/s",
+        "value": n_q / (kern_ms * 1e-3), "ms_per_step": kern_ms, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": 1, "dtype": "int32 coordinates / f64 JI, OC", "data": "synthetic (synth.annotate_workload)",
+        "config": {"workload": f"{n_q} orthologs x {n_a} annotation ranges on 24 chromosomes of 1 Gb, distance 0, strandness on",
+                   "pairs": int(pairs), "l2": "flushed by the inputs of the other side between passes: "
+                   f"{17 * (n_q + n_a) / 1e6:.0f} MB of columns + {20 * pairs / 1e6:.0f} MB of pairs per step",
+                   "gen_seconds": round(gen_s, 1)},
+        "stage_ms": stage, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "algorithmic_bytes": alg_bytes,
+                     "note": "binary searches dominate: latency-bound, not a streaming kernel"},
+        "e2e": {"value": n_q / e2e_s, "unit": "orthologs/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "cpu_baseline": {"value": c_q / best, "unit": "orthologs/s", "cores": threads, "kind": "port",
+                         "sample": f"{c_q} evenly spaced orthologs against the full annotation, best of 2"},
+    }
+    print(json.dumps(line))
 
 
 def stage_ingest(argv):
@@ -423,10 +521,10 @@ def main():
         k = sys.argv.index("--stage")
         stage = sys.argv[k + 1] if k + 1 < len(sys.argv) else ""
         rest = sys.argv[1:k] + sys.argv[k + 2:]
-        fn = {"producer": stage_producer, "ingest": stage_ingest, "files": stage_files}.get(stage)
+        fn = {"producer": stage_producer, "ingest": stage_ingest, "files": stage_files, "annotate": stage_annotate}.get(stage)
         if stage != "build":
             if fn is None:
-                raise SystemExit("--stage must be one of build, producer, ingest, files")
+                raise SystemExit("--stage must be one of build, producer, ingest, files, annotate")
             return fn(rest)
         sys.argv = [sys.argv[0]] + rest
     ap = argparse.ArgumentParser()

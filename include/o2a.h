@@ -242,6 +242,35 @@ int o2a_cut_view(o2a_ctx *ctx, o2a_batch *out);
 /* CUDA-event durations (ms) of the last o2a_cut_batch when timing is enabled: h2d, count pass, scan, write pass */
 int o2a_get_cut_ms(o2a_ctx *ctx, float *ms /*4*/);
 
+/* ---------------------------------------------------------------------------------------------
+ * annotate_orthologs' interval join (pipeline.py:1027-1094):
+ *     subject_orthologs.get_neighbours(annotation, relation='ortholog', strandness=True)
+ *                                       genomicranges.py:2040-2067 -> find_neighbours :635-685
+ *     ortholog.calc_JI(range), ortholog.calc_OC(range)    genomicranges.py:497-547 (intersect :460-495)
+ * for a whole list of orthologs in one call. Both lists are columnar; chromosomes and names are the
+ * caller's ranks in ONE dictionary shared by both lists (rank order = Python's str order, None first),
+ * strands are +1 '+', -1 '-', 0 '.'. The annotation must be sorted by (chrom, start, end, name) like the
+ * reference's GenomicRangesList (_genomic_key_func :1566-1572). Per ortholog the neighbours come out in the
+ * order of that sorted list, like `relations['ortholog']`.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct o2a_ann_input {
+    int64_t n_q, n_a;                                  /* orthologs, annotation ranges (n_a < 2^31) */
+    const int32_t *q_chrom, *q_start, *q_end, *q_name; /* [n_q] */
+    const int8_t  *q_strand;                           /* [n_q] */
+    const int32_t *a_chrom, *a_start, *a_end, *a_name; /* [n_a], sorted */
+    const int8_t  *a_strand;                           /* [n_a] */
+    int64_t distance;                                  /* find_neighbours' distance (annotate_orthologs: 0) */
+    int32_t strandness;                                /* find_neighbours' strandness (annotate_orthologs: 1) */
+    int32_t mem;                                       /* O2A_MEM_HOST | O2A_MEM_DEVICE, applies to every pointer */
+} o2a_ann_input;
+
+int o2a_annotate_batch(o2a_ctx *ctx, const o2a_ann_input *in, int64_t *n_pairs);
+/* any pointer may be NULL. nb_off[n_q+1]; per (ortholog, neighbour) pair: index into the sorted annotation,
+ * Jaccard index, overlap coefficient (float64, the reference's values bit for bit) */
+int o2a_fetch_annotation(o2a_ctx *ctx, int64_t *nb_off, int32_t *nb_idx, double *ji, double *oc);
+/* CUDA-event durations (ms) of the last o2a_annotate_batch when timing is enabled: h2d, running max, count + scan, write */
+int o2a_get_annotate_ms(o2a_ctx *ctx, float *ms /*4*/);
+
 #ifdef __cplusplus
 }
 #endif

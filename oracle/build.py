@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libo2a_oracle.so")
 SRC = os.path.join(HERE, "o2a_oracle.c")
-SRCS = [SRC, os.path.join(HERE, "o2a_oracle_producer.c")]
+SRCS = [SRC, os.path.join(HERE, "o2a_oracle_producer.c"), os.path.join(HERE, "o2a_oracle_annotate.c")]
 
 
 def build(force=False):

@@ -11,7 +11,8 @@ EXPORTS = ["o2a_abi_version", "o2a_create", "o2a_destroy", "o2a_last_error", "o2
            "o2a_host_alloc", "o2a_host_free", "o2a_build_batch", "o2a_fetch_lnc", "o2a_fetch_aln",
            "o2a_fetch_survivors", "o2a_fetch_chains", "o2a_fitter_eval", "o2a_best_chain",
            "o2a_launch_count", "o2a_coords_zero_copy", "o2a_pipeline_chunks", "o2a_set_timing", "o2a_get_stage_ms",
-           "o2a_cut_batch", "o2a_fetch_cut", "o2a_cut_view", "o2a_get_cut_ms"]
+           "o2a_cut_batch", "o2a_fetch_cut", "o2a_cut_view", "o2a_get_cut_ms",
+           "o2a_annotate_batch", "o2a_fetch_annotation", "o2a_get_annotate_ms"]
 
 STAGES = ["h2d", "fit", "filter", "pq", "gather", "chain", "best"]
 
@@ -34,6 +35,15 @@ class O2ACutInput(C.Structure):
                 ("s_start", C.c_void_p), ("s_end", C.c_void_p), ("s_minus", C.c_void_p), ("relative", C.c_void_p),
                 ("qleft", C.c_void_p), ("qright", C.c_void_p), ("sleft", C.c_void_p), ("sright", C.c_void_p),
                 ("mem", C.c_int32), ("reserved", C.c_int32)]
+
+
+class O2AAnnInput(C.Structure):
+    _fields_ = [("n_q", C.c_int64), ("n_a", C.c_int64),
+                ("q_chrom", C.c_void_p), ("q_start", C.c_void_p), ("q_end", C.c_void_p), ("q_name", C.c_void_p),
+                ("q_strand", C.c_void_p),
+                ("a_chrom", C.c_void_p), ("a_start", C.c_void_p), ("a_end", C.c_void_p), ("a_name", C.c_void_p),
+                ("a_strand", C.c_void_p),
+                ("distance", C.c_int64), ("strandness", C.c_int32), ("mem", C.c_int32)]
 
 
 class O2AParams(C.Structure):
@@ -110,6 +120,12 @@ def load():
     lib.o2a_cut_view.argtypes = [P, C.POINTER(O2ABatch)]
     lib.o2a_get_cut_ms.restype = C.c_int
     lib.o2a_get_cut_ms.argtypes = [P, P]
+    lib.o2a_annotate_batch.restype = C.c_int
+    lib.o2a_annotate_batch.argtypes = [P, C.POINTER(O2AAnnInput), C.POINTER(i64)]
+    lib.o2a_fetch_annotation.restype = C.c_int
+    lib.o2a_fetch_annotation.argtypes = [P] + [P] * 4
+    lib.o2a_get_annotate_ms.restype = C.c_int
+    lib.o2a_get_annotate_ms.argtypes = [P, P]
     if lib.o2a_abi_version() != 1:
         raise LibraryMissing("libo2a_cuda.so ABI version mismatch; rebuild")
     _lib = lib

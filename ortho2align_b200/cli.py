@@ -1,9 +1,10 @@
-"""Command line: the reference's `build_orthologs` and `get_best_orthologs` sub-commands with the
-same flags and '@config' files (`cli_scripts.py:7-12, 254-350, 556-561`), plus `-devices`."""
+"""Command line: the reference's `build_orthologs`, `get_best_orthologs` and `annotate_orthologs` sub-commands
+with the same flags and '@config' files (`cli_scripts.py:7-12, 254-405, 556-561`), plus `-devices` / `-device`."""
 from __future__ import annotations
 
 import argparse
 
+from .annotate import annotate_orthologs
 from .pipeline import build_orthologs, get_best_orthologs
 
 
@@ -40,6 +41,15 @@ def make_parser():
     g.add_argument("-outfile_query_total", type=str, nargs="?", required=True)
     g.add_argument("-outfile_subject", type=str, nargs="?", required=True)
     g.add_argument("-outfile_subject_total", type=str, nargs="?", required=True)
+    a = sub.add_parser("annotate_orthologs",
+                       help="Annotate found orthologs with provided annotation of subject genome lncRNAs.")
+    a.set_defaults(func=annotate_orthologs)
+    a.add_argument("-subject_orthologs", type=str, nargs="?", required=True)
+    a.add_argument("-subject_annotation", type=str, nargs="?", required=True)
+    a.add_argument("-subject_name_regex", type=str, nargs="?", default=None)
+    a.add_argument("-output", type=str, nargs="?", required=True)
+    a.add_argument("-float_precision", type=int, nargs="?", default=8)
+    a.add_argument("-device", type=int, nargs="?", default=0, help="CUDA device index (default: 0)")
     return p
 
 

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/o2a.h"
+#include "o2a_annotate.cuh"
 #include "o2a_chain.cuh"
 #include "o2a_cut.cuh"
 #include "o2a_device.cuh"
@@ -73,6 +74,13 @@ struct o2a_ctx {
     long long cut_n_aln = 0, cut_n_kept = 0;
     cudaEvent_t cut_ev[5] = {};
     bool cut_ev_valid = false;
+    // annotate_orthologs' interval join (o2a_annotate_batch)
+    DevBuf an_qc, an_qs, an_qe, an_qn, an_qstr, an_ac, an_as, an_ae, an_an, an_astr;
+    DevBuf an_prefmax, an_chunkmax, an_cnt, an_span, an_off, an_sums, an_n, an_idx, an_ji, an_oc;
+    bool have_ann = false;
+    long long ann_n_q = 0, ann_n_pairs = 0;
+    cudaEvent_t ann_ev[5] = {};
+    bool ann_ev_valid = false;
 };
 
 #define CU(call)                                                                                  \
@@ -253,6 +261,7 @@ extern "C" int o2a_create(o2a_ctx** out, int device)
     cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
     for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
     for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->cut_ev[i]);
+    for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ann_ev[i]);
     *out = ctx;
     return 0;
 }
@@ -276,7 +285,9 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->ci_rel, &ctx->ci_ql, &ctx->ci_qr, &ctx->ci_sl, &ctx->ci_sr, &ctx->ct_n, &ctx->ct_off,
                       &ctx->ct_aln, &ctx->ct_cnt, &ctx->ct_out, &ctx->ct_sums, &ctx->ct_maxq, &ctx->ct_maxs, &ctx->ct_gen, &ctx->ct_gen_n, &ctx->ct_fast, &ctx->ct_nal, &ctx->ct_span,
                       &ctx->co_off, &ctx->co_qs, &ctx->co_qe, &ctx->co_ss, &ctx->co_se, &ctx->co_score, &ctx->co_cut,
-                      &ctx->co_qlen, &ctx->co_slen, &ctx->co_status};
+                      &ctx->co_qlen, &ctx->co_slen, &ctx->co_status,
+                      &ctx->an_qc, &ctx->an_qs, &ctx->an_qe, &ctx->an_qn, &ctx->an_qstr, &ctx->an_ac, &ctx->an_as, &ctx->an_ae, &ctx->an_an, &ctx->an_astr,
+                      &ctx->an_prefmax, &ctx->an_chunkmax, &ctx->an_cnt, &ctx->an_span, &ctx->an_off, &ctx->an_sums, &ctx->an_n, &ctx->an_idx, &ctx->an_ji, &ctx->an_oc};
     for (DevBuf* b : bufs) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }
 
@@ -289,6 +300,7 @@ extern "C" void o2a_destroy(o2a_ctx* ctx)
     for (int i = 0; i < N_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
     for (int i = 0; i < 5; ++i) if (ctx->cut_ev[i]) cudaEventDestroy(ctx->cut_ev[i]);
+    for (int i = 0; i < 5; ++i) if (ctx->ann_ev[i]) cudaEventDestroy(ctx->ann_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
@@ -1201,5 +1213,122 @@ extern "C" int o2a_get_cut_ms(o2a_ctx* ctx, float* ms)
     if (!ctx || !ms) return O2A_EINVAL;
     if (!ctx->cut_ev_valid) { ctx->err = "no timed o2a_cut_batch yet (o2a_set_timing)"; return O2A_ESTATE; }
     for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms[i], ctx->cut_ev[i], ctx->cut_ev[i + 1]));
+    return 0;
+}
+
+
+// --------------------------------------------------------------------------------------------
+// annotate_orthologs: neighbours of every ortholog in the sorted annotation + JI / OC (o2a_annotate.cuh)
+// --------------------------------------------------------------------------------------------
+extern "C" int o2a_annotate_batch(o2a_ctx* ctx, const o2a_ann_input* in, int64_t* n_pairs)
+{
+    if (!ctx) return O2A_EINVAL;
+    if (!in) { ctx->err = "null input"; return O2A_EINVAL; }
+    if (in->n_q < 0 || in->n_a < 0 || in->n_a > INT32_MAX - ANN_CHUNK) { ctx->err = "bad size"; return O2A_EINVAL; }
+    if (in->distance < 0) { ctx->err = "negative distance"; return O2A_EINVAL; }
+    if (in->n_q > 0 && (!in->q_chrom || !in->q_start || !in->q_end || !in->q_name || !in->q_strand)) {
+        ctx->err = "null ortholog array"; return O2A_EINVAL;
+    }
+    if (in->n_a > 0 && (!in->a_chrom || !in->a_start || !in->a_end || !in->a_name || !in->a_strand)) {
+        ctx->err = "null annotation array"; return O2A_EINVAL;
+    }
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_ann = false;
+    ctx->ann_ev_valid = false;
+    const long long n_q = in->n_q, n_a = in->n_a;
+    int r;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[0], ctx->stream));
+    AnnArgs A{};
+    A.n_q = n_q; A.n_a = n_a; A.distance = in->distance; A.strandness = in->strandness;
+    if (in->mem == O2A_MEM_HOST) {
+        const int32_t* p32 = nullptr; const int8_t* p8 = nullptr;
+        if ((r = upload(ctx, ctx->an_qc, in->q_chrom, (size_t)n_q, &p32))) return r; A.q_chrom = p32;
+        if ((r = upload(ctx, ctx->an_qs, in->q_start, (size_t)n_q, &p32))) return r; A.q_start = p32;
+        if ((r = upload(ctx, ctx->an_qe, in->q_end, (size_t)n_q, &p32))) return r; A.q_end = p32;
+        if ((r = upload(ctx, ctx->an_qn, in->q_name, (size_t)n_q, &p32))) return r; A.q_name = p32;
+        if ((r = upload(ctx, ctx->an_qstr, in->q_strand, (size_t)n_q, &p8))) return r; A.q_strand = (const signed char*)p8;
+        if ((r = upload(ctx, ctx->an_ac, in->a_chrom, (size_t)n_a, &p32))) return r; A.a_chrom = p32;
+        if ((r = upload(ctx, ctx->an_as, in->a_start, (size_t)n_a, &p32))) return r; A.a_start = p32;
+        if ((r = upload(ctx, ctx->an_ae, in->a_end, (size_t)n_a, &p32))) return r; A.a_end = p32;
+        if ((r = upload(ctx, ctx->an_an, in->a_name, (size_t)n_a, &p32))) return r; A.a_name = p32;
+        if ((r = upload(ctx, ctx->an_astr, in->a_strand, (size_t)n_a, &p8))) return r; A.a_strand = (const signed char*)p8;
+    } else {
+        A.q_chrom = in->q_chrom; A.q_start = in->q_start; A.q_end = in->q_end; A.q_name = in->q_name;
+        A.q_strand = (const signed char*)in->q_strand;
+        A.a_chrom = in->a_chrom; A.a_start = in->a_start; A.a_end = in->a_end; A.a_name = in->a_name;
+        A.a_strand = (const signed char*)in->a_strand;
+    }
+    if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[1], ctx->stream));
+    const long long a_chunks = (n_a + ANN_CHUNK - 1) / ANN_CHUNK, q_chunks = (n_q + SCAN_CHUNK - 1) / SCAN_CHUNK + 1;
+    ENS(an_prefmax, (n_a + 1) * 8); ENS(an_chunkmax, (a_chunks + 1) * 8);
+    ENS(an_cnt, (n_q + 1) * sizeof(int)); ENS(an_span, (n_q + 1) * sizeof(int4)); ENS(an_off, (n_q + 1) * 8);
+    ENS(an_sums, (q_chunks + 1) * 8); ENS(an_n, 16);
+    A.prefmax = P<unsigned long long>(ctx->an_prefmax); A.chunk_max = P<unsigned long long>(ctx->an_chunkmax);
+    A.cnt = P<int>(ctx->an_cnt); A.span = P<int4>(ctx->an_span); A.off = P<long long>(ctx->an_off);
+    if (n_a > 0) {
+        const int g = grid_for(ctx, a_chunks, 8);
+        k_ann_chunk_max<<<g, 256, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+        k_ann_scan_max<<<1, 1024, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+        k_ann_prefmax<<<g, 256, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+    }
+    if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[2], ctx->stream));
+    const int per_cta = ANN_THREADS / ANN_G;
+    const int qgrid = grid_for(ctx, (n_q + per_cta - 1) / per_cta, 8);
+    if (n_q > 0) {
+        k_annotate<false><<<qgrid, ANN_THREADS, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+    }
+    CU(cudaMemcpyAsync(ctx->an_n.p, &n_q, 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        const int g = grid_for(ctx, q_chunks, 8);
+        k_scan_chunk_sums<<<g, 256, 0, ctx->stream>>>(P<long long>(ctx->an_n), A.cnt, P<long long>(ctx->an_sums));
+        LAUNCH_CHECK();
+        k_scan_sums<<<1, 1024, 0, ctx->stream>>>(P<long long>(ctx->an_n), P<long long>(ctx->an_sums));
+        LAUNCH_CHECK();
+        k_scan_chunks<<<g, 256, 0, ctx->stream>>>(P<long long>(ctx->an_n), A.cnt, P<long long>(ctx->an_sums), P<long long>(ctx->an_off));
+        LAUNCH_CHECK();
+    }
+    long long pairs = 0;
+    CU(cudaMemcpyAsync(&pairs, P<long long>(ctx->an_off) + n_q, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));      // the pair count sizes the outputs
+    if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[3], ctx->stream));
+    ENS(an_idx, (pairs + 1) * sizeof(int)); ENS(an_ji, (pairs + 1) * 8); ENS(an_oc, (pairs + 1) * 8);
+    A.nb_idx = P<int>(ctx->an_idx); A.ji = P<double>(ctx->an_ji); A.oc = P<double>(ctx->an_oc);
+    if (n_q > 0 && pairs > 0) {
+        k_annotate<true><<<qgrid, ANN_THREADS, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+    }
+    if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[4], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ann_n_q = n_q; ctx->ann_n_pairs = pairs;
+    ctx->have_ann = true;
+    ctx->ann_ev_valid = ctx->timing;
+    if (n_pairs) *n_pairs = pairs;
+    return 0;
+}
+
+extern "C" int o2a_fetch_annotation(o2a_ctx* ctx, int64_t* nb_off, int32_t* nb_idx, double* ji, double* oc)
+{
+    if (!ctx) return O2A_EINVAL;
+    if (!ctx->have_ann) { ctx->err = "no result: call o2a_annotate_batch first"; return O2A_ESTATE; }
+    CU(cudaSetDevice(ctx->device));
+    int r;
+    const size_t nq = (size_t)ctx->ann_n_q, np = (size_t)ctx->ann_n_pairs;
+    if ((r = download(ctx, nb_off, ctx->an_off.p, nq + 1))) return r;
+    if ((r = download(ctx, nb_idx, ctx->an_idx.p, np))) return r;
+    if ((r = download(ctx, ji, ctx->an_ji.p, np))) return r;
+    if ((r = download(ctx, oc, ctx->an_oc.p, np))) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int o2a_get_annotate_ms(o2a_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return O2A_EINVAL;
+    if (!ctx->ann_ev_valid) { ctx->err = "no timed o2a_annotate_batch yet (o2a_set_timing)"; return O2A_ESTATE; }
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms[i], ctx->ann_ev[i], ctx->ann_ev[i + 1]));
     return 0;
 }

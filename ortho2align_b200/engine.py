@@ -298,6 +298,58 @@ class Engine:
         self._check(self.lib.o2a_get_cut_ms(self.h, ms), "o2a_get_cut_ms")
         return dict(zip(self.CUT_STAGES, [float(x) for x in ms]))
 
+    # ---- annotate_orthologs' interval join ---------------------------------
+    ANN_STAGES = ["h2d", "prefmax", "count", "write"]
+
+    def ann_struct(self, q, a, distance=0, strandness=True, device=False):
+        """q / a: dicts of chrom, start, end, name (int32) and strand (int8: +1, -1, 0); `a` sorted by
+        (chrom, start, end, name). numpy arrays, or CUDA tensors when device=True."""
+        s = _lib.O2AAnnInput()
+        keep = []
+
+        def ptr(v, dtype):
+            if device:
+                assert v.is_cuda and v.is_contiguous() and str(v.dtype).endswith(np.dtype(dtype).name), (v.dtype, dtype)
+                keep.append(v)
+                return v.data_ptr()
+            arr = np.ascontiguousarray(v, dtype=dtype)
+            keep.append(arr)
+            return arr.ctypes.data
+
+        s.n_q, s.n_a = len(q["start"]), len(a["start"])
+        for side, cols in (("q", q), ("a", a)):
+            for k in ("chrom", "start", "end", "name"):
+                setattr(s, f"{side}_{k}", ptr(cols[k], np.int32))
+            setattr(s, f"{side}_strand", ptr(cols["strand"], np.int8))
+        s.distance, s.strandness, s.mem = int(distance), int(bool(strandness)), 1 if device else 0
+        s._keepalive = keep
+        return s
+
+    def run_annotate(self, ann_struct):
+        n = C.c_int64(0)
+        self._check(self.lib.o2a_annotate_batch(self.h, C.byref(ann_struct), C.byref(n)), "o2a_annotate_batch")
+        self.ann_n_q, self.ann_n_pairs = int(ann_struct.n_q), int(n.value)
+        return self.ann_n_pairs
+
+    def fetch_annotation(self, pinned=False):
+        nq, npairs = self.ann_n_q, self.ann_n_pairs
+        o = lambda k, n, dt: self._out("ann_" + k, n, dt, pinned)
+        out = dict(nb_off=o("nb_off", nq + 1, np.int64), nb_idx=o("nb_idx", npairs, np.int32),
+                   ji=o("ji", npairs, np.float64), oc=o("oc", npairs, np.float64))
+        self._check(self.lib.o2a_fetch_annotation(self.h, *[_p(out[k]) for k in ("nb_off", "nb_idx", "ji", "oc")]),
+                    "o2a_fetch_annotation")
+        return out
+
+    def annotate_batch(self, q, a, distance=0, strandness=True):
+        """find_neighbours + calc_JI + calc_OC for every ortholog: dict(nb_off, nb_idx, ji, oc)."""
+        self.run_annotate(self.ann_struct(q, a, distance, strandness))
+        return self.fetch_annotation()
+
+    def annotate_ms(self):
+        ms = (C.c_float * 4)()
+        self._check(self.lib.o2a_get_annotate_ms(self.h, ms), "o2a_get_annotate_ms")
+        return dict(zip(self.ANN_STAGES, [float(x) for x in ms]))
+
     # ---- operator-level seams -------------------------------------------------------------------
     def fitter_eval(self, fitter, bg, x=None, q=None, kde_factor=1.0):
         bg = np.ascontiguousarray(bg, dtype=np.int32)

@@ -314,3 +314,35 @@ def producer_workload(n_lnc, seed=0, regions=5, hits_per_region=2000, flank=50_0
                   s_start=s_start.astype(np.int64), s_end=s_end.astype(np.int64), s_minus=s_minus,
                   qleft=gene_start.astype(np.int64), qright=(gene_start + gene_len).astype(np.int64))
     return rel, ranges
+
+
+# ---------------------------------------------------------------------------------------------
+# annotate_orthologs: orthologs and a gene annotation as the columns of o2a_ann_input
+# ---------------------------------------------------------------------------------------------
+def annotate_workload(n_q, n_a, seed=0, n_chrom=24, span=100_000_000, inverted=0.0, long_frac=0.01):
+    """-> (q, a): dicts of chrom, start, end, name (int32) and strand (int8: +1, -1, 0), both sorted by the
+    reference's list key (chrom, start, end, name). Annotation lengths are gene-like (log-normal around 8 kb,
+    `long_frac` of them 0.2-2 Mb — the ranges that make a backward scan long); orthologs are 0.2-6 kb chains.
+    `inverted` = fraction of ranges with end < start (the reference's loops accept them)."""
+    rng = np.random.default_rng(4000 + seed)
+
+    def make(n, lengths):
+        chrom = rng.integers(0, n_chrom, n).astype(np.int32)
+        start = rng.integers(0, max(span, 1), n).astype(np.int64)
+        end = start + lengths
+        if inverted > 0 and n:
+            flip = rng.random(n) < inverted
+            start[flip], end[flip] = end[flip], start[flip].copy()
+        name = rng.integers(0, max(n // 3, 1), n).astype(np.int32)
+        strand = rng.choice(np.array([1, -1, 0], dtype=np.int8), n, p=[0.45, 0.45, 0.1])
+        order = np.lexsort((name, end, start, chrom))
+        return dict(chrom=chrom[order], start=np.minimum(start[order], 2**31 - 1).astype(np.int32),
+                    end=np.minimum(end[order], 2**31 - 1).astype(np.int32), name=name[order], strand=strand[order])
+
+    a_len = np.minimum(rng.lognormal(9.0, 1.2, n_a), 5e5).astype(np.int64)
+    if n_a:
+        long_ones = rng.random(n_a) < long_frac
+        a_len[long_ones] = rng.integers(200_000, 2_000_000, int(long_ones.sum()))
+        a_len[rng.random(n_a) < 0.02] = 0                          # zero-length ranges (touching cases)
+    q_len = rng.integers(200, 6000, n_q).astype(np.int64)
+    return make(n_q, q_len), make(n_a, a_len)

@@ -98,3 +98,25 @@ def test_random_cuts_against_live_reference():
         assert (int(r["qlen"][0]), int(r["slen"][0])) == (cut.qlen, cut.slen)
         n_cut += int((r["cut"] & 1).sum())
     assert n_cut > 200
+
+
+def test_random_interval_joins_against_live_reference(tmp_path):
+    """annotate_orthologs' join: fresh random lists through the reference's get_neighbours / calc_JI / calc_OC
+    (genomicranges.py:2040-2067, 635-685, 497-547), and whole files through pipeline.annotate_orthologs."""
+    from oracle import annotate as OA
+    from oracle import make_golden_annotate as G
+    from ortho2align_b200 import annotate as A
+    from test_annotate import _OracleEngine, _check_join
+    ref = rh.import_reference()
+    for k, (n_q, n_a, distance, strandness, inverted) in enumerate(
+            [(80, 200, 0, True, 0.0), (80, 200, 1200, False, 0.0), (200, 90, 0, True, 0.2), (60, 300, 50, True, 0.0)]):
+        case = G.join_case(ref, 900 + k, n_q, n_a, distance, strandness, inverted=inverted, n_chrom=3, span=30000)
+        _check_join(case, lambda q, a, d, s: OA.annotate_batch(q, a, d, s))
+    for i, fmt in enumerate(("bed6", "gtf", "gff")):
+        orth, ann = G.file_texts(950 + i, 50, 120, fmt)
+        case = G.file_case(ref, orth, ann, fmt)
+        po, pa, out, stats = (tmp_path / f"o{i}.bed", tmp_path / f"a{i}.{fmt}", tmp_path / f"out{i}", tmp_path / f"s{i}")
+        po.write_text(orth); pa.write_text(ann)
+        A.annotate_orthologs(str(po), str(pa), str(out), stats_filename=str(stats), engine=_OracleEngine())
+        assert out.read_text() == case["out"]
+        assert stats.read_text() == case["stats"].replace("{orthologs}", str(po))
