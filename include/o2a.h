@@ -254,7 +254,7 @@ int o2a_get_cut_ms(o2a_ctx *ctx, float *ms /*4*/);
  * order of that sorted list, like `relations['ortholog']`.
  * ------------------------------------------------------------------------------------------- */
 typedef struct o2a_ann_input {
-    int64_t n_q, n_a;                                  /* orthologs, annotation ranges (n_a < 2^31) */
+    int64_t n_q, n_a;                                  /* orthologs, annotation ranges (both < 2^31) */
     const int32_t *q_chrom, *q_start, *q_end, *q_name; /* [n_q] */
     const int8_t  *q_strand;                           /* [n_q] */
     const int32_t *a_chrom, *a_start, *a_end, *a_name; /* [n_a], sorted */

@@ -12,7 +12,7 @@
 // end < start, which the reference's loops accept: when max(start, end) >= min(self.start - d, self.end + 1)),
 // and the running maximum is monotone, so the first candidate is a binary search. The chromosome rank is packed above `end`,
 // which restarts the maximum at every chromosome without a segmented scan.
-// One group of ANN_G lanes per ortholog; count pass -> exclusive scan -> write pass (order = the sorted list's).
+// Count pass -> exclusive scan -> write pass (order = the sorted list's).
 #pragma once
 #include "o2a_device.cuh"
 
@@ -26,15 +26,18 @@ struct AnnArgs {
     int strandness;
     unsigned long long* prefmax;   // [n_a] running max of (chrom, max(start, end))
     unsigned long long* chunk_max; // [chunks + 1]
+    int* blkmax;                   // [ceil(n_a / ANN_BLK)] largest max(start, end) of each block of ANN_BLK ranges
     int* cnt;                      // [n_q] neighbours per ortholog
     int4* span;                    // [n_q] (lo, idx, run_end, unused) found by the count pass
     const long long* off;          // [n_q + 1]
     int* nb_idx; double* ji; double* oc;
+    int* pair_q;                   // [pairs] owner of each pair, for k_ann_ji_oc
+    long long n_pairs;
 };
 
-constexpr int ANN_G = 8;             // lanes per ortholog: typical neighbour counts are 0..3
 constexpr int ANN_THREADS = 256;
 constexpr int ANN_CHUNK = 1024;
+constexpr int ANN_BLK = 32;          // annotation ranges per skip block (one warp of k_ann_prefmax)
 
 __device__ __forceinline__ unsigned long long ann_pack(int chrom, int end)
 {
@@ -94,7 +97,12 @@ __global__ void __launch_bounds__(256) k_ann_prefmax(AnnArgs A)
         unsigned long long base = A.chunk_max[c];
         for (long long j0 = i0; j0 < i1; j0 += 256) {
             const long long i = j0 + threadIdx.x;
-            unsigned long long x = i < i1 ? ann_pack(A.a_chrom[i], max(A.a_start[i], A.a_end[i])) : 0;
+            const int raw = i < i1 ? max(A.a_start[i], A.a_end[i]) : INT32_MIN;
+            unsigned long long x = i < i1 ? ann_pack(A.a_chrom[i], raw) : 0;
+            int bm = raw;                                               // a warp covers exactly one skip block
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bm = max(bm, __shfl_xor_sync(FULL_MASK, bm, d));
+            if (lane_id() == 0 && i < i1) A.blkmax[i / ANN_BLK] = bm;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(FULL_MASK, x, d); if (lane_id() >= d) x = max(x, y); }
             if (lane_id() == 31) s_w[warp_id()] = x;
@@ -111,12 +119,14 @@ __global__ void __launch_bounds__(256) k_ann_prefmax(AnnArgs A)
     }
 }
 
-// BaseGenomicRange.distance (genomicranges.py:439-458) on one chromosome; the caller has checked the chromosomes
-__device__ __forceinline__ long long ann_distance(int qs, int qe, int as, int ae)
+// |BaseGenomicRange.distance| (genomicranges.py:439-458) on one chromosome; the caller has checked the chromosomes.
+// Either difference is positive and below 2^32, so it is exact in unsigned 32-bit arithmetic; the caller compares
+// with min(distance, 2^32 - 1). Only "is it zero" matters beyond that (intersect() :479).
+__device__ __forceinline__ unsigned ann_distance(int qs, int qe, int as, int ae)
 {
-    if (qe < as) return (long long)as - qe;
-    if (ae < qs) return (long long)ae - qs;
-    return 0;
+    if (qe < as) return (unsigned)as - (unsigned)qe;
+    if (ae < qs) return (unsigned)qs - (unsigned)ae;
+    return 0u;
 }
 
 __device__ __forceinline__ bool ann_strand_ok(int strandness, int qstrand, int astrand)
@@ -128,7 +138,7 @@ __device__ __forceinline__ bool ann_strand_ok(int strandness, int qstrand, int a
 // (:460-495): the other range's start/end are taken only when STRICTLY inside self, so a range that merely touches
 // self "intersects" it in all of self. Python int / int is the correctly rounded quotient; below 2^53 that is
 // __ddiv_rn of the two exact doubles. ZeroDivisionError -> 0.
-__device__ __forceinline__ void ann_ji_oc(int qs, int qe, int as, int ae, long long dist, double* ji, double* oc)
+__device__ __forceinline__ void ann_ji_oc(int qs, int qe, int as, int ae, unsigned dist, double* ji, double* oc)
 {
     if (dist != 0) { *ji = 0.0; *oc = 0.0; return; }
     const long long is = (qs < as && as < qe) ? as : qs;
@@ -139,102 +149,151 @@ __device__ __forceinline__ void ann_ji_oc(int qs, int qe, int as, int ae, long l
     *oc = mn == 0 ? 0.0 : __ddiv_rn((double)li, (double)mn);
 }
 
+// One LANE per ortholog for the searches (32 binary searches per warp run in lockstep), the whole WARP for every
+// block of ranges that has to be looked at: the lane owning the ortholog broadcasts it, 32 lanes test 32 ranges, one
+// ballot orders the survivors. (First version: 8 lanes per ortholog for everything — the four groups of a warp
+// diverged in every loop and the kernel was bound by instruction issue, 2.0 ms per pass for 4M orthologs.)
 template <bool WRITE>
 __global__ void __launch_bounds__(ANN_THREADS) k_annotate(AnnArgs A)
 {
     const int lane = lane_id();
-    const int gl = lane & (ANN_G - 1);                         // lane within the group
-    const int gshift = lane & ~(ANN_G - 1);
-    const unsigned gmask = (ANN_G == 32 ? FULL_MASK : ((1u << ANN_G) - 1u)) << gshift;
-    const long long groups = (long long)gridDim.x * (ANN_THREADS / ANN_G);
-    for (long long q = (long long)blockIdx.x * (ANN_THREADS / ANN_G) + threadIdx.x / ANN_G; q < A.n_q; q += groups) {
-        const int qc = A.q_chrom[q], qs = A.q_start[q], qe = A.q_end[q], qstr = A.q_strand[q];
-        int lo, idx;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned dmax = A.distance > 0xffffffffll ? 0xffffffffu : (unsigned)A.distance;
+    const long long warps = (long long)gridDim.x * (ANN_THREADS / 32);
+    for (long long q0 = ((long long)blockIdx.x * (ANN_THREADS / 32) + warp_id()) * 32; q0 < A.n_q; q0 += warps * 32) {
+        const long long q = q0 + lane;
+        const bool valid = q < A.n_q;
+        int qc = 0, qs = 0, qe = 0, qstr = 0, lo = 0, idx = 0;
+        if (valid) { qc = A.q_chrom[q]; qs = A.q_start[q]; qe = A.q_end[q]; qstr = A.q_strand[q]; }
         if (!WRITE) {
-            const int qn = A.q_name[q];
-            // idx = bisect_left(annotation, self) on (chrom, start, end, name)
-            int l = 0, h = (int)A.n_a;
-            while (l < h) {
-                const int m = (l + h) >> 1;
-                const int c = A.a_chrom[m];
-                bool less;
-                if (c != qc) less = c < qc;
-                else {
-                    const int s = A.a_start[m];
-                    if (s != qs) less = s < qs;
+            if (valid) {
+                const int qn = A.q_name[q];
+                // idx = bisect_left(annotation, self) on (chrom, start, end, name)
+                int l = 0, h = (int)A.n_a;
+                while (l < h) {
+                    const int m = (l + h) >> 1;
+                    const int c = A.a_chrom[m];
+                    bool less;
+                    if (c != qc) less = c < qc;
                     else {
-                        const int e = A.a_end[m];
-                        less = e != qe ? e < qe : A.a_name[m] < qn;
+                        const int s = A.a_start[m];
+                        if (s != qs) less = s < qs;
+                        else {
+                            const int e = A.a_end[m];
+                            less = e != qe ? e < qe : A.a_name[m] < qn;
+                        }
                     }
+                    if (less) l = m + 1; else h = m;
                 }
-                if (less) l = m + 1; else h = m;
+                idx = l;
+                // first left candidate: running max of (chrom, max(start, end)) >= (self.chrom, t). A left range is a
+                // neighbour through distance()'s second branch only if end >= self.start - d, and through its first
+                // branch (self.end < start, possible on the left only when self is inverted) only if start > self.end.
+                const long long t64 = min((long long)qs - A.distance, (long long)qe + 1);
+                if (t64 > INT32_MAX) lo = idx;
+                else {
+                    const unsigned long long key = ann_pack(qc, t64 < INT32_MIN ? INT32_MIN : (int)t64);
+                    l = 0; h = idx;
+                    while (l < h) { const int m = (l + h) >> 1; if (A.prefmax[m] < key) l = m + 1; else h = m; }
+                    lo = l;
+                }
             }
-            idx = l;
-            // first left candidate: running max of (chrom, max(start, end)) >= (self.chrom, t). A left range is a
-            // neighbour through distance()'s second branch only if end >= self.start - d, and through its first branch
-            // (self.end < start, possible on the left only when self is inverted) only if start > self.end.
-            const long long t = min((long long)qs - A.distance, (long long)qe + 1);
-            if (t > INT32_MAX) lo = idx;
-            else {
-                const unsigned long long key = ann_pack(qc, t < INT32_MIN ? INT32_MIN : (int)t);
-                l = 0; h = idx;
-                while (l < h) { const int m = (l + h) >> 1; if (A.prefmax[m] < key) l = m + 1; else h = m; }
-                lo = l;
-            }
-        } else {
+        } else if (valid) {
             const int4 sp = A.span[q];
             lo = sp.x; idx = sp.y;
         }
-        long long w = WRITE ? A.off[q] : 0;
+        long long w = (WRITE && valid) ? A.off[q] : 0;
         int n = 0;
-        // left side: every candidate in [lo, idx) is on self's chromosome
-        for (int k0 = lo; k0 < idx; k0 += ANN_G) {
-            const int k = k0 + gl;
-            bool keep = false;
-            int as = 0, ae = 0;
-            long long d = 0;
-            if (k < idx) {
-                as = A.a_start[k]; ae = A.a_end[k];
-                d = ann_distance(qs, qe, as, ae);
-                keep = (d < 0 ? -d : d) <= A.distance && ann_strand_ok(A.strandness, qstr, A.a_strand[k]);
+        // ---- left side: every candidate in [lo, idx) is on self's chromosome. The range is walked in blocks of ANN_BLK
+        // ranges; a block whose largest max(start, end) is below the threshold cannot hold a neighbour and is skipped (a
+        // few long genes keep `lo` hundreds of ranges behind idx, but almost every block in between ends before self
+        // starts). Each lane finds the next block worth reading for its ortholog, then the warp reads those blocks.
+        const long long t64 = min((long long)qs - A.distance, (long long)qe + 1);
+        const int t = t64 < INT32_MIN ? INT32_MIN : (int)min(t64, (long long)INT32_MAX);
+        int b = lo / ANN_BLK;
+        const int b_last = lo < idx ? (idx - 1) / ANN_BLK : -1;
+        for (;;) {
+            bool have = false;
+            while (b <= b_last) { if (A.blkmax[b] >= t) { have = true; break; } ++b; }
+            unsigned m = __ballot_sync(FULL_MASK, have);
+            if (!m) break;
+            while (m) {
+                const int L = __ffs(m) - 1;
+                m &= m - 1;
+                const int qs_L = __shfl_sync(FULL_MASK, qs, L), qe_L = __shfl_sync(FULL_MASK, qe, L);
+                const int qstr_L = __shfl_sync(FULL_MASK, qstr, L);
+                const int lo_L = __shfl_sync(FULL_MASK, lo, L), idx_L = __shfl_sync(FULL_MASK, idx, L);
+                const int k = __shfl_sync(FULL_MASK, b, L) * ANN_BLK + lane;
+                bool keep = false;
+                int as = 0, ae = 0;
+                if (k >= lo_L && k < idx_L) {
+                    as = A.a_start[k]; ae = A.a_end[k];
+                    keep = ann_distance(qs_L, qe_L, as, ae) <= dmax && ann_strand_ok(A.strandness, qstr_L, A.a_strand[k]);
+                }
+                const unsigned bal = __ballot_sync(FULL_MASK, keep);
+                if (WRITE) {
+                    const long long w_L = __shfl_sync(FULL_MASK, w, L);
+                    if (keep) {
+                        const long long o = w_L + __popc(bal & lt_mask);
+                        A.nb_idx[o] = k; A.pair_q[o] = (int)(q0 + L);
+                    }
+                }
+                if (lane == L) { const int c = __popc(bal); n += c; w += c; }
             }
-            const unsigned b = (__ballot_sync(gmask, keep) >> gshift) & (ANN_G == 32 ? FULL_MASK : ((1u << ANN_G) - 1u));
-            if (WRITE && keep) {
-                const long long o = w + __popc(b & ((1u << gl) - 1u));
-                double ji, oc;
-                ann_ji_oc(qs, qe, as, ae, d, &ji, &oc);
-                A.nb_idx[o] = k; A.ji[o] = ji; A.oc[o] = oc;
-            }
-            const int c = __popc(b);
-            w += c; n += c;
+            if (have) ++b;
         }
-        // right side: the run of neighbours that starts at idx
-        for (int k0 = idx;; k0 += ANN_G) {
-            const int k = k0 + gl;
-            bool nb = false, keep = false;
-            int as = 0, ae = 0;
-            long long d = 0;
-            if (k < A.n_a && A.a_chrom[k] == qc) {
-                as = A.a_start[k]; ae = A.a_end[k];
-                d = ann_distance(qs, qe, as, ae);
-                nb = (d < 0 ? -d : d) <= A.distance;
-                keep = nb && ann_strand_ok(A.strandness, qstr, A.a_strand[k]);
+        // ---- right side: the run of neighbours that starts at idx, 32 ranges per step
+        int rk = idx;
+        bool open = valid;
+        for (;;) {
+            unsigned m = __ballot_sync(FULL_MASK, open);
+            if (!m) break;
+            while (m) {
+                const int L = __ffs(m) - 1;
+                m &= m - 1;
+                const int qc_L = __shfl_sync(FULL_MASK, qc, L);
+                const int qs_L = __shfl_sync(FULL_MASK, qs, L), qe_L = __shfl_sync(FULL_MASK, qe, L);
+                const int qstr_L = __shfl_sync(FULL_MASK, qstr, L);
+                const long long k = (long long)__shfl_sync(FULL_MASK, rk, L) + lane;
+                bool nb = false, ok = false;
+                int as = 0, ae = 0;
+                if (k < A.n_a && A.a_chrom[k] == qc_L) {
+                    as = A.a_start[k]; ae = A.a_end[k];
+                    nb = ann_distance(qs_L, qe_L, as, ae) <= dmax;
+                    ok = nb && ann_strand_ok(A.strandness, qstr_L, A.a_strand[k]);
+                }
+                const unsigned bn = __ballot_sync(FULL_MASK, nb);
+                const int run = bn == FULL_MASK ? 32 : __ffs(~bn) - 1;      // neighbours before the first miss
+                const bool keep = ok && lane < run;
+                const unsigned bal = __ballot_sync(FULL_MASK, keep);
+                if (WRITE) {
+                    const long long w_L = __shfl_sync(FULL_MASK, w, L);
+                    if (keep) {
+                        const long long o = w_L + __popc(bal & lt_mask);
+                        A.nb_idx[o] = (int)k; A.pair_q[o] = (int)(q0 + L);
+                    }
+                }
+                if (lane == L) {
+                    const int c = __popc(bal);
+                    n += c; w += c;
+                    if (run < 32) open = false; else rk += 32;
+                }
             }
-            const unsigned full = ANN_G == 32 ? FULL_MASK : ((1u << ANN_G) - 1u);
-            const unsigned bn = (__ballot_sync(gmask, nb) >> gshift) & full;
-            const int run = bn == full ? ANN_G : __ffs(~bn) - 1;        // neighbours before the first miss
-            const unsigned bk = (__ballot_sync(gmask, keep && gl < run) >> gshift) & full;
-            if (WRITE && keep && gl < run) {
-                const long long o = w + __popc(bk & ((1u << gl) - 1u));
-                double ji, oc;
-                ann_ji_oc(qs, qe, as, ae, d, &ji, &oc);
-                A.nb_idx[o] = k; A.ji[o] = ji; A.oc[o] = oc;
-            }
-            const int c = __popc(bk);
-            w += c; n += c;
-            if (run < ANN_G) break;
         }
-        if (!WRITE && gl == 0) { A.cnt[q] = n; A.span[q] = make_int4(lo, idx, 0, 0); }
+        if (!WRITE && valid) { A.cnt[q] = n; A.span[q] = make_int4(lo, idx, 0, 0); }
+    }
+}
+
+// JI / OC of every (ortholog, neighbour) pair, one thread per pair. Kept out of k_annotate<true>: there the two fp64
+// divisions ran under divergence, once per block that held a neighbour, and cost more than the scan itself.
+__global__ void __launch_bounds__(256) k_ann_ji_oc(AnnArgs A)
+{
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < A.n_pairs; p += (long long)gridDim.x * 256) {
+        const int q = A.pair_q[p], k = A.nb_idx[p];
+        const int qs = A.q_start[q], qe = A.q_end[q], as = A.a_start[k], ae = A.a_end[k];
+        double ji, oc;
+        ann_ji_oc(qs, qe, as, ae, ann_distance(qs, qe, as, ae), &ji, &oc);
+        A.ji[p] = ji; A.oc[p] = oc;
     }
 }
 

@@ -76,7 +76,7 @@ struct o2a_ctx {
     bool cut_ev_valid = false;
     // annotate_orthologs' interval join (o2a_annotate_batch)
     DevBuf an_qc, an_qs, an_qe, an_qn, an_qstr, an_ac, an_as, an_ae, an_an, an_astr;
-    DevBuf an_prefmax, an_chunkmax, an_cnt, an_span, an_off, an_sums, an_n, an_idx, an_ji, an_oc;
+    DevBuf an_prefmax, an_chunkmax, an_blkmax, an_cnt, an_span, an_off, an_sums, an_n, an_idx, an_ji, an_oc, an_pq;
     bool have_ann = false;
     long long ann_n_q = 0, ann_n_pairs = 0;
     cudaEvent_t ann_ev[5] = {};
@@ -287,7 +287,7 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->co_off, &ctx->co_qs, &ctx->co_qe, &ctx->co_ss, &ctx->co_se, &ctx->co_score, &ctx->co_cut,
                       &ctx->co_qlen, &ctx->co_slen, &ctx->co_status,
                       &ctx->an_qc, &ctx->an_qs, &ctx->an_qe, &ctx->an_qn, &ctx->an_qstr, &ctx->an_ac, &ctx->an_as, &ctx->an_ae, &ctx->an_an, &ctx->an_astr,
-                      &ctx->an_prefmax, &ctx->an_chunkmax, &ctx->an_cnt, &ctx->an_span, &ctx->an_off, &ctx->an_sums, &ctx->an_n, &ctx->an_idx, &ctx->an_ji, &ctx->an_oc};
+                      &ctx->an_prefmax, &ctx->an_chunkmax, &ctx->an_blkmax, &ctx->an_cnt, &ctx->an_span, &ctx->an_off, &ctx->an_sums, &ctx->an_n, &ctx->an_idx, &ctx->an_ji, &ctx->an_oc, &ctx->an_pq};
     for (DevBuf* b : bufs) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }
 
@@ -1224,7 +1224,7 @@ extern "C" int o2a_annotate_batch(o2a_ctx* ctx, const o2a_ann_input* in, int64_t
 {
     if (!ctx) return O2A_EINVAL;
     if (!in) { ctx->err = "null input"; return O2A_EINVAL; }
-    if (in->n_q < 0 || in->n_a < 0 || in->n_a > INT32_MAX - ANN_CHUNK) { ctx->err = "bad size"; return O2A_EINVAL; }
+    if (in->n_q < 0 || in->n_q > INT32_MAX - 64 || in->n_a < 0 || in->n_a > INT32_MAX - ANN_CHUNK) { ctx->err = "bad size"; return O2A_EINVAL; }
     if (in->distance < 0) { ctx->err = "negative distance"; return O2A_EINVAL; }
     if (in->n_q > 0 && (!in->q_chrom || !in->q_start || !in->q_end || !in->q_name || !in->q_strand)) {
         ctx->err = "null ortholog array"; return O2A_EINVAL;
@@ -1260,10 +1260,10 @@ extern "C" int o2a_annotate_batch(o2a_ctx* ctx, const o2a_ann_input* in, int64_t
     }
     if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[1], ctx->stream));
     const long long a_chunks = (n_a + ANN_CHUNK - 1) / ANN_CHUNK, q_chunks = (n_q + SCAN_CHUNK - 1) / SCAN_CHUNK + 1;
-    ENS(an_prefmax, (n_a + 1) * 8); ENS(an_chunkmax, (a_chunks + 1) * 8);
+    ENS(an_prefmax, (n_a + 1) * 8); ENS(an_chunkmax, (a_chunks + 1) * 8); ENS(an_blkmax, (n_a / ANN_BLK + 2) * sizeof(int));
     ENS(an_cnt, (n_q + 1) * sizeof(int)); ENS(an_span, (n_q + 1) * sizeof(int4)); ENS(an_off, (n_q + 1) * 8);
     ENS(an_sums, (q_chunks + 1) * 8); ENS(an_n, 16);
-    A.prefmax = P<unsigned long long>(ctx->an_prefmax); A.chunk_max = P<unsigned long long>(ctx->an_chunkmax);
+    A.prefmax = P<unsigned long long>(ctx->an_prefmax); A.chunk_max = P<unsigned long long>(ctx->an_chunkmax); A.blkmax = P<int>(ctx->an_blkmax);
     A.cnt = P<int>(ctx->an_cnt); A.span = P<int4>(ctx->an_span); A.off = P<long long>(ctx->an_off);
     if (n_a > 0) {
         const int g = grid_for(ctx, a_chunks, 8);
@@ -1275,7 +1275,7 @@ extern "C" int o2a_annotate_batch(o2a_ctx* ctx, const o2a_ann_input* in, int64_t
         LAUNCH_CHECK();
     }
     if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[2], ctx->stream));
-    const int per_cta = ANN_THREADS / ANN_G;
+    const int per_cta = ANN_THREADS;                 // one lane per ortholog
     const int qgrid = grid_for(ctx, (n_q + per_cta - 1) / per_cta, 8);
     if (n_q > 0) {
         k_annotate<false><<<qgrid, ANN_THREADS, 0, ctx->stream>>>(A);
@@ -1295,10 +1295,13 @@ extern "C" int o2a_annotate_batch(o2a_ctx* ctx, const o2a_ann_input* in, int64_t
     CU(cudaMemcpyAsync(&pairs, P<long long>(ctx->an_off) + n_q, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));      // the pair count sizes the outputs
     if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[3], ctx->stream));
-    ENS(an_idx, (pairs + 1) * sizeof(int)); ENS(an_ji, (pairs + 1) * 8); ENS(an_oc, (pairs + 1) * 8);
+    ENS(an_idx, (pairs + 1) * sizeof(int)); ENS(an_ji, (pairs + 1) * 8); ENS(an_oc, (pairs + 1) * 8); ENS(an_pq, (pairs + 1) * sizeof(int));
     A.nb_idx = P<int>(ctx->an_idx); A.ji = P<double>(ctx->an_ji); A.oc = P<double>(ctx->an_oc);
+    A.pair_q = P<int>(ctx->an_pq); A.n_pairs = pairs;
     if (n_q > 0 && pairs > 0) {
         k_annotate<true><<<qgrid, ANN_THREADS, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+        k_ann_ji_oc<<<grid_for(ctx, (pairs + 255) / 256, 8), 256, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
     }
     if (ctx->timing) CU(cudaEventRecord(ctx->ann_ev[4], ctx->stream));
