@@ -540,6 +540,9 @@ def main():
     ap.add_argument("--ref-lnc", type=int, default=20000, help="lncRNAs per step of --impl reference")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="final", choices=["step", "final"],
+                    help="N > 1: all_gather of the result counters after every step (asynchronous), or once for all "
+                         "steps before the timed region closes")
     ap.add_argument("--score-bits", type=int, default=0, choices=[0, 8, 16, 32],
                     help="score layout of the device-resident arm: 0 = float64 (the reference's dtype), "
                          "8/16/32 = lossless narrow ints + exception lists")
@@ -591,11 +594,18 @@ def main():
     counts_host = torch.zeros((n_slots, 5), dtype=torch.int64).pin_memory()
     counts_dev = torch.zeros((n_slots, 5), dtype=torch.int64, device=dev)
     gathered = torch.zeros((n_slots, 5 * world), dtype=torch.int64, device=dev)
+    gathered_all = torch.zeros((world, n_slots, 5), dtype=torch.int64, device=dev)
     pending = []
+
+    steps_done = [0]
 
     def step_device():
         c = eng.run(dstruct, params)
-        if world > 1:
+        if world > 1 and args.gather == "final":
+            k = steps_done[0] % n_slots
+            steps_done[0] += 1
+            counts_host[k].numpy()[:] = (c.n_survivors, c.n_retained, c.n_chain_hsps, c.n_chains, c.n_failed_lnc)
+        elif world > 1:
             k = len(pending) % n_slots
             counts_host[k].numpy()[:] = (c.n_survivors, c.n_retained, c.n_chain_hsps, c.n_chains, c.n_failed_lnc)
             counts_dev[k].copy_(counts_host[k], non_blocking=True)
@@ -603,6 +613,12 @@ def main():
         return c
 
     def drain_gathers():
+        if world > 1 and args.gather == "final" and steps_done[0]:
+            # one exchange for all the steps since the last drain: slot k of `gathered` = every rank's counters of step k
+            counts_dev.copy_(counts_host, non_blocking=True)
+            dist.all_gather_into_tensor(gathered_all.view(-1), counts_dev.view(-1))
+            gathered.copy_(gathered_all.permute(1, 0, 2).reshape(n_slots, 5 * world))
+            steps_done[0] = 0
         for w in pending:
             w.wait()                 # stream-level wait (no host synchronisation)
         del pending[:]
@@ -610,10 +626,14 @@ def main():
     for _ in range(max(args.warmup, 1)):
         step_device()
     drain_gathers()
+    # NVML is initialised BEFORE the barrier: with N ranks doing it at once it takes a variable number of
+    # milliseconds, and a rank that enters the timed region late makes every other rank wait for it in the closing
+    # exchange (measured: 0.5 ms per step of pure start skew at 8 GPUs).
+    sampler = ClockSampler(local_rank)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
+        torch.cuda.synchronize()
     sampler.start()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -627,6 +647,8 @@ def main():
         score_ms.append(sm["filter"])
         for k, v in sm.items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
+    e_own = torch.cuda.Event(enable_timing=True)
+    e_own.record(stream)             # this rank's own K steps end here; what follows waits for the slowest rank
     drain_gathers()
     e1.record(stream)
     torch.cuda.synchronize()
@@ -636,8 +658,16 @@ def main():
     launches = eng.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # diagnostics: every rank's own step time (without the closing exchange) and the sum of its kernel stages
+        mine = torch.tensor([e0.elapsed_time(e_own) / args.steps, sum(stage_acc.values()) / args.steps],
+                            dtype=torch.float64, device=dev)
+        allr = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr.view(-1), mine)
+        per_rank = {"own_ms_per_step": [round(float(x), 4) for x in allr[:, 0].tolist()],
+                    "kernel_stage_ms_per_step": [round(float(x), 4) for x in allr[:, 1].tolist()]}
     ms_step = float(t.item()) / args.steps
     hsps_all = batch.n_hsp * world
     value = hsps_all / (ms_step * 1e-3)
@@ -771,6 +801,8 @@ def main():
                            "gen_seconds": round(t_gen, 1)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks}
+        if per_rank:
+            line["per_rank"] = per_rank
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
