@@ -208,3 +208,24 @@ def test_gpu_join_device_resident_inputs(engine):
     ms = engine.annotate_ms()
     engine.set_timing(False)
     assert set(ms) == {"h2d", "prefmax", "count", "write"} and all(v >= 0 for v in ms.values())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block", range(4))
+def test_gpu_join_random_sweep(engine, block):
+    """Randomised shapes: tiny to mid-size lists, 1-6 chromosomes, dense and sparse spans, inverted ranges, all
+    distance / strandness settings — every batch bit-exact against the oracle."""
+    from oracle import annotate as OA
+    rng = np.random.default_rng(9000 + block)
+    for it in range(60):
+        n_q = int(rng.choice([0, 1, 2, 31, 32, 33, 100, 257, 1500]))
+        n_a = int(rng.choice([0, 1, 2, 31, 32, 33, 64, 65, 1023, 1024, 1025, 5000]))
+        n_chrom = int(rng.integers(1, 7))
+        span = int(rng.choice([50, 1000, 30_000, 1_000_000]))
+        inverted = float(rng.choice([0.0, 0.0, 0.05, 0.5]))
+        distance = int(rng.choice([0, 0, 1, 10, 500, 100_000]))
+        strandness = bool(rng.integers(0, 2))
+        q, a = _random_columns(int(rng.integers(1 << 30)), n_q, n_a, n_chrom, span, inverted,
+                               long_frac=float(rng.choice([0.0, 0.01, 0.2])))
+        _same(engine.annotate_batch(q, a, distance, strandness), OA.annotate_batch(q, a, distance, strandness),
+              f"block {block} it {it}: {n_q}x{n_a} chrom={n_chrom} span={span} inv={inverted} d={distance} s={strandness}")
