@@ -555,7 +555,18 @@ static int run_chain(o2a_ctx* ctx)
         A.lnc_status = P<int>(ctx->status);
         A.mid_list = P<int>(ctx->mid_list); A.mid_count = P<int>(ctx->big_count) + 2;
         A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count) + 1;
-        k_gather_retained<<<grid_for(ctx, (na + 7) / 8, 8), 256, 0, ctx->stream>>>(A);
+        // Coordinates read in place over PCIe: the SMs' 32-byte reads and the copy engine's reads of the next chunk
+        // compete for the link's read-request slots, and a machine-filling gather starves the DMA (8 CTAs per SM:
+        // 13.0 ms per C2 batch, 1 per SM: 12.6 ms). A small grid keeps enough requests in flight for the gather
+        // itself (it is request-latency bound either way) and leaves the rest to the uploads. Measured per C2 batch, one
+        // context / two contexts alternating: 1184 CTAs 13.0 / 12.07 ms, 148: 12.57 / 11.53, 74: 12.04 / 11.14, 32: 12.51 / 10.92.
+        int gather_grid = grid_for(ctx, (na + 7) / 8, 8);
+        if (ctx->coords_zero_copy) {
+            int want = ctx->sm_count / 2;
+            if (const char* e = getenv("O2A_GATHER_CTAS")) { if (atoi(e) > 0) want = atoi(e); }
+            if (want < gather_grid) gather_grid = want;
+        }
+        k_gather_retained<<<gather_grid, 256, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
         {
             int r = stage_event(ctx, O2A_STAGE_CHAIN);
