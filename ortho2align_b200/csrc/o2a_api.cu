@@ -561,7 +561,7 @@ static int run_chain(o2a_ctx* ctx)
         // itself (it is request-latency bound either way) and leaves the rest to the uploads. Measured per C2 batch, one
         // context / two contexts alternating: 1184 CTAs 13.0 / 12.07 ms, 148: 12.57 / 11.53, 74: 12.04 / 11.14, 32: 12.51 / 10.92.
         int gather_grid = grid_for(ctx, (na + 7) / 8, 8);
-        if (ctx->coords_zero_copy) {
+        if (ctx->coords_zero_copy && ctx->pipelined_chunks > 1) {      // only then do uploads run beside the gather
             int want = ctx->sm_count / 2;
             if (const char* e = getenv("O2A_GATHER_CTAS")) { if (atoi(e) > 0) want = atoi(e); }
             if (want < gather_grid) gather_grid = want;
