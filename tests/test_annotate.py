@@ -229,3 +229,26 @@ def test_gpu_join_random_sweep(engine, block):
                                long_frac=float(rng.choice([0.0, 0.01, 0.2])))
         _same(engine.annotate_batch(q, a, distance, strandness), OA.annotate_batch(q, a, distance, strandness),
               f"block {block} it {it}: {n_q}x{n_a} chrom={n_chrom} span={span} inv={inverted} d={distance} s={strandness}")
+
+
+def test_columnar_order_is_pythons_tuple_order():
+    """Ranks + lexsort must order exactly like the reference's SortedKeyList key (chrom, start, end, name) with
+    Python's str comparison (code points: 'Z' < 'a', 'chr10' < 'chr2', non-ASCII last) and be stable for equal keys."""
+    import random
+    from ortho2align_b200 import annotate as A
+    r = random.Random(3)
+    chroms = ["chr1", "chr10", "chr2", "chrX", "Chr1", "1", "10", "2", "chrUn_é", "", "chr1 "]
+    names = ["a", "B", "b", "a1", "a10", "a2", "", "é", "Z", "_"]
+    rows = [(r.choice(chroms), r.randrange(5), r.randrange(5), r.choice(names)) for _ in range(400)]
+    rg = A.Ranges([x[0] for x in rows], [x[1] for x in rows], [x[2] for x in rows], [0] * len(rows),
+                  [x[3] for x in rows], "bed6")
+    other = A.Ranges(["chr3", "chr1"], [1, 2], [3, 4], [0, 0], ["zz", "a"], "bed6")   # widens both dictionaries
+    q, a, q_order, a_order = A.columnar(rg, other)
+    assert q_order.tolist() == sorted(range(len(rows)), key=lambda i: rows[i])          # sorted() is stable too
+    assert a_order.tolist() == [1, 0]
+    # ranks are order-isomorphic to the strings across BOTH lists
+    assert (q["chrom"][0] <= q["chrom"][-1]) and set(a["chrom"].tolist()) <= set(range(len(set(chroms) | {"chr3"})))
+    k = {c: int(v) for c, v in zip([rows[i][0] for i in q_order], q["chrom"])}
+    k.update({c: int(v) for c, v in zip([other.chrom[i] for i in a_order], a["chrom"])})
+    ordered = sorted(k)
+    assert [k[c] for c in ordered] == sorted(k.values())
