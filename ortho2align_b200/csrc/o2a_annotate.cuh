@@ -12,7 +12,7 @@
 // end < start, which the reference's loops accept: when max(start, end) >= min(self.start - d, self.end + 1)),
 // and the running maximum is monotone, so the first candidate is a binary search. The chromosome rank is packed above `end`,
 // which restarts the maximum at every chromosome without a segmented scan.
-// Count pass -> exclusive scan -> write pass (order = the sorted list's).
+// Count pass -> exclusive scan -> write pass (order = the sorted list's) -> JI / OC per pair.
 #pragma once
 #include "o2a_device.cuh"
 
@@ -28,7 +28,7 @@ struct AnnArgs {
     unsigned long long* chunk_max; // [chunks + 1]
     int* blkmax;                   // [ceil(n_a / ANN_BLK)] largest max(start, end) of each block of ANN_BLK ranges
     int* cnt;                      // [n_q] neighbours per ortholog
-    int4* span;                    // [n_q] (lo, idx, run_end, unused) found by the count pass
+    int4* span;                    // [n_q] (lo, idx, -, -) found by the count pass: first left candidate, bisect_left position
     const long long* off;          // [n_q + 1]
     int* nb_idx; double* ji; double* oc;
     int* pair_q;                   // [pairs] owner of each pair, for k_ann_ji_oc
