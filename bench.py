@@ -758,47 +758,63 @@ def main():
     e2e_stage_ms = eng.stage_ms()
     single_engine_ms = dt / e2e_steps * 1e3
     dual_engine_ms = None
+    dual_engine_error = None
     if args.e2e_engines == 2:
         # Two contexts on the same GPU, one host thread each (different ctxs may be driven from different threads,
         # include/o2a.h): every batch still crosses PCIe in full and its result is read back in full, but the link
         # no longer idles while a batch's last chunk computes and its result is downloaded.
+        # Nothing in here may take a rank out of the collectives below: failures are recorded, not raised.
         import threading
-        eng2 = Engine(local_rank)
-        hstruct2 = eng2.host_struct(hb, with_kde, coords=keep_alive["coords"].numpy(), narrow=narrow, bg16=bg16)
-        eng2.run(hstruct2, params)
-        eng2.fetch(survivors=False, pinned=True)
+        eng2 = None
+        try:
+            eng2 = Engine(local_rank)
+            hstruct2 = eng2.host_struct(hb, with_kde, coords=keep_alive["coords"].numpy(), narrow=narrow, bg16=bg16)
+            eng2.run(hstruct2, params)
+            eng2.fetch(survivors=False, pinned=True)
+        except Exception as ex:                                  # e.g. out of device memory for the second workspace
+            dual_engine_error = f"{type(ex).__name__}: {ex}"
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e2e_steps = 2 * ((e2e_steps + 1) // 2)
-        results = [None, None]
+        dual_steps = 2 * ((e2e_steps + 1) // 2)
+        results, errors = [None, None], []
 
         def worker(i, e, hs):
-            for _ in range(e2e_steps // 2):
-                e.run(hs, params)
-                results[i] = e.fetch(survivors=False, pinned=True)
+            try:
+                for _ in range(dual_steps // 2):
+                    e.run(hs, params)
+                    results[i] = e.fetch(survivors=False, pinned=True)
+            except Exception as ex:
+                errors.append(f"{type(ex).__name__}: {ex}")
 
-        threads = [threading.Thread(target=worker, args=(0, eng, hstruct)),
-                   threading.Thread(target=worker, args=(1, eng2, hstruct2))]
-        t0 = time.perf_counter()
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-        torch.cuda.synchronize()
-        dt2 = time.perf_counter() - t0
-        assert np.array_equal(results[0].chain_idx, results[1].chain_idx) and np.array_equal(results[0].chain_idx, res.chain_idx)
-        dual_engine_ms = dt2 / e2e_steps * 1e3
-        # the slower rank decides, on every rank alike (8 ranks x 2 contexts can be host-bound: then one context is kept)
-        both = torch.tensor([single_engine_ms, dual_engine_ms], dtype=torch.float64, device=dev)
+        dt2 = float("inf")
+        if dual_engine_error is None:
+            threads = [threading.Thread(target=worker, args=(0, eng, hstruct)),
+                       threading.Thread(target=worker, args=(1, eng2, hstruct2))]
+            t0 = time.perf_counter()
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            torch.cuda.synchronize()
+            dt2 = time.perf_counter() - t0
+            if errors:
+                dual_engine_error = errors[0]
+            elif not (np.array_equal(results[0].chain_idx, results[1].chain_idx)
+                      and np.array_equal(results[0].chain_idx, res.chain_idx)):
+                dual_engine_error = "the two contexts returned different chains"
+        dual_engine_ms = None if dual_engine_error else dt2 / dual_steps * 1e3
+        # the slowest rank decides, on every rank alike (8 ranks x 2 contexts can be host-bound: then one context is kept)
+        both = torch.tensor([single_engine_ms, dual_engine_ms if dual_engine_ms is not None else 1e30],
+                            dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(both, op=dist.ReduceOp.MAX)
         if float(both[1]) <= float(both[0]):
-            dt = dt2
+            dt, e2e_steps = dt2, dual_steps
         else:
-            dt = single_engine_ms * 1e-3 * e2e_steps
             args.e2e_engines = 1
-        eng2.close()
+        if eng2 is not None:
+            eng2.close()
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -817,7 +833,7 @@ def main():
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy,
            "score_layout": LAYOUTS[narrow_bits],
            "pipelined_chunks": chunks, "engines_per_gpu": args.e2e_engines, "single_engine_ms_per_step": single_engine_ms,
-           "dual_engine_ms_per_step": dual_engine_ms,
+           "dual_engine_ms_per_step": dual_engine_ms, "dual_engine_error": dual_engine_error,
            ("stage_ms_last_step" if chunks <= 1 else "stage_ms_last_chunk"): e2e_stage_ms}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
