@@ -157,3 +157,44 @@ def test_background_patches_follow_the_reference_order():
     assert patch_background([5, 5]) == [5, 5, 1]
     assert patch_background([1, 7]) == [1, 7, 0]
     assert patch_background([3, 4]) == [3, 4]
+
+
+class _OracleEngineForStream:
+    """Stands in for Engine in the CPU test of BatchStream: the oracle computes, with a per-batch delay that makes
+    completion order differ from input order."""
+    created, closed = 0, 0
+
+    def __init__(self, device):
+        type(self).created += 1
+        self.device = device
+
+    def build_batch(self, batch, fitter, fdr, alpha, gapopen, gapextend, **kw):
+        import time
+        from oracle import oracle as O
+        time.sleep(0.02 * (batch.n_lnc % 3))
+        if getattr(batch, "_poison", False):
+            raise RuntimeError("poisoned batch")
+        return O.build_batch(batch, fitter, fdr, alpha, gapopen, gapextend)
+
+    def close(self):
+        type(self).closed += 1
+
+
+def test_batch_stream_keeps_order_and_surfaces_errors():
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    from ortho2align_b200.stream import BatchStream
+    batches = [synth.workload(1, n_lnc=n, seed=s, hsps_per_region=120, n_bg=300) for s, n in enumerate([3, 1, 2, 4, 2, 1, 3])]
+    E = _OracleEngineForStream
+    E.created = E.closed = 0
+    got = list(BatchStream(devices=(0,), contexts=2, engine_factory=E).map(iter(batches), "hist", True))
+    assert len(got) == len(batches) and E.created == 2 and E.closed == 2
+    for b, r in zip(batches, got):
+        exp = O.build_batch(b, "hist", True)
+        assert np.array_equal(r.chain_idx, exp.chain_idx) and np.array_equal(r.thr, exp.thr)
+        assert np.array_equal(r.best_aln, exp.best_aln)
+    assert list(BatchStream(devices=(0, 1), contexts=1, engine_factory=E).map([], "hist", True)) == []
+    batches[3]._poison = True
+    with pytest.raises(RuntimeError, match="poisoned"):
+        list(BatchStream(devices=(0,), contexts=2, engine_factory=E).map(batches, "hist", True))
+    assert E.created == E.closed
