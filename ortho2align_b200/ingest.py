@@ -74,7 +74,7 @@ class IngestResult:
     def range_dict(self, a, which):
         """Decoded qrange ('q') or srange ('s') dict of global alignment index `a`. Consecutive alignments of
         a lncRNA carry the same qrange text: the same dict object is returned for identical text."""
-        return _decode_cached(self, self.range_text(a, which))
+        return _decode_cached(self, self.range_text(a, which), which)
 
     def range_text(self, a, which):
         """Raw JSON text of the qrange / srange object of alignment `a` (bytes)."""
@@ -103,12 +103,15 @@ class IngestResult:
             pass
 
 
-def _decode_cached(owner, text):
-    last = getattr(owner, "_last_range", None)
+def _decode_cached(owner, text, which="q"):
+    """One-entry cache per side: the alignments of a lncRNA repeat the same qrange text (callers ask q, s, q, s, ...,
+    so a shared entry would never hit), and the caller recognises a repeated qrange by object identity."""
+    key = "_last_range_" + which
+    last = getattr(owner, key, None)
     if last is not None and last[0] == text:
         return last[1]
     d = json.loads(text)
-    owner._last_range = (text, d)
+    setattr(owner, key, (text, d))
     return d
 
 
@@ -211,7 +214,7 @@ class SidecarResult:
         return bytes(self._range_text[self._range_off[k]:self._range_off[k + 1]])
 
     def range_dict(self, a, which):
-        return _decode_cached(self, self.range_text(a, which))
+        return _decode_cached(self, self.range_text(a, which), which)
 
     def hsp_dict(self, h):
         return _hsp_dict(self.batch, self.score_is_int, h)

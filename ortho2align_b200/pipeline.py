@@ -81,7 +81,7 @@ def _ingest_json(alignments_files, bg_files):
             continue
         d = alignment_dicts
         out.append((batch, 0, len(d), (lambda k, d=d: d[k]["qrange"]), (lambda k, d=d: d[k]["srange"]),
-                    (lambda k, idx, d=d: [d[k]["HSPs"][int(j)] for j in idx])))
+                    (lambda k, idx, d=d: [d[k]["HSPs"][int(j)] for j in idx]), None))
     return out
 
 
@@ -109,7 +109,8 @@ def _ingest_native(alignments_files, bg_files, threads, cache=None):
         a0, a1 = aln_off[l], aln_off[l + 1]
         out[i] = (b, l, a1 - a0,
                   (lambda k, a0=a0: r.range_dict(a0 + k, "q")), (lambda k, a0=a0: r.range_dict(a0 + k, "s")),
-                  (lambda k, idx, a0=a0: r.hsp_dicts(int(hsp_off[a0 + k]) + idx)))
+                  (lambda k, idx, a0=a0: r.hsp_dicts(int(hsp_off[a0 + k]) + idx)),
+                  (r, a0))                   # columnar source of the lncRNA's HSPs, for the native record formatter
     return out
 
 
@@ -142,9 +143,44 @@ def _run_shards(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
     return results
 
 
+def _format_chains_native(chain_desc, strings, qplus, src, threads):
+    """The four ortholog files as bytes (query TSV, query BED12, subject TSV, subject BED12) for the chains collected by
+    build_orthologs, in their order: one gather per column from the ingest's columnar batch, one library call."""
+    from . import records_native
+    n = len(chain_desc)
+    ids, results = {}, []
+    res_id = np.empty(n, dtype=np.int64)
+    for k, d in enumerate(chain_desc):
+        r = d[0]
+        if id(r) not in ids:
+            ids[id(r)] = len(results)
+            results.append(r)
+        res_id[k] = ids[id(r)]
+    c0 = np.fromiter((d[1] for d in chain_desc), dtype=np.int64, count=n)
+    c1 = np.fromiter((d[2] for d in chain_desc), dtype=np.int64, count=n)
+    base = np.fromiter((d[3] for d in chain_desc), dtype=np.int64, count=n)
+    lens = c1 - c0
+    hsp_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=hsp_off[1:])
+    gidx = np.empty(int(hsp_off[-1]), dtype=np.int64)
+    pval = np.empty(int(hsp_off[-1]), dtype=np.float64)
+    for rid, res in enumerate(results):
+        sel = np.nonzero(res_id == rid)[0]
+        l = lens[sel]
+        within = np.arange(int(l.sum()), dtype=np.int64) - np.repeat(np.cumsum(l) - l, l)   # 0..len-1 inside each chain
+        src_pos = np.repeat(c0[sel], l) + within
+        dst_pos = np.repeat(hsp_off[sel], l) + within
+        gidx[dst_pos] = np.asarray(res.chain_idx)[src_pos].astype(np.int64) + np.repeat(base[sel], l)
+        pval[dst_pos] = np.asarray(res.chain_pq)[src_pos]
+    b = src.batch
+    cols = [np.asarray(getattr(b, k))[gidx] for k in ("qstart", "qend", "sstart", "send")]
+    return records_native.format_records(hsp_off, *cols, np.asarray(b.score)[gidx], np.asarray(src.score_is_int)[gidx],
+                                         pval, np.asarray(qplus, dtype=np.uint8), strings, threads=threads or 1)
+
+
 def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gapopen=5, gapextend=2,
                     fdr=False, cores=1, timeout=None, silent=False, stats_filename=None, devices=None,
-                    ingest="native", cache=None):
+                    ingest="native", cache=None, records="native"):
     """A build_orthologs step of the pipeline (signature of `pipeline.py:801-812`).
 
     `cores` = threads of the native JSON ingest (the per-lncRNA process pool it configured in the
@@ -155,6 +191,8 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     `fitting`: 'hist' | 'kde' (reference) or 'empirical' (extension). `cache`: path of a columnar
     sidecar (ingest.save_sidecar): written after the first native parse of these directories, and read
     back instead of the JSON on later runs as long as file names, sizes and mtimes are unchanged.
+    `records`: 'native' (with the native ingest: the four ortholog files are formatted from the columnar arrays by
+    libo2a_ingest.so, include/o2a_records.h) or 'python' (records.chain_records per chain; same bytes).
     """
     alignments_dir = Path(alignments)
     background_dir = Path(background)
@@ -202,11 +240,15 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     t_phase = time.perf_counter()
     # ---- assemble exactly what the pool would have returned ---------------------------------------------
     orthologs, exceptions = [], []
+    # native record formatting: per chain (result object, chain slice, first HSP of its alignment in the source batch)
+    chain_desc, chain_strings, chain_qplus, chain_src = [], [], [], None
     for i, item in enumerate(loaded):
         if isinstance(item, ExceptionLogger):
             exceptions.append(item)
             continue
-        _, _, n_alns, qrange_of, srange_of, hsps_of = item
+        _, _, n_alns, qrange_of, srange_of, hsps_of, columnar_src = item
+        if records != "native":
+            columnar_src = None
         batch, res, l = per_lnc[i]
         if res.status[l] != STATUS_OK:
             st = int(res.status[l])
@@ -224,7 +266,15 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
             srange = Range.from_dict(srange_of(k))
             srange.name = qrange.name                                   # pipeline.py:781
             c0, c1 = int(res.chain_off[a]), int(res.chain_off[a + 1])
-            if c1 > c0:
+            if c1 > c0 and columnar_src is not None:
+                chain_src, a0_src = columnar_src
+                chain_desc.append((res, c0, c1, int(chain_src.batch.hsp_off[a0_src + k])))
+                chain_strings += [str(qrange.chrom), str(qrange.name), str(srange.chrom)]
+                chain_qplus.append(qrange.strand in ["+", "."])
+                q_orth.append(None)                                     # the text is produced for all chains at once below
+                s_orth.append(None)
+                aligned = True
+            elif c1 > c0:
                 hsps = hsps_of(k, res.chain_idx[c0:c1])
                 rec = chain_records(hsps, as_pvals(res.chain_pq[c0:c1]), qrange, srange.chrom, qrange.name)
                 q_orth.append((rec[0], rec[1]))
@@ -246,10 +296,12 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
             query_exception_ranges.append(exception.variable)
 
     dist_found = [len(group[0]) for group in orthologs]
-    query_orthologs_bed12 = [o[1] for g in orthologs for o in g[0]]
-    subject_orthologs_bed12 = [o[1] for g in orthologs for o in g[1]]
-    query_orthologs_total = [o[0] for g in orthologs for o in g[0]]
-    subject_orthologs_total = [o[0] for g in orthologs for o in g[1]]
+    native_text = _format_chains_native(chain_desc, chain_strings, chain_qplus, chain_src, cores) if chain_desc else None
+    if native_text is None:
+        query_orthologs_bed12 = [o[1] for g in orthologs for o in g[0]]
+        subject_orthologs_bed12 = [o[1] for g in orthologs for o in g[1]]
+        query_orthologs_total = [o[0] for g in orthologs for o in g[0]]
+        subject_orthologs_total = [o[0] for g in orthologs for o in g[1]]
 
     query_dropped, subject_dropped = [], []
     for g in orthologs:                                                 # pipeline.py:895-908
@@ -268,13 +320,19 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     if not os.path.exists(outdir):
         os.mkdir(outdir)
     j = lambda n: os.path.join(outdir, n)
-    for name, records in (("significant.query_orthologs.bed", query_orthologs_bed12),
-                          ("significant.subject_orthologs.bed", subject_orthologs_bed12),
-                          ("significant.query_orthologs.tsv", query_orthologs_total),
-                          ("significant.subject_orthologs.tsv", subject_orthologs_total)):
-        with open(j(name), "w") as f:
-            for record in records:
-                f.write(record + "\n")
+    if native_text is not None:
+        for name, text in (("significant.query_orthologs.tsv", native_text[0]), ("significant.query_orthologs.bed", native_text[1]),
+                           ("significant.subject_orthologs.tsv", native_text[2]), ("significant.subject_orthologs.bed", native_text[3])):
+            with open(j(name), "wb") as f:
+                f.write(text)
+    else:
+        for name, lines in (("significant.query_orthologs.bed", query_orthologs_bed12),
+                            ("significant.subject_orthologs.bed", subject_orthologs_bed12),
+                            ("significant.query_orthologs.tsv", query_orthologs_total),
+                            ("significant.subject_orthologs.tsv", subject_orthologs_total)):
+            with open(j(name), "w") as f:
+                for record in lines:
+                    f.write(record + "\n")
     for name, ranges in (("insignificant.query_orthologs.bed", query_dropped),
                          ("insignificant.subject_orthologs.bed", subject_dropped),
                          ("query_exceptions.bed", query_exception_list)):
