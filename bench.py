@@ -459,7 +459,8 @@ def stage_files(argv):
     cores = args.cores or len(os.sched_getaffinity(0))
     if args.runner == "oracle":
         from oracle import oracle as O
-        pipeline._run_shards = lambda batches, devices, fitter, fdr, alpha, go, ge: [O.build_batch(b, fitter, fdr, alpha, go, ge) for b in batches]
+        pipeline._run_shards = lambda batches, devices, fitter, fdr, alpha, go, ge: [
+            O.build_batch(b.to_columnar() if hasattr(b, "to_columnar") else b, fitter, fdr, alpha, go, ge) for b in batches]
     b, m = synth.workload(2, n_lnc=args.lnc, with_meta=True, seed=1)
     items = synth.to_json_dicts(b, m)
     out = {"lncRNAs": args.lnc, "hsps": b.n_hsp, "cores": cores, "runner": args.runner}

@@ -87,8 +87,8 @@ typedef struct o2a_batch {
     const double  *score;      /* [n_hsp] */
     int32_t mem;               /* O2A_MEM_HOST | O2A_MEM_DEVICE (applies to every pointer above) */
     int32_t reserved;
-    int64_t max_aln_hsps;      /* max over a of hsp_off[a+1]-hsp_off[a]; 0 = let the library find out */
-    int64_t max_lnc_bg;        /* max over l of bg_off[l+1]-bg_off[l];   0 = let the library find out */
+    int64_t max_aln_hsps;      /* max over a of hsp_off[a+1]-hsp_off[a]; 0 = let the library find out. A hint: it is */
+    int64_t max_lnc_bg;        /* max over l of bg_off[l+1]-bg_off[l];   verified, and an understated value fails the call (O2A_EINVAL) */
     const int32_t *coords;     /* optional [4*n_hsp] AoS (qstart,qend,sstart,send) per HSP, 16-byte aligned:
                                   one 16 B read per retained HSP instead of four (matters for zero-copy
                                   reads from pinned host memory); NULL = use the four SoA arrays */
@@ -190,6 +190,20 @@ int  o2a_coords_zero_copy(const o2a_ctx *ctx);
  * O2A_PIPELINE_MIN_HSPS) so that the H2D copy of chunk c+1 overlaps the kernels of chunk c; with more than
  * one chunk the stage times of o2a_get_stage_ms are those of the LAST chunk and "h2d" spans the others. */
 int  o2a_pipeline_chunks(const o2a_ctx *ctx);
+/* How the coordinate records of the retained HSPs (~1 % of a BLAST-like batch) of a HOST batch reach the device:
+ *   ZERO_COPY    read in place over PCIe by the gather kernel (needs pinned, device-mapped caller memory)
+ *   HOST_GATHER  the GPU lists the retained HSP indices into pinned host memory, host threads (O2A_GATHER_THREADS,
+ *                default min(16, cores)) collect the 16-byte records, one small DMA per chunk brings them back;
+ *                works with pageable caller memory; a chunk that retains more than 1/8 of its HSPs is uploaded whole
+ *   UPLOAD       all 16 B per HSP cross PCIe
+ *   AUTO         ZERO_COPY when the caller's coordinate arrays are mapped, else HOST_GATHER
+ * Environment override: O2A_COORDS=zerocopy|gather|upload. o2a_coords_mode: what the last host call used. */
+#define O2A_COORDS_AUTO 0
+#define O2A_COORDS_ZERO_COPY 1
+#define O2A_COORDS_HOST_GATHER 2
+#define O2A_COORDS_UPLOAD 3
+int  o2a_set_coords_mode(o2a_ctx *ctx, int mode);
+int  o2a_coords_mode(const o2a_ctx *ctx);
 int  o2a_set_timing(o2a_ctx *ctx, int enabled);
 int  o2a_get_stage_ms(o2a_ctx *ctx, float *ms /*O2A_STAGE_COUNT*/);
 

@@ -21,8 +21,9 @@ def build_ingest(force=False):
     """Host-only C++ JSON ingest library (g++)."""
     os.makedirs(LIB_DIR, exist_ok=True)
     inc = os.path.join(os.path.dirname(HERE), "include")
-    srcs = [INGEST_SRC, os.path.join(CSRC, "o2a_blast.cpp"), os.path.join(CSRC, "o2a_records.cpp")]   # JSON ingest + BLAST table reader + record formatter, one library
-    deps = srcs + [os.path.join(inc, "o2a_ingest.h"), os.path.join(inc, "o2a_blast.h"), os.path.join(inc, "o2a_records.h")]
+    # JSON ingest + columnar packer + BLAST table reader + record formatter, one library
+    srcs = [INGEST_SRC, os.path.join(CSRC, "o2a_pack.cpp"), os.path.join(CSRC, "o2a_blast.cpp"), os.path.join(CSRC, "o2a_records.cpp")]
+    deps = srcs + [os.path.join(CSRC, "o2a_pack.h"), os.path.join(inc, "o2a_ingest.h"), os.path.join(inc, "o2a_blast.h"), os.path.join(inc, "o2a_records.h")]
     if not force and os.path.exists(INGEST_LIB) and all(os.path.getmtime(INGEST_LIB) >= os.path.getmtime(d) for d in deps):
         return INGEST_LIB
     cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-o", INGEST_LIB] + srcs

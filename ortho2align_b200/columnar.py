@@ -122,7 +122,7 @@ class ColumnarBatch:
         info = np.iinfo(dt)
         sc = self.score
         with np.errstate(invalid="ignore"):
-            ok = (sc == np.floor(sc)) & (sc > info.min) & (sc <= info.max)
+            ok = (sc == np.floor(sc)) & (sc > info.min) & (sc <= info.max) & ~((sc == 0) & np.signbit(sc))
         q = np.where(ok, sc, info.min).astype(dt)
         exc = np.nonzero(~ok)[0]
         aln_of = np.searchsorted(self.hsp_off, exc, side="right") - 1

@@ -3,7 +3,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/o2a.h"
@@ -12,6 +16,7 @@
 #include "o2a_cut.cuh"
 #include "o2a_device.cuh"
 #include "o2a_fit.cuh"
+#include "o2a_front.cuh"
 #include "o2a_score.cuh"
 
 using namespace o2a;
@@ -24,6 +29,63 @@ struct DevBuf {
 };
 
 constexpr int N_EVENTS = O2A_STAGE_COUNT + 1;
+
+// A few persistent host threads for the host-gather mode (collecting the retained HSPs' coordinate records from the
+// caller's host arrays): started on first use, parked on a condition variable between jobs.
+class HostPool {
+public:
+    explicit HostPool(int n) : n_(n < 1 ? 1 : n) {
+        for (int i = 0; i < n_; ++i) threads_.emplace_back([this, i]() { worker(i); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    // fn(k) for k in [0, n): contiguous blocks, one per worker; returns when all are done
+    void run(long long n, const std::function<void(long long)>& fn) {
+        if (n <= 0) return;
+        if (n < 8192) { for (long long k = 0; k < n; ++k) fn(k); return; }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn; total_ = n; pending_ = n_; ++gen_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this]() { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void worker(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(long long)>* fn; long long n;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&]() { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_; n = total_;
+            }
+            const long long lo = n * id / n_, hi = n * (id + 1) / n_;
+            for (long long k = lo; k < hi; ++k) (*fn)(k);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(long long)>* fn_ = nullptr;
+    long long total_ = 0;
+    int pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
 constexpr int SM_COUNT_FALLBACK = 148;
 constexpr long long UV_MAX_RANGE = 1ll << 18;   // 1 MiB of counters per resident CTA
 
@@ -54,6 +116,22 @@ struct o2a_ctx {
     DevBuf ret_coord, ret_score, ret_slot, in_coords;
     const int4* coords4 = nullptr;    // AoS coordinates actually used (device or mapped host), or null
     DevBuf big_list, mid_list, big_count, counters;
+    // per-chunk work lists / counters: stages of different chunks overlap on different streams, so nothing is shared.
+    // stage_cnt: 4 ints per chunk = (alignments queued for k_pq, for k_rank_big, for k_chain_small, for k_chain_big)
+    DevBuf pq_list, cbig_list, stage_cnt;
+    DevBuf csort_k0, csort_k1, csort_v0, csort_v1;   // k_chain_big's sort scratch (k_rank_big has sort_*)
+    DevBuf maxchk;                                   // device-side check of the caller's max_aln_hsps / max_lnc_bg
+    // coordinates of a host batch: how the retained HSPs' records reach the chaining kernels
+    int coords_mode_req = O2A_COORDS_AUTO, coords_mode_used = O2A_COORDS_AUTO;
+    cudaStream_t tail_stream = nullptr;              // host-gather mode: scatter + chaining of chunk c beside the front of chunk c+1
+    cudaEvent_t front_ev[16] = {};
+    cudaEvent_t tail_join = nullptr;
+    DevBuf ret_base, list_cursor, d_stage;
+    long long* h_list = nullptr; size_t h_list_cap = 0;     // mapped pinned: global HSP indices of the retained HSPs
+    int4* h_stage = nullptr; size_t h_stage_cap = 0;        // pinned: their gathered coordinate records
+    long long* h_cursor = nullptr;                          // pinned [16]: retained HSPs listed per chunk
+    int gather_threads = 0;
+    HostPool* pool = nullptr;
     DevBuf fit_cnt, fc_val, fc_cnt, fc_n, fit_list, fit_list_n;
     bool coords_zero_copy = false;   // qstart..send read in place from pinned, device-mapped host memory
     // chunk view [vl0, vl1) lncRNAs / [va0, va1) alignments the stage launchers work on (whole batch by default)
@@ -260,6 +338,15 @@ extern "C" int o2a_create(o2a_ctx** out, int device)
     cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
     for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&ctx->front_ev[i], cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->tail_join, cudaEventDisableTiming);
+    cudaHostAlloc((void**)&ctx->h_cursor, 16 * sizeof(long long), cudaHostAllocPortable);
+    {
+        unsigned hc = std::thread::hardware_concurrency();
+        ctx->gather_threads = hc ? (int)(hc < 16 ? hc : 16) : 4;
+        if (const char* e = getenv("O2A_GATHER_THREADS")) { if (atoi(e) > 0) ctx->gather_threads = atoi(e); }
+    }
     for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->cut_ev[i]);
     for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ann_ev[i]);
     *out = ctx;
@@ -276,7 +363,9 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
                       &ctx->orient_scores, &ctx->chain_slot, &ctx->best_key, &ctx->best_aln, &ctx->ret_coord,
                       &ctx->ret_score, &ctx->ret_slot, &ctx->in_coords, &ctx->big_list,
-                      &ctx->mid_list, &ctx->big_count, &ctx->counters, &ctx->fit_cnt, &ctx->fc_val, &ctx->fc_cnt, &ctx->fc_n, &ctx->fit_list,
+                      &ctx->mid_list, &ctx->big_count, &ctx->counters, &ctx->pq_list, &ctx->cbig_list, &ctx->stage_cnt,
+                      &ctx->csort_k0, &ctx->csort_k1, &ctx->csort_v0, &ctx->csort_v1, &ctx->maxchk, &ctx->ret_base,
+                      &ctx->list_cursor, &ctx->d_stage, &ctx->fit_cnt, &ctx->fc_val, &ctx->fc_cnt, &ctx->fc_n, &ctx->fit_list,
                       &ctx->fit_list_n, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
                       &ctx->cb_qe, &ctx->cb_ss, &ctx->cb_se, &ctx->cb_sc, &ctx->cb_id, &ctx->cb_total, &ctx->cb_prev,
                       &ctx->cb_f, &ctx->cb_chain, &ctx->off_a, &ctx->off_b, &ctx->out_i32, &ctx->out_f64a,
@@ -299,6 +388,13 @@ extern "C" void o2a_destroy(o2a_ctx* ctx)
     free_all(ctx);
     for (int i = 0; i < N_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+    for (int i = 0; i < 16; ++i) if (ctx->front_ev[i]) cudaEventDestroy(ctx->front_ev[i]);
+    if (ctx->tail_join) cudaEventDestroy(ctx->tail_join);
+    if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
+    if (ctx->h_list) cudaFreeHost(ctx->h_list);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_cursor) cudaFreeHost(ctx->h_cursor);
+    delete ctx->pool;
     for (int i = 0; i < 5; ++i) if (ctx->cut_ev[i]) cudaEventDestroy(ctx->cut_ev[i]);
     for (int i = 0; i < 5; ++i) if (ctx->ann_ev[i]) cudaEventDestroy(ctx->ann_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -336,6 +432,13 @@ extern "C" void o2a_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int64_t o2a_launch_count(const o2a_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
 extern "C" int o2a_coords_zero_copy(const o2a_ctx* ctx) { return ctx && ctx->coords_zero_copy ? 1 : 0; }
 extern "C" int o2a_pipeline_chunks(const o2a_ctx* ctx) { return ctx ? ctx->pipelined_chunks : 0; }
+extern "C" int o2a_set_coords_mode(o2a_ctx* ctx, int mode)
+{
+    if (!ctx || mode < O2A_COORDS_AUTO || mode > O2A_COORDS_UPLOAD) return O2A_EINVAL;
+    ctx->coords_mode_req = mode;
+    return 0;
+}
+extern "C" int o2a_coords_mode(const o2a_ctx* ctx) { return ctx ? ctx->coords_mode_used : 0; }
 extern "C" int o2a_set_timing(o2a_ctx* ctx, int enabled) { if (!ctx) return O2A_EINVAL; ctx->timing = enabled != 0; return 0; }
 extern "C" int o2a_get_stage_ms(o2a_ctx* ctx, float* ms)
 {
@@ -454,44 +557,23 @@ static int ensure_sort_scratch(o2a_ctx* ctx, int grid, long long cap)
     return 0;
 }
 
-static int run_score(o2a_ctx* ctx)
+// per-chunk counters inside stage_cnt (see o2a_ctx)
+enum { CNT_PQ = 0, CNT_RANKBIG = 1, CNT_MID = 2, CNT_CBIG = 3, CNT_PER_CHUNK = 4 };
+static int* chunk_cnt(o2a_ctx* ctx, int chunk, int which) { return P<int>(ctx->stage_cnt) + chunk * CNT_PER_CHUNK + which; }
+
+// Front of the path for the view's alignments, on stream `st`: score filter + p / q / keep (k_front: one warp per
+// alignment), then the alignments it queued (k_pq, k_rank_big).
+static int run_score(o2a_ctx* ctx, int chunk, cudaStream_t st)
 {
     const o2a_batch& b = ctx->b;
     const o2a_params& p = ctx->prm;
-    ENS(n_surv, b.n_aln * sizeof(int)); ENS(n_keep, b.n_aln * sizeof(int));
-    ENS(surv_idx, b.n_hsp * sizeof(int)); ENS(surv_p, b.n_hsp * sizeof(double)); ENS(surv_x, b.n_hsp * sizeof(double));
-    ENS(surv_pq, b.n_hsp * sizeof(double)); ENS(surv_keep, b.n_hsp);
-    ENS(big_list, (b.n_aln + 1) * sizeof(int)); ENS(mid_list, (b.n_aln + 1) * sizeof(int));
-    ENS(big_count, 4 * sizeof(int));
-    CU(cudaMemsetAsync(ctx->big_count.p, 0, 4 * sizeof(int), ctx->stream));
     // per-alignment arrays are indexed relative to the view; everything per HSP / per lncRNA absolutely
     const long long a0 = ctx->va0, na = ctx->va1 - ctx->va0;
     if (na <= 0) return stage_event(ctx, O2A_STAGE_PQ);
     const long long* hsp_off_v = (const long long*)b.hsp_off + a0;
     const int* aln_lnc_v = P<int>(ctx->aln_lnc) + a0;
-    if (b.score_bits == 8)
-        k_filter_q<signed char><<<grid_for(ctx, na, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
-            na, hsp_off_v, aln_lnc_v, (const signed char*)b.score_q, (const long long*)b.exc_off + a0,
-            b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
-            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
-    else if (b.score_bits == 16)
-        k_filter_q<short><<<grid_for(ctx, na, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
-            na, hsp_off_v, aln_lnc_v, (const short*)b.score_q, (const long long*)b.exc_off + a0,
-            b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
-            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
-    else if (b.score_bits == 32)
-        k_filter_q<int><<<grid_for(ctx, na, 20), FILTERQ_THREADS, 0, ctx->stream>>>(
-            na, hsp_off_v, aln_lnc_v, (const int*)b.score_q, (const long long*)b.exc_off + a0,
-            b.exc_pos, b.exc_val, b.n_hsp, P<double>(ctx->thr), P<int>(ctx->status),
-            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
-    else
-        k_filter<<<grid_for(ctx, na, 20), FILTER_THREADS, 0, ctx->stream>>>(
-            na, hsp_off_v, aln_lnc_v, b.score, P<double>(ctx->thr), P<int>(ctx->status),
-            P<int>(ctx->n_surv) + a0, P<int>(ctx->surv_idx), P<double>(ctx->surv_x));
-    LAUNCH_CHECK();
-    int r = stage_event(ctx, O2A_STAGE_PQ);
-    if (r) return r;
-    PqArgs A{};
+    FrontArgs F{};
+    PqArgs& A = F.P;
     A.n_aln = na; A.hsp_off = hsp_off_v; A.aln_lnc = aln_lnc_v;
     A.lnc_status = P<int>(ctx->status); A.n_surv = P<int>(ctx->n_surv) + a0; A.thr = P<double>(ctx->thr);
     A.fits = P<LncFit>(ctx->fits); A.tbl_k = P<int>(ctx->tbl_k); A.tbl_cum = P<double>(ctx->tbl_cum);
@@ -500,27 +582,29 @@ static int run_score(o2a_ctx* ctx)
     A.kde_factor = b.kde_factor; A.fitter = p.fitter; A.fdr = p.fdr; A.alpha = p.alpha;
     A.surv_x = P<double>(ctx->surv_x); A.surv_p = P<double>(ctx->surv_p); A.surv_pq = P<double>(ctx->surv_pq);
     A.surv_keep = P<unsigned char>(ctx->surv_keep); A.n_keep = P<int>(ctx->n_keep) + a0;
-    A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count);
-    // warp variant: alignments with <= 256 survivors; CTA variant: the rest (up to RANK_SMALL_MAX in shared
-    // memory, beyond that p only + k_rank_big)
-    // (the two variants own disjoint alignments: the CTA variant runs beside the warp variant on the second stream)
-    const bool fork = b.max_aln_hsps > 256;
-    if (fork) {
-        CU(cudaEventRecord(ctx->aux_fork, ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
-        k_pq<64, 14, 256, RANK_SMALL_MAX, 256, 128, TBL_SMEM_MAX><<<grid_for(ctx, na, 14), 64, 0, ctx->aux_stream>>>(A);
-        LAUNCH_CHECK();
-        CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
-    }
-    k_pq<32, 32, 0, 256, 128, 32, 128><<<grid_for(ctx, na, 32), 32, 0, ctx->stream>>>(A);
+    A.pq_list = P<int>(ctx->pq_list) + a0; A.pq_count = chunk_cnt(ctx, chunk, CNT_PQ);
+    A.big_list = P<int>(ctx->big_list) + a0; A.big_count = chunk_cnt(ctx, chunk, CNT_RANKBIG);
+    F.score = b.score; F.score_q = b.score_q; F.exc_off = b.exc_off ? (const long long*)b.exc_off + a0 : nullptr;
+    F.exc_pos = b.exc_pos; F.exc_val = b.exc_val; F.n_hsp_total = b.n_hsp;
+    F.n_surv = P<int>(ctx->n_surv) + a0; F.surv_idx = P<int>(ctx->surv_idx); F.surv_x = P<double>(ctx->surv_x);
+    F.pq_list = P<int>(ctx->pq_list) + a0; F.pq_count = chunk_cnt(ctx, chunk, CNT_PQ);
+    const int grid = grid_for(ctx, (na + FRONT_WARPS - 1) / FRONT_WARPS, FRONT_CTAS_PER_SM);
+    if (b.score_bits == 8) k_front<signed char><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
+    else if (b.score_bits == 16) k_front<short><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
+    else if (b.score_bits == 32) k_front<int><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
+    else k_front<double><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
     LAUNCH_CHECK();
-    if (fork) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[O2A_STAGE_PQ], st));
+    // what k_front queued: more than FRONT_SCAP survivors, or many non-integral scores (a small grid: the list is
+    // empty for BLAST-like data, and a CTA of an empty list exits at once)
+    k_pq<64, 14, RANK_SMALL_MAX, 256, 128, TBL_SMEM_MAX><<<grid_for(ctx, na, b.max_aln_hsps > 4 * FRONT_SCAP ? 14 : 2), 64, 0, st>>>(A);
+    LAUNCH_CHECK();
     if (p.fdr && b.max_aln_hsps > RANK_SMALL_MAX) {
         int g2 = grid_for(ctx, b.n_aln, 2);
-        r = ensure_sort_scratch(ctx, g2, b.max_aln_hsps);
+        int r = ensure_sort_scratch(ctx, g2, b.max_aln_hsps);
         if (r) return r;
-        k_rank_big<<<g2, RANKBIG_THREADS, 0, ctx->stream>>>(
-            P<int>(ctx->big_list), P<int>(ctx->big_count), hsp_off_v, p.alpha, P<int>(ctx->n_surv) + a0,
+        k_rank_big<<<g2, RANKBIG_THREADS, 0, st>>>(
+            A.big_list, A.big_count, hsp_off_v, p.alpha, P<int>(ctx->n_surv) + a0,
             P<int>(ctx->n_keep) + a0, P<double>(ctx->surv_p), P<double>(ctx->surv_pq), P<unsigned char>(ctx->surv_keep),
             P<unsigned long long>(ctx->sort_k0), P<unsigned long long>(ctx->sort_k1), P<unsigned int>(ctx->sort_v0),
             P<unsigned int>(ctx->sort_v1), b.max_aln_hsps);
@@ -529,94 +613,129 @@ static int run_score(o2a_ctx* ctx)
     return 0;
 }
 
-static int run_chain(o2a_ctx* ctx)
+static void fill_chain_args(o2a_ctx* ctx, int chunk, ChainArgs& A)
 {
     const o2a_batch& b = ctx->b;
     const o2a_params& p = ctx->prm;
+    const long long a0 = ctx->va0, na = ctx->va1 - ctx->va0;
+    A.n_aln = na; A.hsp_off = (const long long*)b.hsp_off + a0; A.aln_lnc = P<int>(ctx->aln_lnc) + a0;
+    A.qlen = (const long long*)b.qlen + a0; A.slen = (const long long*)b.slen + a0;
+    A.qstart = b.qstart; A.qend = b.qend; A.sstart = b.sstart; A.send = b.send; A.score = b.score;
+    A.coords4 = ctx->coords4;
+    A.ret_coord = P<int4>(ctx->ret_coord); A.ret_score = P<double>(ctx->ret_score); A.ret_slot = P<int>(ctx->ret_slot);
+    A.n_surv = P<int>(ctx->n_surv) + a0; A.n_keep = P<int>(ctx->n_keep) + a0; A.surv_idx = P<int>(ctx->surv_idx);
+    A.surv_keep = P<unsigned char>(ctx->surv_keep); A.surv_x = P<double>(ctx->surv_x);
+    A.gapopen = p.gapopen; A.gapextend = p.gapextend;
+    A.best_value = p.best_value;
+    A.chain_len = P<int>(ctx->chain_len) + a0; A.chain_orient = P<unsigned char>(ctx->chain_orient) + a0;
+    A.chain_score = P<double>(ctx->chain_score) + a0; A.orient_scores = P<double>(ctx->orient_scores) + 2 * a0;
+    A.chain_slot = P<int>(ctx->chain_slot); A.best_key = P<double>(ctx->best_key) + a0;
+    A.lnc_status = P<int>(ctx->status);
+    A.mid_list = P<int>(ctx->mid_list) + a0; A.mid_count = chunk_cnt(ctx, chunk, CNT_MID);
+    A.big_list = P<int>(ctx->cbig_list) + a0; A.big_count = chunk_cnt(ctx, chunk, CNT_CBIG);
+}
+
+static int ensure_chain_buffers(o2a_ctx* ctx)
+{
+    const o2a_batch& b = ctx->b;
     ENS(chain_len, b.n_aln * sizeof(int)); ENS(chain_orient, b.n_aln); ENS(chain_score, b.n_aln * sizeof(double));
     ENS(orient_scores, 2 * b.n_aln * sizeof(double)); ENS(chain_slot, b.n_hsp * sizeof(int));
     ENS(best_key, b.n_aln * sizeof(double)); ENS(best_aln, b.n_lnc * sizeof(long long));
     ENS(ret_coord, b.n_hsp * sizeof(int4)); ENS(ret_score, b.n_hsp * sizeof(double)); ENS(ret_slot, b.n_hsp * sizeof(int));
-    const long long l0 = ctx->vl0, nl = ctx->vl1 - ctx->vl0, a0 = ctx->va0, na = ctx->va1 - ctx->va0;
+    return 0;
+}
+
+// Coordinates + score of the retained HSPs next to each other (device-resident, uploaded or zero-copy coordinates)
+static int run_gather(o2a_ctx* ctx, int chunk, cudaStream_t st)
+{
+    const long long na = ctx->va1 - ctx->va0;
+    if (na <= 0) return 0;
+    ChainArgs A{};
+    fill_chain_args(ctx, chunk, A);
+    // Coordinates read in place over PCIe: the SMs' 32-byte reads and the copy engine's reads of the next chunk
+    // compete for the link's read-request slots, and a machine-filling gather starves the DMA (8 CTAs per SM:
+    // 13.0 ms per C2 batch, 1 per SM: 12.6 ms). A small grid keeps enough requests in flight for the gather
+    // itself (it is request-latency bound either way) and leaves the rest to the uploads. Measured per C2 batch, one
+    // context / two contexts alternating: 1184 CTAs 13.0 / 12.07 ms, 148: 12.57 / 11.53, 74: 12.04 / 11.14, 32: 12.51 / 10.92.
+    int gather_grid = grid_for(ctx, (na + 7) / 8, 8);
+    if (ctx->coords_zero_copy && ctx->pipelined_chunks > 1) {      // only then do uploads run beside the gather
+        int want = ctx->sm_count / 2;
+        if (const char* e = getenv("O2A_GATHER_CTAS")) { if (atoi(e) > 0) want = atoi(e); }
+        if (want < gather_grid) gather_grid = want;
+    }
+    k_gather_retained<<<gather_grid, 256, 0, st>>>(A);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// Chaining of the view's alignments + best ortholog of its lncRNAs, on stream `st` (ret_* filled by the gather)
+static int run_chain(o2a_ctx* ctx, int chunk, cudaStream_t st)
+{
+    const o2a_batch& b = ctx->b;
+    const o2a_params& p = ctx->prm;
+    const long long l0 = ctx->vl0, nl = ctx->vl1 - ctx->vl0, na = ctx->va1 - ctx->va0;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[O2A_STAGE_CHAIN], st));
     if (na > 0) {
         ChainArgs A{};
-        A.n_aln = na; A.hsp_off = (const long long*)b.hsp_off + a0; A.aln_lnc = P<int>(ctx->aln_lnc) + a0;
-        A.qlen = (const long long*)b.qlen + a0; A.slen = (const long long*)b.slen + a0;
-        A.qstart = b.qstart; A.qend = b.qend; A.sstart = b.sstart; A.send = b.send; A.score = b.score;
-        A.coords4 = ctx->coords4;
-        A.ret_coord = P<int4>(ctx->ret_coord); A.ret_score = P<double>(ctx->ret_score); A.ret_slot = P<int>(ctx->ret_slot);
-        A.n_surv = P<int>(ctx->n_surv) + a0; A.n_keep = P<int>(ctx->n_keep) + a0; A.surv_idx = P<int>(ctx->surv_idx);
-        A.surv_keep = P<unsigned char>(ctx->surv_keep); A.surv_x = P<double>(ctx->surv_x);
-        A.gapopen = p.gapopen; A.gapextend = p.gapextend;
-        A.best_value = p.best_value;
-        A.chain_len = P<int>(ctx->chain_len) + a0; A.chain_orient = P<unsigned char>(ctx->chain_orient) + a0;
-        A.chain_score = P<double>(ctx->chain_score) + a0; A.orient_scores = P<double>(ctx->orient_scores) + 2 * a0;
-        A.chain_slot = P<int>(ctx->chain_slot); A.best_key = P<double>(ctx->best_key) + a0;
-        A.lnc_status = P<int>(ctx->status);
-        A.mid_list = P<int>(ctx->mid_list); A.mid_count = P<int>(ctx->big_count) + 2;
-        A.big_list = P<int>(ctx->big_list); A.big_count = P<int>(ctx->big_count) + 1;
-        // Coordinates read in place over PCIe: the SMs' 32-byte reads and the copy engine's reads of the next chunk
-        // compete for the link's read-request slots, and a machine-filling gather starves the DMA (8 CTAs per SM:
-        // 13.0 ms per C2 batch, 1 per SM: 12.6 ms). A small grid keeps enough requests in flight for the gather
-        // itself (it is request-latency bound either way) and leaves the rest to the uploads. Measured per C2 batch, one
-        // context / two contexts alternating: 1184 CTAs 13.0 / 12.07 ms, 148: 12.57 / 11.53, 74: 12.04 / 11.14, 32: 12.51 / 10.92.
-        int gather_grid = grid_for(ctx, (na + 7) / 8, 8);
-        if (ctx->coords_zero_copy && ctx->pipelined_chunks > 1) {      // only then do uploads run beside the gather
-            int want = ctx->sm_count / 2;
-            if (const char* e = getenv("O2A_GATHER_CTAS")) { if (atoi(e) > 0) want = atoi(e); }
-            if (want < gather_grid) gather_grid = want;
-        }
-        k_gather_retained<<<gather_grid, 256, 0, ctx->stream>>>(A);
-        LAUNCH_CHECK();
-        {
-            int r = stage_event(ctx, O2A_STAGE_CHAIN);
-            if (r) return r;
-        }
+        fill_chain_args(ctx, chunk, A);
         // The few alignments beyond the warp path (queued by the gather) are chained beside it: k_chain_small goes
-        // first on the main stream (a grid of mostly idle CTAs around ~10^2 long serial ones) and the machine-filling
+        // first on `st` (a grid of mostly idle CTAs around ~10^2 long serial ones) and the machine-filling
         // k_chain_warp follows on the second stream as soon as the gather is done, not after k_chain_small.
         const bool fork = b.max_aln_hsps > CHAIN_WARP_MAX;
         if (fork) {
-            CU(cudaEventRecord(ctx->aux_fork, ctx->stream));
+            CU(cudaEventRecord(ctx->aux_fork, st));
             CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
-            k_chain_small<<<grid_for(ctx, na, 8), CHAIN_THREADS, 0, ctx->stream>>>(A);
+            k_chain_small<<<grid_for(ctx, na, 8), CHAIN_THREADS, 0, st>>>(A);
             LAUNCH_CHECK();
         }
         k_chain_warp<<<grid_for(ctx, (na + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0,
-                       fork ? ctx->aux_stream : ctx->stream>>>(A);
+                       fork ? ctx->aux_stream : st>>>(A);
         LAUNCH_CHECK();
         if (fork) {
             CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
+            CU(cudaStreamWaitEvent(st, ctx->aux_join, 0));
         }
         if (b.max_aln_hsps > CHAIN_SMALL_MAX) {
             int g2 = grid_for(ctx, b.n_aln, 2);
             const long long cap = b.max_aln_hsps;
-            int r = ensure_sort_scratch(ctx, g2, cap);
-            if (r) return r;
+            ENS(csort_k0, (size_t)g2 * cap * 8); ENS(csort_k1, (size_t)g2 * cap * 8);
+            ENS(csort_v0, (size_t)g2 * cap * 4); ENS(csort_v1, (size_t)g2 * cap * 4);
             ENS(cb_qs, (size_t)g2 * cap * 4); ENS(cb_qe, (size_t)g2 * cap * 4); ENS(cb_ss, (size_t)g2 * cap * 4);
             ENS(cb_se, (size_t)g2 * cap * 4); ENS(cb_sc, (size_t)g2 * cap * 8); ENS(cb_id, (size_t)g2 * cap * 4);
             ENS(cb_total, (size_t)g2 * (cap + 2) * 8); ENS(cb_prev, (size_t)g2 * (cap + 2) * 4);
             ENS(cb_f, (size_t)g2 * (cap + 2) * 4); ENS(cb_chain, (size_t)g2 * cap * 2 * 4);
-            ChainBigScratch S{P<unsigned long long>(ctx->sort_k0), P<unsigned long long>(ctx->sort_k1),
-                              P<unsigned int>(ctx->sort_v0), P<unsigned int>(ctx->sort_v1),
+            ChainBigScratch S{P<unsigned long long>(ctx->csort_k0), P<unsigned long long>(ctx->csort_k1),
+                              P<unsigned int>(ctx->csort_v0), P<unsigned int>(ctx->csort_v1),
                               P<int>(ctx->cb_qs), P<int>(ctx->cb_qe), P<int>(ctx->cb_ss), P<int>(ctx->cb_se),
                               P<double>(ctx->cb_sc), P<int>(ctx->cb_id), P<double>(ctx->cb_total), P<int>(ctx->cb_prev),
                               P<int>(ctx->cb_f), P<int>(ctx->cb_chain), cap};
-            k_chain_big<<<g2, CHAINBIG_THREADS, 0, ctx->stream>>>(A, S);
+            k_chain_big<<<g2, CHAINBIG_THREADS, 0, st>>>(A, S);
             LAUNCH_CHECK();
         }
     }
-    int r = stage_event(ctx, O2A_STAGE_BEST);
-    if (r) return r;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[O2A_STAGE_BEST], st));
     if (nl > 0) {
         // aln_off values are absolute alignment indices: per-alignment arrays are passed unshifted here
-        k_best<<<(unsigned)((nl + 127) / 128), 128, 0, ctx->stream>>>(
+        k_best<<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(
             nl, (const long long*)b.aln_off + l0, P<int>(ctx->status) + l0, P<int>(ctx->n_surv), P<int>(ctx->n_keep),
             P<int>(ctx->chain_len), P<double>(ctx->chain_score), P<double>(ctx->orient_scores),
             P<double>(ctx->best_key), p.best_function, P<long long>(ctx->best_aln) + l0);
         LAUNCH_CHECK();
     }
+    return 0;
+}
+
+static int ensure_pinned(o2a_ctx* ctx, void** p, size_t* cap, size_t bytes)
+{
+    if (*cap >= bytes && *p) return 0;
+    if (*p) { cudaFreeHost(*p); *p = nullptr; *cap = 0; }
+    const size_t want = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(p, want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "cudaHostAlloc(" + std::to_string(want) + ") failed";
+        return O2A_ENOMEM;
+    }
+    *cap = want;
     return 0;
 }
 
@@ -651,8 +770,7 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
     int r;
     if ((r = stage_event(ctx, O2A_STAGE_H2D))) return r;
     // Host batches large enough to amortise the extra launches are processed as a few lncRNA chunks:
-    // the bulk arrays of chunk c+1 cross PCIe on the copy stream while the kernels of chunk c (whose
-    // gather reads the coordinates of the retained HSPs in place over the same link) run.
+    // the bulk arrays of chunk c+1 cross PCIe on the copy stream while the kernels of chunk c run.
     std::vector<DeferredCopy> deferred_copies;
     int n_chunks = 1;
     long long pipeline_min_hsps = 4ll << 20;
@@ -669,6 +787,7 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
     }
     std::vector<DeferredCopy>* deferred = n_chunks > 1 ? &deferred_copies : nullptr;
     ctx->pipelined_chunks = n_chunks;
+    int coords_mode = O2A_COORDS_AUTO;           // how the retained HSPs' coordinate records reach the device
     if (batch->mem == O2A_MEM_HOST) {
         // the reference pickles file names to workers which json.load them (pipeline.py:743-754);
         // here the columnar arrays cross PCIe once
@@ -706,9 +825,13 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
             if ((r = upload_bulk(ctx, ctx->in_score, batch->score, (size_t)batch->n_hsp, sizeof(double), SLICE_HSP, deferred, &d8))) return r;
             b.score = (const double*)d8;
         }
-        // Coordinates are only ever read for the HSPs that reach the chaining (~1 %): when the caller's
-        // arrays are pinned + device-mapped (o2a_host_alloc / cudaHostAlloc / cudaHostRegister) the
-        // gather kernel reads them in place over PCIe instead of copying 16 B per HSP.
+        // Coordinates are only ever read for the HSPs that reach the chaining (~1 %). Three ways to get those records
+        // to the device (o2a_set_coords_mode / env O2A_COORDS=zerocopy|gather|upload; AUTO = zero-copy when the
+        // caller's arrays are pinned + device-mapped, else host gather):
+        //   zero-copy   the gather kernel reads them in place over PCIe (32-byte reads)
+        //   host gather the GPU lists the retained HSP indices into pinned host memory, host threads collect the
+        //               16-byte records, one small DMA brings them back (works with pageable caller memory)
+        //   upload      all 16 B per HSP cross PCIe (what a dense batch, where everything is retained, wants)
         ctx->coords_zero_copy = false;
         ctx->coords4 = nullptr;
         auto mapped = [](const void* hp) -> const void* {
@@ -719,26 +842,36 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
             }
             return at.devicePointer;
         };
-        const bool try_zero_copy = batch->n_hsp > 0 && !getenv("O2A_NO_ZERO_COPY");
-        if (batch->coords) {
-            const void* dp = try_zero_copy ? mapped(batch->coords) : nullptr;
-            if (dp) { ctx->coords4 = (const int4*)dp; ctx->coords_zero_copy = true; }
+        int want = ctx->coords_mode_req;
+        if (const char* e = getenv("O2A_COORDS")) {
+            if (!strcmp(e, "zerocopy")) want = O2A_COORDS_ZERO_COPY;
+            else if (!strcmp(e, "gather")) want = O2A_COORDS_HOST_GATHER;
+            else if (!strcmp(e, "upload")) want = O2A_COORDS_UPLOAD;
+        }
+        if (getenv("O2A_NO_ZERO_COPY") && (want == O2A_COORDS_AUTO || want == O2A_COORDS_ZERO_COPY)) want = O2A_COORDS_HOST_GATHER;
+        const void* dp[4] = {nullptr, nullptr, nullptr, nullptr};
+        bool can_map = false;
+        if (batch->n_hsp > 0 && (want == O2A_COORDS_AUTO || want == O2A_COORDS_ZERO_COPY)) {
+            if (batch->coords) { dp[0] = mapped(batch->coords); can_map = dp[0] != nullptr; }
             else {
-                const void* d = nullptr;
+                dp[0] = mapped(batch->qstart); dp[1] = mapped(batch->qend); dp[2] = mapped(batch->sstart); dp[3] = mapped(batch->send);
+                can_map = dp[0] && dp[1] && dp[2] && dp[3];
+            }
+        }
+        if (want == O2A_COORDS_UPLOAD || batch->n_hsp == 0) coords_mode = O2A_COORDS_UPLOAD;
+        else if (can_map) coords_mode = O2A_COORDS_ZERO_COPY;
+        else coords_mode = O2A_COORDS_HOST_GATHER;
+        if (coords_mode == O2A_COORDS_ZERO_COPY) {
+            ctx->coords_zero_copy = true;
+            if (batch->coords) { ctx->coords4 = (const int4*)dp[0]; b.qstart = b.qend = b.sstart = b.send = nullptr; }
+            else { b.qstart = (const int*)dp[0]; b.qend = (const int*)dp[1]; b.sstart = (const int*)dp[2]; b.send = (const int*)dp[3]; }
+        } else if (coords_mode == O2A_COORDS_UPLOAD) {
+            const void* d = nullptr;
+            if (batch->coords) {
                 if ((r = upload_bulk(ctx, ctx->in_coords, batch->coords, (size_t)batch->n_hsp, 16, SLICE_HSP, deferred, &d))) return r;
                 ctx->coords4 = (const int4*)d;
-            }
-            b.qstart = b.qend = b.sstart = b.send = nullptr;
-        } else {
-            if (try_zero_copy) {
-                const void* dp[4] = {mapped(batch->qstart), mapped(batch->qend), mapped(batch->sstart), mapped(batch->send)};
-                if (dp[0] && dp[1] && dp[2] && dp[3]) {
-                    b.qstart = (const int*)dp[0]; b.qend = (const int*)dp[1]; b.sstart = (const int*)dp[2]; b.send = (const int*)dp[3];
-                    ctx->coords_zero_copy = true;
-                }
-            }
-            if (!ctx->coords_zero_copy) {
-                const void* d = nullptr;
+                b.qstart = b.qend = b.sstart = b.send = nullptr;
+            } else {
                 if ((r = upload_bulk(ctx, ctx->in_qs, batch->qstart, (size_t)batch->n_hsp, 4, SLICE_HSP, deferred, &d))) return r;
                 b.qstart = (const int32_t*)d;
                 if ((r = upload_bulk(ctx, ctx->in_qe, batch->qend, (size_t)batch->n_hsp, 4, SLICE_HSP, deferred, &d))) return r;
@@ -748,15 +881,17 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
                 if ((r = upload_bulk(ctx, ctx->in_se, batch->send, (size_t)batch->n_hsp, 4, SLICE_HSP, deferred, &d))) return r;
                 b.send = (const int32_t*)d;
             }
+        } else {
+            b.qstart = b.qend = b.sstart = b.send = nullptr;       // never dereferenced on the device in this mode
         }
-        if (b.max_aln_hsps <= 0) {
+        {   // the caller's maxima are hints: a host batch is checked here (two passes over the offset arrays)
             long long m = 0;
             for (long long a = 0; a < batch->n_aln; ++a) { long long d = batch->hsp_off[a + 1] - batch->hsp_off[a]; if (d > m) m = d; }
+            if (b.max_aln_hsps > 0 && b.max_aln_hsps < m) { ctx->err = "max_aln_hsps is smaller than the largest alignment"; return O2A_EINVAL; }
             b.max_aln_hsps = m;
-        }
-        if (b.max_lnc_bg <= 0) {
-            long long m = 0;
+            m = 0;
             for (long long l = 0; l < batch->n_lnc; ++l) { long long d = batch->bg_off[l + 1] - batch->bg_off[l]; if (d > m) m = d; }
+            if (b.max_lnc_bg > 0 && b.max_lnc_bg < m) { ctx->err = "max_lnc_bg is smaller than the largest background"; return O2A_EINVAL; }
             b.max_lnc_bg = m;
         }
     } else {
@@ -764,25 +899,47 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         ctx->coords_zero_copy = false;
         if (b.max_aln_hsps <= 0 && (r = find_max_diff(ctx, b.n_aln, (const long long*)b.hsp_off, (long long*)&b.max_aln_hsps))) return r;
         if (b.max_lnc_bg <= 0 && (r = find_max_diff(ctx, b.n_lnc, (const long long*)b.bg_off, (long long*)&b.max_lnc_bg))) return r;
+        // caller-supplied maxima of a device batch are verified on the device, without an extra synchronisation:
+        // the true maxima travel back with the result counters and an understated hint fails the call
+        ENS(maxchk, 16);
+        CU(cudaMemsetAsync(ctx->maxchk.p, 0, 16, ctx->stream));
+        if (b.n_aln > 0) { k_max_diff<<<grid_for(ctx, (b.n_aln + 255) / 256, 4), 256, 0, ctx->stream>>>(b.n_aln, (const long long*)b.hsp_off, P<unsigned long long>(ctx->maxchk)); LAUNCH_CHECK(); }
+        if (b.n_lnc > 0) { k_max_diff<<<grid_for(ctx, (b.n_lnc + 255) / 256, 4), 256, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.bg_off, P<unsigned long long>(ctx->maxchk) + 1); LAUNCH_CHECK(); }
     }
+    ctx->coords_mode_used = coords_mode;
     ENS(aln_lnc, b.n_aln * sizeof(int));
     if (b.n_lnc > 0) {
         k_fill_aln_lnc<<<grid_for(ctx, b.n_lnc, 16), 64, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->aln_lnc));
         LAUNCH_CHECK();
     }
-    if (n_chunks > 1) {
-        // lncRNA boundaries that split the HSPs evenly (lncRNAs are independent units of the path)
-        long long lb[17];
-        lb[0] = 0; lb[n_chunks] = batch->n_lnc;
-        for (int c = 1; c < n_chunks; ++c) {
-            const long long target = batch->n_hsp / n_chunks * c;
-            long long lo = lb[c - 1], hi = batch->n_lnc;
-            while (lo < hi) {
-                long long mid = (lo + hi) >> 1;
-                if (batch->hsp_off[batch->aln_off[mid]] < target) lo = mid + 1; else hi = mid;
-            }
-            lb[c] = lo;
+    // workspace of every stage, sized for the whole batch (slot layout: see DESIGN.md)
+    ENS(n_surv, b.n_aln * sizeof(int)); ENS(n_keep, b.n_aln * sizeof(int));
+    ENS(surv_idx, b.n_hsp * sizeof(int)); ENS(surv_p, b.n_hsp * sizeof(double)); ENS(surv_x, b.n_hsp * sizeof(double));
+    ENS(surv_pq, b.n_hsp * sizeof(double)); ENS(surv_keep, b.n_hsp);
+    ENS(big_list, (b.n_aln + 1) * sizeof(int)); ENS(mid_list, (b.n_aln + 1) * sizeof(int));
+    ENS(pq_list, (b.n_aln + 1) * sizeof(int)); ENS(cbig_list, (b.n_aln + 1) * sizeof(int));
+    ENS(stage_cnt, 16 * CNT_PER_CHUNK * sizeof(int));
+    CU(cudaMemsetAsync(ctx->stage_cnt.p, 0, 16 * CNT_PER_CHUNK * sizeof(int), ctx->stream));
+    if ((r = ensure_chain_buffers(ctx))) return r;
+
+    // lncRNA boundaries that split the HSPs evenly (lncRNAs are independent units of the path)
+    long long lb[17];
+    lb[0] = 0; lb[n_chunks] = b.n_lnc;
+    for (int c = 1; c < n_chunks; ++c) {
+        const long long target = batch->n_hsp / n_chunks * c;
+        long long lo = lb[c - 1], hi = batch->n_lnc;
+        while (lo < hi) {
+            long long mid = (lo + hi) >> 1;
+            if (batch->hsp_off[batch->aln_off[mid]] < target) lo = mid + 1; else hi = mid;
         }
+        lb[c] = lo;
+    }
+    auto set_view = [&](int c) {
+        ctx->vl0 = lb[c]; ctx->vl1 = lb[c + 1];
+        if (n_chunks > 1) { ctx->va0 = batch->aln_off[lb[c]]; ctx->va1 = batch->aln_off[lb[c + 1]]; }
+        else { ctx->va0 = 0; ctx->va1 = b.n_aln; }
+    };
+    if (n_chunks > 1) {
         // the copy stream starts after everything already queued on the compute stream
         CU(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
@@ -799,26 +956,113 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
             }
             CU(cudaEventRecord(ctx->copy_ev[c], ctx->copy_stream));
         }
+    }
+    if (coords_mode != O2A_COORDS_HOST_GATHER) {
         for (int c = 0; c < n_chunks; ++c) {
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[c], 0));
-            ctx->vl0 = lb[c]; ctx->vl1 = lb[c + 1];
-            ctx->va0 = batch->aln_off[lb[c]]; ctx->va1 = batch->aln_off[lb[c + 1]];
+            if (n_chunks > 1) CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[c], 0));
+            set_view(c);
             // stage events keep the times of the last chunk; "h2d" then spans the earlier chunks too
             if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
             if ((r = run_fit(ctx))) return r;
             if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
-            if ((r = run_score(ctx))) return r;
+            if ((r = run_score(ctx, c, ctx->stream))) return r;       // records O2A_STAGE_PQ itself
             if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
-            if ((r = run_chain(ctx))) return r;
+            if ((r = run_gather(ctx, c, ctx->stream))) return r;
+            if ((r = run_chain(ctx, c, ctx->stream))) return r;       // records O2A_STAGE_CHAIN and O2A_STAGE_BEST itself
         }
     } else {
-        ctx->vl0 = 0; ctx->vl1 = b.n_lnc; ctx->va0 = 0; ctx->va1 = b.n_aln;
-        if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
-        if ((r = run_fit(ctx))) return r;
-        if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
-        if ((r = run_score(ctx))) return r;       // records O2A_STAGE_PQ itself
-        if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
-        if ((r = run_chain(ctx))) return r;       // records O2A_STAGE_CHAIN and O2A_STAGE_BEST itself
+        // ---- host gather: front of every chunk on the compute stream; the host collects the retained records of chunk
+        // c while the front of chunk c+1 runs; scatter + chaining of chunk c on the tail stream ------------------------
+        long long cap_of[16], base_of[17];
+        base_of[0] = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            const long long h_lo = batch->hsp_off[n_chunks > 1 ? batch->aln_off[lb[c]] : 0];
+            const long long h_hi = batch->hsp_off[n_chunks > 1 ? batch->aln_off[lb[c + 1]] : batch->n_aln];
+            long long cap = (h_hi - h_lo) / 8;                     // ~1 % is retained on BLAST-like data; beyond 12.5 %
+            if (cap < 65536) cap = 65536;                          // the chunk's records are uploaded instead
+            if (cap > h_hi - h_lo) cap = h_hi - h_lo;
+            cap_of[c] = cap; base_of[c + 1] = base_of[c] + cap;
+        }
+        const size_t tot = (size_t)base_of[n_chunks];
+        if ((r = ensure_pinned(ctx, (void**)&ctx->h_list, &ctx->h_list_cap, tot * 8 + 16))) return r;
+        if ((r = ensure_pinned(ctx, (void**)&ctx->h_stage, &ctx->h_stage_cap, tot * 16 + 16))) return r;
+        if (!ctx->h_cursor) { ctx->err = "pinned cursor missing"; return O2A_ENOMEM; }
+        ENS(d_stage, tot * 16 + 16); ENS(ret_base, (b.n_aln + 1) * 8); ENS(list_cursor, 16 * 8);
+        CU(cudaMemsetAsync(ctx->list_cursor.p, 0, 16 * 8, ctx->stream));
+        long long* d_list = nullptr;
+        CU(cudaHostGetDevicePointer((void**)&d_list, ctx->h_list, 0));
+        for (int c = 0; c < n_chunks; ++c) {
+            if (n_chunks > 1) CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[c], 0));
+            set_view(c);
+            if ((r = stage_event(ctx, O2A_STAGE_FIT))) return r;
+            if ((r = run_fit(ctx))) return r;
+            if ((r = stage_event(ctx, O2A_STAGE_FILTER))) return r;
+            if ((r = run_score(ctx, c, ctx->stream))) return r;
+            if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
+            const long long na = ctx->va1 - ctx->va0;
+            if (na > 0) {
+                ChainArgs A{};
+                fill_chain_args(ctx, c, A);
+                k_list_retained<<<grid_for(ctx, (na + 7) / 8, 8), 256, 0, ctx->stream>>>(
+                    A, P<long long>(ctx->ret_base) + ctx->va0, P<long long>(ctx->list_cursor) + c, d_list + base_of[c], cap_of[c]);
+                LAUNCH_CHECK();
+            }
+            CU(cudaMemcpyAsync(ctx->h_cursor + c, P<long long>(ctx->list_cursor) + c, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaEventRecord(ctx->front_ev[c], ctx->stream));
+        }
+        const int4* h_coords = (const int4*)batch->coords;
+        if (!ctx->pool) ctx->pool = new HostPool(ctx->gather_threads);
+        HostPool& pool = *ctx->pool;
+        for (int c = 0; c < n_chunks; ++c) {
+            CU(cudaEventSynchronize(ctx->front_ev[c]));
+            set_view(c);
+            const long long R = ctx->h_cursor[c];
+            const long long na = ctx->va1 - ctx->va0;
+            if (R > 0 && na > 0) {
+                ChainArgs A{};
+                fill_chain_args(ctx, c, A);
+                if (R <= cap_of[c]) {
+                    const long long* list = ctx->h_list + base_of[c];
+                    int4* stage = ctx->h_stage + base_of[c];
+                    if (h_coords) pool.run(R, [=](long long k) { stage[k] = h_coords[list[k]]; });
+                    else {
+                        const int32_t *qs = batch->qstart, *qe = batch->qend, *ss = batch->sstart, *se = batch->send;
+                        pool.run(R, [=](long long k) {
+                            const long long h = list[k];
+                            stage[k] = make_int4(qs[h], qe[h], ss[h], se[h]);
+                        });
+                    }
+                    int4* d_st = P<int4>(ctx->d_stage) + base_of[c];
+                    CU(cudaMemcpyAsync(d_st, stage, (size_t)R * 16, cudaMemcpyHostToDevice, ctx->tail_stream));
+                    k_scatter_coords<<<grid_for(ctx, (na + 7) / 8, 8), 256, 0, ctx->tail_stream>>>(A, P<long long>(ctx->ret_base) + ctx->va0, d_st);
+                    LAUNCH_CHECK();
+                } else {
+                    // a dense chunk: its coordinate records are uploaded whole and read on the device
+                    const long long h_lo = batch->hsp_off[ctx->va0], h_hi = batch->hsp_off[ctx->va1];
+                    ENS(in_coords, (size_t)b.n_hsp * 16);
+                    int4* d_c = P<int4>(ctx->in_coords);
+                    if (h_coords) CU(cudaMemcpyAsync(d_c + h_lo, h_coords + h_lo, (size_t)(h_hi - h_lo) * 16, cudaMemcpyHostToDevice, ctx->tail_stream));
+                    else {
+                        // SoA caller arrays: interleave on the host into the staging records of this chunk, piecewise
+                        const int32_t *qs = batch->qstart, *qe = batch->qend, *ss = batch->sstart, *se = batch->send;
+                        const long long piece = (long long)(ctx->h_stage_cap / 16);
+                        for (long long h = h_lo; h < h_hi; h += piece) {
+                            const long long n = h_hi - h < piece ? h_hi - h : piece;
+                            int4* stage = ctx->h_stage;
+                            CU(cudaStreamSynchronize(ctx->tail_stream));            // the staging buffer is reused
+                            pool.run(n, [=](long long k) { stage[k] = make_int4(qs[h + k], qe[h + k], ss[h + k], se[h + k]); });
+                            CU(cudaMemcpyAsync(d_c + h, stage, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->tail_stream));
+                        }
+                    }
+                    A.coords4 = d_c;
+                    k_fill_coords<<<grid_for(ctx, (na + 7) / 8, 8), 256, 0, ctx->tail_stream>>>(A);
+                    LAUNCH_CHECK();
+                }
+            }
+            if ((r = run_chain(ctx, c, ctx->tail_stream))) return r;
+        }
+        CU(cudaEventRecord(ctx->tail_join, ctx->tail_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->tail_join, 0));
     }
     ctx->vl0 = 0; ctx->vl1 = b.n_lnc; ctx->va0 = 0; ctx->va1 = b.n_aln;
     ENS(counters, 5 * 8);
@@ -831,9 +1075,15 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         LAUNCH_CHECK();
     }
     if ((r = stage_event(ctx, O2A_STAGE_COUNT))) return r;
-    unsigned long long c[5];
+    unsigned long long c[5], mx[2] = {0, 0};
     CU(cudaMemcpyAsync(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    if (batch->mem != O2A_MEM_HOST) CU(cudaMemcpyAsync(mx, ctx->maxchk.p, sizeof(mx), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (batch->mem != O2A_MEM_HOST && ((long long)mx[0] > b.max_aln_hsps || (long long)mx[1] > b.max_lnc_bg)) {
+        ctx->err = "max_aln_hsps / max_lnc_bg smaller than the batch's real maxima (" + std::to_string(mx[0]) + ", " +
+                   std::to_string(mx[1]) + "): the result is not valid";
+        return O2A_EINVAL;
+    }
     ctx->counts.n_survivors = (long long)c[0]; ctx->counts.n_retained = (long long)c[1];
     ctx->counts.n_chain_hsps = (long long)c[2]; ctx->counts.n_chains = (long long)c[3];
     ctx->counts.n_failed_lnc = (long long)c[4];
@@ -1011,11 +1261,13 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     ctx->prm.gapopen = gapopen; ctx->prm.gapextend = gapextend;
     ENS(aln_lnc, 4); ENS(status, 4); ENS(n_surv, 4); ENS(n_keep, 4);
     ENS(surv_idx, (size_t)n * 4); ENS(surv_keep, (size_t)n); ENS(surv_pq, (size_t)n * 8); ENS(surv_x, (size_t)n * 8);
-    ENS(big_list, 2 * sizeof(int)); ENS(mid_list, 2 * sizeof(int)); ENS(big_count, 4 * sizeof(int));
+    ENS(big_list, 2 * sizeof(int)); ENS(mid_list, 2 * sizeof(int)); ENS(pq_list, 2 * sizeof(int)); ENS(cbig_list, 2 * sizeof(int));
+    ENS(stage_cnt, 16 * CNT_PER_CHUNK * sizeof(int));
+    if ((r = ensure_chain_buffers(ctx))) return r;
     int ni = (int)n;
     CU(cudaMemsetAsync(ctx->aln_lnc.p, 0, 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->status.p, 0, 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->big_count.p, 0, 16, ctx->stream));
+    CU(cudaMemsetAsync(ctx->stage_cnt.p, 0, 16 * CNT_PER_CHUNK * sizeof(int), ctx->stream));
     CU(cudaMemcpyAsync(ctx->n_surv.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->n_keep.p, &ni, 4, cudaMemcpyHostToDevice, ctx->stream));
     if (n > 0) {
@@ -1025,7 +1277,9 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     bool timing = ctx->timing;
     ctx->timing = false;
     ctx->vl0 = 0; ctx->vl1 = 1; ctx->va0 = 0; ctx->va1 = 1;
-    r = run_chain(ctx);
+    ctx->coords_zero_copy = false; ctx->pipelined_chunks = 1;
+    r = run_gather(ctx, 0, ctx->stream);
+    if (!r) r = run_chain(ctx, 0, ctx->stream);
     ctx->timing = timing;
     if (r) return r;
     int len = 0, st = 0; unsigned char orr = 1; double cs = 0, os2[2] = {0, 0};

@@ -228,6 +228,72 @@ k_gather_retained(ChainArgs A)
     }
 }
 
+// Host-gather mode (host batches whose coordinate records stay in HOST memory): instead of reading the ~1 % retained
+// records in place over PCIe (32-byte reads that compete with the upload DMA for the link's read-request slots), the
+// GPU lists the global HSP indices of the retained HSPs straight into mapped pinned host memory (posted writes), the
+// host gathers the 16-byte records with its own threads and sends them back as one small DMA, and k_scatter_coords
+// puts them where the chaining kernels expect them. Everything else k_gather_retained does (score, survivor slot,
+// queueing the alignments beyond the warp path) happens here.
+__global__ void __launch_bounds__(256)
+k_list_retained(ChainArgs A, long long* __restrict__ ret_base, long long* __restrict__ cursor,
+                long long* __restrict__ host_list, long long cap)
+{
+    const int lane = lane_id();
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long a = warp; a < A.n_aln; a += nwarps) {
+        const int r = A.n_keep[a];
+        if (r == 0) continue;
+        if (r > CHAIN_WARP_MAX && lane == 0) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
+        long long base = 0;
+        if (lane == 0) { base = (long long)atomicAdd((unsigned long long*)cursor, (unsigned long long)r); ret_base[a] = base; }
+        base = __shfl_sync(FULL_MASK, base, 0);
+        const long long h0 = A.hsp_off[a];
+        const int ns = A.n_surv[a];
+        int got = 0;
+        for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
+            const int k = k0 + lane;
+            const bool keep = (k < ns) && A.surv_keep[h0 + k];
+            const unsigned b = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+                const int pos = got + __popc(b & lanemask_lt());
+                A.ret_score[h0 + pos] = A.surv_x[h0 + k]; A.ret_slot[h0 + pos] = k;
+                if (base + pos < cap) host_list[base + pos] = h0 + A.surv_idx[h0 + k];
+            }
+            got += __popc(b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter_coords(ChainArgs A, const long long* __restrict__ ret_base, const int4* __restrict__ stage)
+{
+    const int lane = lane_id();
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long a = warp; a < A.n_aln; a += nwarps) {
+        const int r = A.n_keep[a];
+        if (r == 0) continue;
+        const long long h0 = A.hsp_off[a], base = ret_base[a];
+        for (int i = lane; i < r; i += 32) A.ret_coord[h0 + i] = stage[base + i];
+    }
+}
+
+// ret_coord of the retained HSPs from device-resident AoS coordinate records (ret_slot already filled by
+// k_list_retained): the dense-chunk fallback of the host-gather mode.
+__global__ void __launch_bounds__(256)
+k_fill_coords(ChainArgs A)
+{
+    const int lane = lane_id();
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long a = warp; a < A.n_aln; a += nwarps) {
+        const int r = A.n_keep[a];
+        const long long h0 = A.hsp_off[a];
+        for (int i = lane; i < r; i += 32) A.ret_coord[h0 + i] = A.coords4[h0 + A.surv_idx[h0 + A.ret_slot[h0 + i]]];
+    }
+}
+
 // Warp path: one warp per alignment with at most CHAIN_WARP_MAX retained HSPs (the common case:
 // ~10-20 retained of ~130 survivors). Everything lives in the warp's slice of shared memory; the
 // begin/end sentinels are stored as ordinary vertices (64-bit coordinates). The two orientations are
@@ -519,6 +585,7 @@ k_chain_big(ChainArgs A, ChainBigScratch S)
         const long long a = A.big_list[b];
         const long long h0 = A.hsp_off[a];
         const int l = A.aln_lnc[a];
+        if ((long long)A.n_keep[a] > S.cap) continue;      // understated max_aln_hsps: the call fails on the host side
         if (tid == 0) s_bad = 0;
         __syncthreads();
         double sco[2];

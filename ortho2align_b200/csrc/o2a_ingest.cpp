@@ -7,14 +7,21 @@
 // alignment.py:588-601); bg_files/<name>.json = JSON list of ints (pipeline.py:266-273).
 // What is extracted per alignment: the HSPs of key "HSPs" ONLY (the reference rebuilds the working
 // list from 'HSPs' and ignores 'filtered_HSPs', genomicranges.py:1094-1100), qlen/slen (null ->
-// max+1 like alignment.py:477-487), and the BYTE SPANS of the "qrange"/"srange" objects so the
+// max+1 like alignment.py:477-487), the truthiness of 'relative' (to_record raises for relative
+// alignments, genomicranges.py:1259), and the BYTE SPANS of the "qrange"/"srange" objects so the
 // host decodes only those few hundred bytes when it formats a record. Scores keep their JSON type
 // (int vs float) in `score_is_int` because the reference's record text depends on it.
 // Background patches of pipeline.py:746-754 are applied here, in the reference's order.
 //
-// Plain C ABI (declared in include/o2a_ingest.h); files are parsed by a pool of std::threads.
+// Two output forms (include/o2a_ingest.h): the plain columnar arrays (o2a_ingest_export), and the
+// PCIe-optimal lossless layout o2a_build_batch takes from host memory (o2a_ingest_export_narrow:
+// int8/int16/int32 scores + exception lists, narrow background; coordinates AoS) written straight
+// into caller-provided — normally pinned — buffers by the same thread pool that parsed the files.
+//
+// Plain C ABI; files are parsed by a pool of std::threads.
 #include <atomic>
 #include <charconv>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +30,13 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "../../include/o2a_ingest.h"
+#include "o2a_pack.h"
 
 namespace {
 
@@ -37,7 +50,20 @@ struct FileResult {
     std::vector<double> score;
     std::vector<uint8_t> score_is_int;
     std::vector<int32_t> bg;
-    std::string text;               // file contents; released after parsing
+    std::vector<uint8_t> relative;  // per alignment: the 'relative' flag is truthy (to_record raises, genomicranges.py:1259)
+    // HSPs of the file whose score does not fit the lossless int8 / int16 / int32 encodings of include/o2a.h
+    int64_t misfit[3] = {0, 0, 0};
+    int32_t bg_min = 0, bg_max = 0;
+    std::string text;               // file contents when they were read (not mapped); released after parsing
+    const char* view = nullptr;     // file contents: mapped (MappedFile) or `text`
+    size_t view_len = 0;
+};
+
+// read-only mapping of a whole file; falls back to read() into `fallback` when mmap is not possible
+struct MappedFile {
+    void* map = MAP_FAILED; size_t len = 0;
+    bool open_file(const char* path, std::string& fallback, const char*& data, size_t& n, bool& missing);
+    ~MappedFile() { if (map != MAP_FAILED) munmap(map, len); }
 };
 
 struct Parser {
@@ -98,6 +124,27 @@ struct Parser {
         kind = 2; iv = 0;
         return true;
     }
+    // Python truthiness of any JSON value (for 'relative'): false / null / 0 / "" / [] / {} are falsy
+    bool truthy(bool& out) {
+        ws();
+        if (p >= end) return fail("unexpected end");
+        const char* s = p;
+        if (!skip()) return false;
+        const size_t n = (size_t)(p - s);
+        if ((n == 5 && !memcmp(s, "false", 5)) || (n == 4 && !memcmp(s, "null", 4))) { out = false; return true; }
+        if (n == 4 && !memcmp(s, "true", 4)) { out = true; return true; }
+        if (*s == '"') { out = n > 2; return true; }
+        if (*s == '[' || *s == '{') {
+            const char* q = s + 1;
+            while (q < p - 1 && (*q == ' ' || *q == '\n' || *q == '\t' || *q == '\r')) ++q;
+            out = q < p - 1;
+            return true;
+        }
+        double dv = 0;
+        auto r = std::from_chars(s, p, dv);
+        out = !(r.ec == std::errc() && dv == 0.0);
+        return true;
+    }
 };
 
 inline bool key_is(const char* b, const char* e, const char* name) {
@@ -107,18 +154,103 @@ inline bool key_is(const char* b, const char* e, const char* name) {
 
 bool read_file(const char* path, std::string& out, bool& missing) {
     missing = false;
-    FILE* f = fopen(path, "rb");
-    if (!f) { missing = true; return false; }
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    out.resize((size_t)(n > 0 ? n : 0));
-    size_t got = n > 0 ? fread(&out[0], 1, (size_t)n, f) : 0;
-    fclose(f);
-    return got == (size_t)(n > 0 ? n : 0);
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { missing = true; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return false; }
+    const size_t n = (size_t)(st.st_size > 0 ? st.st_size : 0);
+    out.resize(n);
+    size_t got = 0;
+    while (got < n) {
+        ssize_t r = read(fd, &out[got], n - got);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    return got == n;
 }
 
-bool parse_hsps(Parser& P, FileResult& R, int64_t& count, int64_t& max_qend, int64_t& max_s, bool& range_err) {
+bool MappedFile::open_file(const char* path, std::string& fallback, const char*& data, size_t& n, bool& missing)
+{
+    missing = false;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { missing = true; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return false; }
+    n = (size_t)(st.st_size > 0 ? st.st_size : 0);
+    if (n >= (1u << 16)) {
+        map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (map != MAP_FAILED) { len = n; close(fd); data = (const char*)map; return true; }
+    }
+    fallback.resize(n);
+    size_t got = 0;
+    while (got < n) {
+        ssize_t r = read(fd, &fallback[got], n - got);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    data = fallback.data();
+    return got == n;
+}
+
+// which narrow encodings cannot hold score `sc` (bit 0: int8, bit 1: int16, bit 2: int32): o2a_pack.h
+using o2a_pack::narrow_misfit;
+
+// Fast path for the text json.dump writes for one HSP (alignment.py:233-249 -> to_dict):
+//   {"qstart": I, "qend": I, "sstart": I, "send": I, "score": N, "pval": null, "kwargs": {}}
+// Matches the five leading keys with their default separators and plain integer literals; anything
+// else returns false with `p` untouched and the general key loop takes the object.
+inline bool fast_int(const char*& q, const char* end, int64_t& v)
+{
+    const char* s = q;
+    bool neg = false;
+    if (s < end && *s == '-') { neg = true; ++s; }
+    const char* d0 = s;
+    uint64_t acc = 0;
+    while (s < end && *s >= '0' && *s <= '9') { acc = acc * 10 + (uint64_t)(*s - '0'); ++s; }
+    const int nd = (int)(s - d0);
+    if (nd == 0 || nd > 18) return false;
+    if (s < end && (*s == '.' || *s == 'e' || *s == 'E')) return false;
+    v = neg ? -(int64_t)acc : (int64_t)acc;
+    q = s;
+    return true;
+}
+
+inline bool fast_hsp(Parser& P, int64_t c[4], double& sc, uint8_t& isint, bool& closed)
+{
+    static const char K0[] = "\"qstart\": ", K1[] = ", \"qend\": ", K2[] = ", \"sstart\": ", K3[] = ", \"send\": ",
+                      K4[] = ", \"score\": ", TAIL[] = ", \"pval\": null, \"kwargs\": {}}";
+    const char* q = P.p;
+    const char* end = P.end;
+#define O2A_KEY(K) if ((size_t)(end - q) < sizeof(K) || memcmp(q, K, sizeof(K) - 1)) return false; q += sizeof(K) - 1
+    O2A_KEY(K0); if (!fast_int(q, end, c[0])) return false;
+    O2A_KEY(K1); if (!fast_int(q, end, c[1])) return false;
+    O2A_KEY(K2); if (!fast_int(q, end, c[2])) return false;
+    O2A_KEY(K3); if (!fast_int(q, end, c[3])) return false;
+    O2A_KEY(K4);
+#undef O2A_KEY
+    int64_t iv;
+    const char* s = q;
+    if (fast_int(q, end, iv)) { sc = (double)iv; isint = 1; }
+    else {
+        while (q < end && ((*q >= '0' && *q <= '9') || *q == '.' || *q == 'e' || *q == 'E' || *q == '-' || *q == '+')) ++q;
+        if (q == s) return false;
+        bool is_float = false;
+        for (const char* t = s; t < q; ++t) if (*t == '.' || *t == 'e' || *t == 'E') is_float = true;
+        if (!is_float) return false;                                    // > 18 digits: the general path decides
+        auto r = std::from_chars(s, q, sc);
+        if (r.ec != std::errc() || r.ptr != q) return false;
+        isint = 0;
+    }
+    closed = false;
+    if ((size_t)(end - q) >= sizeof(TAIL) - 1 && !memcmp(q, TAIL, sizeof(TAIL) - 1)) { q += sizeof(TAIL) - 1; closed = true; }
+    P.p = q;
+    return true;
+}
+
+bool parse_hsps(Parser& P, FileResult& R, int64_t& count, int64_t& max_qend, int64_t& max_s, bool& range_err)
+{
     count = 0; max_qend = 0; max_s = 0;
     if (!P.expect('[')) return false;
     if (P.lit(']')) return true;
@@ -126,7 +258,13 @@ bool parse_hsps(Parser& P, FileResult& R, int64_t& count, int64_t& max_qend, int
         if (!P.expect('{')) return false;
         int64_t c[4] = {0, 0, 0, 0}; bool have[5] = {false, false, false, false, false};
         double sc = 0; uint8_t isint = 1;
-        if (!P.lit('}')) {
+        bool closed = false;
+        bool more = false;              // the general key loop continues after the leading keys
+        if (fast_hsp(P, c, sc, isint, closed)) {
+            have[0] = have[1] = have[2] = have[3] = have[4] = true;
+            if (!closed) { if (P.lit(',')) more = true; else if (!P.expect('}')) return false; }
+        } else if (!P.lit('}')) more = true;
+        if (more) {
             do {
                 const char *kb, *ke;
                 if (!P.str(kb, ke) || !P.expect(':')) return false;
@@ -148,6 +286,8 @@ bool parse_hsps(Parser& P, FileResult& R, int64_t& count, int64_t& max_qend, int
             R.coords.push_back((int32_t)c[k]);
         }
         R.score.push_back(sc); R.score_is_int.push_back(isint);
+        const unsigned mf = narrow_misfit(sc);
+        R.misfit[0] += mf & 1u; R.misfit[1] += (mf >> 1) & 1u; R.misfit[2] += (mf >> 2) & 1u;
         if (count == 0 || c[1] > max_qend) max_qend = c[1];
         int64_t ms = c[2] > c[3] ? c[2] : c[3];
         if (count == 0 || ms > max_s) max_s = ms;
@@ -157,19 +297,31 @@ bool parse_hsps(Parser& P, FileResult& R, int64_t& count, int64_t& max_qend, int
 }
 
 void parse_alignment_file(FileResult& R) {
-    Parser P{R.text.data(), R.text.data(), R.text.data() + R.text.size(), {}};
+    Parser P{R.view, R.view, R.view + R.view_len, {}};
     bool range_err = false;
+    {   // ~232 bytes of JSON per HSP (each HSP is written twice, alignment.py:595-601): one allocation per array
+        const size_t guess = R.view_len / 200 + 16;
+        R.coords.reserve(4 * guess); R.score.reserve(guess); R.score_is_int.reserve(guess);
+    }
     if (!P.expect('[')) { R.status = 1; R.error = P.err; return; }
     if (!P.lit(']')) {
         do {
             if (!P.expect('{')) break;
             int64_t cnt = 0, mq = 0, msub = 0, ql = 0, sl = 0; bool hq = false, hs = false, hh = false;
             int64_t qb = -1, qe = -1, sb = -1, se = -1;
+            bool rel = false;
+            const char *hsps_b = nullptr, *hsps_e = nullptr;        // text of the "HSPs" value
             if (!P.lit('}')) {
                 do {
                     const char *kb, *ke;
                     if (!P.str(kb, ke) || !P.expect(':')) break;
-                    if (key_is(kb, ke, "HSPs")) { if (!parse_hsps(P, R, cnt, mq, msub, range_err)) break; hh = true; }
+                    if (key_is(kb, ke, "HSPs")) {
+                        P.ws();
+                        hsps_b = P.p;
+                        if (!parse_hsps(P, R, cnt, mq, msub, range_err)) break;
+                        hsps_e = P.p;
+                        hh = true;
+                    }
                     else if (key_is(kb, ke, "qlen") || key_is(kb, ke, "slen")) {
                         int kind; int64_t iv; double dv;
                         if (!P.num(kind, iv, dv)) break;
@@ -183,6 +335,15 @@ void parse_alignment_file(FileResult& R) {
                         R.meta.append(vb, (size_t)(P.p - vb));
                         int64_t e = (int64_t)R.meta.size();
                         if (kb[0] == 'q') { qb = b; qe = e; } else { sb = b; se = e; }
+                    } else if (key_is(kb, ke, "relative")) {
+                        if (!P.truthy(rel)) break;
+                    } else if (key_is(kb, ke, "filtered_HSPs") && hsps_b) {
+                        // to_dict writes the working list next to the full one; before any filtering the two texts are
+                        // byte-identical, and the reference ignores this key's content anyway (genomicranges.py:1099-1100)
+                        P.ws();
+                        const size_t n = (size_t)(hsps_e - hsps_b);
+                        if ((size_t)(P.end - P.p) > n && !memcmp(P.p, hsps_b, n)) P.p += n;
+                        else if (!P.skip()) break;
                     } else if (!P.skip()) break;
                 } while (P.lit(','));
                 if (!P.err.empty() || !P.expect('}')) break;
@@ -193,6 +354,7 @@ void parse_alignment_file(FileResult& R) {
             R.qlen.push_back(hq ? ql : (cnt ? mq : 0) + 1);              // alignment.py:477-480
             R.slen.push_back(hs ? sl : (cnt ? msub : 0) + 1);            // alignment.py:481-487
             R.qr_begin.push_back(qb); R.qr_end.push_back(qe); R.sr_begin.push_back(sb); R.sr_end.push_back(se);
+            R.relative.push_back(rel ? 1 : 0);
         } while (P.lit(','));
         if (P.err.empty()) P.expect(']');
     }
@@ -205,10 +367,15 @@ void parse_background(const std::string& text, bool missing, FileResult& R) {
     if (missing) { v = {0, 1}; }                                         // pipeline.py:749-750
     else {
         Parser P{text.data(), text.data(), text.data() + text.size(), {}};
+        v.reserve(text.size() / 3 + 4);
         if (!P.expect('[')) { R.status = 1; R.error = "background: " + P.err; return; }
         if (!P.lit(']')) {
             do {
-                int kind; int64_t iv; double dv;
+                P.ws();
+                int64_t iv;
+                const char* q = P.p;
+                if (fast_int(q, P.end, iv)) { P.p = q; v.push_back(iv); continue; }
+                int kind; double dv;
                 if (!P.num(kind, iv, dv)) break;
                 if (kind != 1) { R.status = 2; R.error = "background scores must be integers within int32"; return; }
                 v.push_back(iv);
@@ -222,10 +389,14 @@ void parse_background(const std::string& text, bool missing, FileResult& R) {
     if (!distinct2) v.push_back(1);
     if (v[0] == 1) v.push_back(0);                                       // bg[0] == 1 -> append(0)
     R.bg.reserve(v.size());
+    int64_t mn = v[0], mx = v[0];
     for (int64_t x : v) {
         if (x > INT32_MAX || x < -(int64_t)INT32_MAX) { R.status = 2; R.error = "background scores must be integers within int32"; return; }
         R.bg.push_back((int32_t)x);
+        if (x < mn) mn = x;
+        if (x > mx) mx = x;
     }
+    R.bg_min = (int32_t)mn; R.bg_max = (int32_t)mx;
 }
 
 }  // namespace
@@ -256,30 +427,23 @@ extern "C" int o2a_ingest_load(o2a_ingest* g, const char* const* align_paths, co
 {
     if (!g || n_files < 0) return -1;
     g->files.assign((size_t)n_files, FileResult());
-    std::atomic<int64_t> next(0);
-    auto work = [&]() {
-        for (;;) {
-            int64_t i = next.fetch_add(1);
-            if (i >= n_files) break;
-            FileResult& R = g->files[(size_t)i];
-            bool missing = false;
-            if (!read_file(align_paths[i], R.text, missing)) { R.status = 1; R.error = "cannot read alignment file"; continue; }
+    o2a_pack::parallel_for(g->n_threads, n_files, [&](int64_t i) {
+        FileResult& R = g->files[(size_t)i];
+        bool missing = false;
+        {
+            MappedFile mf;
+            if (!mf.open_file(align_paths[i], R.text, R.view, R.view_len, missing)) { R.status = 1; R.error = "cannot read alignment file"; return; }
             parse_alignment_file(R);
+            R.view = nullptr; R.view_len = 0;
             std::string().swap(R.text);
-            if (R.status) continue;
-            std::string bgtext;
-            bool bg_missing = false;
-            bool ok = read_file(bg_paths[i], bgtext, bg_missing);
-            if (!ok && !bg_missing) { R.status = 1; R.error = "cannot read background file"; continue; }
-            parse_background(bgtext, bg_missing, R);
         }
-    };
-    int nt = g->n_threads;
-    if (nt > n_files) nt = (int)(n_files > 0 ? n_files : 1);
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-    work();
-    for (auto& t : pool) t.join();
+        if (R.status) return;
+        std::string bgtext;
+        bool bg_missing = false;
+        bool ok = read_file(bg_paths[i], bgtext, bg_missing);
+        if (!ok && !bg_missing) { R.status = 1; R.error = "cannot read background file"; return; }
+        parse_background(bgtext, bg_missing, R);
+    });
     return 0;
 }
 
@@ -295,19 +459,41 @@ extern "C" int o2a_ingest_sizes(const o2a_ingest* g, int64_t* n_lnc, int64_t* n_
     return 0;
 }
 
+namespace {
+// first lncRNA / alignment / HSP / background index of every file (files with status != 0 own nothing)
+struct Bases { std::vector<int64_t> l, a, h, b; };
+Bases file_bases(const o2a_ingest* g)
+{
+    Bases B;
+    const size_t n = g->files.size();
+    B.l.resize(n + 1); B.a.resize(n + 1); B.h.resize(n + 1); B.b.resize(n + 1);
+    int64_t l = 0, a = 0, h = 0, b = 0;
+    for (size_t i = 0; i < n; ++i) {
+        B.l[i] = l; B.a[i] = a; B.h[i] = h; B.b[i] = b;
+        const FileResult& R = g->files[i];
+        if (R.status) continue;
+        ++l; a += (int64_t)R.hsp_count.size(); h += (int64_t)R.score.size(); b += (int64_t)R.bg.size();
+    }
+    B.l[n] = l; B.a[n] = a; B.h[n] = h; B.b[n] = b;
+    return B;
+}
+}  // namespace
+
 extern "C" int o2a_ingest_export(const o2a_ingest* g, int32_t* file_status, int64_t* lnc_file,
                                  int64_t* bg_off, int32_t* bg, int64_t* aln_off, int64_t* hsp_off,
                                  int64_t* qlen, int64_t* slen, int32_t* coords,
                                  int32_t* qstart, int32_t* qend, int32_t* sstart, int32_t* send,
-                                 double* score, uint8_t* score_is_int, int64_t* spans)
+                                 double* score, uint8_t* score_is_int, int64_t* spans, uint8_t* relative)
 {
     if (!g) return -1;
-    int64_t l = 0, a = 0, h = 0, b = 0;
+    const Bases B = file_bases(g);
     if (bg_off) bg_off[0] = 0; if (aln_off) aln_off[0] = 0; if (hsp_off) hsp_off[0] = 0;
-    for (size_t i = 0; i < g->files.size(); ++i) {
+    o2a_pack::parallel_for(g->n_threads, (int64_t)g->files.size(), [&](int64_t fi) {
+        const size_t i = (size_t)fi;
         const FileResult& R = g->files[i];
         if (file_status) file_status[i] = R.status;
-        if (R.status) continue;
+        if (R.status) return;
+        const int64_t l = B.l[i], a = B.a[i], h = B.h[i], b = B.b[i];
         if (lnc_file) lnc_file[l] = (int64_t)i;
         const int64_t na = (int64_t)R.hsp_count.size(), nh = (int64_t)R.score.size(), nb = (int64_t)R.bg.size();
         if (bg) memcpy(bg + b, R.bg.data(), (size_t)nb * 4);
@@ -317,6 +503,7 @@ extern "C" int o2a_ingest_export(const o2a_ingest* g, int32_t* file_status, int6
             if (hsp_off) hsp_off[a + k + 1] = hcur;
             if (qlen) qlen[a + k] = R.qlen[(size_t)k];
             if (slen) slen[a + k] = R.slen[(size_t)k];
+            if (relative) relative[a + k] = R.relative[(size_t)k];
             if (spans) {
                 int64_t* s = spans + 4 * (a + k);
                 s[0] = R.qr_begin[(size_t)k]; s[1] = R.qr_end[(size_t)k]; s[2] = R.sr_begin[(size_t)k]; s[3] = R.sr_end[(size_t)k];
@@ -331,10 +518,58 @@ extern "C" int o2a_ingest_export(const o2a_ingest* g, int32_t* file_status, int6
         }
         if (score) memcpy(score + h, R.score.data(), (size_t)nh * 8);
         if (score_is_int) memcpy(score_is_int + h, R.score_is_int.data(), (size_t)nh);
-        ++l; a += na; h += nh; b += nb;
-        if (bg_off) bg_off[l] = b;
-        if (aln_off) aln_off[l] = a;
+        if (bg_off) bg_off[l + 1] = b + nb;
+        if (aln_off) aln_off[l + 1] = a + na;
+    });
+    return 0;
+}
+
+extern "C" int o2a_ingest_narrow_plan(const o2a_ingest* g, int32_t* score_bits, int32_t* bg_bits, int64_t* n_exc)
+{
+    if (!g) return -1;
+    int64_t mis[3] = {0, 0, 0}, n_hsp = 0;
+    int32_t mn = 0, mx = 0;
+    for (const FileResult& R : g->files) {
+        if (R.status) continue;
+        for (int k = 0; k < 3; ++k) mis[k] += R.misfit[k];
+        n_hsp += (int64_t)R.score.size();
+        if (R.bg_min < mn) mn = R.bg_min;
+        if (R.bg_max > mx) mx = R.bg_max;
     }
+    const int w = o2a_pack::choose_score_bits(mis, n_hsp);
+    if (score_bits) *score_bits = w;
+    if (bg_bits) *bg_bits = o2a_pack::choose_bg_bits(mn, mx);
+    if (n_exc) *n_exc = mis[w == 8 ? 0 : w == 16 ? 1 : 2];
+    return 0;
+}
+
+extern "C" int o2a_ingest_export_narrow(const o2a_ingest* g, int32_t score_bits, int32_t bg_bits, void* score_q,
+                                        int64_t* exc_off, int32_t* exc_pos, double* exc_val, void* bg_q)
+{
+    if (!g || (score_bits != 8 && score_bits != 16 && score_bits != 32) || (bg_bits != 8 && bg_bits != 16 && bg_bits != 32)) return -1;
+    if (!score_q || !exc_off || !bg_q) return -1;
+    const Bases B = file_bases(g);
+    const int wi = score_bits == 8 ? 0 : score_bits == 16 ? 1 : 2;
+    // exception base of every file, then every file fills its own alignments
+    std::vector<int64_t> xbase(g->files.size() + 1, 0);
+    for (size_t i = 0; i < g->files.size(); ++i) xbase[i + 1] = xbase[i] + (g->files[i].status ? 0 : g->files[i].misfit[wi]);
+    if (xbase.back() > 0 && (!exc_pos || !exc_val)) return -1;
+    exc_off[0] = 0;
+    o2a_pack::parallel_for(g->n_threads, (int64_t)g->files.size(), [&](int64_t fi) {
+        const size_t i = (size_t)fi;
+        const FileResult& R = g->files[i];
+        if (R.status) return;
+        const int64_t a0 = B.a[i], h0 = B.h[i];
+        int64_t x = xbase[i], hk = 0;
+        for (size_t k = 0; k < R.hsp_count.size(); ++k) {
+            const int64_t n = R.hsp_count[k];
+            x += o2a_pack::quantize_segment(R.score.data() + hk, n, score_bits, score_q, h0 + hk,
+                                            exc_pos ? exc_pos + x : nullptr, exc_val ? exc_val + x : nullptr);
+            exc_off[a0 + (int64_t)k + 1] = x;
+            hk += n;
+        }
+        o2a_pack::narrow_bg(R.bg.data(), (int64_t)R.bg.size(), bg_bits, bg_q, B.b[i]);
+    });
     return 0;
 }
 
@@ -346,4 +581,27 @@ extern "C" int64_t o2a_ingest_span(const o2a_ingest* g, int64_t file, int64_t be
     int64_t n = end - begin;
     if (out && cap >= n) memcpy(out, t.data() + begin, (size_t)n);
     return n;
+}
+
+// All qrange / srange texts of the batch at once (alignment order: q0, s0, q1, s1, ...): range_off[2*n_aln+1] and,
+// when `blob` is given, the concatenated bytes. Returns the blob size.
+extern "C" int64_t o2a_ingest_range_texts(const o2a_ingest* g, int64_t* range_off, char* blob, int64_t cap)
+{
+    if (!g) return -1;
+    int64_t pos = 0, k = 0;
+    if (range_off) range_off[0] = 0;
+    for (const FileResult& R : g->files) {
+        if (R.status) continue;
+        for (size_t a = 0; a < R.hsp_count.size(); ++a) {
+            const int64_t span[4] = {R.qr_begin[a], R.qr_end[a], R.sr_begin[a], R.sr_end[a]};
+            for (int w = 0; w < 2; ++w) {
+                const int64_t n = span[2 * w + 1] - span[2 * w];
+                if (blob && pos + n <= cap) memcpy(blob + pos, R.meta.data() + span[2 * w], (size_t)n);
+                pos += n;
+                ++k;
+                if (range_off) range_off[k] = pos;
+            }
+        }
+    }
+    return pos;
 }

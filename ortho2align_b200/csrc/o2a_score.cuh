@@ -1,23 +1,17 @@
-// o2a_score.cuh — K3 (streaming score filter) and K4+K5 (p-values, rank, q, keep).
+// o2a_score.cuh — K4+K5 (p-values, rank, q, keep) for the alignments the fused front kernel
+// (o2a_front.cuh: filter + p/q by one warp per alignment) leaves behind, plus helpers it shares.
 //
-// k_filter — the only stage that touches every HSP; HBM-bound. One CTA per alignment
-//   (= lncRNA x syntenic region): filter_by_score(isf(alpha)), strict '>'
-//   (alignment.py:618-646, pipeline.py:765). Scores are read once with coalesced 128-bit loads and
-//   the survivors (position + score) are compacted IN ORDER (ballot + CTA scan) into the
-//   alignment's slot [hsp_off[a], hsp_off[a]+n_surv) of the survivor arrays: no global scan, and
-//   only survivors cost write traffic.
-// k_pq — per alignment, on the ~7 % that survived: pvals = background.sf(scores) (pipeline.py:766);
-//   fdr: q = (m*p)/rank(p), keep q <= alpha, no cummin (fitting.py:359-364, pipeline.py:769-776).
-//   Ranks use the build's tie policy: stable (ties keep HSP order) — SURVEY.md §8a row 7.
+// k_pq — CTA per queued alignment (more than FRONT_SCAP survivors, or many non-integral scores):
+//   pvals = background.sf(scores) (pipeline.py:766); fdr: q = (m*p)/rank(p), keep q <= alpha, no cummin
+//   (fitting.py:359-364, pipeline.py:769-776). Ranks use the build's tie policy: stable (ties keep HSP
+//   order) — SURVEY.md §8a row 7.
+// k_rank_big — survivor sets beyond shared memory: stable radix sort of the p-values in global scratch.
 #pragma once
 #include "o2a_device.cuh"
 #include "o2a_fit.cuh"
 
 namespace o2a {
 
-constexpr int FILTER_THREADS = 64;
-constexpr int FILTER_ROWS = 8;                       // rows (double2 per lane) per warp and pass
-constexpr int FILTER_TILE = FILTER_THREADS * 2 * FILTER_ROWS;
 constexpr int RANK_SMALL_MAX = 1024;                 // survivors ranked in shared memory
 constexpr int TBL_SMEM_MAX = 256;
 
@@ -28,104 +22,16 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double* p)
     return r;
 }
 
-// Layout inside a tile of FILTER_TILE elements: warp w owns the contiguous chunk
-// [w*FILTER_WCHUNK, (w+1)*FILTER_WCHUNK), as FILTER_ROWS rows of 64 elements (32 lanes x double2,
-// 512 contiguous bytes per warp load). Order-preserving positions then need only: the lane prefix
-// (ballots), the running row prefix (registers) and ONE cross-warp prefix per tile (8 counters).
-__global__ void __launch_bounds__(FILTER_THREADS, 20)
-k_filter(long long n_aln, const long long* __restrict__ hsp_off, const int* __restrict__ aln_lnc,
-         const double* __restrict__ score, const double* __restrict__ thr, const int* __restrict__ lnc_status,
-         int* __restrict__ n_surv, int* __restrict__ surv_idx, double* __restrict__ surv_x)
-{
-    constexpr int NW = FILTER_THREADS / 32;
-    constexpr int WCHUNK = FILTER_ROWS * 64;
-    __shared__ int s_wtot[2][NW];
-    const int lane = lane_id(), w = warp_id();
-    const unsigned lt = lanemask_lt();
-    int buf = 0;
-
-    for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
-        const int l = aln_lnc[a];
-        const long long h0 = hsp_off[a];
-        const int m = (int)(hsp_off[a + 1] - h0);
-        if (lnc_status[l] != 0) {                     // fit failed: the reference raised before the loop
-            if (threadIdx.x == 0) n_surv[a] = 0;
-            continue;
-        }
-        const double t = thr[l];
-        // the stream is read from the 16-byte aligned address at or just below score + h0: stream
-        // element i is HSP i - sh of the alignment (sh = 0 or 1); element -1 belongs to the neighbour
-        const int sh = (int)(h0 & 1);
-        const double* sc = score + h0 - sh;
-        const int ms = m + sh;                        // stream length
-        int* out_idx = surv_idx + h0;
-        double* out_x = surv_x + h0;
-        const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);   // never passes the strict '>'
-        int base = 0;
-        for (int t0 = 0; t0 < ms; t0 += FILTER_TILE) {
-            const int e0 = t0 + w * WCHUNK + lane * 2;            // my first stream element of row 0
-            double2 v[FILTER_ROWS];
-#pragma unroll
-            for (int r = 0; r < FILTER_ROWS; ++r) {
-                const int rs = t0 + w * WCHUNK + r * 64;          // row start (warp-uniform)
-                if (rs + 64 <= ms) v[r] = ld_stream_f64x2(sc + e0 + r * 64);
-                else if (rs >= ms) { v[r].x = NEG_INF; v[r].y = NEG_INF; }
-                else {
-                    const int e = e0 + r * 64;
-                    v[r].x = e < ms ? sc[e] : NEG_INF;
-                    v[r].y = e + 1 < ms ? sc[e + 1] : NEG_INF;
-                }
-            }
-            if (sh && t0 == 0 && w == 0 && lane == 0) v[0].x = NEG_INF;   // the neighbour's last HSP
-            unsigned bx[FILTER_ROWS], by[FILTER_ROWS];
-            int wtot = 0;
-#pragma unroll
-            for (int r = 0; r < FILTER_ROWS; ++r) {
-                bx[r] = __ballot_sync(FULL_MASK, v[r].x > t);
-                by[r] = __ballot_sync(FULL_MASK, v[r].y > t);
-                wtot += __popc(bx[r]) + __popc(by[r]);
-            }
-            if (lane == 0) s_wtot[buf][w] = wtot;
-            __syncthreads();
-            int wbase = 0, tile_total = 0;
-#pragma unroll
-            for (int ww = 0; ww < NW; ++ww) { const int c = s_wtot[buf][ww]; wbase += (ww < w) ? c : 0; tile_total += c; }
-            buf ^= 1;                                             // double-buffered: one barrier per tile
-            if (wtot) {
-                int pos = base + wbase;
-#pragma unroll
-                for (int r = 0; r < FILTER_ROWS; ++r) {
-                    const unsigned mx = bx[r], my = by[r];
-                    if (mx | my) {
-                        int p = pos + __popc(mx & lt) + __popc(my & lt);
-                        const int e = e0 + r * 64 - sh;          // HSP position inside the alignment
-                        if ((mx >> lane) & 1u) { out_idx[p] = e; out_x[p] = v[r].x; ++p; }
-                        if ((my >> lane) & 1u) { out_idx[p] = e + 1; out_x[p] = v[r].y; }
-                        pos += __popc(mx) + __popc(my);
-                    }
-                }
-            }
-            base += tile_total;
-        }
-        if (threadIdx.x == 0) n_surv[a] = base;
-    }
-}
-
-// Narrow-score variant: integral scores as int8 / int16 / int32 (BLAST raw scores are integers; only HSPs
+// Narrow scores: integral scores as int8 / int16 / int32 (BLAST raw scores are integers; only HSPs
 // cut at a gene boundary carry fractional scores, alignment.py:330). The sentinel (most negative
 // value of T) marks an HSP whose score is not representable: its exact float64 value sits in the
-// alignment's exception list (exc_pos ascending HSP positions, exc_val). Same ordered compaction as
-// k_filter; one 16-byte load carries 16 (int8), 8 (int16) or 4 (int32) scores per lane, `score > thr` is the
-// integer test `q > floor(thr)` (the sentinel never passes it), and the few exceptions that DO pass
-// (value > thr) are resolved once per alignment into a tiny shared list that sentinel lanes consult.
+// alignment's exception list (exc_pos ascending HSP positions, exc_val). One 16-byte load carries 16 (int8),
+// 8 (int16) or 4 (int32) scores per lane, `score > thr` is the integer test `q > floor(thr)` (the sentinel
+// never passes it), and the few exceptions that DO pass (value > thr) are resolved once per alignment.
 template <typename T> struct QTraits;
 template <> struct QTraits<short> { static constexpr int PER = 8; static constexpr int SENT = -32768; };
 template <> struct QTraits<int> { static constexpr int PER = 4; static constexpr int SENT = INT32_MIN; };
 template <> struct QTraits<signed char> { static constexpr int PER = 16; static constexpr int SENT = -128; };
-
-constexpr int FILTERQ_ROWS = 2;               // 16-byte loads per lane per pass
-constexpr int FILTERQ_THREADS = 64;           // narrow scores: small CTAs, many alignments in flight per SM
-constexpr int FILTERQ_PASS_SMEM = 128;        // passing exceptions kept in shared memory per alignment
 
 template <typename T>
 __device__ __forceinline__ int q_at(const int4& raw, int c)
@@ -141,163 +47,6 @@ __device__ __forceinline__ int q_at(const int4& raw, int c)
     return (c & 1) ? (word >> 16) : (int)(short)(word & 0xffff);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(FILTERQ_THREADS, 20)
-k_filter_q(long long n_aln, const long long* __restrict__ hsp_off, const int* __restrict__ aln_lnc,
-           const T* __restrict__ score_q, const long long* __restrict__ exc_off, const int* __restrict__ exc_pos,
-           const double* __restrict__ exc_val, long long n_hsp_total,
-           const double* __restrict__ thr, const int* __restrict__ lnc_status,
-           int* __restrict__ n_surv, int* __restrict__ surv_idx, double* __restrict__ surv_x)
-{
-    constexpr int NW = FILTERQ_THREADS / 32;
-    constexpr int PER = QTraits<T>::PER;                 // scores per 16-byte load
-    constexpr int SENT = QTraits<T>::SENT;
-    constexpr int ROWLEN = 32 * PER;                     // scores per warp load
-    constexpr int WCHUNK = FILTERQ_ROWS * ROWLEN;
-    constexpr int TILE = NW * WCHUNK;
-    __shared__ int s_wtot[2][NW];
-    __shared__ int s_ppos[FILTERQ_PASS_SMEM];            // positions of the exceptions with value > thr
-    __shared__ double s_pval[FILTERQ_PASS_SMEM];
-    __shared__ int s_np;
-    const int lane = lane_id(), w = warp_id();
-    int buf = 0;
-
-    for (long long a = blockIdx.x; a < n_aln; a += gridDim.x) {
-        const int l = aln_lnc[a];
-        const long long h0 = hsp_off[a];
-        const int m = (int)(hsp_off[a + 1] - h0);
-        if (lnc_status[l] != 0) { if (threadIdx.x == 0) n_surv[a] = 0; continue; }
-        const double t = thr[l];
-        // q > thr  <=>  q > floor(thr) for integers; clamped so that the sentinel can never pass
-        const double tf = floor(t);
-        const int tq = tf >= 2147483647.0 ? 2147483647 : (tf <= (double)SENT ? SENT : (int)tf);
-        const long long x0 = exc_off[a];
-        const int ne = (int)(exc_off[a + 1] - x0);
-        const int sh = (int)(h0 & (PER - 1));                  // stream starts at the aligned address below
-        const T* sc = score_q + h0 - sh;
-        const int ms = m + sh;
-        const long long g0 = h0 - sh;                          // global index of stream element 0
-        int* out_idx = surv_idx + h0;
-        double* out_x = surv_x + h0;
-        auto load_row = [&](int e) -> int4 {
-            if (g0 + e + PER <= n_hsp_total) return *reinterpret_cast<const int4*>(sc + e);
-            T q[PER];                                          // tail of the whole score array
-#pragma unroll
-            for (int c = 0; c < PER; ++c) q[c] = (g0 + e + c < n_hsp_total) ? sc[e + c] : (T)SENT;
-            int4 r4; memcpy(&r4, q, 16); return r4;
-        };
-        // the first tile's loads are issued before the exception pre-pass so both latencies overlap
-        int4 raw[FILTERQ_ROWS];
-#pragma unroll
-        for (int r = 0; r < FILTERQ_ROWS; ++r) raw[r] = load_row(w * WCHUNK + lane * PER + r * ROWLEN);
-        __syncthreads();                                       // previous alignment is done with s_ppos / s_np
-        if (threadIdx.x == 0) s_np = 0;
-        __syncthreads();
-        // exceptions that pass the filter (value > thr): usually a handful; order is irrelevant
-        for (int i = threadIdx.x; i < ne; i += FILTERQ_THREADS) {
-            const double v = exc_val[x0 + i];
-            if (v > t) {
-                const int p = atomicAdd(&s_np, 1);
-                if (p < FILTERQ_PASS_SMEM) { s_ppos[p] = exc_pos[x0 + i]; s_pval[p] = v; }
-            }
-        }
-        __syncthreads();
-        const int np = s_np;                                   // > FILTERQ_PASS_SMEM: fall back to the global list
-        int base = 0;
-        for (int t0 = 0; t0 < ms; t0 += TILE) {
-            const int e0 = t0 + w * WCHUNK + lane * PER;
-            if (t0 > 0) {
-#pragma unroll
-                for (int r = 0; r < FILTERQ_ROWS; ++r) raw[r] = load_row(e0 + r * ROWLEN);
-            }
-            unsigned pass[FILTERQ_ROWS];                       // PER flag bits per row
-            int cnt[FILTERQ_ROWS];
-#pragma unroll
-            for (int r = 0; r < FILTERQ_ROWS; ++r) {
-                const int e = e0 + r * ROWLEN;                 // stream index of my first score of this row
-                unsigned msk = 0, sent = 0;
-#pragma unroll
-                for (int c = 0; c < PER; ++c) {
-                    const int q = q_at<T>(raw[r], c);
-                    msk |= (q > tq ? 1u : 0u) << c;
-                    sent |= (q == SENT ? 1u : 0u) << c;
-                }
-                // lanes straddling the alignment borders drop what is outside [sh, ms)
-                if (e < sh || e + PER > ms) {
-                    unsigned inside = 0;
-#pragma unroll
-                    for (int c = 0; c < PER; ++c) inside |= ((e + c >= sh && e + c < ms) ? 1u : 0u) << c;
-                    msk &= inside; sent &= inside;
-                }
-                // exceptions: pass iff listed among the passing ones
-                while (sent) {
-                    const int c = __ffs(sent) - 1; sent &= sent - 1;
-                    const int pos = e + c - sh;
-                    bool ok = false;
-                    if (np <= FILTERQ_PASS_SMEM) {
-                        for (int i = 0; i < np; ++i) if (s_ppos[i] == pos) { ok = true; break; }
-                    } else {
-                        int lo = 0, hi = ne;
-                        while (lo < hi) { int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < pos) lo = mid + 1; else hi = mid; }
-                        ok = lo < ne && exc_pos[x0 + lo] == pos && exc_val[x0 + lo] > t;
-                    }
-                    if (ok) msk |= 1u << c;
-                }
-                pass[r] = msk;
-                cnt[r] = __popc(msk);
-            }
-            // warp-inclusive scan of the per-lane counts of both rows (row 0 precedes row 1 for every lane?
-            // no: element order is row-major, so each row is scanned on its own)
-            int incl[FILTERQ_ROWS];
-#pragma unroll
-            for (int r = 0; r < FILTERQ_ROWS; ++r) {
-                int x = cnt[r];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += y; }
-                incl[r] = x;
-            }
-            int rowtot[FILTERQ_ROWS];
-            int wtot = 0;
-#pragma unroll
-            for (int r = 0; r < FILTERQ_ROWS; ++r) { rowtot[r] = __shfl_sync(FULL_MASK, incl[r], 31); wtot += rowtot[r]; }
-            if (lane == 0) s_wtot[buf][w] = wtot;
-            __syncthreads();
-            int wbase = 0, tile_total = 0;
-#pragma unroll
-            for (int ww = 0; ww < NW; ++ww) { const int c = s_wtot[buf][ww]; wbase += (ww < w) ? c : 0; tile_total += c; }
-            buf ^= 1;
-            int pos = base + wbase;
-#pragma unroll
-            for (int r = 0; r < FILTERQ_ROWS; ++r) {
-                unsigned msk = pass[r];
-                if (msk) {
-                    int p = pos + incl[r] - cnt[r];
-                    const int e = e0 + r * ROWLEN - sh;        // HSP position of my first score of this row
-#pragma unroll
-                    for (int c = 0; c < PER; ++c) {
-                        if ((msk >> c) & 1u) {
-                            const int q = q_at<T>(raw[r], c);
-                            double x = (double)q;
-                            if (q == SENT) {                    // a passing exception: its float64 value
-                                if (np <= FILTERQ_PASS_SMEM) { for (int i = 0; i < np; ++i) if (s_ppos[i] == e + c) { x = s_pval[i]; break; } }
-                                else {
-                                    int lo = 0, hi = ne;
-                                    while (lo < hi) { int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < e + c) lo = mid + 1; else hi = mid; }
-                                    x = exc_val[x0 + lo];
-                                }
-                            }
-                            out_idx[p] = e + c; out_x[p] = x; ++p;
-                        }
-                    }
-                }
-                pos += rowtot[r];
-            }
-            base += tile_total;
-        }
-        if (threadIdx.x == 0) n_surv[a] = base;
-    }
-}
-
 struct PqArgs {
     long long n_aln;
     const long long* hsp_off;
@@ -310,10 +59,11 @@ struct PqArgs {
     // kde / empirical
     const int* uv_val; const int* uv_cnt; const int* uv_n; const double* kde_factor;
     int fitter; int fdr; double alpha;
-    const double* surv_x;      // survivor scores (written by k_filter)
+    const double* surv_x;      // survivor scores (written by the filter phase of k_front)
     double* surv_p;            // out: p-values
     double* surv_pq; unsigned char* surv_keep; int* n_keep;
-    int* big_list; int* big_count;
+    const int* pq_list; const int* pq_count;   // alignments k_front queued for k_pq
+    int* big_list; int* big_count;             // alignments k_pq queues for k_rank_big
 };
 
 // Survivor scores of one alignment are mostly small integers (BLAST raw scores) with few distinct
@@ -325,10 +75,8 @@ struct PqArgs {
 // counts, per tie group, the survivors seen so far (match.any) -> the stable rank
 //   rank_k = 1 + L[class_k] + #{j < k : p_j == p_k}
 // exactly as np.argsort(kind='stable') would assign it. More than PQ_OVER overflow classes fall back
-// to the plain all-pairs rank.
-// Two instantiations: the warp variant (32 threads, <= 256 survivors, small tables: 32 CTAs per SM, so
-// 32 alignments in flight per SM hide the per-alignment latency chain) and the CTA variant for larger
-// survivor sets. Each skips the alignments of the other's domain.
+// to the plain all-pairs rank. (The common case — at most FRONT_SCAP survivors — never gets here: the
+// same class algorithm runs warp-synchronously inside k_front.)
 
 struct PqFit {
     LncFit f; const int* tk; const double* tc;
@@ -342,11 +90,11 @@ __device__ __forceinline__ double pq_sf(double x, const PqFit& F)
     return emp_sf_compressed(x, F.uval, F.ucnt, F.unv, F.nbg);
 }
 
-template <int PQ_THREADS, int MIN_BLOCKS, int SMAX_LO, int SMAX, int PQ_DIRECT, int PQ_OVER, int TBL_MAX>
+template <int PQ_THREADS, int MIN_BLOCKS, int SMAX, int PQ_DIRECT, int PQ_OVER, int TBL_MAX>
 __global__ void __launch_bounds__(PQ_THREADS, MIN_BLOCKS)
 k_pq(PqArgs A)
 {
-    constexpr int PQ_SLOTS = PQ_DIRECT + PQ_OVER;     // survivors in (SMAX_LO, SMAX] are this instantiation's
+    constexpr int PQ_SLOTS = PQ_DIRECT + PQ_OVER;
     // class tables; the all-pairs fallback (s_p) aliases them — the two are never live together
     __shared__ __align__(16) unsigned char s_raw[PQ_SLOTS * (8 + 4 + 4 + 2 + 2) + PQ_OVER * 8];
     static_assert(sizeof(s_raw) >= SMAX * sizeof(double), "fallback buffer must fit");
@@ -364,10 +112,11 @@ k_pq(PqArgs A)
     __shared__ int s_keepcnt, s_nover, s_maxslot;
     const int tid = threadIdx.x, lane = lane_id();
 
-    for (long long a = blockIdx.x; a < A.n_aln; a += gridDim.x) {
+    const int n_items = *A.pq_count;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const long long a = A.pq_list[it];
         const int ns = A.n_surv[a];
-        if (ns == 0) { if (tid == 0 && SMAX_LO == 0) A.n_keep[a] = 0; continue; }
-        if (ns <= SMAX_LO || (ns > SMAX && SMAX < RANK_SMALL_MAX)) continue;    // the other instantiation's
+        if (ns == 0) { if (tid == 0) A.n_keep[a] = 0; continue; }
         const int l = A.aln_lnc[a];
         const long long h0 = A.hsp_off[a];
         const int m = (int)(A.hsp_off[a + 1] - h0);
@@ -558,6 +307,7 @@ k_rank_big(const int* __restrict__ big_list, const int* __restrict__ big_count,
         const long long h0 = hsp_off[a];
         const int m = (int)(hsp_off[a + 1] - h0);
         const int ns = n_surv[a];
+        if ((long long)ns > cap) continue;                  // understated max_aln_hsps: the call fails on the host side
         for (int k = tid; k < ns; k += RANKBIG_THREADS) { k0[k] = sortable_f64(surv_p[h0 + k]); v0[k] = (unsigned)k; }
         if (tid == 0) s_keepcnt = 0;
         __syncthreads();

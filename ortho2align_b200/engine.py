@@ -67,6 +67,37 @@ class DeviceBatch:
         return s
 
 
+_ENGINES = {}
+_ENGINES_LOCK = None
+
+
+def get_engine(device=0):
+    """The process-wide persistent Engine of `device` (created on first use, closed at interpreter exit): CUDA
+    context, streams and the grow-only device workspace are paid once per process, not once per call."""
+    global _ENGINES_LOCK
+    import atexit
+    import threading
+    if _ENGINES_LOCK is None:
+        _ENGINES_LOCK = threading.Lock()
+        atexit.register(close_engines)
+    with _ENGINES_LOCK:
+        eng = _ENGINES.get(int(device))
+        if eng is None or not eng.h:
+            eng = Engine(int(device))
+            eng.lock = threading.Lock()          # a ctx is single-threaded: callers serialise on it
+            _ENGINES[int(device)] = eng
+        return eng
+
+
+def close_engines():
+    for eng in list(_ENGINES.values()):
+        try:
+            eng.close()
+        except Exception:
+            pass
+    _ENGINES.clear()
+
+
 class Engine:
     def __init__(self, device=0):
         self.lib = _lib.load()
@@ -132,6 +163,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.o2a_launch_count(self.h))
 
+    COORDS_MODES = {"auto": 0, "zerocopy": 1, "gather": 2, "upload": 3}
+
+    def set_coords_mode(self, mode="auto"):
+        """How the retained HSPs' coordinate records of HOST batches reach the device (include/o2a.h, O2A_COORDS_*)."""
+        self._check(self.lib.o2a_set_coords_mode(self.h, self.COORDS_MODES[mode]), "o2a_set_coords_mode")
+
+    def coords_mode(self):
+        """Mode the last host batch used."""
+        k = int(self.lib.o2a_coords_mode(self.h))
+        return {v: n for n, v in self.COORDS_MODES.items()}[k]
+
     @staticmethod
     def params(fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
                best_value="block_length", best_function="max"):
@@ -167,6 +209,28 @@ class Engine:
         s.max_aln_hsps = int(np.diff(batch.hsp_off).max()) if batch.n_aln else 0
         s.max_lnc_bg = int(np.diff(batch.bg_off).max()) if batch.n_lnc else 0
         return s
+
+    @staticmethod
+    def hostbatch_struct(hb, with_kde):
+        """`o2a_batch` over a `hostbatch.HostBatch` (the pinned narrow layout the ingest returns): exactly these
+        buffers cross PCIe. The struct holds raw addresses; it keeps `hb` alive."""
+        s = _lib.O2ABatch()
+        s.n_lnc, s.n_aln, s.n_hsp, s.n_bg = hb.n_lnc, hb.n_aln, hb.n_hsp, hb.n_bg
+        for k in ("bg_off", "aln_off", "hsp_off", "qlen", "slen", "exc_off", "exc_pos", "exc_val", "score_q", "coords"):
+            setattr(s, k, getattr(hb, k).ctypes.data)
+        s.bg, s.bg_bits, s.score_bits = hb.bg_q.ctypes.data, hb.bg_bits, hb.score_bits
+        s.kde_factor = hb.ensure_kde_factor().ctypes.data if with_kde else None
+        s.mem = 0
+        s.max_aln_hsps, s.max_lnc_bg = hb.max_aln_hsps, hb.max_lnc_bg
+        s._keepalive = hb
+        return s
+
+    def build_host(self, hb, fitter="hist", fdr=True, alpha=0.05, gapopen=5, gapextend=2,
+                   best_value="block_length", best_function="max", survivors=True, pinned=False) -> BatchResult:
+        """`build_batch` for a `HostBatch`: what `pipeline.build_orthologs` calls with the ingest's output."""
+        p = self.params(fitter, fdr, alpha, gapopen, gapextend, best_value, best_function)
+        self.run(self.hostbatch_struct(hb, with_kde=(fitter == "kde")), p)
+        return self.fetch(survivors=survivors, pinned=pinned)
 
     def run(self, batch_struct, params):
         """Raw call: `o2a_build_batch` on a prepared struct. Returns the counts."""

@@ -17,7 +17,9 @@ from .columnar import ColumnarBatch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libo2a_ingest.so")
 EXPORTS = ["o2a_ingest_create", "o2a_ingest_destroy", "o2a_ingest_load", "o2a_ingest_sizes",
-           "o2a_ingest_export", "o2a_ingest_span", "o2a_ingest_file_error"]
+           "o2a_ingest_export", "o2a_ingest_span", "o2a_ingest_file_error",
+           "o2a_ingest_narrow_plan", "o2a_ingest_export_narrow", "o2a_ingest_pack_plan", "o2a_ingest_pack_narrow",
+           "o2a_ingest_range_texts"]
 _lib = None
 
 
@@ -36,7 +38,17 @@ def load_lib():
         lib.o2a_ingest_sizes.restype = C.c_int
         lib.o2a_ingest_sizes.argtypes = [P] + [C.POINTER(i64)] * 4
         lib.o2a_ingest_export.restype = C.c_int
-        lib.o2a_ingest_export.argtypes = [P] + [P] * 16
+        lib.o2a_ingest_export.argtypes = [P] + [P] * 17
+        lib.o2a_ingest_narrow_plan.restype = C.c_int
+        lib.o2a_ingest_narrow_plan.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(i64)]
+        lib.o2a_ingest_export_narrow.restype = C.c_int
+        lib.o2a_ingest_export_narrow.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P]
+        lib.o2a_ingest_pack_plan.restype = C.c_int
+        lib.o2a_ingest_pack_plan.argtypes = [P, i64, P, i64, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(i64)]
+        lib.o2a_ingest_pack_narrow.restype = C.c_int
+        lib.o2a_ingest_pack_narrow.argtypes = [i64, P, P, C.c_int32, P, P, P, P, P, i64, C.c_int32, P, P, P, P, P, P, C.c_int]
+        lib.o2a_ingest_range_texts.restype = i64
+        lib.o2a_ingest_range_texts.argtypes = [P, P, P, i64]
         lib.o2a_ingest_span.restype = i64
         lib.o2a_ingest_span.argtypes = [P, i64, i64, i64, P, i64]
         lib.o2a_ingest_file_error.restype = C.c_char_p
@@ -46,30 +58,68 @@ def load_lib():
 
 
 class IngestResult:
-    """batch: ColumnarBatch over the files that parsed (input order); lnc_file[l]: file index of
-    lncRNA l; file_status[i] / errors[i]; score_is_int per HSP; range dicts on demand."""
+    """host: HostBatch over the files that parsed (input order) — the pinned, narrow layout the CUDA library takes;
+    batch: the same lncRNAs as a plain ColumnarBatch (built on first use); lnc_file[l]: file index of lncRNA l;
+    file_status[i] / errors[i]; score (float64) and score_is_int per HSP; relative per alignment; range dicts on demand."""
 
-    def __init__(self, lib, handle, n_files):
+    def __init__(self, lib, handle, n_files, pinned=True, pin_coords=True):
+        from .hostbatch import HostBatch
         self._lib, self._h = lib, handle
         sizes = [C.c_int64(0) for _ in range(4)]
         lib.o2a_ingest_sizes(handle, *[C.byref(s) for s in sizes])
         n_lnc, n_aln, n_hsp, n_bg = [int(s.value) for s in sizes]
+        sb, bb, nx = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        lib.o2a_ingest_narrow_plan(handle, C.byref(sb), C.byref(bb), C.byref(nx))
+        hb = HostBatch(n_lnc, n_aln, n_hsp, n_bg, sb.value, bb.value, nx.value, pinned=pinned, pin_coords=pin_coords)
         z = lambda n, dt: np.zeros(n, dtype=dt)
         self.file_status = z(n_files, np.int32)
         self.lnc_file = z(n_lnc, np.int64)
-        bg_off, aln_off, hsp_off = z(n_lnc + 1, np.int64), z(n_lnc + 1, np.int64), z(n_aln + 1, np.int64)
-        bg, qlen, slen = z(n_bg, np.int32), z(n_aln, np.int64), z(n_aln, np.int64)
-        coords = np.zeros((n_hsp, 4), dtype=np.int32)
-        qs, qe, ss, se = (z(n_hsp, np.int32) for _ in range(4))
-        score, self.score_is_int = z(n_hsp, np.float64), z(n_hsp, np.uint8)
+        self.score, self.score_is_int = np.empty(n_hsp, dtype=np.float64), np.empty(n_hsp, dtype=np.uint8)
         self.spans = np.zeros((n_aln, 4), dtype=np.int64)
+        self.relative = z(n_aln, np.uint8)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        lib.o2a_ingest_export(handle, p(self.file_status), p(self.lnc_file), p(bg_off), p(bg), p(aln_off), p(hsp_off),
-                              p(qlen), p(slen), p(coords), p(qs), p(qe), p(ss), p(se), p(score), p(self.score_is_int),
-                              p(self.spans))
-        self.batch = ColumnarBatch(bg_off, bg, aln_off, hsp_off, qlen, slen, qs, qe, ss, se, score)
-        self.batch._coords4 = coords
+        lib.o2a_ingest_export(handle, p(self.file_status), p(self.lnc_file), p(hb.bg_off), None, p(hb.aln_off), p(hb.hsp_off),
+                              p(hb.qlen), p(hb.slen), p(hb.coords), None, None, None, None, p(self.score),
+                              p(self.score_is_int), p(self.spans), p(self.relative))
+        if lib.o2a_ingest_export_narrow(handle, sb.value, bb.value, p(hb.score_q), p(hb.exc_off), p(hb.exc_pos),
+                                        p(hb.exc_val), p(hb.bg_q)) != 0:
+            raise RuntimeError("o2a_ingest_export_narrow failed")
+        self.host = hb.finish()
+        self._batch = None
+        self._range_off = self._range_blob = None
         self.errors = {i: lib.o2a_ingest_file_error(handle, i).decode() for i in np.nonzero(self.file_status)[0]}
+
+    @property
+    def batch(self):
+        """Plain ColumnarBatch view of the same lncRNAs (int32 background, SoA coordinates, float64 scores)."""
+        if self._batch is None:
+            hb = self.host
+            c = hb.coords
+            b = ColumnarBatch(hb.bg_off, hb.bg_q.astype(np.int32), hb.aln_off, hb.hsp_off, hb.qlen, hb.slen,
+                              np.ascontiguousarray(c[:, 0]), np.ascontiguousarray(c[:, 1]),
+                              np.ascontiguousarray(c[:, 2]), np.ascontiguousarray(c[:, 3]), self.score)
+            b._coords4 = c
+            self._batch = b
+        return self._batch
+
+    @property
+    def hsp_off(self):
+        return self.host.hsp_off
+
+    def gather_hsps(self, gidx):
+        """qstart, qend, sstart, send, score of the HSPs `gidx` (global indices): one gather from the AoS records."""
+        c = self.host.coords[gidx]
+        return c[:, 0], c[:, 1], c[:, 2], c[:, 3], self.score[gidx]
+
+    def _ranges(self):
+        if self._range_off is None:
+            n_aln = self.host.n_aln
+            off = np.zeros(2 * n_aln + 1, dtype=np.int64)
+            total = int(self._lib.o2a_ingest_range_texts(self._h, off.ctypes.data_as(C.c_void_p), None, 0))
+            blob = np.zeros(max(total, 1), dtype=np.uint8)
+            self._lib.o2a_ingest_range_texts(self._h, off.ctypes.data_as(C.c_void_p), blob.ctypes.data_as(C.c_void_p), total)
+            self._range_off, self._range_blob = off, blob[:total]
+        return self._range_off, self._range_blob
 
     def range_dict(self, a, which):
         """Decoded qrange ('q') or srange ('s') dict of global alignment index `a`. Consecutive alignments of
@@ -78,12 +128,9 @@ class IngestResult:
 
     def range_text(self, a, which):
         """Raw JSON text of the qrange / srange object of alignment `a` (bytes)."""
-        l = int(np.searchsorted(self.batch.aln_off, a, side="right") - 1)
-        b, e = (self.spans[a, 0], self.spans[a, 1]) if which == "q" else (self.spans[a, 2], self.spans[a, 3])
-        n = int(e - b)
-        buf = C.create_string_buffer(n)
-        self._lib.o2a_ingest_span(self._h, int(self.lnc_file[l]), int(b), int(e), buf, n)
-        return buf.raw[:n]
+        off, blob = self._ranges()
+        k = 2 * int(a) + (0 if which == "q" else 1)
+        return blob[off[k]:off[k + 1]].tobytes()
 
     def hsp_dict(self, h):
         return _hsp_dict(self.batch, self.score_is_int, h)
@@ -93,12 +140,15 @@ class IngestResult:
 
     def close(self):
         if self._h:
+            self._ranges()                 # the texts outlive the native handle
             self._lib.o2a_ingest_destroy(self._h)
             self._h = None
 
     def __del__(self):
         try:
-            self.close()
+            if self._h:
+                self._lib.o2a_ingest_destroy(self._h)
+                self._h = None
         except Exception:
             pass
 
@@ -139,6 +189,7 @@ def _hsp_dict(b, score_is_int, h):
 # straight into pinned buffers) without any parsing.
 # --------------------------------------------------------------------------------------------------
 SIDECAR_MAGIC = b"O2ACOL01"
+SIDECAR_VERSION = 2
 _SIDECAR_ALIGN = 4096
 _SIDECAR_ARRAYS = ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score")
 
@@ -157,16 +208,14 @@ def _manifest(align_files, bg_files):
 def save_sidecar(path, r, align_files, bg_files):
     """Write the IngestResult `r` (all files parsed) as a columnar sidecar; atomic via rename."""
     b = r.batch
-    n_aln = b.n_aln
-    texts = [r.range_text(a, w) for a in range(n_aln) for w in ("q", "s")]
-    range_off = np.zeros(2 * n_aln + 1, dtype=np.int64)
-    np.cumsum([len(t) for t in texts], out=range_off[1:])
+    range_off, range_blob = r._ranges()
     sections = {k: np.ascontiguousarray(getattr(b, k)) for k in _SIDECAR_ARRAYS}
     sections["score_is_int"] = np.ascontiguousarray(r.score_is_int)
+    sections["relative"] = np.ascontiguousarray(r.relative)
     sections["lnc_file"] = np.ascontiguousarray(r.lnc_file)
-    sections["range_off"] = range_off
-    sections["range_text"] = np.frombuffer(b"".join(texts), dtype=np.uint8)
-    directory = {"version": 1, "n_files": len(align_files), "manifest": _manifest(align_files, bg_files), "sections": {}}
+    sections["range_off"] = np.ascontiguousarray(range_off)
+    sections["range_text"] = np.ascontiguousarray(range_blob)
+    directory = {"version": SIDECAR_VERSION, "n_files": len(align_files), "manifest": _manifest(align_files, bg_files), "sections": {}}
     # two passes: the directory's own length decides where the first section starts
     def layout(base):
         off = base
@@ -204,10 +253,32 @@ class SidecarResult:
             return np.asarray(m)           # plain ndarray view of the mapping: np.memmap's own indexing is slow
         self.batch = ColumnarBatch(*[arr(k) for k in _SIDECAR_ARRAYS])
         self.score_is_int = arr("score_is_int")
+        self.relative = arr("relative")
+        self.score = self.batch.score
         self.lnc_file = arr("lnc_file")
         self._range_off, self._range_text = arr("range_off"), arr("range_text")
+        self._host = None
         self.file_status = np.zeros(directory["n_files"], dtype=np.int32)
         self.errors = {}
+
+    @property
+    def host(self):
+        """The pinned narrow layout of the mapped arrays (packed once, on first use)."""
+        if self._host is None:
+            from .hostbatch import HostBatch
+            self._host = HostBatch.from_columnar(self.batch)
+        return self._host
+
+    @property
+    def hsp_off(self):
+        return self.batch.hsp_off
+
+    def gather_hsps(self, gidx):
+        b = self.batch
+        return tuple(np.asarray(getattr(b, k))[gidx] for k in ("qstart", "qend", "sstart", "send", "score"))
+
+    def _ranges(self):
+        return self._range_off, self._range_text
 
     def range_text(self, a, which):
         k = 2 * a + (0 if which == "q" else 1)
@@ -236,12 +307,14 @@ def open_sidecar(path, align_files, bg_files):
             directory = json.loads(f.read(int(np.frombuffer(pre[8:], dtype=np.int64)[0])))
     except (OSError, ValueError):
         return None
-    if directory.get("version") != 1 or directory.get("manifest") != _manifest(align_files, bg_files):
+    if directory.get("version") != SIDECAR_VERSION or directory.get("manifest") != _manifest(align_files, bg_files):
         return None
     return SidecarResult(path, directory)
 
 
-def load_files(align_files, bg_files, threads=0) -> IngestResult:
+def load_files(align_files, bg_files, threads=0, pinned=True, pin_coords=True) -> IngestResult:
+    """Parse the file pairs on `threads` native threads. The result's `.host` is the pinned narrow layout
+    (`hostbatch.HostBatch`) the CUDA library takes as is; `pinned=False` keeps it in ordinary memory."""
     lib = load_lib()
     n = len(align_files)
     h = C.c_void_p(lib.o2a_ingest_create(int(threads)))
@@ -249,4 +322,4 @@ def load_files(align_files, bg_files, threads=0) -> IngestResult:
     arr_b = (C.c_char_p * n)(*[os.fsencode(p) for p in bg_files])
     if lib.o2a_ingest_load(h, arr_a, arr_b, n) != 0:
         raise RuntimeError("o2a_ingest_load failed")
-    return IngestResult(lib, h, n)
+    return IngestResult(lib, h, n, pinned=pinned, pin_coords=pin_coords)

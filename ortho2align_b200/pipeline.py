@@ -81,7 +81,8 @@ def _ingest_json(alignments_files, bg_files):
             continue
         d = alignment_dicts
         out.append((batch, 0, len(d), (lambda k, d=d: d[k]["qrange"]), (lambda k, d=d: d[k]["srange"]),
-                    (lambda k, idx, d=d: [d[k]["HSPs"][int(j)] for j in idx]), None))
+                    (lambda k, idx, d=d: [d[k]["HSPs"][int(j)] for j in idx]), None,
+                    (lambda k, d=d: bool(d[k].get("relative")))))
     return out
 
 
@@ -103,30 +104,34 @@ def _ingest_native(alignments_files, bg_files, threads, cache=None):
         with open(alignments_files[i]) as f:
             d = json.load(f)
         out[i] = ExceptionLogger(PackError(r.errors[int(i)]), Range.from_dict(d[0]["qrange"]) if d else None)
-    b = r.batch
+    b = r.host                               # the pinned narrow layout: handed to the library as is
     aln_off, hsp_off = b.aln_off.tolist(), b.hsp_off
+    rel = r.relative
     for l, i in enumerate(r.lnc_file.tolist()):
         a0, a1 = aln_off[l], aln_off[l + 1]
         out[i] = (b, l, a1 - a0,
                   (lambda k, a0=a0: r.range_dict(a0 + k, "q")), (lambda k, a0=a0: r.range_dict(a0 + k, "s")),
                   (lambda k, idx, a0=a0: r.hsp_dicts(int(hsp_off[a0 + k]) + idx)),
-                  (r, a0))                   # columnar source of the lncRNA's HSPs, for the native record formatter
+                  (r, a0),                   # columnar source of the lncRNA's HSPs, for the native record formatter
+                  (lambda k, a0=a0: bool(rel[a0 + k])))
     return out
 
 
 def _run_shards(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
-    """One Engine (= one o2a_ctx) per GPU, each on its own thread; ctypes releases the GIL."""
-    from .engine import Engine
+    """One persistent Engine (= one o2a_ctx, `engine.get_engine`) per GPU, each driven from its own thread; ctypes
+    releases the GIL. A `HostBatch` (the ingest's pinned narrow layout) goes to the library as is; a plain
+    `ColumnarBatch` (the Python JSON reader, multi-GPU shards) is packed into that layout first."""
+    from .engine import get_engine
+    from .hostbatch import HostBatch
     results = [None] * len(batches)
     errors = []
 
     def work(k):
         try:
-            eng = Engine(devices[k])
-            try:
-                results[k] = eng.build_batch(batches[k], fitter, fdr, alpha, gapopen, gapextend, survivors=False)
-            finally:
-                eng.close()
+            eng = get_engine(devices[k])
+            hb = batches[k] if isinstance(batches[k], HostBatch) else HostBatch.from_columnar(batches[k])
+            with eng.lock:
+                results[k] = eng.build_host(hb, fitter, fdr, alpha, gapopen, gapextend, survivors=False)
         except Exception as e:  # surfaced below, on the caller's thread
             errors.append(e)
 
@@ -172,9 +177,8 @@ def _format_chains_native(chain_desc, strings, qplus, src, threads):
         dst_pos = np.repeat(hsp_off[sel], l) + within
         gidx[dst_pos] = np.asarray(res.chain_idx)[src_pos].astype(np.int64) + np.repeat(base[sel], l)
         pval[dst_pos] = np.asarray(res.chain_pq)[src_pos]
-    b = src.batch
-    cols = [np.asarray(getattr(b, k))[gidx] for k in ("qstart", "qend", "sstart", "send")]
-    return records_native.format_records(hsp_off, *cols, np.asarray(b.score)[gidx], np.asarray(src.score_is_int)[gidx],
+    *cols, score = src.gather_hsps(gidx)
+    return records_native.format_records(hsp_off, *cols, score, np.asarray(src.score_is_int)[gidx],
                                          pval, np.asarray(qplus, dtype=np.uint8), strings, threads=threads or 1)
 
 
@@ -227,8 +231,11 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
         else:
             weights = [x.n_hsp + 1 for x in src]
         shards = lpt_shards(weights, n_dev)
-        if one_source:
-            batches = [src[0].take_lnc([src_l[j] for j in shard]) for shard in shards]
+        if one_source and n_dev == 1 and shards[0] == list(range(src[0].n_lnc)):
+            batches = [src[0]]                                  # the ingest's buffers, untouched
+        elif one_source:
+            columnar = src[0].to_columnar() if hasattr(src[0], "to_columnar") else src[0]
+            batches = [columnar.take_lnc([src_l[j] for j in shard]) for shard in shards]
         else:
             batches = [concat_batches([src[j] for j in shard]) for shard in shards]
         results = _run_shards(batches, devices[:n_dev], fitting, fdr, threshold, gapopen, gapextend)
@@ -246,7 +253,7 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
         if isinstance(item, ExceptionLogger):
             exceptions.append(item)
             continue
-        _, _, n_alns, qrange_of, srange_of, hsps_of, columnar_src = item
+        _, _, n_alns, qrange_of, srange_of, hsps_of, columnar_src, relative_of = item
         if records != "native":
             columnar_src = None
         batch, res, l = per_lnc[i]
@@ -266,9 +273,11 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
             srange = Range.from_dict(srange_of(k))
             srange.name = qrange.name                                   # pipeline.py:781
             c0, c1 = int(res.chain_off[a]), int(res.chain_off[a + 1])
+            if c1 > c0 and relative_of(k):
+                c1 = c0               # to_record raises ValueError for a relative alignment (genomicranges.py:1259): dropped
             if c1 > c0 and columnar_src is not None:
                 chain_src, a0_src = columnar_src
-                chain_desc.append((res, c0, c1, int(chain_src.batch.hsp_off[a0_src + k])))
+                chain_desc.append((res, c0, c1, int(chain_src.hsp_off[a0_src + k])))
                 chain_strings += [str(qrange.chrom), str(qrange.name), str(srange.chrom)]
                 chain_qplus.append(qrange.strand in ["+", "."])
                 q_orth.append(None)                                     # the text is produced for all chains at once below

@@ -319,3 +319,59 @@ def test_round_trip_properties_at_scale(engine):
     # idempotence
     r2 = engine.build_batch(b, "hist", True)
     compare_results(r2, r, exact_p=True, what="idempotence")
+
+
+@pytest.mark.parametrize("mode", ["zerocopy", "gather", "upload"])
+@pytest.mark.parametrize("cfg,kw,chunks", [(2, dict(n_lnc=40), 4), (5, dict(n_lnc=900), 3), (4, dict(n_lnc=6, hsps_per_region=3000), 2),
+                                           (2, dict(n_lnc=12), 1)])
+def test_host_batch_layouts_and_coordinate_modes(engine, monkeypatch, mode, cfg, kw, chunks):
+    """The pinned narrow layout the ingest returns (HostBatch) through every way the library can fetch the retained
+    HSPs' coordinates — in place over PCIe, listed and gathered by host threads, or uploaded whole — pipelined over
+    lncRNA chunks or not: identical results. Config 4 retains everything, so the gather mode takes its dense fallback."""
+    from oracle import oracle as O
+    from ortho2align_b200 import synth
+    from ortho2align_b200.hostbatch import HostBatch
+    b = synth.workload(cfg, seed=21, **kw)
+    exp = O.build_batch(b, "hist", True)
+    monkeypatch.setenv("O2A_PIPELINE_MIN_HSPS", "0" if chunks > 1 else str(1 << 40))
+    monkeypatch.setenv("O2A_CHUNKS", str(chunks))
+    engine.set_coords_mode(mode)
+    try:
+        hb = HostBatch.from_columnar(b)
+        got = engine.build_host(hb, "hist", True)
+        assert engine.coords_mode() == (mode if (mode != "zerocopy" or hb.pinned) else "gather")
+        compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {mode} chunks={chunks}")
+        # pageable SoA caller arrays (what a plain ColumnarBatch hands over): zero-copy is not possible there
+        got = engine.build_batch(b, "hist", True)
+        assert engine.coords_mode() == ("upload" if mode == "upload" else "gather")
+        compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {mode} chunks={chunks} pageable SoA")
+        got = engine.build_batch(b, "hist", True, aos=True, score_bits=16, bg_bits=16)
+        compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {mode} chunks={chunks} pageable AoS int16")
+    finally:
+        engine.set_coords_mode("auto")
+
+
+def test_understated_size_hints_fail_the_call(engine):
+    """max_aln_hsps / max_lnc_bg are hints that size per-CTA scratch: an understated value must not be trusted."""
+    import torch
+    from ortho2align_b200 import synth
+    from ortho2align_b200.engine import DeviceBatch, O2AError
+    b = synth.workload(4, n_lnc=3, hsps_per_region=2500, seed=2)
+    p = engine.params("hist", True)
+    s = engine.host_struct(b, False)
+    s.max_aln_hsps = 100
+    with pytest.raises(O2AError):
+        engine.run(s, p)
+    db = DeviceBatch(b, torch.device("cuda", 0))
+    s = db.struct(False)
+    s.max_aln_hsps = 100
+    with pytest.raises(O2AError):
+        engine.run(s, p)
+    s = db.struct(False)
+    s.max_lnc_bg = 10
+    with pytest.raises(O2AError):
+        engine.run(s, p)
+    s = db.struct(False)                     # and the engine is still usable afterwards
+    engine.run(s, p)
+    from oracle import oracle as O
+    compare_results(engine.fetch(), O.build_batch(b, "hist", True), exact_p=True, what="after a rejected call")

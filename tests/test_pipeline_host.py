@@ -22,7 +22,9 @@ def _materialise(tmp_path, g):
 
 def _oracle_runner(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
     from oracle import oracle as O
-    return [O.build_batch(b, fitter, fdr, alpha, gapopen, gapextend) for b in batches]
+    # the native ingest hands over its pinned narrow layout (HostBatch); the oracle takes the plain columnar form
+    plain = [b.to_columnar() if hasattr(b, "to_columnar") else b for b in batches]
+    return [O.build_batch(b, fitter, fdr, alpha, gapopen, gapextend) for b in plain]
 
 
 def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest="native", cache=None, dirs=None,
