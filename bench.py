@@ -116,6 +116,18 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, config, n_lnc, fitter):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    of this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+    except (OSError, ValueError):
+        return None
+    e = table.get(f"{kernel}|C{config}|{n_lnc}|{fitter}")
+    return float(e["dram_bytes"]) if e else None
+
+
 def cpu_port_rate(batch, fitter, threads, repeats=1):
     """Oracle port (TEST INFRASTRUCTURE used as the reported CPU baseline) on `batch`: HSPs/s."""
     from oracle import oracle as O
@@ -544,15 +556,21 @@ def main():
                     help="library contexts per GPU in the e2e arm: with 2, two host threads alternate batches, so the "
                          "uploads of one batch overlap the last kernels and the result download of the other")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident arm only (profiling runs under ncu)")
     ap.add_argument("--gather", default="final", choices=["step", "final"],
                     help="N > 1: all_gather of the result counters after every step (asynchronous), or once for all "
                          "steps before the timed region closes")
     ap.add_argument("--score-bits", type=int, default=0, choices=[0, 8, 16, 32],
                     help="score layout of the device-resident arm: 0 = float64 (the reference's dtype), "
                          "8/16/32 = lossless narrow ints + exception lists")
-    ap.add_argument("--e2e-score-bits", type=int, default=8, choices=[0, 8, 16, 32],
-                    help="score layout of the pinned host buffers of the e2e arm (PCIe-bound: narrow is faster; every "
-                         "width is lossless — scores that do not fit go to per-alignment exception lists as float64)")
+    ap.add_argument("--e2e-score-bits", type=int, default=0, choices=[0, 8, 16, 32],
+                    help="force the score width of the e2e arm's host layout (0 = what the ingest's planner picks: the "
+                         "narrowest lossless width that sends at most 10 %% of the scores to the exception lists)")
+    ap.add_argument("--e2e-coords", default="zerocopy,gather",
+                    help="comma list of coordinate modes to measure in the e2e arm (zerocopy, gather, upload); the "
+                         "fastest is the one the headline e2e uses")
+    ap.add_argument("--no-e2e-f64", dest="e2e_f64", action="store_false",
+                    help="skip the second e2e figure (float64 / int32 host buffers)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -676,86 +694,101 @@ def main():
     hsps_all = batch.n_hsp * world
     value = hsps_all / (ms_step * 1e-3)
 
-    # roofline of the dominant (streaming) kernel
+    # roofline of the dominant kernel: k_front = score filter + p-values + ranks + q + keep flags, one warp per alignment
+    # (stage "filter" of the library's event timeline; the alignments it leaves to k_pq / k_rank_big are stage "pq").
+    # Algorithmic bytes (SURVEY.md 8d, K3+K4a+K5): the score of every HSP read once (8 B float64, or 1/2/4 B narrow +
+    # 12 B per exception entry) + per SURVIVOR 4 B position + 8 B score + 8 B p + 8 B q + 1 B keep written.
     peak, peak_src = measured_peak()
-    # k_filter: score read per HSP (8 B float64, or 2/4 B narrow + 12 B per exception entry) +
-    # (4 B position + 8 B score) written per survivor
     score_bytes = {0: 8.0, 8: 1.0, 16: 2.0, 32: 4.0}[args.score_bits]
     n_exc = int(dbatch.t["exc_pos"].numel()) if args.score_bits else 0
-    alg_bytes = score_bytes * batch.n_hsp + 12.0 * n_exc + 12.0 * c.n_survivors
+    alg_bytes = score_bytes * batch.n_hsp + 12.0 * n_exc + 29.0 * c.n_survivors
     avg_score_ms = float(np.mean(score_ms))
     achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of one k_filter launch from the `ncu --set full` capture of
-    # this command at the default workload (profiles/r1_ncu_full_summary_c2.txt); other workloads: not captured
-    traffic = 1.746377e9 if (args.config == 2 and batch.n_lnc == 20_000 and args.score_bits == 0) else None
-    roofline = {"bound": "hbm", "kernel": "k_filter" if args.score_bits == 0 else "k_filter_q", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    kernel = "k_front<%s>" % {0: "double", 8: "signed char", 16: "short", 32: "int"}[args.score_bits]
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(kernel, args.config, batch.n_lnc, args.fitter), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}}
+    # the same figure for the whole step: every algorithmic byte of the path (fit: the background read once, 4 B per
+    # score here; gather + chain: 28 B per retained HSP) over the step time
+    step_bytes = alg_bytes + 4.0 * batch.n_bg + 28.0 * c.n_retained
+    roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                              "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
 
     # ---------------- end-to-end arm (host buffers through the C-ABI) ----------------
+    # The host batch is the layout `ingest.load_files` returns (hostbatch.HostBatch: pinned, lossless narrow scores +
+    # exception lists, narrow background, AoS coordinates), produced here from the synthetic columnar batch by the
+    # same native encoder + allocator the ingest uses (HostBatch.from_columnar -> o2a_ingest_pack_narrow); the time
+    # that packing takes is reported as `pack_ms` (a caller that parses JSON gets the layout from the parser itself).
+    from ortho2align_b200.hostbatch import HostBatch
     e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
     del dbatch, dstruct
     torch.cuda.empty_cache()
-
-    def pin(arr):
-        tp = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
-        tp.numpy()[...] = arr
-        return tp
-
-    # only what the chosen layout actually hands to the library is pinned (host RAM: 8 ranks share one box)
-    narrow_bits = args.e2e_score_bits
-    keep_alive = {k: pin(getattr(batch, k)) for k in ("bg_off", "aln_off", "hsp_off", "qlen", "slen")}
-    # coordinates as one AoS array in pinned memory: read in place (zero-copy), 16 B per retained HSP
-    keep_alive["coords"] = pin(batch.coords4())
-    batch._coords4 = None
-    fields = {k: keep_alive[k].numpy() for k in ("bg_off", "aln_off", "hsp_off", "qlen", "slen")}
-    narrow, bg16 = None, None
-    if narrow_bits:
-        qs = batch.quantized_scores(narrow_bits)
-        # a width that sends many scores to the exception lists (12 B each) is the wrong choice for this data:
-        # what a caller would do is take the next one
-        while narrow_bits < 32 and len(qs[2]) > 0.1 * max(batch.n_hsp, 1):
-            narrow_bits *= 2
-            qs = batch.quantized_scores(narrow_bits)
-        for name, arr in zip(("score_q", "exc_off", "exc_pos", "exc_val"), qs):
-            keep_alive[name] = pin(arr)
-        del qs
-        narrow = (narrow_bits,) + tuple(keep_alive[n].numpy() for n in ("score_q", "exc_off", "exc_pos", "exc_val"))
-        fields["score"] = batch.score            # not handed to the library in this layout
-    else:
-        keep_alive["score"] = pin(batch.score)
-        fields["score"] = keep_alive["score"].numpy()
-    if narrow_bits in (8, 16):
-        keep_alive["bg16"] = pin(batch.bg_narrow(narrow_bits))
-        batch._bg_narrow = None
-        bg16 = keep_alive["bg16"].numpy()
-        fields["bg"] = batch.bg
-    else:
-        keep_alive["bg"] = pin(batch.bg)
-        fields["bg"] = keep_alive["bg"].numpy()
-    for k in ("qstart", "qend", "sstart", "send"):
-        fields[k] = getattr(batch, k)            # SoA coordinates are ignored when `coords` is set
-    hb = type(batch)(**fields, kde_factor=batch.kde_factor, names=None)
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": ms_step, "roofline": roofline, "e2e": None,
+                              "gpu_launches": int(launches), "clocks": clocks, "note": "--no-e2e profiling run"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        eng.close()
+        return
+    t0 = time.perf_counter()
+    hb = HostBatch.from_columnar(batch, threads=procs, pinned=True,
+                                 score_bits=args.e2e_score_bits or None)
+    pack_ms = (time.perf_counter() - t0) * 1e3
     if with_kde:
         hb.ensure_kde_factor()
-    hstruct = eng.host_struct(hb, with_kde, coords=keep_alive["coords"].numpy(), narrow=narrow, bg16=bg16)
-    h2d = sum(int(keep_alive[k].numpy().nbytes) for k in keep_alive if k != "coords")
+    hstruct = eng.hostbatch_struct(hb, with_kde)
+    h2d = hb.h2d_bytes()
 
-    def step_e2e():
-        eng.run(hstruct, params)
-        res = eng.fetch(survivors=False, pinned=True)   # per-lncRNA thr/status/best + per-alignment chains
-        return res
+    def time_e2e(engines, structs, steps):
+        """`steps` batches through `engines` (one host thread each, alternating batches): wall seconds, last results."""
+        results, errors = [None] * len(engines), []
 
-    step_e2e()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = step_e2e()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+        def worker(i):
+            try:
+                for _ in range(steps // len(engines)):
+                    engines[i].run(structs[i], params)
+                    results[i] = engines[i].fetch(survivors=False, pinned=True)   # per-lncRNA thr/status/best + chains
+            except Exception as ex:
+                errors.append(f"{type(ex).__name__}: {ex}")
+
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if len(engines) == 1:
+            worker(0)
+        else:
+            ths = [threading.Thread(target=worker, args=(i,)) for i in range(len(engines))]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, results, errors
+
+    # how the retained HSPs' coordinate records reach the device: every requested mode is measured with one context,
+    # the fastest (max over ranks) is the one the headline uses
+    modes = [m for m in args.e2e_coords.split(",") if m]
+    mode_ms = {}
+    for m in modes:
+        eng.set_coords_mode(m)
+        time_e2e([eng], [hstruct], 1)                                  # warm-up: buffers of this mode
+        dt_m, res_m, err_m = time_e2e([eng], [hstruct], e2e_steps)
+        tm = torch.tensor([dt_m / e2e_steps * 1e3 if not err_m else 1e30], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        mode_ms[m] = float(tm.item())
+    best_mode = min(mode_ms, key=mode_ms.get)
+    eng.set_coords_mode(best_mode)
+    time_e2e([eng], [hstruct], 1)
+    dt, results, errors = time_e2e([eng], [hstruct], e2e_steps)
+    if errors:
+        raise RuntimeError(errors[0])
+    res = results[0]
     e2e_stage_ms = eng.stage_ms()
     single_engine_ms = dt / e2e_steps * 1e3
     dual_engine_ms = None
@@ -765,45 +798,27 @@ def main():
         # include/o2a.h): every batch still crosses PCIe in full and its result is read back in full, but the link
         # no longer idles while a batch's last chunk computes and its result is downloaded.
         # Nothing in here may take a rank out of the collectives below: failures are recorded, not raised.
-        import threading
         eng2 = None
         try:
             eng2 = Engine(local_rank)
-            hstruct2 = eng2.host_struct(hb, with_kde, coords=keep_alive["coords"].numpy(), narrow=narrow, bg16=bg16)
+            eng2.set_coords_mode(best_mode)
+            hstruct2 = eng2.hostbatch_struct(hb, with_kde)
             eng2.run(hstruct2, params)
             eng2.fetch(survivors=False, pinned=True)
         except Exception as ex:                                  # e.g. out of device memory for the second workspace
             dual_engine_error = f"{type(ex).__name__}: {ex}"
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         dual_steps = 2 * ((e2e_steps + 1) // 2)
-        results, errors = [None, None], []
-
-        def worker(i, e, hs):
-            try:
-                for _ in range(dual_steps // 2):
-                    e.run(hs, params)
-                    results[i] = e.fetch(survivors=False, pinned=True)
-            except Exception as ex:
-                errors.append(f"{type(ex).__name__}: {ex}")
-
         dt2 = float("inf")
         if dual_engine_error is None:
-            threads = [threading.Thread(target=worker, args=(0, eng, hstruct)),
-                       threading.Thread(target=worker, args=(1, eng2, hstruct2))]
-            t0 = time.perf_counter()
-            for th in threads:
-                th.start()
-            for th in threads:
-                th.join()
-            torch.cuda.synchronize()
-            dt2 = time.perf_counter() - t0
-            if errors:
-                dual_engine_error = errors[0]
-            elif not (np.array_equal(results[0].chain_idx, results[1].chain_idx)
-                      and np.array_equal(results[0].chain_idx, res.chain_idx)):
+            dt2, results2, errors2 = time_e2e([eng, eng2], [hstruct, hstruct2], dual_steps)
+            if errors2:
+                dual_engine_error = errors2[0]
+            elif not (np.array_equal(results2[0].chain_idx, results2[1].chain_idx)
+                      and np.array_equal(results2[0].chain_idx, res.chain_idx)):
                 dual_engine_error = "the two contexts returned different chains"
+        elif world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
         dual_engine_ms = None if dual_engine_error else dt2 / dual_steps * 1e3
         # the slowest rank decides, on every rank alike (8 ranks x 2 contexts can be host-bound: then one context is kept)
         both = torch.tensor([single_engine_ms, dual_engine_ms if dual_engine_ms is not None else 1e30],
@@ -823,19 +838,58 @@ def main():
     d2h = int(res.thr.nbytes + res.status.nbytes + res.best_aln.nbytes + res.n_surv.nbytes + res.n_keep.nbytes
               + res.chain_len.nbytes + res.chain_orient.nbytes + res.chain_score.nbytes + res.orient_scores.nbytes
               + res.chain_off.nbytes + res.chain_idx.nbytes + res.chain_pq.nbytes + 40)
-    zero_copy = bool(eng.lib.o2a_coords_zero_copy(eng.h))
     chunks = int(eng.lib.o2a_pipeline_chunks(eng.h))
-    if zero_copy:
+    n_ret = int(res.n_keep.sum())
+    if best_mode == "zerocopy":
         # coordinates stay in pinned host memory; only the retained HSPs are read over PCIe (one 32 B sector each)
-        h2d = int(h2d + 32 * int(res.n_keep.sum()))
+        h2d_total = int(h2d + 32 * n_ret)
+    elif best_mode == "gather":
+        # the GPU writes the retained HSPs' indices to host memory (8 B each, counted as D2H), the host sends back
+        # their 16-byte records
+        h2d_total, d2h = int(h2d + 16 * n_ret), int(d2h + 8 * n_ret)
     else:
-        h2d = int(h2d + keep_alive["coords"].numpy().nbytes)
-    e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "coords_zero_copy": zero_copy,
-           "score_layout": LAYOUTS[narrow_bits],
+        h2d_total = int(h2d + hb.coords.nbytes)
+    e2e = {"value": hsps_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "host_layout": "hostbatch.HostBatch = what ingest.load_files returns (pinned; native encoder o2a_ingest_pack_narrow)",
+           "score_layout": LAYOUTS[hb.score_bits], "bg_bits": hb.bg_bits, "pinned": bool(hb.pinned), "pack_ms": pack_ms,
+           "coords_mode": best_mode, "coords_mode_ms_single_engine": mode_ms, "coords_zero_copy": best_mode == "zerocopy",
            "pipelined_chunks": chunks, "engines_per_gpu": args.e2e_engines, "single_engine_ms_per_step": single_engine_ms,
            "dual_engine_ms_per_step": dual_engine_ms, "dual_engine_error": dual_engine_error,
            ("stage_ms_last_step" if chunks <= 1 else "stage_ms_last_chunk"): e2e_stage_ms}
+
+    # second end-to-end figure: the reference's own dtypes in host memory (float64 scores, int32 background, AoS
+    # int32 coordinates, all pinned) through the same call, one context
+    if args.e2e_f64 and world == 1:
+        del hstruct
+        hb.close()
+
+        def pin(arr):
+            tp = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
+            tp.numpy()[...] = arr
+            return tp
+        keep_alive = {k: pin(getattr(batch, k)) for k in ("bg_off", "aln_off", "hsp_off", "qlen", "slen", "bg", "score")}
+        keep_alive["coords"] = pin(batch.coords4())
+        batch._coords4 = None
+        fields = {k: keep_alive[k].numpy() for k in ("bg_off", "aln_off", "hsp_off", "qlen", "slen", "bg", "score")}
+        for k in ("qstart", "qend", "sstart", "send"):
+            fields[k] = getattr(batch, k)            # SoA coordinates are ignored when `coords` is set
+        fb = type(batch)(**fields, kde_factor=batch.kde_factor, names=None)
+        fstruct = eng.host_struct(fb, with_kde, coords=keep_alive["coords"].numpy())
+        eng.set_coords_mode(best_mode)
+        time_e2e([eng], [fstruct], 1)
+        f_steps = max(2, min(e2e_steps, 3))
+        dt_f, res_f, err_f = time_e2e([eng], [fstruct], f_steps)
+        tf = torch.tensor([dt_f / f_steps if not err_f else 1e30], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        f_h2d = sum(int(keep_alive[k].numpy().nbytes) for k in keep_alive if k != "coords") + 16 * n_ret
+        e2e["float64_host_input"] = {
+            "value": hsps_all / float(tf.item()), "unit": UNIT, "ms_per_step": float(tf.item()) * 1e3, "steps": f_steps,
+            "h2d_bytes_per_step": int(f_h2d), "engines_per_gpu": 1, "coords_mode": best_mode,
+            "score_layout": LAYOUTS[0], "error": err_f[0] if err_f else None,
+            "same_chains": bool(res_f[0] is not None and np.array_equal(res_f[0].chain_idx, res.chain_idx))}
+        del fstruct, keep_alive
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

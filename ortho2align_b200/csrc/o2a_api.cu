@@ -109,7 +109,7 @@ struct o2a_ctx {
     // owned copies of host inputs
     DevBuf in_bg_off, in_bg, in_kde, in_aln_off, in_hsp_off, in_qlen, in_slen, in_qs, in_qe, in_ss, in_se, in_score;
     // workspace
-    DevBuf aln_lnc, thr_aln, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
+    DevBuf aln_lnc, thr, fits, tbl_k, tbl_cum, status, uv_val, uv_cnt, uv_n;
     DevBuf n_surv, n_keep, surv_idx, surv_x, surv_p, surv_pq, surv_keep;
     DevBuf in_score_q, in_exc_off, in_exc_pos, in_exc_val;
     DevBuf chain_len, chain_orient, chain_score, orient_scores, chain_slot, best_key, best_aln;
@@ -123,6 +123,7 @@ struct o2a_ctx {
     DevBuf maxchk;                                   // device-side check of the caller's max_aln_hsps / max_lnc_bg
     // coordinates of a host batch: how the retained HSPs' records reach the chaining kernels
     int coords_mode_req = O2A_COORDS_AUTO, coords_mode_used = O2A_COORDS_AUTO;
+    bool coords_on_device = false;                   // the coordinate records are in device memory: k_front reads them itself
     cudaStream_t tail_stream = nullptr;              // host-gather mode: scatter + chaining of chunk c beside the front of chunk c+1
     cudaEvent_t front_ev[16] = {};
     cudaEvent_t tail_join = nullptr;
@@ -132,7 +133,7 @@ struct o2a_ctx {
     long long* h_cursor = nullptr;                          // pinned [16]: retained HSPs listed per chunk
     int gather_threads = 0;
     HostPool* pool = nullptr;
-    DevBuf fit_cnt, fc_val, fc_cnt, fc_n, fit_list, fit_list_n;
+    DevBuf fit_cnt, fc_val, fc_cnt, fc_n, fit_list, fit_list_n, fit_list2, fit_list2_n, fit_scratch;
     bool coords_zero_copy = false;   // qstart..send read in place from pinned, device-mapped host memory
     // chunk view [vl0, vl1) lncRNAs / [va0, va1) alignments the stage launchers work on (whole batch by default)
     long long vl0 = 0, vl1 = 0, va0 = 0, va1 = 0;
@@ -357,7 +358,7 @@ static void free_all(o2a_ctx* ctx)
 {
     DevBuf* bufs[] = {&ctx->in_bg_off, &ctx->in_bg, &ctx->in_kde, &ctx->in_aln_off, &ctx->in_hsp_off, &ctx->in_qlen,
                       &ctx->in_slen, &ctx->in_qs, &ctx->in_qe, &ctx->in_ss, &ctx->in_se, &ctx->in_score,
-                      &ctx->aln_lnc, &ctx->thr_aln, &ctx->thr, &ctx->fits, &ctx->tbl_k, &ctx->tbl_cum, &ctx->status, &ctx->uv_val,
+                      &ctx->aln_lnc, &ctx->thr, &ctx->fits, &ctx->tbl_k, &ctx->tbl_cum, &ctx->status, &ctx->uv_val,
                       &ctx->uv_cnt, &ctx->uv_n, &ctx->n_surv, &ctx->n_keep, &ctx->surv_idx, &ctx->surv_x, &ctx->in_score_q,
                       &ctx->in_exc_off, &ctx->in_exc_pos, &ctx->in_exc_val, &ctx->surv_p,
                       &ctx->surv_pq, &ctx->surv_keep, &ctx->chain_len, &ctx->chain_orient, &ctx->chain_score,
@@ -365,7 +366,7 @@ static void free_all(o2a_ctx* ctx)
                       &ctx->ret_score, &ctx->ret_slot, &ctx->in_coords, &ctx->big_list,
                       &ctx->mid_list, &ctx->big_count, &ctx->counters, &ctx->pq_list, &ctx->cbig_list, &ctx->stage_cnt,
                       &ctx->csort_k0, &ctx->csort_k1, &ctx->csort_v0, &ctx->csort_v1, &ctx->maxchk, &ctx->ret_base,
-                      &ctx->list_cursor, &ctx->d_stage, &ctx->fit_cnt, &ctx->fc_val, &ctx->fc_cnt, &ctx->fc_n, &ctx->fit_list,
+                      &ctx->list_cursor, &ctx->d_stage, &ctx->fit_list2, &ctx->fit_list2_n, &ctx->fit_scratch, &ctx->fit_cnt, &ctx->fc_val, &ctx->fc_cnt, &ctx->fc_n, &ctx->fit_list,
                       &ctx->fit_list_n, &ctx->sort_k0, &ctx->sort_k1, &ctx->sort_v0, &ctx->sort_v1, &ctx->cb_qs,
                       &ctx->cb_qe, &ctx->cb_ss, &ctx->cb_se, &ctx->cb_sc, &ctx->cb_id, &ctx->cb_total, &ctx->cb_prev,
                       &ctx->cb_f, &ctx->cb_chain, &ctx->off_a, &ctx->off_b, &ctx->out_i32, &ctx->out_f64a,
@@ -499,11 +500,9 @@ static int run_fit(o2a_ctx* ctx)
     const o2a_params& p = ctx->prm;
     ENS(thr, b.n_lnc * sizeof(double));
     ENS(status, b.n_lnc * sizeof(int));
-    ENS(thr_aln, b.n_aln * sizeof(double));
     const long long l0 = ctx->vl0, nl = ctx->vl1 - ctx->vl0;
     if (nl <= 0) return 0;
     FitArgs A{};
-    A.aln_off = (const long long*)b.aln_off + l0; A.thr_aln = P<double>(ctx->thr_aln);
     A.n_lnc = nl; A.bg_off = (const long long*)b.bg_off + l0; A.bg = b.bg;
     A.kde_factor = b.kde_factor ? b.kde_factor + l0 : nullptr;
     A.fitter = p.fitter; A.alpha = p.alpha;
@@ -543,10 +542,28 @@ static int run_fit(o2a_ctx* ctx)
         k_fit_hist_tail<<<grid_for(ctx, (nl + FITW_WARPS - 1) / FITW_WARPS, 8), FITW_WARPS * 32, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
     }
+    // what this launch cannot take without per-CTA scratch (value range beyond the counters, more distinct values
+    // than the shared staging) is listed for a second launch on a few CTAs that own sort / table scratch in HBM
+    ENS(fit_list2, (b.n_lnc + 1) * sizeof(int)); ENS(fit_list2_n, sizeof(int));
+    CU(cudaMemsetAsync(ctx->fit_list2_n.p, 0, sizeof(int), ctx->stream));
+    A.list2 = P<int>(ctx->fit_list2); A.list2_n = P<int>(ctx->fit_list2_n);
+    A.scratch = nullptr; A.scratch_stride = 0; A.scratch_cap = 0;
     if (b.bg_bits == 8) k_fit<signed char><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     else if (b.bg_bits == 16) k_fit<short><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     else k_fit<int><<<grid, FIT_THREADS, 0, ctx->stream>>>(A);
     LAUNCH_CHECK();
+    {
+        const int g2 = grid_for(ctx, nl, 1) < 32 ? grid_for(ctx, nl, 1) : 32;
+        const long long cap = b.max_lnc_bg > 0 ? b.max_lnc_bg : 1;
+        const long long stride = ((cap * FIT_SCRATCH_BYTES_PER_ENTRY + 255) / 256) * 256;
+        ENS(fit_scratch, (size_t)g2 * stride);
+        A.list = A.list2; A.list_n = A.list2_n; A.list2 = nullptr; A.list2_n = nullptr;
+        A.scratch = P<unsigned char>(ctx->fit_scratch); A.scratch_stride = stride; A.scratch_cap = cap;
+        if (b.bg_bits == 8) k_fit<signed char><<<g2, FIT_THREADS, 0, ctx->stream>>>(A);
+        else if (b.bg_bits == 16) k_fit<short><<<g2, FIT_THREADS, 0, ctx->stream>>>(A);
+        else k_fit<int><<<g2, FIT_THREADS, 0, ctx->stream>>>(A);
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -560,6 +577,8 @@ static int ensure_sort_scratch(o2a_ctx* ctx, int grid, long long cap)
 // per-chunk counters inside stage_cnt (see o2a_ctx)
 enum { CNT_PQ = 0, CNT_RANKBIG = 1, CNT_MID = 2, CNT_CBIG = 3, CNT_PER_CHUNK = 4 };
 static int* chunk_cnt(o2a_ctx* ctx, int chunk, int which) { return P<int>(ctx->stage_cnt) + chunk * CNT_PER_CHUNK + which; }
+
+static void fill_chain_args(o2a_ctx* ctx, int chunk, ChainArgs& A);
 
 // Front of the path for the view's alignments, on stream `st`: score filter + p / q / keep (k_front: one warp per
 // alignment), then the alignments it queued (k_pq, k_rank_big).
@@ -588,11 +607,22 @@ static int run_score(o2a_ctx* ctx, int chunk, cudaStream_t st)
     F.exc_pos = b.exc_pos; F.exc_val = b.exc_val; F.n_hsp_total = b.n_hsp;
     F.n_surv = P<int>(ctx->n_surv) + a0; F.surv_idx = P<int>(ctx->surv_idx); F.surv_x = P<double>(ctx->surv_x);
     F.pq_list = P<int>(ctx->pq_list) + a0; F.pq_count = chunk_cnt(ctx, chunk, CNT_PQ);
+    {
+        ChainArgs C{};
+        fill_chain_args(ctx, chunk, C);
+        F.ret_slot = C.ret_slot; F.ret_score = C.ret_score; F.ret_coord = C.ret_coord;
+        F.fetch_coords = ctx->coords_on_device ? 1 : 0;
+        F.coords4 = C.coords4; F.qstart = C.qstart; F.qend = C.qend; F.sstart = C.sstart; F.send = C.send;
+        F.qlen = C.qlen; F.slen = C.slen; F.mid_list = C.mid_list; F.mid_count = C.mid_count;
+    }
     const int grid = grid_for(ctx, (na + FRONT_WARPS - 1) / FRONT_WARPS, FRONT_CTAS_PER_SM);
-    if (b.score_bits == 8) k_front<signed char><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
-    else if (b.score_bits == 16) k_front<short><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
-    else if (b.score_bits == 32) k_front<int><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
-    else k_front<double><<<grid, FRONT_WARPS * 32, 0, st>>>(F);
+#define O2A_FRONT(T) do { if (p.fitter == O2A_FIT_HIST) k_front<T, 0><<<grid, FRONT_WARPS * 32, 0, st>>>(F); \
+                         else k_front<T, 1><<<grid, FRONT_WARPS * 32, 0, st>>>(F); } while (0)
+    if (b.score_bits == 8) O2A_FRONT(signed char);
+    else if (b.score_bits == 16) O2A_FRONT(short);
+    else if (b.score_bits == 32) O2A_FRONT(int);
+    else O2A_FRONT(double);
+#undef O2A_FRONT
     LAUNCH_CHECK();
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[O2A_STAGE_PQ], st));
     // what k_front queued: more than FRONT_SCAP survivors, or many non-integral scores (a small grid: the list is
@@ -633,6 +663,8 @@ static void fill_chain_args(o2a_ctx* ctx, int chunk, ChainArgs& A)
     A.lnc_status = P<int>(ctx->status);
     A.mid_list = P<int>(ctx->mid_list) + a0; A.mid_count = chunk_cnt(ctx, chunk, CNT_MID);
     A.big_list = P<int>(ctx->cbig_list) + a0; A.big_count = chunk_cnt(ctx, chunk, CNT_CBIG);
+    // what k_front left to k_pq still needs its retained list (k_retained_slots) and, on the device, its coordinates
+    A.work_list = P<int>(ctx->pq_list) + a0; A.work_count = chunk_cnt(ctx, chunk, CNT_PQ);
 }
 
 static int ensure_chain_buffers(o2a_ctx* ctx)
@@ -645,13 +677,25 @@ static int ensure_chain_buffers(o2a_ctx* ctx)
     return 0;
 }
 
-// Coordinates + score of the retained HSPs next to each other (device-resident, uploaded or zero-copy coordinates)
-static int run_gather(o2a_ctx* ctx, int chunk, cudaStream_t st)
+// What k_front left open for the chaining: the retained lists of the alignments that went through k_pq, and the
+// coordinates of the retained HSPs wherever k_front could not read them itself (`all` = every alignment: the operator
+// seam o2a_best_chain, which does not run k_front).
+static int run_gather(o2a_ctx* ctx, int chunk, cudaStream_t st, bool all = false)
 {
     const long long na = ctx->va1 - ctx->va0;
     if (na <= 0) return 0;
     ChainArgs A{};
     fill_chain_args(ctx, chunk, A);
+    if (all) { A.work_list = nullptr; A.work_count = nullptr; }
+    const int small_grid = grid_for(ctx, (na + 7) / 8, 2);
+    k_retained_slots<<<all ? grid_for(ctx, (na + 7) / 8, 8) : small_grid, 256, 0, st>>>(A);
+    LAUNCH_CHECK();
+    if (ctx->coords_mode_used == O2A_COORDS_HOST_GATHER && !all) return 0;     // the host supplies the coordinates
+    if (ctx->coords_on_device && !all) {
+        k_fetch_coords<<<small_grid, 256, 0, st>>>(A);                          // only what went through k_pq
+        LAUNCH_CHECK();
+        return 0;
+    }
     // Coordinates read in place over PCIe: the SMs' 32-byte reads and the copy engine's reads of the next chunk
     // compete for the link's read-request slots, and a machine-filling gather starves the DMA (8 CTAs per SM:
     // 13.0 ms per C2 batch, 1 per SM: 12.6 ms). A small grid keeps enough requests in flight for the gather
@@ -663,7 +707,8 @@ static int run_gather(o2a_ctx* ctx, int chunk, cudaStream_t st)
         if (const char* e = getenv("O2A_GATHER_CTAS")) { if (atoi(e) > 0) want = atoi(e); }
         if (want < gather_grid) gather_grid = want;
     }
-    k_gather_retained<<<gather_grid, 256, 0, st>>>(A);
+    A.work_list = nullptr; A.work_count = nullptr;
+    k_fetch_coords<<<gather_grid, 256, 0, st>>>(A);
     LAUNCH_CHECK();
     return 0;
 }
@@ -907,6 +952,7 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         if (b.n_lnc > 0) { k_max_diff<<<grid_for(ctx, (b.n_lnc + 255) / 256, 4), 256, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.bg_off, P<unsigned long long>(ctx->maxchk) + 1); LAUNCH_CHECK(); }
     }
     ctx->coords_mode_used = coords_mode;
+    ctx->coords_on_device = batch->mem != O2A_MEM_HOST || coords_mode == O2A_COORDS_UPLOAD;
     ENS(aln_lnc, b.n_aln * sizeof(int));
     if (b.n_lnc > 0) {
         k_fill_aln_lnc<<<grid_for(ctx, b.n_lnc, 16), 64, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->aln_lnc));
@@ -1000,6 +1046,7 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
             if ((r = run_score(ctx, c, ctx->stream))) return r;
             if ((r = stage_event(ctx, O2A_STAGE_GATHER))) return r;
             const long long na = ctx->va1 - ctx->va0;
+            if ((r = run_gather(ctx, c, ctx->stream))) return r;      // retained lists of what went through k_pq
             if (na > 0) {
                 ChainArgs A{};
                 fill_chain_args(ctx, c, A);
@@ -1024,7 +1071,10 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
                 if (R <= cap_of[c]) {
                     const long long* list = ctx->h_list + base_of[c];
                     int4* stage = ctx->h_stage + base_of[c];
-                    if (h_coords) pool.run(R, [=](long long k) { stage[k] = h_coords[list[k]]; });
+                    if (h_coords) pool.run(R, [=](long long k) {
+                        if (k + 8 < R) __builtin_prefetch(h_coords + list[k + 8]);     // random 16-byte records of a multi-GB array
+                        stage[k] = h_coords[list[k]];
+                    });
                     else {
                         const int32_t *qs = batch->qstart, *qe = batch->qend, *ss = batch->sstart, *se = batch->send;
                         pool.run(R, [=](long long k) {
@@ -1054,8 +1104,8 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
                             CU(cudaMemcpyAsync(d_c + h, stage, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->tail_stream));
                         }
                     }
-                    A.coords4 = d_c;
-                    k_fill_coords<<<grid_for(ctx, (na + 7) / 8, 8), 256, 0, ctx->tail_stream>>>(A);
+                    A.coords4 = d_c; A.work_list = nullptr; A.work_count = nullptr;
+                    k_fetch_coords<<<grid_for(ctx, (na + 7) / 8, 8), 256, 0, ctx->tail_stream>>>(A);
                     LAUNCH_CHECK();
                 }
             }
@@ -1277,8 +1327,8 @@ extern "C" int o2a_best_chain(o2a_ctx* ctx, int64_t n, const int32_t* qstart, co
     bool timing = ctx->timing;
     ctx->timing = false;
     ctx->vl0 = 0; ctx->vl1 = 1; ctx->va0 = 0; ctx->va1 = 1;
-    ctx->coords_zero_copy = false; ctx->pipelined_chunks = 1;
-    r = run_gather(ctx, 0, ctx->stream);
+    ctx->coords_zero_copy = false; ctx->pipelined_chunks = 1; ctx->coords_on_device = true; ctx->coords_mode_used = O2A_COORDS_AUTO;
+    r = run_gather(ctx, 0, ctx->stream, true);
     if (!r) r = run_chain(ctx, 0, ctx->stream);
     ctx->timing = timing;
     if (r) return r;

@@ -18,7 +18,7 @@
 namespace o2a {
 
 constexpr int CHAIN_THREADS = 128;
-constexpr int CHAIN_WARP_MAX = 32;        // retained HSPs per alignment handled by ONE warp
+constexpr int CHAIN_WARP_MAX = 30;        // retained HSPs per alignment handled by ONE warp (one graph + 2 sentinels <= 32 lanes)
 constexpr int CHAIN_SMALL_MAX = 192;      // retained HSPs per alignment handled by a CTA in shared memory
 constexpr int CHAINBIG_THREADS = 512;
 
@@ -153,6 +153,8 @@ struct ChainArgs {
     int* chain_slot;           // slot layout: positions in the retained list of the chain HSPs, chain order
     double* best_key;          // per alignment: get_best_orthologs key of the chosen chain
     int* lnc_status;
+    // k_retained_slots / k_fetch_coords: the alignments of work_list[0..*work_count) only (nullptr: all)
+    const int* work_list; const int* work_count;
     int* mid_list; int* mid_count;     // alignments with > CHAIN_WARP_MAX retained HSPs (-> k_chain_small)
     int* big_list; int* big_count;     // alignments with > CHAIN_SMALL_MAX retained HSPs (-> k_chain_big)
 };
@@ -174,56 +176,66 @@ __device__ double best_key_of_chain(const ChainArgs& A, long long h0, const int*
     return wsum;
 }
 
-// Gather stage: one warp per alignment compacts the retained HSPs (keep flags of k_pq) in list order
-// and copies their coordinates + score next to each other. This is the only place that touches the
-// coordinate arrays — ~1 % of the HSPs — and, for host batches in pinned memory, the only traffic
-// they ever cause over PCIe (zero-copy reads straight from the caller's arrays).
+// Alignments the warp path of the chaining cannot take: too many retained HSPs, or sentinels beyond 32 bits
+__device__ __forceinline__ bool chain_needs_cta(int r, long long qlen, long long slen)
+{
+    return r > CHAIN_WARP_MAX || qlen > 0x7fffffffll || slen > 0x7fffffffll || qlen < 0 || slen < 0;
+}
+
+// Gather stage. The retained HSPs of alignment a (list order) live in the slot [hsp_off[a], hsp_off[a] + n_keep[a]) of
+//   ret_slot (position in the survivor list), ret_score, ret_coord (qstart, qend, sstart, send).
+// k_front fills ret_slot / ret_score (and ret_coord when the coordinate records are in device memory) for the alignments
+// it finished itself; what is left:
+//   k_retained_slots  ret_slot / ret_score + queueing for k_chain_small, from the keep flags, for the alignments of
+//                     work_list (those that went through k_pq) or for all (work_list == nullptr)
+//   k_fetch_coords    ret_coord from device-readable coordinate records — device memory, or pinned host memory read in
+//                     place over PCIe (zero-copy: the only traffic the coordinate arrays ever cause, ~1 % of the HSPs)
+//   k_list_retained / k_scatter_coords   the host-gather mode (see below)
 __global__ void __launch_bounds__(256)
-k_gather_retained(ChainArgs A)
+k_retained_slots(ChainArgs A)
 {
     const int lane = lane_id();
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long a = warp; a < A.n_aln; a += nwarps) {
+    const long long n_items = A.work_list ? (long long)*A.work_count : A.n_aln;
+    for (long long it = warp; it < n_items; it += nwarps) {
+        const long long a = A.work_list ? (long long)A.work_list[it] : it;
         const int r = A.n_keep[a];
         if (r == 0) continue;
-        // alignments too large for the warp path are queued here, so that k_chain_small can run beside k_chain_warp
-        if (r > CHAIN_WARP_MAX && lane == 0) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
+        if (lane == 0 && chain_needs_cta(r, A.qlen[a], A.slen[a])) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
         const long long h0 = A.hsp_off[a];
         const int ns = A.n_surv[a];
         int got = 0;
-        // up to 128 survivors per round; each dependent level (keep flags -> survivor index -> coordinates / score)
-        // is issued for all four rows before the next level uses it
-        for (int k0 = 0; k0 < ns && got < r; k0 += 128) {
-            bool keep[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = k0 + u * 32 + lane;
-                keep[u] = (k < ns) && A.surv_keep[h0 + k];
+        for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
+            const int k = k0 + lane;
+            const bool keep = (k < ns) && A.surv_keep[h0 + k];
+            const unsigned b = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+                const long long pos = h0 + got + __popc(b & lanemask_lt());
+                A.ret_slot[pos] = k; A.ret_score[pos] = A.surv_x[h0 + k];
             }
-            long long pos[4], h[4];
-            double x[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = k0 + u * 32 + lane;
-                const unsigned b = __ballot_sync(FULL_MASK, keep[u]);
-                pos[u] = h0 + got + __popc(b & lanemask_lt());
-                got += __popc(b);
-                h[u] = keep[u] ? h0 + A.surv_idx[h0 + k] : 0;
-                x[u] = keep[u] ? A.surv_x[h0 + k] : 0.0;
-            }
-            int4 c[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (keep[u]) {
-                    if (A.coords4) c[u] = A.coords4[h[u]];
-                    else { c[u].x = A.qstart[h[u]]; c[u].y = A.qend[h[u]]; c[u].z = A.sstart[h[u]]; c[u].w = A.send[h[u]]; }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (keep[u]) { A.ret_coord[pos[u]] = c[u]; A.ret_score[pos[u]] = x[u]; A.ret_slot[pos[u]] = k0 + u * 32 + lane; }
-            }
+            got += __popc(b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fetch_coords(ChainArgs A)
+{
+    const int lane = lane_id();
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n_items = A.work_list ? (long long)*A.work_count : A.n_aln;
+    for (long long it = warp; it < n_items; it += nwarps) {
+        const long long a = A.work_list ? (long long)A.work_list[it] : it;
+        const int r = A.n_keep[a];
+        const long long h0 = A.hsp_off[a];
+        for (int i = lane; i < r; i += 32) {
+            const long long h = h0 + A.surv_idx[h0 + A.ret_slot[h0 + i]];
+            int4 c;
+            if (A.coords4) c = A.coords4[h];
+            else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
+            A.ret_coord[h0 + i] = c;
         }
     }
 }
@@ -232,8 +244,7 @@ k_gather_retained(ChainArgs A)
 // records in place over PCIe (32-byte reads that compete with the upload DMA for the link's read-request slots), the
 // GPU lists the global HSP indices of the retained HSPs straight into mapped pinned host memory (posted writes), the
 // host gathers the 16-byte records with its own threads and sends them back as one small DMA, and k_scatter_coords
-// puts them where the chaining kernels expect them. Everything else k_gather_retained does (score, survivor slot,
-// queueing the alignments beyond the warp path) happens here.
+// puts them where the chaining kernels expect them.
 __global__ void __launch_bounds__(256)
 k_list_retained(ChainArgs A, long long* __restrict__ ret_base, long long* __restrict__ cursor,
                 long long* __restrict__ host_list, long long cap)
@@ -244,24 +255,12 @@ k_list_retained(ChainArgs A, long long* __restrict__ ret_base, long long* __rest
     for (long long a = warp; a < A.n_aln; a += nwarps) {
         const int r = A.n_keep[a];
         if (r == 0) continue;
-        if (r > CHAIN_WARP_MAX && lane == 0) { int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
         long long base = 0;
         if (lane == 0) { base = (long long)atomicAdd((unsigned long long*)cursor, (unsigned long long)r); ret_base[a] = base; }
         base = __shfl_sync(FULL_MASK, base, 0);
         const long long h0 = A.hsp_off[a];
-        const int ns = A.n_surv[a];
-        int got = 0;
-        for (int k0 = 0; k0 < ns && got < r; k0 += 32) {
-            const int k = k0 + lane;
-            const bool keep = (k < ns) && A.surv_keep[h0 + k];
-            const unsigned b = __ballot_sync(FULL_MASK, keep);
-            if (keep) {
-                const int pos = got + __popc(b & lanemask_lt());
-                A.ret_score[h0 + pos] = A.surv_x[h0 + k]; A.ret_slot[h0 + pos] = k;
-                if (base + pos < cap) host_list[base + pos] = h0 + A.surv_idx[h0 + k];
-            }
-            got += __popc(b);
-        }
+        for (int i = lane; i < r; i += 32)
+            if (base + i < cap) host_list[base + i] = h0 + A.surv_idx[h0 + A.ret_slot[h0 + i]];
     }
 }
 
@@ -279,191 +278,215 @@ k_scatter_coords(ChainArgs A, const long long* __restrict__ ret_base, const int4
     }
 }
 
-// ret_coord of the retained HSPs from device-resident AoS coordinate records (ret_slot already filled by
-// k_list_retained): the dense-chunk fallback of the host-gather mode.
-__global__ void __launch_bounds__(256)
-k_fill_coords(ChainArgs A)
+// Warp path: one warp per alignment with at most CHAIN_WARP_MAX retained HSPs (the common case: ~10-20 retained of
+// ~130 survivors), entirely in REGISTERS: every vertex of an orientation graph — begin sentinel, HSPs in
+// (qstart, sstart, list order), end sentinel — is one lane; a vertex's data is broadcast with shuffles when it is its
+// turn. The two graphs are independent (alignment.py:1015-1030): when both fit the warp together (n_direct + n_reverse +
+// 4 sentinels <= 32) the direct graph takes lanes [0, N0), the reverse graph [N0, N0 + N1) and they advance in the
+// same instructions (at step s every lane looks at vertex s of ITS graph); otherwise they are chained one after the other.
+//   pass 1  successor masks M_i = {j > i : precede(i, j)} by ballot; f(i) = lowest bit; edges of i = M_i below f(f(i))
+//   pass 2  push DP in vertex order: the lanes in the edge mask relax themselves (distinct targets, strict '>')
+//   result  chain = vertices on the prev-path from the end sentinel; ascending vertex index IS chain order
+// Coordinates and sentinels are 32-bit here: alignments whose qlen / slen do not fit (or with negative coordinates) are
+// queued for k_chain_small like the ones with too many retained HSPs (chain_needs_cta).
+// (Round 1 kept the graphs in shared memory as 64-bit arrays: 2.6 k warp instructions per alignment.)
+constexpr int CHAINW_WARPS = 4;
+constexpr int CHAINW_SMEM = 128;          // bytes of shared memory per warp: inverse permutation, two staged chains, flags
+
+struct WarpChainResult { int pick; int len; double sco0, sco1; double key; bool bad; };
+
+// Neumaier-compensated running sum, the float branch of CPython >= 3.12's sum() (Python/bltinmodule.c)
+__device__ __forceinline__ void neumaier_add(double& f_result, double& c, double x)
 {
-    const int lane = lane_id();
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long a = warp; a < A.n_aln; a += nwarps) {
-        const int r = A.n_keep[a];
-        const long long h0 = A.hsp_off[a];
-        for (int i = lane; i < r; i += 32) A.ret_coord[h0 + i] = A.coords4[h0 + A.surv_idx[h0 + A.ret_slot[h0 + i]]];
-    }
+    const double t = __dadd_rn(f_result, x);
+    if (fabs(f_result) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dsub_rn(f_result, t), x));
+    else c = __dadd_rn(c, __dadd_rn(__dsub_rn(x, t), f_result));
+    f_result = t;
 }
 
-// Warp path: one warp per alignment with at most CHAIN_WARP_MAX retained HSPs (the common case:
-// ~10-20 retained of ~130 survivors). Everything lives in the warp's slice of shared memory; the
-// begin/end sentinels are stored as ordinary vertices (64-bit coordinates). The two orientations are
-// independent graphs (alignment.py:1015-1030) and are chained AT THE SAME TIME: their vertices sit in
-// consecutive index ranges [0, N0) and [N0, N0 + N1), lanes 0-15 push the window of the direct
-// graph's vertex `step` while lanes 16-31 push the reverse graph's, so the serial part of the DP is
-// max(N0, N1) steps instead of N0 + N1.
-constexpr int CHAINW_WARPS = 4;
+// All 32 lanes call this. Lane p < r holds the p-th retained HSP (list order); r <= CHAIN_WARP_MAX and qlen, slen fit
+// int32. `sm`: CHAINW_SMEM bytes of shared memory owned by the warp. The chosen chain (retained-list positions, chain
+// order) goes to chain_out[0..len).
+//
+// Inside, the subject coordinates of the REVERSE graph are stored bit-complemented (~x = -x - 1 reverses the order and
+// cannot overflow): `a.send > b.sstart` becomes `~a.send < ~b.sstart` and `a.send - b.sstart` becomes
+// `~b.sstart - ~a.send`, so both graphs run the direct graph's formulas
+//     precede(i, j) = qend_i < qstart_j and send_i < sstart_j            (alignment.py:137-168)
+//     distance      = (qstart_j - qend_i) + (sstart_j - send_i)          (alignment.py:170-217)
+// and a step of either pass is the same dozen instructions for every lane. The integer distance is evaluated as
+// (qstart_j + sstart_j) - (qend_i + send_i) — exact in 64 bits, hence the same double as the reference's.
+__device__ __forceinline__ WarpChainResult warp_chain(int r, int qs, int qe, int ss, int se, double sc, int qlen, int slen,
+                                                      double G, double E, int best_value, unsigned char* sm,
+                                                      int* __restrict__ chain_out)
+{
+    const int lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
+    const double POS_INF = __longlong_as_double(0x7ff0000000000000ll);
+    unsigned char* inv = sm;                                      // vertex lane -> retained-list position
+    WarpChainResult R; R.pick = 1; R.len = 0; R.sco0 = R.sco1 = NEG_INF; R.key = 0.0; R.bad = false;
+    const bool mine = lane < r;
+    const bool dir = mine && (se - ss > 0);                       // alignment.py:107-110
+    // orientation None: the reference raises in _split_orientations
+    if (__any_sync(FULL_MASK, mine && !(qe - qs > 0))) { R.bad = true; return R; }
+    const unsigned mem_d = __ballot_sync(FULL_MASK, dir), mem_r = __ballot_sync(FULL_MASK, mine && !dir);
+    const int n0 = __popc(mem_d), n1 = __popc(mem_r);
+    // stable rank by (qstart, sstart, list order) among the HSPs of the own orientation:
+    //   #{peers with a smaller key} + #{earlier peers with the same key}
+    const unsigned peers = dir ? mem_d : mem_r;
+    const unsigned long long key = ((unsigned long long)((unsigned)qs ^ 0x80000000u) << 32) | (unsigned long long)((unsigned)ss ^ 0x80000000u);
+    int rank = __popc(__match_any_sync(FULL_MASK, key) & peers & lt);
+#pragma unroll 1
+    for (int q = 0; q < r; ++q) {
+        const unsigned long long ok = __shfl_sync(FULL_MASK, key, q);
+        if (((peers >> q) & 1u) && ok < key) ++rank;
+    }
+    const bool together = (n0 ? n0 + 2 : 0) + (n1 ? n1 + 2 : 0) <= 32;
+    int len_d = 0, len_r = 0;
+    sm[96 + lane] = 0;                                            // flag[p]: retained HSP p is on its graph's best chain
+#pragma unroll 1
+    for (int round = 0; round < (together ? 1 : 2); ++round) {
+        const bool use_d = together || round == 0, use_r = together || round == 1;
+        const int N0 = (use_d && n0) ? n0 + 2 : 0, N1 = (use_r && n1) ? n1 + 2 : 0;     // vertices incl. sentinels
+        __syncwarp();
+        if (mine && (dir ? use_d : use_r)) inv[(dir ? 0 : N0) + 1 + rank] = (unsigned char)lane;
+        __syncwarp();
+        // ---- my vertex: lane v of graph D = [0, N0) or R = [N0, N0 + N1) ---------------------------------------------
+        const int v = lane;
+        const bool active = v < N0 + N1;
+        const bool gD = v < N0;
+        const int base = gD ? 0 : N0, Nn = gD ? N0 : N1;
+        const int me = active ? v - base : -1;                    // my index inside my graph (-1: no vertex)
+        const bool is_begin = me == 0, is_end = active && me == Nn - 1;
+        const bool is_hsp = active && !is_begin && !is_end;
+        const int src = is_hsp ? inv[v] : 0;                      // retained-list position of my HSP
+        int Qs = __shfl_sync(FULL_MASK, qs, src), Qe = __shfl_sync(FULL_MASK, qe, src);
+        int Ss = __shfl_sync(FULL_MASK, ss, src), Se = __shfl_sync(FULL_MASK, se, src);
+        double Sc = __shfl_sync(FULL_MASK, sc, src);
+        if (is_begin) { Qs = 0; Qe = 0; Ss = gD ? 0 : slen; Se = Ss; Sc = 0.0; }        // alignment.py:893-902
+        if (is_end) { Qs = qlen; Qe = qlen; Ss = gD ? slen : 0; Se = Ss; Sc = 0.0; }
+        if (!gD) { Ss = ~Ss; Se = ~Se; }                          // reverse graph: complemented subject axis
+        const long long in_sum = (long long)Qs + (long long)Ss;   // what an edge INTO me adds to the distance
+        const long long out_sum = (long long)Qe + (long long)Se;  // what an edge OUT of me subtracts
+        const unsigned below_end = (N0 + N1) >= 32 ? 0xffffffffu : ((1u << (N0 + N1)) - 1u);
+        const unsigned gmask = !active ? 0u : (gD ? ((N0 >= 32) ? 0xffffffffu : ((1u << N0) - 1u)) : (below_end & ~((1u << N0) - 1u)));
+        const int steps = max(N0, N1);
+        // ---- pass 1: successor masks M_i = {j > i : precede(i, j)} ---------------------------------------------------
+        unsigned M = 0;
+#pragma unroll 1
+        for (int s = 0; s < steps; ++s) {
+            const int i = (base + s) & 31;                        // the vertex of my graph whose turn it is
+            const int qe_i = __shfl_sync(FULL_MASK, Qe, i), se_i = __shfl_sync(FULL_MASK, Se, i);
+            const unsigned bm = __ballot_sync(FULL_MASK, me > s && qe_i < Qs && se_i < Ss);
+            if (me == s) M = bm & gmask;
+        }
+        // the begin-end pair is tested with the REVERSE rule in both graphs (both sentinels have orientation None,
+        // alignment.py:162-165): in the direct graph that is 0 > slen, never true
+        if (is_begin && gD) M &= ~(1u << (N0 - 1));
+        const int f = M ? __ffs(M) - 1 : 32;                      // first successor (32: none)
+        const int ff = __shfl_sync(FULL_MASK, f, f & 31);
+        const int g = f >= 32 ? 32 : ff;                          // f(f(i))
+        const unsigned Ed = g >= 32 ? M : (M & ((1u << g) - 1u)); // kept edges: precede(i, j) and j < f(f(i))
+        // ---- pass 2: push DP in vertex order (HSPVertex._relax, alignment.py:388-411): strict '>', first wins ----------
+        double tot = is_begin ? 0.0 : POS_INF;
+        int prev = -1;
+#pragma unroll 1
+        for (int s = 0; s + 1 < steps; ++s) {
+            const int i = (base + s) & 31;
+            const unsigned e_i = __shfl_sync(FULL_MASK, Ed, i);
+            const double t_i = __shfl_sync(FULL_MASK, tot, i);
+            const long long o_i = __shfl_sync(FULL_MASK, out_sum, i);
+            // an unreached source carries +inf and cannot improve anything; a lane outside the edge mask does not relax
+            const double nsc = __dadd_rn(t_i, __dsub_rn(__dadd_rn(G, __dmul_rn(E, (double)(in_sum - o_i))), Sc));
+            if (((e_i >> v) & 1u) && me > s && tot > nsc) { tot = nsc; prev = i; }
+        }
+        // ---- scores and backtrack (alignment.py:1007-1013) --------------------------------------------------------
+        const double t0 = __shfl_sync(FULL_MASK, tot, (N0 - 1) & 31), t1 = __shfl_sync(FULL_MASK, tot, (N0 + N1 - 1) & 31);
+        if (N0) R.sco0 = -t0;
+        if (N1) R.sco1 = -t1;
+        unsigned cm = 0;                                          // vertices on the path of MY graph (begin included)
+        {
+            int cur = active ? base + Nn - 1 : 0;
+#pragma unroll 1
+            for (int s = 0; s + 1 < steps; ++s) {
+                const int pv = __shfl_sync(FULL_MASK, prev, cur & 31);
+                if (active && pv >= 0) { cm |= 1u << pv; cur = pv; }
+            }
+        }
+        const bool on_chain = is_hsp && ((cm >> v) & 1u);
+        const unsigned cb_d = __ballot_sync(FULL_MASK, on_chain && gD), cb_r = __ballot_sync(FULL_MASK, on_chain && !gD);
+        // stage both chains (retained-list positions in chain order = ascending vertex index)
+        if (on_chain) { sm[32 + (gD ? 0 : 32) + __popc((gD ? cb_d : cb_r) & lt)] = (unsigned char)src; sm[96 + src] = 1; }
+        if (N0) len_d = __popc(cb_d);
+        if (N1) len_r = __popc(cb_r);
+    }
+    __syncwarp();
+    R.pick = (R.sco0 > R.sco1) ? 0 : 1;                           // alignment.py:1043-1046
+    R.len = R.pick ? len_r : len_d;
+    const unsigned char* staged = sm + 32 + (R.pick ? 32 : 0);
+    if (lane < R.len) chain_out[lane] = staged[lane];
+    // ---- key of get_best_orthologs on the query BED12 line of the chosen chain (pipeline.py:981-987) -----------------
+    if (R.len) {
+        const bool on_chain = mine && sm[96 + lane] != 0 && (dir ? R.pick == 0 : R.pick == 1);   // lane p holds retained HSP p
+        if (best_value == 0) {                                    // block_length: sum of abs(qend - qstart)
+            long long d = on_chain ? (long long)(qe - qs < 0 ? qs - qe : qe - qs) : 0;
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) d += __shfl_xor_sync(FULL_MASK, d, k);
+            R.key = (double)d;
+        } else if (best_value == 1) {                             // total_length: chromEnd - chromStart
+            int lo = on_chain ? min(qs, qe) : INT32_MAX, hi = on_chain ? max(qs, qe) : INT32_MIN;
+            lo = __reduce_min_sync(FULL_MASK, lo); hi = __reduce_max_sync(FULL_MASK, hi);
+            R.key = (double)((long long)hi - (long long)lo);
+        } else if (best_value == 2) R.key = (double)R.len;        // block_count
+        else {
+            // weight = float(str(sum(scores))) of the BED score column (genomicranges.py:1225): CPython >= 3.12's sum()
+            // adds ints exactly while every item is an int, then switches to Neumaier-compensated float addition
+            long long isum = 0; bool in_int = true; double fr = 0.0, cc = 0.0;
+#pragma unroll 1
+            for (int c = 0; c < R.len; ++c) {
+                const double x = __shfl_sync(FULL_MASK, sc, staged[c]);
+                if (in_int && x == (double)(long long)x && fabs(x) < 9007199254740992.0) isum += (long long)x;
+                else {
+                    if (in_int) { in_int = false; fr = (double)isum; cc = 0.0; }
+                    neumaier_add(fr, cc, x);
+                }
+            }
+            R.key = in_int ? (double)isum : (cc != 0.0 && cc == cc && fabs(cc) <= 1.79769313486231570815e308 ? __dadd_rn(fr, cc) : fr);
+        }
+    }
+    return R;
+}
 
 __global__ void __launch_bounds__(CHAINW_WARPS * 32)
 k_chain_warp(ChainArgs A)
 {
-    constexpr int C = CHAIN_WARP_MAX, V = CHAIN_WARP_MAX + 4;
-    __shared__ long long s_qs[CHAINW_WARPS][V], s_qe[CHAINW_WARPS][V], s_ss[CHAINW_WARPS][V], s_se[CHAINW_WARPS][V];
-    __shared__ double s_sc[CHAINW_WARPS][V], s_total[CHAINW_WARPS][V];
-    __shared__ int s_id[CHAINW_WARPS][V], s_prev[CHAINW_WARPS][V], s_f[CHAINW_WARPS][V];
-    __shared__ int s_chain[CHAINW_WARPS][2][C];
+    __shared__ unsigned char s_mem[CHAINW_WARPS][CHAINW_SMEM];
     const int lane = lane_id(), w = warp_id();
-    const int half = lane >> 4, hl = lane & 15;          // half 0: direct graph, half 1: reverse graph
     const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
-    const double POS_INF = __longlong_as_double(0x7ff0000000000000ll);
     const long long nwarps_total = (long long)gridDim.x * CHAINW_WARPS;
-    long long* Qs = s_qs[w]; long long* Qe = s_qe[w]; long long* Ss = s_ss[w]; long long* Se = s_se[w];
-    double* Sc = s_sc[w]; double* Tot = s_total[w]; int* Id = s_id[w]; int* Prev = s_prev[w]; int* F = s_f[w];
-
     for (long long a = (long long)blockIdx.x * CHAINW_WARPS + w; a < A.n_aln; a += nwarps_total) {
         const int r = A.n_keep[a];
         const int l = A.aln_lnc[a];
-        if (r > C) continue;                              // queued for k_chain_small by k_gather_retained
-        if (r == 0 || A.lnc_status[l] >= 2) {
-            if (lane == 0) {
-                A.chain_len[a] = 0; A.chain_orient[a] = 1; A.chain_score[a] = NEG_INF;
-                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = NEG_INF; A.best_key[a] = 0.0;
-            }
-            continue;
-        }
-        const long long h0 = A.hsp_off[a];
-        // lane p owns the p-th retained HSP (list order)
-        int qs = 0, qe = 0, ss = 0, se = 0; double sc = 0.0; bool dir = false; bool bad = false;
-        if (lane < r) {
-            const int4 c = A.ret_coord[h0 + lane];
-            qs = c.x; qe = c.y; ss = c.z; se = c.w; sc = A.ret_score[h0 + lane];
-            dir = (se - ss > 0);                         // alignment.py:107-110
-            bad = !(qe - qs > 0);                        // orientation None
-        }
-        if (__any_sync(FULL_MASK, bad)) {                // reference raises in _split_orientations
-            if (lane == 0) {
-                atomicMax(&A.lnc_status[l], 1);
-                A.chain_len[a] = 0; A.chain_orient[a] = 1; A.chain_score[a] = NEG_INF;
-                A.orient_scores[2 * a] = A.orient_scores[2 * a + 1] = NEG_INF; A.best_key[a] = 0.0;
-            }
-            continue;
-        }
         const long long qlen = A.qlen[a], slen = A.slen[a];
-        const double G = (double)A.gapopen, E = (double)A.gapextend;
-        const unsigned mem_d = __ballot_sync(FULL_MASK, lane < r && dir);
-        const unsigned mem_r = __ballot_sync(FULL_MASK, lane < r && !dir);
-        const int n0 = __popc(mem_d), n1 = __popc(mem_r);
-        const int N0 = n0 ? n0 + 2 : 0, N1 = n1 ? n1 + 2 : 0;     // vertices per graph incl. sentinels
-        // stable rank by (qstart, sstart, list order) among the HSPs of the own orientation
-        int rank = 0;
-        for (int q = 0; q < r; ++q) {
-            const int oqs = __shfl_sync(FULL_MASK, qs, q), oss = __shfl_sync(FULL_MASK, ss, q);
-            const bool same = (((mem_d >> q) & 1u) != 0) == dir;
-            rank += same && ((oqs < qs) || (oqs == qs && (oss < ss || (oss == ss && q < lane))));
-        }
-        __syncwarp();
-        if (lane < r) {
-            const int v = (dir ? 0 : N0) + rank + 1;
-            Qs[v] = qs; Qe[v] = qe; Ss[v] = ss; Se[v] = se; Sc[v] = sc; Id[v] = lane;
-        }
-        if (hl == 0) {           // sentinels (alignment.py:893-902): lane 0 for the direct graph, lane 16 for the reverse one
-            const int Nn = half ? N1 : N0, base = half ? N0 : 0;
-            if (Nn) {
-                const bool d = half == 0;
-                Qs[base] = 0; Qe[base] = 0; Ss[base] = d ? 0 : slen; Se[base] = Ss[base]; Sc[base] = 0.0;
-                const int e = base + Nn - 1;
-                Qs[e] = qlen; Qe[e] = qlen; Ss[e] = d ? slen : 0; Se[e] = Ss[e]; Sc[e] = 0.0;
+        if (r > 0 && chain_needs_cta(r, qlen, slen)) continue;    // queued for k_chain_small by the gather
+        WarpChainResult R; R.pick = 1; R.len = 0; R.sco0 = R.sco1 = NEG_INF; R.key = 0.0; R.bad = false;
+        const long long h0 = A.hsp_off[a];
+        if (r > 0 && A.lnc_status[l] < 2) {
+            int qs = 0, qe = 0, ss = 0, se = 0; double sc = 0.0;
+            if (lane < r) {
+                const int4 c = A.ret_coord[h0 + lane];
+                qs = c.x; qe = c.y; ss = c.z; se = c.w; sc = A.ret_score[h0 + lane];
             }
+            R = warp_chain(r, qs, qe, ss, se, sc, (int)qlen, (int)slen, (double)A.gapopen, (double)A.gapextend,
+                           A.best_value, s_mem[w], A.chain_slot + h0);
         }
-        __syncwarp();
-        // HSP.precede (alignment.py:137-168) inside graph [base, end); the begin-end pair uses the reverse rule (both None)
-#define O2A_PREC(isdir, base, end, i, j) ((Qe[i] < Qs[j]) && (((isdir) && !((i) == (base) && (j) == (end) - 1)) ? (Se[i] < Ss[j]) : (Se[i] > Ss[j])))
-        // f(i): every vertex scans forward inside its own graph
-        for (int v = lane; v < N0 + N1; v += 32) {
-            const bool isd = v < N0;
-            const int base = isd ? 0 : N0, end = isd ? N0 : N0 + N1;
-            int fi = end;
-            for (int j = v + 1; j < end; ++j) if (O2A_PREC(isd, base, end, v, j)) { fi = j; break; }
-            F[v] = fi;
-            Tot[v] = v == base ? 0.0 : POS_INF;
-            Prev[v] = -1;
-        }
-        __syncwarp();
-        {
-            const bool isd = half == 0;
-            const int Nn = isd ? N0 : N1, base = isd ? 0 : N0, end = base + Nn;
-            const int steps = max(N0, N1) - 1;
-            for (int step = 0; step < steps; ++step) {
-                if (step < Nn - 1) {
-                    const int i = base + step;
-                    const double ti = Tot[i];
-                    const int fi = F[i];
-                    if (fi < end && ti < POS_INF) {
-                        const int gi = F[fi];                    // f(f(i)), `end` if none
-                        for (int j = fi + hl; j < gi; j += 16) {
-                            if (O2A_PREC(isd, base, end, i, j)) {
-                                // HSP.distance (alignment.py:170-217) + HSPVertex._relax (:388-411)
-                                const long long qd = Qs[j] - Qe[i];
-                                const long long sd = isd ? (Ss[j] - Se[i]) : (Se[i] - Ss[j]);
-                                const double wgt = __dsub_rn(__dadd_rn(G, __dmul_rn(E, (double)(qd + sd))), Sc[j]);
-                                const double nsc = __dadd_rn(ti, wgt);
-                                if (Tot[j] > nsc) { Tot[j] = nsc; Prev[j] = i; }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-#undef O2A_PREC
-        // per graph (half-warp): score, backtrack, key of get_best_orthologs
-        const bool isd = half == 0;
-        const int Nn = isd ? N0 : N1, base = isd ? 0 : N0, end = base + Nn;
-        const double sco_h = Nn ? -Tot[end - 1] : NEG_INF;
-        int ln = 0;
-        if (hl == 0 && Nn) {     // backtrack (alignment.py:1007-1013): reversed chain into F[base..]
-            int cur = end - 1;
-            while (Prev[cur] != -1) { cur = Prev[cur]; if (cur != base) F[base + ln++] = cur; }
-        }
-        ln = __shfl_sync(FULL_MASK, ln, half << 4);
-        __syncwarp();
-        double key = 0.0;
-        {
-            long long blen = 0, lo = INT64_MAX, hi = INT64_MIN;
-            for (int c = hl; c < ln; c += 16) {
-                const int v = F[base + ln - 1 - c];
-                s_chain[w][half][c] = Id[v];
-                const long long d = Qe[v] - Qs[v];
-                blen += d < 0 ? -d : d;
-                lo = min(lo, min(Qs[v], Qe[v])); hi = max(hi, max(Qs[v], Qe[v]));
-            }
-#pragma unroll
-            for (int d = 8; d > 0; d >>= 1) {        // stays inside the half-warp
-                blen += __shfl_xor_sync(FULL_MASK, blen, d);
-                const long long olo = __shfl_xor_sync(FULL_MASK, lo, d), ohi = __shfl_xor_sync(FULL_MASK, hi, d);
-                lo = olo < lo ? olo : lo; hi = ohi > hi ? ohi : hi;
-            }
-            if (A.best_value == 0) key = (double)blen;
-            else if (A.best_value == 1) key = ln ? (double)(hi - lo) : 0.0;
-            else if (A.best_value == 2) key = (double)ln;
-            else {              // weight: Python sum() left to right (genomicranges.py:1225)
-                double wsum = 0.0;
-                for (int c = ln - 1; c >= 0; --c) wsum = __dadd_rn(wsum, Sc[F[base + c]]);
-                key = wsum;
-            }
-        }
-        const double sco0 = __shfl_sync(FULL_MASK, sco_h, 0), sco1 = __shfl_sync(FULL_MASK, sco_h, 16);
-        const double key0 = __shfl_sync(FULL_MASK, key, 0), key1 = __shfl_sync(FULL_MASK, key, 16);
-        const int len0 = __shfl_sync(FULL_MASK, ln, 0), len1 = __shfl_sync(FULL_MASK, ln, 16);
-        __syncwarp();
-        const int pick = (sco0 > sco1) ? 0 : 1;          // alignment.py:1043-1046
-        const int lnp = pick ? len1 : len0;
-        for (int c = lane; c < lnp; c += 32) A.chain_slot[h0 + c] = s_chain[w][pick][c];
         if (lane == 0) {
-            A.chain_len[a] = lnp; A.chain_orient[a] = (unsigned char)pick; A.chain_score[a] = pick ? sco1 : sco0;
-            A.orient_scores[2 * a] = sco0; A.orient_scores[2 * a + 1] = sco1;
-            A.best_key[a] = lnp ? (pick ? key1 : key0) : 0.0;
+            if (R.bad) atomicMax(&A.lnc_status[l], 1);   // the reference raises in _split_orientations
+            A.chain_len[a] = R.len; A.chain_orient[a] = (unsigned char)R.pick;
+            A.chain_score[a] = R.pick ? R.sco1 : R.sco0;
+            A.orient_scores[2 * a] = R.sco0; A.orient_scores[2 * a + 1] = R.sco1;
+            A.best_key[a] = R.len ? R.key : 0.0;
         }
-        __syncwarp();
     }
 }
 

@@ -25,9 +25,6 @@ namespace o2a {
 constexpr int FIT_THREADS = 64;
 constexpr int FIT_SMEM_RANGE = 1024;    // distinct-value counters kept in shared memory up to this range
 constexpr int FIT_SMEM_NNZ = 512;       // distinct values / non-empty bins staged in shared memory
-#ifndef O2A_FIT_MATCH
-#define O2A_FIT_MATCH 0                 // 1: warp-aggregate equal values (match.any) before the shared atomic
-#endif
 
 // ndtr(z) = 0.5*erfc(-z/sqrt2): scipy.special.ndtr is cephes-derived and not bit-reproducible with
 // CUDA's erfc (<= 2.3e-16 absolute apart) — KDE parity is to tolerance.
@@ -191,21 +188,36 @@ struct FitArgs {
     int* uv_val; int* uv_cnt; int* uv_n; // kde / empirical: distinct values, slot bg_off[l]
     int* status;
     int* g_cnt; long long max_range;     // per-CTA global counters for value ranges > FIT_SMEM_RANGE
-    const long long* aln_off;            // [n_lnc+1]
-    double* thr_aln;                     // [n_aln] threshold of every alignment (+inf if the fit failed)
+    // Backgrounds beyond the counting envelope (value range > max_range, or more distinct values than the shared
+    // staging holds) need per-CTA global scratch: a launch without it (scratch == nullptr) lists them in list2 and a
+    // second, small-grid launch with scratch takes that list. np.histogram / gaussian_kde have no such limits.
+    unsigned char* scratch; long long scratch_stride; long long scratch_cap;   // bytes per CTA, entries per CTA
+    int* list2; int* list2_n;
     // hist fast path (k_fit_count + k_fit_hist_tail): fixed-capacity (value, count) slots per lncRNA;
     // lncRNAs it cannot take (wide value range, > FITW_CAP distinct values) are listed for k_fit
     int* fc_val; int* fc_cnt; int* fc_n;
     int* list; int* list_n;              // when list != nullptr, k_fit processes list[0..*list_n) only
 };
 
-// thr_aln[a] for the alignments of lncRNA l: what k_filter compares against (+inf: nothing survives,
-// the reference raised before its alignment loop)
-__device__ __forceinline__ void fit_publish_thr(const FitArgs& A, long long l, double t, int st)
+// per-CTA global scratch of the general fit kernel (entries = scratch_cap >= the largest background)
+struct FitScratch {
+    unsigned long long* k0; unsigned long long* k1; unsigned int* v0; unsigned int* v1;   // radix sort
+    int* K; int* C; double* T; double* LS; short* LD;                                     // value/bin, count, term, leaf sums
+};
+__device__ __forceinline__ FitScratch fit_scratch(const FitArgs& A)
 {
-    const double v = st == 0 ? t : __longlong_as_double(0x7ff0000000000000ll);
-    for (long long a = A.aln_off[l] + threadIdx.x; a < A.aln_off[l + 1]; a += blockDim.x) A.thr_aln[a] = v;
+    FitScratch S{};
+    if (!A.scratch) return S;
+    unsigned char* p = A.scratch + (long long)blockIdx.x * A.scratch_stride;
+    const long long n = A.scratch_cap;
+    S.k0 = (unsigned long long*)p; p += n * 8; S.k1 = (unsigned long long*)p; p += n * 8;
+    S.T = (double*)p; p += n * 8; S.LS = (double*)p; p += n * 8;
+    S.v0 = (unsigned int*)p; p += n * 4; S.v1 = (unsigned int*)p; p += n * 4;
+    S.K = (int*)p; p += n * 4; S.C = (int*)p; p += n * 4;
+    S.LD = (short*)p;
+    return S;
 }
+constexpr int FIT_SCRATCH_BYTES_PER_ENTRY = 8 * 4 + 4 * 4 + 2;
 
 // every background value packed in one 32-bit word of a 16-byte load (BG = int, short or signed char)
 #define O2A_BG_WORD(OP, w) do {                                                                                   \
@@ -215,7 +227,12 @@ __device__ __forceinline__ void fit_publish_thr(const FitArgs& A, long long l, d
                OP((int)(signed char)(((w) >> 16) & 0xff)); OP((w) >> 24); } } while (0)
 #define O2A_BG_VEC(OP, v) do { O2A_BG_WORD(OP, (v).x); O2A_BG_WORD(OP, (v).y); O2A_BG_WORD(OP, (v).z); O2A_BG_WORD(OP, (v).w); } while (0)
 
-// status 4 = value range larger than the counting scratch (max_range)
+// General fit kernel: one CTA per lncRNA, any integer background (any value range, any number of distinct values).
+//   counting   values in [0, FIT_SMEM_RANGE): shared counters during the min/max pass; range <= FIT_SMEM_RANGE:
+//              shared counters relative to min; range <= max_range: per-CTA global counters; beyond: the values are
+//              radix-sorted in per-CTA global scratch and run-length encoded
+//   tables     up to FIT_SMEM_NNZ distinct values / non-empty bins in shared memory, more in the global scratch
+// A launch without scratch lists what needs it (list2) for a second, small-grid launch that has it.
 template <typename BG>
 __global__ void __launch_bounds__(FIT_THREADS)
 k_fit(FitArgs A)
@@ -236,23 +253,20 @@ k_fit(FitArgs A)
     __shared__ short s_ostk[72];
     const int tid = threadIdx.x;
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
+    const FitScratch G = fit_scratch(A);
 
     const long long n_items = A.list ? (long long)*A.list_n : A.n_lnc;
     for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
         const long long l = A.list ? (long long)A.list[it] : it;
-        if (it != (long long)blockIdx.x) {
-            // results of the previous lncRNA are visible to the whole CTA (every path ends in a barrier)
-            const long long ip = it - gridDim.x;
-            const long long lp = A.list ? (long long)A.list[ip] : ip;
-            fit_publish_thr(A, lp, A.thr[lp], A.status[lp]);
-        }
         const long long b0 = A.bg_off[l];
         const long long n = A.bg_off[l + 1] - b0;
         const BG* x = reinterpret_cast<const BG*>(A.bg) + b0;
+        if (A.scratch && n > A.scratch_cap) continue;    // understated max_lnc_bg: the call fails on the host side
         // ---- pass over the background: min / max, and (optimistically) the multiplicities ----------
         // BLAST scores are small non-negative integers: values in [0, FIT_SMEM_RANGE) are counted
         // directly in shared memory during the same pass; anything else falls back to the general
         // two-pass path (min first, then counts relative to it).
+        __syncthreads();                                 // the previous lncRNA is done with the shared tables
         {
             int4* z = reinterpret_cast<int4*>(s_cnt);
             for (int k = tid; k < FIT_SMEM_RANGE / 4; k += FIT_THREADS) z[k] = make_int4(0, 0, 0, 0);
@@ -262,14 +276,8 @@ k_fit(FitArgs A)
         int mn = INT32_MAX, mx = INT32_MIN;
         {
             bool oor = false;
-#if O2A_FIT_MATCH
-#define O2A_FIT_ADD(v) do { int v__ = (v); mn = min(mn, v__); mx = max(mx, v__);                              \
-                if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) { unsigned pe__ = __match_any_sync(__activemask(), v__); \
-                    if ((pe__ & lanemask_lt()) == 0) atomicAdd(&s_cnt[v__], __popc(pe__)); } else oor = true; } while (0)
-#else
 #define O2A_FIT_ADD(v) do { int v__ = (v); mn = min(mn, v__); mx = max(mx, v__);                              \
                 if ((unsigned)v__ < (unsigned)FIT_SMEM_RANGE) atomicAdd(&s_cnt[v__], 1); else oor = true; } while (0)
-#endif
             // 16-byte vector loads over the aligned middle part
             long long head = ((PER - (b0 & (PER - 1))) & (PER - 1)); if (head > n) head = n;
             for (long long i = tid; i < head; i += FIT_THREADS) O2A_FIT_ADD(x[i]);
@@ -296,56 +304,83 @@ k_fit(FitArgs A)
         const bool fast = (s_oor == 0);
         const long long R = (long long)mx - (long long)mn + 1;
         const long long B = n / 2;
-        if ((!fast && R > A.max_range && R > FIT_SMEM_RANGE) || (A.fitter == 0 && B < 1)) {
-            if (tid == 0) {
-                A.thr[l] = NaN; A.status[l] = (B < 1 && A.fitter == 0) ? 3 : 4;
-                if (A.fitter == 0) { LncFit f{}; A.fits[l] = f; } else A.uv_n[l] = 0;
-            }
-            __syncthreads();
+        if (A.fitter == 0 && B < 1) {                   // np.histogram(bins=0): ValueError
+            if (tid == 0) { A.thr[l] = NaN; A.status[l] = 3; LncFit f{}; A.fits[l] = f; }
             continue;
         }
-        // cnt[k] = multiplicity of value mn + k
-        int* cnt = s_cnt + mn;
-        if (!fast) {
-            cnt = (R <= FIT_SMEM_RANGE) ? s_cnt : (A.g_cnt + (long long)blockIdx.x * A.max_range);
-            for (long long k = tid; k < R; k += FIT_THREADS) cnt[k] = 0;
-            __syncthreads();
-            for (long long i0 = 0; i0 < n; i0 += FIT_THREADS) {
-                long long i = i0 + tid;
-                bool valid = i < n;
-                unsigned m = __ballot_sync(FULL_MASK, valid);
-                if (valid) {
-                    int c = (int)x[i] - mn;
-                    unsigned peers = __match_any_sync(m, c);
-                    if ((peers & lanemask_lt()) == 0) atomicAdd(&cnt[c], __popc(peers));
-                }
-            }
-            __syncthreads();
+        const bool by_sort = !fast && R > A.max_range && R > FIT_SMEM_RANGE;
+        if (by_sort && !A.scratch) {                    // needs the sort scratch: second launch
+            if (tid == 0) { const int slot = atomicAdd(A.list2_n, 1); A.list2[slot] = (int)l; }
+            continue;
         }
-        // ---- compact to (value, count), ascending ------------------------------------------------
-        // staged in shared memory when they fit, else directly in the lncRNA's global slot
+        // ---- distinct values with multiplicities, ascending: (K, Cn), in shared memory when they fit -----------
         int* uval = A.fitter == 0 ? nullptr : A.uv_val + b0;
         int* ucnt = A.fitter == 0 ? nullptr : A.uv_cnt + b0;
         int nv = 0;
-        bool overflow = false;
-        for (long long k0 = 0; k0 < R; k0 += FIT_THREADS) {
-            long long k = k0 + tid;
-            int c = k < R ? cnt[k] : 0;
-            int tot;
-            int pos = cta_exclusive_scan(c != 0, s_scan, &tot);
-            if (c != 0) {
-                int p = nv + pos;
-                if (p < FIT_SMEM_NNZ) { s_k[p] = (int)(mn + k); s_c[p] = c; }
-                if (uval) { uval[p] = (int)(mn + k); ucnt[p] = c; }
+        if (by_sort) {
+            for (long long i = tid; i < n; i += FIT_THREADS) { G.k0[i] = (unsigned long long)((unsigned)(int)x[i] ^ 0x80000000u); G.v0[i] = 0u; }
+            __syncthreads();
+            const int where = cta_radix_sort(G.k0, G.v0, G.k1, G.v1, (int)n, s_cnt);     // s_cnt: free in this path
+            __syncthreads();
+            const unsigned long long* ks = where ? G.k1 : G.k0;
+            // run heads -> (value, first index); counts from the distance to the next head
+            for (long long i0 = 0; i0 < n; i0 += FIT_THREADS) {
+                const long long i = i0 + tid;
+                const bool headf = i < n && (i == 0 || ks[i] != ks[i - 1]);
+                int tot;
+                const int pos = cta_exclusive_scan(headf ? 1 : 0, s_scan, &tot);
+                if (headf) { G.K[nv + pos] = (int)((unsigned)ks[i] ^ 0x80000000u); G.C[nv + pos] = (int)i; }
+                nv += tot;
+                __syncthreads();
             }
-            nv += tot;
+            for (int t = tid; t < nv; t += FIT_THREADS) {
+                const int nxt = t + 1 < nv ? G.C[t + 1] : (int)n;
+                G.T[t] = (double)(nxt - G.C[t]);          // parked: C[t + 1] is still needed by the neighbour
+            }
             __syncthreads();
+            for (int t = tid; t < nv; t += FIT_THREADS) {
+                G.C[t] = (int)G.T[t];
+                if (t < FIT_SMEM_NNZ) { s_k[t] = G.K[t]; s_c[t] = G.C[t]; }
+                if (uval) { uval[t] = G.K[t]; ucnt[t] = G.C[t]; }
+            }
+            __syncthreads();
+        } else {
+            // cnt[k] = multiplicity of value mn + k
+            int* cnt = s_cnt + mn;
+            if (!fast) {
+                cnt = (R <= FIT_SMEM_RANGE) ? s_cnt : (A.g_cnt + (long long)blockIdx.x * A.max_range);
+                for (long long k = tid; k < R; k += FIT_THREADS) cnt[k] = 0;
+                __syncthreads();
+                for (long long i0 = 0; i0 < n; i0 += FIT_THREADS) {
+                    long long i = i0 + tid;
+                    bool valid = i < n;
+                    unsigned m = __ballot_sync(FULL_MASK, valid);
+                    if (valid) {
+                        int c = (int)x[i] - mn;
+                        unsigned peers = __match_any_sync(m, c);
+                        if ((peers & lanemask_lt()) == 0) atomicAdd(&cnt[c], __popc(peers));
+                    }
+                }
+                __syncthreads();
+            }
+            for (long long k0 = 0; k0 < R; k0 += FIT_THREADS) {
+                long long k = k0 + tid;
+                int c = k < R ? cnt[k] : 0;
+                int tot;
+                int pos = cta_exclusive_scan(c != 0, s_scan, &tot);
+                if (c != 0) {
+                    int p = nv + pos;
+                    if (p < FIT_SMEM_NNZ) { s_k[p] = (int)(mn + k); s_c[p] = c; }
+                    if (G.K && p < A.scratch_cap) { G.K[p] = (int)(mn + k); G.C[p] = c; }
+                    if (uval) { uval[p] = (int)(mn + k); ucnt[p] = c; }
+                }
+                nv += tot;
+                __syncthreads();
+            }
         }
-        if (nv > FIT_SMEM_NNZ) overflow = true;
-        if (A.fitter == 0 && overflow) {
-            // more distinct values than the staging area: not reachable with BLAST scores; report
-            if (tid == 0) { A.thr[l] = NaN; A.status[l] = 4; LncFit f{}; A.fits[l] = f; }
-            __syncthreads();
+        const bool overflow = nv > FIT_SMEM_NNZ;
+        if (A.fitter == 0 && overflow && !A.scratch) {  // more distinct values than the shared staging: second launch
+            if (tid == 0) { const int slot = atomicAdd(A.list2_n, 1); A.list2[slot] = (int)l; }
             continue;
         }
         if (A.fitter == 1) {
@@ -360,7 +395,6 @@ k_fit(FitArgs A)
                 r = fb < fa ? (double)mx : (double)mn;
             } else if (err == -2) st = 2;
             if (tid == 0) { A.thr[l] = r; A.uv_n[l] = nv; A.status[l] = st; }
-            __syncthreads();
             continue;
         }
         if (A.fitter == 2) {
@@ -376,10 +410,11 @@ k_fit(FitArgs A)
                 for (int i = nv - 1; i >= 0; --i) { suf += ucnt[i]; ucnt[i] = (int)suf; }
                 A.uv_n[l] = nv; A.status[l] = 0;
             }
-            __syncthreads();
             continue;
         }
         // ---- histogram fitter ------------------------------------------------------------------------
+        int* K = overflow ? G.K : s_k; int* Cn = overflow ? G.C : s_c;
+        double* T = overflow ? G.T : s_t; double* LS = overflow ? G.LS : s_lsum; short* LD = overflow ? G.LD : s_ldep;
         LncFit f;
         f.first = (double)mn; f.last = (double)mx;
         if (mn == mx) { f.first = __dsub_rn(f.first, 0.5); f.last = __dadd_rn(f.last, 0.5); }
@@ -401,35 +436,34 @@ k_fit(FitArgs A)
         __syncthreads();
         if (s_bad) {
             if (tid == 0) { A.thr[l] = NaN; A.fits[l] = f; A.status[l] = 3; }
-            __syncthreads();
             continue;
         }
         for (int i = tid; i < nv; i += FIT_THREADS) {
-            double v = (double)s_k[i];
+            double v = (double)K[i];
             double g = __dmul_rn(__ddiv_rn(__dsub_rn(v, f.first), f.denom), (double)B);
             long long idx = (long long)g;
             if (idx == B) idx -= 1;
             if (v < hist_edge(idx, f)) idx -= 1;
             if (v >= hist_edge(idx + 1, f) && idx != B - 1) idx += 1;
-            s_k[i] = (int)idx;            // value -> bin index (non-decreasing in i)
+            K[i] = (int)idx;              // value -> bin index (non-decreasing in i)
         }
         __syncthreads();
         // merge distinct values that share a bin: head flags -> bin slots
         int nnz = 0;
         for (int i0 = 0; i0 < nv; i0 += FIT_THREADS) {
             int i = i0 + tid;
-            bool head = i < nv && (i == 0 || s_k[i] != s_k[i - 1]);
+            bool head = i < nv && (i == 0 || K[i] != K[i - 1]);
             int tot;
             int pos = cta_exclusive_scan(head ? 1 : 0, s_scan, &tot);
             // slot of element i = (number of heads up to and including i) - 1
             int slot = nnz + pos + (head ? 1 : 0) - 1;
-            int kk = i < nv ? s_k[i] : 0, cc = i < nv ? s_c[i] : 0;
-            __syncthreads();                       // everyone has read s_k/s_c of this chunk
+            int kk = i < nv ? K[i] : 0, cc = i < nv ? Cn[i] : 0;
+            __syncthreads();                       // everyone has read K/Cn of this chunk
             if (i < nv) {
-                if (head) { s_k[slot] = kk; s_c[slot] = 0; }
+                if (head) { K[slot] = kk; Cn[slot] = 0; }
             }
             __syncthreads();
-            if (i < nv) atomicAdd(&s_c[slot], cc);
+            if (i < nv) atomicAdd(&Cn[slot], cc);
             nnz += tot;
             __syncthreads();
         }
@@ -437,23 +471,23 @@ k_fit(FitArgs A)
         const double total = (double)n;
         for (int t = tid; t < nnz; t += FIT_THREADS) {
             double hp0, w;
-            s_t[t] = fit_term(s_c[t], s_k[t], f, total, &hp0, &w);
+            T[t] = fit_term(Cn[t], K[t], f, total, &hp0, &w);
         }
         __syncthreads();
         // (1)+(2): leaf of every entry; the first entry of each leaf sums its leaf
         for (int t = tid; t < nnz; t += FIT_THREADS) {
-            const PwLeaf L = pw_find_leaf(s_k[t], B);
+            const PwLeaf L = pw_find_leaf(K[t], B);
             bool head = true; int dep = -1;
             if (t > 0) {
-                const PwLeaf P = pw_find_leaf(s_k[t - 1], B);
-                head = (P.off != L.off);
-                if (head) dep = pw_lca_depth(P, L);
+                const PwLeaf Pl = pw_find_leaf(K[t - 1], B);
+                head = (Pl.off != L.off);
+                if (head) dep = pw_lca_depth(Pl, L);
             }
-            s_ldep[t] = (short)(head ? dep : -2);          // -2: not a leaf head
+            LD[t] = (short)(head ? dep : -2);          // -2: not a leaf head
             if (head) {
                 int hi = t + 1;
-                while (hi < nnz && (long long)s_k[hi] < L.off + L.n) ++hi;
-                s_lsum[t] = pw_leaf_sum(s_k, s_t, t, hi, L.off, L.n);
+                while (hi < nnz && (long long)K[hi] < L.off + L.n) ++hi;
+                LS[t] = pw_leaf_sum(K, T, t, hi, L.off, L.n);
             }
         }
         __syncthreads();
@@ -461,7 +495,7 @@ k_fit(FitArgs A)
         if (tid == 0) {
             int vp = 0, op = 0;
             for (int t = 0; t < nnz; ++t) {
-                const int d = s_ldep[t];
+                const int d = LD[t];
                 if (d == -2) continue;
                 if (t > 0) {                                // operator between the previous leaf and this one
                     while (op > 0 && s_ostk[op - 1] > d) {
@@ -470,7 +504,7 @@ k_fit(FitArgs A)
                     }
                     s_ostk[op++] = (short)d;
                 }
-                s_vstk[vp++] = s_lsum[t];
+                s_vstk[vp++] = LS[t];
             }
             while (op > 0) { double b = s_vstk[--vp], a = s_vstk[--vp]; s_vstk[vp++] = __dadd_rn(a, b); --op; }
             s_S = nnz > 0 ? s_vstk[0] : 0.0;
@@ -479,14 +513,14 @@ k_fit(FitArgs A)
         const double S = s_S;
         for (int t = tid; t < nnz; t += FIT_THREADS) {
             double hp0, w;
-            fit_term(s_c[t], s_k[t], f, total, &hp0, &w);
-            s_t[t] = __dmul_rn(__ddiv_rn(hp0, S), w);
+            fit_term(Cn[t], K[t], f, total, &hp0, &w);
+            T[t] = __dmul_rn(__ddiv_rn(hp0, S), w);
         }
         __syncthreads();
         if (tid == 0) {
             // np.cumsum: sequential left to right
             double acc = 0.0;
-            for (int t = 0; t < nnz; ++t) { acc = __dadd_rn(acc, s_t[t]); s_t[t] = acc; }
+            for (int t = 0; t < nnz; ++t) { acc = __dadd_rn(acc, T[t]); T[t] = acc; }
             // isf(alpha) = np.interp(1 - alpha, hcdf, hbins)
             double r;
             const double alpha = A.alpha;
@@ -496,11 +530,11 @@ k_fit(FitArgs A)
             else {
                 double y = __dsub_rn(1.0, alpha);
                 int lo = 0, hi = nnz;                       // first entry with cum > y
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (s_t[mid] > y) hi = mid; else lo = mid + 1; }
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (T[mid] > y) hi = mid; else lo = mid + 1; }
                 if (lo == nnz) r = f.last;                 // y >= hcdf[B]
                 else {
-                    long long j = s_k[lo];
-                    double c0 = lo > 0 ? s_t[lo - 1] : 0.0, c1 = s_t[lo];
+                    long long j = K[lo];
+                    double c0 = lo > 0 ? T[lo - 1] : 0.0, c1 = T[lo];
                     double xj = hist_edge(j, f);
                     if (c0 == y) r = xj;
                     else {
@@ -516,13 +550,7 @@ k_fit(FitArgs A)
         }
         __syncthreads();
         const long long tbase = b0 >> 1;                   // table slot (capacity >= B >= nnz)
-        for (int t = tid; t < nnz; t += FIT_THREADS) { A.tbl_k[tbase + t] = s_k[t]; A.tbl_cum[tbase + t] = s_t[t]; }
-        __syncthreads();
-    }
-    {   // the last lncRNA of this CTA
-        long long last = -1;
-        for (long long it = blockIdx.x; it < n_items; it += gridDim.x) last = it;
-        if (last >= 0) { const long long ll = A.list ? (long long)A.list[last] : last; fit_publish_thr(A, ll, A.thr[ll], A.status[ll]); }
+        for (int t = tid; t < nnz; t += FIT_THREADS) { A.tbl_k[tbase + t] = K[t]; A.tbl_cum[tbase + t] = T[t]; }
     }
 }
 
@@ -761,10 +789,6 @@ k_fit_hist_tail(FitArgs A)
         if (lane == 0) {
             LncFit fo = f; fo.tbl_n = st == 0 ? nnz : 0;
             A.thr[l] = st == 0 ? thr_v : NaN; A.fits[l] = fo; A.status[l] = st;
-        }
-        {   // thr_aln for the alignments of this lncRNA
-            const double v = st == 0 ? thr_v : __longlong_as_double(0x7ff0000000000000ll);
-            for (long long a = A.aln_off[l] + lane; a < A.aln_off[l + 1]; a += 32) A.thr_aln[a] = v;
         }
         __syncwarp();
     }

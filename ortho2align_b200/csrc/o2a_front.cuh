@@ -11,14 +11,15 @@
 // rank arithmetic of others, one launch and one global round trip of the survivor scores disappear, and no
 // barrier is left (everything is warp-synchronous).
 //
-// The warp streams the alignment's scores with 16-byte loads, eight in flight per lane, and compacts the
-// survivors IN ORDER (ballot / popc prefixes) into the alignment's slot [hsp_off[a], hsp_off[a] + n_surv) of the
+// The warp streams the alignment's scores (float64: 32-byte loads, a 4 KB tile in flight per warp) and compacts the
+// survivors IN ORDER (popc + warp scan) into the alignment's slot [hsp_off[a], hsp_off[a] + n_surv) of the
 // survivor arrays and into shared memory. The p/q stage works on SCORE CLASSES like k_pq (o2a_score.cuh): sf once
 // per distinct score, L = #{survivors with smaller p} per class, then one ordered walk that hands out the stable
 // ranks 1 + L + #{earlier survivors with the same p} = np.argsort(kind='stable').
 // Alignments with more than FRONT_SCAP survivors or more than FRONT_OVER non-class scores are only filtered here
 // and queued for the CTA-wide k_pq.
 #pragma once
+#include "o2a_chain.cuh"
 #include "o2a_device.cuh"
 #include "o2a_fit.cuh"
 #include "o2a_score.cuh"
@@ -31,7 +32,6 @@ constexpr int FRONT_SCAP = 192;           // survivors per alignment kept on chi
 constexpr int FRONT_DIRECT = 128;         // integer score classes floor(thr) + [0, 128)
 constexpr int FRONT_OVER = 32;            // other scores (cut HSPs, huge values): one class each
 constexpr int FRONT_SLOTS = FRONT_DIRECT + FRONT_OVER;
-constexpr int FRONT_ROWS = 8;             // 16-byte loads in flight per lane (f64: 8 x 512 B per warp)
 constexpr int FRONT_PASS = 32;            // passing exceptions of a narrow-score alignment kept on chip
 
 struct FrontArgs {
@@ -42,18 +42,27 @@ struct FrontArgs {
     long long n_hsp_total;
     int* n_surv; int* surv_idx; double* surv_x;
     int* pq_list; int* pq_count;          // alignments left to k_pq
+    // the retained HSPs of the alignments finished here, for the chaining (slot layout, see o2a_chain.cuh):
+    int* ret_slot; double* ret_score;     // position in the survivor list, score
+    int4* ret_coord;                      // coordinates — fetched here only when fetch_coords != 0 (device memory)
+    int fetch_coords;
+    const int4* coords4; const int* qstart; const int* qend; const int* sstart; const int* send;
+    const long long* qlen; const long long* slen;
+    int* mid_list; int* mid_count;        // alignments the warp path of the chaining cannot take (-> k_chain_small)
 };
 
 struct FrontWarpSmem {
     double x[FRONT_SCAP];                 // survivor scores, list order
-    double pe[FRONT_SLOTS];               // p of the class (narrow filter phase: values of the passing exceptions)
-    double ox[FRONT_OVER];                // scores of the overflow classes
-    int cnt[FRONT_SLOTS];                 // class multiplicity, later: survivors seen per tie group
-    int L[FRONT_SLOTS];                   // survivors with strictly smaller p (narrow filter phase: positions of passing exceptions)
-    short g[FRONT_SLOTS];                 // tie group = first class (dense order) with the same p
+    double pe[FRONT_SLOTS];               // p of the class
+    double ox[FRONT_OVER];                // scores of the overflow classes (narrow filter phase: values of the passing exceptions)
+    int cnt[FRONT_SLOTS];                 // class multiplicity, later: survivors seen per tie group (narrow filter phase: positions of the passing exceptions)
+    int L[FRONT_SLOTS];                   // survivors with strictly smaller p    } float64 filter phase: L and g together hold
+    short g[FRONT_SLOTS];                 // tie group = first class with the same p } the survivors' positions (FRONT_SCAP ints)
     short dense[FRONT_SLOTS];             // non-empty classes in slot order
     short slot[FRONT_SCAP];               // class of every survivor
 };
+
+static_assert(FRONT_SLOTS * (sizeof(int) + sizeof(short)) >= FRONT_SCAP * sizeof(int) && FRONT_PASS <= FRONT_OVER, "aliases of the filter phase");
 
 template <typename T> struct FrontTraits;
 template <> struct FrontTraits<double> { static constexpr int PER = 2; };
@@ -69,38 +78,89 @@ __device__ __forceinline__ int4 ld_stream_16(const void* p)
 }
 
 // ---- filter phase, float64 scores: returns n_surv; survivors to global slots and (first FRONT_SCAP) to S.x ------
-__device__ __forceinline__ int front_filter_f64(const double* __restrict__ score, long long h0, int m, double t,
-                                                int* __restrict__ out_idx, double* __restrict__ out_x, FrontWarpSmem& S)
+// Tile = 512 scores; lane i owns the 16 CONSECUTIVE scores [16 i, 16 i + 16) of the tile (four 32-byte loads, one
+// full DRAM sector each: LDG.E.256 on sm_100), so the order-preserving position of a survivor is
+//   (survivors of earlier tiles) + (exclusive warp scan of the per-lane counts) + (rank inside the lane's 16 bits):
+// one popc + one 5-step shuffle scan per 512 scores instead of two ballots per 64. The few survivors (~1 per lane and
+// tile) are then written in a loop over the set bits; their value is re-read (an L2 hit) rather than selected out of
+// 16 registers with a run-time index.
+__device__ __forceinline__ void ld_stream_f64x4(const double* p, double& a, double& b, double& c, double& d)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// 16 scores of one lane -> bit c set when score c passes the strict '>' (alignment.py:32-33)
+__device__ __forceinline__ unsigned front_mask16(const double (&v)[16], double t)
+{
+    unsigned mask = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) mask |= (v[c] > t ? 1u : 0u) << c;
+    return mask;
+}
+
+__device__ __forceinline__ void front_load16(const double* __restrict__ sc, long long g0, long long n_total, int e0, double t,
+                                             double (&v)[16], bool inside)
+{
+    // vector loads may run past the alignment's end (the next alignment's scores, masked by the caller) but not past
+    // the end of the score array; `inside` (warp-uniform): the whole tile is inside the array
+    if (inside) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ld_stream_f64x4(sc + e0 + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = (g0 + e0 + c < n_total) ? sc[e0 + c] : t;      // the last tile of the whole array
+}
+
+__device__ __forceinline__ int front_filter_f64(const double* __restrict__ score, long long n_total, long long h0, int m,
+                                                double t, int* __restrict__ out_idx, double* __restrict__ out_x,
+                                                FrontWarpSmem& S)
 {
     const int lane = lane_id();
-    const unsigned lt = lanemask_lt();
-    const int sh = (int)(h0 & 1);                       // stream starts at the 16-byte aligned address at / below h0
+    const int sh = (int)(h0 & 3);                       // stream starts at the 32-byte aligned address at / below h0
     const double* sc = score + h0 - sh;
+    const long long g0 = h0 - sh;                       // global index of stream element 0
     const int ms = m + sh;
-    const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
+    int* s_idx = S.L;                                   // survivor positions (S.L and S.g are free until the p/q phase)
     int base = 0;
-    for (int t0 = 0; t0 < ms; t0 += FRONT_ROWS * 64) {
-        double2 v[FRONT_ROWS];
+    double v[16];
+    front_load16(sc, g0, n_total, lane * 16, t, v, g0 + 512 <= n_total);
+#pragma unroll 1
+    for (int t0 = 0; t0 < ms; t0 += 512) {
+        const int e0 = t0 + lane * 16;                  // my first stream element
+        unsigned mask = front_mask16(v, t);
+        // the next tile's loads are in flight while this tile's survivors are placed
+        if (t0 + 512 < ms) front_load16(sc, g0, n_total, e0 + 512, t, v, g0 + t0 + 1024 <= n_total);
+        const int left = ms - e0;                       // my scores inside the alignment
+        if (left < 16) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
+        if (t0 == 0 && lane == 0) mask &= ~((1u << sh) - 1u);          // the neighbour's last HSPs
+        const int cnt = __popc(mask);
+        int incl = cnt;
 #pragma unroll
-        for (int r = 0; r < FRONT_ROWS; ++r) {
-            const int rs = t0 + r * 64;                 // row start (warp-uniform)
-            const int e = rs + lane * 2;
-            if (rs + 64 <= ms) v[r] = ld_stream_f64x2(sc + e);
-            else if (rs >= ms) { v[r].x = NEG_INF; v[r].y = NEG_INF; }
-            else { v[r].x = e < ms ? sc[e] : NEG_INF; v[r].y = e + 1 < ms ? sc[e + 1] : NEG_INF; }
-        }
-        if (sh && t0 == 0 && lane == 0) v[0].x = NEG_INF;    // the neighbour's last HSP
-#pragma unroll
-        for (int r = 0; r < FRONT_ROWS; ++r) {
-            const unsigned mx = __ballot_sync(FULL_MASK, v[r].x > t), my = __ballot_sync(FULL_MASK, v[r].y > t);
-            if (mx | my) {
-                int p = base + __popc(mx & lt) + __popc(my & lt);
-                const int e = t0 + r * 64 + lane * 2 - sh;   // HSP position inside the alignment
-                if ((mx >> lane) & 1u) { out_idx[p] = e; out_x[p] = v[r].x; if (p < FRONT_SCAP) S.x[p] = v[r].x; ++p; }
-                if ((my >> lane) & 1u) { out_idx[p] = e + 1; out_x[p] = v[r].y; if (p < FRONT_SCAP) S.x[p] = v[r].y; }
-                base += __popc(mx) + __popc(my);
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += y; }
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        if (total) {
+            int p = base + incl - cnt;
+#pragma unroll 1
+            while (mask) {
+                const int c = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int pos = e0 + c - sh;            // HSP position inside the alignment
+                out_idx[p] = pos;
+                if (p < FRONT_SCAP) s_idx[p] = pos;
+                ++p;
             }
         }
+        base += total;
+    }
+    // the survivors' scores: one independent (L2-resident) load each, all in flight together
+    __syncwarp();
+    const double* al = score + h0;
+#pragma unroll 1
+    for (int k = lane; k < base; k += 32) {
+        const double x = al[k < FRONT_SCAP ? s_idx[k] : out_idx[k]];
+        out_x[k] = x;
+        if (k < FRONT_SCAP) S.x[k] = x;
     }
     return base;
 }
@@ -121,7 +181,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
     // q > thr  <=>  q > floor(thr) for integers; clamped so that the sentinel can never pass
     const double tf = floor(t);
     const int tq = tf >= 2147483647.0 ? 2147483647 : (tf <= (double)SENT ? SENT : (int)tf);
-    // exceptions that pass (value > thr): positions in S.L, values in S.pe (both free during the filter phase)
+    // exceptions that pass (value > thr): positions in S.cnt, values in S.ox (both free during the filter phase)
     int np = 0;
     for (int i0 = 0; i0 < ne; i0 += 32) {
         const int i = i0 + lane;
@@ -129,7 +189,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
         const bool pass = i < ne && v > t;
         const unsigned b = __ballot_sync(FULL_MASK, pass);
         const int p = np + __popc(b & lt);
-        if (pass && p < FRONT_PASS) { S.L[p] = exc_pos[x0 + i]; S.pe[p] = v; }
+        if (pass && p < FRONT_PASS) { S.cnt[p] = exc_pos[x0 + i]; S.ox[p] = v; }
         np += __popc(b);
     }
     __syncwarp();
@@ -173,7 +233,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
                 const int c = __ffs(sent) - 1; sent &= sent - 1;
                 const int pos = e + c - sh;
                 bool ok = false;
-                if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (S.L[i] == pos) { ok = true; break; } }
+                if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (S.cnt[i] == pos) { ok = true; break; } }
                 else {
                     int lo = 0, hi = ne;
                     while (lo < hi) { const int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < pos) lo = mid + 1; else hi = mid; }
@@ -195,7 +255,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
                     if ((msk >> c) & 1u) {
                         double x = (double)q_at<T>(raw[r], c);
                         if ((sent_pass >> c) & 1u) {     // a passing exception: its exact float64 value
-                            if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (S.L[i] == ep + c) { x = S.pe[i]; break; } }
+                            if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (S.cnt[i] == ep + c) { x = S.ox[i]; break; } }
                             else {
                                 int lo = 0, hi = ne;
                                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < ep + c) lo = mid + 1; else hi = mid; }
@@ -214,10 +274,20 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
     return base;
 }
 
+template <int FIT>
+__device__ __forceinline__ double front_sf(double x, const PqFit& F)
+{
+    if (FIT == 0) return hist_sf(x, F.f, F.tk, F.tc);
+    if (F.fitter == 1) return kde_sf_compressed(x, F.uval, F.ucnt, F.unv, F.kfac, F.nbg);
+    return emp_sf_compressed(x, F.uval, F.ucnt, F.unv, F.nbg);
+}
+
 // ---- p / q phase on the survivors in S.x[0..ns) --------------------------------------------------------------------
 // Returns false when the alignment has more than FRONT_OVER non-class scores (left to k_pq).
+// On success S.slot[0..kept) holds the survivor-list positions of the retained HSPs and *kept_out their number.
+template <int FIT>
 __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double thr, int ns, int m, long long h0,
-                                         long long a, FrontWarpSmem& S)
+                                         long long a, FrontWarpSmem& S, int* kept_out)
 {
     const int lane = lane_id();
     const unsigned lt = lanemask_lt();
@@ -226,6 +296,7 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double
     // ---- classes ---------------------------------------------------------------------------------
     const long long xlo = (long long)floor(thr);
     int nover = 0, maxslot = 0;
+#pragma unroll 1
     for (int k0 = 0; k0 < ns; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < ns;
@@ -252,11 +323,12 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double
     const int ndir = maxslot + 1;
     const int ncls = ndir + nover;
     int nd = 0;
+#pragma unroll 1
     for (int e0 = 0; e0 < ncls; e0 += 32) {
         const int e = e0 + lane;
         const int slot = e < ndir ? e : FRONT_DIRECT + (e - ndir);
         const bool used = e < ncls && S.cnt[slot] > 0;
-        if (used) S.pe[slot] = pq_sf(e < ndir ? (double)(xlo + slot) : S.ox[e - ndir], F);
+        if (used) S.pe[slot] = front_sf<FIT>(e < ndir ? (double)(xlo + slot) : S.ox[e - ndir], F);
         const unsigned ub = __ballot_sync(FULL_MASK, used);
         if (used) S.dense[nd + __popc(ub & lt)] = (short)slot;
         nd += __popc(ub);
@@ -268,21 +340,73 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double
             const double p = S.pe[S.slot[k]];
             xs[k] = p; A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1;
         }
+        __syncwarp();
+        for (int k = lane; k < ns; k += 32) S.slot[k] = (short)k;       // everything is retained
         if (lane == 0) A.n_keep[a] = ns;
+        *kept_out = ns;
         return true;
     }
-    // ---- per class: survivors with strictly smaller p, and the tie group ------------------------------------
-    for (int d = lane; d < nd; d += 32) {
-        const int slot = S.dense[d];
-        const double p = S.pe[slot];
-        int L = 0, g = slot;
-        for (int d2 = 0; d2 < nd; ++d2) {
-            const int s2 = S.dense[d2];
-            const double p2 = S.pe[s2];
-            L += (p2 < p) ? S.cnt[s2] : 0;
-            if (p2 == p && s2 < g) g = s2;
+    // ---- per class: survivors with strictly smaller p (L), and the tie group (g) ------------------------------------
+    // sf is non-increasing in the score, so along the dense list (ascending integer scores) p normally never rises:
+    // tie groups are runs, L = survivors after the run. That takes two ballots and two scans for up to 64 classes.
+    // Anything else (overflow classes, more than 64 classes, a p that rises by an ulp) takes the all-pairs form.
+    bool fast = nover == 0 && nd <= 64;
+    int slot_u[2], cn_u[2]; double p_u[2]; bool head_u[2];
+    if (fast) {
+        bool mono = true;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int d = lane + 32 * u;
+            const bool valid = d < nd;
+            slot_u[u] = valid ? S.dense[d] : 0;
+            cn_u[u] = valid ? S.cnt[slot_u[u]] : 0;
+            p_u[u] = valid ? S.pe[slot_u[u]] : 0.0;
+            const double pprev = (valid && d > 0) ? S.pe[S.dense[d - 1]] : 0.0;
+            head_u[u] = valid && (d == 0 || p_u[u] != pprev);
+            if (valid && d > 0 && p_u[u] > pprev) mono = false;
         }
-        S.L[slot] = L; S.g[slot] = (short)g;
+        fast = __all_sync(FULL_MASK, mono);
+    }
+    if (fast) {
+        const unsigned H0 = __ballot_sync(FULL_MASK, head_u[0]), H1 = __ballot_sync(FULL_MASK, head_u[1]);
+        int incl0 = cn_u[0], incl1 = cn_u[1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y0 = __shfl_up_sync(FULL_MASK, incl0, d), y1 = __shfl_up_sync(FULL_MASK, incl1, d);
+            if (lane >= d) { incl0 += y0; incl1 += y1; }
+        }
+        incl1 += __shfl_sync(FULL_MASK, incl0, 31);
+        const int total = __shfl_sync(FULL_MASK, incl1, 31);
+        const int cprev0 = incl0 - cn_u[0], cprev1 = incl1 - cn_u[1];      // survivors before this class
+        const unsigned le = lt | (1u << lane), gt = ~le;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const unsigned Hu = u ? H1 : H0;
+            // head of my run (at or below me) and the next head (above me), as dense indices
+            int hidx, nidx;
+            if (Hu & le) hidx = 32 * u + 31 - __clz(Hu & le); else hidx = 31 - __clz(H0);
+            if (Hu & gt) nidx = 32 * u + __ffs(Hu & gt) - 1;
+            else if (u == 0 && H1) nidx = 32 + __ffs(H1) - 1;
+            else nidx = -1;
+            const int c0 = __shfl_sync(FULL_MASK, cprev0, nidx & 31), c1 = __shfl_sync(FULL_MASK, cprev1, nidx & 31);
+            const int before_next = nidx < 0 ? total : (nidx < 32 ? c0 : c1);
+            if (lane + 32 * u < nd) { S.L[slot_u[u]] = total - before_next; S.g[slot_u[u]] = S.dense[hidx]; }
+        }
+    } else {
+#pragma unroll 1
+        for (int d = lane; d < nd; d += 32) {
+            const int slot = S.dense[d];
+            const double p = S.pe[slot];
+            int L = 0, g = slot;
+#pragma unroll 1
+            for (int d2 = 0; d2 < nd; ++d2) {
+                const int s2 = S.dense[d2];
+                const double p2 = S.pe[s2];
+                L += (p2 < p) ? S.cnt[s2] : 0;
+                if (p2 == p && s2 < g) g = s2;
+            }
+            S.L[slot] = L; S.g[slot] = (short)g;
+        }
     }
     __syncwarp();
     for (int d = lane; d < nd; d += 32) S.cnt[S.dense[d]] = 0;         // now: survivors seen per tie group
@@ -290,11 +414,13 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double
     // ---- ordered walk: rank = 1 + L + #{earlier survivors of the tie group} ------------------------------------
     const double md = (double)m;                       // total_hsps = len(alignment._all_HSPs), pipeline.py:770
     int kept = 0;
+#pragma unroll 1
     for (int k0 = 0; k0 < ns; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < ns;
         const unsigned vm = __ballot_sync(FULL_MASK, valid);
         int slot = 0, g = 0, seen = 0, before = 0; unsigned peers = 0;
+        bool is_kept = false;
         if (valid) {
             slot = S.slot[k]; g = S.g[slot];
             peers = __match_any_sync(vm, g);
@@ -310,15 +436,23 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double
             const double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);     // multiply first, like the reference
             const bool keep = q <= A.alpha;
             xs[k] = p; A.surv_pq[h0 + k] = q; A.surv_keep[h0 + k] = keep ? 1 : 0;
-            kept += keep;
+            is_kept = keep;
         }
+        // the retained HSPs in list order, compacted in place: the slot entries at or below k have been read
+        const unsigned kb = __ballot_sync(FULL_MASK, is_kept);
+        if (is_kept) S.slot[kept + __popc(kb & lt)] = (short)k;
+        kept += __popc(kb);
     }
-    kept = __reduce_add_sync(FULL_MASK, kept);
     if (lane == 0) A.n_keep[a] = kept;
+    *kept_out = kept;
     return true;
 }
 
-template <typename T>
+// FIT = 0: histogram fitter only (its sf is the only one compiled in: the kernel's hot code has to stay small — the
+// instruction caches hold 32 KB, and 32 warps per SM in different phases of a large kernel miss them constantly: a variant
+// of this kernel that also gathered coordinates and chained ran at 44 % issue utilisation with 6.9 stall cycles per
+// instruction on instruction fetch); FIT = 1: KDE / empirical.
+template <typename T, int FIT>
 __global__ void __launch_bounds__(FRONT_WARPS * 32, FRONT_CTAS_PER_SM)
 k_front(FrontArgs A)
 {
@@ -338,20 +472,28 @@ k_front(FrontArgs A)
         const double thr = P.thr[l];
         int ns;
         __syncwarp();                                  // the previous alignment is done with S
-        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, h0, m, thr, A.surv_idx + h0, A.surv_x + h0, S);
+        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, h0, m, thr, A.surv_idx + h0, A.surv_x + h0, S);
         else {
             const long long x0 = A.exc_off[a];
             ns = front_filter_q<T>(reinterpret_cast<const T*>(A.score_q), A.n_hsp_total, h0, m, thr, A.exc_pos, A.exc_val,
                                    x0, (int)(A.exc_off[a + 1] - x0), A.surv_idx + h0, A.surv_x + h0, S);
         }
         if (lane == 0) A.n_surv[a] = ns;
+        if constexpr (sizeof(T) == 8) {
+            // the first tile of my next alignment: one 128-byte line per lane into L2 while the p/q phase runs
+            if (a + nwarps < P.n_aln) {
+                const long long hn = P.hsp_off[a + nwarps] & ~3ll;
+                if (hn + 512 <= A.n_hsp_total) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.score + hn + lane * 16));
+            }
+        }
         if (ns == 0) { if (lane == 0) P.n_keep[a] = 0; continue; }
         bool done = false;
+        int kept = 0;
         if (ns <= FRONT_SCAP) {
             __syncwarp();
-            PqFit F; F.fitter = P.fitter; F.tk = nullptr; F.tc = nullptr; F.uval = nullptr; F.ucnt = nullptr;
+            PqFit F; F.fitter = FIT == 0 ? 0 : P.fitter; F.tk = nullptr; F.tc = nullptr; F.uval = nullptr; F.ucnt = nullptr;
             F.unv = 0; F.kfac = 1.0; F.nbg = 1.0;
-            if (P.fitter == 0) {
+            if (FIT == 0) {
                 F.f = P.fits[l];
                 const long long tb = P.bg_off[l] >> 1;
                 F.tk = P.tbl_k + tb; F.tc = P.tbl_cum + tb;
@@ -361,12 +503,31 @@ k_front(FrontArgs A)
                 F.nbg = (double)(P.bg_off[l + 1] - b0);
                 if (P.fitter == 1) F.kfac = P.kde_factor[l];
             }
-            done = front_pq(P, F, thr, ns, m, h0, a, S);
+            done = front_pq<FIT>(P, F, thr, ns, m, h0, a, S, &kept);
         }
-        if (!done && lane == 0) {                      // k_pq takes it (many survivors / many non-class scores)
-            P.n_keep[a] = 0;
-            const int slot = atomicAdd(A.pq_count, 1);
-            A.pq_list[slot] = (int)a;
+        if (!done) {                                   // k_pq takes it (many survivors / many non-class scores)
+            if (lane == 0) {
+                P.n_keep[a] = 0;
+                const int slot = atomicAdd(A.pq_count, 1);
+                A.pq_list[slot] = (int)a;
+            }
+            continue;
+        }
+        // ---- the retained HSPs for the chaining: survivor slot, score and (device-resident records) coordinates ------
+        if (kept == 0) continue;
+        if (lane == 0 && chain_needs_cta(kept, A.qlen[a], A.slen[a])) { const int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
+        __syncwarp();
+#pragma unroll 1
+        for (int p = lane; p < kept; p += 32) {
+            const int k = S.slot[p];
+            A.ret_slot[h0 + p] = k; A.ret_score[h0 + p] = S.x[k];
+            if (A.fetch_coords) {
+                const long long h = h0 + A.surv_idx[h0 + k];
+                int4 c;
+                if (A.coords4) c = A.coords4[h];
+                else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
+                A.ret_coord[h0 + p] = c;
+            }
         }
     }
 }
