@@ -730,7 +730,7 @@ static int run_chain(o2a_ctx* ctx, int chunk, cudaStream_t st)
         if (fork) {
             CU(cudaEventRecord(ctx->aux_fork, st));
             CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
-            k_chain_small<<<grid_for(ctx, na, 8), CHAIN_THREADS, 0, st>>>(A);
+            k_chain_small<<<grid_for(ctx, na, 12), CHAIN_THREADS, 0, st>>>(A);
             LAUNCH_CHECK();
         }
         k_chain_warp<<<grid_for(ctx, (na + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0,

@@ -17,7 +17,7 @@
 
 namespace o2a {
 
-constexpr int CHAIN_THREADS = 128;
+constexpr int CHAIN_THREADS = 32;         // k_chain_small: one warp per queued alignment (31..192 retained HSPs)
 constexpr int CHAIN_WARP_MAX = 30;        // retained HSPs per alignment handled by ONE warp (one graph + 2 sentinels <= 32 lanes)
 constexpr int CHAIN_SMALL_MAX = 192;      // retained HSPs per alignment handled by a CTA in shared memory
 constexpr int CHAINBIG_THREADS = 512;

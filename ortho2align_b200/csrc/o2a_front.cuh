@@ -479,13 +479,6 @@ k_front(FrontArgs A)
                                    x0, (int)(A.exc_off[a + 1] - x0), A.surv_idx + h0, A.surv_x + h0, S);
         }
         if (lane == 0) A.n_surv[a] = ns;
-        if constexpr (sizeof(T) == 8) {
-            // the first tile of my next alignment: one 128-byte line per lane into L2 while the p/q phase runs
-            if (a + nwarps < P.n_aln) {
-                const long long hn = P.hsp_off[a + nwarps] & ~3ll;
-                if (hn + 512 <= A.n_hsp_total) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.score + hn + lane * 16));
-            }
-        }
         if (ns == 0) { if (lane == 0) P.n_keep[a] = 0; continue; }
         bool done = false;
         int kept = 0;
