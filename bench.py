@@ -529,15 +529,130 @@ def stage_files(argv):
 
 
 
+def strong_scaling(args, eng, params, dev, rank, world, procs, config, n_lnc, steps, warmup):
+    """ONE fixed workload (BASELINE configs[4] by default: 100 k lncRNAs, ~2e7 HSPs) LPT-sharded by lncRNA over the
+    ranks (ortho2align_b200.distributed.my_shard = pipeline.lpt_shards by HSP count); every rank runs its shard, the
+    per-lncRNA results are gathered on every rank (distributed.gather_best_orthologs: counts + one padded all_gather)
+    inside the timed region, and rank 0 checks them against the whole workload run on one GPU. Returns the dict that
+    goes into the JSON line (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+    from ortho2align_b200 import distributed as D
+    from ortho2align_b200.engine import DeviceBatch
+    with_kde = args.fitter == "kde"
+    t0 = time.perf_counter()
+    n_lnc = n_lnc or {1: 96, 2: 20_000, 3: 20_000, 4: 5_000, 5: 100_000}[config]
+    batch = generate(config, n_lnc, args.seed, procs)                       # the same workload on every rank
+    t_gen = time.perf_counter() - t0
+    idx, shard = D.my_shard(batch, rank, world)
+    db = DeviceBatch(shard, dev, aos=True)
+    st = db.struct(with_kde)
+    for _ in range(max(warmup, 1)):
+        eng.run(st, params)
+    res = eng.fetch(survivors=False)
+    if world > 1:
+        D.gather_best_orthologs(res, idx, batch.n_lnc, dev)                 # warm-up of the collective
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launch_count()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(steps):
+        c = eng.run(st, params)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / steps
+    # the job's result exchange: every rank learns which lncRNAs have an ortholog (what get_best_orthologs consumes)
+    res = eng.fetch(survivors=False)
+    has = D.gather_best_orthologs(res, idx, batch.n_lnc, dev) if world > 1 else (res.best_aln >= 0).astype(np.int64)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    launches = (eng.launch_count() - l0) // steps
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([c.n_survivors, c.n_retained, c.n_chain_hsps, c.n_chains, shard.n_hsp], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        # the whole workload on this GPU: the sharded job must reproduce it
+        full = DeviceBatch(batch, dev, aos=True)
+        cf = eng.run(full.struct(with_kde), params)
+        rf = eng.fetch(survivors=False)
+        same = (int(tot[0]) == cf.n_survivors and int(tot[1]) == cf.n_retained and int(tot[2]) == cf.n_chain_hsps
+                and int(tot[3]) == cf.n_chains and np.array_equal(has, (rf.best_aln >= 0).astype(np.int64)))
+        out = {"scaling": "strong", "workload": CONFIG_NAMES[config], "lncRNAs": batch.n_lnc, "hsps": batch.n_hsp,
+               "n_gpus": world, "steps": steps, "ms_per_step": float(t[0]), "value": batch.n_hsp / (float(t[0]) * 1e-3),
+               "unit": UNIT, "wall_ms_per_step_incl_result_gather": float(t[1]),
+               "value_incl_result_gather": batch.n_hsp / (float(t[1]) * 1e-3),
+               "launches_per_step": int(launches), "hsps_on_rank0": shard.n_hsp,
+               "identical_to_single_gpu": bool(same), "shard": "LPT by HSP count (pipeline.lpt_shards)",
+               "gen_seconds": round(t_gen, 1)}
+        assert same, "sharded result differs from the single-GPU result"
+        del full
+    del db
+    torch.cuda.empty_cache()
+    return out
+
+
+def stage_pcie(argv):
+    """Host->device ceiling of the box: every rank copies a pinned buffer to its GPU at the same time (plain
+    cudaMemcpyAsync); prints per-rank and aggregate GB/s. Run under torchrun with N = 1, 2, 4, 8 (VERDICT r1 weak #2)."""
+    ap = argparse.ArgumentParser(prog="bench.py --stage pcie")
+    ap.add_argument("--mb", type=int, default=512)
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args(argv)
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.mb << 20
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True); h.fill_(1)
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (src, dst) in (("h2d", (h, d)), ("d2h", (d, h))):
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.reps):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        gbs = torch.tensor([n * args.reps / dt / 1e9], dtype=torch.float64, device=dev)
+        allg = torch.zeros(world, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(allg, gbs)
+        else:
+            allg = gbs
+        out[name] = {"per_rank_gbs": [round(float(x), 2) for x in allg.tolist()], "aggregate_gbs": round(float(allg.sum()), 2)}
+    if rank == 0:
+        print(json.dumps({"stage": "pcie", "n_gpus": world, "mb": args.mb, "reps": args.reps, **out}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     if "--stage" in sys.argv:
         k = sys.argv.index("--stage")
         stage = sys.argv[k + 1] if k + 1 < len(sys.argv) else ""
         rest = sys.argv[1:k] + sys.argv[k + 2:]
-        fn = {"producer": stage_producer, "ingest": stage_ingest, "files": stage_files, "annotate": stage_annotate}.get(stage)
+        fn = {"producer": stage_producer, "ingest": stage_ingest, "files": stage_files, "annotate": stage_annotate,
+              "pcie": stage_pcie}.get(stage)
         if stage != "build":
             if fn is None:
-                raise SystemExit("--stage must be one of build, producer, ingest, files, annotate")
+                raise SystemExit("--stage must be one of build, producer, ingest, files, annotate, pcie")
             return fn(rest)
         sys.argv = [sys.argv[0]] + rest
     ap = argparse.ArgumentParser()
@@ -555,6 +670,15 @@ def main():
     ap.add_argument("--e2e-engines", type=int, default=2, choices=[1, 2],
                     help="library contexts per GPU in the e2e arm: with 2, two host threads alternate batches, so the "
                          "uploads of one batch overlap the last kernels and the result download of the other")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every rank owns a full shard of --config; strong: ONE fixed workload "
+                         "(--strong-config, default BASELINE configs[4]) LPT-sharded over the ranks, result checked against 1 GPU")
+    ap.add_argument("--strong-config", type=int, default=5)
+    ap.add_argument("--strong-lnc", type=int, default=None)
+    ap.add_argument("--no-strong", action="store_true", help="N > 1 default run: skip the attached strong-scaling measurement")
+    ap.add_argument("--batches", type=int, default=1,
+                    help="device-resident arm: the workload as this many batches of --lnc lncRNAs each, all resident in HBM, "
+                         "one step = one pass over all of them (config 3 at full size: --lnc 1000 --batches 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident arm only (profiling runs under ncu)")
     ap.add_argument("--gather", default="final", choices=["step", "final"],
@@ -588,7 +712,7 @@ def main():
     procs = max(1, min(32, ncpu // max(world, 1)))
     t_gen = time.perf_counter()
     # weak scaling: every rank owns its own full-size shard of lncRNAs (independent units, no exchange)
-    batch = generate(args.config, n_lnc, args.seed + 1000 * rank, procs)
+    batch = generate(args.config, n_lnc, args.seed + 1000 * rank, procs) if args.scaling == "weak" else None
     t_gen = time.perf_counter() - t_gen
 
     import torch
@@ -606,9 +730,42 @@ def main():
     params = eng.params(args.fitter, True, 0.05, 5, 2, "block_length", "max")
     with_kde = args.fitter == "kde"
 
+    if args.scaling == "strong":
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ss = strong_scaling(args, eng, params, dev, rank, world, procs, args.strong_config, args.strong_lnc,
+                            args.steps, args.warmup)
+        clocks = sampler.stop()
+        if rank == 0:
+            line = {"metric": METRIC, "value": ss["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": ss["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": ss["workload"], "lncRNAs": ss["lncRNAs"], "hsps": ss["hsps"], "fitter": args.fitter,
+                               "fdr": True, "alpha": 0.05, "parallelism": f"one workload LPT-sharded by lncRNA over {world} GPU(s)",
+                               "l2": "every step re-reads its shard from HBM; C5 per-GPU shards below L2 size at N >= 4 are noted in DESIGN.md"},
+                    "strong_scaling": ss, "gpu_launches": ss["launches_per_step"] * args.steps, "clocks": clocks,
+                    "e2e": None, "roofline": None, "cpu_baseline": None}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        eng.close()
+        return
+
     # ---------------- device-resident arm (value) ----------------
-    dbatch = DeviceBatch(batch, dev, aos=True, score_bits=args.score_bits, bg_bits=args.score_bits if args.score_bits in (8, 16) else 32)
+    bg_bits = args.score_bits if args.score_bits in (8, 16) else 32
+    dbatch = DeviceBatch(batch, dev, aos=True, score_bits=args.score_bits, bg_bits=bg_bits)
     dstruct = dbatch.struct(with_kde)
+    # --batches B: B - 1 more batches of the same shape (other seeds), generated one at a time and kept in HBM only
+    more, more_hsp, more_bg, more_exc = [], 0, 0, 0
+    for bi in range(1, args.batches):
+        t0 = time.perf_counter()
+        hb_i = generate(args.config, n_lnc, args.seed + 1000 * rank + 7919 * bi, procs)
+        t_gen += time.perf_counter() - t0
+        db_i = DeviceBatch(hb_i, dev, aos=True, score_bits=args.score_bits, bg_bits=bg_bits)
+        more.append((db_i, db_i.struct(with_kde)))
+        more_hsp += hb_i.n_hsp; more_bg += hb_i.n_bg
+        more_exc += int(db_i.t["exc_pos"].numel()) if args.score_bits else 0
+        del hb_i
     # the only collective of the path: every rank learns every shard's result counts (NCCL all_gather, 40 B per
     # rank and step). It is issued asynchronously from its own ring slot, so the next step's kernels do not wait
     # for the other ranks; all of them are waited for before the timed region closes.
@@ -621,8 +778,30 @@ def main():
 
     steps_done = [0]
 
-    def step_device():
+    class _Sum:
+        n_survivors = n_retained = n_chain_hsps = n_chains = n_failed_lnc = 0
+
+    def step_device(acc=None):
         c = eng.run(dstruct, params)
+        if more:
+            tot = _Sum()
+            for cc in [c]:
+                for f in ("n_survivors", "n_retained", "n_chain_hsps", "n_chains", "n_failed_lnc"):
+                    setattr(tot, f, getattr(tot, f) + int(getattr(cc, f)))
+            if acc is not None:
+                for k, v in eng.stage_ms().items():
+                    acc[k] = acc.get(k, 0.0) + v
+            for _, st_i in more:
+                cc = eng.run(st_i, params)
+                for f in ("n_survivors", "n_retained", "n_chain_hsps", "n_chains", "n_failed_lnc"):
+                    setattr(tot, f, getattr(tot, f) + int(getattr(cc, f)))
+                if acc is not None:
+                    for k, v in eng.stage_ms().items():
+                        acc[k] = acc.get(k, 0.0) + v
+            c = tot
+        elif acc is not None:
+            for k, v in eng.stage_ms().items():
+                acc[k] = acc.get(k, 0.0) + v
         if world > 1 and args.gather == "final":
             k = steps_done[0] % n_slots
             steps_done[0] += 1
@@ -664,11 +843,9 @@ def main():
     torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(args.steps):
-        c = step_device()
-        sm = eng.stage_ms()
-        score_ms.append(sm["filter"])
-        for k, v in sm.items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        before = stage_acc.get("filter", 0.0)
+        c = step_device(stage_acc)
+        score_ms.append(stage_acc["filter"] - before)
     e_own = torch.cuda.Event(enable_timing=True)
     e_own.record(stream)             # this rank's own K steps end here; what follows waits for the slowest rank
     drain_gathers()
@@ -691,8 +868,9 @@ def main():
         per_rank = {"own_ms_per_step": [round(float(x), 4) for x in allr[:, 0].tolist()],
                     "kernel_stage_ms_per_step": [round(float(x), 4) for x in allr[:, 1].tolist()]}
     ms_step = float(t.item()) / args.steps
-    hsps_all = batch.n_hsp * world
-    value = hsps_all / (ms_step * 1e-3)
+    hsps_all = batch.n_hsp * world                       # one batch per rank: what the e2e arm moves per step
+    hsps_value = (batch.n_hsp + more_hsp) * world        # the device-resident arm passes over every batch per step
+    value = hsps_value / (ms_step * 1e-3)
 
     # roofline of the dominant kernel: k_front = score filter + p-values + ranks + q + keep flags, one warp per alignment
     # (stage "filter" of the library's event timeline; the alignments it leaves to k_pq / k_rank_big are stage "pq").
@@ -700,8 +878,8 @@ def main():
     # 12 B per exception entry) + per SURVIVOR 4 B position + 8 B score + 8 B p + 8 B q + 1 B keep written.
     peak, peak_src = measured_peak()
     score_bytes = {0: 8.0, 8: 1.0, 16: 2.0, 32: 4.0}[args.score_bits]
-    n_exc = int(dbatch.t["exc_pos"].numel()) if args.score_bits else 0
-    alg_bytes = score_bytes * batch.n_hsp + 12.0 * n_exc + 29.0 * c.n_survivors
+    n_exc = (int(dbatch.t["exc_pos"].numel()) if args.score_bits else 0) + more_exc
+    alg_bytes = score_bytes * (batch.n_hsp + more_hsp) + 12.0 * n_exc + 29.0 * c.n_survivors
     avg_score_ms = float(np.mean(score_ms))
     achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9
     kernel = "k_front<%s>" % {0: "double", 8: "signed char", 16: "short", 32: "int"}[args.score_bits]
@@ -712,7 +890,7 @@ def main():
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}}
     # the same figure for the whole step: every algorithmic byte of the path (fit: the background read once, 4 B per
     # score here; gather + chain: 28 B per retained HSP) over the step time
-    step_bytes = alg_bytes + 4.0 * batch.n_bg + 28.0 * c.n_retained
+    step_bytes = alg_bytes + 4.0 * (batch.n_bg + more_bg) + 28.0 * c.n_retained
     roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
 
@@ -723,7 +901,24 @@ def main():
     # that packing takes is reported as `pack_ms` (a caller that parses JSON gets the layout from the parser itself).
     from ortho2align_b200.hostbatch import HostBatch
     e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
-    del dbatch, dstruct
+    # KDE: the reference evaluates ndtr once per (surviving HSP x background score) (fitting.py:295); the library
+    # evaluates it per (score class x distinct background value). Both counts, against the device's measured ndtr rate.
+    kde = None
+    if with_kde:
+        r_k = eng.fetch(survivors=False)                 # last batch of the last step
+        last = more[-1][0] if more else dbatch
+        aln_off = last.t["aln_off"].cpu().numpy(); bg_off = last.t["bg_off"].cpu().numpy()
+        surv_l = np.add.reduceat(r_k.n_surv.astype(np.int64), aln_off[:-1][aln_off[:-1] < len(r_k.n_surv)]) if len(r_k.n_surv) else np.zeros(0)
+        n_bg_l = np.diff(bg_off)[:len(surv_l)]
+        ref_evals = float((surv_l * n_bg_l).sum()) * args.batches
+        ndtr_rate = eng.fp64_probe("ndtr", 4000)
+        dfma_rate = eng.fp64_probe("dfma", 20000)
+        kde = {"reference_ndtr_evals_per_step": ref_evals, "reference_equivalent_evals_per_s": ref_evals / (ms_step * 1e-3),
+               "device_ndtr_evals_per_s_probe": ndtr_rate, "device_dfma_per_s_probe": dfma_rate,
+               "note": "value compression (integer backgrounds: ~50 distinct scores) replaces survivors x n_bg evaluations "
+                       "by classes x distinct values; the probe is the library's own ndtr (0.5 erfc) at full occupancy"}
+        roofline["kde"] = kde
+    del dbatch, dstruct, more
     torch.cuda.empty_cache()
     if args.no_e2e:
         if rank == 0:
@@ -735,8 +930,8 @@ def main():
         eng.close()
         return
     t0 = time.perf_counter()
-    hb = HostBatch.from_columnar(batch, threads=procs, pinned=True,
-                                 score_bits=args.e2e_score_bits or None)
+    hb = HostBatch.from_columnar(batch, threads=procs, pinned=True, score_bits=args.e2e_score_bits or None,
+                                 pin_coords="zerocopy" in args.e2e_coords)
     pack_ms = (time.perf_counter() - t0) * 1e3
     if with_kde:
         hb.ensure_kde_factor()
@@ -902,6 +1097,11 @@ def main():
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {k} lncRNAs ({sample.n_hsp} HSPs) of the workload, {secs:.2f} s per pass, best of 3"}
 
+    strong = None
+    if world > 1 and not args.no_strong:
+        # beside the weak-scaling figure: ONE fixed workload (BASELINE configs[4]) sharded over the ranks
+        strong = strong_scaling(args, eng, params, dev, rank, world, procs, args.strong_config, args.strong_lnc,
+                                max(args.steps, 10), max(args.warmup, 3))
     if world > 1:
         g = gathered[0].view(world, 5).cpu().numpy()          # slot 0: first timed step (same batch every step)
         assert int(g[rank, 0]) == int(c.n_survivors)
@@ -909,9 +1109,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": CONFIG_NAMES[args.config], "lncRNAs_per_gpu": batch.n_lnc,
-                           "alignments_per_gpu": batch.n_aln, "hsps_per_gpu": batch.n_hsp,
-                           "bg_scores_per_gpu": batch.n_bg, "fitter": args.fitter, "fdr": True, "alpha": 0.05,
+                "config": {"workload": CONFIG_NAMES[args.config], "batches_resident": args.batches, "lncRNAs_per_gpu": batch.n_lnc * args.batches,
+                           "alignments_per_gpu": batch.n_aln * args.batches, "hsps_per_gpu": batch.n_hsp + more_hsp,
+                           "bg_scores_per_gpu": batch.n_bg + more_bg, "fitter": args.fitter, "fdr": True, "alpha": 0.05,
                            "score_layout": LAYOUTS[args.score_bits],
                            "survivors_per_gpu": int(c.n_survivors), "orthologs_per_gpu": int(c.n_chains),
                            "parallelism": f"lncRNA shards x{world}, no data-path collective",
@@ -921,6 +1121,8 @@ def main():
                 "clocks": clocks}
         if per_rank:
             line["per_rank"] = per_rank
+        if strong:
+            line["strong_scaling"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -196,7 +196,8 @@ int  o2a_pipeline_chunks(const o2a_ctx *ctx);
  *                default min(16, cores)) collect the 16-byte records, one small DMA per chunk brings them back;
  *                works with pageable caller memory; a chunk that retains more than 1/8 of its HSPs is uploaded whole
  *   UPLOAD       all 16 B per HSP cross PCIe
- *   AUTO         ZERO_COPY when the caller's coordinate arrays are mapped, else HOST_GATHER
+ *   AUTO         HOST_GATHER (as fast or faster than ZERO_COPY on a B200 box, and indifferent to how the caller
+ *                allocated its coordinate arrays)
  * Environment override: O2A_COORDS=zerocopy|gather|upload. o2a_coords_mode: what the last host call used. */
 #define O2A_COORDS_AUTO 0
 #define O2A_COORDS_ZERO_COPY 1
@@ -204,6 +205,10 @@ int  o2a_pipeline_chunks(const o2a_ctx *ctx);
 #define O2A_COORDS_UPLOAD 3
 int  o2a_set_coords_mode(o2a_ctx *ctx, int mode);
 int  o2a_coords_mode(const o2a_ctx *ctx);
+/* FP64 pipe probes of the whole device (what the KDE p-value evaluations are bound by; MEASURED_PEAKS.json has no
+ * FP64 figure): kind 0 = dependent-chain DFMA rate (fma/s; x2 = FLOP/s), kind 1 = ndtr (0.5 erfc) evaluations/s with the
+ * library's own device function. iters = chain length per thread. */
+int  o2a_fp64_probe(o2a_ctx *ctx, int kind, int64_t iters, double *per_second);
 int  o2a_set_timing(o2a_ctx *ctx, int enabled);
 int  o2a_get_stage_ms(o2a_ctx *ctx, float *ms /*O2A_STAGE_COUNT*/);
 

@@ -163,6 +163,12 @@ class Engine:
     def launch_count(self):
         return int(self.lib.o2a_launch_count(self.h))
 
+    def fp64_probe(self, kind="dfma", iters=20000):
+        """Sustained FP64 rate of the device: 'dfma' -> fused multiply-adds per second, 'ndtr' -> ndtr evaluations per second."""
+        v = C.c_double(0.0)
+        self._check(self.lib.o2a_fp64_probe(self.h, {"dfma": 0, "ndtr": 1}[kind], int(iters), C.byref(v)), "o2a_fp64_probe")
+        return float(v.value)
+
     COORDS_MODES = {"auto": 0, "zerocopy": 1, "gather": 2, "upload": 3}
 
     def set_coords_mode(self, mode="auto"):

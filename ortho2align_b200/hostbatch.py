@@ -8,10 +8,11 @@ in the lossless narrow encoding of `include/o2a.h`:
     score_q   int8 / int16 / int32 per HSP   (BLAST raw scores are integers; the most negative value marks an
     exc_*     exception lists                  HSP whose exact float64 score — a cut HSP, alignment.py:330 — is listed)
     bg_q      int8 / int16 / int32 per background score (after the reference's patches, pipeline.py:746-754)
-    coords    int32 [n_hsp, 4] AoS (qstart, qend, sstart, send): only the retained ~1 % is ever read
+    coords    int32 [n_hsp, 4] AoS (qstart, qend, sstart, send): only the retained ~1 % is ever read — by host threads
+              of the library (host-gather mode), so this array stays in ordinary memory unless pin_coords=True
     offsets   bg_off, aln_off, hsp_off, qlen, slen (int64)
 
-`Engine.run_host(hb, params)` passes exactly these pointers to the library: what the ingest returns is what
+`Engine.build_host(hb, ...)` passes exactly these pointers to the library: what the ingest returns is what
 crosses PCIe. Without a CUDA device (`o2a_host_alloc` fails) the same layout lives in ordinary memory — the
 layout is host logic and is tested on CPU; the compute still has no CPU path.
 """
@@ -78,7 +79,7 @@ class HostBatch:
 
     ARRAYS = ("bg_off", "aln_off", "hsp_off", "qlen", "slen", "bg_q", "score_q", "exc_off", "exc_pos", "exc_val", "coords")
 
-    def __init__(self, n_lnc, n_aln, n_hsp, n_bg, score_bits, bg_bits, n_exc, pinned=True, pin_coords=True):
+    def __init__(self, n_lnc, n_aln, n_hsp, n_bg, score_bits, bg_bits, n_exc, pinned=True, pin_coords=False):
         self.n_lnc, self.n_aln, self.n_hsp, self.n_bg = int(n_lnc), int(n_aln), int(n_hsp), int(n_bg)
         self.score_bits, self.bg_bits, self.n_exc = int(score_bits), int(bg_bits), int(n_exc)
         self._blocks = []
@@ -98,7 +99,7 @@ class HostBatch:
         self.exc_pos = self._new(self.n_exc, np.int32, pinned)
         self.exc_val = self._new(self.n_exc, np.float64, pinned)
         self.coords = self._new((self.n_hsp, 4), np.int32, pinned and pin_coords)
-        self.pinned = all(b.pinned for b in self._blocks) if pinned else False
+        self.pinned = all(b.pinned for b in self._blocks[:-1]) if pinned else False      # everything that is uploaded
 
     def _new(self, shape, dtype, pinned):
         n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
@@ -139,7 +140,7 @@ class HostBatch:
         return b
 
     @classmethod
-    def from_columnar(cls, batch: ColumnarBatch, threads=0, pinned=True, score_bits=None, bg_bits=None, pin_coords=True):
+    def from_columnar(cls, batch: ColumnarBatch, threads=0, pinned=True, score_bits=None, bg_bits=None, pin_coords=False):
         """Native multi-threaded packer (`o2a_ingest_pack_narrow`, libo2a_ingest.so). `score_bits` / `bg_bits`: force a
         width (8, 16, 32) instead of the planner's choice; a background that does not fit `bg_bits` is an error."""
         from . import ingest

@@ -62,7 +62,7 @@ class IngestResult:
     batch: the same lncRNAs as a plain ColumnarBatch (built on first use); lnc_file[l]: file index of lncRNA l;
     file_status[i] / errors[i]; score (float64) and score_is_int per HSP; relative per alignment; range dicts on demand."""
 
-    def __init__(self, lib, handle, n_files, pinned=True, pin_coords=True):
+    def __init__(self, lib, handle, n_files, pinned=True, pin_coords=False):
         from .hostbatch import HostBatch
         self._lib, self._h = lib, handle
         sizes = [C.c_int64(0) for _ in range(4)]
@@ -312,7 +312,7 @@ def open_sidecar(path, align_files, bg_files):
     return SidecarResult(path, directory)
 
 
-def load_files(align_files, bg_files, threads=0, pinned=True, pin_coords=True) -> IngestResult:
+def load_files(align_files, bg_files, threads=0, pinned=True, pin_coords=False) -> IngestResult:
     """Parse the file pairs on `threads` native threads. The result's `.host` is the pinned narrow layout
     (`hostbatch.HostBatch`) the CUDA library takes as is; `pinned=False` keeps it in ordinary memory."""
     lib = load_lib()

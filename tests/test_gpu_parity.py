@@ -337,9 +337,13 @@ def test_host_batch_layouts_and_coordinate_modes(engine, monkeypatch, mode, cfg,
     monkeypatch.setenv("O2A_CHUNKS", str(chunks))
     engine.set_coords_mode(mode)
     try:
-        hb = HostBatch.from_columnar(b)
+        hb = HostBatch.from_columnar(b, pin_coords=True)
         got = engine.build_host(hb, "hist", True)
-        assert engine.coords_mode() == (mode if (mode != "zerocopy" or hb.pinned) else "gather")
+        assert engine.coords_mode() == (mode if (mode != "zerocopy" or hb._blocks[-1].pinned) else "gather")
+        engine.set_coords_mode("auto")
+        compare_results(engine.build_host(hb, "hist", True), exp, exact_p=True, what=f"cfg{cfg} auto chunks={chunks}")
+        assert engine.coords_mode() == "gather"
+        engine.set_coords_mode(mode)
         compare_results(got, exp, exact_p=True, what=f"cfg{cfg} {mode} chunks={chunks}")
         # pageable SoA caller arrays (what a plain ColumnarBatch hands over): zero-copy is not possible there
         got = engine.build_batch(b, "hist", True)
