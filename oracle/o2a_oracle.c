@@ -509,7 +509,12 @@ int o2a_oracle_build_batch(
             if (cl > 0) {
                 /* get_best_orthologs key on the QUERY bed12 line (pipeline.py:981-987) */
                 double key;
-                int64_t blen = 0; int32_t lo = INT32_MAX, hi = INT32_MIN; double w = 0.0;
+                int64_t blen = 0; int32_t lo = INT32_MAX, hi = INT32_MIN;
+                /* weight = float(str(sum(scores))) (pipeline.py:986, genomicranges.py:1225) under the pinned interpreter
+                 * (CPython 3.12 bltinmodule.c, builtin_sum): ints are added exactly while every item is an int; from the
+                 * first float on, Neumaier-compensated addition. A score is taken for an int when it is integral (the
+                 * columnar batch does not carry the JSON number type; the sums are equal either way below 2^53). */
+                int64_t isum = 0; int in_int = 1; double fr = 0.0, cc = 0.0;
                 for (int64_t k = 0; k < cl; k++) {
                     int64_t h = h0 + ch[k];
                     int32_t d = qend[h] - qstart[h]; blen += d < 0 ? -d : d;
@@ -517,8 +522,18 @@ int o2a_oracle_build_batch(
                     if (qend[h] < lo) lo = qend[h];
                     if (qstart[h] > hi) hi = qstart[h];
                     if (qend[h] > hi) hi = qend[h];
-                    w = (k == 0) ? (0.0 + score[h]) : w + score[h];   /* sum(): genomicranges.py:1225 */
+                    {
+                        double x = score[h];
+                        if (in_int && x == (double)(int64_t)x && fabs(x) < 9007199254740992.0) isum += (int64_t)x;
+                        else {
+                            if (in_int) { in_int = 0; fr = (double)isum; cc = 0.0; }
+                            double t = fr + x;
+                            if (fabs(fr) >= fabs(x)) cc += (fr - t) + x; else cc += (x - t) + fr;
+                            fr = t;
+                        }
+                    }
                 }
+                double w = in_int ? (double)isum : ((cc != 0.0 && isfinite(cc)) ? fr + cc : fr);
                 if (best_value == 0) key = (double)blen;
                 else if (best_value == 1) key = (double)((int64_t)hi - (int64_t)lo);
                 else if (best_value == 2) key = (double)cl;

@@ -345,8 +345,12 @@ extern "C" int o2a_create(o2a_ctx** out, int device)
     cudaEventCreateWithFlags(&ctx->tail_join, cudaEventDisableTiming);
     cudaHostAlloc((void**)&ctx->h_cursor, 16 * sizeof(long long), cudaHostAllocPortable);
     {
+        // host-gather threads: the box's cores shared among the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
         unsigned hc = std::thread::hardware_concurrency();
-        ctx->gather_threads = hc ? (int)(hc < 16 ? hc : 16) : 4;
+        int share = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) { if (atoi(e) > 1) share = atoi(e); }
+        int nt = hc ? (int)hc / share : 4;
+        ctx->gather_threads = nt < 2 ? 2 : (nt > 16 ? 16 : nt);
         if (const char* e = getenv("O2A_GATHER_THREADS")) { if (atoi(e) > 0) ctx->gather_threads = atoi(e); }
     }
     for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->cut_ev[i]);

@@ -159,21 +159,48 @@ struct ChainArgs {
     int* big_list; int* big_count;     // alignments with > CHAIN_SMALL_MAX retained HSPs (-> k_chain_big)
 };
 
+// Neumaier-compensated running sum, the float branch of CPython >= 3.12's sum() (Python/bltinmodule.c)
+__device__ __forceinline__ void neumaier_add(double& f_result, double& c, double x)
+{
+    const double t = __dadd_rn(f_result, x);
+    if (fabs(f_result) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dsub_rn(f_result, t), x));
+    else c = __dadd_rn(c, __dadd_rn(__dsub_rn(x, t), f_result));
+    f_result = t;
+}
+
+// sum(scores) as the pinned interpreter computes it for the BED score column (genomicranges.py:1225): ints exactly while
+// every item is an int, Neumaier-compensated floats from the first float on. The columnar batch does not carry the JSON
+// number type: an integral score counts as an int (the two sums are equal below 2^53).
+struct PySum {
+    long long isum = 0; bool in_int = true; double fr = 0.0, cc = 0.0;
+    __device__ __forceinline__ void add(double x)
+    {
+        if (in_int && x == (double)(long long)x && fabs(x) < 9007199254740992.0) { isum += (long long)x; return; }
+        if (in_int) { in_int = false; fr = (double)isum; cc = 0.0; }
+        neumaier_add(fr, cc, x);
+    }
+    __device__ __forceinline__ double value() const
+    {
+        if (in_int) return (double)isum;
+        return (cc != 0.0 && cc == cc && fabs(cc) <= 1.79769313486231570815e308) ? __dadd_rn(fr, cc) : fr;
+    }
+};
+
 // key of get_best_orthologs on the QUERY bed12 line (pipeline.py:981-987) for the chosen chain
 __device__ double best_key_of_chain(const ChainArgs& A, long long h0, const int* slots, int len, int which)
 {
-    long long blen = 0; int lo = INT32_MAX, hi = INT32_MIN; double wsum = 0.0;
+    long long blen = 0; int lo = INT32_MAX, hi = INT32_MIN; PySum w;
     for (int c = 0; c < len; ++c) {
         const int4 q = A.ret_coord[h0 + slots[c]];
         int qs = q.x, qe = q.y;
         int d = qe - qs; blen += d < 0 ? -d : d;
         lo = min(lo, min(qs, qe)); hi = max(hi, max(qs, qe));
-        wsum = __dadd_rn(wsum, A.ret_score[h0 + slots[c]]);   // Python sum(): 0 + s0 + s1 + ...
+        if (which == 3) w.add(A.ret_score[h0 + slots[c]]);
     }
     if (which == 0) return (double)blen;
     if (which == 1) return (double)((long long)hi - (long long)lo);
     if (which == 2) return (double)len;
-    return wsum;
+    return w.value();                                  // weight = float(str(sum(scores))), pipeline.py:986
 }
 
 // Alignments the warp path of the chaining cannot take: too many retained HSPs, or sentinels beyond 32 bits
@@ -294,15 +321,6 @@ constexpr int CHAINW_WARPS = 4;
 constexpr int CHAINW_SMEM = 128;          // bytes of shared memory per warp: inverse permutation, two staged chains, flags
 
 struct WarpChainResult { int pick; int len; double sco0, sco1; double key; bool bad; };
-
-// Neumaier-compensated running sum, the float branch of CPython >= 3.12's sum() (Python/bltinmodule.c)
-__device__ __forceinline__ void neumaier_add(double& f_result, double& c, double x)
-{
-    const double t = __dadd_rn(f_result, x);
-    if (fabs(f_result) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dsub_rn(f_result, t), x));
-    else c = __dadd_rn(c, __dadd_rn(__dsub_rn(x, t), f_result));
-    f_result = t;
-}
 
 // All 32 lanes call this. Lane p < r holds the p-th retained HSP (list order); r <= CHAIN_WARP_MAX and qlen, slen fit
 // int32. `sm`: CHAINW_SMEM bytes of shared memory owned by the warp. The chosen chain (retained-list positions, chain
@@ -441,17 +459,10 @@ __device__ __forceinline__ WarpChainResult warp_chain(int r, int qs, int qe, int
         else {
             // weight = float(str(sum(scores))) of the BED score column (genomicranges.py:1225): CPython >= 3.12's sum()
             // adds ints exactly while every item is an int, then switches to Neumaier-compensated float addition
-            long long isum = 0; bool in_int = true; double fr = 0.0, cc = 0.0;
+            PySum w;
 #pragma unroll 1
-            for (int c = 0; c < R.len; ++c) {
-                const double x = __shfl_sync(FULL_MASK, sc, staged[c]);
-                if (in_int && x == (double)(long long)x && fabs(x) < 9007199254740992.0) isum += (long long)x;
-                else {
-                    if (in_int) { in_int = false; fr = (double)isum; cc = 0.0; }
-                    neumaier_add(fr, cc, x);
-                }
-            }
-            R.key = in_int ? (double)isum : (cc != 0.0 && cc == cc && fabs(cc) <= 1.79769313486231570815e308 ? __dadd_rn(fr, cc) : fr);
+            for (int c = 0; c < R.len; ++c) w.add(__shfl_sync(FULL_MASK, sc, staged[c]));
+            R.key = w.value();
         }
     }
     return R;

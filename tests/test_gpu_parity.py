@@ -236,10 +236,17 @@ def test_pinned_host_inputs_use_zero_copy_coordinates(engine):
     hb = ColumnarBatch(**{k: v.numpy() for k, v in pinned.items()})
     c4 = torch.empty((b.n_hsp, 4), dtype=torch.int32, pin_memory=True)
     c4.numpy()[...] = b.coords4()
-    for coords in (None, c4.numpy()):
-        engine.run(engine.host_struct(hb, False, coords=coords), engine.params("hist", True))
-        assert engine.lib.o2a_coords_zero_copy(engine.h) == 1
-        compare_results(engine.fetch(), ref, exact_p=True, what="pinned zero-copy")
+    engine.set_coords_mode("zerocopy")          # AUTO is the host-gather mode since round 2; zero-copy is opt-in
+    try:
+        for coords in (None, c4.numpy()):
+            engine.run(engine.host_struct(hb, False, coords=coords), engine.params("hist", True))
+            assert engine.lib.o2a_coords_zero_copy(engine.h) == 1 and engine.coords_mode() == "zerocopy"
+            compare_results(engine.fetch(), ref, exact_p=True, what="pinned zero-copy")
+    finally:
+        engine.set_coords_mode("auto")
+    engine.run(engine.host_struct(hb, False, coords=c4.numpy()), engine.params("hist", True))
+    assert engine.lib.o2a_coords_zero_copy(engine.h) == 0 and engine.coords_mode() == "gather"
+    compare_results(engine.fetch(), ref, exact_p=True, what="pinned, default mode")
 
 
 @pytest.mark.parametrize("chunks", [2, 3, 16])
