@@ -465,29 +465,56 @@ def stage_files(argv):
     ap.add_argument("--runner", default="gpu", choices=["gpu", "oracle"])
     ap.add_argument("--reference", action="store_true")
     ap.add_argument("--ref-lnc", type=int, default=8)
+    ap.add_argument("--config", type=int, default=2, help="shape of the synthetic lncRNAs (2: 5 regions x ~2k HSPs; 5: genome-scale mix)")
+    ap.add_argument("--tmp", default=None, help="where the JSON directories are written (default: /dev/shm if present)")
     args = ap.parse_args(argv)
+    print(json.dumps(files_to_files(args.config, args.lnc, args.cores, args.runner, args.reference, args.ref_lnc, args.tmp)))
+
+
+def _write_json_block(a):
+    cfg, lo, hi, total, ad, bd = a
+    b, m = synth.workload(cfg, n_lnc=total, with_meta=True, seed=1, lnc_range=(lo, hi))
+    nbytes = 0
+    for name, alns, bg in synth.to_json_dicts(b, m):
+        for d, obj in ((ad, alns), (bd, bg)):
+            p = os.path.join(d, name + ".json")
+            with open(p, "w") as f:
+                json.dump(obj, f)
+            nbytes += os.path.getsize(p)
+    return b.n_hsp, nbytes
+
+
+def files_to_files(config, n_lnc, cores=0, runner="gpu", reference=False, ref_lnc=8, tmp_root=None):
+    """Directories of the reference's JSON files -> the 7 + 4 output files through the drop-in build_orthologs +
+    get_best_orthologs (cold: native JSON parse; warm: columnar sidecar). Returns the report dict."""
     import tempfile
-    from ortho2align_b200 import pipeline, synth
-    cores = args.cores or len(os.sched_getaffinity(0))
+    from ortho2align_b200 import pipeline
+    cores = cores or len(os.sched_getaffinity(0))
+    args = argparse.Namespace(lnc=n_lnc, runner=runner, reference=reference, ref_lnc=ref_lnc)
+    if tmp_root is None and os.path.isdir("/dev/shm"):
+        tmp_root = "/dev/shm"
     if args.runner == "oracle":
         from oracle import oracle as O
         pipeline._run_shards = lambda batches, devices, fitter, fdr, alpha, go, ge: [
             O.build_batch(b.to_columnar() if hasattr(b, "to_columnar") else b, fitter, fdr, alpha, go, ge) for b in batches]
-    b, m = synth.workload(2, n_lnc=args.lnc, with_meta=True, seed=1)
-    items = synth.to_json_dicts(b, m)
-    out = {"lncRNAs": args.lnc, "hsps": b.n_hsp, "cores": cores, "runner": args.runner}
-    with tempfile.TemporaryDirectory(prefix="o2a_e2e_") as tmp:
+    out = {"workload": CONFIG_NAMES[config], "lncRNAs": args.lnc, "cores": cores, "runner": args.runner}
+    with tempfile.TemporaryDirectory(prefix="o2a_e2e_", dir=tmp_root) as tmp:
         ad, bd = os.path.join(tmp, "align"), os.path.join(tmp, "bg")
         os.makedirs(ad), os.makedirs(bd)
-        nbytes = 0
-        for name, alns, bg in items:
-            for d, obj in ((ad, alns), (bd, bg)):
-                p = os.path.join(d, name + ".json")
-                with open(p, "w") as f:
-                    json.dump(obj, f)
-                nbytes += os.path.getsize(p)
-        out["json_mb"] = round(nbytes / 1e6, 1)
-        del items
+        t0 = time.perf_counter()
+        step = 64 if config != 1 else 1
+        spans = [(config, lo, min(lo + step, args.lnc), args.lnc, ad, bd) for lo in range(0, args.lnc, step)]
+        if cores > 1 and len(spans) > 1:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(min(cores, 32)) as pool:
+                parts = pool.map(_write_json_block, spans)
+        else:
+            parts = [_write_json_block(sp) for sp in spans]
+        n_hsp = sum(p[0] for p in parts)
+        out["hsps"] = n_hsp
+        out["json_mb"] = round(sum(p[1] for p in parts) / 1e6, 1)
+        out["write_json_s"] = round(time.perf_counter() - t0, 2)
+        b = argparse.Namespace(n_hsp=n_hsp)
 
         def run(tag, **kw):
             od = os.path.join(tmp, "out_" + tag)
@@ -525,7 +552,7 @@ def stage_files(argv):
                 rh.run_reference_build(sub_a, sub_b, os.path.join(tmp, "ref_out"), fitting="hist", fdr=True, cores=1, pool="serial")
                 dt = time.perf_counter() - t0
                 out["reference_1_core"] = {"lncRNAs": len(names), "hsps": h, "seconds": dt, "hsps_per_s": h / dt}
-    print(json.dumps(out))
+    return out
 
 
 

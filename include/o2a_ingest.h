@@ -78,6 +78,14 @@ int o2a_ingest_pack_narrow(int64_t n_aln, const int64_t *hsp_off, const double *
  * and, when blob != NULL and cap is large enough, the concatenated bytes. Returns the total size. */
 int64_t o2a_ingest_range_texts(const o2a_ingest *g, int64_t *range_off, char *blob, int64_t cap);
 
+/* What the record formatter (o2a_records.h) needs from the range objects, decoded natively: per alignment the three
+ * strings str(qrange.chrom), str(qrange.name) (with GenomicRange.name's fall-back to "chrom:start-endstrand",
+ * genomicranges.py:427-433) and str(srange.chrom) as name_off[3*n_aln+1] offsets into blob (UTF-8), q_plus[n_aln] =
+ * qrange.strand in ('+', '.') (nxor_strands' test, alignment.py:48-64), simple[n_aln] = 1 when every value was a JSON
+ * string / null / int as json.dump writes them (0: decode the object with a full JSON reader). Returns the blob size. */
+int64_t o2a_ingest_range_fields(const o2a_ingest *g, int64_t *name_off, char *blob, int64_t cap, uint8_t *q_plus,
+                                uint8_t *simple);
+
 /* The JSON text of a qrange / srange object of `file` (span from o2a_ingest_export): returns its
  * length; copies it when out != NULL and cap is large enough. */
 int64_t o2a_ingest_span(const o2a_ingest *g, int64_t file, int64_t begin, int64_t end, char *out, int64_t cap);

@@ -39,6 +39,21 @@ void o2a_records_free(char *p);
 /* repr(float) of one value into buf (at least 32 bytes); returns its length. Exposed for the tests. */
 int o2a_records_repr_double(double x, char *buf);
 
+/*
+ * get_best_orthologs on files (pipeline.py:959-1024): the four significant.* files are read in lock-step, consecutive
+ * records with the same query name (column 4 of the query BED12 line) form a group, and the FIRST record with the
+ * maximal / minimal key(query BED12 line) of each group is written to the four output files.
+ *   value    0 block_length  = sum(int(i) for i in col11.split(','))     1 total_length = int(col3) - int(col2)
+ *            2 block_count   = int(col10)                                3 weight       = float(col5)
+ *   function 0 max, 1 min
+ * Returns 0; -1 on an I/O error; 1 when the input holds anything Python would treat differently from this reader
+ * (carriage returns, short records, numbers that are not plain decimal literals, NaN): nothing has been written then and
+ * the caller runs the text-level restatement, which raises or decides exactly like the reference.
+ */
+int o2a_best_orthologs_files(const char *q_bed, const char *q_tsv, const char *s_bed, const char *s_tsv,
+                             int value, int function, const char *out_q_bed, const char *out_q_tsv,
+                             const char *out_s_bed, const char *out_s_tsv, int64_t *n_records, int64_t *n_groups);
+
 #ifdef __cplusplus
 }
 #endif

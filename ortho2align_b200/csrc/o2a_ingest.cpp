@@ -51,6 +51,12 @@ struct FileResult {
     std::vector<uint8_t> score_is_int;
     std::vector<int32_t> bg;
     std::vector<uint8_t> relative;  // per alignment: the 'relative' flag is truthy (to_record raises, genomicranges.py:1259)
+    // per alignment, for the record formatter: str(qrange.chrom), str(qrange.name), str(srange.chrom) back to back in
+    // `names` (offsets 3 per alignment + 1), qrange.strand in ('+', '.'), and whether these were plain JSON strings /
+    // nulls / ints (else the host decodes the range object itself)
+    std::string names;
+    std::vector<int64_t> name_off;
+    std::vector<uint8_t> q_plus, simple;
     // HSPs of the file whose score does not fit the lossless int8 / int16 / int32 encodings of include/o2a.h
     int64_t misfit[3] = {0, 0, 0};
     int32_t bg_min = 0, bg_max = 0;
@@ -196,6 +202,88 @@ bool MappedFile::open_file(const char* path, std::string& fallback, const char*&
 
 // which narrow encodings cannot hold score `sc` (bit 0: int8, bit 1: int16, bit 2: int32): o2a_pack.h
 using o2a_pack::narrow_misfit;
+
+
+// JSON string contents [b, e) -> UTF-8 (json.dump writes non-ASCII as \uXXXX). Returns false on a malformed escape.
+bool json_unescape(const char* b, const char* e, std::string& out)
+{
+    auto hex4 = [](const char* p, unsigned& v) {
+        v = 0;
+        for (int k = 0; k < 4; ++k) {
+            const char c = p[k]; unsigned d;
+            if (c >= '0' && c <= '9') d = (unsigned)(c - '0'); else if (c >= 'a' && c <= 'f') d = (unsigned)(c - 'a' + 10);
+            else if (c >= 'A' && c <= 'F') d = (unsigned)(c - 'A' + 10); else return false;
+            v = v * 16 + d;
+        }
+        return true;
+    };
+    auto utf8 = [&](unsigned cp) {
+        if (cp < 0x80) out.push_back((char)cp);
+        else if (cp < 0x800) { out.push_back((char)(0xC0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+        else if (cp < 0x10000) { out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+        else { out.push_back((char)(0xF0 | (cp >> 18))); out.push_back((char)(0x80 | ((cp >> 12) & 0x3F))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+    };
+    for (const char* p = b; p < e; ++p) {
+        if (*p != '\\') { out.push_back(*p); continue; }
+        if (++p >= e) return false;
+        switch (*p) {
+            case '"': out.push_back('"'); break; case '\\': out.push_back('\\'); break; case '/': out.push_back('/'); break;
+            case 'b': out.push_back('\b'); break; case 'f': out.push_back('\f'); break; case 'n': out.push_back('\n'); break;
+            case 'r': out.push_back('\r'); break; case 't': out.push_back('\t'); break;
+            case 'u': {
+                unsigned cp;
+                if (e - p < 5 || !hex4(p + 1, cp)) return false;
+                p += 4;
+                if (cp >= 0xD800 && cp < 0xDC00) {                       // surrogate pair
+                    unsigned lo;
+                    if (e - p < 7 || p[1] != '\\' || p[2] != 'u' || !hex4(p + 3, lo) || lo < 0xDC00 || lo > 0xDFFF) return false;
+                    cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                    p += 6;
+                } else if (cp >= 0xDC00 && cp <= 0xDFFF) return false;   // lone surrogate: Python keeps it, UTF-8 cannot
+                utf8(cp);
+                break;
+            }
+            default: return false;
+        }
+    }
+    return true;
+}
+
+// What the record formatter needs from a qrange / srange object (GenomicRange.from_dict, genomicranges.py:816-855):
+// str(chrom), the strand, and str(name) with the reference's fall-back to "chrom:start-endstrand" for a null name
+// (genomicranges.py:427-433). ok = false: a value has a JSON type this reader does not render (numbers as chrom / name,
+// nested values, lone surrogates): the host then decodes the object with Python's json.
+struct RangeMini { std::string chrom, name, strand; bool ok = true; };
+
+void extract_range(const char* b, const char* e, RangeMini& out)
+{
+    Parser P{b, b, e, {}};
+    bool have_chrom = false, have_name = false, name_null = false, have_strand = false, have_s = false, have_e = false;
+    int64_t start = 0, end = 0;
+    auto text_value = [&](std::string& dst, bool* is_null) -> bool {       // string or null
+        P.ws();
+        if (P.p < P.end && *P.p == '"') { const char *sb, *se; return P.str(sb, se) && json_unescape(sb, se, dst); }
+        if (P.p + 4 <= P.end && !memcmp(P.p, "null", 4)) { P.p += 4; if (is_null) *is_null = true; else dst = "None"; return true; }
+        return false;
+    };
+    if (!P.expect('{')) { out.ok = false; return; }
+    if (!P.lit('}')) {
+        do {
+            const char *kb, *ke;
+            if (!P.str(kb, ke) || !P.expect(':')) { out.ok = false; return; }
+            if (key_is(kb, ke, "chrom")) { if (!text_value(out.chrom, nullptr)) { out.ok = false; return; } have_chrom = true; }
+            else if (key_is(kb, ke, "name")) { if (!text_value(out.name, &name_null)) { out.ok = false; return; } have_name = true; }
+            else if (key_is(kb, ke, "strand")) { if (!text_value(out.strand, nullptr)) { out.ok = false; return; } have_strand = true; }
+            else if (key_is(kb, ke, "start") || key_is(kb, ke, "end")) {
+                int kind; int64_t iv; double dv;
+                if (!P.num(kind, iv, dv) || kind != 1) { out.ok = false; return; }
+                if (kb[0] == 's') { start = iv; have_s = true; } else { end = iv; have_e = true; }
+            } else if (!P.skip()) { out.ok = false; return; }
+        } while (P.lit(','));
+    }
+    if (!(have_chrom && have_name && have_strand && have_s && have_e)) { out.ok = false; return; }
+    if (name_null) out.name = out.chrom + ":" + std::to_string(start) + "-" + std::to_string(end) + out.strand;
+}
 
 // Fast path for the text json.dump writes for one HSP (alignment.py:233-249 -> to_dict):
 //   {"qstart": I, "qend": I, "sstart": I, "send": I, "score": N, "pval": null, "kwargs": {}}
@@ -355,6 +443,29 @@ void parse_alignment_file(FileResult& R) {
             R.slen.push_back(hs ? sl : (cnt ? msub : 0) + 1);            // alignment.py:481-487
             R.qr_begin.push_back(qb); R.qr_end.push_back(qe); R.sr_begin.push_back(sb); R.sr_end.push_back(se);
             R.relative.push_back(rel ? 1 : 0);
+            {
+                RangeMini q, sr;
+                // consecutive alignments of a lncRNA repeat the same qrange text: decode it once
+                const size_t na = R.qr_begin.size();
+                const bool same_q = na >= 2 && (qe - qb) == (R.qr_end[na - 2] - R.qr_begin[na - 2]) &&
+                                    !memcmp(R.meta.data() + qb, R.meta.data() + R.qr_begin[na - 2], (size_t)(qe - qb));
+                if (R.name_off.empty()) R.name_off.push_back(0);
+                if (same_q) {
+                    const size_t o = R.name_off.size() - 4;       // previous alignment's three strings
+                    const std::string qc = R.names.substr((size_t)R.name_off[o], (size_t)(R.name_off[o + 1] - R.name_off[o]));
+                    const std::string qn = R.names.substr((size_t)R.name_off[o + 1], (size_t)(R.name_off[o + 2] - R.name_off[o + 1]));
+                    q.chrom = qc; q.name = qn; q.ok = R.simple.back() & 1;
+                    R.q_plus.push_back(R.q_plus.back());
+                } else {
+                    extract_range(R.meta.data() + qb, R.meta.data() + qe, q);
+                    R.q_plus.push_back((q.strand == "+" || q.strand == ".") ? 1 : 0);
+                }
+                extract_range(R.meta.data() + sb, R.meta.data() + se, sr);
+                R.names += q.chrom; R.name_off.push_back((int64_t)R.names.size());
+                R.names += q.name; R.name_off.push_back((int64_t)R.names.size());
+                R.names += sr.chrom; R.name_off.push_back((int64_t)R.names.size());
+                R.simple.push_back((q.ok ? 1 : 0) | (sr.ok ? 2 : 0));
+            }
         } while (P.lit(','));
         if (P.err.empty()) P.expect(']');
     }
@@ -581,6 +692,30 @@ extern "C" int64_t o2a_ingest_span(const o2a_ingest* g, int64_t file, int64_t be
     int64_t n = end - begin;
     if (out && cap >= n) memcpy(out, t.data() + begin, (size_t)n);
     return n;
+}
+
+// str(qrange.chrom), str(qrange.name), str(srange.chrom) of every alignment (3 strings each, UTF-8) as offsets
+// name_off[3*n_aln+1] into `blob`; q_plus[n_aln] = qrange.strand in ('+', '.'); simple[n_aln] = 1 when all three could be
+// rendered natively (else the host decodes the range objects with Python's json). Returns the blob size.
+extern "C" int64_t o2a_ingest_range_fields(const o2a_ingest* g, int64_t* name_off, char* blob, int64_t cap, uint8_t* q_plus,
+                                           uint8_t* simple)
+{
+    if (!g) return -1;
+    int64_t pos = 0, a = 0;
+    if (name_off) name_off[0] = 0;
+    for (const FileResult& R : g->files) {
+        if (R.status) continue;
+        const size_t na = R.hsp_count.size();
+        if (blob && pos + (int64_t)R.names.size() <= cap) memcpy(blob + pos, R.names.data(), R.names.size());
+        for (size_t k = 0; k < na; ++k) {
+            if (name_off) for (int t = 1; t <= 3; ++t) name_off[3 * (a + (int64_t)k) + t] = pos + R.name_off[3 * k + (size_t)t];
+            if (q_plus) q_plus[a + (int64_t)k] = R.q_plus[k];
+            if (simple) simple[a + (int64_t)k] = R.simple[k] == 3 ? 1 : 0;
+        }
+        pos += (int64_t)R.names.size();
+        a += (int64_t)na;
+    }
+    return pos;
 }
 
 // All qrange / srange texts of the batch at once (alignment order: q0, s0, q1, s1, ...): range_off[2*n_aln+1] and,

@@ -179,3 +179,150 @@ extern "C" int o2a_records_format(const o2a_records_input* in, int n_threads, ch
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// get_best_orthologs on files (pipeline.py:959-1024): the four significant.* files are read in lock-step, CONSECUTIVE
+// records with the same query name (column 4 of the query BED12 line) form a group, and max() / min() over
+// key(query BED12 line) keeps the FIRST extremal record of each group:
+//   total_length = int(col3) - int(col2)   block_count = int(col10)   block_length = sum(int(i) for i in col11.split(','))
+//   weight = float(col5)
+// Anything Python would treat differently from this reader — '\r', a record with fewer columns, a number that is not a
+// plain decimal literal, NaN keys, integers beyond int64 — returns 1: the caller then runs the text-level Python
+// restatement, which raises or decides exactly like the reference.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+bool slurp(const char* path, std::string& out)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize((size_t)(n > 0 ? n : 0));
+    size_t got = n > 0 ? fread(&out[0], 1, (size_t)n, f) : 0;
+    fclose(f);
+    return got == out.size();
+}
+
+struct LineIter {
+    const char* p; const char* end;
+    bool next(const char*& b, const char*& e) {              // [b, e) includes the '\n' when there is one
+        if (p >= end) return false;
+        b = p;
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        e = nl ? nl + 1 : end;
+        p = e;
+        return true;
+    }
+};
+
+inline bool is_py_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
+
+// field `idx` (0-based) of line.strip().split('\t'); false if the record has fewer fields
+bool field(const char* b, const char* e, int idx, const char*& fb, const char*& fe)
+{
+    while (b < e && is_py_space(*b)) ++b;
+    while (e > b && is_py_space(e[-1])) --e;
+    const char* s = b;
+    for (int k = 0;; ++k) {
+        const char* t = (const char*)memchr(s, '\t', (size_t)(e - s));
+        const char* stop = t ? t : e;
+        if (k == idx) { fb = s; fe = stop; return true; }
+        if (!t) return false;
+        s = t + 1;
+    }
+}
+
+bool parse_i64(const char* b, const char* e, long long& v)   // int(): plain optional sign + digits only (else: fallback)
+{
+    if (b >= e) return false;
+    const char* s = b;
+    if (*s == '+' ) ++s;
+    auto r = std::from_chars(s, e, v);
+    return s < e && r.ec == std::errc() && r.ptr == e && (*s == '-' || (*s >= '0' && *s <= '9'));
+}
+
+}  // namespace
+
+extern "C" int o2a_best_orthologs_files(const char* q_bed, const char* q_tsv, const char* s_bed, const char* s_tsv,
+                                        int value, int function, const char* out_q_bed, const char* out_q_tsv,
+                                        const char* out_s_bed, const char* out_s_tsv, int64_t* n_records, int64_t* n_groups)
+{
+    if (value < 0 || value > 3 || function < 0 || function > 1) return -1;
+    std::string in[4];
+    const char* paths[4] = {q_bed, q_tsv, s_bed, s_tsv};
+    for (int k = 0; k < 4; ++k) {
+        if (!paths[k] || !slurp(paths[k], in[k])) return -1;
+        if (memchr(in[k].data(), '\r', in[k].size())) return 1;          // universal newlines would rewrite the records
+    }
+    LineIter it[4];
+    for (int k = 0; k < 4; ++k) it[k] = {in[k].data(), in[k].data() + in[k].size()};
+    std::string out[4];
+    for (int k = 0; k < 4; ++k) out[k].reserve(in[k].size() / 2 + 64);
+    const char *lb[4], *le[4];               // current record
+    const char *bb[4] = {nullptr, nullptr, nullptr, nullptr}, *be[4] = {nullptr, nullptr, nullptr, nullptr};   // best of the group
+    const char *gname_b = nullptr, *gname_e = nullptr;
+    bool have = false;
+    long long best_i = 0; double best_d = 0.0;
+    int64_t nrec = 0, ngrp = 0;
+    auto flush = [&]() { for (int k = 0; k < 4; ++k) out[k].append(bb[k], (size_t)(be[k] - bb[k])); ++ngrp; };
+    for (;;) {
+        bool all = true;
+        for (int k = 0; k < 4; ++k) all = it[k].next(lb[k], le[k]) && all;   // zip(): stops at the shortest file
+        if (!all) break;
+        ++nrec;
+        const char *nb, *ne;
+        if (!field(lb[0], le[0], 3, nb, ne)) return 1;
+        // key of this record
+        long long ki = 0; double kd = 0.0;
+        const char *fb, *fe;
+        if (value == 1) {                    // total_length
+            long long a, b2;
+            if (!field(lb[0], le[0], 2, fb, fe) || !parse_i64(fb, fe, a)) return 1;
+            if (!field(lb[0], le[0], 1, fb, fe) || !parse_i64(fb, fe, b2)) return 1;
+            if (__builtin_sub_overflow(a, b2, &ki)) return 1;
+        } else if (value == 2) {             // block_count
+            if (!field(lb[0], le[0], 9, fb, fe) || !parse_i64(fb, fe, ki)) return 1;
+        } else if (value == 0) {             // block_length
+            if (!field(lb[0], le[0], 10, fb, fe)) return 1;
+            const char* s = fb;
+            for (;;) {
+                const char* c = (const char*)memchr(s, ',', (size_t)(fe - s));
+                long long v;
+                if (!parse_i64(s, c ? c : fe, v) || __builtin_add_overflow(ki, v, &ki)) return 1;
+                if (!c) break;
+                s = c + 1;
+            }
+        } else {                             // weight: float(col5)
+            if (!field(lb[0], le[0], 4, fb, fe) || fb >= fe) return 1;
+            for (const char* c = fb; c < fe; ++c)
+                if (!((*c >= '0' && *c <= '9') || *c == '.' || *c == 'e' || *c == 'E' || *c == '-' || *c == '+')) return 1;   // inf, nan, '_' ...
+            const char* s = *fb == '+' ? fb + 1 : fb;
+            auto r = std::from_chars(s, fe, kd);
+            if (r.ec != std::errc() || r.ptr != fe || kd != kd) return 1;
+        }
+        const bool same = have && (size_t)(ne - nb) == (size_t)(gname_e - gname_b) && !memcmp(nb, gname_b, (size_t)(ne - nb));
+        if (have && !same) { flush(); have = false; }
+        bool take;
+        if (!have) take = true;
+        else if (value == 3) take = function == 0 ? kd > best_d : kd < best_d;       // strict: the first extremal record wins
+        else take = function == 0 ? ki > best_i : ki < best_i;
+        if (take) { for (int k = 0; k < 4; ++k) { bb[k] = lb[k]; be[k] = le[k]; } best_i = ki; best_d = kd; }
+        // the reference compares the name with the LAST record of the group (purge[-1]): all of them carry the same name
+        gname_b = nb; gname_e = ne;
+        have = true;
+    }
+    if (have) flush();
+    const char* outs[4] = {out_q_bed, out_q_tsv, out_s_bed, out_s_tsv};
+    for (int k = 0; k < 4; ++k) {
+        FILE* f = fopen(outs[k], "wb");
+        if (!f) return -1;
+        const size_t w = out[k].empty() ? 0 : fwrite(out[k].data(), 1, out[k].size(), f);
+        fclose(f);
+        if (w != out[k].size()) return -1;
+    }
+    if (n_records) *n_records = nrec;
+    if (n_groups) *n_groups = ngrp;
+    return 0;
+}

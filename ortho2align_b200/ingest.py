@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libo2a_ingest.so")
 EXPORTS = ["o2a_ingest_create", "o2a_ingest_destroy", "o2a_ingest_load", "o2a_ingest_sizes",
            "o2a_ingest_export", "o2a_ingest_span", "o2a_ingest_file_error",
            "o2a_ingest_narrow_plan", "o2a_ingest_export_narrow", "o2a_ingest_pack_plan", "o2a_ingest_pack_narrow",
-           "o2a_ingest_range_texts"]
+           "o2a_ingest_range_texts", "o2a_ingest_range_fields"]
 _lib = None
 
 
@@ -49,6 +49,8 @@ def load_lib():
         lib.o2a_ingest_pack_narrow.argtypes = [i64, P, P, C.c_int32, P, P, P, P, P, i64, C.c_int32, P, P, P, P, P, P, C.c_int]
         lib.o2a_ingest_range_texts.restype = i64
         lib.o2a_ingest_range_texts.argtypes = [P, P, P, i64]
+        lib.o2a_ingest_range_fields.restype = i64
+        lib.o2a_ingest_range_fields.argtypes = [P, P, P, i64, P, P]
         lib.o2a_ingest_span.restype = i64
         lib.o2a_ingest_span.argtypes = [P, i64, i64, i64, P, i64]
         lib.o2a_ingest_file_error.restype = C.c_char_p
@@ -86,6 +88,7 @@ class IngestResult:
             raise RuntimeError("o2a_ingest_export_narrow failed")
         self.host = hb.finish()
         self._batch = None
+        self._fields = None
         self._range_off = self._range_blob = None
         self.errors = {i: lib.o2a_ingest_file_error(handle, i).decode() for i in np.nonzero(self.file_status)[0]}
 
@@ -121,6 +124,21 @@ class IngestResult:
             self._range_off, self._range_blob = off, blob[:total]
         return self._range_off, self._range_blob
 
+    def range_fields(self):
+        """(name_off[3*n_aln+1], blob, q_plus[n_aln], simple[n_aln]): per alignment str(qrange.chrom), str(qrange.name),
+        str(srange.chrom) as UTF-8 slices of `blob`, qrange.strand in ('+', '.'), and whether the native reader could
+        render all three (o2a_ingest_range_fields) — what the record formatter needs, without a JSON decode in Python."""
+        if self._fields is None:
+            n_aln = self.host.n_aln
+            off = np.zeros(3 * n_aln + 1, dtype=np.int64)
+            qp, simple = np.zeros(n_aln, dtype=np.uint8), np.zeros(n_aln, dtype=np.uint8)
+            p = lambda a: a.ctypes.data_as(C.c_void_p)
+            total = int(self._lib.o2a_ingest_range_fields(self._h, p(off), None, 0, p(qp), p(simple)))
+            blob = np.zeros(max(total, 1), dtype=np.uint8)
+            self._lib.o2a_ingest_range_fields(self._h, p(off), p(blob), total, p(qp), p(simple))
+            self._fields = (off, blob[:total], qp, simple)
+        return self._fields
+
     def range_dict(self, a, which):
         """Decoded qrange ('q') or srange ('s') dict of global alignment index `a`. Consecutive alignments of
         a lncRNA carry the same qrange text: the same dict object is returned for identical text."""
@@ -141,6 +159,7 @@ class IngestResult:
     def close(self):
         if self._h:
             self._ranges()                 # the texts outlive the native handle
+            self.range_fields()
             self._lib.o2a_ingest_destroy(self._h)
             self._h = None
 
@@ -189,7 +208,7 @@ def _hsp_dict(b, score_is_int, h):
 # straight into pinned buffers) without any parsing.
 # --------------------------------------------------------------------------------------------------
 SIDECAR_MAGIC = b"O2ACOL01"
-SIDECAR_VERSION = 2
+SIDECAR_VERSION = 3
 _SIDECAR_ALIGN = 4096
 _SIDECAR_ARRAYS = ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score")
 
@@ -215,6 +234,9 @@ def save_sidecar(path, r, align_files, bg_files):
     sections["lnc_file"] = np.ascontiguousarray(r.lnc_file)
     sections["range_off"] = np.ascontiguousarray(range_off)
     sections["range_text"] = np.ascontiguousarray(range_blob)
+    name_off, name_blob, q_plus, simple = r.range_fields()
+    sections["name_off"], sections["name_blob"] = np.ascontiguousarray(name_off), np.ascontiguousarray(name_blob)
+    sections["q_plus"], sections["simple"] = np.ascontiguousarray(q_plus), np.ascontiguousarray(simple)
     directory = {"version": SIDECAR_VERSION, "n_files": len(align_files), "manifest": _manifest(align_files, bg_files), "sections": {}}
     # two passes: the directory's own length decides where the first section starts
     def layout(base):
@@ -257,6 +279,7 @@ class SidecarResult:
         self.score = self.batch.score
         self.lnc_file = arr("lnc_file")
         self._range_off, self._range_text = arr("range_off"), arr("range_text")
+        self._fields = (arr("name_off"), arr("name_blob"), arr("q_plus"), arr("simple"))
         self._host = None
         self.file_status = np.zeros(directory["n_files"], dtype=np.int32)
         self.errors = {}
@@ -279,6 +302,9 @@ class SidecarResult:
 
     def _ranges(self):
         return self._range_off, self._range_text
+
+    def range_fields(self):
+        return self._fields
 
     def range_text(self, a, which):
         k = 2 * a + (0 if which == "q" else 1)

@@ -95,7 +95,9 @@ def _ingest_native(alignments_files, bg_files, threads, cache=None):
     if r is None:
         r = native.load_files(alignments_files, bg_files, threads=threads or 1)
         if cache and not r.file_status.any():
+            t0 = time.perf_counter()
             native.save_sidecar(cache, r, alignments_files, bg_files)
+            PHASES["sidecar_write"] = time.perf_counter() - t0
     out = [None] * len(alignments_files)
     for i in np.nonzero(r.file_status)[0]:
         if r.file_status[i] == 1:
@@ -182,6 +184,73 @@ def _format_chains_native(chain_desc, strings, qplus, src, threads):
                                          pval, np.asarray(qplus, dtype=np.uint8), strings, threads=threads or 1)
 
 
+def _assemble_columnar(r, res, loaded_errors, n_files, threads):
+    """The records of a whole run from columnar data, without a Python object per alignment: the native ingest's range
+    fields (`IngestResult.range_fields`) + the batch result -> (native_text, dist_found, dropped (query Range, [subject
+    Ranges]) list, exceptions in file order), or None when some range object needs a full JSON decode (the caller then
+    takes the per-alignment path). `r`: IngestResult / SidecarResult whose `.host` batch is what `res` was computed on;
+    `loaded_errors`: {file index: ExceptionLogger} of the files that did not load."""
+    from . import records_native
+    if not hasattr(r, "range_fields"):
+        return None
+    name_off, blob, q_plus, simple = r.range_fields()
+    b = r.host
+    n_lnc, n_aln = b.n_lnc, b.n_aln
+    aln_off = np.asarray(b.aln_off)
+    lnc_of_aln = np.repeat(np.arange(n_lnc), np.diff(aln_off))
+    ok_lnc = np.asarray(res.status) == STATUS_OK
+    chain_off = np.asarray(res.chain_off)
+    has_chain = (np.diff(chain_off) > 0) & (np.asarray(r.relative) == 0) & ok_lnc[lnc_of_aln]     # relative: to_record raises
+    csum = np.concatenate([[0], np.cumsum(has_chain)])
+    n_orth = csum[aln_off[1:]] - csum[aln_off[:-1]]
+    A = np.nonzero(has_chain)[0]
+    if len(A) and not simple[A].all():
+        return None
+    native_text = None
+    if len(A):
+        c0, c1 = chain_off[A], chain_off[A + 1]
+        lens = c1 - c0
+        hsp_off = np.zeros(len(A) + 1, dtype=np.int64)
+        np.cumsum(lens, out=hsp_off[1:])
+        within = np.arange(int(hsp_off[-1]), dtype=np.int64) - np.repeat(hsp_off[:-1], lens)
+        src_pos = np.repeat(c0, lens) + within
+        gidx = np.asarray(res.chain_idx)[src_pos].astype(np.int64) + np.repeat(np.asarray(b.hsp_off)[A], lens)
+        pval = np.asarray(res.chain_pq)[src_pos]
+        # the three strings of every chain, re-packed back to back
+        k3 = (3 * A[:, None] + np.arange(3)[None, :]).reshape(-1)
+        s_len = name_off[k3 + 1] - name_off[k3]
+        str_off = np.zeros(len(k3) + 1, dtype=np.int64)
+        np.cumsum(s_len, out=str_off[1:])
+        sblob = blob[np.repeat(name_off[k3] - str_off[:-1], s_len) + np.arange(int(str_off[-1]), dtype=np.int64)] \
+            if int(str_off[-1]) else np.zeros(0, dtype=np.uint8)
+        *cols, score = r.gather_hsps(gidx)
+        native_text = records_native.format_records(hsp_off, *cols, score, np.asarray(r.score_is_int)[gidx], pval,
+                                                    q_plus[A], (str_off, sblob), threads=threads or 1)
+    # what needs Python objects: lncRNAs without any ortholog (dropped) and lncRNAs the reference would have aborted
+    exceptions = dict(loaded_errors)
+    lnc_file = np.asarray(r.lnc_file)
+    for l in np.nonzero(~ok_lnc)[0].tolist():
+        st = int(res.status[l])
+        err = KeyError(None) if st == 1 else (RuntimeError if st == 2 else ValueError)(_STATUS_TEXT.get(st, st))
+        a0, a1 = int(aln_off[l]), int(aln_off[l + 1])
+        exceptions[int(lnc_file[l])] = ExceptionLogger(err, Range.from_dict(r.range_dict(a0, "q")) if a1 > a0 else None)
+    dropped = []
+    for l in np.nonzero(ok_lnc & (n_orth == 0))[0].tolist():
+        a0, a1 = int(aln_off[l]), int(aln_off[l + 1])
+        q_dropped, s_dropped, last_qd, qrange = None, [], None, None
+        for a in range(a0, a1):                              # pipeline.py:789-791, per alignment
+            qd = r.range_dict(a, "q")
+            if qd is not last_qd:
+                last_qd, qrange = qd, Range.from_dict(qd)
+            srange = Range.from_dict(r.range_dict(a, "s"))
+            srange.name = qrange.name
+            q_dropped = qrange
+            s_dropped.append(srange)
+        dropped.append((q_dropped, s_dropped))
+    dist_found = n_orth[ok_lnc].tolist()
+    return native_text, dist_found, dropped, [exceptions[i] for i in sorted(exceptions)]
+
+
 def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gapopen=5, gapextend=2,
                     fdr=False, cores=1, timeout=None, silent=False, stats_filename=None, devices=None,
                     ingest="native", cache=None, records="native"):
@@ -217,7 +286,7 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
         else _ingest_json(alignments_files, bg_files)
     ok_idx = [i for i, x in enumerate(loaded) if not isinstance(x, ExceptionLogger)]
 
-    PHASES["ingest"] = time.perf_counter() - t_phase
+    PHASES["ingest"] = time.perf_counter() - t_phase - PHASES.get("sidecar_write", 0.0)
     t_phase = time.perf_counter()
     # ---- compute: shard by lncRNA across GPUs, one batched call each ---------------------------------
     per_lnc = {}
@@ -246,7 +315,15 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     PHASES["compute"] = time.perf_counter() - t_phase
     t_phase = time.perf_counter()
     # ---- assemble exactly what the pool would have returned ---------------------------------------------
+    fast = None
+    if ingest == "native" and records == "native" and ok_idx and len(batches) == 1 and batches[0] is loaded[ok_idx[0]][0]:
+        r_src = loaded[ok_idx[0]][6][0]
+        fast = _assemble_columnar(r_src, results[0], {i: x for i, x in enumerate(loaded) if isinstance(x, ExceptionLogger)},
+                                  len(loaded), cores)
     orthologs, exceptions = [], []
+    if fast is not None:
+        native_text_fast, dist_found_fast, dropped_fast, exceptions = fast
+        loaded = []                                                   # nothing left for the per-alignment path
     # native record formatting: per chain (result object, chain slice, first HSP of its alignment in the source batch)
     chain_desc, chain_strings, chain_qplus, chain_src = [], [], [], None
     for i, item in enumerate(loaded):
@@ -306,6 +383,10 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
 
     dist_found = [len(group[0]) for group in orthologs]
     native_text = _format_chains_native(chain_desc, chain_strings, chain_qplus, chain_src, cores) if chain_desc else None
+    if fast is not None:
+        dist_found = dist_found_fast
+        native_text = native_text_fast if native_text_fast is not None else (b"", b"", b"", b"")
+        orthologs = [([], [], [qd, sds]) for qd, sds in dropped_fast]
     if native_text is None:
         query_orthologs_bed12 = [o[1] for g in orthologs for o in g[0]]
         subject_orthologs_bed12 = [o[1] for g in orthologs for o in g[1]]
@@ -383,6 +464,15 @@ def get_best_orthologs(query_orthologs, query_total, subject_orthologs, subject_
     file-based step costs < 1 ms per 100 records and stays text-driven like the reference's.)"""
     func = {"min": min, "max": max}[function]
     key = _EXTRACT[value]
+    try:
+        # native reader (libo2a_ingest.so, include/o2a_records.h); it declines anything it would not decide exactly
+        # like the text-level restatement below (odd number literals, short records, carriage returns)
+        from . import records_native
+        if records_native.best_orthologs_files((query_orthologs, query_total, subject_orthologs, subject_total), value, function,
+                                               (outfile_query, outfile_query_total, outfile_subject, outfile_subject_total)) is not None:
+            return
+    except (RuntimeError, OSError):
+        pass                                  # library not built / unreadable file: the text path reports it
     with open(Path(query_orthologs)) as q_in, open(Path(query_total)) as qt_in, \
             open(Path(subject_orthologs)) as s_in, open(Path(subject_total)) as st_in, \
             open(Path(outfile_query), "w") as q_out, open(Path(outfile_query_total), "w") as qt_out, \

@@ -200,3 +200,105 @@ def test_batch_stream_keeps_order_and_surfaces_errors():
     with pytest.raises(RuntimeError, match="poisoned"):
         list(BatchStream(devices=(0,), contexts=2, engine_factory=E).map(batches, "hist", True))
     assert E.created == E.closed
+
+
+def test_columnar_assembly_is_the_path_taken_and_matches_the_per_alignment_one(tmp_path, monkeypatch):
+    """With the native ingest + native records the run is assembled from columnar data (pipeline._assemble_columnar: no
+    Python object per alignment); records='python' forces the per-alignment path. Same bytes, and the reference's."""
+    from ortho2align_b200 import pipeline
+    calls = []
+    real = pipeline._assemble_columnar
+
+    def spy(*a, **k):
+        out = real(*a, **k)
+        calls.append(out is not None)
+        return out
+    monkeypatch.setattr(pipeline, "_assemble_columnar", spy)
+    monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
+    g = load_golden("e2e.json")
+    dirs = _materialise(tmp_path, g)
+    _run_and_compare(tmp_path, monkeypatch, g, "hist_1", "hist", True, True, ingest="native", dirs=dirs)
+    assert calls == [True]
+    od_fast = {fn: open(os.path.join(tmp_path, "out_hist_1", fn)).read() for fn in os.listdir(tmp_path / "out_hist_1")}
+    real_listdir = os.listdir
+    monkeypatch.setattr(os, "listdir", lambda p: list(g["listdir_order"]) if str(p) == dirs[0] else real_listdir(p))
+    pipeline.build_orthologs(dirs[0], dirs[1], "hist", str(tmp_path / "slow"), fdr=True, silent=True,
+                             stats_filename=str(tmp_path / "slow.stats"), records="python")
+    assert calls == [True]                                   # not consulted for records='python'
+    for fn in ("significant.query_orthologs.bed", "significant.query_orthologs.tsv", "significant.subject_orthologs.bed",
+               "significant.subject_orthologs.tsv", "insignificant.query_orthologs.bed", "insignificant.subject_orthologs.bed",
+               "query_exceptions.bed"):
+        assert open(tmp_path / "slow" / fn).read() == od_fast[fn], fn
+
+
+def test_range_objects_with_null_names_escapes_and_odd_types(tmp_path, monkeypatch):
+    """Names the native range reader renders itself (null name -> 'chrom:start-endstrand', \\u escapes, quotes) and
+    values it leaves to Python's json (a numeric chrom): both give the files of the json.load path."""
+    from ortho2align_b200 import pipeline, synth
+    monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
+    b, m = synth.workload(1, n_lnc=5, with_meta=True, hsps_per_region=150, n_bg=400, seed=19)
+    items = synth.to_json_dicts(b, m)
+    for a in items[0][1]:
+        a["qrange"]["name"] = None
+    for a in items[1][1]:
+        a["qrange"]["name"] = 'lnc "β" \\ tab\tend'
+        a["srange"]["chrom"] = "chré/1"
+    for a in items[2][1]:
+        a["qrange"]["chrom"] = 7                               # str(7): not a JSON string -> the Python path for this run
+    outs = {}
+    for tag, its in (("simple", [it for k, it in enumerate(items) if k != 2]), ("odd", items)):
+        d = tmp_path / tag
+        d.mkdir()
+        ad, bd = d / "align", d / "bg"
+        ad.mkdir(); bd.mkdir()
+        for name, alns, bg in its:
+            (ad / (name + ".json")).write_text(json.dumps(alns))
+            (bd / (name + ".json")).write_text(json.dumps(bg))
+        for ing, rec in (("native", "native"), ("json", "python")):
+            od = str(d / f"out_{ing}")
+            pipeline.build_orthologs(str(ad), str(bd), "hist", od, fdr=True, silent=True, stats_filename=str(d / "s.txt"),
+                                     ingest=ing, records=rec)
+            outs[(tag, ing)] = {fn: open(os.path.join(od, fn), encoding="utf-8").read() for fn in sorted(os.listdir(od))}
+        assert outs[(tag, "native")] == outs[(tag, "json")], tag
+    q = outs[("simple", "native")]["significant.query_orthologs.bed"]
+    assert 'lnc "β" \\ tab' in q and any(":" in ln.split("\t")[3] and ln.split("\t")[3][-1] in "+-." for ln in q.splitlines())
+
+
+@pytest.mark.parametrize("value", ["total_length", "block_count", "block_length", "weight"])
+@pytest.mark.parametrize("function", ["max", "min"])
+def test_native_get_best_orthologs_equals_the_text_statement(tmp_path, monkeypatch, value, function):
+    from ortho2align_b200 import pipeline, records_native
+    g = load_golden("r2_best_weight.json")
+    ins = []
+    for k, fn in enumerate(("significant.query_orthologs.bed", "significant.query_orthologs.tsv",
+                            "significant.subject_orthologs.bed", "significant.subject_orthologs.tsv")):
+        p = tmp_path / fn
+        p.write_text(g["build"][fn])
+        ins.append(str(p))
+    outs_n = [str(tmp_path / f"n{k}") for k in range(4)]
+    outs_p = [str(tmp_path / f"p{k}") for k in range(4)]
+    assert records_native.best_orthologs_files(ins, value, function, outs_n) is not None
+    monkeypatch.setattr(records_native, "best_orthologs_files", lambda *a, **k: None)       # decline -> text path
+    pipeline.get_best_orthologs(*ins, value, function, *outs_p)
+    want = g["runs"][f"{value}.{function}"]
+    assert [open(p).read() for p in outs_n] == want and [open(p).read() for p in outs_p] == want
+
+
+def test_native_get_best_orthologs_declines_what_it_would_not_decide_like_python(tmp_path):
+    from ortho2align_b200 import pipeline, records_native
+    line = "chr1\t10\t50\tlncA\t12\t+\t10\t50\t0\t2\t10,20\t0,30\n"
+    for bad in (line.replace("\n", "\r\n"), line.replace("10,20", "10, 20"), line.replace("\t12\t", "\tinf\t"), "chr1\t10\t50\n"):
+        paths = []
+        for k in range(4):
+            p = tmp_path / f"in{k}"
+            p.write_text(line + bad, newline="")
+            paths.append(str(p))
+        outs = [str(tmp_path / f"o{k}") for k in range(4)]
+        value = "weight" if "inf" in bad else "block_length"
+        assert records_native.best_orthologs_files(paths, value, "max", outs) is None
+        if bad.count("\t") < 11:
+            with pytest.raises(IndexError):
+                pipeline.get_best_orthologs(*paths, value, "max", *outs)
+        else:
+            pipeline.get_best_orthologs(*paths, value, "max", *outs)
+            assert open(outs[0]).read().count("\n") == 1

@@ -14,7 +14,7 @@ def test_records_library_exports_every_declared_symbol():
     build.build_ingest()
     with open(os.path.join(ROOT, "include", "o2a_records.h")) as f:
         src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
-    names = sorted(set(re.findall(r"\b(o2a_records_[a-z_0-9]+)\s*\(", src)))
+    names = sorted(set(re.findall(r"\b(o2a_(?:records|best)_[a-z_0-9]+)\s*\(", src)))
     assert set(names) == set(R.EXPORTS)
     for n in names:
         assert hasattr(R.lib(), n)
