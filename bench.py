@@ -128,6 +128,40 @@ def ncu_traffic(kernel, config, n_lnc, fitter):
     return float(e["dram_bytes"]) if e else None
 
 
+def python_reference_rate(config, fitter, cores, n_lnc, timeout_s=240):
+    """The UNMODIFIED Python reference (baseline/_ref = the offline pip install of /root/reference, or /root/reference)
+    on `n_lnc` lncRNAs of `config` written as its own JSON files: build_orthologs through its TimeoutProcessPool with
+    `cores` processes + get_best_orthologs (oracle/ref_bench.py, run as a subprocess under a timeout). HSPs/s or a reason."""
+    import subprocess
+    import tempfile
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(prefix="o2a_pyref_", dir=tmp_root) as tmp:
+        ad, bd, od = os.path.join(tmp, "align"), os.path.join(tmp, "bg"), os.path.join(tmp, "out")
+        os.makedirs(ad), os.makedirs(bd)
+        step = 8
+        spans = [(config, lo, min(lo + step, n_lnc), n_lnc, ad, bd) for lo in range(0, n_lnc, step)]
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(cores, 32, len(spans))) as pool:
+            parts = pool.map(_write_json_block, spans)
+        n_hsp = sum(p[0] for p in parts)
+        try:
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--align", ad, "--bg", bd,
+                                  "--out", od, "--cores", str(cores), "--fitting", fitter],
+                                 capture_output=True, text=True, timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            return {"unavailable": f"the reference did not finish {n_lnc} lncRNAs within {timeout_s} s"}
+        line = (res.stdout.strip().splitlines() or ["{}"])[-1]
+        try:
+            d = json.loads(line)
+        except ValueError:
+            return {"unavailable": f"reference run failed: {res.stderr.strip()[-300:]}"}
+        if "unavailable" in d:
+            return d
+        secs = d["build_orthologs_s"] + d["get_best_orthologs_s"]
+        return {"value": n_hsp / secs, "unit": UNIT, "cores": cores, "kind": "reference (unmodified Python package, pebble stand-in)",
+                "sample": f"{n_lnc} lncRNAs ({n_hsp} HSPs) as JSON directories -> 7 + 4 files, {secs:.2f} s wall", **d}
+
+
 def cpu_port_rate(batch, fitter, threads, repeats=1):
     """Oracle port (TEST INFRASTRUCTURE used as the reported CPU baseline) on `batch`: HSPs/s."""
     from oracle import oracle as O
@@ -534,9 +568,10 @@ def files_to_files(config, n_lnc, cores=0, runner="gpu", reference=False, ref_ln
             return od
 
         if args.runner == "gpu":
-            run("warmup")                                    # CUDA context, library load
+            run("warmup")                                    # CUDA context, library load, workspace
+        run("cold_json")                                     # JSON parse -> files, nothing cached
         cache = os.path.join(tmp, "columnar.o2ac")
-        run("cold_json", cache=cache)
+        run("cold_json_writing_sidecar", cache=cache)        # the same plus writing the columnar sidecar
         run("warm_sidecar", cache=cache)
         if args.reference:
             from oracle import ref_harness as rh
@@ -707,6 +742,10 @@ def main():
                     help="device-resident arm: the workload as this many batches of --lnc lncRNAs each, all resident in HBM, "
                          "one step = one pass over all of them (config 3 at full size: --lnc 1000 --batches 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true", help="skip timing the unmodified Python reference (baseline/_ref)")
+    ap.add_argument("--pyref-lnc", type=int, default=64, help="lncRNAs in the Python reference's sample")
+    ap.add_argument("--no-files", action="store_true", help="skip the directories -> files figure (N = 1 default run)")
+    ap.add_argument("--files-lnc", type=int, default=100_000, help="lncRNAs of the directories -> files figure (config 5 shape)")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident arm only (profiling runs under ncu)")
     ap.add_argument("--gather", default="final", choices=["step", "final"],
                     help="N > 1: all_gather of the result counters after every step (asynchronous), or once for all "
@@ -1032,12 +1071,23 @@ def main():
         dual_steps = 2 * ((e2e_steps + 1) // 2)
         dt2 = float("inf")
         if dual_engine_error is None:
-            dt2, results2, errors2 = time_e2e([eng, eng2], [hstruct, hstruct2], dual_steps)
-            if errors2:
-                dual_engine_error = errors2[0]
-            elif not (np.array_equal(results2[0].chain_idx, results2[1].chain_idx)
-                      and np.array_equal(results2[0].chain_idx, res.chain_idx)):
-                dual_engine_error = "the two contexts returned different chains"
+            # the product's scheduler for many host batches (ortho2align_b200.stream.BatchStream): one worker thread
+            # per context, batches handed out in order, results collected in order
+            from ortho2align_b200.stream import BatchStream
+            bs = BatchStream(engines=[eng, eng2])
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            try:
+                t0 = time.perf_counter()
+                results2 = list(bs.map((hb for _ in range(dual_steps)), args.fitter, True, 0.05, 5, 2,
+                                       survivors=False, pinned=True))
+                torch.cuda.synchronize()
+                dt2 = time.perf_counter() - t0
+                if not (np.array_equal(results2[-1].chain_idx, res.chain_idx) and np.array_equal(results2[-2].chain_idx, res.chain_idx)):
+                    dual_engine_error = "the two contexts returned different chains"
+            except Exception as ex:
+                dual_engine_error = f"{type(ex).__name__}: {ex}"
         elif world > 1:
             torch.cuda.synchronize()
             dist.barrier()
@@ -1123,12 +1173,33 @@ def main():
         rate, secs = cpu_port_rate(sample, args.fitter, threads, repeats=3)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {k} lncRNAs ({sample.n_hsp} HSPs) of the workload, {secs:.2f} s per pass, best of 3"}
+        if not args.no_python_reference:
+            # beside the C port (the harder baseline): the reference itself, through its own process pool, on all cores
+            try:
+                cpu["python_reference"] = python_reference_rate(args.config if args.config in (1, 2, 5) else 2, args.fitter
+                                                                if args.fitter in ("hist", "kde") else "hist",
+                                                                os.cpu_count() or 1, args.pyref_lnc)
+            except Exception as ex:
+                cpu["python_reference"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
 
     strong = None
     if world > 1 and not args.no_strong:
         # beside the weak-scaling figure: ONE fixed workload (BASELINE configs[4]) sharded over the ranks
         strong = strong_scaling(args, eng, params, dev, rank, world, procs, args.strong_config, args.strong_lnc,
                                 max(args.steps, 10), max(args.warmup, 3))
+    files = None
+    if rank == 0 and world == 1 and not args.no_files:
+        # directories of the reference's JSON files -> the 7 + 4 output files (drop-in build_orthologs +
+        # get_best_orthologs), BASELINE configs[4] shape; the JSON is written to /dev/shm by a fork pool first
+        try:
+            n_files_lnc = args.files_lnc
+            if os.path.isdir("/dev/shm"):
+                free = os.statvfs("/dev/shm"); free_gb = free.f_bavail * free.f_frsize / 1e9
+                if free_gb < 12:
+                    n_files_lnc = min(n_files_lnc, 10_000)
+            files = files_to_files(5, n_files_lnc, 0, "gpu", False, 0, None)
+        except Exception as ex:                                # never lose the headline line to the secondary figure
+            files = {"error": f"{type(ex).__name__}: {ex}"}
     if world > 1:
         g = gathered[0].view(world, 5).cpu().numpy()          # slot 0: first timed step (same batch every step)
         assert int(g[rank, 0]) == int(c.n_survivors)
@@ -1150,6 +1221,8 @@ def main():
             line["per_rank"] = per_rank
         if strong:
             line["strong_scaling"] = strong
+        if files:
+            line["files"] = files
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -386,3 +386,27 @@ def test_understated_size_hints_fail_the_call(engine):
     engine.run(s, p)
     from oracle import oracle as O
     compare_results(engine.fetch(), O.build_batch(b, "hist", True), exact_p=True, what="after a rejected call")
+
+
+def test_batch_stream_with_real_engines(engine):
+    """stream.BatchStream (the scheduler bench.py's two-context e2e figure runs on): several host batches through two
+    library contexts on one GPU, HostBatch and ColumnarBatch alike — results in input order, equal to a plain engine's."""
+    from ortho2align_b200 import synth
+    from ortho2align_b200.engine import Engine
+    from ortho2align_b200.hostbatch import HostBatch
+    from ortho2align_b200.stream import BatchStream
+    batches = [synth.workload(2, n_lnc=6 + 3 * k, seed=50 + k, hsps_per_region=400, n_bg=900) for k in range(5)]
+    want = [engine.build_batch(b, "hist", True) for b in batches]
+    mixed = [HostBatch.from_columnar(b) if k % 2 == 0 else b for k, b in enumerate(batches)]
+    got = list(BatchStream(devices=(0,), contexts=2).map(iter(mixed), "hist", True))
+    assert len(got) == len(want)
+    for k, (g, w) in enumerate(zip(got, want)):
+        compare_results(g, w, exact_p=True, what=f"stream batch {k}")
+    e1, e2 = Engine(0), Engine(0)
+    try:
+        got = list(BatchStream(engines=[e1, e2]).map(iter(mixed), "hist", True, survivors=False))
+        for g, w in zip(got, want):
+            assert np.array_equal(g.chain_idx, w.chain_idx) and np.array_equal(g.best_aln, w.best_aln)
+        assert e1.h and e2.h                                   # caller-owned engines stay open
+    finally:
+        e1.close(); e2.close()
