@@ -580,7 +580,7 @@ static int ensure_sort_scratch(o2a_ctx* ctx, int grid, long long cap)
 }
 
 // per-chunk counters inside stage_cnt (see o2a_ctx)
-enum { CNT_PQ = 0, CNT_RANKBIG = 1, CNT_MID = 2, CNT_CBIG = 3, CNT_PER_CHUNK = 4 };
+enum { CNT_PQ = 0, CNT_RANKBIG = 1, CNT_MID = 2, CNT_CBIG = 3, CNT_FRONT = 4, CNT_PER_CHUNK = 5 };
 static int* chunk_cnt(o2a_ctx* ctx, int chunk, int which) { return P<int>(ctx->stage_cnt) + chunk * CNT_PER_CHUNK + which; }
 
 static void fill_chain_args(o2a_ctx* ctx, int chunk, ChainArgs& A);
@@ -621,6 +621,19 @@ static int run_score(o2a_ctx* ctx, int chunk, cudaStream_t st)
         F.qlen = C.qlen; F.slen = C.slen; F.mid_list = C.mid_list; F.mid_count = C.mid_count;
     }
     const int grid = grid_for(ctx, (na + FRONT_WARPS - 1) / FRONT_WARPS, FRONT_CTAS_PER_SM);
+    // one ticket = about one lncRNA's alignments (they share the class table k_front keeps on chip), but never so many
+    // that the warps get fewer than ~4 tickets each
+    F.ticket = chunk_cnt(ctx, chunk, CNT_FRONT);
+    {
+        const long long nl_view = ctx->vl1 - ctx->vl0 > 0 ? ctx->vl1 - ctx->vl0 : 1;
+        long long per_lnc = (na + nl_view / 2) / nl_view;
+        const long long balance = na / (4ll * grid * FRONT_WARPS);
+        if (per_lnc > balance) per_lnc = balance;
+        if (per_lnc > 64) per_lnc = 64;
+        if (per_lnc < 1) per_lnc = 1;
+        F.chunk_aln = (int)per_lnc;
+        if (const char* e = getenv("O2A_FRONT_CHUNK")) { if (atoi(e) > 0) F.chunk_aln = atoi(e); }
+    }
 #define O2A_FRONT(T) do { if (p.fitter == O2A_FIT_HIST) k_front<T, 0><<<grid, FRONT_WARPS * 32, 0, st>>>(F); \
                          else k_front<T, 1><<<grid, FRONT_WARPS * 32, 0, st>>>(F); } while (0)
     if (b.score_bits == 8) O2A_FRONT(signed char);

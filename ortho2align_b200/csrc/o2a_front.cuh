@@ -11,13 +11,30 @@
 // rank arithmetic of others, one launch and one global round trip of the survivor scores disappear, and no
 // barrier is left (everything is warp-synchronous).
 //
-// The warp streams the alignment's scores (float64: 32-byte loads, a 4 KB tile in flight per warp) and compacts the
-// survivors IN ORDER (popc + warp scan) into the alignment's slot [hsp_off[a], hsp_off[a] + n_surv) of the
-// survivor arrays and into shared memory. The p/q stage works on SCORE CLASSES like k_pq (o2a_score.cuh): sf once
-// per distinct score, L = #{survivors with smaller p} per class, then one ordered walk that hands out the stable
-// ranks 1 + L + #{earlier survivors with the same p} = np.argsort(kind='stable').
-// Alignments with more than FRONT_SCAP survivors or more than FRONT_OVER non-class scores are only filtered here
-// and queued for the CTA-wide k_pq.
+// Work distribution: groups of consecutive alignments (about one lncRNA's worth, FrontArgs::chunk_aln) are handed to
+// the warps through a ticket counter. Consecutive alignments belong to the same lncRNA (one background fit, one
+// threshold), so what depends on the lncRNA only is kept in shared memory across them:
+//   ptab[s]  p = sf(floor(thr) + s) of the integer score classes ("direct slots"), computed lazily up to the
+//            highest slot any alignment of the lncRNA has needed so far (hist: one table search per slot and
+//            lncRNA instead of one per class and alignment; KDE: one value-compressed sum per slot and lncRNA)
+//   grp[s]   first slot of the run of equal p that s belongs to (sf is non-increasing in the score; the table is
+//            CHECKED to be non-increasing — anything else sends the lncRNA's alignments to k_pq)
+//
+// The filter streams the alignment's scores (float64: 32-byte loads, a 4 KB tile in flight per warp) and writes the
+// survivors IN ORDER (popc + warp scan per tile) into the alignment's slot [hsp_off[a], hsp_off[a] + n_surv) of the
+// survivor arrays.
+//
+// Ranks (np.argsort(kind='stable') of the p-values, rank_k = 1 + #{p_j < p_k} + #{j < k : p_j == p_k}) come from
+// KEYS that order the survivors by p without comparing p-values pairwise:
+//   direct survivor in slot s                          key 2 * grp[s]        (all members share one p)
+//   other score x (cut HSP, huge score) with p equal to a neighbouring slot's   that slot's key
+//   other score strictly between slots s and s + 1     key 2 * s + 1         (p[s + 1] < p < p[s] is CHECKED)
+// A larger key means a strictly smaller p, so #{p_j < p_k} is a suffix sum of the key histogram, and the ties of
+// an even key are counted in list order while the histogram is built (match.any, like k_pq's ordered walk). The
+// few members of one odd key are ordered among themselves by (p, list position).
+// Alignments with more than FRONT_SCAP survivors or more than FRONT_OVER non-class scores, and everything that
+// fails a monotonicity check, are only filtered here and queued for the CTA-wide k_pq (o2a_score.cuh), which
+// makes no such assumption.
 #pragma once
 #include "o2a_chain.cuh"
 #include "o2a_device.cuh"
@@ -27,12 +44,16 @@
 namespace o2a {
 
 constexpr int FRONT_WARPS = 4;            // warps per CTA; every warp owns its alignments
-constexpr int FRONT_CTAS_PER_SM = 8;      // 32 warps per SM
+#ifndef O2A_FRONT_CTAS
+#define O2A_FRONT_CTAS 8
+#endif
+constexpr int FRONT_CTAS_PER_SM = O2A_FRONT_CTAS;      // 32 warps per SM
 constexpr int FRONT_SCAP = 192;           // survivors per alignment kept on chip
 constexpr int FRONT_DIRECT = 128;         // integer score classes floor(thr) + [0, 128)
-constexpr int FRONT_OVER = 32;            // other scores (cut HSPs, huge values): one class each
-constexpr int FRONT_SLOTS = FRONT_DIRECT + FRONT_OVER;
+constexpr int FRONT_OVER = 32;            // other scores (cut HSPs, huge values): one lane each
+constexpr int FRONT_KEYS = 2 * FRONT_DIRECT;
 constexpr int FRONT_PASS = 32;            // passing exceptions of a narrow-score alignment kept on chip
+constexpr int FRONT_XR = FRONT_SCAP / 32; // survivor scores per lane
 
 struct FrontArgs {
     PqArgs P;                             // geometry, fit tables, p / q / keep outputs (n_surv, surv_x are outputs here)
@@ -49,20 +70,28 @@ struct FrontArgs {
     const int4* coords4; const int* qstart; const int* qend; const int* sstart; const int* send;
     const long long* qlen; const long long* slen;
     int* mid_list; int* mid_count;        // alignments the warp path of the chaining cannot take (-> k_chain_small)
+    int chunk_aln; int* ticket;           // groups of chunk_aln (>= 1) consecutive alignments are handed out through *ticket
 };
 
-struct FrontWarpSmem {
+struct __align__(16) FrontWarpSmem {
+    double ptab[FRONT_DIRECT];            // per lncRNA: p of the direct slots [0, tab_n)
+    double ox[FRONT_OVER];                // scores of the non-class survivors
+    double op[FRONT_OVER];                // their p (narrow filter phase: values of the passing exceptions)
     double x[FRONT_SCAP];                 // survivor scores, list order
-    double pe[FRONT_SLOTS];               // p of the class
-    double ox[FRONT_OVER];                // scores of the overflow classes (narrow filter phase: values of the passing exceptions)
-    int cnt[FRONT_SLOTS];                 // class multiplicity, later: survivors seen per tie group (narrow filter phase: positions of the passing exceptions)
-    int L[FRONT_SLOTS];                   // survivors with strictly smaller p    } float64 filter phase: L and g together hold
-    short g[FRONT_SLOTS];                 // tie group = first class with the same p } the survivors' positions (FRONT_SCAP ints)
-    short dense[FRONT_SLOTS];             // non-empty classes in slot order
-    short slot[FRONT_SCAP];               // class of every survivor
+    int sidx[FRONT_SCAP];                 // HSP position of every survivor
+    unsigned short cnt[FRONT_KEYS];       // members per key, then: survivors with a larger key (narrow filter phase: positions of the passing exceptions)
+    unsigned char grp[FRONT_DIRECT];      // per lncRNA: head slot of the run of equal p
+    unsigned char slot[FRONT_SCAP];       // direct slot, or FRONT_DIRECT + o for non-class survivor o
+    unsigned char key[FRONT_SCAP];
+    unsigned char aux[FRONT_SCAP];        // even key: earlier members of the key; odd key: o
+    unsigned char kept[FRONT_SCAP];       // survivor-list positions of the retained HSPs
+    unsigned char okey[FRONT_OVER];
+    unsigned char oin[FRONT_OVER];        // members of the same odd key that rank before o
 };
 
-static_assert(FRONT_SLOTS * (sizeof(int) + sizeof(short)) >= FRONT_SCAP * sizeof(int) && FRONT_PASS <= FRONT_OVER, "aliases of the filter phase");
+static_assert(FRONT_KEYS * sizeof(unsigned short) >= FRONT_PASS * sizeof(int) && FRONT_PASS <= FRONT_OVER, "aliases of the filter phase");
+static_assert(FRONT_SCAP <= 256 && FRONT_KEYS <= 256 && FRONT_DIRECT + FRONT_OVER <= 256, "byte-sized indices");
+static_assert(FRONT_KEYS == 8 * 32, "the suffix sums take eight keys per lane");
 
 template <typename T> struct FrontTraits;
 template <> struct FrontTraits<double> { static constexpr int PER = 2; };
@@ -77,13 +106,13 @@ __device__ __forceinline__ int4 ld_stream_16(const void* p)
     return r;
 }
 
-// ---- filter phase, float64 scores: returns n_surv; survivors to global slots and (first FRONT_SCAP) to S.x ------
+// ---- filter phase, float64 scores: returns n_surv; survivor positions to global slots and (first FRONT_SCAP) S.sidx --
 // Tile = 512 scores; lane i owns the 16 CONSECUTIVE scores [16 i, 16 i + 16) of the tile (four 32-byte loads, one
 // full DRAM sector each: LDG.E.256 on sm_100), so the order-preserving position of a survivor is
-//   (survivors of earlier tiles) + (exclusive warp scan of the per-lane counts) + (rank inside the lane's 16 bits):
-// one popc + one 5-step shuffle scan per 512 scores instead of two ballots per 64. The few survivors (~1 per lane and
-// tile) are then written in a loop over the set bits; their value is re-read (an L2 hit) rather than selected out of
-// 16 registers with a run-time index.
+//   (survivors of earlier tiles) + (exclusive warp scan of the per-lane counts) + (rank inside the lane's 16 bits).
+// The loads of tile t + 1 are issued right after tile t's compares, so their DRAM latency hides under the scan and the
+// placement of tile t. (Scanning four tiles' counts together as packed shuffle chains saves shuffles but leaves nothing
+// to overlap the loads with: 0.67 against 0.65 ms on BASELINE config 2.)
 __device__ __forceinline__ void ld_stream_f64x4(const double* p, double& a, double& b, double& c, double& d)
 {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
@@ -108,64 +137,57 @@ __device__ __forceinline__ void front_load16(const double* __restrict__ sc, long
         for (int q = 0; q < 4; ++q) ld_stream_f64x4(sc + e0 + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         return;
     }
+    const long long left = n_total - (g0 + e0);        // the last tile of the whole array: my scores inside it
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = (g0 + e0 + c < n_total) ? sc[e0 + c] : t;      // the last tile of the whole array
+    for (int q = 0; q < 4; ++q) {
+        if (left >= 4 * q + 4) ld_stream_f64x4(sc + e0 + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        else {
+#pragma unroll
+            for (int c = 4 * q; c < 4 * q + 4; ++c) v[c] = c < left ? sc[e0 + c] : t;
+        }
+    }
 }
 
 __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score, long long n_total, long long h0, int m,
-                                                double t, int* __restrict__ out_idx, double* __restrict__ out_x,
-                                                FrontWarpSmem& S)
+                                                     double t, int* __restrict__ out_idx, FrontWarpSmem& S)
 {
     const int lane = lane_id();
-    const int sh = (int)(h0 & 3);                       // stream starts at the 32-byte aligned address at / below h0
+    const int sh = (int)(h0 & 3);
     const double* sc = score + h0 - sh;
-    const long long g0 = h0 - sh;                       // global index of stream element 0
+    const long long g0 = h0 - sh;
     const int ms = m + sh;
-    int* s_idx = S.L;                                   // survivor positions (S.L and S.g are free until the p/q phase)
     int base = 0;
     double v[16];
     front_load16(sc, g0, n_total, lane * 16, t, v, g0 + 512 <= n_total);
 #pragma unroll 1
     for (int t0 = 0; t0 < ms; t0 += 512) {
-        const int e0 = t0 + lane * 16;                  // my first stream element
+        const int e0 = t0 + lane * 16;
         unsigned mask = front_mask16(v, t);
-        // the next tile's loads are in flight while this tile's survivors are placed
         if (t0 + 512 < ms) front_load16(sc, g0, n_total, e0 + 512, t, v, g0 + t0 + 1024 <= n_total);
-        const int left = ms - e0;                       // my scores inside the alignment
+        const int left = ms - e0;
         if (left < 16) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
-        if (t0 == 0 && lane == 0) mask &= ~((1u << sh) - 1u);          // the neighbour's last HSPs
+        if (t0 == 0 && lane == 0) mask &= ~((1u << sh) - 1u);
         const int cnt = __popc(mask);
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += y; }
         const int total = __shfl_sync(FULL_MASK, incl, 31);
-        if (total) {
-            int p = base + incl - cnt;
+        int p = base + incl - cnt;
 #pragma unroll 1
-            while (mask) {
-                const int c = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int pos = e0 + c - sh;            // HSP position inside the alignment
-                out_idx[p] = pos;
-                if (p < FRONT_SCAP) s_idx[p] = pos;
-                ++p;
-            }
+        while (mask) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            out_idx[p] = e0 + c - sh;
+            if (p < FRONT_SCAP) S.sidx[p] = e0 + c - sh;
+            ++p;
         }
         base += total;
-    }
-    // the survivors' scores: one independent (L2-resident) load each, all in flight together
-    __syncwarp();
-    const double* al = score + h0;
-#pragma unroll 1
-    for (int k = lane; k < base; k += 32) {
-        const double x = al[k < FRONT_SCAP ? s_idx[k] : out_idx[k]];
-        out_x[k] = x;
-        if (k < FRONT_SCAP) S.x[k] = x;
     }
     return base;
 }
 
-// ---- filter phase, narrow scores (int8 / int16 / int32 + exception lists; see k_filter_q's contract) --------------
+// ---- filter phase, narrow scores (int8 / int16 / int32 + exception lists; see QTraits' contract) -----------------
+// Survivor positions to out_idx and (first FRONT_SCAP) S.sidx, survivor scores to out_x.
 template <typename T>
 __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, long long n_hsp_total, long long h0, int m,
                                               double t, const int* __restrict__ exc_pos, const double* __restrict__ exc_val,
@@ -181,7 +203,9 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
     // q > thr  <=>  q > floor(thr) for integers; clamped so that the sentinel can never pass
     const double tf = floor(t);
     const int tq = tf >= 2147483647.0 ? 2147483647 : (tf <= (double)SENT ? SENT : (int)tf);
-    // exceptions that pass (value > thr): positions in S.cnt, values in S.ox (both free during the filter phase)
+    // exceptions that pass (value > thr): positions in e_pos, values in e_val (both free during the filter phase)
+    int* e_pos = reinterpret_cast<int*>(S.cnt);
+    double* e_val = S.op;
     int np = 0;
     for (int i0 = 0; i0 < ne; i0 += 32) {
         const int i = i0 + lane;
@@ -189,7 +213,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
         const bool pass = i < ne && v > t;
         const unsigned b = __ballot_sync(FULL_MASK, pass);
         const int p = np + __popc(b & lt);
-        if (pass && p < FRONT_PASS) { S.cnt[p] = exc_pos[x0 + i]; S.ox[p] = v; }
+        if (pass && p < FRONT_PASS) { e_pos[p] = exc_pos[x0 + i]; e_val[p] = v; }
         np += __popc(b);
     }
     __syncwarp();
@@ -233,7 +257,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
                 const int c = __ffs(sent) - 1; sent &= sent - 1;
                 const int pos = e + c - sh;
                 bool ok = false;
-                if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (S.cnt[i] == pos) { ok = true; break; } }
+                if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (e_pos[i] == pos) { ok = true; break; } }
                 else {
                     int lo = 0, hi = ne;
                     while (lo < hi) { const int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < pos) lo = mid + 1; else hi = mid; }
@@ -255,7 +279,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
                     if ((msk >> c) & 1u) {
                         double x = (double)q_at<T>(raw[r], c);
                         if ((sent_pass >> c) & 1u) {     // a passing exception: its exact float64 value
-                            if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (S.cnt[i] == ep + c) { x = S.ox[i]; break; } }
+                            if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (e_pos[i] == ep + c) { x = e_val[i]; break; } }
                             else {
                                 int lo = 0, hi = ne;
                                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < ep + c) lo = mid + 1; else hi = mid; }
@@ -263,7 +287,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
                             }
                         }
                         out_idx[p] = ep + c; out_x[p] = x;
-                        if (p < FRONT_SCAP) S.x[p] = x;
+                        if (p < FRONT_SCAP) S.sidx[p] = ep + c;
                         ++p;
                     }
                 }
@@ -282,20 +306,64 @@ __device__ __forceinline__ double front_sf(double x, const PqFit& F)
     return emp_sf_compressed(x, F.uval, F.ucnt, F.unv, F.nbg);
 }
 
-// ---- p / q phase on the survivors in S.x[0..ns) --------------------------------------------------------------------
-// Returns false when the alignment has more than FRONT_OVER non-class scores (left to k_pq).
-// On success S.slot[0..kept) holds the survivor-list positions of the retained HSPs and *kept_out their number.
 template <int FIT>
-__device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double thr, int ns, int m, long long h0,
-                                         long long a, FrontWarpSmem& S, int* kept_out)
+__device__ __forceinline__ PqFit front_fit_of(const PqArgs& P, int l)
+{
+    PqFit F; F.fitter = FIT == 0 ? 0 : P.fitter; F.tk = nullptr; F.tc = nullptr; F.uval = nullptr; F.ucnt = nullptr;
+    F.unv = 0; F.kfac = 1.0; F.nbg = 1.0;
+    if (FIT == 0) {
+        F.f = P.fits[l];
+        const long long tb = P.bg_off[l] >> 1;
+        F.tk = P.tbl_k + tb; F.tc = P.tbl_cum + tb;
+    } else {
+        const long long b0 = P.bg_off[l];
+        F.uval = P.uv_val + b0; F.ucnt = P.uv_cnt + b0; F.unv = P.uv_n[l];
+        F.nbg = (double)(P.bg_off[l + 1] - b0);
+        if (P.fitter == 1) F.kfac = P.kde_factor[l];
+    }
+    return F;
+}
+
+// ---- the lncRNA's class table: slots [tab_n, need) ----------------------------------------------------------------
+// Returns false when p rises somewhere (or is NaN): the run structure the ranks rely on does not hold.
+template <int FIT>
+__device__ __forceinline__ bool front_extend_table(const PqArgs& P, int l, long long xlo, int tab_n, int need, FrontWarpSmem& S)
+{
+    const int lane = lane_id();
+    const unsigned le = lanemask_lt() | (1u << lane);
+    const PqFit F = front_fit_of<FIT>(P, l);
+    bool ok = true;
+#pragma unroll 1
+    for (int s0 = tab_n; s0 < need; s0 += 32) {
+        const int s = s0 + lane;
+        const bool valid = s < need;
+        double p = 0.0;
+        if (valid) { p = front_sf<FIT>((double)(xlo + s), F); S.ptab[s] = p; }
+        double pprev = __shfl_up_sync(FULL_MASK, p, 1);
+        if (lane == 0 && s > 0) pprev = S.ptab[s - 1];              // written by an earlier round / an earlier call
+        const bool head = valid && (s == 0 || p != pprev);
+        if (valid && s > 0 && !(p <= pprev)) ok = false;
+        const unsigned H = __ballot_sync(FULL_MASK, head);
+        if (valid) S.grp[s] = (unsigned char)((H & le) ? s0 + 31 - __clz(H & le) : S.grp[s0 - 1]);
+        __syncwarp();
+    }
+    return __all_sync(FULL_MASK, ok);
+}
+
+// ---- p / q phase on the survivors (positions in S.sidx, scores in S.x) ------------------------------------------------
+// Returns false when the alignment has to go to k_pq. On success S.kept[0..*kept_out) holds the survivor-list
+// positions of the retained HSPs. `tab_n` (warp-uniform, per lncRNA) is the number of valid ptab / grp slots, -1 once
+// the lncRNA's table has failed its check.
+template <int FIT>
+__device__ __forceinline__ bool front_pq(const PqArgs& A, double thr, int ns, int m, long long h0,
+                                         long long a, int l, int& tab_n, FrontWarpSmem& S, int* kept_out)
 {
     const int lane = lane_id();
     const unsigned lt = lanemask_lt();
-    for (int t = lane; t < FRONT_SLOTS; t += 32) S.cnt[t] = 0;
-    __syncwarp();
-    // ---- classes ---------------------------------------------------------------------------------
+    if (tab_n < 0) return false;
+    // ---- slots ----------------------------------------------------------------------------------------------
     const long long xlo = (long long)floor(thr);
-    int nover = 0, maxslot = 0;
+    int nover = 0, maxslot = -1;
 #pragma unroll 1
     for (int k0 = 0; k0 < ns; k0 += 32) {
         const int k = k0 + lane;
@@ -307,140 +375,136 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double
         const bool over = valid && !direct;
         const unsigned ob = __ballot_sync(FULL_MASK, over);
         int slot = 0;
-        if (direct) { slot = (int)off; atomicAdd(&S.cnt[slot], 1); maxslot = max(maxslot, slot); }
+        if (direct) { slot = (int)off; maxslot = max(maxslot, slot); }
         else if (over) {
             const int o = nover + __popc(ob & lt);
             slot = FRONT_DIRECT + (o < FRONT_OVER ? o : 0);
-            if (o < FRONT_OVER) { S.ox[o] = x; S.cnt[slot] = 1; }
+            if (o < FRONT_OVER) S.ox[o] = x;
         }
         nover += __popc(ob);
-        if (valid) S.slot[k] = (short)slot;
+        if (valid) S.slot[k] = (unsigned char)slot;
     }
     if (nover > FRONT_OVER) return false;
-    maxslot = __reduce_max_sync(FULL_MASK, maxslot);
+    // zero the key histogram while the slot stores settle
+    reinterpret_cast<uint4*>(S.cnt)[lane] = make_uint4(0u, 0u, 0u, 0u);
+    // ---- non-class scores: the slots around them ---------------------------------------------------------------
+    int o_lo = 0; bool o_beyond = false, bad = false;
     __syncwarp();
-    // ---- sf once per class; dense list of the non-empty classes (slot order) ---------------------------
-    const int ndir = maxslot + 1;
-    const int ncls = ndir + nover;
-    int nd = 0;
+    const double ox = lane < nover ? S.ox[lane] : 0.0;
+    if (lane < nover) {
+        const double d = floor(ox) - (double)xlo;      // slots below x (exact: both are integers of moderate size, or d is huge)
+        if (!(d >= 0.0)) bad = true;                   // x below floor(thr) (or NaN): cannot have passed a sane threshold
+        else if (d >= (double)(FRONT_DIRECT - 1)) { o_beyond = true; maxslot = max(maxslot, FRONT_DIRECT - 1); }
+        else { o_lo = (int)d; maxslot = max(maxslot, o_lo + 1); }
+    }
+    if (__any_sync(FULL_MASK, bad)) return false;
+    const int need = __reduce_max_sync(FULL_MASK, maxslot) + 1;
+    if (need > tab_n) {
+        const bool ok = front_extend_table<FIT>(A, l, xlo, tab_n, need, S);
+        tab_n = ok ? need : -1;
+        if (!ok) return false;
+    }
+    // ---- non-class scores: p, key, order inside an odd key -------------------------------------------------------
+    if (nover > 0) {
+        double p = 0.0; int key = 0;
+        if (lane < nover) {
+            const PqFit F = front_fit_of<FIT>(A, l);
+            p = front_sf<FIT>(ox, F);
+            if (o_beyond) {
+                const double pl = S.ptab[FRONT_DIRECT - 1];
+                if (!(p <= pl)) bad = true;
+                key = p == pl ? 2 * S.grp[FRONT_DIRECT - 1] : FRONT_KEYS - 1;
+            } else {
+                const double pl = S.ptab[o_lo], ph = S.ptab[o_lo + 1];
+                if (!(ph <= p && p <= pl)) bad = true;
+                key = p == pl ? 2 * S.grp[o_lo] : (p == ph ? 2 * S.grp[o_lo + 1] : 2 * o_lo + 1);
+            }
+            S.okey[lane] = (unsigned char)key; S.op[lane] = p;
+        }
+        if (__any_sync(FULL_MASK, bad)) return false;
+        // several survivors in one odd key: earlier in (p, list order) first; o is list order
+        const unsigned om = __ballot_sync(FULL_MASK, lane < nover);
+        int inner = 0;
+        if (lane < nover) {
+            const unsigned peers = __match_any_sync(om, (key & 1) ? key : FRONT_KEYS + lane);
+            bad = __popc(peers) > 1;
+        }
+        if (__any_sync(FULL_MASK, bad)) {
 #pragma unroll 1
-    for (int e0 = 0; e0 < ncls; e0 += 32) {
-        const int e = e0 + lane;
-        const int slot = e < ndir ? e : FRONT_DIRECT + (e - ndir);
-        const bool used = e < ncls && S.cnt[slot] > 0;
-        if (used) S.pe[slot] = front_sf<FIT>(e < ndir ? (double)(xlo + slot) : S.ox[e - ndir], F);
-        const unsigned ub = __ballot_sync(FULL_MASK, used);
-        if (used) S.dense[nd + __popc(ub & lt)] = (short)slot;
-        nd += __popc(ub);
+            for (int o2 = 0; o2 < nover; ++o2) {
+                const int k2 = __shfl_sync(FULL_MASK, key, o2);
+                const double p2 = __shfl_sync(FULL_MASK, p, o2);
+                if ((key & 1) && k2 == key && o2 != lane && (p2 < p || (p2 == p && o2 < lane))) ++inner;
+            }
+        }
+        if (lane < nover) S.oin[lane] = (unsigned char)inner;
     }
     __syncwarp();
     double* xs = A.surv_p + h0;
     if (!A.fdr) {                                      // pipeline.py:778-780: hsp.pval = p, nothing dropped
         for (int k = lane; k < ns; k += 32) {
-            const double p = S.pe[S.slot[k]];
+            const int v = S.slot[k];
+            const double p = v < FRONT_DIRECT ? S.ptab[v] : S.op[v - FRONT_DIRECT];
             xs[k] = p; A.surv_pq[h0 + k] = p; A.surv_keep[h0 + k] = 1;
+            S.kept[k] = (unsigned char)k;              // everything is retained
         }
-        __syncwarp();
-        for (int k = lane; k < ns; k += 32) S.slot[k] = (short)k;       // everything is retained
         if (lane == 0) A.n_keep[a] = ns;
         *kept_out = ns;
         return true;
     }
-    // ---- per class: survivors with strictly smaller p (L), and the tie group (g) ------------------------------------
-    // sf is non-increasing in the score, so along the dense list (ascending integer scores) p normally never rises:
-    // tie groups are runs, L = survivors after the run. That takes two ballots and two scans for up to 64 classes.
-    // Anything else (overflow classes, more than 64 classes, a p that rises by an ulp) takes the all-pairs form.
-    bool fast = nover == 0 && nd <= 64;
-    int slot_u[2], cn_u[2]; double p_u[2]; bool head_u[2];
-    if (fast) {
-        bool mono = true;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int d = lane + 32 * u;
-            const bool valid = d < nd;
-            slot_u[u] = valid ? S.dense[d] : 0;
-            cn_u[u] = valid ? S.cnt[slot_u[u]] : 0;
-            p_u[u] = valid ? S.pe[slot_u[u]] : 0.0;
-            const double pprev = (valid && d > 0) ? S.pe[S.dense[d - 1]] : 0.0;
-            head_u[u] = valid && (d == 0 || p_u[u] != pprev);
-            if (valid && d > 0 && p_u[u] > pprev) mono = false;
-        }
-        fast = __all_sync(FULL_MASK, mono);
-    }
-    if (fast) {
-        const unsigned H0 = __ballot_sync(FULL_MASK, head_u[0]), H1 = __ballot_sync(FULL_MASK, head_u[1]);
-        int incl0 = cn_u[0], incl1 = cn_u[1];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y0 = __shfl_up_sync(FULL_MASK, incl0, d), y1 = __shfl_up_sync(FULL_MASK, incl1, d);
-            if (lane >= d) { incl0 += y0; incl1 += y1; }
-        }
-        incl1 += __shfl_sync(FULL_MASK, incl0, 31);
-        const int total = __shfl_sync(FULL_MASK, incl1, 31);
-        const int cprev0 = incl0 - cn_u[0], cprev1 = incl1 - cn_u[1];      // survivors before this class
-        const unsigned le = lt | (1u << lane), gt = ~le;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const unsigned Hu = u ? H1 : H0;
-            // head of my run (at or below me) and the next head (above me), as dense indices
-            int hidx, nidx;
-            if (Hu & le) hidx = 32 * u + 31 - __clz(Hu & le); else hidx = 31 - __clz(H0);
-            if (Hu & gt) nidx = 32 * u + __ffs(Hu & gt) - 1;
-            else if (u == 0 && H1) nidx = 32 + __ffs(H1) - 1;
-            else nidx = -1;
-            const int c0 = __shfl_sync(FULL_MASK, cprev0, nidx & 31), c1 = __shfl_sync(FULL_MASK, cprev1, nidx & 31);
-            const int before_next = nidx < 0 ? total : (nidx < 32 ? c0 : c1);
-            if (lane + 32 * u < nd) { S.L[slot_u[u]] = total - before_next; S.g[slot_u[u]] = S.dense[hidx]; }
-        }
-    } else {
-#pragma unroll 1
-        for (int d = lane; d < nd; d += 32) {
-            const int slot = S.dense[d];
-            const double p = S.pe[slot];
-            int L = 0, g = slot;
-#pragma unroll 1
-            for (int d2 = 0; d2 < nd; ++d2) {
-                const int s2 = S.dense[d2];
-                const double p2 = S.pe[s2];
-                L += (p2 < p) ? S.cnt[s2] : 0;
-                if (p2 == p && s2 < g) g = s2;
-            }
-            S.L[slot] = L; S.g[slot] = (short)g;
-        }
-    }
-    __syncwarp();
-    for (int d = lane; d < nd; d += 32) S.cnt[S.dense[d]] = 0;         // now: survivors seen per tie group
-    __syncwarp();
-    // ---- ordered walk: rank = 1 + L + #{earlier survivors of the tie group} ------------------------------------
-    const double md = (double)m;                       // total_hsps = len(alignment._all_HSPs), pipeline.py:770
-    int kept = 0;
+    // ---- key histogram; ties of an even key in list order ---------------------------------------------------------
 #pragma unroll 1
     for (int k0 = 0; k0 < ns; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < ns;
         const unsigned vm = __ballot_sync(FULL_MASK, valid);
-        int slot = 0, g = 0, seen = 0, before = 0; unsigned peers = 0;
-        bool is_kept = false;
+        int key = 0, seen = 0, before = 0, v = 0; unsigned peers = 0;
         if (valid) {
-            slot = S.slot[k]; g = S.g[slot];
-            peers = __match_any_sync(vm, g);
+            v = S.slot[k];
+            key = v < FRONT_DIRECT ? 2 * S.grp[v] : S.okey[v - FRONT_DIRECT];
+            peers = __match_any_sync(vm, key);
             before = __popc(peers & lt);
-            seen = S.cnt[g];
+            seen = S.cnt[key];
         }
         __syncwarp();
-        if (valid && before == 0) S.cnt[g] = seen + __popc(peers);
-        __syncwarp();
+        if (valid && before == 0) S.cnt[key] = (unsigned short)(seen + __popc(peers));
         if (valid) {
-            const double p = S.pe[slot];
-            const int rank = 1 + S.L[slot] + seen + before;
-            const double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);     // multiply first, like the reference
-            const bool keep = q <= A.alpha;
-            xs[k] = p; A.surv_pq[h0 + k] = q; A.surv_keep[h0 + k] = keep ? 1 : 0;
-            is_kept = keep;
+            S.key[k] = (unsigned char)key;
+            S.aux[k] = (unsigned char)((key & 1) ? v - FRONT_DIRECT : seen + before);
         }
-        // the retained HSPs in list order, compacted in place: the slot entries at or below k have been read
+        __syncwarp();
+    }
+    // ---- survivors with a larger key (= strictly smaller p): suffix sums, eight keys per lane --------------------
+    {
+        const uint4 c = reinterpret_cast<const uint4*>(S.cnt)[lane];
+        const int c0 = c.x & 0xffff, c1 = c.x >> 16, c2 = c.y & 0xffff, c3 = c.y >> 16;
+        const int c4 = c.z & 0xffff, c5 = c.z >> 16, c6 = c.w & 0xffff, c7 = c.w >> 16;
+        const int tot = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+        int incl = tot;                                // inclusive suffix over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_down_sync(FULL_MASK, incl, d); if (lane + d < 32) incl += y; }
+        const int s7 = incl - tot, s6 = s7 + c7, s5 = s6 + c6, s4 = s5 + c5, s3 = s4 + c4, s2 = s3 + c3, s1 = s2 + c2, s0 = s1 + c1;
+        reinterpret_cast<uint4*>(S.cnt)[lane] = make_uint4((unsigned)s0 | ((unsigned)s1 << 16), (unsigned)s2 | ((unsigned)s3 << 16),
+                                                           (unsigned)s4 | ((unsigned)s5 << 16), (unsigned)s6 | ((unsigned)s7 << 16));
+    }
+    __syncwarp();
+    // ---- rank, q, keep ------------------------------------------------------------------------------------------------
+    const double md = (double)m;                       // total_hsps = len(alignment._all_HSPs), pipeline.py:770
+    int kept = 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < ns; k0 += 32) {
+        const int k = k0 + lane;
+        bool is_kept = false;
+        if (k < ns) {
+            const int key = S.key[k], aux = S.aux[k];
+            const double p = (key & 1) ? S.op[aux] : S.ptab[key >> 1];
+            const int rank = 1 + S.cnt[key] + ((key & 1) ? (int)S.oin[aux] : aux);
+            const double q = __ddiv_rn(__dmul_rn(md, p), (double)rank);     // multiply first, like the reference
+            is_kept = q <= A.alpha;
+            xs[k] = p; A.surv_pq[h0 + k] = q; A.surv_keep[h0 + k] = is_kept ? 1 : 0;
+        }
         const unsigned kb = __ballot_sync(FULL_MASK, is_kept);
-        if (is_kept) S.slot[kept + __popc(kb & lt)] = (short)k;
+        if (is_kept) S.kept[kept + __popc(kb & lt)] = (unsigned char)k;
         kept += __popc(kb);
     }
     if (lane == 0) A.n_keep[a] = kept;
@@ -452,76 +516,102 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, const PqFit& F, double
 // instruction caches hold 32 KB, and 32 warps per SM in different phases of a large kernel miss them constantly: a variant
 // of this kernel that also gathered coordinates and chained ran at 44 % issue utilisation with 6.9 stall cycles per
 // instruction on instruction fetch); FIT = 1: KDE / empirical.
+// Registers: 64 per thread (8 CTAs per SM) with NOTHING spilled — what is carried from one alignment to the next is
+// kept to a handful of 32-bit values on purpose (a build with 264 bytes of spills ran 8 % slower, one at 48 registers
+// and 10 CTAs per SM 60 % slower: the L1 left beside 170 KB of shared memory does not hold the local memory of 1024 threads).
 template <typename T, int FIT>
 __global__ void __launch_bounds__(FRONT_WARPS * 32, FRONT_CTAS_PER_SM)
-k_front(FrontArgs A)
+k_front(const __grid_constant__ FrontArgs A)
 {
     __shared__ FrontWarpSmem s_all[FRONT_WARPS];
     FrontWarpSmem& S = s_all[warp_id()];
     const int lane = lane_id();
     const PqArgs& P = A.P;
-    const long long nwarps = (long long)gridDim.x * FRONT_WARPS;
-    for (long long a = (long long)blockIdx.x * FRONT_WARPS + warp_id(); a < P.n_aln; a += nwarps) {
+    // groups of chunk_aln consecutive alignments (about one lncRNA) are handed out through a ticket counter; the next
+    // ticket is drawn while the current group is processed
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(A.ticket, 1);
+    ticket = __shfl_sync(FULL_MASK, ticket, 0);
+    int cur_l = -1, tab_n = 0;
+    double thr = 0.0;
+#pragma unroll 1
+    while ((long long)ticket * A.chunk_aln < P.n_aln) {
+    const int a_lo = ticket * A.chunk_aln;
+    if (lane == 0) ticket = atomicAdd(A.ticket, 1);           // read after the group
+#pragma unroll 1
+    for (int a = a_lo; a < min(a_lo + A.chunk_aln, (int)P.n_aln); ++a) {
         const int l = P.aln_lnc[a];
-        const long long h0 = P.hsp_off[a];
-        const int m = (int)(P.hsp_off[a + 1] - h0);
-        if (P.lnc_status[l] != 0) {                    // fit failed: the reference raised before its alignment loop
-            if (lane == 0) { A.n_surv[a] = 0; P.n_keep[a] = 0; }
-            continue;
+        const long long hbeg = P.hsp_off[a];
+        const int m = (int)(P.hsp_off[a + 1] - hbeg);
+        if (l != cur_l) {
+            cur_l = l; tab_n = 0;
+            // fit failed: the reference raised before its alignment loop — nothing passes an infinite threshold
+            thr = P.lnc_status[l] != 0 ? __longlong_as_double(0x7ff0000000000000ll) : P.thr[l];
         }
-        const double thr = P.thr[l];
         int ns;
         __syncwarp();                                  // the previous alignment is done with S
-        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, h0, m, thr, A.surv_idx + h0, A.surv_x + h0, S);
+        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S);
         else {
             const long long x0 = A.exc_off[a];
-            ns = front_filter_q<T>(reinterpret_cast<const T*>(A.score_q), A.n_hsp_total, h0, m, thr, A.exc_pos, A.exc_val,
-                                   x0, (int)(A.exc_off[a + 1] - x0), A.surv_idx + h0, A.surv_x + h0, S);
+            ns = front_filter_q<T>(reinterpret_cast<const T*>(A.score_q), A.n_hsp_total, hbeg, m, thr, A.exc_pos, A.exc_val,
+                                   x0, (int)(A.exc_off[a + 1] - x0), A.surv_idx + hbeg, A.surv_x + hbeg, S);
         }
         if (lane == 0) A.n_surv[a] = ns;
         if (ns == 0) { if (lane == 0) P.n_keep[a] = 0; continue; }
+        __syncwarp();
+        // the survivors' scores: independent loads, all in flight together (float64: L2-resident lines of the stream
+        // just read; narrow: what the filter has just written)
+        double* out_x = A.surv_x + hbeg;
+        {
+            double xr[FRONT_XR];
+            if constexpr (sizeof(T) == 8) {
+                const double* al = A.score + hbeg;
+#pragma unroll
+                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; xr[j] = k < ns ? al[S.sidx[k]] : 0.0; }
+#pragma unroll
+                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; if (k < ns) { out_x[k] = xr[j]; S.x[k] = xr[j]; } }
+#pragma unroll 1
+                for (int k = FRONT_SCAP + lane; k < ns; k += 32) out_x[k] = al[A.surv_idx[hbeg + k]];
+            } else if (ns <= FRONT_SCAP) {
+#pragma unroll
+                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; xr[j] = k < ns ? __ldcg(out_x + k) : 0.0; }
+#pragma unroll
+                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; if (k < ns) S.x[k] = xr[j]; }
+            }
+        }
+        __syncwarp();
         bool done = false;
         int kept = 0;
-        if (ns <= FRONT_SCAP) {
-            __syncwarp();
-            PqFit F; F.fitter = FIT == 0 ? 0 : P.fitter; F.tk = nullptr; F.tc = nullptr; F.uval = nullptr; F.ucnt = nullptr;
-            F.unv = 0; F.kfac = 1.0; F.nbg = 1.0;
-            if (FIT == 0) {
-                F.f = P.fits[l];
-                const long long tb = P.bg_off[l] >> 1;
-                F.tk = P.tbl_k + tb; F.tc = P.tbl_cum + tb;
-            } else {
-                const long long b0 = P.bg_off[l];
-                F.uval = P.uv_val + b0; F.ucnt = P.uv_cnt + b0; F.unv = P.uv_n[l];
-                F.nbg = (double)(P.bg_off[l + 1] - b0);
-                if (P.fitter == 1) F.kfac = P.kde_factor[l];
-            }
-            done = front_pq<FIT>(P, F, thr, ns, m, h0, a, S, &kept);
-        }
-        if (!done) {                                   // k_pq takes it (many survivors / many non-class scores)
+        if (ns <= FRONT_SCAP) done = front_pq<FIT>(P, thr, ns, m, hbeg, a, l, tab_n, S, &kept);
+        if (!done) {                                   // k_pq takes it (many survivors / many non-class scores / a failed check)
             if (lane == 0) {
                 P.n_keep[a] = 0;
                 const int slot = atomicAdd(A.pq_count, 1);
-                A.pq_list[slot] = (int)a;
+                A.pq_list[slot] = a;
             }
             continue;
         }
         // ---- the retained HSPs for the chaining: survivor slot, score and (device-resident records) coordinates ------
         if (kept == 0) continue;
-        if (lane == 0 && chain_needs_cta(kept, A.qlen[a], A.slen[a])) { const int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = (int)a; }
+        if (lane == 0 && chain_needs_cta(kept, A.qlen[a], A.slen[a])) { const int slot = atomicAdd(A.mid_count, 1); A.mid_list[slot] = a; }
         __syncwarp();
+        const long long xlo = (long long)floor(thr);
 #pragma unroll 1
         for (int p = lane; p < kept; p += 32) {
-            const int k = S.slot[p];
-            A.ret_slot[h0 + p] = k; A.ret_score[h0 + p] = S.x[k];
+            const int k = S.kept[p];
+            const int v = S.slot[k];
+            A.ret_slot[hbeg + p] = k;
+            A.ret_score[hbeg + p] = v < FRONT_DIRECT ? (double)(xlo + v) : S.ox[v - FRONT_DIRECT];
             if (A.fetch_coords) {
-                const long long h = h0 + A.surv_idx[h0 + k];
+                const long long h = hbeg + S.sidx[k];
                 int4 c;
                 if (A.coords4) c = A.coords4[h];
                 else { c.x = A.qstart[h]; c.y = A.qend[h]; c.z = A.sstart[h]; c.w = A.send[h]; }
-                A.ret_coord[h0 + p] = c;
+                A.ret_coord[hbeg + p] = c;
             }
         }
+    }
+    ticket = __shfl_sync(FULL_MASK, ticket, 0);
     }
 }
 
