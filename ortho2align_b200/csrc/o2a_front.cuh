@@ -516,9 +516,12 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, double thr, int ns, in
 // instruction caches hold 32 KB, and 32 warps per SM in different phases of a large kernel miss them constantly: a variant
 // of this kernel that also gathered coordinates and chained ran at 44 % issue utilisation with 6.9 stall cycles per
 // instruction on instruction fetch); FIT = 1: KDE / empirical.
-// Registers: 64 per thread (8 CTAs per SM) with NOTHING spilled — what is carried from one alignment to the next is
+// Registers: 64 per thread (8 CTAs per SM) with next to nothing spilled (16 bytes, touched once per group) — what is carried from one alignment to the next is
 // kept to a handful of 32-bit values on purpose (a build with 264 bytes of spills ran 8 % slower, one at 48 registers
 // and 10 CTAs per SM 60 % slower: the L1 left beside 170 KB of shared memory does not hold the local memory of 1024 threads).
+// Also measured and not kept (BASELINE config 2, ms per launch): the next alignment's header prefetched through lanes
+// or through cp.async into shared memory (0.563 -> 0.581), L2::128B / evict_last hints on the stream loads (0.557),
+// scans of four tiles as packed shuffle chains after the round instead of one scan per tile (0.674 against 0.647).
 template <typename T, int FIT>
 __global__ void __launch_bounds__(FRONT_WARPS * 32, FRONT_CTAS_PER_SM)
 k_front(const __grid_constant__ FrontArgs A)

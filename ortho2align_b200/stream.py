@@ -47,17 +47,16 @@ class BatchStream:
         done = {}
         cond = threading.Condition()
         errors = []
-        stop = threading.Event()
 
         def worker(device):
             eng = None
             try:
                 eng = self.factory(device)
-                while not stop.is_set():
-                    try:
-                        i, batch = work.get(timeout=0.05)
-                    except queue.Empty:
-                        continue
+                while True:
+                    item = work.get()                     # None = no more work (one per worker, see the end of map)
+                    if item is None:
+                        break
+                    i, batch = item
                     run = eng.build_host if isinstance(batch, HostBatch) else eng.build_batch
                     res = run(batch, fitter, fdr, alpha, gapopen, gapextend, **build_kwargs)
                     with cond:
@@ -108,6 +107,11 @@ class BatchStream:
                     collected += 1
                     yield res
         finally:
-            stop.set()
+            # wake every worker at once (a polling get() here cost up to 50 ms per map() call)
+            for _ in threads:
+                try:
+                    work.put(None, timeout=5)
+                except queue.Full:
+                    pass
             for t in threads:
                 t.join(timeout=5)

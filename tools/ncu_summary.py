@@ -7,3 +7,27 @@ for r in rows[2:]:
     print('----')
     for w in want:
         if w in idx: print(' ', w.replace('smsp__average_warps_issue_stalled_','stall_').replace('_per_issue_active.ratio',''), '=', r[idx[w]], units[idx[w]])
+
+# --traffic OUT.json TAG: record dram__bytes_read + dram__bytes_write per launch of every kernel in the capture under
+# the key "<kernel>|<TAG>" (TAG = "C<config>|<n_lnc>|<fitter>", what bench.py's ncu_traffic() looks up); the capture's
+# file name is kept beside the number so a stale entry can be traced.
+if '--traffic' in sys.argv:
+    import json, os, re
+    out, tag = sys.argv[sys.argv.index('--traffic') + 1], sys.argv[sys.argv.index('--traffic') + 2]
+    table = json.load(open(out)) if os.path.exists(out) else {}
+    to_bytes = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+    acc = {}
+    for r in rows[2:]:
+        name = r[idx['Kernel Name']]
+        m = re.match(r'(?:void )?(\w+)(<[^>]*>)?', name)
+        base = m.group(1)
+        targs = (m.group(2) or '')
+        if base == 'k_front' and targs:               # k_front<double, 0> -> k_front<double>
+            targs = '<' + targs[1:-1].split(',')[0].strip() + '>'
+        key = base + (targs if base == 'k_front' else '')
+        b = sum(float(r[idx[k]]) * to_bytes[units[idx[k]]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        acc.setdefault(key, []).append((b, float(r[idx['gpu__time_duration.sum']])))
+    for key, v in acc.items():
+        table[f'{key}|{tag}'] = {'dram_bytes': sum(x[0] for x in v) / len(v), 'launches': len(v),
+                                 'gpu_time_us_under_ncu': sum(x[1] for x in v) / len(v), 'capture': os.path.basename(sys.argv[1])}
+    json.dump(table, open(out, 'w'), indent=1, sort_keys=True)
