@@ -8,6 +8,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <map>
 #include <vector>
 
 #include "../../include/o2a.h"
@@ -499,6 +500,26 @@ static int grid_for(o2a_ctx* ctx, long long items, int per_sm)
     return (int)g;
 }
 
+// Grid of a persistent (grid-stride) kernel with items of EQUAL cost: exactly the CTAs the device holds at once, so no
+// partly filled last wave is left. The occupancy query is cached per kernel.
+template <typename K>
+static int grid_resident(o2a_ctx* ctx, K kernel, int block, long long items)
+{
+    static std::map<const void*, int> cache;               // per process: the device kind is the same for every ctx
+    static std::mutex mu;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find((const void*)kernel);
+        if (it != cache.end()) per_sm = it->second;
+        else {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+            cache[(const void*)kernel] = per_sm;
+        }
+    }
+    return grid_for(ctx, items, per_sm);
+}
+
 static int run_fit(o2a_ctx* ctx)
 {
     const o2a_batch& b = ctx->b;
@@ -539,12 +560,14 @@ static int run_fit(o2a_ctx* ctx)
         A.fc_val = P<int>(ctx->fc_val) + l0 * FITW_CAP; A.fc_cnt = P<int>(ctx->fc_cnt) + l0 * FITW_CAP;
         A.fc_n = P<int>(ctx->fc_n) + l0;
         A.list = P<int>(ctx->fit_list); A.list_n = P<int>(ctx->fit_list_n);
-        const int gc = grid_for(ctx, nl, 8);
+        int fit_per_sm = 10;
+        if (const char* e = getenv("O2A_FITC_PER_SM")) { if (atoi(e) > 0) fit_per_sm = atoi(e); }
+        const int gc = grid_for(ctx, nl, fit_per_sm);
         if (b.bg_bits == 8) k_fit_count<signed char><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
         else if (b.bg_bits == 16) k_fit_count<short><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
         else k_fit_count<int><<<gc, FITC_THREADS, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
-        k_fit_hist_tail<<<grid_for(ctx, (nl + FITW_WARPS - 1) / FITW_WARPS, 8), FITW_WARPS * 32, 0, ctx->stream>>>(A);
+        k_fit_hist_tail<<<grid_resident(ctx, k_fit_hist_tail, FITW_WARPS * 32, (nl + FITW_WARPS - 1) / FITW_WARPS), FITW_WARPS * 32, 0, ctx->stream>>>(A);
         LAUNCH_CHECK();
     }
     // what this launch cannot take without per-CTA scratch (value range beyond the counters, more distinct values
@@ -751,7 +774,12 @@ static int run_chain(o2a_ctx* ctx, int chunk, cudaStream_t st)
             k_chain_small<<<grid_for(ctx, na, 12), CHAIN_THREADS, 0, st>>>(A);
             LAUNCH_CHECK();
         }
-        k_chain_warp<<<grid_for(ctx, (na + CHAINW_WARPS - 1) / CHAINW_WARPS, 16), CHAINW_WARPS * 32, 0,
+        // more CTAs than the device holds at once (7 per SM at 72 registers), on purpose: the alignments' costs differ,
+        // and the block scheduler hands the queued CTAs to whichever SM frees a slot first (exactly one resident wave:
+        // 0.283 -> 0.323 ms on BASELINE config 2; 16 per SM 0.283, 32: 0.273, 64: 0.266)
+        int chain_per_sm = 64;
+        if (const char* e = getenv("O2A_CHAINW_PER_SM")) { if (atoi(e) > 0) chain_per_sm = atoi(e); }
+        k_chain_warp<<<grid_for(ctx, (na + CHAINW_WARPS - 1) / CHAINW_WARPS, chain_per_sm), CHAINW_WARPS * 32, 0,
                        fork ? ctx->aux_stream : st>>>(A);
         LAUNCH_CHECK();
         if (fork) {
