@@ -183,6 +183,12 @@ int o2a_best_chain(o2a_ctx *ctx, int64_t n, const int32_t *qstart, const int32_t
 #define O2A_STAGE_BEST 6
 #define O2A_STAGE_COUNT 7
 int64_t o2a_launch_count(const o2a_ctx *ctx);
+/* How the last o2a_build_batch issued its kernels: 0 = plain launches; 1 = captured into a CUDA graph and launched;
+ * 2 = replay of that graph (one launch). A DEVICE batch whose pointers, sizes, maxima hints and parameters equal the
+ * previous call's, with stage timing off, is captured on the second such call and replayed from the third (the
+ * reference has no counterpart: its unit of dispatch is one process-pool task per lncRNA, parallel.py:296-488).
+ * Replays count their kernels in o2a_launch_count. Environment O2A_NO_GRAPH=1 disables it. */
+int  o2a_graph_state(const o2a_ctx *ctx);
 /* 1 if the last host-memory o2a_build_batch read the HSP coordinates in place (pinned, mapped) */
 int  o2a_coords_zero_copy(const o2a_ctx *ctx);
 /* number of lncRNA chunks the last o2a_build_batch pipelined its host uploads in (1 = single pass).

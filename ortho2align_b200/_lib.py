@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libo2a_cuda.so")
 EXPORTS = ["o2a_abi_version", "o2a_create", "o2a_destroy", "o2a_last_error", "o2a_set_stream",
            "o2a_host_alloc", "o2a_host_free", "o2a_build_batch", "o2a_fetch_lnc", "o2a_fetch_aln",
            "o2a_fetch_survivors", "o2a_fetch_chains", "o2a_fitter_eval", "o2a_best_chain",
-           "o2a_launch_count", "o2a_coords_zero_copy", "o2a_pipeline_chunks", "o2a_set_coords_mode", "o2a_coords_mode", "o2a_fp64_probe", "o2a_set_timing", "o2a_get_stage_ms",
+           "o2a_launch_count", "o2a_graph_state", "o2a_coords_zero_copy", "o2a_pipeline_chunks", "o2a_set_coords_mode", "o2a_coords_mode", "o2a_fp64_probe", "o2a_set_timing", "o2a_get_stage_ms",
            "o2a_cut_batch", "o2a_fetch_cut", "o2a_cut_view", "o2a_get_cut_ms",
            "o2a_annotate_batch", "o2a_fetch_annotation", "o2a_get_annotate_ms"]
 
@@ -104,6 +104,8 @@ def load():
     lib.o2a_best_chain.argtypes = [P, i64, P, P, P, P, P, i64, i64, i32, i32, P, P, P, P, P, P]
     lib.o2a_launch_count.restype = i64
     lib.o2a_launch_count.argtypes = [P]
+    lib.o2a_graph_state.restype = C.c_int
+    lib.o2a_graph_state.argtypes = [P]
     lib.o2a_coords_zero_copy.restype = C.c_int
     lib.o2a_coords_zero_copy.argtypes = [P]
     lib.o2a_pipeline_chunks.restype = C.c_int

@@ -144,6 +144,14 @@ struct o2a_ctx {
     cudaStream_t copy_stream = nullptr;      // host path: H2D of chunk c+1 overlaps the kernels of chunk c
     cudaEvent_t copy_ev[16] = {};
     int pipelined_chunks = 0;
+    // CUDA graph of the launch sequence of a device-resident batch (same pointers, sizes and parameters as the call
+    // before): captured on the second identical call, replayed from the third; dropped when a buffer is reallocated
+    unsigned long long alloc_epoch = 0;
+    std::vector<long long> graph_key, seen_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_launches = 0;
+    bool graph_disabled = false;
+    int graph_state = 0;                     // last call: 0 eager, 1 captured + launched, 2 replayed
     DevBuf sort_k0, sort_k1, sort_v0, sort_v1;
     DevBuf cb_qs, cb_qe, cb_ss, cb_se, cb_sc, cb_id, cb_total, cb_prev, cb_f, cb_chain;
     DevBuf off_a, off_b, out_i32, out_f64a, out_f64b, out_u8, maxred;
@@ -188,6 +196,7 @@ static int ensure(o2a_ctx* ctx, DevBuf& b, size_t bytes)
     if (bytes == 0) bytes = 16;
     if (b.cap >= bytes) return 0;
     if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    ctx->alloc_epoch++;
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
@@ -389,6 +398,7 @@ static void free_all(o2a_ctx* ctx)
 
 extern "C" void o2a_destroy(o2a_ctx* ctx)
 {
+    if (ctx && ctx->graph_exec) { cudaSetDevice(ctx->device); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -437,6 +447,7 @@ extern "C" void* o2a_host_alloc(size_t bytes)
 extern "C" void o2a_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int64_t o2a_launch_count(const o2a_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
+extern "C" int o2a_graph_state(const o2a_ctx* ctx) { return ctx ? ctx->graph_state : 0; }
 extern "C" int o2a_coords_zero_copy(const o2a_ctx* ctx) { return ctx && ctx->coords_zero_copy ? 1 : 0; }
 extern "C" int o2a_pipeline_chunks(const o2a_ctx* ctx) { return ctx ? ctx->pipelined_chunks : 0; }
 extern "C" int o2a_set_coords_mode(o2a_ctx* ctx, int mode)
@@ -991,6 +1002,37 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         ctx->coords_zero_copy = false;
         if (b.max_aln_hsps <= 0 && (r = find_max_diff(ctx, b.n_aln, (const long long*)b.hsp_off, (long long*)&b.max_aln_hsps))) return r;
         if (b.max_lnc_bg <= 0 && (r = find_max_diff(ctx, b.n_lnc, (const long long*)b.bg_off, (long long*)&b.max_lnc_bg))) return r;
+    }
+    ctx->coords_mode_used = coords_mode;
+    ctx->coords_on_device = batch->mem != O2A_MEM_HOST || coords_mode == O2A_COORDS_UPLOAD;
+
+    // ---- everything below up to the result counters is stream work without a host decision in between. For a
+    // device-resident batch it is captured into a CUDA graph on the second call with identical arguments and replayed
+    // from then on (17 launches of BASELINE config 2 -> one graph launch; what it saves is the launch gaps, which is
+    // most of the step for small shards: config 1, config 5 sharded over 8 GPUs).
+    std::vector<long long> key;
+    bool replay = false, capture = false;
+    ctx->graph_state = 0;
+    if (batch->mem != O2A_MEM_HOST && !ctx->timing && !ctx->graph_disabled && !getenv("O2A_NO_GRAPH") &&
+        batch->max_aln_hsps > 0 && batch->max_lnc_bg > 0) {
+        const long long fields[] = {
+            batch->n_lnc, batch->n_aln, batch->n_hsp, batch->n_bg, (long long)batch->bg_off, (long long)batch->bg,
+            (long long)batch->kde_factor, (long long)batch->aln_off, (long long)batch->hsp_off, (long long)batch->qlen,
+            (long long)batch->slen, (long long)batch->qstart, (long long)batch->qend, (long long)batch->sstart,
+            (long long)batch->send, (long long)batch->score, batch->mem, batch->max_aln_hsps, batch->max_lnc_bg,
+            (long long)batch->coords, batch->score_bits, batch->bg_bits, (long long)batch->score_q, (long long)batch->exc_off,
+            (long long)batch->exc_pos, (long long)batch->exc_val, params->fitter, params->fdr,
+            __builtin_bit_cast(long long, params->alpha), params->gapopen, params->gapextend, params->best_value,
+            params->best_function, (long long)ctx->stream, (long long)ctx->alloc_epoch};
+        key.assign(fields, fields + sizeof(fields) / sizeof(fields[0]));
+        if (ctx->graph_exec && key == ctx->graph_key) replay = true;
+        else if (key == ctx->seen_key) capture = true;
+    }
+    if (!replay && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
+
+    auto stream_work = [&]() -> int {
+    int r;
+    if (batch->mem != O2A_MEM_HOST) {
         // caller-supplied maxima of a device batch are verified on the device, without an extra synchronisation:
         // the true maxima travel back with the result counters and an understated hint fails the call
         ENS(maxchk, 16);
@@ -998,8 +1040,6 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         if (b.n_aln > 0) { k_max_diff<<<grid_for(ctx, (b.n_aln + 255) / 256, 4), 256, 0, ctx->stream>>>(b.n_aln, (const long long*)b.hsp_off, P<unsigned long long>(ctx->maxchk)); LAUNCH_CHECK(); }
         if (b.n_lnc > 0) { k_max_diff<<<grid_for(ctx, (b.n_lnc + 255) / 256, 4), 256, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.bg_off, P<unsigned long long>(ctx->maxchk) + 1); LAUNCH_CHECK(); }
     }
-    ctx->coords_mode_used = coords_mode;
-    ctx->coords_on_device = batch->mem != O2A_MEM_HOST || coords_mode == O2A_COORDS_UPLOAD;
     ENS(aln_lnc, b.n_aln * sizeof(int));
     if (b.n_lnc > 0) {
         k_fill_aln_lnc<<<grid_for(ctx, b.n_lnc, 16), 64, 0, ctx->stream>>>(b.n_lnc, (const long long*)b.aln_off, P<int>(ctx->aln_lnc));
@@ -1172,6 +1212,46 @@ extern "C" int o2a_build_batch(o2a_ctx* ctx, const o2a_batch* batch, const o2a_p
         LAUNCH_CHECK();
     }
     if ((r = stage_event(ctx, O2A_STAGE_COUNT))) return r;
+    return 0;
+    };   // stream_work
+
+    if (replay) {
+        CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        ctx->launches += ctx->graph_launches;
+        ctx->vl0 = 0; ctx->vl1 = b.n_lnc; ctx->va0 = 0; ctx->va1 = b.n_aln;
+        ctx->graph_state = 2;
+    } else {
+        bool captured = false;
+        if (capture) {
+            const long long launches0 = ctx->launches;
+            const unsigned long long epoch0 = ctx->alloc_epoch;
+            cudaGraph_t g = nullptr;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = stream_work();
+                const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &g);
+                if (rc == 0 && ee == cudaSuccess && g && ctx->alloc_epoch == epoch0 &&
+                    cudaGraphInstantiate(&ctx->graph_exec, g, 0) == cudaSuccess &&
+                    cudaGraphLaunch(ctx->graph_exec, ctx->stream) == cudaSuccess) {
+                    ctx->graph_key = key;
+                    ctx->graph_launches = ctx->launches - launches0;
+                    ctx->graph_state = 1;
+                    captured = true;
+                } else {
+                    // anything the capture could not take: this context goes back to plain launches for good
+                    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+                    ctx->graph_disabled = true;
+                    ctx->launches = launches0;
+                }
+                if (g) cudaGraphDestroy(g);
+            } else ctx->graph_disabled = true;
+            cudaGetLastError();
+        }
+        if (!captured) {
+            if ((r = stream_work())) return r;
+        }
+        ctx->seen_key = key;
+        if (!key.empty()) ctx->seen_key.back() = (long long)ctx->alloc_epoch;   // the epoch after this call's allocations
+    }
     unsigned long long c[5], mx[2] = {0, 0};
     CU(cudaMemcpyAsync(c, ctx->counters.p, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
     if (batch->mem != O2A_MEM_HOST) CU(cudaMemcpyAsync(mx, ctx->maxchk.p, sizeof(mx), cudaMemcpyDeviceToHost, ctx->stream));

@@ -163,6 +163,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.o2a_launch_count(self.h))
 
+    def graph_state(self):
+        """How the last `run` was issued: 0 plain launches, 1 captured into a CUDA graph and launched, 2 graph replay."""
+        return int(self.lib.o2a_graph_state(self.h))
+
     def fp64_probe(self, kind="dfma", iters=20000):
         """Sustained FP64 rate of the device: 'dfma' -> fused multiply-adds per second, 'ndtr' -> ndtr evaluations per second."""
         v = C.c_double(0.0)

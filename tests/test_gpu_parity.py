@@ -410,3 +410,47 @@ def test_batch_stream_with_real_engines(engine):
         assert e1.h and e2.h                                   # caller-owned engines stay open
     finally:
         e1.close(); e2.close()
+
+
+def test_cuda_graph_replay_of_a_device_batch(engine):
+    """A device-resident batch issued again with identical arguments (stage timing off) is captured into a CUDA graph
+    on the second call and replayed from the third: every call returns the oracle's result, a changed parameter or a
+    different batch goes back to plain launches, and o2a_launch_count keeps counting the kernels of a replay."""
+    import torch
+    from ortho2align_b200 import synth
+    from ortho2align_b200.engine import DeviceBatch, Engine
+    from oracle import oracle as O
+    eng = Engine(0)                                   # own context: the shared fixture has stage timing on
+    try:
+        eng.set_timing(False)
+        dev = torch.device("cuda", 0)
+        for fitter, cfg, kw in (("hist", 2, dict(n_lnc=40, seed=61)), ("kde", 2, dict(n_lnc=12, seed=62, hsps_per_region=500)),
+                                ("hist", 4, dict(n_lnc=3, seed=63, hsps_per_region=2500)), ("hist", 5, dict(n_lnc=300, seed=64))):
+            b = synth.workload(cfg, **kw)
+            want = O.build_batch(b, fitter, True)
+            db = DeviceBatch(b, dev, aos=True)
+            s, p = db.struct(with_kde=(fitter == "kde")), eng.params(fitter, True)
+            states, per_call = [], []
+            for k in range(5):
+                l0 = eng.launch_count()
+                eng.run(s, p)
+                states.append(eng.graph_state()); per_call.append(eng.launch_count() - l0)
+                compare_results(eng.fetch(), want, exact_p=(fitter == "hist"), what=f"{fitter} C{cfg} call {k}")
+            # (the first fetch allocates its staging buffers, which postpones the capture by one call)
+            assert states[0] == 0 and states.count(1) == 1 and states[-2:] == [2, 2], states
+            assert states.index(1) < states.index(2) and per_call[-1] == per_call[0] > 0, (states, per_call)
+            # a changed parameter: plain launches again, and the result follows the parameter
+            p2 = eng.params(fitter, True, alpha=0.01)
+            eng.run(s, p2)
+            assert eng.graph_state() == 0
+            compare_results(eng.fetch(), O.build_batch(b, fitter, True, alpha=0.01), exact_p=(fitter == "hist"), what="alpha 0.01")
+            eng.run(s, p)
+            compare_results(eng.fetch(), want, exact_p=(fitter == "hist"), what="back to alpha 0.05")
+        # stage timing on: never a graph
+        eng.set_timing(True)
+        for _ in range(3):
+            eng.run(s, p)
+            assert eng.graph_state() == 0
+        assert sum(eng.stage_ms().values()) > 0
+    finally:
+        eng.close()
