@@ -407,9 +407,26 @@ __device__ __forceinline__ bool front_pq(const PqArgs& A, double thr, int ns, in
     // ---- non-class scores: p, key, order inside an odd key -------------------------------------------------------
     if (nover > 0) {
         double p = 0.0; int key = 0;
+        const PqFit F = front_fit_of<FIT>(A, l);
+        bool have_p = false;
+        if (FIT == 1 && F.fitter == 1 && nover * ((F.unv + 31) >> 5) < F.unv) {
+            // KDE: a few scores against many background values — the warp shares each sum (lane-strided partial sums,
+            // fixed xor tree: the same order for every score, so the results stay monotone in the score among
+            // themselves; against the table's sequential sums the order can differ in the last bit, which the checks
+            // below catch) instead of one lane walking all values per score
+#pragma unroll 1
+            for (int o = 0; o < nover; ++o) {
+                const double xo = __shfl_sync(FULL_MASK, ox, o);
+                double acc = 0.0;
+                for (int i = lane; i < F.unv; i += 32) acc += (double)F.ucnt[i] * ndtr_dev((xo - (double)F.uval[i]) / F.kfac);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, d);
+                if (lane == o) p = 1.0 - acc / F.nbg;
+            }
+            have_p = true;
+        }
         if (lane < nover) {
-            const PqFit F = front_fit_of<FIT>(A, l);
-            p = front_sf<FIT>(ox, F);
+            if (!have_p) p = front_sf<FIT>(ox, F);
             if (o_beyond) {
                 const double pl = S.ptab[FRONT_DIRECT - 1];
                 if (!(p <= pl)) bad = true;
