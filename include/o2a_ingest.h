@@ -27,6 +27,10 @@ void o2a_ingest_destroy(o2a_ingest *g);
 /* Parse n_files (alignment file, background file) pairs. A missing background file is the
  * reference's `[0, 1]` case; a missing/malformed alignment file gets file status 1; values outside
  * the int32 columnar types get status 2. Always returns 0 unless the arguments are invalid. */
+/* Size and modification time (ns) of n files, stat'ed on n_threads threads (<= 0: hardware concurrency); size -1 =
+ * missing. Guards the columnar sidecar (ortho2align_b200/ingest.py::_manifest); no reference counterpart. */
+int o2a_stat_files(const char *const *paths, int64_t n, int n_threads, int64_t *size, int64_t *mtime_ns);
+
 int o2a_ingest_load(o2a_ingest *g, const char *const *align_paths, const char *const *bg_paths, int64_t n_files);
 
 /* Totals over the files with status 0 (in input order; each such file is one lncRNA). */

@@ -71,6 +71,7 @@ struct FrontArgs {
     const long long* qlen; const long long* slen;
     int* mid_list; int* mid_count;        // alignments the warp path of the chaining cannot take (-> k_chain_small)
     int chunk_aln; int* ticket;           // groups of chunk_aln (>= 1) consecutive alignments are handed out through *ticket
+    int pf_tiles;                         // float64 stream: L2 prefetch distance in 4 KB tiles beyond the tile being loaded (0 = off)
 };
 
 struct __align__(16) FrontWarpSmem {
@@ -148,8 +149,29 @@ __device__ __forceinline__ void front_load16(const double* __restrict__ sc, long
     }
 }
 
+// One 128-byte line per lane = one 4 KB tile per warp, requested from DRAM into L2 and nothing else: no register and no
+// shared memory is tied up, so the bytes a warp has in flight are no longer bounded by the 32 registers of its tile.
+__device__ __forceinline__ void front_prefetch_tile(const double* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+#ifndef O2A_FRONT_CPX
+#define O2A_FRONT_CPX 1
+#endif
+// survivor score -> S.x[p] by an asynchronous 8-byte global->shared copy (LDGSTS: no register, no scoreboard wait at the
+// point of issue); the line has just been streamed, so the copy is served by L2
+__device__ __forceinline__ void front_copy_score_async(double* dst_smem, const double* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void front_copy_wait()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score, long long n_total, long long h0, int m,
-                                                     double t, int* __restrict__ out_idx, FrontWarpSmem& S)
+                                                     double t, int* __restrict__ out_idx, FrontWarpSmem& S, int pf_tiles)
 {
     const int lane = lane_id();
     const int sh = (int)(h0 & 3);
@@ -159,11 +181,18 @@ __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score
     int base = 0;
     double v[16];
     front_load16(sc, g0, n_total, lane * 16, t, v, g0 + 512 <= n_total);
+    // The prefetch runs ahead of the loads by pf_tiles tiles and does not stop at the alignment's end: the scores of the
+    // group's next alignment follow in memory and are streamed by this warp next.
+    const long long pf_lim = n_total - g0 - 16;        // last element offset a lane's line may start at
+    if (pf_tiles > 0) {
+        for (int k = 1; k <= pf_tiles; ++k) { const long long e = 512ll * k + lane * 16; if (e <= pf_lim) front_prefetch_tile(sc + e); }
+    }
 #pragma unroll 1
     for (int t0 = 0; t0 < ms; t0 += 512) {
         const int e0 = t0 + lane * 16;
         unsigned mask = front_mask16(v, t);
         if (t0 + 512 < ms) front_load16(sc, g0, n_total, e0 + 512, t, v, g0 + t0 + 1024 <= n_total);
+        if (pf_tiles > 0) { const long long e = (long long)e0 + 512ll * (pf_tiles + 1); if (e <= pf_lim) front_prefetch_tile(sc + e); }
         const int left = ms - e0;
         if (left < 16) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
         if (t0 == 0 && lane == 0) mask &= ~((1u << sh) - 1u);
@@ -178,11 +207,19 @@ __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score
             const int c = __ffs(mask) - 1;
             mask &= mask - 1;
             out_idx[p] = e0 + c - sh;
-            if (p < FRONT_SCAP) S.sidx[p] = e0 + c - sh;
+            if (p < FRONT_SCAP) {
+                S.sidx[p] = e0 + c - sh;
+#if O2A_FRONT_CPX
+                front_copy_score_async(&S.x[p], sc + e0 + c);
+#endif
+            }
             ++p;
         }
         base += total;
     }
+#if O2A_FRONT_CPX
+    front_copy_wait();
+#endif
     return base;
 }
 
@@ -570,7 +607,7 @@ k_front(const __grid_constant__ FrontArgs A)
         }
         int ns;
         __syncwarp();                                  // the previous alignment is done with S
-        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S);
+        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S, A.pf_tiles);
         else {
             const long long x0 = A.exc_off[a];
             ns = front_filter_q<T>(reinterpret_cast<const T*>(A.score_q), A.n_hsp_total, hbeg, m, thr, A.exc_pos, A.exc_val,
@@ -579,20 +616,22 @@ k_front(const __grid_constant__ FrontArgs A)
         if (lane == 0) A.n_surv[a] = ns;
         if (ns == 0) { if (lane == 0) P.n_keep[a] = 0; continue; }
         __syncwarp();
-        // the survivors' scores: independent loads, all in flight together (float64: L2-resident lines of the stream
-        // just read; narrow: what the filter has just written)
+        // the survivors' scores in S.x. float64: copied asynchronously while the filter placed them (or, without
+        // O2A_FRONT_CPX, independent loads of the L2-resident lines all in flight together); narrow: what the filter has
+        // just written. surv_x in HBM is read by k_pq and k_retained_slots only, i.e. for the alignments queued below.
         double* out_x = A.surv_x + hbeg;
         {
-            double xr[FRONT_XR];
             if constexpr (sizeof(T) == 8) {
+#if !O2A_FRONT_CPX
+                double xr[FRONT_XR];
                 const double* al = A.score + hbeg;
 #pragma unroll
                 for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; xr[j] = k < ns ? al[S.sidx[k]] : 0.0; }
 #pragma unroll
-                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; if (k < ns) { out_x[k] = xr[j]; S.x[k] = xr[j]; } }
-#pragma unroll 1
-                for (int k = FRONT_SCAP + lane; k < ns; k += 32) out_x[k] = al[A.surv_idx[hbeg + k]];
+                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; if (k < ns) S.x[k] = xr[j]; }
+#endif
             } else if (ns <= FRONT_SCAP) {
+                double xr[FRONT_XR];
 #pragma unroll
                 for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; xr[j] = k < ns ? __ldcg(out_x + k) : 0.0; }
 #pragma unroll
@@ -604,6 +643,11 @@ k_front(const __grid_constant__ FrontArgs A)
         int kept = 0;
         if (ns <= FRONT_SCAP) done = front_pq<FIT>(P, thr, ns, m, hbeg, a, l, tab_n, S, &kept);
         if (!done) {                                   // k_pq takes it (many survivors / many non-class scores / a failed check)
+            if constexpr (sizeof(T) == 8) {            // ... and reads the survivors' scores from HBM
+                const double* al = A.score + hbeg;
+#pragma unroll 1
+                for (int k = lane; k < ns; k += 32) out_x[k] = k < FRONT_SCAP ? S.x[k] : al[A.surv_idx[hbeg + k]];
+            }
             if (lane == 0) {
                 P.n_keep[a] = 0;
                 const int slot = atomicAdd(A.pq_count, 1);

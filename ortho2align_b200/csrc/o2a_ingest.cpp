@@ -558,6 +558,22 @@ extern "C" int o2a_ingest_load(o2a_ingest* g, const char* const* align_paths, co
     return 0;
 }
 
+// size and mtime (ns) of n files on a pool of threads; size -1 = the file cannot be stat'ed (sidecar manifest check:
+// 2 x 10^5 os.stat calls from Python cost more than memory-mapping the sidecar they guard)
+extern "C" int o2a_stat_files(const char* const* paths, int64_t n, int n_threads, int64_t* size, int64_t* mtime_ns)
+{
+    if (!paths || !size || !mtime_ns || n < 0) return 1;
+    const int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    o2a_pack::parallel_for(nt, n, [&](int64_t i) {
+        struct stat st;
+        if (paths[i] && stat(paths[i], &st) == 0) {
+            size[i] = (int64_t)st.st_size;
+            mtime_ns[i] = (int64_t)st.st_mtim.tv_sec * 1000000000ll + (int64_t)st.st_mtim.tv_nsec;
+        } else { size[i] = -1; mtime_ns[i] = 0; }
+    });
+    return 0;
+}
+
 extern "C" int o2a_ingest_sizes(const o2a_ingest* g, int64_t* n_lnc, int64_t* n_aln, int64_t* n_hsp, int64_t* n_bg)
 {
     if (!g) return -1;

@@ -35,6 +35,8 @@ def load_lib():
         lib.o2a_ingest_destroy.argtypes = [P]
         lib.o2a_ingest_load.restype = C.c_int
         lib.o2a_ingest_load.argtypes = [P, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), i64]
+        lib.o2a_stat_files.restype = C.c_int
+        lib.o2a_stat_files.argtypes = [C.POINTER(C.c_char_p), i64, C.c_int, P, P]
         lib.o2a_ingest_sizes.restype = C.c_int
         lib.o2a_ingest_sizes.argtypes = [P] + [C.POINTER(i64)] * 4
         lib.o2a_ingest_export.restype = C.c_int
@@ -214,14 +216,16 @@ _SIDECAR_ARRAYS = ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart
 
 
 def _manifest(align_files, bg_files):
-    """What makes a sidecar stale: the ordered file list with sizes and mtimes (missing bg files included)."""
-    def stat(p):
-        try:
-            st = os.stat(p)
-            return [st.st_size, st.st_mtime_ns]
-        except OSError:
-            return None
-    return [[os.path.basename(a), stat(a), stat(b)] for a, b in zip(align_files, bg_files)]
+    """What makes a sidecar stale: the ordered file list with sizes and mtimes (missing bg files included). The files
+    are stat'ed by the native library on a pool of threads (`o2a_stat_files`)."""
+    lib = load_lib()
+    n = len(align_files)
+    paths = (C.c_char_p * (2 * n))(*[os.fsencode(p) for p in align_files], *[os.fsencode(p) for p in bg_files])
+    size, mtime = np.empty(2 * n, dtype=np.int64), np.empty(2 * n, dtype=np.int64)
+    if lib.o2a_stat_files(paths, 2 * n, 0, size.ctypes.data_as(C.c_void_p), mtime.ctypes.data_as(C.c_void_p)) != 0:
+        raise RuntimeError("o2a_stat_files failed")
+    st = [[sz, mt] if sz >= 0 else None for sz, mt in zip(size.tolist(), mtime.tolist())]
+    return [[a.rsplit(os.sep, 1)[-1], sa, sb] for a, sa, sb in zip(align_files, st[:n], st[n:])]
 
 
 def save_sidecar(path, r, align_files, bg_files):

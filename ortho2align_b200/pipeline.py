@@ -106,17 +106,45 @@ def _ingest_native(alignments_files, bg_files, threads, cache=None):
         with open(alignments_files[i]) as f:
             d = json.load(f)
         out[i] = ExceptionLogger(PackError(r.errors[int(i)]), Range.from_dict(d[0]["qrange"]) if d else None)
-    b = r.host                               # the pinned narrow layout: handed to the library as is
-    aln_off, hsp_off = b.aln_off.tolist(), b.hsp_off
-    rel = r.relative
-    for l, i in enumerate(r.lnc_file.tolist()):
-        a0, a1 = aln_off[l], aln_off[l + 1]
-        out[i] = (b, l, a1 - a0,
-                  (lambda k, a0=a0: r.range_dict(a0 + k, "q")), (lambda k, a0=a0: r.range_dict(a0 + k, "s")),
-                  (lambda k, idx, a0=a0: r.hsp_dicts(int(hsp_off[a0 + k]) + idx)),
-                  (r, a0),                   # columnar source of the lncRNA's HSPs, for the native record formatter
-                  (lambda k, a0=a0: bool(rel[a0 + k])))
-    return out
+    return _NativeLoaded(r, out)
+
+
+class _NativeLoaded:
+    """The per-file items of a native ingest, built on demand: with 10^5 lncRNAs the tuples and accessor closures of every
+    file cost more than parsing them, and the columnar assembly (`_assemble_columnar`) never looks at one. Indexing and
+    iteration give what the list of `_ingest_json` holds: an ExceptionLogger, or (source batch, lncRNA index in it,
+    n_alignments, qrange_of, srange_of, hsps_of, (columnar source, first alignment), relative_of)."""
+
+    def __init__(self, r, errors):
+        self.r, self.b = r, r.host           # the pinned narrow layout: handed to the library as is
+        self.errors = {i: x for i, x in enumerate(errors) if x is not None}
+        self.n = len(errors)
+        lnc_file = np.asarray(r.lnc_file)
+        self.lnc_of_file = np.full(self.n, -1, dtype=np.int64)
+        self.lnc_of_file[lnc_file] = np.arange(len(lnc_file))
+
+    def __len__(self):
+        return self.n
+
+    def ok_indices(self):
+        return np.nonzero(self.lnc_of_file >= 0)[0].tolist()
+
+    def __getitem__(self, i):
+        if i in self.errors:
+            return self.errors[i]
+        r, b, l = self.r, self.b, int(self.lnc_of_file[i])
+        if l < 0:
+            return None
+        a0, a1 = int(b.aln_off[l]), int(b.aln_off[l + 1])
+        hsp_off, rel = b.hsp_off, r.relative
+        return (b, l, a1 - a0,
+                (lambda k: r.range_dict(a0 + k, "q")), (lambda k: r.range_dict(a0 + k, "s")),
+                (lambda k, idx: r.hsp_dicts(int(hsp_off[a0 + k]) + idx)),
+                (r, a0),                     # columnar source of the lncRNA's HSPs, for the native record formatter
+                (lambda k: bool(rel[a0 + k])))
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
 
 
 def _run_shards(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
@@ -284,7 +312,8 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     t_phase = time.perf_counter()
     loaded = _ingest_native(alignments_files, bg_files, cores, cache) if ingest == "native" \
         else _ingest_json(alignments_files, bg_files)
-    ok_idx = [i for i, x in enumerate(loaded) if not isinstance(x, ExceptionLogger)]
+    native_loaded = isinstance(loaded, _NativeLoaded)
+    ok_idx = loaded.ok_indices() if native_loaded else [i for i, x in enumerate(loaded) if not isinstance(x, ExceptionLogger)]
 
     PHASES["ingest"] = time.perf_counter() - t_phase - PHASES.get("sidecar_write", 0.0)
     t_phase = time.perf_counter()
@@ -292,15 +321,19 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     per_lnc = {}
     if ok_idx:
         n_dev = min(len(devices), len(ok_idx))
-        src, src_l = [loaded[i][0] for i in ok_idx], [loaded[i][1] for i in ok_idx]
-        one_source = all(x is src[0] for x in src)             # native ingest: every lncRNA lives in one batch
-        if one_source:
-            per_lnc_hsps = src[0].hsp_off[src[0].aln_off[1:]] - src[0].hsp_off[src[0].aln_off[:-1]]
-            weights = (per_lnc_hsps[src_l] + 1).tolist()
+        if native_loaded:                                       # every lncRNA lives in one batch
+            src, src_l, one_source = [loaded.b], loaded.lnc_of_file[ok_idx].tolist(), True
         else:
-            weights = [x.n_hsp + 1 for x in src]
-        shards = lpt_shards(weights, n_dev)
-        if one_source and n_dev == 1 and shards[0] == list(range(src[0].n_lnc)):
+            src, src_l = [loaded[i][0] for i in ok_idx], [loaded[i][1] for i in ok_idx]
+            one_source = all(x is src[0] for x in src)
+        if n_dev == 1:
+            shards = [list(range(len(ok_idx)))]
+        elif one_source:
+            per_lnc_hsps = src[0].hsp_off[src[0].aln_off[1:]] - src[0].hsp_off[src[0].aln_off[:-1]]
+            shards = lpt_shards((per_lnc_hsps[src_l] + 1).tolist(), n_dev)
+        else:
+            shards = lpt_shards([x.n_hsp + 1 for x in src], n_dev)
+        if one_source and n_dev == 1 and src_l == list(range(src[0].n_lnc)):
             batches = [src[0]]                                  # the ingest's buffers, untouched
         elif one_source:
             columnar = src[0].to_columnar() if hasattr(src[0], "to_columnar") else src[0]
@@ -308,22 +341,21 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
         else:
             batches = [concat_batches([src[j] for j in shard]) for shard in shards]
         results = _run_shards(batches, devices[:n_dev], fitting, fdr, threshold, gapopen, gapextend)
-        for shard, batch, res in zip(shards, batches, results):
-            for local, j in enumerate(shard):
-                per_lnc[ok_idx[j]] = (batch, res, local)
 
     PHASES["compute"] = time.perf_counter() - t_phase
     t_phase = time.perf_counter()
     # ---- assemble exactly what the pool would have returned ---------------------------------------------
     fast = None
-    if ingest == "native" and records == "native" and ok_idx and len(batches) == 1 and batches[0] is loaded[ok_idx[0]][0]:
-        r_src = loaded[ok_idx[0]][6][0]
-        fast = _assemble_columnar(r_src, results[0], {i: x for i, x in enumerate(loaded) if isinstance(x, ExceptionLogger)},
-                                  len(loaded), cores)
+    if native_loaded and records == "native" and ok_idx and len(batches) == 1 and batches[0] is loaded.b:
+        fast = _assemble_columnar(loaded.r, results[0], loaded.errors, len(loaded), cores)
     orthologs, exceptions = [], []
     if fast is not None:
         native_text_fast, dist_found_fast, dropped_fast, exceptions = fast
         loaded = []                                                   # nothing left for the per-alignment path
+    elif ok_idx:
+        for shard, batch, res in zip(shards, batches, results):
+            for local, j in enumerate(shard):
+                per_lnc[ok_idx[j]] = (batch, res, local)
     # native record formatting: per chain (result object, chain slice, first HSP of its alignment in the source batch)
     chain_desc, chain_strings, chain_qplus, chain_src = [], [], [], None
     for i, item in enumerate(loaded):
