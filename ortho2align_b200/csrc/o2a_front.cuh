@@ -223,6 +223,98 @@ __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score
     return base;
 }
 
+#ifndef O2A_FRONT_ROWS
+#define O2A_FRONT_ROWS 0
+#endif
+// Row layout of the float64 filter (O2A_FRONT_ROWS = 1): the 512-score tile is four rows of 128 scores and lane i owns
+// scores [4 i, 4 i + 4) of EVERY row, so each 32-byte load of the warp covers 1 KB of consecutive memory (eight full
+// lines per request instead of one sector of 32 different lines). v[4 q + c] / mask bit 4 q + c = score 128 q + 4 i + c
+// of the tile. Order-preserving positions need the lanes' counts per row: the four counts (<= 4 each, row totals
+// <= 128) are scanned together as the bytes of one word, so the scan costs what the single count of the lane layout did.
+__device__ __forceinline__ void front_load_rows(const double* __restrict__ sc, long long g0, long long n_total, int t0, int lane,
+                                                double t, double (&v)[16], bool inside)
+{
+    const double* p0 = sc + t0 + 4 * lane;
+    if (inside) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ld_stream_f64x4(p0 + 128 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long left = n_total - (g0 + t0 + 128 * q + 4 * lane);
+        if (left >= 4) ld_stream_f64x4(p0 + 128 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[4 * q + c] = c < left ? p0[128 * q + c] : t;
+        }
+    }
+}
+
+__device__ __forceinline__ int front_filter_f64_rows(const double* __restrict__ score, long long n_total, long long h0, int m,
+                                                     double t, int* __restrict__ out_idx, FrontWarpSmem& S)
+{
+    const int lane = lane_id();
+    const int sh = (int)(h0 & 3);
+    const double* sc = score + h0 - sh;
+    const long long g0 = h0 - sh;
+    const int ms = m + sh;
+    int base = 0;
+    double v[16];
+    front_load_rows(sc, g0, n_total, 0, lane, t, v, g0 + 512 <= n_total);
+#pragma unroll 1
+    for (int t0 = 0; t0 < ms; t0 += 512) {
+        unsigned mask = front_mask16(v, t);
+        if (t0 + 512 < ms) front_load_rows(sc, g0, n_total, t0 + 512, lane, t, v, g0 + t0 + 1024 <= n_total);
+        const int e0 = t0 + 4 * lane;                  // my first score of row 0
+        if (t0 + 512 > ms) {                           // the alignment ends inside this tile (warp-uniform)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int left = ms - (e0 + 128 * q);
+                const unsigned keep = left >= 4 ? 0xfu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                mask &= ~(0xfu << (4 * q)) | (keep << (4 * q));
+            }
+        }
+        if (t0 == 0 && lane == 0) mask &= ~((1u << sh) - 1u);
+        const unsigned pk = (unsigned)__popc(mask & 0xfu) | ((unsigned)__popc(mask & 0xf0u) << 8) |
+                            ((unsigned)__popc(mask & 0xf00u) << 16) | ((unsigned)__popc(mask & 0xf000u) << 24);
+        unsigned incl = pk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += y; }
+        const unsigned tot = __shfl_sync(FULL_MASK, incl, 31);
+        const unsigned excl = incl - pk;
+        // first position of my survivors of row q, relative to `base`: the totals of the rows before + the lanes before me
+        // (row totals can reach 128: the running sums over the rows need more than a byte)
+        const int T0 = tot & 0xff, T1 = (tot >> 8) & 0xff, T2 = (tot >> 16) & 0xff, T3 = tot >> 24;
+        const int s0 = (int)(excl & 0xff), s1 = T0 + (int)((excl >> 8) & 0xff), s2 = T0 + T1 + (int)((excl >> 16) & 0xff),
+                  s3 = T0 + T1 + T2 + (int)(excl >> 24);
+        const unsigned long long W = (unsigned long long)s0 | ((unsigned long long)s1 << 16) | ((unsigned long long)s2 << 32) |
+                                     ((unsigned long long)s3 << 48);
+        int curq = -1, p = 0;
+#pragma unroll 1
+        while (mask) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int q = c >> 2;
+            if (q != curq) { curq = q; p = base + (int)((W >> (16 * q)) & 0xffffull); }
+            const int e = e0 + (q << 7) + (c & 3);
+            out_idx[p] = e - sh;
+            if (p < FRONT_SCAP) {
+                S.sidx[p] = e - sh;
+#if O2A_FRONT_CPX
+                front_copy_score_async(&S.x[p], sc + e);
+#endif
+            }
+            ++p;
+        }
+        base += T0 + T1 + T2 + T3;
+    }
+#if O2A_FRONT_CPX
+    front_copy_wait();
+#endif
+    return base;
+}
+
 // ---- filter phase, narrow scores (int8 / int16 / int32 + exception lists; see QTraits' contract) -----------------
 // Survivor positions to out_idx and (first FRONT_SCAP) S.sidx, survivor scores to out_x.
 template <typename T>
@@ -607,7 +699,11 @@ k_front(const __grid_constant__ FrontArgs A)
         }
         int ns;
         __syncwarp();                                  // the previous alignment is done with S
+#if O2A_FRONT_ROWS
+        if constexpr (sizeof(T) == 8) ns = front_filter_f64_rows(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S);
+#else
         if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S, A.pf_tiles);
+#endif
         else {
             const long long x0 = A.exc_off[a];
             ns = front_filter_q<T>(reinterpret_cast<const T*>(A.score_q), A.n_hsp_total, hbeg, m, thr, A.exc_pos, A.exc_val,
