@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 
 import numpy as np
 
@@ -215,12 +216,18 @@ _SIDECAR_ALIGN = 4096
 _SIDECAR_ARRAYS = ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score")
 
 
+def _encode_paths(paths):
+    """os.fsencode of every path, without its per-call type dispatch for the usual list of str."""
+    enc, err = sys.getfilesystemencoding(), sys.getfilesystemencodeerrors()
+    return [p.encode(enc, err) if type(p) is str else os.fsencode(p) for p in paths]
+
+
 def _manifest(align_files, bg_files):
     """What makes a sidecar stale: the ordered file list with sizes and mtimes (missing bg files included). The files
     are stat'ed by the native library on a pool of threads (`o2a_stat_files`)."""
     lib = load_lib()
     n = len(align_files)
-    paths = (C.c_char_p * (2 * n))(*[os.fsencode(p) for p in align_files], *[os.fsencode(p) for p in bg_files])
+    paths = (C.c_char_p * (2 * n))(*_encode_paths(align_files), *_encode_paths(bg_files))
     size, mtime = np.empty(2 * n, dtype=np.int64), np.empty(2 * n, dtype=np.int64)
     if lib.o2a_stat_files(paths, 2 * n, 0, size.ctypes.data_as(C.c_void_p), mtime.ctypes.data_as(C.c_void_p)) != 0:
         raise RuntimeError("o2a_stat_files failed")
@@ -348,8 +355,8 @@ def load_files(align_files, bg_files, threads=0, pinned=True, pin_coords=False) 
     lib = load_lib()
     n = len(align_files)
     h = C.c_void_p(lib.o2a_ingest_create(int(threads)))
-    arr_a = (C.c_char_p * n)(*[os.fsencode(p) for p in align_files])
-    arr_b = (C.c_char_p * n)(*[os.fsencode(p) for p in bg_files])
+    arr_a = (C.c_char_p * n)(*_encode_paths(align_files))
+    arr_b = (C.c_char_p * n)(*_encode_paths(bg_files))
     if lib.o2a_ingest_load(h, arr_a, arr_b, n) != 0:
         raise RuntimeError("o2a_ingest_load failed")
     return IngestResult(lib, h, n, pinned=pinned, pin_coords=pin_coords)
