@@ -63,8 +63,9 @@ extern "C" {
 #define O2A_STATUS_ORIENTATION_NONE 1  /* alignment.py:865-872 KeyError/TypeError */
 #define O2A_STATUS_BRENTQ 2            /* fitting.py:239 RuntimeError (no convergence) */
 #define O2A_STATUS_TOO_MANY_BINS 3     /* fitting.py:152 np.histogram ValueError */
-#define O2A_STATUS_UNSUPPORTED 4       /* library limit, not a reference error: background value range
-                                          > 2^18 or > 512 distinct background values (hist) */
+#define O2A_STATUS_UNSUPPORTED 4       /* round 1: library limit on the background's value range / distinct values.
+                                          No longer produced — any integer background is fitted (the general path
+                                          sorts it in HBM scratch); the value stays reserved */
 
 #define O2A_EINVAL (-1)
 #define O2A_ECUDA (-2)

@@ -14,7 +14,7 @@ STATUS_OK = 0
 STATUS_ORIENTATION_NONE = 1     # KeyError/TypeError in _split_orientations (alignment.py:865-872)
 STATUS_BRENTQ_NOT_CONVERGED = 2  # RuntimeError from scipy.optimize.brentq (fitting.py:239)
 STATUS_TOO_MANY_BINS = 3        # ValueError from np.histogram (fitting.py:152)
-STATUS_UNSUPPORTED = 4          # library limit (background value range / distinct values), not a reference error
+STATUS_UNSUPPORTED = 4          # reserved (round 1's fitter envelope; no longer produced)
 
 
 @dataclass
