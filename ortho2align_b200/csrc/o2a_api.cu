@@ -668,10 +668,6 @@ static int run_score(o2a_ctx* ctx, int chunk, cudaStream_t st)
         F.chunk_aln = (int)per_lnc;
         if (const char* e = getenv("O2A_FRONT_CHUNK")) { if (atoi(e) > 0) F.chunk_aln = atoi(e); }
     }
-    // L2 prefetch of the float64 score stream: measured on BASELINE config 2, k_front per launch 0.541 ms without,
-    // 0.558 / 0.615 / 0.723 / 0.831 ms with 1 / 2 / 4 / 6 tiles of distance — off; the knob stays for other shapes
-    F.pf_tiles = 0;
-    if (const char* e = getenv("O2A_FRONT_PF")) F.pf_tiles = atoi(e) < 0 ? 0 : (atoi(e) > 8 ? 8 : atoi(e));
 #define O2A_FRONT(T) do { if (p.fitter == O2A_FIT_HIST) k_front<T, 0><<<grid, FRONT_WARPS * 32, 0, st>>>(F); \
                          else k_front<T, 1><<<grid, FRONT_WARPS * 32, 0, st>>>(F); } while (0)
     if (b.score_bits == 8) O2A_FRONT(signed char);

@@ -20,8 +20,8 @@
 //   grp[s]   first slot of the run of equal p that s belongs to (sf is non-increasing in the score; the table is
 //            CHECKED to be non-increasing — anything else sends the lncRNA's alignments to k_pq)
 //
-// The filter streams the alignment's scores (float64: 32-byte loads, a 4 KB tile in flight per warp) and writes the
-// survivors IN ORDER (popc + warp scan per tile) into the alignment's slot [hsp_off[a], hsp_off[a] + n_surv) of the
+// The filter streams the alignment's scores (float64: 32-byte loads covering 1 KB of consecutive memory per warp request,
+// a 4 KB tile in flight per warp) and writes the survivors IN ORDER (popc + one packed warp scan per tile) into the alignment's slot [hsp_off[a], hsp_off[a] + n_surv) of the
 // survivor arrays.
 //
 // Ranks (np.argsort(kind='stable') of the p-values, rank_k = 1 + #{p_j < p_k} + #{j < k : p_j == p_k}) come from
@@ -71,7 +71,6 @@ struct FrontArgs {
     const long long* qlen; const long long* slen;
     int* mid_list; int* mid_count;        // alignments the warp path of the chaining cannot take (-> k_chain_small)
     int chunk_aln; int* ticket;           // groups of chunk_aln (>= 1) consecutive alignments are handed out through *ticket
-    int pf_tiles;                         // float64 stream: L2 prefetch distance in 4 KB tiles beyond the tile being loaded (0 = off)
 };
 
 struct __align__(16) FrontWarpSmem {
@@ -108,12 +107,7 @@ __device__ __forceinline__ int4 ld_stream_16(const void* p)
 }
 
 // ---- filter phase, float64 scores: returns n_surv; survivor positions to global slots and (first FRONT_SCAP) S.sidx --
-// Tile = 512 scores; lane i owns the 16 CONSECUTIVE scores [16 i, 16 i + 16) of the tile (four 32-byte loads, one
-// full DRAM sector each: LDG.E.256 on sm_100), so the order-preserving position of a survivor is
-//   (survivors of earlier tiles) + (exclusive warp scan of the per-lane counts) + (rank inside the lane's 16 bits).
-// The loads of tile t + 1 are issued right after tile t's compares, so their DRAM latency hides under the scan and the
-// placement of tile t. (Scanning four tiles' counts together as packed shuffle chains saves shuffles but leaves nothing
-// to overlap the loads with: 0.67 against 0.65 ms on BASELINE config 2.)
+// Tile = 512 scores = 4 KB per warp in flight (see front_filter_f64 for the layout).
 __device__ __forceinline__ void ld_stream_f64x4(const double* p, double& a, double& b, double& c, double& d)
 {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
@@ -126,34 +120,6 @@ __device__ __forceinline__ unsigned front_mask16(const double (&v)[16], double t
 #pragma unroll
     for (int c = 0; c < 16; ++c) mask |= (v[c] > t ? 1u : 0u) << c;
     return mask;
-}
-
-__device__ __forceinline__ void front_load16(const double* __restrict__ sc, long long g0, long long n_total, int e0, double t,
-                                             double (&v)[16], bool inside)
-{
-    // vector loads may run past the alignment's end (the next alignment's scores, masked by the caller) but not past
-    // the end of the score array; `inside` (warp-uniform): the whole tile is inside the array
-    if (inside) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ld_stream_f64x4(sc + e0 + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        return;
-    }
-    const long long left = n_total - (g0 + e0);        // the last tile of the whole array: my scores inside it
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (left >= 4 * q + 4) ld_stream_f64x4(sc + e0 + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        else {
-#pragma unroll
-            for (int c = 4 * q; c < 4 * q + 4; ++c) v[c] = c < left ? sc[e0 + c] : t;
-        }
-    }
-}
-
-// One 128-byte line per lane = one 4 KB tile per warp, requested from DRAM into L2 and nothing else: no register and no
-// shared memory is tied up, so the bytes a warp has in flight are no longer bounded by the 32 registers of its tile.
-__device__ __forceinline__ void front_prefetch_tile(const double* p)
-{
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
 #ifndef O2A_FRONT_CPX
@@ -170,67 +136,16 @@ __device__ __forceinline__ void front_copy_wait()
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-__device__ __forceinline__ int front_filter_f64(const double* __restrict__ score, long long n_total, long long h0, int m,
-                                                     double t, int* __restrict__ out_idx, FrontWarpSmem& S, int pf_tiles)
-{
-    const int lane = lane_id();
-    const int sh = (int)(h0 & 3);
-    const double* sc = score + h0 - sh;
-    const long long g0 = h0 - sh;
-    const int ms = m + sh;
-    int base = 0;
-    double v[16];
-    front_load16(sc, g0, n_total, lane * 16, t, v, g0 + 512 <= n_total);
-    // The prefetch runs ahead of the loads by pf_tiles tiles and does not stop at the alignment's end: the scores of the
-    // group's next alignment follow in memory and are streamed by this warp next.
-    const long long pf_lim = n_total - g0 - 16;        // last element offset a lane's line may start at
-    if (pf_tiles > 0) {
-        for (int k = 1; k <= pf_tiles; ++k) { const long long e = 512ll * k + lane * 16; if (e <= pf_lim) front_prefetch_tile(sc + e); }
-    }
-#pragma unroll 1
-    for (int t0 = 0; t0 < ms; t0 += 512) {
-        const int e0 = t0 + lane * 16;
-        unsigned mask = front_mask16(v, t);
-        if (t0 + 512 < ms) front_load16(sc, g0, n_total, e0 + 512, t, v, g0 + t0 + 1024 <= n_total);
-        if (pf_tiles > 0) { const long long e = (long long)e0 + 512ll * (pf_tiles + 1); if (e <= pf_lim) front_prefetch_tile(sc + e); }
-        const int left = ms - e0;
-        if (left < 16) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
-        if (t0 == 0 && lane == 0) mask &= ~((1u << sh) - 1u);
-        const int cnt = __popc(mask);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += y; }
-        const int total = __shfl_sync(FULL_MASK, incl, 31);
-        int p = base + incl - cnt;
-#pragma unroll 1
-        while (mask) {
-            const int c = __ffs(mask) - 1;
-            mask &= mask - 1;
-            out_idx[p] = e0 + c - sh;
-            if (p < FRONT_SCAP) {
-                S.sidx[p] = e0 + c - sh;
-#if O2A_FRONT_CPX
-                front_copy_score_async(&S.x[p], sc + e0 + c);
-#endif
-            }
-            ++p;
-        }
-        base += total;
-    }
-#if O2A_FRONT_CPX
-    front_copy_wait();
-#endif
-    return base;
-}
-
-#ifndef O2A_FRONT_ROWS
-#define O2A_FRONT_ROWS 0
-#endif
-// Row layout of the float64 filter (O2A_FRONT_ROWS = 1): the 512-score tile is four rows of 128 scores and lane i owns
-// scores [4 i, 4 i + 4) of EVERY row, so each 32-byte load of the warp covers 1 KB of consecutive memory (eight full
-// lines per request instead of one sector of 32 different lines). v[4 q + c] / mask bit 4 q + c = score 128 q + 4 i + c
-// of the tile. Order-preserving positions need the lanes' counts per row: the four counts (<= 4 each, row totals
-// <= 128) are scanned together as the bytes of one word, so the scan costs what the single count of the lane layout did.
+// Row layout: the 512-score tile is four rows of 128 scores and lane i owns scores [4 i, 4 i + 4) of EVERY row, so each
+// 32-byte load of the warp (LDG.E.256) covers 1 KB of consecutive memory — eight full lines per request.
+// v[4 q + c] / mask bit 4 q + c = score 128 q + 4 i + c of the tile. Order-preserving positions need the lanes' counts
+// per row: the four counts (<= 4 each, row totals <= 128) are scanned together as the bytes of one word, so the scan
+// costs what a single count would. The loads of tile t + 1 are issued right after tile t's compares, so their DRAM
+// latency hides under the scan and the placement of tile t.
+// (Until round 2's last change lane i owned 16 CONSECUTIVE scores: one scan of plain counts, but every request touched
+// one 32-byte sector of 32 different lines, four requests per line: 0.539 ms per launch on BASELINE config 2 against
+// 0.484 ms with full-line requests. Scanning four tiles' counts together as packed shuffle chains saves shuffles but
+// leaves nothing to overlap the loads with: 0.67 against 0.65 ms.)
 __device__ __forceinline__ void front_load_rows(const double* __restrict__ sc, long long g0, long long n_total, int t0, int lane,
                                                 double t, double (&v)[16], bool inside)
 {
@@ -251,7 +166,7 @@ __device__ __forceinline__ void front_load_rows(const double* __restrict__ sc, l
     }
 }
 
-__device__ __forceinline__ int front_filter_f64_rows(const double* __restrict__ score, long long n_total, long long h0, int m,
+__device__ __forceinline__ int front_filter_f64(const double* __restrict__ score, long long n_total, long long h0, int m,
                                                      double t, int* __restrict__ out_idx, FrontWarpSmem& S)
 {
     const int lane = lane_id();
@@ -699,11 +614,7 @@ k_front(const __grid_constant__ FrontArgs A)
         }
         int ns;
         __syncwarp();                                  // the previous alignment is done with S
-#if O2A_FRONT_ROWS
-        if constexpr (sizeof(T) == 8) ns = front_filter_f64_rows(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S);
-#else
-        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S, A.pf_tiles);
-#endif
+        if constexpr (sizeof(T) == 8) ns = front_filter_f64(A.score, A.n_hsp_total, hbeg, m, thr, A.surv_idx + hbeg, S);
         else {
             const long long x0 = A.exc_off[a];
             ns = front_filter_q<T>(reinterpret_cast<const T*>(A.score_q), A.n_hsp_total, hbeg, m, thr, A.exc_pos, A.exc_val,
