@@ -384,8 +384,11 @@ __device__ __forceinline__ WarpChainResult warp_chain(int r, int qs, int qe, int
         if (is_begin) { Qs = 0; Qe = 0; Ss = gD ? 0 : slen; Se = Ss; Sc = 0.0; }        // alignment.py:893-902
         if (is_end) { Qs = qlen; Qe = qlen; Ss = gD ? slen : 0; Se = Ss; Sc = 0.0; }
         if (!gD) { Ss = ~Ss; Se = ~Se; }                          // reverse graph: complemented subject axis
-        const long long in_sum = (long long)Qs + (long long)Ss;   // what an edge INTO me adds to the distance
-        const long long out_sum = (long long)Qe + (long long)Se;  // what an edge OUT of me subtracts
+        // what an edge INTO me adds to the distance and what an edge OUT of me subtracts, as doubles: both sums are
+        // integers below 2^33, so is their difference, hence din - dout_i is exact and equals (double)(in_sum - out_sum_i)
+        // — one DADD per step instead of a 64-bit subtraction and an I2F.F64.S64
+        const double din = (double)((long long)Qs + (long long)Ss);
+        const double dout = (double)((long long)Qe + (long long)Se);
         const unsigned below_end = (N0 + N1) >= 32 ? 0xffffffffu : ((1u << (N0 + N1)) - 1u);
         const unsigned gmask = !active ? 0u : (gD ? ((N0 >= 32) ? 0xffffffffu : ((1u << N0) - 1u)) : (below_end & ~((1u << N0) - 1u)));
         const int steps = max(N0, N1);
@@ -413,9 +416,9 @@ __device__ __forceinline__ WarpChainResult warp_chain(int r, int qs, int qe, int
             const int i = (base + s) & 31;
             const unsigned e_i = __shfl_sync(FULL_MASK, Ed, i);
             const double t_i = __shfl_sync(FULL_MASK, tot, i);
-            const long long o_i = __shfl_sync(FULL_MASK, out_sum, i);
+            const double o_i = __shfl_sync(FULL_MASK, dout, i);
             // an unreached source carries +inf and cannot improve anything; a lane outside the edge mask does not relax
-            const double nsc = __dadd_rn(t_i, __dsub_rn(__dadd_rn(G, __dmul_rn(E, (double)(in_sum - o_i))), Sc));
+            const double nsc = __dadd_rn(t_i, __dsub_rn(__dadd_rn(G, __dmul_rn(E, __dsub_rn(din, o_i))), Sc));
             if (((e_i >> v) & 1u) && me > s && tot > nsc) { tot = nsc; prev = i; }
         }
         // ---- scores and backtrack (alignment.py:1007-1013) --------------------------------------------------------
@@ -468,7 +471,10 @@ __device__ __forceinline__ WarpChainResult warp_chain(int r, int qs, int qe, int
     return R;
 }
 
-__global__ void __launch_bounds__(CHAINW_WARPS * 32)
+#ifndef O2A_CHAINW_MIN_CTAS
+#define O2A_CHAINW_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(CHAINW_WARPS * 32, O2A_CHAINW_MIN_CTAS)
 k_chain_warp(ChainArgs A)
 {
     __shared__ unsigned char s_mem[CHAINW_WARPS][CHAINW_SMEM];

@@ -213,17 +213,20 @@ __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score
             const int q = c >> 2;
             if (q != curq) { curq = q; p = base + (int)((W >> (16 * q)) & 0xffffull); }
             const int e = e0 + (q << 7) + (c & 3);
-            out_idx[p] = e - sh;
             if (p < FRONT_SCAP) {
                 S.sidx[p] = e - sh;
 #if O2A_FRONT_CPX
                 front_copy_score_async(&S.x[p], sc + e);
 #endif
-            }
+            } else out_idx[p] = e - sh;
             ++p;
         }
         base += T0 + T1 + T2 + T3;
     }
+    // the first FRONT_SCAP positions go to HBM as a few full-width stores instead of one scattered 4-byte store per
+    // survivor (133 store requests per alignment on BASELINE config 2 become 5)
+    __syncwarp();
+    for (int k = lane; k < min(base, FRONT_SCAP); k += 32) out_idx[k] = S.sidx[k];
 #if O2A_FRONT_CPX
     front_copy_wait();
 #endif
@@ -231,7 +234,8 @@ __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score
 }
 
 // ---- filter phase, narrow scores (int8 / int16 / int32 + exception lists; see QTraits' contract) -----------------
-// Survivor positions to out_idx and (first FRONT_SCAP) S.sidx, survivor scores to out_x.
+// Survivor positions and scores: the first FRONT_SCAP to S.sidx / S.x (positions then to out_idx as full-width stores),
+// the rest straight to out_idx / out_x.
 template <typename T>
 __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, long long n_hsp_total, long long h0, int m,
                                               double t, const int* __restrict__ exc_pos, const double* __restrict__ exc_val,
@@ -330,8 +334,8 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
                                 x = exc_val[x0 + lo];
                             }
                         }
-                        out_idx[p] = ep + c; out_x[p] = x;
-                        if (p < FRONT_SCAP) S.sidx[p] = ep + c;
+                        if (p < FRONT_SCAP) { S.sidx[p] = ep + c; S.x[p] = x; }
+                        else { out_idx[p] = ep + c; out_x[p] = x; }
                         ++p;
                     }
                 }
@@ -339,6 +343,8 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
             base += rowtot;
         }
     }
+    __syncwarp();
+    for (int k = lane; k < min(base, FRONT_SCAP); k += 32) out_idx[k] = S.sidx[k];       // full-width stores
     return base;
 }
 
@@ -623,9 +629,9 @@ k_front(const __grid_constant__ FrontArgs A)
         if (lane == 0) A.n_surv[a] = ns;
         if (ns == 0) { if (lane == 0) P.n_keep[a] = 0; continue; }
         __syncwarp();
-        // the survivors' scores in S.x. float64: copied asynchronously while the filter placed them (or, without
-        // O2A_FRONT_CPX, independent loads of the L2-resident lines all in flight together); narrow: what the filter has
-        // just written. surv_x in HBM is read by k_pq and k_retained_slots only, i.e. for the alignments queued below.
+        // the survivors' scores are in S.x. float64: copied asynchronously while the filter placed them (or, without
+        // O2A_FRONT_CPX, independent loads of the L2-resident lines all in flight together); narrow: stored by the filter.
+        // surv_x in HBM is read by k_pq and k_retained_slots only, i.e. for the alignments queued below.
         double* out_x = A.surv_x + hbeg;
         {
             if constexpr (sizeof(T) == 8) {
@@ -637,12 +643,6 @@ k_front(const __grid_constant__ FrontArgs A)
 #pragma unroll
                 for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; if (k < ns) S.x[k] = xr[j]; }
 #endif
-            } else if (ns <= FRONT_SCAP) {
-                double xr[FRONT_XR];
-#pragma unroll
-                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; xr[j] = k < ns ? __ldcg(out_x + k) : 0.0; }
-#pragma unroll
-                for (int j = 0; j < FRONT_XR; ++j) { const int k = 32 * j + lane; if (k < ns) S.x[k] = xr[j]; }
             }
         }
         __syncwarp();
@@ -654,6 +654,9 @@ k_front(const __grid_constant__ FrontArgs A)
                 const double* al = A.score + hbeg;
 #pragma unroll 1
                 for (int k = lane; k < ns; k += 32) out_x[k] = k < FRONT_SCAP ? S.x[k] : al[A.surv_idx[hbeg + k]];
+            } else {                                   // narrow: the filter wrote the scores beyond FRONT_SCAP itself
+#pragma unroll 1
+                for (int k = lane; k < min(ns, FRONT_SCAP); k += 32) out_x[k] = S.x[k];
             }
             if (lane == 0) {
                 P.n_keep[a] = 0;

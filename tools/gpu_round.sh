@@ -17,4 +17,8 @@ if [ "$NCU" = "ncu" ]; then
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_front|k_chain_warp|k_fit_count|k_fit_hist_tail|k_gather_retained' \
       --launch-skip 10 -c 5 -o $OUT/full_c2 -f python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
   ncu -i $OUT/full_c2.ncu-rep --page raw --csv > $OUT/full_c2_raw.csv 2>/dev/null
+  # the KDE branch: k_fit<int> (value compression + brentq) and k_front<double, 1> (class table by value-compressed ndtr sums)
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_front|k_fit' \
+      --launch-skip 6 -c 4 -o $OUT/full_c2_kde -f python bench.py --fitter kde --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/ncu_full_kde.log 2>&1; echo "ncu full kde rc=$?"
+  ncu -i $OUT/full_c2_kde.ncu-rep --page raw --csv > $OUT/full_c2_kde_raw.csv 2>/dev/null
 fi
