@@ -233,6 +233,33 @@ __device__ __forceinline__ int front_filter_f64(const double* __restrict__ score
     return base;
 }
 
+// One 16-byte load of narrow scores -> bit c of `msk`: score c > tq, bit c of `sent`: score c is the exception sentinel.
+// int8: the 16 scores are compared inside their 32-bit words (__vcmpgts4 / __vcmpeq4: about 3.5 instructions per score
+// instead of extract + two compares + two inserts each) and the per-byte flags are packed by one multiplication.
+// tq is clamped to the type's maximum first: no score can exceed it, none may pass.
+template <typename T>
+__device__ __forceinline__ void front_cmp_row(const int4& raw, int tq, unsigned& msk, unsigned& sent)
+{
+    if constexpr (sizeof(T) == 1) {
+        const unsigned t4 = (unsigned)(tq > 127 ? 127 : tq) & 0xffu, tb = t4 * 0x01010101u;
+        const unsigned w[4] = {(unsigned)raw.x, (unsigned)raw.y, (unsigned)raw.z, (unsigned)raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned gt = __vcmpgts4(w[j], tb) & 0x01010101u, eq = __vcmpeq4(w[j], 0x80808080u) & 0x01010101u;
+            msk |= ((gt * 0x01020408u) >> 24) << (4 * j);          // flag of byte b -> bit b
+            sent |= ((eq * 0x01020408u) >> 24) << (4 * j);
+        }
+    } else {                                             // int16 measured no faster with __vcmpgts2 (0.886 against 0.862 ms)
+        constexpr int SENT = QTraits<T>::SENT;
+#pragma unroll
+        for (int c = 0; c < QTraits<T>::PER; ++c) {
+            const int q = q_at<T>(raw, c);
+            msk |= (q > tq ? 1u : 0u) << c;
+            sent |= (q == SENT ? 1u : 0u) << c;
+        }
+    }
+}
+
 // ---- filter phase, narrow scores (int8 / int16 / int32 + exception lists; see QTraits' contract) -----------------
 // Survivor positions and scores: the first FRONT_SCAP to S.sidx / S.x (positions then to out_idx as full-width stores),
 // the rest straight to out_idx / out_x.
@@ -288,12 +315,7 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
         for (int r = 0; r < ROWS; ++r) {
             const int e = t0 + r * ROWLEN + lane * PER;  // stream index of my first score of this row
             unsigned msk = 0, sent = 0;
-#pragma unroll
-            for (int c = 0; c < PER; ++c) {
-                const int q = q_at<T>(raw[r], c);
-                msk |= (q > tq ? 1u : 0u) << c;
-                sent |= (q == SENT ? 1u : 0u) << c;
-            }
+            front_cmp_row<T>(raw[r], tq, msk, sent);
             if (e < sh || e + PER > ms) {                // lanes straddling the alignment borders
                 unsigned inside = 0;
 #pragma unroll
@@ -319,25 +341,27 @@ __device__ __forceinline__ int front_filter_q(const T* __restrict__ score_q, lon
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += y; }
             const int rowtot = __shfl_sync(FULL_MASK, incl, 31);
-            if (msk) {
+            {
+                // one iteration per survivor of the lane (a few per row), not one per score (a fully predicated walk over
+                // the row's 16 / 8 scores cost more than the compares: 1.06 ms per C2 launch with int8 scores)
                 int p = base + incl - cnt;
                 const int ep = e - sh;                   // HSP position of my first score of this row
-#pragma unroll
-                for (int c = 0; c < PER; ++c) {
-                    if ((msk >> c) & 1u) {
-                        double x = (double)q_at<T>(raw[r], c);
-                        if ((sent_pass >> c) & 1u) {     // a passing exception: its exact float64 value
-                            if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (e_pos[i] == ep + c) { x = e_val[i]; break; } }
-                            else {
-                                int lo = 0, hi = ne;
-                                while (lo < hi) { const int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < ep + c) lo = mid + 1; else hi = mid; }
-                                x = exc_val[x0 + lo];
-                            }
+                unsigned mm = msk;
+#pragma unroll 1
+                while (mm) {
+                    const int c = __ffs(mm) - 1; mm &= mm - 1;
+                    double x = (double)q_at<T>(raw[r], c);
+                    if ((sent_pass >> c) & 1u) {         // a passing exception: its exact float64 value
+                        if (np <= FRONT_PASS) { for (int i = 0; i < np; ++i) if (e_pos[i] == ep + c) { x = e_val[i]; break; } }
+                        else {
+                            int lo = 0, hi = ne;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (exc_pos[x0 + mid] < ep + c) lo = mid + 1; else hi = mid; }
+                            x = exc_val[x0 + lo];
                         }
-                        if (p < FRONT_SCAP) { S.sidx[p] = ep + c; S.x[p] = x; }
-                        else { out_idx[p] = ep + c; out_x[p] = x; }
-                        ++p;
                     }
+                    if (p < FRONT_SCAP) { S.sidx[p] = ep + c; S.x[p] = x; }
+                    else { out_idx[p] = ep + c; out_x[p] = x; }
+                    ++p;
                 }
             }
             base += rowtot;
