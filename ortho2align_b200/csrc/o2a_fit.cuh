@@ -642,9 +642,11 @@ k_fit_hist_tail(FitArgs A)
     __shared__ double s_lsum[FITW_WARPS][FITW_CAP];
     __shared__ short s_ldep[FITW_WARPS][FITW_CAP];
     __shared__ short s_rep[FITW_WARPS][FITW_CAP];
+    __shared__ double s_hp0[FITW_WARPS][FITW_CAP];       // hp0 and bin width of every non-empty bin: three divisions and two
+    __shared__ double s_w[FITW_WARPS][FITW_CAP];         // edges per bin that the normalised pass would otherwise repeat
     const int lane = lane_id(), w = warp_id();
     int* K = s_k[w]; int* Cn = s_c[w]; double* T = s_t[w]; double* LS = s_lsum[w]; short* LD = s_ldep[w];
-    short* RP = s_rep[w];
+    short* RP = s_rep[w]; double* HP = s_hp0[w]; double* WW = s_w[w];
     const double NaN = __longlong_as_double(0x7ff8000000000000ll);
     const long long nwarps = (long long)gridDim.x * FITW_WARPS;
     for (long long l = (long long)blockIdx.x * FITW_WARPS + w; l < A.n_lnc; l += nwarps) {
@@ -705,14 +707,21 @@ k_fit_hist_tail(FitArgs A)
                 __syncwarp();
             }
             const double total = (double)n;
-            for (int t = lane; t < nnz; t += 32) { double hp0, ww; T[t] = fit_term(Cn[t], K[t], f, total, &hp0, &ww); }
+            for (int t = lane; t < nnz; t += 32) { double hp0, ww; T[t] = fit_term(Cn[t], K[t], f, total, &hp0, &ww); HP[t] = hp0; WW[t] = ww; }
             __syncwarp();
             // numpy pairwise sum: leaves (heads sum their leaf), then precedence evaluation
-            for (int t = lane; t < nnz; t += 32) {
-                const PwLeaf L = pw_find_leaf(K[t], B);
+            for (int t0 = 0; t0 < nnz; t0 += 32) {
+                const int t = t0 + lane;
+                // every lane takes part in the shuffles; lanes past the end compute a leaf nobody uses
+                const PwLeaf L = pw_find_leaf(K[t < nnz ? t : nnz - 1], B);
+                // the leaf of entry t - 1: the neighbouring lane has just found it (lane 0: an entry of the previous round)
+                PwLeaf P;
+                P.off = __shfl_up_sync(FULL_MASK, L.off, 1); P.n = __shfl_up_sync(FULL_MASK, L.n, 1);
+                P.depth = __shfl_up_sync(FULL_MASK, L.depth, 1); P.path = __shfl_up_sync(FULL_MASK, L.path, 1);
+                if (lane == 0 && t > 0) P = pw_find_leaf(K[t - 1], B);
+                if (t >= nnz) continue;
                 bool head = true; int dep = -1;
                 if (t > 0) {
-                    const PwLeaf P = pw_find_leaf(K[t - 1], B);
                     head = (P.off != L.off);
                     if (head) dep = pw_lca_depth(P, L);
                 }
@@ -749,11 +758,7 @@ k_fit_hist_tail(FitArgs A)
                 __syncwarp();
             }
             double S = nnz > 0 ? LS[0] : 0.0;
-            for (int t = lane; t < nnz; t += 32) {
-                double hp0, ww;
-                fit_term(Cn[t], K[t], f, total, &hp0, &ww);
-                T[t] = __dmul_rn(__ddiv_rn(hp0, S), ww);
-            }
+            for (int t = lane; t < nnz; t += 32) T[t] = __dmul_rn(__ddiv_rn(HP[t], S), WW[t]);
             __syncwarp();
             if (lane == 0) {
                 double acc = 0.0;                          // np.cumsum: sequential left to right
