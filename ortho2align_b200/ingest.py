@@ -211,7 +211,7 @@ def _hsp_dict(b, score_is_int, h):
 # straight into pinned buffers) without any parsing.
 # --------------------------------------------------------------------------------------------------
 SIDECAR_MAGIC = b"O2ACOL01"
-SIDECAR_VERSION = 3
+SIDECAR_VERSION = 4
 _SIDECAR_ALIGN = 4096
 _SIDECAR_ARRAYS = ("bg_off", "bg", "aln_off", "hsp_off", "qlen", "slen", "qstart", "qend", "sstart", "send", "score")
 
@@ -223,16 +223,18 @@ def _encode_paths(paths):
 
 
 def _manifest(align_files, bg_files):
-    """What makes a sidecar stale: the ordered file list with sizes and mtimes (missing bg files included). The files
-    are stat'ed by the native library on a pool of threads (`o2a_stat_files`)."""
+    """What makes a sidecar stale: the ordered file list with sizes and mtimes (missing bg files: size -1), as three
+    arrays — names (newline-joined basenames, uint8), sizes and mtimes (int64, alignment files then background files).
+    The files are stat'ed by the native library on a pool of threads (`o2a_stat_files`); at 10^5 lncRNAs a JSON manifest
+    cost more to decode and compare than the mapped arrays it guards."""
     lib = load_lib()
     n = len(align_files)
     paths = (C.c_char_p * (2 * n))(*_encode_paths(align_files), *_encode_paths(bg_files))
     size, mtime = np.empty(2 * n, dtype=np.int64), np.empty(2 * n, dtype=np.int64)
     if lib.o2a_stat_files(paths, 2 * n, 0, size.ctypes.data_as(C.c_void_p), mtime.ctypes.data_as(C.c_void_p)) != 0:
         raise RuntimeError("o2a_stat_files failed")
-    st = [[sz, mt] if sz >= 0 else None for sz, mt in zip(size.tolist(), mtime.tolist())]
-    return [[a.rsplit(os.sep, 1)[-1], sa, sb] for a, sa, sb in zip(align_files, st[:n], st[n:])]
+    names = "\n".join(a.rsplit(os.sep, 1)[-1] for a in align_files).encode("utf-8", "surrogateescape")
+    return np.frombuffer(names, dtype=np.uint8), size, mtime
 
 
 def save_sidecar(path, r, align_files, bg_files):
@@ -248,7 +250,9 @@ def save_sidecar(path, r, align_files, bg_files):
     name_off, name_blob, q_plus, simple = r.range_fields()
     sections["name_off"], sections["name_blob"] = np.ascontiguousarray(name_off), np.ascontiguousarray(name_blob)
     sections["q_plus"], sections["simple"] = np.ascontiguousarray(q_plus), np.ascontiguousarray(simple)
-    directory = {"version": SIDECAR_VERSION, "n_files": len(align_files), "manifest": _manifest(align_files, bg_files), "sections": {}}
+    man_names, man_size, man_mtime = _manifest(align_files, bg_files)
+    sections["man_names"], sections["man_size"], sections["man_mtime"] = np.ascontiguousarray(man_names), man_size, man_mtime
+    directory = {"version": SIDECAR_VERSION, "n_files": len(align_files), "sections": {}}
     # two passes: the directory's own length decides where the first section starts
     def layout(base):
         off = base
@@ -291,6 +295,7 @@ class SidecarResult:
         self.lnc_file = arr("lnc_file")
         self._range_off, self._range_text = arr("range_off"), arr("range_text")
         self._fields = (arr("name_off"), arr("name_blob"), arr("q_plus"), arr("simple"))
+        self._manifest = (arr("man_names"), arr("man_size"), arr("man_mtime"))
         self._host = None
         self.file_status = np.zeros(directory["n_files"], dtype=np.int32)
         self.errors = {}
@@ -344,9 +349,13 @@ def open_sidecar(path, align_files, bg_files):
             directory = json.loads(f.read(int(np.frombuffer(pre[8:], dtype=np.int64)[0])))
     except (OSError, ValueError):
         return None
-    if directory.get("version") != SIDECAR_VERSION or directory.get("manifest") != _manifest(align_files, bg_files):
+    if directory.get("version") != SIDECAR_VERSION or directory.get("n_files") != len(align_files):
         return None
-    return SidecarResult(path, directory)
+    r = SidecarResult(path, directory)
+    names, size, mtime = _manifest(align_files, bg_files)
+    if not (np.array_equal(r._manifest[0], names) and np.array_equal(r._manifest[1], size) and np.array_equal(r._manifest[2], mtime)):
+        return None
+    return r
 
 
 def load_files(align_files, bg_files, threads=0, pinned=True, pin_coords=False) -> IngestResult:
