@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import json
 import os
+import re
 import threading
 import time
 from collections import Counter
@@ -212,6 +213,25 @@ def _format_chains_native(chain_desc, strings, qplus, src, threads):
                                          pval, np.asarray(qplus, dtype=np.uint8), strings, threads=threads or 1)
 
 
+# A range object exactly as `json.dump(GenomicRange.to_dict())` writes it when it has no relations (every subject range of
+# an alignment file): fixed key order, plain ASCII strings. Anything else (escapes, other key order, nested relations)
+# does not match and goes through json.loads + Range.from_dict.
+_PLAIN_RANGE = re.compile(
+    rb'\{"chrom": "([^"\\]*)", "start": (-?\d+), "end": (-?\d+), "strand": "([^"\\]*)", "genome": (null|"[^"\\]*"), '
+    rb'"sequence_file_path": \{"path": (?:null|"[^"\\]*")\}, "name": (null|"[^"\\]*"), "relations": \{\}, '
+    rb'"relations_class": null\}\Z')
+
+
+def _plain_range(text):
+    """`Range.from_dict(json.loads(text))` for the common flat form, or None."""
+    m = _PLAIN_RANGE.match(text)
+    if m is None:
+        return None
+    chrom, start, end, strand, genome, name = m.groups()
+    return Range(chrom.decode(), int(start), int(end), strand.decode(),
+                 None if name == b"null" else name[1:-1].decode(), None if genome == b"null" else genome[1:-1].decode(), None)
+
+
 def _assemble_columnar(r, res, loaded_errors, n_files, threads):
     """The records of a whole run from columnar data, without a Python object per alignment: the native ingest's range
     fields (`IngestResult.range_fields`) + the batch result -> (native_text, dist_found, dropped (query Range, [subject
@@ -270,7 +290,7 @@ def _assemble_columnar(r, res, loaded_errors, n_files, threads):
             qd = r.range_dict(a, "q")
             if qd is not last_qd:
                 last_qd, qrange = qd, Range.from_dict(qd)
-            srange = Range.from_dict(r.range_dict(a, "s"))
+            srange = _plain_range(r.range_text(a, "s")) or Range.from_dict(r.range_dict(a, "s"))
             srange.name = qrange.name
             q_dropped = qrange
             s_dropped.append(srange)
