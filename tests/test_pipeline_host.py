@@ -302,3 +302,36 @@ def test_native_get_best_orthologs_declines_what_it_would_not_decide_like_python
         else:
             pipeline.get_best_orthologs(*paths, value, "max", *outs)
             assert open(outs[0]).read().count("\n") == 1
+
+
+def test_plain_range_fast_path_equals_json_decode():
+    """pipeline._plain_range (one anchored regular expression for the flat subject ranges of dropped lncRNAs) returns
+    what Range.from_dict(json.loads(text)) returns, or None for anything it does not cover (escapes, relations, other
+    key orders, non-string chrom) — then the caller falls back to the JSON decode."""
+    import random
+    from ortho2align_b200.pipeline import _plain_range
+    from ortho2align_b200.records import Range
+    rng = random.Random(5)
+    names = [None, "lnc1", "gene (copy)", "a\\b", 'q"uote', "naïve", ""]
+    covered = 0
+    for _ in range(400):
+        d = {"chrom": rng.choice(["chr1", "chrX", "scaffold_12", 'c"hr', 7]), "start": rng.randint(-10, 10 ** 9),
+             "end": rng.randint(0, 10 ** 9), "strand": rng.choice(["+", "-", "."]), "genome": rng.choice([None, "hg38", "mm10"]),
+             "sequence_file_path": {"path": rng.choice([None, "/data/genome.fa"])}, "name": rng.choice(names),
+             "relations": rng.choice([{}, {}, {}, {"lifted": {"collection": [], "sequence_file_path": {"path": None},
+                                                            "grange_class": "GenomicRange"}}]),
+             "relations_class": None}
+        if d["relations"]:
+            d["relations_class"] = "GenomicRangesList"
+        if rng.random() < 0.1:                                    # another key order
+            d = dict(reversed(list(d.items())))
+        text = json.dumps(d).encode()
+        want = Range.from_dict(json.loads(text))
+        got = _plain_range(text)
+        if got is None:
+            continue
+        covered += 1
+        assert (got.chrom, got.start, got.end, got.strand, got._name, got.genome, got.lifted) == \
+               (want.chrom, want.start, want.end, want.strand, want._name, want.genome, want.lifted)
+        assert type(got.start) is int and type(got.chrom) is str
+    assert covered > 100
