@@ -232,10 +232,81 @@ def _plain_range(text):
                  None if name == b"null" else name[1:-1].decode(), None if genome == b"null" else genome[1:-1].decode(), None)
 
 
+_DROPPED_PER_WORKER = 2000     # dropped lncRNAs per forked worker below which the pool is not worth its start-up
+_DROP_CTX = None       # (ingest result, aln_off) of the run whose dropped lncRNAs are being rendered; inherited by fork
+
+
+def _dropped_chunk(lncs):
+    """What build_orthologs writes for the lncRNAs `lncs` that ended without an ortholog (pipeline.py:789-791, 895-908), as
+    plain tuples: per lncRNA (sort key, BED6 line) of its query range; per neighbour found by
+    `find_neighbours(srange, qrange.lifted)` (sort key, the fields `same()` compares, a token that is equal exactly when
+    the `lifted` lists compare equal, BED6 line). Runs in the calling process or in forked workers (`_render_dropped`)."""
+    r, aln_off = _DROP_CTX
+    q_items, s_items = [], []
+    for l in lncs:
+        a0, a1 = int(aln_off[l]), int(aln_off[l + 1])
+        q_dropped, s_dropped, last_qd, qrange = None, [], None, None
+        for a in range(a0, a1):                              # pipeline.py:789-791, per alignment
+            qd = r.range_dict(a, "q")
+            if qd is not last_qd:
+                last_qd, qrange = qd, Range.from_dict(qd)
+            srange = _plain_range(r.range_text(a, "s")) or Range.from_dict(r.range_dict(a, "s"))
+            srange.name = qrange.name
+            q_dropped = qrange
+            s_dropped.append(srange)
+        q_items.append((sort_key(q_dropped), bed6_lines([q_dropped])[0]))
+        ids = None
+        for grange in s_dropped:
+            for nb in find_neighbours(grange, q_dropped.lifted):
+                if nb.lifted is None:
+                    token = None
+                elif not nb.lifted:
+                    token = ()                               # empty lists compare equal whoever owns them
+                else:                                        # Range has no __eq__: lists are equal iff it is the same object
+                    if ids is None:
+                        ids = {id(x): k for k, x in enumerate(q_dropped.lifted)}
+                    token = (l, ids[id(nb)])
+                s_items.append((sort_key(nb), (nb.chrom, nb.start, nb.end, nb.strand, nb.name, nb.genome), token,
+                                bed6_lines([nb])[0]))
+    return q_items, s_items
+
+
+def _render_dropped(r, aln_off, lncs, cores):
+    """The lines of insignificant.query_orthologs.bed / insignificant.subject_orthologs.bed for the dropped lncRNAs `lncs`
+    (file order): sorted by `_genomic_key_func`, the subject side without consecutive duplicates
+    (`drop_duplicates`, genomicranges.py:1853-1865). The per-lncRNA work (JSON decode of the range objects,
+    `find_neighbours`) is Python; from a few thousand lncRNAs on it is spread over forked workers that return tuples."""
+    global _DROP_CTX
+    _DROP_CTX = (r, aln_off)
+    try:
+        n_proc = min(int(cores or 1), 16, len(lncs) // _DROPPED_PER_WORKER)
+        if n_proc > 1:
+            import multiprocessing as mp
+            step = -(-len(lncs) // (4 * n_proc))
+            chunks = [lncs[i:i + step] for i in range(0, len(lncs), step)]
+            with mp.get_context("fork").Pool(n_proc) as pool:
+                parts = pool.map(_dropped_chunk, chunks)
+        else:
+            parts = [_dropped_chunk(lncs)]
+    finally:
+        _DROP_CTX = None
+    q_items = [x for part in parts for x in part[0]]
+    s_items = [x for part in parts for x in part[1]]
+    q_items.sort(key=lambda x: x[0])                          # list.sort is stable, like sorted()
+    s_items.sort(key=lambda x: x[0])
+    s_lines, last = [], None
+    for key, same, token, line in s_items:
+        if last is not None and same == last[0] and token == last[1]:
+            continue
+        s_lines.append(line)
+        last = (same, token)
+    return [x[1] for x in q_items], s_lines
+
+
 def _assemble_columnar(r, res, loaded_errors, n_files, threads):
     """The records of a whole run from columnar data, without a Python object per alignment: the native ingest's range
-    fields (`IngestResult.range_fields`) + the batch result -> (native_text, dist_found, dropped (query Range, [subject
-    Ranges]) list, exceptions in file order), or None when some range object needs a full JSON decode (the caller then
+    fields (`IngestResult.range_fields`) + the batch result -> (native_text, dist_found, dropped = (query lines, subject lines)
+    of the two insignificant.* files, exceptions in file order), or None when some range object needs a full JSON decode (the caller then
     takes the per-alignment path). `r`: IngestResult / SidecarResult whose `.host` batch is what `res` was computed on;
     `loaded_errors`: {file index: ExceptionLogger} of the files that did not load."""
     from . import records_native
@@ -282,19 +353,7 @@ def _assemble_columnar(r, res, loaded_errors, n_files, threads):
         err = KeyError(None) if st == 1 else (RuntimeError if st == 2 else ValueError)(_STATUS_TEXT.get(st, st))
         a0, a1 = int(aln_off[l]), int(aln_off[l + 1])
         exceptions[int(lnc_file[l])] = ExceptionLogger(err, Range.from_dict(r.range_dict(a0, "q")) if a1 > a0 else None)
-    dropped = []
-    for l in np.nonzero(ok_lnc & (n_orth == 0))[0].tolist():
-        a0, a1 = int(aln_off[l]), int(aln_off[l + 1])
-        q_dropped, s_dropped, last_qd, qrange = None, [], None, None
-        for a in range(a0, a1):                              # pipeline.py:789-791, per alignment
-            qd = r.range_dict(a, "q")
-            if qd is not last_qd:
-                last_qd, qrange = qd, Range.from_dict(qd)
-            srange = _plain_range(r.range_text(a, "s")) or Range.from_dict(r.range_dict(a, "s"))
-            srange.name = qrange.name
-            q_dropped = qrange
-            s_dropped.append(srange)
-        dropped.append((q_dropped, s_dropped))
+    dropped = _render_dropped(r, aln_off, np.nonzero(ok_lnc & (n_orth == 0))[0].tolist(), threads)
     dist_found = n_orth[ok_lnc].tolist()
     return native_text, dist_found, dropped, [exceptions[i] for i in sorted(exceptions)]
 
@@ -441,7 +500,7 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     if fast is not None:
         dist_found = dist_found_fast
         native_text = native_text_fast if native_text_fast is not None else (b"", b"", b"", b"")
-        orthologs = [([], [], [qd, sds]) for qd, sds in dropped_fast]
+        orthologs = []                                                # the dropped lncRNAs come as finished lines
     if native_text is None:
         query_orthologs_bed12 = [o[1] for g in orthologs for o in g[0]]
         subject_orthologs_bed12 = [o[1] for g in orthologs for o in g[1]]
@@ -457,9 +516,11 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
         query_dropped.append(qd)
         for grange in sds:
             subject_dropped.extend(find_neighbours(grange, qd.lifted))
-    query_dropped = sorted(query_dropped, key=sort_key)
-    subject_dropped = drop_duplicates(sorted(subject_dropped, key=sort_key))
-    total_dropped = len(query_dropped)
+    query_dropped_lines = bed6_lines(sorted(query_dropped, key=sort_key))
+    subject_dropped_lines = bed6_lines(drop_duplicates(sorted(subject_dropped, key=sort_key)))
+    if fast is not None:
+        query_dropped_lines, subject_dropped_lines = dropped_fast
+    total_dropped = len(query_dropped_lines)
     query_exception_list = sorted(query_exception_ranges, key=sort_key)
 
     if not os.path.exists(outdir):
@@ -478,11 +539,11 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
             with open(j(name), "w") as f:
                 for record in lines:
                     f.write(record + "\n")
-    for name, ranges in (("insignificant.query_orthologs.bed", query_dropped),
-                         ("insignificant.subject_orthologs.bed", subject_dropped),
-                         ("query_exceptions.bed", query_exception_list)):
+    for name, lines in (("insignificant.query_orthologs.bed", query_dropped_lines),
+                        ("insignificant.subject_orthologs.bed", subject_dropped_lines),
+                        ("query_exceptions.bed", bed6_lines(query_exception_list))):
         with open(j(name), "w") as f:
-            f.writelines(bed6_lines(ranges))
+            f.writelines(lines)
 
     stats_msg = "-----------------------\n" \
                 f"build_orthologs stats:\n" \

@@ -28,14 +28,14 @@ def _oracle_runner(batches, devices, fitter, fdr, alpha, gapopen, gapextend):
 
 
 def _run_and_compare(tmp_path, monkeypatch, g, key, fitting, fdr, exact, ingest="native", cache=None, dirs=None,
-                     devices=None):
+                     devices=None, cores=1):
     from ortho2align_b200 import pipeline
     ad, bd = dirs or _materialise(tmp_path, g)
     real_listdir = os.listdir
     monkeypatch.setattr(os, "listdir", lambda p: list(g["listdir_order"]) if str(p) == ad else real_listdir(p))
     od = str(tmp_path / f"out_{key}")
     stats = str(tmp_path / f"{key}.stats.txt")
-    pipeline.build_orthologs(ad, bd, fitting, od, threshold=0.05, gapopen=5, gapextend=2, fdr=fdr, cores=1,
+    pipeline.build_orthologs(ad, bd, fitting, od, threshold=0.05, gapopen=5, gapextend=2, fdr=fdr, cores=cores,
                              timeout=None, silent=True, stats_filename=stats, ingest=ingest, cache=cache, devices=devices)
     j = lambda n: os.path.join(od, n)
     pipeline.get_best_orthologs(j("significant.query_orthologs.bed"), j("significant.query_orthologs.tsv"),
@@ -335,3 +335,37 @@ def test_plain_range_fast_path_equals_json_decode():
                (want.chrom, want.start, want.end, want.strand, want._name, want.genome, want.lifted)
         assert type(got.start) is int and type(got.chrom) is str
     assert covered > 100
+
+
+def test_dropped_lncrnas_rendered_by_forked_workers_give_the_same_files(tmp_path, monkeypatch):
+    """pipeline._render_dropped spreads the Python-side bookkeeping of lncRNAs without orthologs over forked workers
+    (from a few thousand on); forced here on a genome-scale-shaped sample: every output file must be byte-identical to
+    the single-process run."""
+    import filecmp
+    from ortho2align_b200 import pipeline, synth
+    monkeypatch.setattr(pipeline, "_run_shards", _oracle_runner)
+    b, m = synth.workload(5, n_lnc=400, with_meta=True, seed=9)
+    ad, bd = tmp_path / "align", tmp_path / "bg"
+    ad.mkdir(), bd.mkdir()
+    for name, alns, bg in synth.to_json_dicts(b, m):
+        (ad / f"{name}.json").write_text(json.dumps(alns))
+        (bd / f"{name}.json").write_text(json.dumps(bg))
+    pools = []
+    import multiprocessing as mp
+    real_ctx = mp.get_context
+
+    def spy(method=None):
+        pools.append(method)
+        return real_ctx(method)
+    monkeypatch.setattr(mp, "get_context", spy)
+    outs = {}
+    for tag, cores, per_worker in (("serial", 1, 2000), ("forked", 3, 1)):
+        monkeypatch.setattr(pipeline, "_DROPPED_PER_WORKER", per_worker)
+        outs[tag] = str(tmp_path / tag)
+        pipeline.build_orthologs(str(ad), str(bd), "hist", outs[tag], fdr=True, cores=cores, silent=True)
+    assert pools == ["fork"]                                 # the second run went through the pool
+    files = sorted(os.listdir(outs["serial"]))
+    assert "insignificant.subject_orthologs.bed" in files
+    assert os.path.getsize(os.path.join(outs["serial"], "insignificant.query_orthologs.bed")) > 0
+    for fn in files:
+        assert filecmp.cmp(os.path.join(outs["serial"], fn), os.path.join(outs["forked"], fn), shallow=False), fn
