@@ -278,8 +278,10 @@ def _render_dropped(r, aln_off, lncs, cores):
     `find_neighbours`) is Python; from a few thousand lncRNAs on it is spread over forked workers that return tuples."""
     global _DROP_CTX
     _DROP_CTX = (r, aln_off)
+    if lncs and hasattr(r, "_ranges"):
+        r._ranges()                                           # the range texts are exported once, here, not once per worker
     try:
-        n_proc = min(int(cores or 1), 16, len(lncs) // _DROPPED_PER_WORKER)
+        n_proc = min(int(cores or 1), 8, len(lncs) // _DROPPED_PER_WORKER)      # a fork of a genome-scale process costs ~25 ms
         if n_proc > 1:
             import multiprocessing as mp
             step = -(-len(lncs) // (4 * n_proc))
