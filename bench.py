@@ -1247,7 +1247,14 @@ def main():
                 free = os.statvfs("/dev/shm"); free_gb = free.f_bavail * free.f_frsize / 1e9
                 if free_gb < 12:
                     n_files_lnc = min(n_files_lnc, 10_000)
-            files = files_to_files(5, n_files_lnc, 0, "gpu", False, 0, None)
+            # in a process of its own, like a user's `build_orthologs` run: this one holds gigabytes of synthetic batches
+            # and pinned buffers, which makes every fork of the drop-in's worker pools (and every page fault) dearer
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--stage", "files", "--config", "5",
+                                "--lnc", str(n_files_lnc)], capture_output=True, text=True, timeout=900)
+            if r.returncode != 0:
+                raise RuntimeError(r.stderr.strip().splitlines()[-1] if r.stderr.strip() else f"exit code {r.returncode}")
+            files = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as ex:                                # never lose the headline line to the secondary figure
             files = {"error": f"{type(ex).__name__}: {ex}"}
     if world > 1:
