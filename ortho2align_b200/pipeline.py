@@ -271,15 +271,6 @@ def _dropped_chunk(lncs):
     return q_items, s_items
 
 
-def _release_later(r):
-    """Hand the native ingest handle of `r` to a daemon thread for destruction: 10^5 parsed files are ~10^6 heap blocks,
-    and releasing them is not something the caller of build_orthologs has to wait for."""
-    h, lib = getattr(r, "_h", None), getattr(r, "_lib", None)
-    if h and lib is not None:
-        r._h = None
-        threading.Thread(target=lib.o2a_ingest_destroy, args=(h,), daemon=True).start()
-
-
 def _render_dropped(r, aln_off, lncs, cores):
     """The lines of insignificant.query_orthologs.bed / insignificant.subject_orthologs.bed for the dropped lncRNAs `lncs`
     (file order): sorted by `_genomic_key_func`, the subject side without consecutive duplicates
@@ -444,7 +435,6 @@ def build_orthologs(alignments, background, fitting, outdir, threshold=0.05, gap
     orthologs, exceptions = [], []
     if fast is not None:
         native_text_fast, dist_found_fast, dropped_fast, exceptions = fast
-        _release_later(loaded.r)                                      # every record has been rendered
         loaded = []                                                   # nothing left for the per-alignment path
     elif ok_idx:
         for shard, batch, res in zip(shards, batches, results):
